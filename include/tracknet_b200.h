@@ -1,0 +1,174 @@
+/* tracknet_b200 — C ABI of the B200-native (sm_100a) TrackNetV3 hot path.
+ *
+ * The reference (qaz812345/TrackNetV3) is pure Python and has no FFI of its own: its hot path is the
+ * torch.nn modules in model.py and the functions in utils/metric.py / test.py, which dispatch to
+ * cuDNN/ATen. This header is the boundary a maintainer binds instead (ctypes stub in INTEGRATION.md).
+ * Every entry point cites the reference code it replaces as file:line into the reference tree.
+ *
+ * Conventions
+ *   - plain C types only: raw DEVICE pointers, ints, a cudaStream_t passed as void*;
+ *   - no ownership transfer: every buffer (inputs, outputs, saved-for-backward, workspace) is allocated
+ *     by the caller (PyTorch in the shipped host code) and passed in;
+ *   - return 0 on success, non-zero on error; tnb_last_error() gives the message (thread-local);
+ *   - all activations are fp32; internal activation layout is NHWC, model inputs/outputs are NCHW
+ *     exactly as the reference's modules take/return them;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef TRACKNET_B200_H
+#define TRACKNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TNB_ABI_VERSION 1
+
+/* ---- descriptors -------------------------------------------------------------------------- */
+
+/* How one channel-slice of a conv layer's logical input is produced from a stored tensor. */
+enum { TNB_SRC_IDENTITY = 0, TNB_SRC_AFFINE_RELU = 1, TNB_SRC_AFFINE_RELU_POOL = 2, TNB_SRC_AFFINE_RELU_UP = 3 };
+typedef struct {
+  const float* ptr;   /* [N, Hs, Ws, C] fp32 NHWC */
+  const float* scale; /* [C] fused BatchNorm scale (gamma * invstd), NULL for IDENTITY */
+  const float* shift; /* [C] fused BatchNorm shift (beta - mean * scale) */
+  int C, Hs, Ws, mode;
+} tnb_src_t;
+
+/* Logical input of a conv layer = channel concat of up to two sources (torch.cat order, model.py:65). */
+typedef struct {
+  tnb_src_t s[2];
+  int C0; /* channels taken from s[0]; the rest come from s[1] */
+  int C;  /* total channels, multiple of 32 */
+  int N, H, W;
+} tnb_view_t;
+
+enum { TNB_GRAD_SAME = 0, TNB_GRAD_POOL = 1, TNB_GRAD_UP = 2 };
+typedef struct {
+  const float* ptr; /* consumer's input-gradient tensor [N, Hs, Ws, C] */
+  int C, coff, mode, Hs, Ws;
+} tnb_gradsrc_t;
+
+typedef struct {
+  tnb_gradsrc_t g[2];
+  int ng;
+  const float* z;
+  const float *scale, *shift, *mean, *invstd;
+  int N, H, W, C;
+  float* part;       /* reduce: [tnb_bn_bwd_blocks()][2][C] */
+  const float* sums; /* apply:  [2][C] */
+  float* dz;         /* apply:  [N,H,W,C] */
+  float inv_count;
+} tnb_bnbwd_t;
+
+typedef struct {
+  int n, h, w;     /* batch, height, width (h, w multiples of 8 like the reference, model.py:59-69) */
+  int in_dim;      /* TrackNet(in_dim, out_dim), reference model.py:45 */
+  int out_dim;
+  int training;    /* 1: BatchNorm uses batch statistics and updates running stats (model.train()) */
+  int fwd_terms;   /* 3 = fp16 hi/lo split, fp32-faithful (default); 1 = single fp16 pass (TF32-class) */
+  int bwd_terms;   /* 3 = bf16 hi/lo split (default); 1 = single bf16 pass */
+  int variant;     /* bring-up probe bits; 0 in production */
+  float bn_eps;    /* 1e-5 */
+  float bn_momentum; /* 0.1 */
+} tnb_tracknet_cfg_t;
+
+/* ---- misc ---------------------------------------------------------------------------------- */
+const char* tnb_last_error(void);
+int tnb_abi_version(void);
+
+/* ---- operator level (each is one or two kernel launches on `stream`) ----------------------- */
+
+/* NCHW fp32 -> NHWC fp32 with channels zero-padded to cpad. Replaces the layout the reference feeds
+ * to Conv2d directly (train.py:86 `x.float().cuda()`, model.py:58). */
+int tnb_pack_nchw_to_nhwc(const float* x_nchw, float* out_nhwc, int n, int c, int h, int w, int cpad, void* stream);
+
+/* Weight pre-packing for the tcgen05 kernels. mode 0: forward operand, mode 1: dgrad operand (rotated,
+ * transposed). fmt 0: fp16 split, 1: bf16 split. Source is the reference's canonical OIHW parameter
+ * (`<block>.conv.weight`, model.py:8). */
+size_t tnb_conv3x3_wpack_elems(int k_side, int n_side); /* number of uint16 elements */
+int tnb_conv3x3_pack_weights(const float* w_oihw, uint16_t* out, int cout, int cin, int mode, int fmt, void* stream);
+
+/* 3x3 'same' convolution, bias-free (nn.Conv2d in Conv2DBlock, model.py:8,13), with BatchNorm/ReLU/
+ * MaxPool/Upsample/cat of the PRODUCING layers fused into the operand load (view), and per-tile
+ * BatchNorm (sum, sumsq) partials of the OUTPUT emitted by the epilogue (stat_part may be NULL).
+ * Also used for dgrad (view = dz, weights packed with mode 1). out: [N,H,W,cout] fp32. */
+int tnb_conv3x3_stat_rows(int n, int h, int w, int cin, int cout, int terms);
+int tnb_conv3x3_fwd(const tnb_view_t* view, const uint16_t* wpack, float* out, float* stat_part, int cout,
+                    int terms, int fmt, int variant, void* stream);
+
+/* Weight gradient of the same convolution (autograd of model.py:13 via train.py:95):
+ * dw[cout][cin_real][3][3] += sum dz * view. dw must be zeroed by the caller. */
+int tnb_conv3x3_wgrad(const tnb_view_t* view, const float* dz, float* dw_oihw, int cout, int cin_real, int terms,
+                      int fmt, int variant, void* stream);
+
+/* BatchNorm2d statistics -> fused affine + running-stat update (model.py:9; torch defaults eps 1e-5,
+ * momentum 0.1, unbiased running_var). training==0 uses the running statistics (model.eval()). */
+int tnb_bn_finalize(const float* stat_part, int rows, double count, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float momentum, float eps, int training,
+                    float* scale, float* shift, float* mean, float* invstd, int c, void* stream);
+
+/* BatchNorm+ReLU backward with MaxPool/Upsample/cat gradient routing (autograd of model.py:13-15,59-69). */
+int tnb_bn_bwd_blocks(int n, int h, int w, int c);
+int tnb_bn_relu_bwd_reduce(const tnb_bnbwd_t* args, void* stream);
+int tnb_bn_relu_bwd_finalize(const float* part, int rows, int c, float* sums, float* dgamma, float* dbeta, void* stream);
+int tnb_bn_relu_bwd_apply(const tnb_bnbwd_t* args, void* stream);
+
+/* predictor: 1x1 conv + bias + sigmoid (model.py:54-55,71-72). y / dy are NCHW [n,out_dim,h,w]. */
+int tnb_conv1x1_bias_sigmoid_fwd(const tnb_src_t* src, int n, int h, int w, const float* weight, const float* bias,
+                                 int out_dim, float* y_nchw, void* stream);
+int tnb_conv1x1_bias_sigmoid_bwd(const tnb_src_t* src, int n, int h, int w, const float* weight, int out_dim,
+                                 const float* dy_nchw, const float* y_nchw, float* d_act_nhwc, float* dweight,
+                                 float* dbias, void* stream);
+
+/* WBCELoss(y_pred, y, reduce) (utils/metric.py:3-20). out: 1 float (reduce) or nsamples floats.
+ * part: workspace of tnb_wbce_workspace_bytes(nsamples) bytes. gout: upstream gradient (1 or nsamples). */
+size_t tnb_wbce_workspace_bytes(int nsamples);
+int tnb_wbce_fwd(const float* y_pred, const float* y, int nsamples, long long per_sample, int reduce, void* part,
+                 float* out, void* stream);
+int tnb_wbce_bwd(const float* y_pred, const float* y, const float* gout, int nsamples, long long per_sample,
+                 int reduce, float* d_y_pred, void* stream);
+
+/* mixup (train.py:37-38): out[i] = x[i]*lam[i] + x[perm[i]]*(1-lam[i]). */
+int tnb_mixup(const float* x, const float* lam, const long long* perm, float* out, int n, long long per_sample,
+              void* stream);
+
+/* torch.optim.Adam step over many tensors in one launch (train.py:96,242). table: device array of
+ * {float* p; const float* g; float* m; float* v; long long n;}. step counts from 1. */
+int tnb_adam_multi(const void* table_dev, int ntensors, long long max_n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int step, void* stream);
+
+/* predict_location (test.py:52-79) for a batch of maps on the GPU. maps: nmaps x h x w, float (foreground =
+ * value > thresh, predict.py:35) or uint8 (foreground = non-zero, as to_img() output). out: nmaps x 4 int32
+ * (x, y, w, h), all zeros for an empty map. */
+size_t tnb_heatmap_decode_workspace_bytes(int nmaps, int h, int w);
+int tnb_heatmap_decode(const void* maps, int is_u8, float thresh, int nmaps, int h, int w, void* workspace,
+                       int* out_xywh, void* stream);
+
+/* InpaintNet.forward(x, m) (model.py:113-129) in one kernel. params: 18 device pointers in state_dict
+ * order (down_1.conv.weight, down_1.conv.bias, ..., predictor.weight, predictor.bias). */
+int tnb_inpaintnet_fwd(const float* coords, const float* mask, const void* const* params, int n, int l, float* out,
+                       void* stream);
+
+/* ---- network level: TrackNet.forward / its autograd backward (model.py:57-73) --------------- */
+
+/* params: 104 device pointers in state_dict order: for each of the 17 Conv2DBlocks
+ *   conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked (int64),
+ * then predictor.weight, predictor.bias.
+ * grads:  53 device pointers in parameters() order: per block conv.weight, bn.weight, bn.bias grads, then
+ * predictor.weight, predictor.bias grads (all overwritten, not accumulated). */
+size_t tnb_tracknet_workspace_bytes(const tnb_tracknet_cfg_t* cfg);
+int tnb_tracknet_forward(const tnb_tracknet_cfg_t* cfg, const float* x_nchw, void* const* params, float* y_nchw,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int tnb_tracknet_backward(const tnb_tracknet_cfg_t* cfg, const float* dy_nchw, const float* y_nchw,
+                          void* const* params, void* const* grads, void* workspace, size_t workspace_bytes,
+                          void* stream);
+/* number of kernels launched by one forward / backward call (for bench.py's gpu_launches) */
+int tnb_tracknet_num_launches(const tnb_tracknet_cfg_t* cfg, int backward);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRACKNET_B200_H */

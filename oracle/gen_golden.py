@@ -1,0 +1,161 @@
+"""Generate tests/golden/*.npz by RUNNING THE REAL REFERENCE (read from /root/reference, never copied).
+
+Run in the build container only (the GPU box has no /root/reference):  python oracle/gen_golden.py
+  * model.py and utils/metric.py import cleanly (they need only torch) and are executed as-is;
+  * test.py cannot be imported (pycocotools / parse are not installed), so `predict_location` and
+    `get_ensemble_weight` are extracted from its source with `ast` at generation time and exec'd against
+    the real OpenCV; train.py's `mixup` likewise.
+The fixtures pin oracle/ (tests/test_oracle.py) and, through it, the CUDA path (tests/test_gpu_*.py).
+"""
+import ast
+import importlib.util
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def load_module(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def extract_functions(path, names, env):
+    src = open(path).read()
+    tree = ast.parse(src)
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), env)
+    return env
+
+
+def grad_stats(g):
+    g = g.detach().double().flatten()
+    idx = torch.linspace(0, g.numel() - 1, 16).long()
+    return np.concatenate([[g.sum().item(), g.abs().sum().item(), g.abs().max().item()], g[idx].numpy()])
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    refmodel = load_module("ref_model", f"{REF}/model.py")
+    refmetric = load_module("ref_metric", f"{REF}/utils/metric.py")
+    import cv2
+    env = {"np": np, "cv2": cv2, "torch": torch, "math": math}
+    extract_functions(f"{REF}/test.py", {"predict_location", "get_ensemble_weight"}, env)
+    extract_functions(f"{REF}/train.py", {"mixup"}, env)
+
+    # ---- C1: TrackNet forward, seq_len 4, bg none, bs 1, 288x512 (BASELINE.json configs[0]) ----
+    torch.manual_seed(13)
+    m = refmodel.TrackNet(12, 4)
+    x = torch.rand(1, 12, 288, 512)
+    with torch.no_grad():
+        m.train()
+        y_train = m(x)
+        m.eval()  # running stats now hold one momentum-0.1 update
+        y_eval = m(x)
+    np.savez_compressed(f"{OUT}/tracknet_c1.npz", seed=13, in_dim=12, out_dim=4, shape=np.array(x.shape),
+                        y_train=y_train.numpy(), y_eval=y_eval.numpy(),
+                        x_checksum=np.array([x.double().sum().item(), x[0, 3, 17, 99].item()]))
+
+    # ---- small train step: seq_len 8, bg concat (in 27, out 8), bs 2, 32x64 ----
+    torch.manual_seed(21)
+    m = refmodel.TrackNet(27, 8)
+    x = torch.rand(2, 27, 32, 64)
+    y = (torch.rand(2, 8, 32, 64) > 0.97).float() * torch.rand(2, 8, 32, 64).clamp_min(0.3)
+    m.train()
+    y_pred = m(x)
+    loss = refmetric.WBCELoss(y_pred, y)
+    loss_ns = refmetric.WBCELoss(y_pred, y, reduce=False)
+    loss.backward()
+    names = [n for n, _ in m.named_parameters()]
+    gstats = np.stack([grad_stats(p.grad) for _, p in m.named_parameters()])
+    sd = m.state_dict()
+    np.savez_compressed(f"{OUT}/tracknet_step.npz", seed=21, x=x.numpy(), y=y.numpy(), y_pred=y_pred.detach().numpy(),
+                        loss=loss.item(), loss_per_sample=loss_ns.detach().numpy(), grad_stats=gstats,
+                        grad_names=np.array(names),
+                        grad_first=m.down_block_1.conv_1.conv.weight.grad.numpy(),
+                        grad_last=m.up_block_3.conv_2.conv.weight.grad.numpy(),
+                        grad_pred_w=m.predictor.weight.grad.numpy(), grad_pred_b=m.predictor.bias.grad.numpy(),
+                        grad_bn_w=m.up_block_1.conv_1.bn.weight.grad.numpy(),
+                        running_mean_first=sd["down_block_1.conv_1.bn.running_mean"].numpy(),
+                        running_var_last=sd["up_block_3.conv_2.bn.running_var"].numpy(),
+                        nbt=int(sd["bottleneck.conv_2.bn.num_batches_tracked"]))
+
+    # ---- WBCE incl. clamp edges ----
+    torch.manual_seed(3)
+    p = torch.rand(3, 2, 16, 24)
+    p.view(-1)[:6] = torch.tensor([0.0, 1.0, 1e-8, 1 - 1e-8, 1e-7, 0.5])
+    t = (torch.rand(3, 2, 16, 24) > 0.9).float()
+    t.view(-1)[:6] = torch.tensor([1.0, 0.0, 1.0, 0.0, 0.3, 0.7])
+    p.requires_grad_(True)
+    l1 = refmetric.WBCELoss(p, t)
+    (g1,) = torch.autograd.grad(l1, p)
+    l2 = refmetric.WBCELoss(p, t, reduce=False)
+    wts = torch.tensor([1.0, -2.0, 0.5])
+    (g2,) = torch.autograd.grad((l2 * wts).sum(), p)
+    np.savez_compressed(f"{OUT}/wbce.npz", p=p.detach().numpy(), y=t.numpy(), loss=l1.item(), grad=g1.numpy(),
+                        loss_ns=l2.detach().numpy(), gout_ns=wts.numpy(), grad_ns=g2.numpy())
+
+    # ---- decode: crafted + random masks, real OpenCV through the reference's predict_location ----
+    rng = np.random.default_rng(0)
+    H, W = 48, 64
+    masks = []
+    def blank(): return np.zeros((H, W), np.uint8)
+    masks.append(blank())                                            # empty
+    a = blank(); a[10:13, 5:9] = 255; masks.append(a)               # one blob
+    a = blank(); a[5:8, 5:8] = 255; a[20:23, 30:33] = 255; a[40:43, 10:13] = 255; masks.append(a)  # 3-way area tie
+    a = blank(); a[5:8, 5:8] = 255; a[8, 8] = 255; masks.append(a)  # diagonal touch (8-connectivity)
+    a = blank(); a[5:15, 5:15] = 255; a[7:13, 7:13] = 0; a[9:11, 9:11] = 255; masks.append(a)  # ring + nested dot
+    a = blank(); a[0:2, 0:3] = 255; a[H - 2:H, W - 3:W] = 255; masks.append(a)  # image corners, tie
+    a = blank(); a[3, 2:40] = 255; a[10:20, 50] = 255; masks.append(a)  # thin lines: 38x1 vs 1x10
+    a = blank(); a[:, :] = 255; masks.append(a)                      # full
+    a = blank(); a[::2, ::2] = 255; masks.append(a)                  # isolated pixels, massive tie
+    a = blank(); a[::2, :] = 255; masks.append(a)                    # stripes (tie)
+    for dens in (0.02, 0.1, 0.3, 0.5, 0.7):
+        for _ in range(6):
+            masks.append(((rng.random((H, W)) < dens) * 255).astype(np.uint8))
+    for _ in range(10):                                              # few gaussian-ish blobs, realistic
+        a = blank()
+        for _ in range(rng.integers(1, 4)):
+            cy, cx, r = rng.integers(0, H), rng.integers(0, W), rng.integers(1, 5)
+            yy, xx = np.ogrid[:H, :W]
+            a[(yy - cy) ** 2 + (xx - cx) ** 2 <= r * r] = 255
+        masks.append(a)
+    masks = np.stack(masks)
+    boxes = np.array([env["predict_location"](mm) for mm in masks], dtype=np.int32)
+    np.savez_compressed(f"{OUT}/decode_golden.npz", masks=masks, boxes=boxes, cv2_version=cv2.__version__)
+
+    # ---- InpaintNet forward ----
+    torch.manual_seed(7)
+    net = refmodel.InpaintNet().eval()
+    coor = torch.rand(4, 16, 2)
+    mask = (torch.rand(4, 16, 1) < 0.3).float()
+    coor = coor * (1 - mask)
+    with torch.no_grad():
+        out = net(coor, mask)
+    np.savez_compressed(f"{OUT}/inpaintnet.npz", seed=7, coor=coor.numpy(), mask=mask.numpy(), out=out.numpy())
+
+    # ---- small host-side pieces: ensemble weights, mixup ----
+    ew = {f"weight_{L}": env["get_ensemble_weight"](L, "weight").numpy() for L in (1, 4, 7, 8)}
+    ew["average_8"] = env["get_ensemble_weight"](8, "average").numpy()
+    np.random.seed(11); torch.manual_seed(11)
+    xm, ym = torch.rand(4, 3, 8, 8), torch.rand(4, 2, 8, 8)
+    np.random.seed(11); torch.manual_seed(11)
+    lamb = np.random.beta(0.5, 0.5, size=4); index = torch.randperm(4)  # the draws mixup() makes, in its order
+    np.random.seed(11); torch.manual_seed(11)
+    x_mix, y_mix = env["mixup"](xm, ym, 0.5)
+    np.savez_compressed(f"{OUT}/host_pieces.npz", x=xm.numpy(), y=ym.numpy(), lamb=lamb, index=index.numpy(),
+                        x_mix=x_mix.numpy(), y_mix=y_mix.numpy(), **ew)
+    print("golden fixtures written to", os.path.normpath(OUT))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,100 @@
+"""CPU tests of the host-side mirror of the reference interface: module tree / state_dict layout,
+get_model table and errors, data-parallel sharding + gradient bucket (gloo, world_size 2)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import tracknet_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_state_dict_layout_matches_reference():
+    import tracknetv3_b200 as T
+    m = T.TrackNet(27, 8)
+    sd = m.state_dict()
+    assert [(k, tuple(v.shape)) for k, v in sd.items()] == O.tracknet_state_keys(27, 8)
+    assert len(sd) == 104 and sum(p.numel() for p in m.parameters()) == 11341000
+    assert sd["bottleneck.conv_2.bn.num_batches_tracked"].dtype == torch.int64
+    assert [t.data_ptr() for t in m._state_tensors()] == [v.data_ptr() for v in sd.values()]
+    i = T.InpaintNet()
+    assert list(i.state_dict().keys()) == list(O.init_inpaintnet_state(0).keys())
+    assert sum(p.numel() for p in i.parameters()) == 520610
+    # torch-default init under the same seed reproduces the oracle's (and hence the reference's) init
+    torch.manual_seed(5)
+    m2 = T.TrackNet(12, 4)
+    ref = O.init_tracknet_state(5, 12, 4)
+    assert all(torch.equal(v.float(), ref[k].float()) for k, v in m2.state_dict().items())
+
+
+def test_get_model_table_and_errors():
+    from utils.general import get_model, COOR_TH, HEIGHT, WIDTH
+    assert get_model("TrackNet", 8, "concat").in_dim == 27
+    assert get_model("TrackNet", 8, "subtract").in_dim == 8
+    assert get_model("TrackNet", 8, "subtract_concat").in_dim == 32
+    assert get_model("TrackNet", 4, "").in_dim == 12 and get_model("TrackNet", 4, "").out_dim == 4
+    assert type(get_model("InpaintNet")).__name__ == "InpaintNet"
+    with pytest.raises(ValueError, match="Invalid model name"):
+        get_model("YOLO")
+    assert (HEIGHT, WIDTH) == (288, 512) and abs(COOR_TH - 50 / np.sqrt(288 ** 2 + 512 ** 2)) < 1e-12
+
+
+def test_predict_coordinate_branch_and_errors():
+    import predict as P
+    idx = torch.tensor([[[0, 0], [0, 1], [0, 2]], [[0, 2], [0, 3], [0, 3]]])
+    c = torch.tensor([[[0.5, 0.5], [0.0, 0.0], [0.25, 0.75]], [[0.9, 0.9], [0.1, 0.2], [0.3, 0.3]]])
+    out = P.predict(idx, c_pred=c, img_scaler=(2.5, 2.5))
+    # frame 2 is repeated at the start of sample 1 -> that sample stops immediately (reference predict.py:46-67)
+    assert out["Frame"] == [0, 1, 2] and out["X"] == [640, 0, 320] and out["Y"] == [360, 0, 540]
+    assert out["Visibility"] == [1, 0, 1]
+    with pytest.raises(ValueError, match="Invalid input"):
+        P.predict(idx)
+
+
+def test_shard_batch_partitions_exactly():
+    from tracknetv3_b200.parallel import shard_batch
+    for n, w in ((80, 8), (10, 4), (7, 2), (3, 8)):
+        ranges = [shard_batch(n, r, w) for r in range(w)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tracknetv3_b200.parallel import GradBucket, broadcast_module
+    torch.manual_seed(100 + rank)  # different init per rank: broadcast must fix it
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4))
+    broadcast_module(net)
+    w0 = torch.cat([p.detach().flatten() for p in net.parameters()]).clone()
+    for i, p in enumerate(net.parameters()):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    GradBucket(net).allreduce()
+    g = torch.cat([p.grad.flatten() for p in net.parameters()])
+    q.put((rank, w0.numpy(), g.numpy()))
+    dist.destroy_process_group()
+
+
+def test_gradient_bucket_allreduce_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    [p.join(60) for p in procs]
+    assert np.array_equal(res[0][1], res[1][1])              # identical replicas after broadcast
+    assert np.array_equal(res[0][2], res[1][2])              # identical averaged gradients
+    # rank grads were (r+1)*(i+1): mean over ranks = 1.5*(i+1)
+    assert np.allclose(np.unique(res[0][2]), [1.5, 3.0, 4.5, 6.0])

@@ -1,0 +1,119 @@
+// extern "C" surface of libtracknet_b200.so (declared in include/tracknet_b200.h).
+#include "kernels.cuh"
+#include <stdarg.h>
+
+namespace tnb {
+static thread_local char g_err[1024] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+size_t tracknet_workspace_bytes(const tnb_tracknet_cfg_t& c);
+int tracknet_forward(const tnb_tracknet_cfg_t& c, const float* x, void* const* params, float* y, void* ws,
+                     size_t ws_bytes, cudaStream_t st);
+int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float* y, void* const* params,
+                      void* const* grads, void* ws, size_t ws_bytes, cudaStream_t st);
+int tracknet_num_launches(const tnb_tracknet_cfg_t& c, int backward);
+}  // namespace tnb
+
+using namespace tnb;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+const char* tnb_last_error(void) { return g_err; }
+int tnb_abi_version(void) { return TNB_ABI_VERSION; }
+
+int tnb_pack_nchw_to_nhwc(const float* x, float* out, int n, int c, int h, int w, int cpad, void* stream) {
+  TNB_REQUIRE(cpad % 4 == 0 && cpad >= c, "pack_nchw_to_nhwc: bad cpad %d for c %d", cpad, c);
+  return launch_pack_input(x, out, n, c, h, w, cpad, ST(stream));
+}
+size_t tnb_conv3x3_wpack_elems(int k_side, int n_side) { return conv3x3_wpack_elems(k_side, n_side); }
+int tnb_conv3x3_pack_weights(const float* w, uint16_t* out, int cout, int cin, int mode, int fmt, void* stream) {
+  // the tile width must match what the conv launcher will pick for this N side
+  ConvPlan p;
+  const int nside = mode == 0 ? cout : cin, kside = mode == 0 ? cin : cout;
+  if (int rc = conv3x3_plan(1, 16, 16, (kside + 31) / 32 * 32, nside, 3, &p)) return rc;
+  return launch_pack_weights(w, out, cout, cin, mode, fmt, p.BN, ST(stream));
+}
+int tnb_conv3x3_stat_rows(int n, int h, int w, int cin, int cout, int terms) {
+  return conv3x3_num_stat_rows(n, h, w, cin, cout, terms);
+}
+int tnb_conv3x3_fwd(const tnb_view_t* view, const uint16_t* wpack, float* out, float* stat_part, int cout, int terms,
+                    int fmt, int variant, void* stream) {
+  return launch_conv3x3(*view, wpack, out, stat_part, cout, terms, fmt, variant, ST(stream));
+}
+int tnb_conv3x3_wgrad(const tnb_view_t* view, const float* dz, float* dw, int cout, int cin_real, int terms, int fmt,
+                      int variant, void* stream) {
+  return launch_wgrad3x3(*view, dz, dw, cout, cin_real, terms, fmt, variant, ST(stream));
+}
+int tnb_bn_finalize(const float* part, int rows, double count, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float momentum, float eps, int training, float* scale,
+                    float* shift, float* mean, float* invstd, int c, void* stream) {
+  return launch_bn_finalize(part, rows, count, gamma, beta, running_mean, running_var, momentum, eps, training, scale,
+                            shift, mean, invstd, c, ST(stream));
+}
+int tnb_bn_bwd_blocks(int n, int h, int w, int c) { return bn_bwd_num_blocks(n, h, w, c); }
+int tnb_bn_relu_bwd_reduce(const tnb_bnbwd_t* a, void* stream) { return launch_bn_bwd_reduce(*a, ST(stream)); }
+int tnb_bn_relu_bwd_finalize(const float* part, int rows, int c, float* sums, float* dgamma, float* dbeta,
+                             void* stream) {
+  return launch_bn_bwd_finalize(part, rows, c, sums, dgamma, dbeta, ST(stream));
+}
+int tnb_bn_relu_bwd_apply(const tnb_bnbwd_t* a, void* stream) { return launch_bn_bwd_apply(*a, ST(stream)); }
+
+int tnb_conv1x1_bias_sigmoid_fwd(const tnb_src_t* src, int n, int h, int w, const float* weight, const float* bias,
+                                 int out_dim, float* y, void* stream) {
+  return launch_predictor_fwd(*src, n, h, w, weight, bias, out_dim, y, ST(stream));
+}
+int tnb_conv1x1_bias_sigmoid_bwd(const tnb_src_t* src, int n, int h, int w, const float* weight, int out_dim,
+                                 const float* dy, const float* y, float* d_act, float* dweight, float* dbias,
+                                 void* stream) {
+  return launch_predictor_bwd(*src, n, h, w, weight, out_dim, dy, y, d_act, dweight, dbias, ST(stream));
+}
+
+size_t tnb_wbce_workspace_bytes(int nsamples) { return sizeof(double) * (size_t)nsamples * wbce_num_blocks(0); }
+int tnb_wbce_fwd(const float* p, const float* y, int nsamples, long long per_sample, int reduce, void* part,
+                 float* out, void* stream) {
+  return launch_wbce_fwd(p, y, nsamples, per_sample, reduce, (double*)part, out, ST(stream));
+}
+int tnb_wbce_bwd(const float* p, const float* y, const float* gout, int nsamples, long long per_sample, int reduce,
+                 float* dp, void* stream) {
+  return launch_wbce_bwd(p, y, gout, nsamples, per_sample, reduce, dp, ST(stream));
+}
+int tnb_mixup(const float* x, const float* lam, const long long* perm, float* out, int n, long long per_sample,
+              void* stream) {
+  return launch_mixup(x, lam, perm, out, n, per_sample, ST(stream));
+}
+int tnb_adam_multi(const void* table, int ntensors, long long max_n, float lr, float b1, float b2, float eps, float wd,
+                   int step, void* stream) {
+  TNB_REQUIRE(step >= 1, "adam_multi: step counts from 1");
+  return launch_adam((const AdamTensor*)table, ntensors, max_n, lr, b1, b2, eps, wd, step, ST(stream));
+}
+size_t tnb_heatmap_decode_workspace_bytes(int nmaps, int h, int w) { return decode_workspace_bytes(nmaps, h, w); }
+int tnb_heatmap_decode(const void* maps, int is_u8, float thresh, int nmaps, int h, int w, void* workspace, int* out,
+                       void* stream) {
+  return launch_decode(maps, is_u8, thresh, nmaps, h, w, workspace, out, ST(stream));
+}
+int tnb_inpaintnet_fwd(const float* coords, const float* mask, const void* const* params, int n, int l, float* out,
+                       void* stream) {
+  InpaintParams p;
+  for (int i = 0; i < 9; ++i) { p.w[i] = (const float*)params[2 * i]; p.b[i] = (const float*)params[2 * i + 1]; }
+  return launch_inpaint_fwd(coords, mask, p, n, l, out, ST(stream));
+}
+
+size_t tnb_tracknet_workspace_bytes(const tnb_tracknet_cfg_t* cfg) { return tracknet_workspace_bytes(*cfg); }
+int tnb_tracknet_forward(const tnb_tracknet_cfg_t* cfg, const float* x, void* const* params, float* y, void* ws,
+                         size_t ws_bytes, void* stream) {
+  return tracknet_forward(*cfg, x, params, y, ws, ws_bytes, ST(stream));
+}
+int tnb_tracknet_backward(const tnb_tracknet_cfg_t* cfg, const float* dy, const float* y, void* const* params,
+                          void* const* grads, void* ws, size_t ws_bytes, void* stream) {
+  return tracknet_backward(*cfg, dy, y, params, grads, ws, ws_bytes, ST(stream));
+}
+int tnb_tracknet_num_launches(const tnb_tracknet_cfg_t* cfg, int backward) {
+  return tracknet_num_launches(*cfg, backward);
+}
+
+}  // extern "C"

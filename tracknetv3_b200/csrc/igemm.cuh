@@ -1,0 +1,85 @@
+// Shared declarations for the tcgen05 implicit-GEMM convolution kernels (igemm.cu) and the
+// elementwise kernels that consume the same "view" description of a layer input.
+#pragma once
+#include "common.cuh"
+#include "../../include/tracknet_b200.h"
+
+namespace tnb {
+
+// How a layer's logical input (what the reference's Conv2d sees, model.py:57-73) is produced from
+// the tensors we actually keep in HBM. We never materialise BN-apply / ReLU / MaxPool / Upsample /
+// concat: each consumer recomputes them on the fly from the producer's raw conv output z.
+enum SrcMode : int {
+  SRC_IDENTITY = TNB_SRC_IDENTITY,                  // plain NHWC fp32 tensor (packed network input, or dz)
+  SRC_AFFINE_RELU = TNB_SRC_AFFINE_RELU,            // relu(z*scale + shift)                  (model.py:12-16)
+  SRC_AFFINE_RELU_POOL = TNB_SRC_AFFINE_RELU_POOL,  // maxpool2x2(relu(z*scale+shift)), z is 2H x 2W (model.py:59,61,63)
+  SRC_AFFINE_RELU_UP = TNB_SRC_AFFINE_RELU_UP       // nearest x2 upsample of relu(z*scale+shift)  (model.py:65,67,69)
+};
+using SrcDesc = tnb_src_t;    // see include/tracknet_b200.h
+using ViewDesc = tnb_view_t;
+
+// pixel offset (in pixels, not elements) of view pixel (n,h,w) inside source s
+TNB_DEVINL int view_pix_off(const SrcDesc& s, int n, int h, int w) {
+  if (s.mode == SRC_AFFINE_RELU_POOL) return (n * s.Hs + 2 * h) * s.Ws + 2 * w;
+  if (s.mode == SRC_AFFINE_RELU_UP) return (n * s.Hs + (h >> 1)) * s.Ws + (w >> 1);
+  return (n * s.Hs + h) * s.Ws + w;
+}
+
+TNB_DEVINL void ld8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// 8 consecutive channels [c, c+8) of the view at a pixel whose source pixel offset is `poff`.
+TNB_DEVINL void view_load8(const SrcDesc& s, int poff, int c, float (&v)[8]) {
+  const float* p = s.ptr + (size_t)poff * s.C + c;
+  if (s.mode == SRC_IDENTITY) {
+    ld8(p, v);
+    return;
+  }
+  float sc[8], sh[8];
+  ld8(s.scale + c, sc);
+  ld8(s.shift + c, sh);
+  if (s.mode == SRC_AFFINE_RELU_POOL) {
+    float a[8], m[8];
+    ld8(p, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = fmaf(a[i], sc[i], sh[i]);
+    ld8(p + s.C, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], fmaf(a[i], sc[i], sh[i]));
+    ld8(p + (size_t)s.Ws * s.C, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], fmaf(a[i], sc[i], sh[i]));
+    ld8(p + (size_t)s.Ws * s.C + s.C, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf(fmaxf(m[i], fmaf(a[i], sc[i], sh[i])), 0.f);
+  } else {
+    float a[8];
+    ld8(p, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf(fmaf(a[i], sc[i], sh[i]), 0.f);
+  }
+}
+
+// ---- host-side launchers (igemm.cu) ----------------------------------------------------------
+struct ConvPlan {
+  int BN, MT, SA, SB, tmem_cols;
+  size_t smem_bytes;
+  int tiles_h, tiles_w;
+};
+// fmt: 0 = fp16 split, 1 = bf16 split. nterms: 1 (single pass) or 3 (hi*hi + lo*hi + hi*lo).
+int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* plan);
+size_t conv3x3_wpack_elems(int Kside, int Nside);  // uint16 elements of a packed weight buffer
+int launch_pack_weights(const float* w_oihw, uint16_t* out, int Co, int Ci, int mode /*0 fwd, 1 dgrad*/,
+                        int fmt, int BN, cudaStream_t st);
+int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout,
+                   int nterms, int fmt, int variant, cudaStream_t st);
+int conv3x3_num_stat_rows(int N, int H, int W, int Cin, int Cout, int nterms);
+
+int launch_wgrad3x3(const ViewDesc& view, const float* dz, float* dw_oihw, int Cout, int CinReal, int nterms,
+                    int fmt, int variant, cudaStream_t st);
+
+}  // namespace tnb

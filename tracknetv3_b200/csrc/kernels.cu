@@ -1,0 +1,723 @@
+// HBM-bound sm_100a kernels of the TrackNet / InpaintNet hot path. Each cites the reference lines it
+// replaces; none of them falls back to a library.
+#include "kernels.cuh"
+#include <limits.h>
+
+namespace tnb {
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// =============================================================================================
+// input packing: NCHW fp32 (reference train.py:86 x.float().cuda()) -> NHWC fp32, channels padded to Cpad
+// =============================================================================================
+__global__ void pack_input_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int C, int H, int W,
+                                  int Cpad) {
+  const long long npix = (long long)N * H * W;
+  const long long hw = (long long)H * W;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix;
+       p += (long long)gridDim.x * blockDim.x) {
+    const long long n = p / hw, r = p - n * hw;
+    const float* src = x + n * C * hw + r;
+    float4* dst = reinterpret_cast<float4*>(out + p * Cpad);
+    for (int c4 = 0; c4 < Cpad; c4 += 4) {
+      float4 v;
+      v.x = (c4 + 0 < C) ? __ldg(src + (long long)(c4 + 0) * hw) : 0.f;
+      v.y = (c4 + 1 < C) ? __ldg(src + (long long)(c4 + 1) * hw) : 0.f;
+      v.z = (c4 + 2 < C) ? __ldg(src + (long long)(c4 + 2) * hw) : 0.f;
+      v.w = (c4 + 3 < C) ? __ldg(src + (long long)(c4 + 3) * hw) : 0.f;
+      dst[c4 >> 2] = v;
+    }
+  }
+}
+int launch_pack_input(const float* x, float* out, int N, int C, int H, int W, int Cpad, cudaStream_t st) {
+  const long long npix = (long long)N * H * W;
+  pack_input_kernel<<<min(cdiv(npix, 256), 148 * 16), 256, 0, st>>>(x, out, N, C, H, W, Cpad);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// BatchNorm2d statistics finalisation (reference model.py:9 nn.BatchNorm2d, eps 1e-5, momentum 0.1).
+// Consumes the per-tile (sum, sumsq) partials written by the conv epilogue in a fixed order
+// (deterministic), combines in fp64, emits the fused affine (scale, shift) used by every consumer,
+// and updates the running statistics exactly like torch (biased var to normalise, unbiased to track).
+// =============================================================================================
+__global__ void bn_finalize_kernel(const float* __restrict__ part, int rows, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* running_mean, float* running_var, float momentum, float eps, int training,
+                                   float* scale, float* shift, float* mean_out, float* invstd_out, int C) {
+  __shared__ double s1[8][33], s2[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double a = 0.0, b = 0.0;
+  if (training && c < C) {
+    for (int r = threadIdx.y; r < rows; r += 8) {
+      a += (double)part[((size_t)r * 2 + 0) * C + c];
+      b += (double)part[((size_t)r * 2 + 1) * C + c];
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float mean, invstd;
+    if (training) {
+      double sa = 0.0, sb = 0.0;
+      for (int i = 0; i < 8; ++i) { sa += s1[i][threadIdx.x]; sb += s2[i][threadIdx.x]; }
+      const double m = sa / count;
+      double var = sb / count - m * m;
+      if (var < 0.0) var = 0.0;
+      mean = (float)m;
+      invstd = (float)(1.0 / sqrt(var + (double)eps));
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    } else {
+      mean = running_mean[c];
+      invstd = (float)(1.0 / sqrt((double)running_var[c] + (double)eps));
+    }
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - mean * sc;
+    mean_out[c] = mean;
+    invstd_out[c] = invstd;
+  }
+}
+int launch_bn_finalize(const float* part, int rows, double count, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, float momentum, float eps, int training,
+                       float* scale, float* shift, float* mean, float* invstd, int C, cudaStream_t st) {
+  bn_finalize_kernel<<<cdiv(C, 32), dim3(32, 8), 0, st>>>(part, rows, count, gamma, beta, running_mean,
+                                                           running_var, momentum, eps, training, scale, shift, mean,
+                                                           invstd, C);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// predictor: 1x1 conv (+bias) + sigmoid on relu(bn(z)) (reference model.py:54-55,71-72). fp32 FFMA: the
+// 0.07% of the FLOPs that sit directly in front of the 1e-3 parity bound stay in full precision.
+// Output is NCHW fp32, the layout the reference's callers consume (train.py:93, predict.py:140).
+// =============================================================================================
+static constexpr int kMaxPredO = 16;
+__global__ void __launch_bounds__(256) predictor_fwd_kernel(SrcDesc src, int N, int H, int W,
+                                                            const float* __restrict__ wp,
+                                                            const float* __restrict__ bias, int O,
+                                                            float* __restrict__ y) {
+  __shared__ float sw[kMaxPredO * 64 + kMaxPredO];
+  for (int i = threadIdx.x; i < O * 64; i += blockDim.x) sw[i] = wp[i];
+  for (int i = threadIdx.x; i < O; i += blockDim.x) sw[kMaxPredO * 64 + i] = bias[i];
+  __syncthreads();
+  const long long hw = (long long)H * W, npix = (long long)N * hw;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix;
+       p += (long long)gridDim.x * blockDim.x) {
+    float a[64];
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) {
+      float v[8];
+      view_load8(src, (int)p, c8 * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[c8 * 8 + i] = v[i];
+    }
+    const long long n = p / hw, r = p - n * hw;
+    for (int o = 0; o < O; ++o) {
+      float s = sw[kMaxPredO * 64 + o];
+#pragma unroll
+      for (int c = 0; c < 64; ++c) s = fmaf(a[c], sw[o * 64 + c], s);
+      y[(n * O + o) * hw + r] = 1.f / (1.f + expf(-s));
+    }
+  }
+}
+int launch_predictor_fwd(const SrcDesc& src, int N, int H, int W, const float* wp, const float* bias, int O,
+                         float* y, cudaStream_t st) {
+  TNB_REQUIRE(src.C == 64 && O <= kMaxPredO, "predictor: expects 64 input channels and out_dim <= %d", kMaxPredO);
+  const long long npix = (long long)N * H * W;
+  predictor_fwd_kernel<<<min(cdiv(npix, 256), 148 * 8), 256, 0, st>>>(src, N, H, W, wp, bias, O, y);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// backward of sigmoid + 1x1 conv: dl = dy*y*(1-y); dA[p][c] = sum_o dl[o] W[o][c];
+// dW[o][c] = sum_p dl[p][o] a[p][c]; db[o] = sum_p dl[p][o]   (autograd of model.py:71-72)
+__global__ void __launch_bounds__(256) predictor_bwd_kernel(SrcDesc src, int N, int H, int W,
+                                                            const float* __restrict__ wp, int O,
+                                                            const float* __restrict__ dy,
+                                                            const float* __restrict__ y, float* __restrict__ dA,
+                                                            float* dwp, float* dbias) {
+  constexpr int TP = 64;  // pixels per tile
+  __shared__ float sw[kMaxPredO * 64];
+  __shared__ float sdl[kMaxPredO][TP];
+  __shared__ float sa[TP][65];
+  for (int i = threadIdx.x; i < O * 64; i += 256) sw[i] = wp[i];
+  const long long hw = (long long)H * W, npix = (long long)N * hw;
+  const long long ntiles = (npix + TP - 1) / TP;
+  float accw[4] = {0.f, 0.f, 0.f, 0.f};  // pairs (o,c) = threadIdx.x + 256*k, k < O*64/256
+  float accb = 0.f;
+  const int npairs = O * 64;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    __syncthreads();
+    const long long p0 = tile * TP;
+    for (int i = threadIdx.x; i < TP * O; i += 256) {
+      const int pl = i % TP, o = i / TP;
+      const long long p = p0 + pl;
+      float d = 0.f;
+      if (p < npix) {
+        const long long n = p / hw, r = p - n * hw;
+        const float yy = y[(n * O + o) * hw + r];
+        d = dy[(n * O + o) * hw + r] * yy * (1.f - yy);
+      }
+      sdl[o][pl] = d;
+    }
+    __syncthreads();
+    {
+      const int pl = threadIdx.x >> 2, qd = threadIdx.x & 3;
+      const long long p = p0 + pl;
+      float a[16];
+      if (p < npix) {
+        float v[8];
+        view_load8(src, (int)p, qd * 16, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = v[i];
+        view_load8(src, (int)p, qd * 16 + 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[8 + i] = v[i];
+        float g[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) g[i] = 0.f;
+        for (int o = 0; o < O; ++o) {
+          const float d = sdl[o][pl];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) g[i] = fmaf(d, sw[o * 64 + qd * 16 + i], g[i]);
+        }
+        float4* dst = reinterpret_cast<float4*>(dA + p * 64 + qd * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sa[pl][qd * 16 + i] = a[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int pair = threadIdx.x + 256 * k;
+      if (pair < npairs) {
+        const int o = pair >> 6, c = pair & 63;
+        float s = accw[k];
+#pragma unroll 8
+        for (int pl = 0; pl < TP; ++pl) s = fmaf(sdl[o][pl], sa[pl][c], s);
+        accw[k] = s;
+      }
+    }
+    if (threadIdx.x < O) {
+      float s = accb;
+      for (int pl = 0; pl < TP; ++pl) s += sdl[threadIdx.x][pl];
+      accb = s;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int pair = threadIdx.x + 256 * k;
+    if (pair < npairs) atomicAdd(dwp + pair, accw[k]);
+  }
+  if (threadIdx.x < O) atomicAdd(dbias + threadIdx.x, accb);
+}
+int launch_predictor_bwd(const SrcDesc& src, int N, int H, int W, const float* wp, int O, const float* dy,
+                         const float* y, float* dA, float* dwp, float* dbias, cudaStream_t st) {
+  TNB_REQUIRE(src.C == 64 && O <= kMaxPredO, "predictor_bwd: expects 64 channels, out_dim <= %d", kMaxPredO);
+  const long long npix = (long long)N * H * W;
+  TNB_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * O * 64, st));
+  TNB_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * O, st));
+  predictor_bwd_kernel<<<min(cdiv(npix, 64), 148 * 4), 256, 0, st>>>(src, N, H, W, wp, O, dy, y, dA, dwp, dbias);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// BatchNorm + ReLU backward (autograd of model.py:13-15), fused with the gradient routing of
+// MaxPool2d / Upsample / cat (autograd of model.py:59-69): each thread owns a 2x2 window x 4 channels,
+// gathers dL/da from the consumers' dgrad outputs, masks by ReLU, and either reduces
+// (sum dy, sum dy*xhat) or writes dz = scale * (dy - mean(dy) - xhat * mean(dy*xhat)).
+// =============================================================================================
+TNB_DEVINL float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+TNB_DEVINL float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+template <bool APPLY>
+__global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnBwdArgs a) {
+  const int CQ = a.C >> 2;
+  const int Hw = (a.H + 1) >> 1, Ww = (a.W + 1) >> 1;
+  const long long items = (long long)a.N * Hw * Ww * CQ;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float4 acc1 = make_float4(0, 0, 0, 0), acc2 = make_float4(0, 0, 0, 0);
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += stride) {
+    const int cq = (int)(it % CQ);
+    long long r = it / CQ;
+    const int ww = (int)(r % Ww); r /= Ww;
+    const int wh = (int)(r % Hw);
+    const int n = (int)(r / Hw);
+    const int c = cq * 4;
+    const float4 sc = ld4(a.scale + c), sh = ld4(a.shift + c), mu = ld4(a.mean + c), is = ld4(a.invstd + c);
+    float4 m1 = make_float4(0, 0, 0, 0), m2 = m1;
+    if (APPLY) {
+      m1 = ld4(a.sums + c);
+      m2 = ld4(a.sums + a.C + c);
+      m1 = make_float4(m1.x * a.inv_count, m1.y * a.inv_count, m1.z * a.inv_count, m1.w * a.inv_count);
+      m2 = make_float4(m2.x * a.inv_count, m2.y * a.inv_count, m2.z * a.inv_count, m2.w * a.inv_count);
+    }
+    float4 z[4], act[4], dy[4];
+    bool valid[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int h = 2 * wh + (k >> 1), w = 2 * ww + (k & 1);
+      valid[k] = (h < a.H) && (w < a.W);
+      dy[k] = make_float4(0, 0, 0, 0);
+      z[k] = make_float4(0, 0, 0, 0);
+      if (valid[k]) z[k] = ld4(a.z + ((size_t)(n * a.H + h) * a.W + w) * a.C + c);
+      act[k] = make_float4(fmaf(z[k].x, sc.x, sh.x), fmaf(z[k].y, sc.y, sh.y), fmaf(z[k].z, sc.z, sh.z),
+                           fmaf(z[k].w, sc.w, sh.w));
+    }
+    for (int gi = 0; gi < a.ng; ++gi) {
+      const GradSrc& g = a.g[gi];
+      if (g.mode == GRAD_SAME) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int h = 2 * wh + (k >> 1), w = 2 * ww + (k & 1);
+          if (valid[k]) dy[k] = f4add(dy[k], ld4(g.ptr + ((size_t)(n * g.Hs + h) * g.Ws + w) * g.C + g.coff + c));
+        }
+      } else if (g.mode == GRAD_UP) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int h = 2 * wh + (k >> 1), w = 2 * ww + (k & 1);
+          if (valid[k]) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int hh = 2 * h + (j >> 1), wv = 2 * w + (j & 1);
+              dy[k] = f4add(dy[k], ld4(g.ptr + ((size_t)(n * g.Hs + hh) * g.Ws + wv) * g.C + g.coff + c));
+            }
+          }
+        }
+      } else {  // GRAD_POOL: the consumer saw maxpool2x2(relu(act)); first maximum in window scan order wins
+        if (wh < g.Hs && ww < g.Ws && valid[3]) {
+          const float4 gp = ld4(g.ptr + ((size_t)(n * g.Hs + wh) * g.Ws + ww) * g.C + g.coff + c);
+          int ix = 0, iy = 0, iz = 0, iw = 0;
+          float bx = act[0].x, by = act[0].y, bz = act[0].z, bw = act[0].w;
+#pragma unroll
+          for (int k = 1; k < 4; ++k) {
+            if (act[k].x > bx) { bx = act[k].x; ix = k; }
+            if (act[k].y > by) { by = act[k].y; iy = k; }
+            if (act[k].z > bz) { bz = act[k].z; iz = k; }
+            if (act[k].w > bw) { bw = act[k].w; iw = k; }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (ix == k) dy[k].x += gp.x;
+            if (iy == k) dy[k].y += gp.y;
+            if (iz == k) dy[k].z += gp.z;
+            if (iw == k) dy[k].w += gp.w;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!valid[k]) continue;
+      float4 d = dy[k];
+      d.x = act[k].x > 0.f ? d.x : 0.f;
+      d.y = act[k].y > 0.f ? d.y : 0.f;
+      d.z = act[k].z > 0.f ? d.z : 0.f;
+      d.w = act[k].w > 0.f ? d.w : 0.f;
+      const float4 xh = make_float4((z[k].x - mu.x) * is.x, (z[k].y - mu.y) * is.y, (z[k].z - mu.z) * is.z,
+                                    (z[k].w - mu.w) * is.w);
+      if (APPLY) {
+        const int h = 2 * wh + (k >> 1), w = 2 * ww + (k & 1);
+        float4 o;
+        o.x = sc.x * (d.x - m1.x - xh.x * m2.x);
+        o.y = sc.y * (d.y - m1.y - xh.y * m2.y);
+        o.z = sc.z * (d.z - m1.z - xh.z * m2.z);
+        o.w = sc.w * (d.w - m1.w - xh.w * m2.w);
+        *reinterpret_cast<float4*>(a.dz + ((size_t)(n * a.H + h) * a.W + w) * a.C + c) = o;
+      } else {
+        acc1 = f4add(acc1, d);
+        acc2.x = fmaf(d.x, xh.x, acc2.x);
+        acc2.y = fmaf(d.y, xh.y, acc2.y);
+        acc2.z = fmaf(d.z, xh.z, acc2.z);
+        acc2.w = fmaf(d.w, xh.w, acc2.w);
+      }
+    }
+  }
+  if (!APPLY) {
+    // every thread keeps one channel quad for its whole grid-stride loop (256 % CQ == 0, stride % CQ == 0)
+    __shared__ float red[8][256];
+    red[0][threadIdx.x] = acc1.x; red[1][threadIdx.x] = acc1.y; red[2][threadIdx.x] = acc1.z; red[3][threadIdx.x] = acc1.w;
+    red[4][threadIdx.x] = acc2.x; red[5][threadIdx.x] = acc2.y; red[6][threadIdx.x] = acc2.z; red[7][threadIdx.x] = acc2.w;
+    __syncthreads();
+    for (int j = threadIdx.x; j < 8 * CQ; j += 256) {
+      const int comp = j / CQ, cq = j - comp * CQ;
+      float s = 0.f;
+      for (int t = cq; t < 256; t += CQ) s += red[comp][t];
+      const int which = comp >> 2, cc = comp & 3;
+      a.part[((size_t)blockIdx.x * 2 + which) * a.C + cq * 4 + cc] = s;
+    }
+  }
+}
+
+int bn_bwd_num_blocks(int N, int H, int W, int C) {
+  const long long items = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
+  return min(cdiv(items, 256), 148 * 8);
+}
+static int bn_bwd_check(const BnBwdArgs& a) {
+  TNB_REQUIRE(a.C % 4 == 0 && 256 % (a.C / 4) == 0, "bn_bwd: unsupported channel count %d", a.C);
+  return 0;
+}
+int launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t st) {
+  if (int rc = bn_bwd_check(a)) return rc;
+  bn_bwd_kernel<false><<<bn_bwd_num_blocks(a.N, a.H, a.W, a.C), 256, 0, st>>>(a);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st) {
+  if (int rc = bn_bwd_check(a)) return rc;
+  bn_bwd_kernel<true><<<bn_bwd_num_blocks(a.N, a.H, a.W, a.C), 256, 0, st>>>(a);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int rows, int C, float* sums, float* dgamma,
+                                       float* dbeta) {
+  __shared__ double s1[8][33], s2[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    for (int r = threadIdx.y; r < rows; r += 8) {
+      a += (double)part[((size_t)r * 2 + 0) * C + c];
+      b += (double)part[((size_t)r * 2 + 1) * C + c];
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    double sa = 0.0, sb = 0.0;
+    for (int i = 0; i < 8; ++i) { sa += s1[i][threadIdx.x]; sb += s2[i][threadIdx.x]; }
+    sums[c] = (float)sa;
+    sums[C + c] = (float)sb;
+    dbeta[c] = (float)sa;   // d/dbeta  = sum dy
+    dgamma[c] = (float)sb;  // d/dgamma = sum dy * xhat
+  }
+}
+int launch_bn_bwd_finalize(const float* part, int rows, int C, float* sums, float* dgamma, float* dbeta,
+                           cudaStream_t st) {
+  bn_bwd_finalize_kernel<<<cdiv(C, 32), dim3(32, 8), 0, st>>>(part, rows, C, sums, dgamma, dbeta);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// WBCE / focal loss (reference utils/metric.py:3-20) forward + backward, one pass each.
+// =============================================================================================
+TNB_DEVINL float wbce_elem(float p, float y) {
+  const float lp = logf(fminf(fmaxf(p, 1e-7f), 1.f));
+  const float lq = logf(fminf(fmaxf(1.f - p, 1e-7f), 1.f));
+  return -((1.f - p) * (1.f - p) * y * lp + p * p * (1.f - y) * lq);
+}
+TNB_DEVINL float wbce_grad(float p, float y) {
+  const float q = 1.f - p;
+  const float cp = fminf(fmaxf(p, 1e-7f), 1.f), cq = fminf(fmaxf(q, 1e-7f), 1.f);
+  const float lp = logf(cp), lq = logf(cq);
+  const float gp = (p >= 1e-7f && p <= 1.f) ? 1.f / cp : 0.f;   // d clamp(p)/dp, closed interval like torch
+  const float gq = (q >= 1e-7f && q <= 1.f) ? -1.f / cq : 0.f;  // d log(clamp(1-p))/dp
+  const float t1 = -2.f * q * y * lp + q * q * y * gp;
+  const float t2 = 2.f * p * (1.f - y) * lq + p * p * (1.f - y) * gq;
+  return -(t1 + t2);
+}
+static constexpr int kWbceBlocks = 592;  // 148 SMs x 4
+int wbce_num_blocks(long long) { return kWbceBlocks; }
+
+__global__ void __launch_bounds__(256) wbce_fwd_kernel(const float* __restrict__ p, const float* __restrict__ y,
+                                                       long long per_sample, double* part) {
+  const float* ps = p + (size_t)blockIdx.y * per_sample;
+  const float* ys = y + (size_t)blockIdx.y * per_sample;
+  float acc = 0.f;
+  double dacc = 0.0;
+  int cnt = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample;
+       i += (long long)gridDim.x * blockDim.x) {
+    acc += wbce_elem(ps[i], ys[i]);
+    if (++cnt == 64) { dacc += (double)acc; acc = 0.f; cnt = 0; }
+  }
+  dacc += (double)acc;
+  __shared__ double sd[256];
+  sd[threadIdx.x] = dacc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sd[threadIdx.x] += sd[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = sd[0];
+}
+__global__ void wbce_final_kernel(const double* part, int nsamples, int nblocks, long long per_sample, int reduce,
+                                  float* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double total = 0.0;
+  for (int n = 0; n < nsamples; ++n) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += part[(size_t)n * nblocks + b];
+    if (!reduce) out[n] = (float)(s / (double)per_sample);
+    total += s;
+  }
+  if (reduce) out[0] = (float)(total / ((double)per_sample * nsamples));
+}
+int launch_wbce_fwd(const float* p, const float* y, int nsamples, long long per_sample, int reduce, double* part,
+                    float* out, cudaStream_t st) {
+  wbce_fwd_kernel<<<dim3(kWbceBlocks, nsamples), 256, 0, st>>>(p, y, per_sample, part);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  wbce_final_kernel<<<1, 32, 0, st>>>(part, nsamples, kWbceBlocks, per_sample, reduce, out);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+__global__ void __launch_bounds__(256) wbce_bwd_kernel(const float* __restrict__ p, const float* __restrict__ y,
+                                                       const float* __restrict__ gout, long long per_sample,
+                                                       int nsamples, int reduce, float* __restrict__ dp) {
+  const long long total = per_sample * nsamples;
+  const float inv = reduce ? (float)(1.0 / (double)total) : (float)(1.0 / (double)per_sample);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float g = reduce ? gout[0] : gout[i / per_sample];
+    dp[i] = g * inv * wbce_grad(p[i], y[i]);
+  }
+}
+int launch_wbce_bwd(const float* p, const float* y, const float* gout, int nsamples, long long per_sample,
+                    int reduce, float* dp, cudaStream_t st) {
+  wbce_bwd_kernel<<<148 * 8, 256, 0, st>>>(p, y, gout, per_sample, nsamples, reduce, dp);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// sample mixup (reference train.py:37-38): out[n] = x[n]*lam[n] + x[perm[n]]*(1-lam[n])
+// =============================================================================================
+__global__ void mixup_kernel(const float* __restrict__ x, const float* __restrict__ lam,
+                             const long long* __restrict__ perm, float* __restrict__ out, long long per_sample) {
+  const int n = blockIdx.y;
+  const float l = lam[n];
+  const float* a = x + (size_t)n * per_sample;
+  const float* b = x + (size_t)perm[n] * per_sample;
+  float* o = out + (size_t)n * per_sample;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample;
+       i += (long long)gridDim.x * blockDim.x)
+    o[i] = a[i] * l + b[i] * (1.f - l);
+}
+int launch_mixup(const float* x, const float* lam, const long long* perm, float* out, int N, long long per_sample,
+                 cudaStream_t st) {
+  mixup_kernel<<<dim3(min(cdiv(per_sample, 1024), 148 * 2), N), 256, 0, st>>>(x, lam, perm, out, per_sample);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// multi-tensor Adam (reference train.py:242 torch.optim.Adam(lr), betas (0.9,0.999), eps 1e-8):
+//   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+// =============================================================================================
+__global__ void adam_kernel(const AdamTensor* __restrict__ tab, float lr, float b1, float b2, float eps, float wd,
+                            float bc1, float bc2_sqrt) {
+  const AdamTensor t = tab[blockIdx.y];
+  const float step_size = lr / bc1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < t.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float g = t.g[i];
+    const float p = t.p[i];
+    if (wd != 0.f) g = fmaf(wd, p, g);
+    const float m = b1 * t.m[i] + (1.f - b1) * g;
+    const float v = b2 * t.v[i] + (1.f - b2) * g * g;
+    t.m[i] = m;
+    t.v[i] = v;
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    t.p[i] = p - step_size * (m / denom);
+  }
+}
+int launch_adam(const AdamTensor* tab, int ntensors, long long max_n, float lr, float b1, float b2, float eps,
+                float wd, int step, cudaStream_t st) {
+  const float bc1 = (float)(1.0 - pow((double)b1, (double)step));
+  const float bc2 = (float)(1.0 - pow((double)b2, (double)step));
+  const int bx = max(1, min(cdiv(max_n, 256 * 4), 64));
+  adam_kernel<<<dim3(bx, ntensors), 256, 0, st>>>(tab, lr, b1, b2, eps, wd, bc1, sqrtf(bc2));
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// heatmap -> bounding box decode (reference test.py:52-79 predict_location on predict.py:35's y_pred > 0.5).
+// One CTA per heatmap: threshold, 8-connected union-find labelling (root = raster-first pixel of each
+// component), per-component bounding boxes, then the reference's selection rule: maximum bbox area
+// w*h, ties resolved towards the component OpenCV lists first, i.e. the one whose raster-first pixel
+// comes LAST (OpenCV returns external contours in reverse raster order of their start pixel).
+// Components nested inside a hole of another component are dropped by RETR_EXTERNAL, but their bbox is
+// strictly inside the enclosing one, so they can never win or tie the maximum.
+// =============================================================================================
+TNB_DEVINL int uf_find(volatile int* parent, int x) {
+  int p = parent[x];
+  while (p != x) { x = p; p = parent[x]; }
+  return x;
+}
+TNB_DEVINL void uf_union(int* parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }
+    const int old = atomicMin(parent + a, b);
+    if (old == a) return;
+    a = old;
+  }
+}
+template <bool U8>
+__global__ void __launch_bounds__(512) decode_kernel(const void* __restrict__ maps, float thresh, int H, int W,
+                                                     int* ws, int* out) {
+  const int HW = H * W;
+  int* parent = ws + (size_t)blockIdx.x * 5 * HW;
+  int* minx = parent + HW; int* maxx = minx + HW; int* miny = maxx + HW; int* maxy = miny + HW;
+  const float* mf = reinterpret_cast<const float*>(maps) + (size_t)blockIdx.x * HW;
+  const unsigned char* mu = reinterpret_cast<const unsigned char*>(maps) + (size_t)blockIdx.x * HW;
+  __shared__ int s_any;
+  __shared__ unsigned long long s_best[16];
+  if (threadIdx.x == 0) s_any = 0;
+  __syncthreads();
+  int any = 0;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    const bool fg = U8 ? (mu[p] != 0) : (mf[p] > thresh);
+    parent[p] = fg ? p : -1;
+    if (fg) { any = 1; minx[p] = INT_MAX; maxx[p] = -1; miny[p] = INT_MAX; maxy[p] = -1; }
+  }
+  if (any) s_any = 1;
+  __syncthreads();
+  if (!s_any) {
+    if (threadIdx.x < 4) out[blockIdx.x * 4 + threadIdx.x] = 0;
+    return;
+  }
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    if (parent[p] < 0) continue;
+    const int y = p / W, x = p - y * W;
+    if (x > 0 && ((volatile int*)parent)[p - 1] >= 0) uf_union(parent, p, p - 1);
+    if (y > 0) {
+      if (((volatile int*)parent)[p - W] >= 0) uf_union(parent, p, p - W);
+      if (x > 0 && ((volatile int*)parent)[p - W - 1] >= 0) uf_union(parent, p, p - W - 1);
+      if (x + 1 < W && ((volatile int*)parent)[p - W + 1] >= 0) uf_union(parent, p, p - W + 1);
+    }
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    if (parent[p] < 0) continue;
+    const int r = uf_find(parent, p);
+    const int y = p / W, x = p - y * W;
+    atomicMin(minx + r, x); atomicMax(maxx + r, x);
+    atomicMin(miny + r, y); atomicMax(maxy + r, y);
+  }
+  __syncthreads();
+  unsigned long long best = 0ull;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    if (((volatile int*)parent)[p] != p) continue;
+    const unsigned long long area = (unsigned long long)(maxx[p] - minx[p] + 1) * (unsigned)(maxy[p] - miny[p] + 1);
+    const unsigned long long key = (area << 32) | (unsigned)p;
+    best = key > best ? key : best;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other > best ? other : best;
+  }
+  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) best = s_best[i] > best ? s_best[i] : best;
+    const int r = (int)(best & 0xffffffffu);
+    out[blockIdx.x * 4 + 0] = minx[r];
+    out[blockIdx.x * 4 + 1] = miny[r];
+    out[blockIdx.x * 4 + 2] = maxx[r] - minx[r] + 1;
+    out[blockIdx.x * 4 + 3] = maxy[r] - miny[r] + 1;
+  }
+}
+size_t decode_workspace_bytes(int nmaps, int H, int W) { return (size_t)nmaps * 5 * H * W * sizeof(int); }
+int launch_decode(const void* maps, int is_u8, float thresh, int nmaps, int H, int W, void* ws, int* out,
+                  cudaStream_t st) {
+  if (nmaps == 0) return 0;
+  if (is_u8) decode_kernel<true><<<nmaps, 512, 0, st>>>(maps, thresh, H, W, (int*)ws, out);
+  else       decode_kernel<false><<<nmaps, 512, 0, st>>>(maps, thresh, H, W, (int*)ws, out);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// InpaintNet forward (reference model.py:100-129): the whole 1-D U-Net in ONE kernel, one CTA per
+// trajectory, activations resident in shared memory (the reference launches ~30 tiny kernels).
+// =============================================================================================
+TNB_DEVINL void conv1d_k3(float* out, int Cout, const float* inA, int CA, const float* inB, int CB,
+                          const float* __restrict__ w, const float* __restrict__ b, int L, int act) {
+  const int Cin = CA + CB;
+  for (int idx = threadIdx.x; idx < Cout * L; idx += blockDim.x) {
+    const int l = idx % L, co = idx / L;
+    const float* wr = w + (size_t)co * Cin * 3;
+    float s = b[co];
+    for (int ci = 0; ci < CA; ++ci) {
+      const float* row = inA + ci * L;
+      const float w0 = __ldg(wr + ci * 3), w1 = __ldg(wr + ci * 3 + 1), w2 = __ldg(wr + ci * 3 + 2);
+      const float xm = l > 0 ? row[l - 1] : 0.f, xp = l + 1 < L ? row[l + 1] : 0.f;
+      s = fmaf(w0, xm, s); s = fmaf(w1, row[l], s); s = fmaf(w2, xp, s);
+    }
+    for (int ci = 0; ci < CB; ++ci) {
+      const float* row = inB + ci * L;
+      const float* wq = wr + (size_t)(CA + ci) * 3;
+      const float w0 = __ldg(wq), w1 = __ldg(wq + 1), w2 = __ldg(wq + 2);
+      const float xm = l > 0 ? row[l - 1] : 0.f, xp = l + 1 < L ? row[l + 1] : 0.f;
+      s = fmaf(w0, xm, s); s = fmaf(w1, row[l], s); s = fmaf(w2, xp, s);
+    }
+    if (act == 1) s = s > 0.f ? s : 0.01f * s;          // LeakyReLU(0.01), model.py:81
+    else if (act == 2) s = 1.f / (1.f + expf(-s));      // sigmoid, model.py:127
+    out[idx] = s;
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(256) inpaint_fwd_kernel(const float* __restrict__ coords,
+                                                          const float* __restrict__ mask, InpaintParams P, int L,
+                                                          float* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* in0 = sm;            // [3][L]   cat(x, m) permuted (model.py:114-115)
+  float* x1 = in0 + 3 * L;    // [32][L]
+  float* x2 = x1 + 32 * L;    // [64][L]
+  float* x3 = x2 + 64 * L;    // [128][L]
+  float* t1 = x3 + 128 * L;   // [256][L]
+  float* t2 = t1 + 256 * L;   // [256][L]
+  float* u1 = t2 + 256 * L;   // [128][L]
+  float* u2 = u1 + 128 * L;   // [64][L]
+  float* u3 = u2 + 64 * L;    // [32][L]
+  float* o = u3 + 32 * L;     // [2][L]
+  const int n = blockIdx.x;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    in0[0 * L + i] = coords[((size_t)n * L + i) * 2 + 0];
+    in0[1 * L + i] = coords[((size_t)n * L + i) * 2 + 1];
+    in0[2 * L + i] = mask[(size_t)n * L + i];
+  }
+  __syncthreads();
+  conv1d_k3(x1, 32, in0, 3, nullptr, 0, P.w[0], P.b[0], L, 1);
+  conv1d_k3(x2, 64, x1, 32, nullptr, 0, P.w[1], P.b[1], L, 1);
+  conv1d_k3(x3, 128, x2, 64, nullptr, 0, P.w[2], P.b[2], L, 1);
+  conv1d_k3(t1, 256, x3, 128, nullptr, 0, P.w[3], P.b[3], L, 1);
+  conv1d_k3(t2, 256, t1, 256, nullptr, 0, P.w[4], P.b[4], L, 1);
+  conv1d_k3(u1, 128, t2, 256, x3, 128, P.w[5], P.b[5], L, 1);  // cat([x, x3]) model.py:120
+  conv1d_k3(u2, 64, u1, 128, x2, 64, P.w[6], P.b[6], L, 1);    // cat([x, x2]) model.py:122
+  conv1d_k3(u3, 32, u2, 64, x1, 32, P.w[7], P.b[7], L, 1);     // cat([x, x1]) model.py:124
+  conv1d_k3(o, 2, u3, 32, nullptr, 0, P.w[8], P.b[8], L, 2);
+  for (int i = threadIdx.x; i < L * 2; i += blockDim.x) {
+    const int l = i >> 1, c = i & 1;
+    out[((size_t)n * L + l) * 2 + c] = o[c * L + l];
+  }
+}
+int launch_inpaint_fwd(const float* coords, const float* mask, const InpaintParams& p, int N, int L, float* out,
+                       cudaStream_t st) {
+  const size_t smem = (size_t)(3 + 32 + 64 + 128 + 256 + 256 + 128 + 64 + 32 + 2) * L * sizeof(float);
+  TNB_REQUIRE(smem <= 227 * 1024, "inpaint_fwd: sequence length %d too long for the fused kernel", L);
+  TNB_CHECK_CUDA(cudaFuncSetAttribute(inpaint_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  inpaint_fwd_kernel<<<N, 256, smem, st>>>(coords, mask, p, L, out);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace tnb

@@ -1,0 +1,45 @@
+// HBM-bound kernels of the TrackNet hot path (everything that is not a 3x3 convolution).
+#pragma once
+#include "igemm.cuh"
+
+namespace tnb {
+
+enum GradMode : int { GRAD_SAME = TNB_GRAD_SAME, GRAD_POOL = TNB_GRAD_POOL, GRAD_UP = TNB_GRAD_UP };
+using GradSrc = tnb_gradsrc_t;  // see include/tracknet_b200.h
+using BnBwdArgs = tnb_bnbwd_t;
+
+int launch_pack_input(const float* x_nchw, float* out_nhwc, int N, int C, int H, int W, int Cpad, cudaStream_t st);
+int launch_bn_finalize(const float* part, int rows, double count, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, float momentum, float eps, int training,
+                       float* scale, float* shift, float* mean, float* invstd, int C, cudaStream_t st);
+int launch_predictor_fwd(const SrcDesc& src, int N, int H, int W, const float* wp, const float* bias, int O,
+                         float* y_nchw, cudaStream_t st);
+int launch_predictor_bwd(const SrcDesc& src, int N, int H, int W, const float* wp, int O, const float* dy,
+                         const float* y, float* dA, float* dwp, float* dbias, cudaStream_t st);
+int bn_bwd_num_blocks(int N, int H, int W, int C);
+int launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t st);
+int launch_bn_bwd_finalize(const float* part, int rows, int C, float* sums, float* dgamma, float* dbeta,
+                           cudaStream_t st);
+int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st);
+
+int wbce_num_blocks(long long per_sample);
+int launch_wbce_fwd(const float* p, const float* y, int nsamples, long long per_sample, int reduce,
+                    double* part, float* out, cudaStream_t st);
+int launch_wbce_bwd(const float* p, const float* y, const float* gout, int nsamples, long long per_sample,
+                    int reduce, float* dp, cudaStream_t st);
+int launch_mixup(const float* x, const float* lam, const long long* perm, float* out, int N, long long per_sample,
+                 cudaStream_t st);
+
+struct AdamTensor { float* p; const float* g; float* m; float* v; long long n; };
+int launch_adam(const AdamTensor* table_dev, int ntensors, long long max_n, float lr, float b1, float b2, float eps,
+                float wd, int step, cudaStream_t st);
+
+size_t decode_workspace_bytes(int nmaps, int H, int W);
+int launch_decode(const void* maps, int is_u8, float thresh, int nmaps, int H, int W, void* ws, int* out_xywh,
+                  cudaStream_t st);
+
+struct InpaintParams { const float* w[9]; const float* b[9]; };
+int launch_inpaint_fwd(const float* coords, const float* mask, const InpaintParams& p, int N, int L, float* out,
+                       cudaStream_t st);
+
+}  // namespace tnb

@@ -1,0 +1,249 @@
+// TrackNet.forward and its autograd backward as one C-ABI call each (reference model.py:44-73).
+// This file is host-side orchestration only: it wires the 17 Conv2DBlocks' tensors into the view /
+// gradient-source descriptors the kernels consume and lays out the caller-provided workspace.
+#include "kernels.cuh"
+#include <string.h>
+
+namespace tnb {
+
+namespace {
+
+constexpr int kLayers = 17;
+// Layer wiring of TrackNet (reference model.py:47-53 constructor, :58-70 forward).
+struct LayerDef {
+  int cout, level;  // level: spatial size = (H >> level, W >> level)
+  int src0, mode0;  // producer layer (-1 = packed network input) and how the consumer sees it
+  int src1, mode1;  // second (skip) source for the concat layers, -1 if none
+};
+const LayerDef kDefs[kLayers] = {
+    {64, 0, -1, SRC_IDENTITY, -1, 0},                         //  0 down_block_1.conv_1
+    {64, 0, 0, SRC_AFFINE_RELU, -1, 0},                       //  1 down_block_1.conv_2   -> x1
+    {128, 1, 1, SRC_AFFINE_RELU_POOL, -1, 0},                 //  2 down_block_2.conv_1   (MaxPool, model.py:59)
+    {128, 1, 2, SRC_AFFINE_RELU, -1, 0},                      //  3 down_block_2.conv_2   -> x2
+    {256, 2, 3, SRC_AFFINE_RELU_POOL, -1, 0},                 //  4 down_block_3.conv_1   (model.py:61)
+    {256, 2, 4, SRC_AFFINE_RELU, -1, 0},                      //  5 down_block_3.conv_2
+    {256, 2, 5, SRC_AFFINE_RELU, -1, 0},                      //  6 down_block_3.conv_3   -> x3
+    {512, 3, 6, SRC_AFFINE_RELU_POOL, -1, 0},                 //  7 bottleneck.conv_1     (model.py:63)
+    {512, 3, 7, SRC_AFFINE_RELU, -1, 0},                      //  8 bottleneck.conv_2
+    {512, 3, 8, SRC_AFFINE_RELU, -1, 0},                      //  9 bottleneck.conv_3
+    {256, 2, 9, SRC_AFFINE_RELU_UP, 6, SRC_AFFINE_RELU},      // 10 up_block_1.conv_1     cat[up(x), x3] (model.py:65)
+    {256, 2, 10, SRC_AFFINE_RELU, -1, 0},                     // 11 up_block_1.conv_2
+    {256, 2, 11, SRC_AFFINE_RELU, -1, 0},                     // 12 up_block_1.conv_3
+    {128, 1, 12, SRC_AFFINE_RELU_UP, 3, SRC_AFFINE_RELU},     // 13 up_block_2.conv_1     cat[up(x), x2] (model.py:67)
+    {128, 1, 13, SRC_AFFINE_RELU, -1, 0},                     // 14 up_block_2.conv_2
+    {64, 0, 14, SRC_AFFINE_RELU_UP, 1, SRC_AFFINE_RELU},      // 15 up_block_3.conv_1     cat[up(x), x1] (model.py:69)
+    {64, 0, 15, SRC_AFFINE_RELU, -1, 0},                      // 16 up_block_3.conv_2
+};
+
+struct LayerBuf {
+  int H, W, cin, cin_real, cout;
+  float *z, *scale, *shift, *mean, *invstd, *stat_part;
+  int stat_rows;
+  float *dz, *din, *bwd_part, *bwd_sums;
+  int bwd_rows;
+  uint16_t *wf, *wd;
+};
+struct Plan {
+  LayerBuf L[kLayers];
+  float* xin;
+  float* dA_pred;
+  int cpad;
+  size_t bytes;
+};
+
+struct Bump {
+  uint8_t* base;
+  size_t off;
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+int layer_cin(const tnb_tracknet_cfg_t& c, int l) {
+  if (l == 0) return (c.in_dim + 31) / 32 * 32;
+  const LayerDef& d = kDefs[l];
+  int cin = kDefs[d.src0].cout;
+  if (d.src1 >= 0) cin += kDefs[d.src1].cout;
+  return cin;
+}
+
+int build_plan(const tnb_tracknet_cfg_t& c, void* ws, Plan* P) {
+  TNB_REQUIRE(c.n > 0 && c.h > 0 && c.w > 0 && c.h % 8 == 0 && c.w % 8 == 0,
+              "tracknet: input %dx%d must be divisible by 8 (reference model.py:59-69 pools 3x then concatenates)",
+              c.h, c.w);
+  TNB_REQUIRE(c.in_dim > 0 && c.out_dim > 0 && c.out_dim <= 16, "tracknet: bad in_dim/out_dim %d/%d", c.in_dim,
+              c.out_dim);
+  TNB_REQUIRE((c.fwd_terms == 1 || c.fwd_terms == 3) && (c.bwd_terms == 1 || c.bwd_terms == 3),
+              "tracknet: terms must be 1 or 3");
+  Bump b{reinterpret_cast<uint8_t*>(ws), 0};
+  P->cpad = (c.in_dim + 31) / 32 * 32;
+  const size_t npix0 = (size_t)c.n * c.h * c.w;
+  P->xin = b.take<float>(npix0 * P->cpad);
+  P->dA_pred = b.take<float>(npix0 * 64);
+  for (int l = 0; l < kLayers; ++l) {
+    LayerBuf& B = P->L[l];
+    const LayerDef& d = kDefs[l];
+    B.H = c.h >> d.level; B.W = c.w >> d.level;
+    B.cout = d.cout; B.cin = layer_cin(c, l); B.cin_real = (l == 0) ? c.in_dim : B.cin;
+    const size_t npix = (size_t)c.n * B.H * B.W;
+    B.z = b.take<float>(npix * B.cout);
+    B.scale = b.take<float>(B.cout); B.shift = b.take<float>(B.cout);
+    B.mean = b.take<float>(B.cout); B.invstd = b.take<float>(B.cout);
+    B.stat_rows = conv3x3_num_stat_rows(c.n, B.H, B.W, B.cin, B.cout, c.fwd_terms);
+    if (B.stat_rows < 0) return -2;
+    B.stat_part = b.take<float>((size_t)B.stat_rows * 2 * B.cout);
+    B.wf = b.take<uint16_t>(conv3x3_wpack_elems(B.cin, B.cout));
+    if (c.training) {
+      B.dz = b.take<float>(npix * B.cout);
+      B.din = (l > 0) ? b.take<float>(npix * B.cin) : nullptr;
+      B.bwd_rows = bn_bwd_num_blocks(c.n, B.H, B.W, B.cout);
+      B.bwd_part = b.take<float>((size_t)B.bwd_rows * 2 * B.cout);
+      B.bwd_sums = b.take<float>(2 * B.cout);
+      B.wd = (l > 0) ? b.take<uint16_t>(conv3x3_wpack_elems(B.cout, B.cin)) : nullptr;
+    } else {
+      B.dz = B.din = B.bwd_part = B.bwd_sums = nullptr; B.wd = nullptr; B.bwd_rows = 0;
+    }
+  }
+  P->bytes = (b.off + 255) & ~(size_t)255;
+  return 0;
+}
+
+SrcDesc make_src(const Plan& P, const tnb_tracknet_cfg_t& c, int layer, int mode) {
+  SrcDesc s;
+  if (layer < 0) {
+    s.ptr = P.xin; s.scale = nullptr; s.shift = nullptr; s.C = P.cpad; s.Hs = c.h; s.Ws = c.w; s.mode = SRC_IDENTITY;
+  } else {
+    const LayerBuf& B = P.L[layer];
+    s.ptr = B.z; s.scale = B.scale; s.shift = B.shift; s.C = B.cout; s.Hs = B.H; s.Ws = B.W; s.mode = mode;
+  }
+  return s;
+}
+ViewDesc make_view(const Plan& P, const tnb_tracknet_cfg_t& c, int l) {
+  const LayerDef& d = kDefs[l];
+  const LayerBuf& B = P.L[l];
+  ViewDesc v;
+  memset(&v, 0, sizeof(v));
+  v.s[0] = make_src(P, c, d.src0, d.mode0);
+  v.C0 = v.s[0].C;
+  if (d.src1 >= 0) v.s[1] = make_src(P, c, d.src1, d.mode1);
+  else v.s[1] = v.s[0];
+  v.C = B.cin; v.N = c.n; v.H = B.H; v.W = B.W;
+  return v;
+}
+
+struct CounterTable { long long* p[kLayers]; };
+__global__ void inc_counters_kernel2(CounterTable t) {
+  if (threadIdx.x < kLayers) *t.p[threadIdx.x] += 1;
+}
+
+}  // namespace
+
+size_t tracknet_workspace_bytes(const tnb_tracknet_cfg_t& c) {
+  Plan P;
+  if (build_plan(c, nullptr, &P)) return 0;
+  return P.bytes;
+}
+
+int tracknet_forward(const tnb_tracknet_cfg_t& c, const float* x, void* const* params, float* y, void* ws,
+                     size_t ws_bytes, cudaStream_t st) {
+  Plan P;
+  if (int rc = build_plan(c, ws, &P)) return rc;
+  TNB_REQUIRE(ws_bytes >= P.bytes, "tracknet_forward: workspace too small (%zu < %zu)", ws_bytes, P.bytes);
+  if (int rc = launch_pack_input(x, P.xin, c.n, c.in_dim, c.h, c.w, P.cpad, st)) return rc;
+  for (int l = 0; l < kLayers; ++l) {
+    LayerBuf& B = P.L[l];
+    const float* w = (const float*)params[l * 6 + 0];
+    ConvPlan cp;
+    if (int rc = conv3x3_plan(c.n, B.H, B.W, B.cin, B.cout, c.fwd_terms, &cp)) return rc;
+    if (int rc = launch_pack_weights(w, B.wf, B.cout, B.cin_real, 0, 0, cp.BN, st)) return rc;
+    const ViewDesc v = make_view(P, c, l);
+    if (int rc = launch_conv3x3(v, B.wf, B.z, c.training ? B.stat_part : nullptr, B.cout, c.fwd_terms, 0,
+                                c.variant & 3, st))
+      return rc;
+    if (int rc = launch_bn_finalize(B.stat_part, B.stat_rows, (double)c.n * B.H * B.W, (const float*)params[l * 6 + 1],
+                                    (const float*)params[l * 6 + 2], (float*)params[l * 6 + 3],
+                                    (float*)params[l * 6 + 4], c.bn_momentum, c.bn_eps, c.training, B.scale, B.shift,
+                                    B.mean, B.invstd, B.cout, st))
+      return rc;
+  }
+  if (c.training) {
+    CounterTable t;
+    for (int l = 0; l < kLayers; ++l) t.p[l] = (long long*)params[l * 6 + 5];
+    inc_counters_kernel2<<<1, 32, 0, st>>>(t);
+    TNB_CHECK_CUDA(cudaGetLastError());
+  }
+  const SrcDesc last = make_src(P, c, kLayers - 1, SRC_AFFINE_RELU);
+  return launch_predictor_fwd(last, c.n, c.h, c.w, (const float*)params[kLayers * 6 + 0],
+                              (const float*)params[kLayers * 6 + 1], c.out_dim, y, st);
+}
+
+int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float* y, void* const* params,
+                      void* const* grads, void* ws, size_t ws_bytes, cudaStream_t st) {
+  TNB_REQUIRE(c.training, "tracknet_backward: only the training-mode (batch-statistics) backward is implemented");
+  Plan P;
+  if (int rc = build_plan(c, ws, &P)) return rc;
+  TNB_REQUIRE(ws_bytes >= P.bytes, "tracknet_backward: workspace too small (%zu < %zu)", ws_bytes, P.bytes);
+  const SrcDesc last = make_src(P, c, kLayers - 1, SRC_AFFINE_RELU);
+  if (int rc = launch_predictor_bwd(last, c.n, c.h, c.w, (const float*)params[kLayers * 6 + 0], c.out_dim, dy, y,
+                                    P.dA_pred, (float*)grads[kLayers * 3 + 0], (float*)grads[kLayers * 3 + 1], st))
+    return rc;
+  for (int l = kLayers - 1; l >= 0; --l) {
+    LayerBuf& B = P.L[l];
+    BnBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    // consumers of this layer's activation = every later layer that lists it as a source (+ the predictor)
+    if (l == kLayers - 1) {
+      a.g[a.ng++] = GradSrc{P.dA_pred, 64, 0, GRAD_SAME, c.h, c.w};
+    }
+    for (int j = l + 1; j < kLayers; ++j) {
+      const LayerDef& d = kDefs[j];
+      const LayerBuf& J = P.L[j];
+      if (d.src0 == l) {
+        const int m = d.mode0 == SRC_AFFINE_RELU_POOL ? GRAD_POOL : d.mode0 == SRC_AFFINE_RELU_UP ? GRAD_UP : GRAD_SAME;
+        TNB_REQUIRE(a.ng < 2, "tracknet_backward: too many consumers");
+        a.g[a.ng++] = GradSrc{J.din, J.cin, 0, m, J.H, J.W};
+      }
+      if (d.src1 == l) {
+        TNB_REQUIRE(a.ng < 2, "tracknet_backward: too many consumers");
+        a.g[a.ng++] = GradSrc{J.din, J.cin, kDefs[d.src0].cout, GRAD_SAME, J.H, J.W};
+      }
+    }
+    a.z = B.z; a.scale = B.scale; a.shift = B.shift; a.mean = B.mean; a.invstd = B.invstd;
+    a.N = c.n; a.H = B.H; a.W = B.W; a.C = B.cout;
+    a.part = B.bwd_part; a.sums = B.bwd_sums; a.dz = B.dz;
+    a.inv_count = (float)(1.0 / ((double)c.n * B.H * B.W));
+    if (int rc = launch_bn_bwd_reduce(a, st)) return rc;
+    if (int rc = launch_bn_bwd_finalize(B.bwd_part, B.bwd_rows, B.cout, B.bwd_sums, (float*)grads[l * 3 + 1],
+                                        (float*)grads[l * 3 + 2], st))
+      return rc;
+    if (int rc = launch_bn_bwd_apply(a, st)) return rc;
+    const float* w = (const float*)params[l * 6 + 0];
+    if (l > 0) {
+      ViewDesc dv;
+      memset(&dv, 0, sizeof(dv));
+      dv.s[0] = SrcDesc{B.dz, nullptr, nullptr, B.cout, B.H, B.W, SRC_IDENTITY};
+      dv.s[1] = dv.s[0];
+      dv.C0 = dv.C = B.cout; dv.N = c.n; dv.H = B.H; dv.W = B.W;
+      ConvPlan cp;
+      if (int rc = conv3x3_plan(c.n, B.H, B.W, B.cout, B.cin, c.bwd_terms, &cp)) return rc;
+      if (int rc = launch_pack_weights(w, B.wd, B.cout, B.cin, 1, 1, cp.BN, st)) return rc;
+      if (int rc = launch_conv3x3(dv, B.wd, B.din, nullptr, B.cin, c.bwd_terms, 1, c.variant & 3, st)) return rc;
+    }
+    float* dw = (float*)grads[l * 3 + 0];
+    TNB_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)B.cout * B.cin_real * 9, st));
+    const ViewDesc v = make_view(P, c, l);
+    if (int rc = launch_wgrad3x3(v, B.dz, dw, B.cout, B.cin_real, c.bwd_terms, 1, (c.variant >> 2) & 3, st)) return rc;
+  }
+  return 0;
+}
+
+int tracknet_num_launches(const tnb_tracknet_cfg_t& c, int backward) {
+  if (!backward) return 1 + kLayers * 3 + (c.training ? 1 : 0) + 1;  // pack, (wpack, conv, bn_finalize) x17, counters, predictor
+  return 1 + kLayers * 4 + (kLayers - 1) * 2;                         // predictor_bwd, (reduce, finalize, apply, wgrad) x17, (wpack, dgrad) x16
+}
+
+}  // namespace tnb

@@ -1,0 +1,210 @@
+"""TrackNet / InpaintNet with the reference's class names, constructor arguments, forward signatures
+and state_dict layout (reference model.py:4-129), executing on hand-written sm_100a kernels.
+
+The sub-modules (``conv``, ``bn``, ``relu`` ...) exist only as parameter/buffer containers so that
+``state_dict()`` / ``load_state_dict()`` / ``parameters()`` order are byte-compatible with reference
+checkpoints (104 entries for TrackNet, 20 for InpaintNet). ``forward`` never calls
+them: the whole network runs through ``tnb_tracknet_forward`` / ``tnb_tracknet_backward`` (C ABI).
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class Conv2DBlock(nn.Module):
+    """ Conv2D + BN + ReLU (parameter container; reference model.py:4-16) """
+
+    def __init__(self, in_dim, out_dim, **kwargs):
+        super(Conv2DBlock, self).__init__(**kwargs)
+        self.conv = nn.Conv2d(in_dim, out_dim, kernel_size=3, padding='same', bias=False)
+        self.bn = nn.BatchNorm2d(out_dim)
+        self.relu = nn.ReLU()
+
+
+class Double2DConv(nn.Module):
+    """ Conv2DBlock x 2 (reference model.py:18-28) """
+
+    def __init__(self, in_dim, out_dim):
+        super(Double2DConv, self).__init__()
+        self.conv_1 = Conv2DBlock(in_dim, out_dim)
+        self.conv_2 = Conv2DBlock(out_dim, out_dim)
+
+
+class Triple2DConv(nn.Module):
+    """ Conv2DBlock x 3 (reference model.py:30-42) """
+
+    def __init__(self, in_dim, out_dim):
+        super(Triple2DConv, self).__init__()
+        self.conv_1 = Conv2DBlock(in_dim, out_dim)
+        self.conv_2 = Conv2DBlock(out_dim, out_dim)
+        self.conv_3 = Conv2DBlock(out_dim, out_dim)
+
+
+def _cfg(n, h, w, in_dim, out_dim, training, precision, variant=0):
+    terms = {"fp32x3": (3, 3), "tf32like": (1, 1)}[precision]
+    return _lib.TrackNetCfg(n=n, h=h, w=w, in_dim=in_dim, out_dim=out_dim, training=int(training),
+                            fwd_terms=terms[0], bwd_terms=terms[1], variant=variant, bn_eps=1e-5, bn_momentum=0.1)
+
+
+class _TrackNetFunction(torch.autograd.Function):
+    """autograd bridge: forward = tnb_tracknet_forward, backward = tnb_tracknet_backward."""
+
+    @staticmethod
+    def forward(ctx, x, module, *params):
+        lib = _lib.load()
+        n, _, h, w = x.shape
+        cfg = _cfg(n, h, w, module.in_dim, module.out_dim, module.training, module.precision, module._variant)
+        nbytes = lib.tnb_tracknet_workspace_bytes(C.byref(cfg))
+        if nbytes == 0:
+            # mirror the reference's failure for sizes its pooling / concat cannot handle (model.py:59-69)
+            raise RuntimeError(lib.tnb_last_error().decode())
+        ws = module._workspace(nbytes, x.device)
+        y = torch.empty((n, module.out_dim, h, w), dtype=torch.float32, device=x.device)
+        tensors = module._state_tensors()
+        _lib.check(lib.tnb_tracknet_forward(C.byref(cfg), x.data_ptr(), _lib.ptr_array(tensors), y.data_ptr(),
+                                            ws.data_ptr(), nbytes, _lib.stream_ptr()))
+        ctx.module, ctx.cfg, ctx.ws, ctx.nbytes = module, cfg, ws, nbytes
+        ctx.save_for_backward(y)
+        ctx.set_materialize_grads(True)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        (y,) = ctx.saved_tensors
+        module = ctx.module
+        if not ctx.cfg.training:
+            raise RuntimeError("tracknet_b200: backward through an eval()-mode TrackNet is not implemented")
+        params = list(module.parameters())
+        grads = [torch.empty_like(p) for p in params]
+        dy = dy.contiguous()
+        _lib.check(lib.tnb_tracknet_backward(C.byref(ctx.cfg), dy.data_ptr(), y.data_ptr(),
+                                             _lib.ptr_array(module._state_tensors()), _lib.ptr_array(grads),
+                                             ctx.ws.data_ptr(), ctx.nbytes, _lib.stream_ptr()))
+        return (None, None) + tuple(grads)
+
+
+class TrackNet(nn.Module):
+    """Drop-in for reference ``model.TrackNet`` (model.py:44-73).
+
+    ``precision``: "fp32x3" (default) computes every 3x3 convolution as a 3-term fp16 (forward) / bf16
+    (backward) split product with fp32 accumulation - within ~2e-5 of the reference's fp32 heatmaps;
+    "tf32like" is a single 16-bit pass (what the reference's own cuDNN TF32 path amounts to; ~7e-3).
+    """
+
+    def __init__(self, in_dim, out_dim, precision="fp32x3"):
+        super(TrackNet, self).__init__()
+        self.down_block_1 = Double2DConv(in_dim, 64)
+        self.down_block_2 = Double2DConv(64, 128)
+        self.down_block_3 = Triple2DConv(128, 256)
+        self.bottleneck = Triple2DConv(256, 512)
+        self.up_block_1 = Triple2DConv(768, 256)
+        self.up_block_2 = Double2DConv(384, 128)
+        self.up_block_3 = Double2DConv(192, 64)
+        self.predictor = nn.Conv2d(64, out_dim, (1, 1))
+        self.sigmoid = nn.Sigmoid()
+        self.in_dim, self.out_dim = in_dim, out_dim
+        if precision not in ("fp32x3", "tf32like"):
+            raise ValueError("precision must be 'fp32x3' or 'tf32like'")
+        self.precision = precision
+        self._variant = 0
+        self._ws = None
+
+    def _blocks(self):
+        for blk in (self.down_block_1, self.down_block_2, self.down_block_3, self.bottleneck, self.up_block_1,
+                    self.up_block_2, self.up_block_3):
+            for name in ("conv_1", "conv_2", "conv_3"):
+                if hasattr(blk, name):
+                    yield getattr(blk, name)
+
+    def _state_tensors(self):
+        """104 tensors in state_dict order (what tnb_tracknet_forward expects as ``params``)."""
+        out = []
+        for b in self._blocks():
+            out += [b.conv.weight, b.bn.weight, b.bn.bias, b.bn.running_mean, b.bn.running_var,
+                    b.bn.num_batches_tracked]
+        out += [self.predictor.weight, self.predictor.bias]
+        return out
+
+    def _workspace(self, nbytes, device):
+        # In training the workspace holds the saved-for-backward tensors of THIS forward, so every
+        # forward gets its own buffer; in inference one buffer is reused.
+        if self.training and torch.is_grad_enabled():
+            return torch.empty(nbytes, dtype=torch.uint8, device=device)
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != device:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return self._ws
+
+    def forward(self, x):
+        _lib.require_cuda(x)
+        if x.dim() != 4 or x.shape[1] != self.in_dim:
+            raise RuntimeError(f"TrackNet expects input (N, {self.in_dim}, H, W), got {tuple(x.shape)}")
+        for t in self._state_tensors():
+            _lib.require_cuda(t)
+        x = x.contiguous().float()
+        return _TrackNetFunction.apply(x, self, *self.parameters())
+
+
+class Conv1DBlock(nn.Module):
+    """ Conv1D + LeakyReLU (parameter container; reference model.py:76-86) """
+
+    def __init__(self, in_dim, out_dim, **kwargs):
+        super(Conv1DBlock, self).__init__(**kwargs)
+        self.conv = nn.Conv1d(in_dim, out_dim, kernel_size=3, padding='same', bias=True)
+        self.relu = nn.LeakyReLU()
+
+
+class Double1DConv(nn.Module):
+    """ Conv1DBlock x 2 (reference model.py:88-98) """
+
+    def __init__(self, in_dim, out_dim):
+        super(Double1DConv, self).__init__()
+        self.conv_1 = Conv1DBlock(in_dim, out_dim)
+        self.conv_2 = Conv1DBlock(out_dim, out_dim)
+
+
+class InpaintNet(nn.Module):
+    """Drop-in for reference ``model.InpaintNet`` (model.py:100-129); forward is one fused kernel.
+
+    Inference only in this round: ``forward`` does not record an autograd graph.
+    """
+
+    def __init__(self):
+        super(InpaintNet, self).__init__()
+        self.down_1 = Conv1DBlock(3, 32)
+        self.down_2 = Conv1DBlock(32, 64)
+        self.down_3 = Conv1DBlock(64, 128)
+        self.buttleneck = Double1DConv(128, 256)
+        self.up_1 = Conv1DBlock(384, 128)
+        self.up_2 = Conv1DBlock(192, 64)
+        self.up_3 = Conv1DBlock(96, 32)
+        self.predictor = nn.Conv1d(32, 2, 3, padding='same')
+        self.sigmoid = nn.Sigmoid()
+
+    def _param_tensors(self):
+        convs = [self.down_1.conv, self.down_2.conv, self.down_3.conv, self.buttleneck.conv_1.conv,
+                 self.buttleneck.conv_2.conv, self.up_1.conv, self.up_2.conv, self.up_3.conv, self.predictor]
+        out = []
+        for c in convs:
+            out += [c.weight, c.bias]
+        return out
+
+    def forward(self, x, m):
+        _lib.require_cuda(x, m)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise RuntimeError("tracknet_b200: InpaintNet training (backward) is not implemented; "
+                               "call under torch.no_grad() / model.eval()")
+        lib = _lib.load()
+        n, l = x.shape[0], x.shape[1]
+        x = x.contiguous().float()
+        m = m.contiguous().float()
+        out = torch.empty((n, l, 2), dtype=torch.float32, device=x.device)
+        tensors = self._param_tensors()
+        for t in tensors:
+            _lib.require_cuda(t)
+        _lib.check(lib.tnb_inpaintnet_fwd(x.data_ptr(), m.data_ptr(), _lib.ptr_array(tensors), n, l,
+                                          out.data_ptr(), _lib.stream_ptr()))
+        return out

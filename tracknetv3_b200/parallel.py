@@ -1,0 +1,41 @@
+"""Data-parallel training across the GPUs of one box: one process per GPU, replicas hold identical
+parameters, the only collective is ONE allreduce of the flat fp32 gradient bucket (45.36 MB for
+TrackNet(27, 8)) over NCCL/NVLink per step. The reference has no multi-GPU code;
+semantics follow torch DDP's defaults: gradients averaged over ranks, BatchNorm statistics per replica.
+"""
+import torch
+import torch.distributed as dist
+from torch._utils import _flatten_dense_tensors, _unflatten_dense_tensors
+
+
+def broadcast_module(module, src=0):
+    """Make every rank's parameters and buffers equal to rank ``src``'s (what DDP does at construction)."""
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src)
+
+
+class GradBucket:
+    """Flat gradient bucket: ``allreduce()`` averages all parameter gradients across ranks in one call."""
+
+    def __init__(self, module, process_group=None):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+
+    def allreduce(self):
+        if self.world == 1:
+            return
+        grads = [p.grad for p in self.params if p.grad is not None]
+        flat = _flatten_dense_tensors(grads)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        flat.div_(self.world)
+        for g, f in zip(grads, _unflatten_dense_tensors(flat, grads)):
+            g.copy_(f)
+
+
+def shard_batch(n_total, rank, world):
+    """Contiguous sample range of a global batch owned by ``rank`` (pure data parallelism)."""
+    per = n_total // world
+    rem = n_total % world
+    start = rank * per + min(rank, rem)
+    return start, start + per + (1 if rank < rem else 0)
