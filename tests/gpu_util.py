@@ -1,0 +1,85 @@
+"""Helpers for the -m gpu parity tests: everything below goes through the C ABI (ctypes)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from tracknetv3_b200 import _lib
+from tracknetv3_b200._lib import Src, View, GradSrc, BnBwd
+
+DEV = "cuda"
+
+
+def lib():
+    return _lib.load()
+
+
+def st():
+    return _lib.stream_ptr()
+
+
+def nhwc(t):
+    """NCHW torch tensor -> contiguous NHWC CUDA fp32."""
+    return t.permute(0, 2, 3, 1).contiguous().float().to(DEV)
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+def make_src(t_nhwc, mode=_lib.SRC_IDENTITY, scale=None, shift=None):
+    n, h, w, c = t_nhwc.shape
+    return Src(ptr=t_nhwc.data_ptr(), scale=scale.data_ptr() if scale is not None else None,
+               shift=shift.data_ptr() if shift is not None else None, C=c, Hs=h, Ws=w, mode=mode)
+
+
+def make_view(srcs, n, h, w):
+    v = View()
+    v.s[0] = srcs[0]
+    v.s[1] = srcs[1] if len(srcs) > 1 else srcs[0]
+    v.C0 = srcs[0].C
+    v.C = sum(s.C for s in srcs)
+    v.N, v.H, v.W = n, h, w
+    return v
+
+
+def pack_weights(w_oihw, mode, fmt):
+    L = lib()
+    co, ci = w_oihw.shape[:2]
+    kside, nside = (ci, co) if mode == 0 else (co, ci)
+    out = torch.zeros(L.tnb_conv3x3_wpack_elems(kside, nside), dtype=torch.int16, device=DEV)
+    _lib.check(L.tnb_conv3x3_pack_weights(w_oihw.contiguous().data_ptr(), out.data_ptr(), co, ci, mode, fmt, st()))
+    return out
+
+
+def conv3x3(view, w_oihw, cout, terms=3, fmt=0, variant=0, stats=False, mode=0):
+    """Run tnb_conv3x3_fwd; returns (out NHWC, stat partials or None)."""
+    L = lib()
+    wp = pack_weights(w_oihw, mode, fmt)
+    out = torch.full((view.N, view.H, view.W, cout), float("nan"), device=DEV)
+    part = None
+    if stats:
+        rows = L.tnb_conv3x3_stat_rows(view.N, view.H, view.W, view.C, cout, terms)
+        part = torch.full((rows, 2, cout), float("nan"), device=DEV)
+    _lib.check(L.tnb_conv3x3_fwd(C.byref(view), wp.data_ptr(), out.data_ptr(), part.data_ptr() if stats else None,
+                                 cout, terms, fmt, variant, st()))
+    torch.cuda.synchronize()
+    return out, part
+
+
+def wgrad3x3(view, dz_nhwc, cout, cin_real, terms=3, fmt=1, variant=0):
+    L = lib()
+    dw = torch.zeros((cout, cin_real, 3, 3), device=DEV)
+    _lib.check(L.tnb_conv3x3_wgrad(C.byref(view), dz_nhwc.data_ptr(), dw.data_ptr(), cout, cin_real, terms, fmt,
+                                   variant, st()))
+    torch.cuda.synchronize()
+    return dw
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def max_abs(a, b):
+    return (a.detach().double().cpu() - b.detach().double().cpu()).abs().max().item()

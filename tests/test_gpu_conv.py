@@ -1,0 +1,133 @@
+"""-m gpu: the tcgen05 implicit-GEMM kernels (conv fwd / dgrad / wgrad) against the CPU fp32 oracle ops."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tracknetv3_b200 import _lib
+from tests import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+
+TOL = {3: 2e-5, 1: 4e-3}  # relative to the output max-abs: 3-term split is fp32-faithful, 1-term is TF32-class
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    return (torch.rand(*shape, generator=torch.Generator().manual_seed(seed)) * 2 - 1) * scale
+
+
+@pytest.mark.parametrize("terms", [3, 1])
+@pytest.mark.parametrize("n,h,w,cin,cout", [
+    (1, 16, 16, 32, 64),     # one full tile
+    (2, 16, 24, 64, 64),     # batch, 3 column tiles of 8
+    (1, 20, 40, 64, 128),    # ragged rows (20 = 16 + 4) and columns
+    (1, 8, 8, 128, 256),     # image smaller than a tile, BN = 256
+    (1, 24, 16, 192, 64),    # 6 K chunks
+    (1, 16, 16, 256, 512),   # two N tiles
+    (1, 16, 32, 64, 192),    # BN = 192
+    (1, 16, 16, 96, 384),    # 2 x BN 192
+])
+def test_conv3x3_forward_identity_view(n, h, w, cin, cout, terms):
+    x = _rand(n, cin, h, w, seed=1)
+    wt = _rand(cout, cin, 3, 3, seed=2, scale=0.2)
+    ref = F.conv2d(x, wt, padding=1)
+    xin = G.nhwc(x)
+    view = G.make_view([G.make_src(xin)], n, h, w)
+    out, part = G.conv3x3(view, wt.to(G.DEV), cout, terms=terms, stats=True)
+    assert G.rel_err(G.nchw(out), ref) < TOL[terms]
+    # BatchNorm partials emitted by the epilogue: per-channel sum and sum of squares of the OUTPUT
+    s = part.sum(0).cpu()
+    assert torch.allclose(s[0], ref.sum((0, 2, 3)), rtol=1e-3, atol=2e-2 * ref.abs().max().item())
+    assert torch.allclose(s[1], (ref * ref).sum((0, 2, 3)), rtol=2e-3 if terms == 3 else 2e-2)
+
+
+def test_conv3x3_first_layer_padding_27_channels():
+    """Reference layer 1 has 27 input channels (seq_len 8, bg concat): padded to 32 with zero weights."""
+    L = G.lib()
+    x = torch.rand(2, 27, 16, 16, generator=torch.Generator().manual_seed(3))
+    wt = _rand(64, 27, 3, 3, seed=4, scale=0.2)
+    xin = torch.empty(2, 16, 16, 32, device=G.DEV)
+    xg = x.to(G.DEV)
+    _lib.check(L.tnb_pack_nchw_to_nhwc(xg.data_ptr(), xin.data_ptr(), 2, 27, 16, 16, 32, G.st()))
+    assert torch.equal(xin[..., :27].cpu(), x.permute(0, 2, 3, 1)) and xin[..., 27:].abs().max() == 0
+    out, _ = G.conv3x3(G.make_view([G.make_src(xin)], 2, 16, 16), wt.to(G.DEV), 64)
+    assert G.rel_err(G.nchw(out), F.conv2d(x, wt, padding=1)) < TOL[3]
+
+
+@pytest.mark.parametrize("mode", ["affine_relu", "pool", "up_concat"])
+def test_conv3x3_fused_views(mode):
+    """BatchNorm-apply + ReLU (+ MaxPool | Upsample + cat) fused into the operand load (model.py:14-15,59-69)."""
+    n, h, w = 1, 16, 24
+    gen = torch.Generator().manual_seed(5)
+    if mode == "up_concat":
+        z0 = _rand(n, 64, h // 2, w // 2, seed=6); z1 = _rand(n, 32, h, w, seed=7)
+        sc0, sh0 = torch.rand(64, generator=gen) + 0.5, _rand(64, seed=8, scale=0.3)
+        sc1, sh1 = -(torch.rand(32, generator=gen) + 0.5), _rand(32, seed=9, scale=0.3)  # negative scale too
+        a0 = F.relu(z0 * sc0[None, :, None, None] + sh0[None, :, None, None])
+        a1 = F.relu(z1 * sc1[None, :, None, None] + sh1[None, :, None, None])
+        xin = torch.cat([F.interpolate(a0, scale_factor=2, mode="nearest"), a1], 1)
+        t0, t1 = G.nhwc(z0), G.nhwc(z1)
+        srcs = [G.make_src(t0, _lib.SRC_AFFINE_RELU_UP, sc0.to(G.DEV), sh0.to(G.DEV)),
+                G.make_src(t1, _lib.SRC_AFFINE_RELU, sc1.to(G.DEV), sh1.to(G.DEV))]
+        keep = (t0, t1)
+    else:
+        hs, ws = (2 * h, 2 * w) if mode == "pool" else (h, w)
+        z0 = _rand(n, 64, hs, ws, seed=6)
+        sc0 = torch.where(torch.arange(64) % 3 == 0, -1.0, 1.0) * (torch.rand(64, generator=gen) + 0.5)
+        sh0 = _rand(64, seed=8, scale=0.3)
+        a0 = F.relu(z0 * sc0[None, :, None, None] + sh0[None, :, None, None])
+        xin = F.max_pool2d(a0, 2, 2) if mode == "pool" else a0
+        t0 = G.nhwc(z0)
+        srcs = [G.make_src(t0, _lib.SRC_AFFINE_RELU_POOL if mode == "pool" else _lib.SRC_AFFINE_RELU,
+                           sc0.to(G.DEV), sh0.to(G.DEV))]
+        keep = (t0,)
+    wt = _rand(64, xin.shape[1], 3, 3, seed=10, scale=0.2)
+    out, _ = G.conv3x3(G.make_view(srcs, n, h, w), wt.to(G.DEV), 64)
+    assert G.rel_err(G.nchw(out), F.conv2d(xin, wt, padding=1)) < TOL[3]
+    del keep
+
+
+@pytest.mark.parametrize("terms", [3, 1])
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 16, 16, 64, 64), (2, 20, 24, 192, 64), (1, 16, 16, 128, 256)])
+def test_conv3x3_dgrad(n, h, w, cin, cout, terms):
+    """dIn = conv(dz, rot180(W)^T) through the same kernel with mode-1 packed bf16 weights."""
+    dz = _rand(n, cout, h, w, seed=11, scale=1e-6)  # realistic tiny gradients: bf16 has fp32's range
+    wt = _rand(cout, cin, 3, 3, seed=12, scale=0.2)
+    ref = F.conv_transpose2d(dz, wt, padding=1)
+    t = G.nhwc(dz)
+    out, _ = G.conv3x3(G.make_view([G.make_src(t)], n, h, w), wt.to(G.DEV), cin, terms=terms, fmt=1, mode=1)
+    assert G.rel_err(G.nchw(out), ref) < (1e-4 if terms == 3 else 2e-2)
+
+
+@pytest.mark.parametrize("terms", [3, 1])
+@pytest.mark.parametrize("n,h,w,cin,cin_real,cout", [
+    (1, 8, 16, 32, 27, 64),      # first layer: 27 real channels, one K tile
+    (2, 16, 32, 64, 64, 64),     # Cout 64 (half of the 128 accumulator rows unused)
+    (1, 20, 24, 64, 64, 128),    # ragged tiles
+    (1, 16, 16, 192, 192, 64),   # NT = 48
+    (1, 8, 16, 128, 128, 256),   # two co tiles
+])
+def test_conv3x3_wgrad(n, h, w, cin, cin_real, cout, terms):
+    x = _rand(n, cin, h, w, seed=13)
+    x[:, cin_real:] = 0
+    dz = _rand(n, cout, h, w, seed=14, scale=1e-5)
+    xr = x[:, :cin_real].clone().requires_grad_(False)
+    wt = torch.zeros(cout, cin_real, 3, 3, requires_grad=True)
+    (F.conv2d(xr, wt, padding=1) * dz).sum().backward()
+    t, d = G.nhwc(x), G.nhwc(dz)
+    dw = G.wgrad3x3(G.make_view([G.make_src(t)], n, h, w), d, cout, cin_real, terms=terms)
+    assert G.rel_err(dw, wt.grad) < (1e-4 if terms == 3 else 2e-2)
+
+
+def test_conv3x3_full_resolution_layer_vs_torch_cuda():
+    """down_block_1.conv_2 shape at the reference resolution (64->64 @ 288x512), checked on-device against
+    torch's fp32 convolution (TF32 disabled) - the oracle op, just executed on the GPU for speed."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x = _rand(1, 64, 288, 512, seed=15).to(G.DEV)
+    wt = _rand(64, 64, 3, 3, seed=16, scale=0.1).to(G.DEV)
+    ref = F.conv2d(x, wt, padding=1)
+    t = x.permute(0, 2, 3, 1).contiguous()
+    out, part = G.conv3x3(G.make_view([G.make_src(t)], 1, 288, 512), wt, 64, stats=True)
+    assert G.rel_err(G.nchw(out), ref) < 2e-5
+    assert torch.allclose(part.sum(0)[0], ref.sum((0, 2, 3)), rtol=1e-3, atol=1.0)

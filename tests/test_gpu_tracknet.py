@@ -1,0 +1,142 @@
+"""-m gpu: TrackNet forward / backward through the reference's module interface against the oracle and
+the fixtures produced by the real reference. Tolerances: heatmap max-abs <= 1e-3 (north_star), met with
+large margin by the default fp32x3 mode; integer decode bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import tracknetv3_b200 as T
+from oracle import decode_oracle as D
+from oracle import tracknet_oracle as O
+from tests import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+HEAT_TOL = 1e-3  # BASELINE.json north_star: heatmap max-abs vs the reference's fp32 path
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def _model(seed, in_dim, out_dim, precision="fp32x3"):
+    torch.manual_seed(seed)
+    return T.TrackNet(in_dim, out_dim, precision=precision).to(G.DEV)
+
+
+def test_small_forward_train_and_eval_vs_oracle():
+    m = _model(1, 12, 4)
+    sd = O.init_tracknet_state(1, 12, 4)
+    x = torch.rand(2, 12, 32, 48, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        m.train(); y_t = m(x.to(G.DEV))
+        m.eval(); y_e = m(x.to(G.DEV))
+        r_t = O.tracknet_forward(sd, x, True)
+        r_e = O.tracknet_forward(sd, x, False)
+    assert G.max_abs(y_t, r_t) < 1e-4 and G.max_abs(y_e, r_e) < 1e-4
+    msd = m.state_dict()
+    for k in ("down_block_1.conv_1.bn.running_mean", "bottleneck.conv_3.bn.running_var",
+              "up_block_3.conv_2.bn.running_var"):
+        assert G.max_abs(msd[k], sd[k]) < 1e-4, k
+    assert int(msd["up_block_2.conv_1.bn.num_batches_tracked"]) == 1
+
+
+def test_train_step_vs_reference_fixture(golden_dir):
+    """fwd + WBCE + backward on the reference's own numbers (tests/golden/tracknet_step.npz)."""
+    g = _load(golden_dir, "tracknet_step.npz")
+    m = _model(int(g["seed"]), 27, 8)
+    m.train()
+    x, y = torch.from_numpy(g["x"]).to(G.DEV), torch.from_numpy(g["y"]).to(G.DEV)
+    y_pred = m(x)
+    loss = T.WBCELoss(y_pred, y)
+    loss.backward()
+    assert np.abs(y_pred.detach().cpu().numpy() - g["y_pred"]).max() < 1e-4
+    assert abs(loss.item() - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    named = dict(m.named_parameters())
+    for k, ref in (("down_block_1.conv_1.conv.weight", "grad_first"), ("up_block_3.conv_2.conv.weight", "grad_last"),
+                   ("predictor.weight", "grad_pred_w"), ("predictor.bias", "grad_pred_b"),
+                   ("up_block_1.conv_1.bn.weight", "grad_bn_w")):
+        assert G.rel_err(named[k].grad, torch.from_numpy(g[ref])) < 2e-3, k
+    names = [str(n) for n in g["grad_names"]]
+    assert names == list(named.keys())
+    for i, k in enumerate(names):  # all 53 gradients through their statistics
+        gs = g["grad_stats"][i]
+        mine = named[k].grad.double().flatten().cpu()
+        assert abs(mine.abs().sum().item() - gs[1]) <= 5e-3 * gs[1] + 1e-12, k
+        idx = torch.linspace(0, mine.numel() - 1, 16).long()
+        assert np.abs(mine[idx].numpy() - gs[3:]).max() <= 5e-3 * gs[2] + 1e-12, k
+    sd = m.state_dict()
+    assert np.abs(sd["down_block_1.conv_1.bn.running_mean"].cpu().numpy() - g["running_mean_first"]).max() < 1e-5
+    assert np.abs(sd["up_block_3.conv_2.bn.running_var"].cpu().numpy() - g["running_var_last"]).max() < 1e-4
+
+
+def test_c1_full_size_heatmap_parity_vs_reference_fixture(golden_dir):
+    """BASELINE.json configs[0]: 288x512, seq_len 4, bs 1 - heatmap max-abs <= 1e-3, train and eval BN."""
+    g = _load(golden_dir, "tracknet_c1.npz")
+    seed = int(g["seed"])
+    torch.manual_seed(seed)
+    m = T.TrackNet(12, 4).to(G.DEV)     # consumes the default generator exactly like the reference module
+    x = torch.rand(tuple(g["shape"]))
+    assert x[0, 3, 17, 99].item() == g["x_checksum"][1]
+    with torch.no_grad():
+        m.train(); y_t = m(x.to(G.DEV))
+        m.eval(); y_e = m(x.to(G.DEV))
+    e_t, e_e = G.max_abs(y_t, torch.from_numpy(g["y_train"])), G.max_abs(y_e, torch.from_numpy(g["y_eval"]))
+    print(f"C1 heatmap max-abs error: train {e_t:.3e} eval {e_e:.3e}")
+    assert e_t < HEAT_TOL and e_e < HEAT_TOL
+    # integer peak coordinates: decode of our heatmaps == OpenCV-rule decode of the reference heatmaps wherever
+    # the reference heatmap is not within 2e-3 of the 0.5 threshold (a 1e-3 deviation may flip such pixels)
+    ours = T.decode_heatmaps(y_e).cpu().numpy()[0]
+    for f in range(4):
+        ref_map = g["y_eval"][0, f]
+        if np.abs(ref_map - 0.5).min() > 2e-3:
+            assert tuple(ours[f]) == tuple(D.predict_location(D.to_img(ref_map > 0.5)))
+
+
+def test_tf32like_mode_is_close_but_not_fp32():
+    m3, m1 = _model(3, 12, 4), _model(3, 12, 4, precision="tf32like")
+    x = torch.rand(1, 12, 64, 96, generator=torch.Generator().manual_seed(4)).to(G.DEV)
+    with torch.no_grad():
+        m3.eval(); m1.eval()
+        for mm in (m3, m1):  # give BN non-trivial statistics
+            for b in mm._blocks():
+                b.bn.running_var.fill_(0.05)
+        a, b = m3(x), m1(x)
+    assert 1e-7 < G.max_abs(a, b) < 5e-2
+
+
+def test_errors_mirror_reference():
+    m = _model(5, 12, 4)
+    with pytest.raises(RuntimeError, match="divisible by 8"):
+        m(torch.zeros(1, 12, 36, 64, device=G.DEV))     # reference: torch.cat size mismatch RuntimeError
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 11, 32, 64, device=G.DEV))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 12, 32, 64))
+
+
+def test_c2_shape_train_step_vs_oracle_on_device():
+    """seq_len 8, bg concat at the reference resolution (bs 2 for the checker's sake): full fwd+bwd against the
+    oracle executed in fp32 on the same GPU (TF32 off). Size-independent properties: loss and every gradient."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = _model(13, 27, 8)
+    sd = {k: v.to(G.DEV) for k, v in O.init_tracknet_state(13, 27, 8).items()}
+    gen = torch.Generator().manual_seed(14)
+    x = torch.rand(2, 27, 288, 512, generator=gen)
+    y = torch.zeros(2, 8, 288, 512)
+    for n in range(2):
+        for f in range(8):
+            cx, cy = int(torch.randint(0, 512, (1,), generator=gen)), int(torch.randint(0, 288, (1,), generator=gen))
+            y[n, f] = torch.from_numpy(O.label_disc(cx, cy)) if f != 3 else 0
+    x, y = x.to(G.DEV), y.to(G.DEV)
+    m.train()
+    y_pred = m(x)
+    loss = T.WBCELoss(y_pred, y)
+    loss.backward()
+    r_pred, r_loss, r_grads = O.tracknet_loss_and_grads(sd, x, y, True)
+    assert G.max_abs(y_pred, r_pred) < HEAT_TOL
+    assert abs(loss.item() - r_loss.item()) < 1e-4 * abs(r_loss.item())
+    for k, p in m.named_parameters():
+        assert G.rel_err(p.grad, r_grads[k]) < 5e-3, k
