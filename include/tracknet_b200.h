@@ -168,6 +168,14 @@ int tnb_tracknet_backward(const tnb_tracknet_cfg_t* cfg, const float* dy_nchw, c
 /* number of kernels launched by one forward / backward call (for bench.py's gpu_launches) */
 int tnb_tracknet_num_launches(const tnb_tracknet_cfg_t* cfg, int backward);
 
+/* ---- measurement support (bench.py roofline leg) -------------------------------------------- */
+/* Per-launch CUDA-event timing of the tensor-core and BN-backward kernels, recorded on the launching
+ * stream. enable(1) clears and starts recording, enable(0) stops. collect() synchronises and returns the
+ * number of records: desc[6*i..] = {kind (0 conv fwd, 1 dgrad, 2 wgrad, 3 bn_bwd, 4 predictor), n, h, w,
+ * cin, cout}, ms[i] = device duration of that launch. */
+int tnb_profile_enable(int on);
+int tnb_profile_collect(int max_records, int* desc, float* ms);
+
 #ifdef __cplusplus
 }
 #endif

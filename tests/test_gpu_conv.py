@@ -59,6 +59,12 @@ def test_conv3x3_fused_views(mode):
     """BatchNorm-apply + ReLU (+ MaxPool | Upsample + cat) fused into the operand load (model.py:14-15,59-69)."""
     n, h, w = 1, 16, 24
     gen = torch.Generator().manual_seed(5)
+    keep = []  # every device tensor whose raw pointer sits in a descriptor must outlive the launch
+
+    def dev(t):
+        keep.append(t.contiguous().to(G.DEV))
+        return keep[-1]
+
     if mode == "up_concat":
         z0 = _rand(n, 64, h // 2, w // 2, seed=6); z1 = _rand(n, 32, h, w, seed=7)
         sc0, sh0 = torch.rand(64, generator=gen) + 0.5, _rand(64, seed=8, scale=0.3)
@@ -66,10 +72,8 @@ def test_conv3x3_fused_views(mode):
         a0 = F.relu(z0 * sc0[None, :, None, None] + sh0[None, :, None, None])
         a1 = F.relu(z1 * sc1[None, :, None, None] + sh1[None, :, None, None])
         xin = torch.cat([F.interpolate(a0, scale_factor=2, mode="nearest"), a1], 1)
-        t0, t1 = G.nhwc(z0), G.nhwc(z1)
-        srcs = [G.make_src(t0, _lib.SRC_AFFINE_RELU_UP, sc0.to(G.DEV), sh0.to(G.DEV)),
-                G.make_src(t1, _lib.SRC_AFFINE_RELU, sc1.to(G.DEV), sh1.to(G.DEV))]
-        keep = (t0, t1)
+        srcs = [G.make_src(dev(z0.permute(0, 2, 3, 1)), _lib.SRC_AFFINE_RELU_UP, dev(sc0), dev(sh0)),
+                G.make_src(dev(z1.permute(0, 2, 3, 1)), _lib.SRC_AFFINE_RELU, dev(sc1), dev(sh1))]
     else:
         hs, ws = (2 * h, 2 * w) if mode == "pool" else (h, w)
         z0 = _rand(n, 64, hs, ws, seed=6)
@@ -77,13 +81,17 @@ def test_conv3x3_fused_views(mode):
         sh0 = _rand(64, seed=8, scale=0.3)
         a0 = F.relu(z0 * sc0[None, :, None, None] + sh0[None, :, None, None])
         xin = F.max_pool2d(a0, 2, 2) if mode == "pool" else a0
-        t0 = G.nhwc(z0)
-        srcs = [G.make_src(t0, _lib.SRC_AFFINE_RELU_POOL if mode == "pool" else _lib.SRC_AFFINE_RELU,
-                           sc0.to(G.DEV), sh0.to(G.DEV))]
-        keep = (t0,)
+        srcs = [G.make_src(dev(z0.permute(0, 2, 3, 1)),
+                           _lib.SRC_AFFINE_RELU_POOL if mode == "pool" else _lib.SRC_AFFINE_RELU, dev(sc0), dev(sh0))]
     wt = _rand(64, xin.shape[1], 3, 3, seed=10, scale=0.2)
-    out, _ = G.conv3x3(G.make_view(srcs, n, h, w), wt.to(G.DEV), 64)
+    out, _ = G.conv3x3(G.make_view(srcs, n, h, w), dev(wt), 64)
     assert G.rel_err(G.nchw(out), F.conv2d(xin, wt, padding=1)) < TOL[3]
+    # the same fused view as the wgrad B operand
+    dz = _rand(n, 64, h, w, seed=17, scale=1e-5)
+    wz = torch.zeros(64, xin.shape[1], 3, 3, requires_grad=True)
+    (F.conv2d(xin, wz, padding=1) * dz).sum().backward()
+    dw = G.wgrad3x3(G.make_view(srcs, n, h, w), dev(dz.permute(0, 2, 3, 1)), 64, xin.shape[1])
+    assert G.rel_err(dw, wz.grad) < 1e-4
     del keep
 
 

@@ -58,8 +58,8 @@ def probe_wgrad(variant, terms=3):
     wt = torch.zeros(cout, cin, 3, 3, requires_grad=True)
     (F.conv2d(xr, wt, padding=1) * dz).sum().backward()
     ref = wt.grad
-    dw = G.wgrad3x3(G.make_view([G.make_src(G.nhwc(x))], n, h, w), G.nhwc(dz), cout, cin, terms=terms,
-                    variant=variant).cpu()
+    tx, tz = G.nhwc(x), G.nhwc(dz)  # keep alive: descriptors hold raw pointers
+    dw = G.wgrad3x3(G.make_view([G.make_src(tx)], n, h, w), tz, cout, cin, terms=terms, variant=variant).cpu()
     bad = dw != ref
     print(f"[wgrad variant {variant} terms {terms}] mismatches {int(bad.sum())} / {bad.numel()} "
           f"max_abs {float((dw - ref).abs().nan_to_num(1e30).max()):.4g}")
@@ -71,7 +71,8 @@ def probe_wgrad(variant, terms=3):
     dz = (torch.rand(2, 128, 16, 32) - 0.5) * 1e-4
     wt = torch.zeros(128, 64, 3, 3, requires_grad=True)
     (F.conv2d(x, wt, padding=1) * dz).sum().backward()
-    dw = G.wgrad3x3(G.make_view([G.make_src(G.nhwc(x))], 2, 16, 32), G.nhwc(dz), 128, 64, terms=terms, variant=variant)
+    tx, tz = G.nhwc(x), G.nhwc(dz)
+    dw = G.wgrad3x3(G.make_view([G.make_src(tx)], 2, 16, 32), tz, 128, 64, terms=terms, variant=variant)
     print(f"   random 64->128 16x32 rel err {G.rel_err(dw, wt.grad):.3e}")
 
 

@@ -21,6 +21,7 @@
 //   * Weight tiles are pre-packed into the exact smem image and staged with 1-D bulk TMA
 //     (cp.async.bulk + mbarrier complete_tx).
 #include "igemm.cuh"
+#include "prof.cuh"
 #include <stdio.h>
 
 namespace tnb {
@@ -406,6 +407,7 @@ int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, floa
   dim3 grid(view.N * p.tiles_h * p.tiles_w, Cout / p.BN);
   auto kern = fmt == 0 ? conv3x3_kernel<0> : conv3x3_kernel<1>;
   TNB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+  ProfScope prof(fmt == 0 ? PROF_CONV_FWD : PROF_CONV_DGRAD, st, view.N, view.H, view.W, view.C, Cout);
   kern<<<grid, kThreads, p.smem_bytes, st>>>(a);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -620,6 +622,7 @@ int launch_wgrad3x3(const ViewDesc& view, const float* dz, float* dw, int Cout, 
   const size_t smem = kHdrBytes + 2 * (size_t)(TP * 16 * pad_px(128) * 16 + TP * (a.NT / 8) * pad_px(kWgHaloPx) * 16);
   auto kern = fmt == 0 ? wgrad3x3_kernel<0> : wgrad3x3_kernel<1>;
   TNB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope prof(PROF_WGRAD, st, view.N, view.H, view.W, view.C, Cout);
   kern<<<dim3(gx, splits), kThreads, smem, st>>>(a);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;

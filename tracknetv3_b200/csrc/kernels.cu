@@ -1,6 +1,7 @@
 // HBM-bound sm_100a kernels of the TrackNet / InpaintNet hot path. Each cites the reference lines it
 // replaces; none of them falls back to a library.
 #include "kernels.cuh"
+#include "prof.cuh"
 #include <limits.h>
 
 namespace tnb {
@@ -130,6 +131,7 @@ int launch_predictor_fwd(const SrcDesc& src, int N, int H, int W, const float* w
                          float* y, cudaStream_t st) {
   TNB_REQUIRE(src.C == 64 && O <= kMaxPredO, "predictor: expects 64 input channels and out_dim <= %d", kMaxPredO);
   const long long npix = (long long)N * H * W;
+  ProfScope prof(PROF_PRED, st, N, H, W, 64, O);
   predictor_fwd_kernel<<<min(cdiv(npix, 256), 148 * 8), 256, 0, st>>>(src, N, H, W, wp, bias, O, y);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -228,6 +230,7 @@ int launch_predictor_bwd(const SrcDesc& src, int N, int H, int W, const float* w
   const long long npix = (long long)N * H * W;
   TNB_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * O * 64, st));
   TNB_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * O, st));
+  ProfScope prof(PROF_PRED, st, N, H, W, 64, O);
   predictor_bwd_kernel<<<min(cdiv(npix, 64), 148 * 4), 256, 0, st>>>(src, N, H, W, wp, O, dy, y, dA, dwp, dbias);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -371,12 +374,14 @@ static int bn_bwd_check(const BnBwdArgs& a) {
 }
 int launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t st) {
   if (int rc = bn_bwd_check(a)) return rc;
+  ProfScope prof(PROF_BN_BWD, st, a.N, a.H, a.W, a.C, a.C);
   bn_bwd_kernel<false><<<bn_bwd_num_blocks(a.N, a.H, a.W, a.C), 256, 0, st>>>(a);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st) {
   if (int rc = bn_bwd_check(a)) return rc;
+  ProfScope prof(PROF_BN_BWD, st, a.N, a.H, a.W, a.C, a.C);
   bn_bwd_kernel<true><<<bn_bwd_num_blocks(a.N, a.H, a.W, a.C), 256, 0, st>>>(a);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
