@@ -105,8 +105,9 @@ def cpu_reference_step_rate(steps, warmup, batch=1):
     `batch` samples of the same 288x512 seq_len-8 workload per step. Returns (frames/s, ms/step, cores)."""
     import torch
     from oracle import tracknet_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    # torch's default intra-op pool = the physical cores it detects; oversubscribing all SMT siblings of a big
+    # host makes these small convolutions slower, so the default is "all the threads torch will use"
+    cores = torch.get_num_threads()
     sd = O.init_tracknet_state(13, IN_DIM, OUT_DIM)
     x, y = synthetic_batch(batch, 13)
     for _ in range(warmup):

@@ -32,7 +32,9 @@ extern "C" {
 enum { TNB_SRC_IDENTITY = 0, TNB_SRC_AFFINE_RELU = 1, TNB_SRC_AFFINE_RELU_POOL = 2, TNB_SRC_AFFINE_RELU_UP = 3 };
 typedef struct {
   const float* ptr;   /* [N, Hs, Ws, C] fp32 NHWC */
-  const float* scale; /* [C] fused BatchNorm scale (gamma * invstd), NULL for IDENTITY */
+  const float* scale; /* [C] fused BatchNorm scale (gamma * invstd). IDENTITY: NULL, or a pointer to ONE float =
+                         max|tensor| -> the kernel pre-scales by a power of two before its fp16 hi/lo split and
+                         un-scales the result (used for gradients, whose magnitude is ~1e-8) */
   const float* shift; /* [C] fused BatchNorm shift (beta - mean * scale) */
   int C, Hs, Ws, mode;
 } tnb_src_t;
@@ -61,6 +63,7 @@ typedef struct {
   const float* sums; /* apply:  [2][C] */
   float* dz;         /* apply:  [N,H,W,C] */
   float inv_count;
+  float* amax;       /* apply, optional: device scalar, atomically raised to max|dz| (zero it first) */
 } tnb_bnbwd_t;
 
 typedef struct {
@@ -69,7 +72,7 @@ typedef struct {
   int out_dim;
   int training;    /* 1: BatchNorm uses batch statistics and updates running stats (model.train()) */
   int fwd_terms;   /* 3 = fp16 hi/lo split, fp32-faithful (default); 1 = single fp16 pass (TF32-class) */
-  int bwd_terms;   /* 3 = bf16 hi/lo split (default); 1 = single bf16 pass */
+  int bwd_terms;   /* 3 = fp16 hi/lo split of power-of-two pre-scaled gradients (default); 1 = single pass */
   int variant;     /* bring-up probe bits; 0 in production */
   float bn_eps;    /* 1e-5 */
   float bn_momentum; /* 0.1 */
@@ -100,9 +103,10 @@ int tnb_conv3x3_fwd(const tnb_view_t* view, const uint16_t* wpack, float* out, f
                     int terms, int fmt, int variant, void* stream);
 
 /* Weight gradient of the same convolution (autograd of model.py:13 via train.py:95):
- * dw[cout][cin_real][3][3] += sum dz * view. dw must be zeroed by the caller. */
-int tnb_conv3x3_wgrad(const tnb_view_t* view, const float* dz, float* dw_oihw, int cout, int cin_real, int terms,
-                      int fmt, int variant, void* stream);
+ * dw[cout][cin_real][3][3] += sum dz * view. dw must be zeroed by the caller. dz_amax: optional device scalar
+ * max|dz| enabling power-of-two pre-scaling (see tnb_src_t.scale). */
+int tnb_conv3x3_wgrad(const tnb_view_t* view, const float* dz, const float* dz_amax, float* dw_oihw, int cout,
+                      int cin_real, int terms, int fmt, int variant, void* stream);
 
 /* BatchNorm2d statistics -> fused affine + running-stat update (model.py:9; torch defaults eps 1e-5,
  * momentum 0.1, unbiased running_var). training==0 uses the running statistics (model.eval()). */

@@ -67,11 +67,13 @@ def conv3x3(view, w_oihw, cout, terms=3, fmt=0, variant=0, stats=False, mode=0):
     return out, part
 
 
-def wgrad3x3(view, dz_nhwc, cout, cin_real, terms=3, fmt=1, variant=0):
+def wgrad3x3(view, dz_nhwc, cout, cin_real, terms=3, fmt=0, variant=0, scaled=True):
+    """fmt 0 + scaled: the production configuration (fp16 split of power-of-two pre-scaled dz)."""
     L = lib()
     dw = torch.zeros((cout, cin_real, 3, 3), device=DEV)
-    _lib.check(L.tnb_conv3x3_wgrad(C.byref(view), dz_nhwc.data_ptr(), dw.data_ptr(), cout, cin_real, terms, fmt,
-                                   variant, st()))
+    amax = dz_nhwc.abs().max().reshape(1).contiguous() if scaled else None
+    _lib.check(L.tnb_conv3x3_wgrad(C.byref(view), dz_nhwc.data_ptr(), amax.data_ptr() if scaled else None,
+                                   dw.data_ptr(), cout, cin_real, terms, fmt, variant, st()))
     torch.cuda.synchronize()
     return dw
 

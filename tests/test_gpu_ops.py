@@ -206,11 +206,14 @@ def test_bn_relu_backward_with_gradient_routing(consumers):
     args.N, args.H, args.W, args.C = n, h, w, c
     args.part, args.sums, args.dz = part.data_ptr(), sums.data_ptr(), dz.data_ptr()
     args.inv_count = 1.0 / (n * h * w)
+    amax = torch.zeros(1, device=G.DEV)
+    args.amax = amax.data_ptr()
     _lib.check(L.tnb_bn_relu_bwd_reduce(C.byref(args), G.st()))
     _lib.check(L.tnb_bn_relu_bwd_finalize(part.data_ptr(), rows, c, sums.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), G.st()))
     _lib.check(L.tnb_bn_relu_bwd_apply(C.byref(args), G.st()))
     torch.cuda.synchronize()
     assert G.rel_err(G.nchw(dz), z.grad) < 2e-4
+    assert amax.item() == dz.abs().max().item()  # feeds the power-of-two pre-scaling of dgrad / wgrad
     # d gamma / d beta from the same reductions (checked through a second autograd pass)
     z2 = z.detach().clone(); g2 = gamma.clone().requires_grad_(True); b2 = beta.clone().requires_grad_(True)
     a2 = F.relu(F.batch_norm(z2, None, None, g2, b2, True, 0.1, 1e-5))

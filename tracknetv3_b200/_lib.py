@@ -32,7 +32,8 @@ class BnBwd(C.Structure):  # tnb_bnbwd_t
     _fields_ = [("g", GradSrc * 2), ("ng", C.c_int), ("z", C.c_void_p),
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
                 ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
-                ("part", C.c_void_p), ("sums", C.c_void_p), ("dz", C.c_void_p), ("inv_count", C.c_float)]
+                ("part", C.c_void_p), ("sums", C.c_void_p), ("dz", C.c_void_p), ("inv_count", C.c_float),
+                ("amax", C.c_void_p)]
 
 
 class TrackNetCfg(C.Structure):  # tnb_tracknet_cfg_t
@@ -55,7 +56,7 @@ SIGNATURES = {
     "tnb_conv3x3_pack_weights": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "tnb_conv3x3_stat_rows": (i32, [i32, i32, i32, i32, i32, i32]),
     "tnb_conv3x3_fwd": (i32, [C.POINTER(View), vp, vp, vp, i32, i32, i32, i32, vp]),
-    "tnb_conv3x3_wgrad": (i32, [C.POINTER(View), vp, vp, i32, i32, i32, i32, i32, vp]),
+    "tnb_conv3x3_wgrad": (i32, [C.POINTER(View), vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "tnb_bn_finalize": (i32, [vp, i32, f64, vp, vp, vp, vp, f32, f32, i32, vp, vp, vp, vp, i32, vp]),
     "tnb_bn_bwd_blocks": (i32, [i32, i32, i32, i32]),
     "tnb_bn_relu_bwd_reduce": (i32, [C.POINTER(BnBwd), vp]),

@@ -45,9 +45,9 @@ int tnb_conv3x3_fwd(const tnb_view_t* view, const uint16_t* wpack, float* out, f
                     int fmt, int variant, void* stream) {
   return launch_conv3x3(*view, wpack, out, stat_part, cout, terms, fmt, variant, ST(stream));
 }
-int tnb_conv3x3_wgrad(const tnb_view_t* view, const float* dz, float* dw, int cout, int cin_real, int terms, int fmt,
-                      int variant, void* stream) {
-  return launch_wgrad3x3(*view, dz, dw, cout, cin_real, terms, fmt, variant, ST(stream));
+int tnb_conv3x3_wgrad(const tnb_view_t* view, const float* dz, const float* dz_amax, float* dw, int cout,
+                      int cin_real, int terms, int fmt, int variant, void* stream) {
+  return launch_wgrad3x3(*view, dz, dz_amax, dw, cout, cin_real, terms, fmt, variant, ST(stream));
 }
 int tnb_bn_finalize(const float* part, int rows, double count, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, float momentum, float eps, int training, float* scale,

@@ -23,6 +23,7 @@
 #include "igemm.cuh"
 #include "prof.cuh"
 #include <stdio.h>
+#include <type_traits>
 
 namespace tnb {
 
@@ -197,6 +198,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // dgrad: dz is multiplied by a power of two on the way in (so that its fp16 hi/lo split keeps ~22 bits) and
+  // the accumulator by the inverse on the way out; forward views use BN scale/shift instead (in_mul = 1).
+  const float in_mul = (V.s[0].mode == SRC_IDENTITY) ? pow2_scale_for(V.s[0].scale) : 1.f;
+  const float out_mul = 1.f / in_mul;
 
   if (warp == 0) {
     // =========================== MMA issuer (single elected thread) ===========================
@@ -263,27 +268,57 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
   } else {
     // =========================== A producers: gather + BN/ReLU/pool/upsample + split ===========
     const int ftid = tid - 64;
+    const int j = ftid & 3;            // plane (8 channels) this thread fills: fixed, 256 % 4 == 0
+    const int pbase = ftid >> 2;       // first halo pixel; stride 64 pixels
     for (int c = 0; c < nchunks; ++c) {
       const int sa = c % a.SA;
       const uint32_t pha = (c / a.SA) & 1;
+      const int cch = c * 32 + j * 8;
+      const bool second = cch >= V.C0;
+      const SrcDesc& S = second ? V.s[1] : V.s[0];
+      const int cc = second ? cch - V.C0 : cch;
+      float sc[8], sh[8];
+      if (S.mode != SRC_IDENTITY) { ld8(S.scale + cc, sc); ld8(S.shift + cc, sh); }
       mbar_wait(&empty_A[sa], pha ^ 1);
-      uint8_t* stage = a_base + sa * A_STAGE;
-      for (int item = ftid; item < HALO_PX * 4; item += kFillThreads) {
-        const int p = item >> 2, j = item & 3;
-        const int cch = c * 32 + j * 8;
-        const int2 e = table[p];
-        const bool second = cch >= V.C0;
-        const int off = second ? e.y : e.x;
-        uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-        if (off >= 0) {
-          float v[8];
-          if (second) view_load8(V.s[1], off, cch - V.C0, v);
-          else        view_load8(V.s[0], off, cch, v);
-          split8<FMT>(v, hi, lo);
+      uint8_t* stage = a_base + sa * A_STAGE + j * PLANE;
+      auto run = [&](auto mode_tag, auto batch_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;
+        constexpr int U = decltype(batch_tag)::value;
+        for (int p0 = pbase; p0 < HALO_PX; p0 += 64 * U) {
+          Raw8 raw[U][RawCount<MODE>::value];
+          int off[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int p = p0 + 64 * u;
+            off[u] = -1;
+            if (p < HALO_PX) {
+              const int2 e = table[p];
+              off[u] = second ? e.y : e.x;
+              if (off[u] >= 0) view_issue<MODE>(S, off[u], cc, raw[u]);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int p = p0 + 64 * u;
+            if (p < HALO_PX) {
+              uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+              if (off[u] >= 0) {
+                float v[8];
+                view_finish<MODE>(raw[u], sc, sh, in_mul, v);
+                split8<FMT>(v, hi, lo);
+              }
+              uint8_t* dst = stage + p * 16;
+              *reinterpret_cast<uint4*>(dst) = hi;
+              if (a.nterms > 1) *reinterpret_cast<uint4*>(dst + 4 * PLANE) = lo;
+            }
+          }
         }
-        uint8_t* dst = stage + j * PLANE + p * 16;
-        *reinterpret_cast<uint4*>(dst) = hi;
-        if (a.nterms > 1) *reinterpret_cast<uint4*>(dst + 4 * PLANE) = lo;
+      };
+      switch (S.mode) {
+        case SRC_IDENTITY: run(std::integral_constant<int, SRC_IDENTITY>{}, std::integral_constant<int, 4>{}); break;
+        case SRC_AFFINE_RELU_POOL: run(std::integral_constant<int, SRC_AFFINE_RELU_POOL>{}, std::integral_constant<int, 2>{}); break;
+        case SRC_AFFINE_RELU_UP: run(std::integral_constant<int, SRC_AFFINE_RELU_UP>{}, std::integral_constant<int, 4>{}); break;
+        default: run(std::integral_constant<int, SRC_AFFINE_RELU>{}, std::integral_constant<int, 4>{}); break;
       }
       fence_proxy_async_smem();
       mbar_arrive(&full_A[sa]);
@@ -307,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
           tmem_ld_wait();
           float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rg[i]);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rg[i]) * out_mul;
           if (valid) {
             float4* dst = reinterpret_cast<float4*>(a.out + ((size_t)(n * V.H + h) * V.W + w) * a.Cout + n0 + col0);
 #pragma unroll
@@ -407,7 +442,7 @@ int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, floa
   dim3 grid(view.N * p.tiles_h * p.tiles_w, Cout / p.BN);
   auto kern = fmt == 0 ? conv3x3_kernel<0> : conv3x3_kernel<1>;
   TNB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-  ProfScope prof(fmt == 0 ? PROF_CONV_FWD : PROF_CONV_DGRAD, st, view.N, view.H, view.W, view.C, Cout);
+  ProfScope prof((view.s[0].mode == SRC_IDENTITY && view.s[0].scale != nullptr) ? PROF_CONV_DGRAD : PROF_CONV_FWD, st, view.N, view.H, view.W, view.C, Cout);
   kern<<<grid, kThreads, p.smem_bytes, st>>>(a);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -420,8 +455,9 @@ int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, floa
 // =============================================================================================
 struct WgradArgs {
   ViewDesc view;
-  const float* dz;  // [N,H,W,Cout]
-  float* dw;        // [Cout][CinReal][3][3], accumulated with atomics (must be zeroed by the caller)
+  const float* dz;       // [N,H,W,Cout]
+  const float* dz_amax;  // optional: max|dz| (device scalar) -> power-of-two pre-scaling for the fp16 split
+  float* dw;             // [Cout][CinReal][3][3], accumulated with atomics (must be zeroed by the caller)
   int Cout, CinReal, NT, nterms, variant;
   int tiles_h, tiles_w, ktiles, ktiles_per_cta, ncot;
 };
@@ -484,6 +520,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const float dz_mul = pow2_scale_for(a.dz_amax);
+  const float out_mul = 1.f / dz_mul;
 
   if (warp == 0) {
     if (elect_one()) {
@@ -527,6 +565,17 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   } else if (warp >= 2) {
     const int ftid = tid - 64;
     const int tiles_per_img = a.tiles_h * a.tiles_w;
+    // dz items: thread owns plane dpl, pixels dpx0 + k*DG;  view items: plane vpl, halo pixels vpx0 + k*VG
+    const int dpl = ftid % npld, dpx0 = ftid / npld, DG = kFillThreads / npld;
+    const int VG = kFillThreads / NPL;
+    const bool vactive = ftid < VG * NPL;
+    const int vpl = ftid % NPL, vpx0 = ftid / NPL;
+    const int vch = ci0 + vpl * 8;
+    const bool vsecond = vch >= V.C0;
+    const SrcDesc& VS = vsecond ? V.s[1] : V.s[0];
+    const int vcc = vsecond ? vch - V.C0 : vch;
+    float sc[8], sh[8];
+    if (VS.mode != SRC_IDENTITY && vactive) { ld8(VS.scale + vcc, sc); ld8(VS.shift + vcc, sh); }
     int it = 0;
     for (int kt = kt0; kt < kt1; ++kt, ++it) {
       const int s = it % S;
@@ -537,36 +586,76 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
       const int th = trem / a.tiles_w, tw = trem - th * a.tiles_w;
       const int h0 = th * kWgTileH, w0 = tw * kWgTileW;
       uint8_t* stage = st_base + s * STAGE;
-      // dz tile: 128 pixels x npld planes
-      for (int item = ftid; item < 128 * npld; item += kFillThreads) {
-        const int px = item / npld, pl = item - px * npld;
-        const int h = h0 + (px >> 4), w = w0 + (px & 15);
-        uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-        if (h < V.H && w < V.W) {
-          float v[8];
-          ld8(a.dz + ((size_t)(n * V.H + h) * V.W + w) * a.Cout + co0 + pl * 8, v);
-          split8<FMT>(v, hi, lo);
+      // ---- dz tile: 128 pixels x npld planes, 4 pixels per batch ----
+      {
+        uint8_t* dstp = stage + dpl * DZPL;
+        for (int px0 = dpx0; px0 < 128; px0 += DG * 4) {
+          Raw8 raw[4];
+          bool ok[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int px = px0 + u * DG;
+            const int h = h0 + (px >> 4), w = w0 + (px & 15);
+            ok[u] = px < 128 && h < V.H && w < V.W;
+            if (ok[u]) raw[u] = ld_raw8(a.dz + ((size_t)(n * V.H + h) * V.W + w) * a.Cout + co0 + dpl * 8);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int px = px0 + u * DG;
+            if (px < 128) {
+              uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+              if (ok[u]) {
+                float v[8];
+                raw_to_arr(raw[u], v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] *= dz_mul;
+                split8<FMT>(v, hi, lo);
+              }
+              *reinterpret_cast<uint4*>(dstp + px * 16) = hi;
+              if (a.nterms > 1) *reinterpret_cast<uint4*>(dstp + px * 16 + 16 * DZPL) = lo;
+            }
+          }
         }
-        uint8_t* dst = stage + pl * DZPL + px * 16;
-        *reinterpret_cast<uint4*>(dst) = hi;
-        if (a.nterms > 1) *reinterpret_cast<uint4*>(dst + 16 * DZPL) = lo;
       }
-      // view halo tile: 180 pixels x NPL planes
-      for (int item = ftid; item < kWgHaloPx * NPL; item += kFillThreads) {
-        const int p = item / NPL, pl = item - p * NPL;
-        const int hr = p / kWgHaloW, hc = p - hr * kWgHaloW;
-        const int h = h0 - 1 + hr, w = w0 - 1 + hc;
-        const int cch = ci0 + pl * 8;
-        uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-        if (h >= 0 && h < V.H && w >= 0 && w < V.W) {
-          float v[8];
-          if (cch >= V.C0) view_load8(V.s[1], view_pix_off(V.s[1], n, h, w), cch - V.C0, v);
-          else             view_load8(V.s[0], view_pix_off(V.s[0], n, h, w), cch, v);
-          split8<FMT>(v, hi, lo);
+      // ---- view halo tile: 180 pixels x NPL planes ----
+      if (vactive) {
+        uint8_t* dstp = stage + DZ_BYTES + vpl * VPL;
+        auto run = [&](auto mode_tag, auto batch_tag) {
+          constexpr int MODE = decltype(mode_tag)::value;
+          constexpr int U = decltype(batch_tag)::value;
+          for (int p0 = vpx0; p0 < kWgHaloPx; p0 += VG * U) {
+            Raw8 raw[U][RawCount<MODE>::value];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int p = p0 + u * VG;
+              const int hr = p / kWgHaloW, hc = p - hr * kWgHaloW;
+              const int h = h0 - 1 + hr, w = w0 - 1 + hc;
+              ok[u] = p < kWgHaloPx && h >= 0 && h < V.H && w >= 0 && w < V.W;
+              if (ok[u]) view_issue<MODE>(VS, view_pix_off(VS, n, h, w), vcc, raw[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int p = p0 + u * VG;
+              if (p < kWgHaloPx) {
+                uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+                if (ok[u]) {
+                  float v[8];
+                  view_finish<MODE>(raw[u], sc, sh, 1.f, v);
+                  split8<FMT>(v, hi, lo);
+                }
+                *reinterpret_cast<uint4*>(dstp + p * 16) = hi;
+                if (a.nterms > 1) *reinterpret_cast<uint4*>(dstp + p * 16 + NPL * VPL) = lo;
+              }
+            }
+          }
+        };
+        switch (VS.mode) {
+          case SRC_IDENTITY: run(std::integral_constant<int, SRC_IDENTITY>{}, std::integral_constant<int, 4>{}); break;
+          case SRC_AFFINE_RELU_POOL: run(std::integral_constant<int, SRC_AFFINE_RELU_POOL>{}, std::integral_constant<int, 2>{}); break;
+          case SRC_AFFINE_RELU_UP: run(std::integral_constant<int, SRC_AFFINE_RELU_UP>{}, std::integral_constant<int, 4>{}); break;
+          default: run(std::integral_constant<int, SRC_AFFINE_RELU>{}, std::integral_constant<int, 4>{}); break;
         }
-        uint8_t* dst = stage + DZ_BYTES + pl * VPL + p * 16;
-        *reinterpret_cast<uint4*>(dst) = hi;
-        if (a.nterms > 1) *reinterpret_cast<uint4*>(dst + NPL * VPL) = lo;
       }
       fence_proxy_async_smem();
       mbar_arrive(&full[s]);
@@ -586,7 +675,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
             for (int j = 0; j < 16; ++j) {
               const int ci = ci0 + col0 + j;
               if (ci < a.CinReal)
-                atomicAdd(a.dw + ((size_t)(co0 + row) * a.CinReal + ci) * 9 + t, __uint_as_float(rg[j]));
+                atomicAdd(a.dw + ((size_t)(co0 + row) * a.CinReal + ci) * 9 + t, __uint_as_float(rg[j]) * out_mul);
             }
           }
         }
@@ -601,11 +690,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   }
 }
 
-int launch_wgrad3x3(const ViewDesc& view, const float* dz, float* dw, int Cout, int CinReal, int nterms, int fmt,
-                    int variant, cudaStream_t st) {
+int launch_wgrad3x3(const ViewDesc& view, const float* dz, const float* dz_amax, float* dw, int Cout, int CinReal,
+                    int nterms, int fmt, int variant, cudaStream_t st) {
   TNB_REQUIRE(view.C % 32 == 0 && Cout % 64 == 0, "wgrad3x3: unsupported channels Cin=%d Cout=%d", view.C, Cout);
   WgradArgs a;
-  a.view = view; a.dz = dz; a.dw = dw; a.Cout = Cout; a.CinReal = CinReal; a.nterms = nterms; a.variant = variant;
+  a.view = view; a.dz = dz; a.dz_amax = dz_amax; a.dw = dw; a.Cout = Cout; a.CinReal = CinReal; a.nterms = nterms; a.variant = variant;
   a.NT = (view.C % 48 == 0) ? 48 : 32;
   a.tiles_h = (view.H + kWgTileH - 1) / kWgTileH;
   a.tiles_w = (view.W + kWgTileW - 1) / kWgTileW;

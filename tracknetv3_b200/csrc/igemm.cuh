@@ -64,6 +64,65 @@ TNB_DEVINL void view_load8(const SrcDesc& s, int poff, int c, float (&v)[8]) {
   }
 }
 
+// ---- batched gather: issue all global loads of a batch first, then convert/store (memory-level parallelism)
+struct Raw8 { float4 a, b; };
+TNB_DEVINL Raw8 ld_raw8(const float* p) {
+  Raw8 r;
+  r.a = __ldg(reinterpret_cast<const float4*>(p));
+  r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  return r;
+}
+TNB_DEVINL void raw_to_arr(const Raw8& r, float (&v)[8]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w;
+  v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+// number of raw 8-float loads one view element needs
+template <int MODE> struct RawCount { static constexpr int value = (MODE == SRC_AFFINE_RELU_POOL) ? 4 : 1; };
+template <int MODE>
+TNB_DEVINL void view_issue(const SrcDesc& s, int poff, int c, Raw8 (&raw)[RawCount<MODE>::value]) {
+  const float* p = s.ptr + (size_t)poff * s.C + c;
+  raw[0] = ld_raw8(p);
+  if (MODE == SRC_AFFINE_RELU_POOL) {
+    raw[1 % RawCount<MODE>::value] = ld_raw8(p + s.C);
+    raw[2 % RawCount<MODE>::value] = ld_raw8(p + (size_t)s.Ws * s.C);
+    raw[3 % RawCount<MODE>::value] = ld_raw8(p + (size_t)s.Ws * s.C + s.C);
+  }
+}
+// finish: BN affine + ReLU (+ max over the 2x2 window); IDENTITY multiplies by `mul` (power-of-two scaling of dz)
+template <int MODE>
+TNB_DEVINL void view_finish(const Raw8 (&raw)[RawCount<MODE>::value], const float (&sc)[8], const float (&sh)[8],
+                            float mul, float (&v)[8]) {
+  float a[8];
+  raw_to_arr(raw[0], a);
+  if (MODE == SRC_IDENTITY) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = a[i] * mul;
+    return;
+  }
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = fmaf(a[i], sc[i], sh[i]);
+  if (MODE == SRC_AFFINE_RELU_POOL) {
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      raw_to_arr(raw[k % RawCount<MODE>::value], a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], fmaf(a[i], sc[i], sh[i]));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = fmaxf(m[i], 0.f);
+}
+// power-of-two multiplier that brings a tensor with max |x| = amax into [2^9, 2^10): safe for fp16 hi/lo splitting
+TNB_DEVINL float pow2_scale_for(const float* amax_ptr) {
+  if (amax_ptr == nullptr) return 1.f;
+  const float amax = *amax_ptr;
+  if (!(amax > 0.f) || !(amax < 3.0e38f)) return 1.f;
+  int e;
+  frexpf(amax, &e);
+  return ldexpf(1.f, 10 - e);
+}
+
 // ---- host-side launchers (igemm.cu) ----------------------------------------------------------
 struct ConvPlan {
   int BN, MT, SA, SB, tmem_cols;
@@ -79,7 +138,7 @@ int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, floa
                    int nterms, int fmt, int variant, cudaStream_t st);
 int conv3x3_num_stat_rows(int N, int H, int W, int Cin, int Cout, int nterms);
 
-int launch_wgrad3x3(const ViewDesc& view, const float* dz, float* dw_oihw, int Cout, int CinReal, int nterms,
-                    int fmt, int variant, cudaStream_t st);
+int launch_wgrad3x3(const ViewDesc& view, const float* dz, const float* dz_amax, float* dw_oihw, int Cout, int CinReal,
+                    int nterms, int fmt, int variant, cudaStream_t st);
 
 }  // namespace tnb

@@ -43,15 +43,26 @@ int launch_pack_input(const float* x, float* out, int N, int C, int H, int W, in
 // (deterministic), combines in fp64, emits the fused affine (scale, shift) used by every consumer,
 // and updates the running statistics exactly like torch (biased var to normalise, unbiased to track).
 // =============================================================================================
-__global__ void bn_finalize_kernel(const float* __restrict__ part, int rows, double count,
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ part, int rows, double count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* running_mean, float* running_var, float momentum, float eps, int training,
                                    float* scale, float* shift, float* mean_out, float* invstd_out, int C) {
-  __shared__ double s1[8][33], s2[8][33];
+  __shared__ double s1[32][33], s2[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   double a = 0.0, b = 0.0;
   if (training && c < C) {
-    for (int r = threadIdx.y; r < rows; r += 8) {
+    float fa[4] = {0.f, 0.f, 0.f, 0.f}, fb[4] = {0.f, 0.f, 0.f, 0.f};
+    int r = threadIdx.y;
+    for (; r + 96 < rows; r += 128) {  // 4 independent loads in flight per thread
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        fa[u] = part[((size_t)(r + 32 * u) * 2 + 0) * C + c];
+        fb[u] = part[((size_t)(r + 32 * u) * 2 + 1) * C + c];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a += (double)fa[u]; b += (double)fb[u]; }
+    }
+    for (; r < rows; r += 32) {
       a += (double)part[((size_t)r * 2 + 0) * C + c];
       b += (double)part[((size_t)r * 2 + 1) * C + c];
     }
@@ -63,7 +74,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int rows, dou
     float mean, invstd;
     if (training) {
       double sa = 0.0, sb = 0.0;
-      for (int i = 0; i < 8; ++i) { sa += s1[i][threadIdx.x]; sb += s2[i][threadIdx.x]; }
+      for (int i = 0; i < 32; ++i) { sa += s1[i][threadIdx.x]; sb += s2[i][threadIdx.x]; }
       const double m = sa / count;
       double var = sb / count - m * m;
       if (var < 0.0) var = 0.0;
@@ -86,7 +97,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int rows, dou
 int launch_bn_finalize(const float* part, int rows, double count, const float* gamma, const float* beta,
                        float* running_mean, float* running_var, float momentum, float eps, int training,
                        float* scale, float* shift, float* mean, float* invstd, int C, cudaStream_t st) {
-  bn_finalize_kernel<<<cdiv(C, 32), dim3(32, 8), 0, st>>>(part, rows, count, gamma, beta, running_mean,
+  bn_finalize_kernel<<<cdiv(C, 32), dim3(32, 32), 0, st>>>(part, rows, count, gamma, beta, running_mean,
                                                            running_var, momentum, eps, training, scale, shift, mean,
                                                            invstd, C);
   TNB_CHECK_CUDA(cudaGetLastError());
@@ -252,6 +263,7 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnB
   const long long items = (long long)a.N * Hw * Ww * CQ;
   const long long stride = (long long)gridDim.x * blockDim.x;
   float4 acc1 = make_float4(0, 0, 0, 0), acc2 = make_float4(0, 0, 0, 0);
+  float amax = 0.f;
   for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += stride) {
     const int cq = (int)(it % CQ);
     long long r = it / CQ;
@@ -339,6 +351,7 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnB
         o.z = sc.z * (d.z - m1.z - xh.z * m2.z);
         o.w = sc.w * (d.w - m1.w - xh.w * m2.w);
         *reinterpret_cast<float4*>(a.dz + ((size_t)(n * a.H + h) * a.W + w) * a.C + c) = o;
+        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
       } else {
         acc1 = f4add(acc1, d);
         acc2.x = fmaf(d.x, xh.x, acc2.x);
@@ -347,6 +360,10 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnB
         acc2.w = fmaf(d.w, xh.w, acc2.w);
       }
     }
+  }
+  if (APPLY && a.amax != nullptr) {
+    amax = warp_max(amax);  // non-negative floats order like their bit patterns
+    if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(reinterpret_cast<int*>(a.amax), __float_as_int(amax));
   }
   if (!APPLY) {
     // every thread keeps one channel quad for its whole grid-stride loop (256 % CQ == 0, stride % CQ == 0)
@@ -386,13 +403,24 @@ int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st) {
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int rows, int C, float* sums, float* dgamma,
-                                       float* dbeta) {
-  __shared__ double s1[8][33], s2[8][33];
+__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ part, int rows, int C,
+                                                               float* sums, float* dgamma, float* dbeta) {
+  __shared__ double s1[32][33], s2[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   double a = 0.0, b = 0.0;
   if (c < C) {
-    for (int r = threadIdx.y; r < rows; r += 8) {
+    float fa[4], fb[4];
+    int r = threadIdx.y;
+    for (; r + 96 < rows; r += 128) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        fa[u] = part[((size_t)(r + 32 * u) * 2 + 0) * C + c];
+        fb[u] = part[((size_t)(r + 32 * u) * 2 + 1) * C + c];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a += (double)fa[u]; b += (double)fb[u]; }
+    }
+    for (; r < rows; r += 32) {
       a += (double)part[((size_t)r * 2 + 0) * C + c];
       b += (double)part[((size_t)r * 2 + 1) * C + c];
     }
@@ -402,7 +430,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int rows,
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
     double sa = 0.0, sb = 0.0;
-    for (int i = 0; i < 8; ++i) { sa += s1[i][threadIdx.x]; sb += s2[i][threadIdx.x]; }
+    for (int i = 0; i < 32; ++i) { sa += s1[i][threadIdx.x]; sb += s2[i][threadIdx.x]; }
     sums[c] = (float)sa;
     sums[C + c] = (float)sb;
     dbeta[c] = (float)sa;   // d/dbeta  = sum dy
@@ -411,7 +439,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int rows,
 }
 int launch_bn_bwd_finalize(const float* part, int rows, int C, float* sums, float* dgamma, float* dbeta,
                            cudaStream_t st) {
-  bn_bwd_finalize_kernel<<<cdiv(C, 32), dim3(32, 8), 0, st>>>(part, rows, C, sums, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<cdiv(C, 32), dim3(32, 32), 0, st>>>(part, rows, C, sums, dgamma, dbeta);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -459,23 +487,33 @@ __global__ void __launch_bounds__(256) wbce_fwd_kernel(const float* __restrict__
   }
   if (threadIdx.x == 0) part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = sd[0];
 }
-__global__ void wbce_final_kernel(const double* part, int nsamples, int nblocks, long long per_sample, int reduce,
-                                  float* out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(256) wbce_final_kernel(const double* part, int nsamples, int nblocks,
+                                                         long long per_sample, int reduce, float* out) {
+  // one block; fixed summation order => deterministic. sample sums first, then the batch total.
+  __shared__ double sd[256];
   double total = 0.0;
   for (int n = 0; n < nsamples; ++n) {
     double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += part[(size_t)n * nblocks + b];
-    if (!reduce) out[n] = (float)(s / (double)per_sample);
-    total += s;
+    for (int b = threadIdx.x; b < nblocks; b += 256) s += part[(size_t)n * nblocks + b];
+    sd[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+      if (threadIdx.x < k) sd[threadIdx.x] += sd[threadIdx.x + k];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      if (!reduce) out[n] = (float)(sd[0] / (double)per_sample);
+      total += sd[0];
+    }
+    __syncthreads();
   }
-  if (reduce) out[0] = (float)(total / ((double)per_sample * nsamples));
+  if (threadIdx.x == 0 && reduce) out[0] = (float)(total / ((double)per_sample * nsamples));
 }
 int launch_wbce_fwd(const float* p, const float* y, int nsamples, long long per_sample, int reduce, double* part,
                     float* out, cudaStream_t st) {
   wbce_fwd_kernel<<<dim3(kWbceBlocks, nsamples), 256, 0, st>>>(p, y, per_sample, part);
   TNB_CHECK_CUDA(cudaGetLastError());
-  wbce_final_kernel<<<1, 32, 0, st>>>(part, nsamples, kWbceBlocks, per_sample, reduce, out);
+  wbce_final_kernel<<<1, 256, 0, st>>>(part, nsamples, kWbceBlocks, per_sample, reduce, out);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -39,12 +39,13 @@ struct LayerBuf {
   int H, W, cin, cin_real, cout;
   float *z, *scale, *shift, *mean, *invstd, *stat_part;
   int stat_rows;
-  float *dz, *din, *bwd_part, *bwd_sums;
+  float *dz, *din, *bwd_part, *bwd_sums, *amax;
   int bwd_rows;
   uint16_t *wf, *wd;
 };
 struct Plan {
   LayerBuf L[kLayers];
+  float* amax_all;  // [kLayers] max|dz| per layer, raised atomically by bn_bwd apply
   float* xin;
   float* dA_pred;
   int cpad;
@@ -82,6 +83,7 @@ int build_plan(const tnb_tracknet_cfg_t& c, void* ws, Plan* P) {
   Bump b{reinterpret_cast<uint8_t*>(ws), 0};
   P->cpad = (c.in_dim + 31) / 32 * 32;
   const size_t npix0 = (size_t)c.n * c.h * c.w;
+  P->amax_all = b.take<float>(kLayers);
   P->xin = b.take<float>(npix0 * P->cpad);
   P->dA_pred = b.take<float>(npix0 * 64);
   for (int l = 0; l < kLayers; ++l) {
@@ -103,9 +105,10 @@ int build_plan(const tnb_tracknet_cfg_t& c, void* ws, Plan* P) {
       B.bwd_rows = bn_bwd_num_blocks(c.n, B.H, B.W, B.cout);
       B.bwd_part = b.take<float>((size_t)B.bwd_rows * 2 * B.cout);
       B.bwd_sums = b.take<float>(2 * B.cout);
+      B.amax = P->amax_all + l;
       B.wd = (l > 0) ? b.take<uint16_t>(conv3x3_wpack_elems(B.cout, B.cin)) : nullptr;
     } else {
-      B.dz = B.din = B.bwd_part = B.bwd_sums = nullptr; B.wd = nullptr; B.bwd_rows = 0;
+      B.dz = B.din = B.bwd_part = B.bwd_sums = B.amax = nullptr; B.wd = nullptr; B.bwd_rows = 0;
     }
   }
   P->bytes = (b.off + 255) & ~(size_t)255;
@@ -187,6 +190,7 @@ int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float*
   Plan P;
   if (int rc = build_plan(c, ws, &P)) return rc;
   TNB_REQUIRE(ws_bytes >= P.bytes, "tracknet_backward: workspace too small (%zu < %zu)", ws_bytes, P.bytes);
+  TNB_CHECK_CUDA(cudaMemsetAsync(P.amax_all, 0, sizeof(float) * kLayers, st));
   const SrcDesc last = make_src(P, c, kLayers - 1, SRC_AFFINE_RELU);
   if (int rc = launch_predictor_bwd(last, c.n, c.h, c.w, (const float*)params[kLayers * 6 + 0], c.out_dim, dy, y,
                                     P.dA_pred, (float*)grads[kLayers * 3 + 0], (float*)grads[kLayers * 3 + 1], st))
@@ -214,7 +218,7 @@ int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float*
     }
     a.z = B.z; a.scale = B.scale; a.shift = B.shift; a.mean = B.mean; a.invstd = B.invstd;
     a.N = c.n; a.H = B.H; a.W = B.W; a.C = B.cout;
-    a.part = B.bwd_part; a.sums = B.bwd_sums; a.dz = B.dz;
+    a.part = B.bwd_part; a.sums = B.bwd_sums; a.dz = B.dz; a.amax = B.amax;
     a.inv_count = (float)(1.0 / ((double)c.n * B.H * B.W));
     if (int rc = launch_bn_bwd_reduce(a, st)) return rc;
     if (int rc = launch_bn_bwd_finalize(B.bwd_part, B.bwd_rows, B.cout, B.bwd_sums, (float*)grads[l * 3 + 1],
@@ -225,18 +229,19 @@ int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float*
     if (l > 0) {
       ViewDesc dv;
       memset(&dv, 0, sizeof(dv));
-      dv.s[0] = SrcDesc{B.dz, nullptr, nullptr, B.cout, B.H, B.W, SRC_IDENTITY};
+      dv.s[0] = SrcDesc{B.dz, B.amax, nullptr, B.cout, B.H, B.W, SRC_IDENTITY};  // scale slot = max|dz|
       dv.s[1] = dv.s[0];
       dv.C0 = dv.C = B.cout; dv.N = c.n; dv.H = B.H; dv.W = B.W;
       ConvPlan cp;
       if (int rc = conv3x3_plan(c.n, B.H, B.W, B.cout, B.cin, c.bwd_terms, &cp)) return rc;
-      if (int rc = launch_pack_weights(w, B.wd, B.cout, B.cin, 1, 1, cp.BN, st)) return rc;
-      if (int rc = launch_conv3x3(dv, B.wd, B.din, nullptr, B.cin, c.bwd_terms, 1, c.variant & 3, st)) return rc;
+      if (int rc = launch_pack_weights(w, B.wd, B.cout, B.cin, 1, 0, cp.BN, st)) return rc;
+      if (int rc = launch_conv3x3(dv, B.wd, B.din, nullptr, B.cin, c.bwd_terms, 0, c.variant & 3, st)) return rc;
     }
     float* dw = (float*)grads[l * 3 + 0];
     TNB_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)B.cout * B.cin_real * 9, st));
     const ViewDesc v = make_view(P, c, l);
-    if (int rc = launch_wgrad3x3(v, B.dz, dw, B.cout, B.cin_real, c.bwd_terms, 1, (c.variant >> 2) & 3, st)) return rc;
+    if (int rc = launch_wgrad3x3(v, B.dz, B.amax, dw, B.cout, B.cin_real, c.bwd_terms, 0, (c.variant >> 2) & 3, st))
+      return rc;
   }
   return 0;
 }

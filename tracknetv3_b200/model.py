@@ -90,8 +90,8 @@ class _TrackNetFunction(torch.autograd.Function):
 class TrackNet(nn.Module):
     """Drop-in for reference ``model.TrackNet`` (model.py:44-73).
 
-    ``precision``: "fp32x3" (default) computes every 3x3 convolution as a 3-term fp16 (forward) / bf16
-    (backward) split product with fp32 accumulation - within ~2e-5 of the reference's fp32 heatmaps;
+    ``precision``: "fp32x3" (default) computes every 3x3 convolution as a 3-term fp16 hi/lo split product with
+    fp32 accumulation (gradients are pre-scaled by a power of two) - within ~4e-5 of the reference's fp32 heatmaps;
     "tf32like" is a single 16-bit pass (what the reference's own cuDNN TF32 path amounts to; ~7e-3).
     """
 
