@@ -1,0 +1,427 @@
+// Persistent tcgen05 implicit-GEMM 3x3 convolution (forward and dgrad) for sm_100a.
+//
+// Replaces cuDNN's nn.Conv2d(3x3, padding='same', bias=False) forward (reference model.py:8,13) and its
+// autograd dgrad (reference train.py:95), with BatchNorm-apply + ReLU (model.py:14-15), MaxPool2d
+// (model.py:59,61,63) and Upsample + torch.cat (model.py:65,67,69) of the producing layers fused into the
+// operand gather, and the BatchNorm statistics of the output fused into the epilogue.
+//
+// One CTA per SM loops over (pixel tile, channel tile) work items:
+//   warp 0      one elected thread issues tcgen05.mma (kind::f16, M=128, N=BN, K=16; 3 MMAs per K step in the
+//               fp32-faithful hi/lo split mode) into one of up to two TMEM accumulator buffers
+//   warp 1      weight tiles: 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx) of pre-packed smem images
+//   warps 2-5   epilogue: tcgen05.ld -> fp32 NHWC stores + per-channel (sum, sumsq) partials; overlaps the
+//               next tile's MMAs when two accumulator buffers fit in TMEM (2*MT*BN <= 512 columns)
+//   warps 6-11  operand producers: batched global gathers -> BN affine/ReLU/pool/upsample/concat ->
+//               16-bit hi/lo split -> planar smem halo tile -> fence.proxy.async -> mbarrier
+// The planar tile [plane = 8 channels][pixel][16 B] is a SWIZZLE_NONE K-major operand in which every 3x3 tap
+// is just a different 16-byte aligned start address: one halo tile serves all 9 taps.
+#include "igemm.cuh"
+#include "prof.cuh"
+#include <type_traits>
+
+namespace tnb {
+
+static constexpr int kThreads = 384;
+static constexpr int kFillThreads = 192;
+static constexpr int kEpiThreads = 128;
+static constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
+static constexpr int kHdrBytes = 512;
+
+struct ConvArgs {
+  ViewDesc view;
+  const uint16_t* wpack;
+  float* out;        // [N,H,W,Cout]
+  float* stat_part;  // [ntiles][2][Cout] per-tile (sum, sumsq) partials, or nullptr
+  int Cout, BN, MT, SA, SB, nbuf, nterms, variant, tmem_cols;
+  int tiles_h, tiles_w, ntiles, nwork;
+};
+
+// 31-shuffle transpose-reduce: on return lane j holds the sum over the 32 lanes of v[j].
+TNB_DEVINL float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_constant__ ConvArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  const ViewDesc& V = a.view;
+  const int MT = a.MT, BN = a.BN;
+  const int PITCH = 8 * MT + 2;
+  const int HALO_PX = 18 * PITCH;
+  const int PLANE = pad_px(HALO_PX) * 16;  // bytes
+  const int TP = a.nterms > 1 ? 2 : 1;     // operand term planes stored (hi[,lo])
+  const int A_STAGE = TP * 4 * PLANE;
+  const int B_STAGE = TP * 64 * BN;        // bytes: [term][4 planes][BN][16B]
+  const int nchunks = V.C / 32;
+  const int BUFCOLS = MT * BN;
+
+  uint64_t* full_A = reinterpret_cast<uint64_t*>(smem);       // [4]
+  uint64_t* empty_A = full_A + 4;                             // [4]
+  uint64_t* full_B = full_A + 8;                              // [8]
+  uint64_t* empty_B = full_A + 16;                            // [8]
+  uint64_t* tmem_full = full_A + 24;                          // [2]
+  uint64_t* tmem_empty = full_A + 26;                         // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(full_A + 28);
+  int2* table = reinterpret_cast<int2*>(smem + kHdrBytes);
+  const int table_bytes = (HALO_PX * 8 + 127) & ~127;
+  float* sstat = reinterpret_cast<float*>(smem + kHdrBytes + table_bytes);  // [4 warps][2][BN]
+  uint8_t* a_base = smem + kHdrBytes + table_bytes + 4 * 2 * BN * 4;
+  uint8_t* b_base = a_base + a.SA * A_STAGE;
+
+  // ---- one-time setup ----
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int i = 0; i < a.SA; ++i) { mbar_init(&full_A[i], kFillThreads); mbar_init(&empty_A[i], 1); }
+      for (int i = 0; i < a.SB; ++i) { mbar_init(&full_B[i], 1); mbar_init(&empty_B[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, a.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  // dgrad: dz is multiplied by a power of two on the way in (so that its fp16 hi/lo split keeps ~22 bits) and
+  // the accumulator by the inverse on the way out; forward views use BN scale/shift instead (in_mul = 1).
+  const float in_mul = (V.s[0].mode == SRC_IDENTITY) ? pow2_scale_for(V.s[0].scale) : 1.f;
+  const float out_mul = 1.f / in_mul;
+
+  if (warp == 0) {
+    // =========================== MMA issuer ===========================
+    // The whole warp runs the (warp-uniform) loops so that the descriptor arithmetic stays in uniform
+    // registers; only the tcgen05 instructions themselves are predicated on one elected lane.
+    {
+      const bool lead = elect_one();
+      const uint32_t idesc = make_idesc(128, BN, FMT, 0, 0);
+      // A: K-major planar halo tile. LBO = plane stride (next 8 channels), SBO = halo row pitch (next 8 output
+      // pixels = next image row of the 16x8 tile). B: K-major packed weights. variant bits swap them (probe).
+      uint32_t a_lbo = PLANE, a_sbo = PITCH * 16;
+      uint32_t b_lbo = BN * 16, b_sbo = 128;
+      if (a.variant & 1) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; }
+      if (a.variant & 2) { uint32_t t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
+      // descriptors are base + (byte offset >> 4): the start-address field never carries into the next field
+      const uint64_t a_desc0 = make_smem_desc(smem_u32(a_base), a_lbo, a_sbo);
+      const uint64_t b_desc0 = make_smem_desc(smem_u32(b_base), b_lbo, b_sbo);
+      const uint32_t a_stage16 = A_STAGE >> 4, b_stage16 = B_STAGE >> 4;
+      const uint32_t a_k16 = (2 * PLANE) >> 4, a_lo16 = (4 * PLANE) >> 4;
+      const uint32_t b_k16 = (2 * BN * 16) >> 4, b_lo16 = (4 * BN * 16) >> 4;
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      int k = 0;
+      for (int work = blockIdx.x; work < a.nwork; work += gridDim.x, ++k) {
+        const int buf = k % a.nbuf;
+        const uint32_t use = (uint32_t)(k / a.nbuf);
+        mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);  // epilogue has drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t d_buf = tmem_base + buf * BUFCOLS;
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(&full_A[sa], pha);
+          tc_fence_after();
+          const uint64_t a_st = a_desc0 + (uint64_t)(sa * a_stage16);
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&full_B[sb], phb);
+            tc_fence_after();
+            const uint64_t b_st = b_desc0 + (uint64_t)(sb * b_stage16);
+            const int dy = t / 3, dx = t - dy * 3;
+            const uint64_t a_tap = a_st + (uint64_t)(dy * PITCH + dx);
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint32_t d_tmem = d_buf + mt * BN;
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {
+                const uint64_t a_hi = a_tap + (uint64_t)(8 * mt + kk * a_k16);
+                const uint64_t b_hi = b_st + (uint64_t)(kk * b_k16);
+                const uint32_t acc = (c | t | kk) != 0;
+                if (lead) {
+                  umma_f16(d_tmem, a_hi, b_hi, idesc, acc);
+                  if (a.nterms > 1) {
+                    umma_f16(d_tmem, a_hi + a_lo16, b_hi, idesc, 1);
+                    umma_f16(d_tmem, a_hi, b_hi + b_lo16, idesc, 1);
+                  }
+                }
+              }
+            }
+            if (lead) umma_commit(&empty_B[sb]);
+            if (++sb == a.SB) { sb = 0; phb ^= 1; }
+          }
+          if (lead) umma_commit(&empty_A[sa]);
+          if (++sa == a.SA) { sa = 0; pha ^= 1; }
+        }
+        if (lead) umma_commit(&tmem_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =========================== weight loader (bulk TMA) ===========================
+    if (elect_one()) {
+      int sb = 0;
+      uint32_t phb = 0;
+      for (int work = blockIdx.x; work < a.nwork; work += gridDim.x) {
+        const int nt = work / a.ntiles;
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)nt * nchunks * 9 * (size_t)(128 * BN);
+        for (int i = 0; i < nchunks * 9; ++i) {
+          mbar_wait(&empty_B[sb], phb ^ 1);
+          mbar_arrive_expect_tx(&full_B[sb], (uint32_t)B_STAGE);
+          bulk_g2s(b_base + sb * B_STAGE, wsrc + (size_t)i * (128 * BN), (uint32_t)B_STAGE, &full_B[sb]);
+          if (++sb == a.SB) { sb = 0; phb ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 6) {
+    // =========================== epilogue (warps 2..5) ===========================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = 32 * q + lane;
+    const int r = row >> 3, cc = row & 7;
+    const int et = tid - 64;  // 0..127
+    int k = 0;
+    for (int work = blockIdx.x; work < a.nwork; work += gridDim.x, ++k) {
+      const int nt = work / a.ntiles;
+      int tile = work - nt * a.ntiles;
+      const int tile_id = tile;
+      const int tw = tile % a.tiles_w; tile /= a.tiles_w;
+      const int th = tile % a.tiles_h;
+      const int n = tile / a.tiles_h;
+      const int h0 = th * 16, w0 = tw * 8 * MT, n0 = nt * BN;
+      const int buf = k % a.nbuf;
+      const uint32_t use = (uint32_t)(k / a.nbuf);
+      mbar_wait(&tmem_full[buf], use & 1);
+      tc_fence_after();
+      for (int col0 = 0; col0 < BN; col0 += 32) {
+        float csum = 0.f, csq = 0.f;
+        for (int mt = 0; mt < MT; ++mt) {
+          const int h = h0 + r, w = w0 + 8 * mt + cc;
+          const bool valid = (h < V.H) && (w < V.W);
+          uint32_t rg[32];
+          tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * BUFCOLS + mt * BN + col0), rg);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rg[i]) * out_mul;
+          if (valid) {
+            float4* dst = reinterpret_cast<float4*>(a.out + ((size_t)(n * V.H + h) * V.W + w) * a.Cout + n0 + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          if (a.stat_part != nullptr) {
+            if (!valid) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            float s[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s[i] = v[i];
+            csum += warp_transpose_sum(s, lane);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s[i] = v[i] * v[i];
+            csq += warp_transpose_sum(s, lane);
+          }
+        }
+        if (a.stat_part != nullptr) {
+          sstat[(q * 2 + 0) * BN + col0 + lane] = csum;
+          sstat[(q * 2 + 1) * BN + col0 + lane] = csq;
+        }
+      }
+      // all TMEM reads of this buffer are complete: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (a.stat_part != nullptr) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int j = et; j < 2 * BN; j += kEpiThreads) {
+          const int which = j / BN, col = j - which * BN;
+          const float s = sstat[(0 * 2 + which) * BN + col] + sstat[(1 * 2 + which) * BN + col] +
+                          sstat[(2 * 2 + which) * BN + col] + sstat[(3 * 2 + which) * BN + col];
+          a.stat_part[((size_t)tile_id * 2 + which) * a.Cout + n0 + col] = s;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // sstat is reused by the next tile
+      }
+    }
+  } else {
+    // =========================== A producers: gather + BN/ReLU/pool/upsample + split ===========
+    const int ftid = tid - 192;
+    const int j = ftid & 3;       // plane (8 channels) this thread fills: fixed, kFillThreads % 4 == 0
+    const int pbase = ftid >> 2;  // first halo pixel; stride kFillThreads/4 pixels
+    int sa = 0;
+    uint32_t pha = 0;
+    for (int work = blockIdx.x; work < a.nwork; work += gridDim.x) {
+      const int nt = work / a.ntiles;
+      int tile = work - nt * a.ntiles;
+      const int tw = tile % a.tiles_w; tile /= a.tiles_w;
+      const int th = tile % a.tiles_h;
+      const int n = tile / a.tiles_h;
+      const int h0 = th * 16, w0 = tw * 8 * MT;
+      asm volatile("bar.sync 2, 192;" ::: "memory");  // previous tile's table is no longer read
+      for (int p = ftid; p < HALO_PX; p += kFillThreads) {
+        const int hr = p / PITCH, hc = p - hr * PITCH;
+        const int h = h0 - 1 + hr, w = w0 - 1 + hc;
+        int2 e = make_int2(-1, -1);
+        if (h >= 0 && h < V.H && w >= 0 && w < V.W) {
+          e.x = view_pix_off(V.s[0], n, h, w);
+          if (V.C0 < V.C) e.y = view_pix_off(V.s[1], n, h, w);
+        }
+        table[p] = e;
+      }
+      asm volatile("bar.sync 2, 192;" ::: "memory");
+      for (int c = 0; c < nchunks; ++c) {
+        const int cch = c * 32 + j * 8;
+        const bool second = cch >= V.C0;
+        const SrcDesc& S = second ? V.s[1] : V.s[0];
+        const int cc = second ? cch - V.C0 : cch;
+        float sc[8], sh[8];
+        if (S.mode != SRC_IDENTITY) { ld8(S.scale + cc, sc); ld8(S.shift + cc, sh); }
+        mbar_wait(&empty_A[sa], pha ^ 1);
+        uint8_t* stage = a_base + sa * A_STAGE + j * PLANE;
+        auto run = [&](auto mode_tag, auto batch_tag) {
+          constexpr int MODE = decltype(mode_tag)::value;
+          constexpr int U = decltype(batch_tag)::value;
+          for (int p0 = pbase; p0 < HALO_PX; p0 += (kFillThreads / 4) * U) {
+            Raw8 raw[U][RawCount<MODE>::value];
+            int off[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int p = p0 + (kFillThreads / 4) * u;
+              off[u] = -1;
+              if (p < HALO_PX) {
+                const int2 e = table[p];
+                off[u] = second ? e.y : e.x;
+                if (off[u] >= 0) view_issue<MODE>(S, off[u], cc, raw[u]);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int p = p0 + (kFillThreads / 4) * u;
+              if (p < HALO_PX) {
+                uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+                if (off[u] >= 0) {
+                  float v[8];
+                  view_finish<MODE>(raw[u], sc, sh, in_mul, v);
+                  split8<FMT>(v, hi, lo);
+                }
+                uint8_t* dst = stage + p * 16;
+                *reinterpret_cast<uint4*>(dst) = hi;
+                if (a.nterms > 1) *reinterpret_cast<uint4*>(dst + 4 * PLANE) = lo;
+              }
+            }
+          }
+        };
+        switch (S.mode) {
+          case SRC_IDENTITY: run(std::integral_constant<int, SRC_IDENTITY>{}, std::integral_constant<int, 4>{}); break;
+          case SRC_AFFINE_RELU_POOL: run(std::integral_constant<int, SRC_AFFINE_RELU_POOL>{}, std::integral_constant<int, 1>{}); break;
+          case SRC_AFFINE_RELU_UP: run(std::integral_constant<int, SRC_AFFINE_RELU_UP>{}, std::integral_constant<int, 4>{}); break;
+          default: run(std::integral_constant<int, SRC_AFFINE_RELU>{}, std::integral_constant<int, 4>{}); break;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&full_A[sa]);
+        if (++sa == a.SA) { sa = 0; pha ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, a.tmem_cols);
+  }
+}
+
+static int pick_bn(int nside) {
+  if (nside % 256 == 0) return 256;
+  if (nside % 192 == 0) return 192;
+  if (nside % 128 == 0) return 128;
+  if (nside % 64 == 0) return 64;
+  if (nside % 32 == 0) return 32;
+  return 0;
+}
+static int pow2_cols(int c) {
+  int p = 32;
+  while (p < c) p <<= 1;
+  return p;
+}
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* plan) {
+  TNB_REQUIRE(Cin % 32 == 0, "conv3x3: view channels %d must be a multiple of 32", Cin);
+  const int BN = pick_bn(Cout);
+  TNB_REQUIRE(BN >= 32 && BN % 16 == 0, "conv3x3: unsupported output channel count %d", Cout);
+  const int TP = nterms > 1 ? 2 : 1;
+  int MT = 512 / BN;
+  if (MT > 4) MT = 4;
+  while (MT > 1 && 8 * (MT - 1) >= W) --MT;  // do not tile wider than the image
+  int SA = 2, SB = 0;
+  size_t smem = 0;
+  for (;; --MT) {
+    const int pitch = 8 * MT + 2, halo = 18 * pitch;
+    const size_t a_stage = (size_t)TP * 4 * pad_px(halo) * 16;
+    const size_t b_stage = (size_t)TP * 64 * BN;
+    const size_t fixed = kHdrBytes + ((halo * 8 + 127) & ~127) + (size_t)4 * 2 * BN * 4 + SA * a_stage;
+    if (fixed + 2 * b_stage <= (size_t)kMaxSmem) {
+      SB = (int)((kMaxSmem - fixed) / b_stage);
+      if (SB > 8) SB = 8;
+      smem = fixed + SB * b_stage;
+      break;
+    }
+    TNB_REQUIRE(MT > 1, "conv3x3: no shared-memory plan for Cin=%d Cout=%d", Cin, Cout);
+  }
+  plan->BN = BN; plan->MT = MT; plan->SA = SA; plan->SB = SB;
+  plan->nbuf = (2 * MT * BN <= 512) ? 2 : 1;
+  plan->tmem_cols = pow2_cols(plan->nbuf * MT * BN);
+  plan->smem_bytes = smem;
+  plan->tiles_h = (H + 15) / 16;
+  plan->tiles_w = (W + 8 * MT - 1) / (8 * MT);
+  (void)N;
+  return 0;
+}
+
+int conv3x3_num_stat_rows(int N, int H, int W, int Cin, int Cout, int nterms) {
+  ConvPlan p;
+  if (conv3x3_plan(N, H, W, Cin, Cout, nterms, &p)) return -1;
+  return N * p.tiles_h * p.tiles_w;
+}
+
+int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout,
+                   int nterms, int fmt, int variant, cudaStream_t st) {
+  ConvPlan p;
+  int rc = conv3x3_plan(view.N, view.H, view.W, view.C, Cout, nterms, &p);
+  if (rc) return rc;
+  ConvArgs a;
+  a.view = view; a.wpack = wpack; a.out = out; a.stat_part = stat_part;
+  a.Cout = Cout; a.BN = p.BN; a.MT = p.MT; a.SA = p.SA; a.SB = p.SB; a.nbuf = p.nbuf; a.nterms = nterms;
+  a.variant = variant; a.tmem_cols = p.tmem_cols; a.tiles_h = p.tiles_h; a.tiles_w = p.tiles_w;
+  a.ntiles = view.N * p.tiles_h * p.tiles_w;
+  a.nwork = a.ntiles * (Cout / p.BN);
+  const int grid = a.nwork < num_sms() ? a.nwork : num_sms();
+  auto kern = fmt == 0 ? conv3x3_kernel<0> : conv3x3_kernel<1>;
+  TNB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+  ProfScope prof((view.s[0].mode == SRC_IDENTITY && view.s[0].scale != nullptr) ? PROF_CONV_DGRAD : PROF_CONV_FWD, st,
+                 view.N, view.H, view.W, view.C, Cout);
+  kern<<<grid, kThreads, p.smem_bytes, st>>>(a);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace tnb

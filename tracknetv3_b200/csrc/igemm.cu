@@ -27,15 +27,10 @@
 
 namespace tnb {
 
-static constexpr int kThreads = 320;      // warp0: MMA issue + TMEM alloc, warp1: weight TMA, warps 2..9: fill
+static constexpr int kThreads = 320;      // wgrad: warp0 MMA issue + TMEM alloc, warp1 idle, warps 2..9 fill
 static constexpr int kFillThreads = 256;  // warps 2..5 double as the epilogue warps
 static constexpr int kMaxSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100
 static constexpr int kHdrBytes = 256;
-
-__host__ __device__ inline int pad_px(int px) {  // plane stride ≡ 2 (mod 8) pixels -> conflict-free fill stores
-  int r = px & 7;
-  return px + ((2 - r) & 7);
-}
 
 // =============================================================================================
 // weight packing: OIHW fp32 -> per (n-tile, k-chunk, tap) smem images [term][plane(4)][BN][8] (uint16)
@@ -80,15 +75,6 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __res
   }
 }
 
-static int pick_bn(int nside) {
-  if (nside % 256 == 0) return 256;
-  if (nside % 192 == 0) return 192;
-  if (nside % 128 == 0) return 128;
-  if (nside % 64 == 0) return 64;
-  if (nside % 32 == 0) return 32;
-  return 0;
-}
-
 size_t conv3x3_wpack_elems(int Kside, int Nside) {
   const int Kpad = (Kside + 31) / 32 * 32;
   return (size_t)Nside * Kpad * 9 * 2;
@@ -107,343 +93,6 @@ int launch_pack_weights(const float* w, uint16_t* out, int Co, int Ci, int mode,
     pack_weights_kernel<0><<<blocks, threads, 0, st>>>(w, out, Co, Ci, Nside, Kpad, BN, mode);
   else
     pack_weights_kernel<1><<<blocks, threads, 0, st>>>(w, out, Co, Ci, Nside, Kpad, BN, mode);
-  TNB_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
-// =============================================================================================
-// conv3x3 forward / dgrad
-// =============================================================================================
-struct ConvArgs {
-  ViewDesc view;
-  const uint16_t* wpack;
-  float* out;        // [N,H,W,Cout]
-  float* stat_part;  // [gridDim.x][2][Cout] per-tile (sum, sumsq) partials, or nullptr
-  int Cout, BN, MT, SA, SB, nterms, variant, tmem_cols;
-  int tiles_h, tiles_w;
-};
-
-// 31-shuffle transpose-reduce: on return lane j holds sum over the 32 lanes of v[j].
-TNB_DEVINL float warp_transpose_sum(float (&v)[32], int lane) {
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int i = 0; i < o; ++i) {
-      const float send = up ? v[i] : v[i + o];
-      const float keep = up ? v[i + o] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-    }
-  }
-  return v[0];
-}
-
-template <int FMT>
-__global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_constant__ ConvArgs a) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-
-  const ViewDesc& V = a.view;
-  const int MT = a.MT, BN = a.BN;
-  const int PITCH = 8 * MT + 2;
-  const int HALO_PX = 18 * PITCH;
-  const int PLANE = pad_px(HALO_PX) * 16;  // bytes
-  const int TP = a.nterms > 1 ? 2 : 1;     // operand term planes stored (hi[,lo])
-  const int A_STAGE = TP * 4 * PLANE;
-  const int B_STAGE = TP * 64 * BN;        // bytes: [term][4 planes][BN][16B]
-  const int nchunks = V.C / 32;
-
-  uint64_t* full_A = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* empty_A = full_A + 2;
-  uint64_t* full_B = full_A + 4;
-  uint64_t* empty_B = full_A + 12;
-  uint64_t* tmem_full = full_A + 20;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(full_A + 21);
-  int2* table = reinterpret_cast<int2*>(smem + kHdrBytes);
-  const int table_bytes = (HALO_PX * 8 + 127) & ~127;
-  uint8_t* a_base = smem + kHdrBytes + table_bytes;
-  uint8_t* b_base = a_base + a.SA * A_STAGE;
-
-  // ---- tile coordinates ----
-  int tile = blockIdx.x;
-  const int tw = tile % a.tiles_w; tile /= a.tiles_w;
-  const int th = tile % a.tiles_h;
-  const int n = tile / a.tiles_h;
-  const int h0 = th * 16, w0 = tw * 8 * MT;
-  const int n0 = blockIdx.y * BN;
-
-  // ---- one-time setup ----
-  if (warp == 0) {
-    if (elect_one()) {
-      for (int i = 0; i < a.SA; ++i) { mbar_init(&full_A[i], kFillThreads); mbar_init(&empty_A[i], 1); }
-      for (int i = 0; i < a.SB; ++i) { mbar_init(&full_B[i], 1); mbar_init(&empty_B[i], 1); }
-      mbar_init(tmem_full, 1);
-      fence_mbar_init();
-    }
-    __syncwarp();
-    tmem_alloc(tmem_ptr, a.tmem_cols);
-  }
-  for (int p = tid; p < HALO_PX; p += kThreads) {
-    const int hr = p / PITCH, hc = p - hr * PITCH;
-    const int h = h0 - 1 + hr, w = w0 - 1 + hc;
-    int2 e = make_int2(-1, -1);
-    if (h >= 0 && h < V.H && w >= 0 && w < V.W) {
-      e.x = view_pix_off(V.s[0], n, h, w);
-      if (V.C0 < V.C) e.y = view_pix_off(V.s[1], n, h, w);
-    }
-    table[p] = e;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  // dgrad: dz is multiplied by a power of two on the way in (so that its fp16 hi/lo split keeps ~22 bits) and
-  // the accumulator by the inverse on the way out; forward views use BN scale/shift instead (in_mul = 1).
-  const float in_mul = (V.s[0].mode == SRC_IDENTITY) ? pow2_scale_for(V.s[0].scale) : 1.f;
-  const float out_mul = 1.f / in_mul;
-
-  if (warp == 0) {
-    // =========================== MMA issuer (single elected thread) ===========================
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc(128, BN, FMT, 0, 0);
-      // A: K-major planar halo tile. LBO = plane stride (next 8 channels), SBO = halo row pitch (next
-      // 8 output pixels = next image row of the 16x8 tile). variant bit0 swaps the two (bring-up probe).
-      uint32_t a_lbo = PLANE, a_sbo = PITCH * 16;
-      uint32_t b_lbo = BN * 16, b_sbo = 128;
-      if (a.variant & 1) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; }
-      if (a.variant & 2) { uint32_t t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
-      int sb = 0; uint32_t phb = 0;
-      for (int c = 0; c < nchunks; ++c) {
-        const int sa = c % a.SA;
-        const uint32_t pha = (c / a.SA) & 1;
-        mbar_wait(&full_A[sa], pha);
-        tc_fence_after();
-        const uint32_t a_stage = smem_u32(a_base + sa * A_STAGE);
-        for (int t = 0; t < 9; ++t) {
-          mbar_wait(&full_B[sb], phb);
-          tc_fence_after();
-          const uint32_t b_stage = smem_u32(b_base + sb * B_STAGE);
-          const int dy = t / 3, dx = t - dy * 3;
-          for (int mt = 0; mt < MT; ++mt) {
-            const uint32_t d_tmem = tmem_base + mt * BN;
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-              const uint32_t a_addr = a_stage + (2 * kk) * PLANE + (dy * PITCH + dx + 8 * mt) * 16;
-              const uint32_t b_addr = b_stage + (2 * kk) * BN * 16;
-              const uint64_t a_hi = make_smem_desc(a_addr, a_lbo, a_sbo);
-              const uint64_t b_hi = make_smem_desc(b_addr, b_lbo, b_sbo);
-              const uint32_t acc = (c | t | kk) != 0;
-              umma_f16(d_tmem, a_hi, b_hi, idesc, acc);
-              if (a.nterms > 1) {
-                const uint64_t a_lo = make_smem_desc(a_addr + 4 * PLANE, a_lbo, a_sbo);
-                const uint64_t b_lo = make_smem_desc(b_addr + 4 * BN * 16, b_lbo, b_sbo);
-                umma_f16(d_tmem, a_lo, b_hi, idesc, 1);
-                umma_f16(d_tmem, a_hi, b_lo, idesc, 1);
-              }
-            }
-          }
-          umma_commit(&empty_B[sb]);
-          if (++sb == a.SB) { sb = 0; phb ^= 1; }
-        }
-        umma_commit(&empty_A[sa]);
-      }
-      umma_commit(tmem_full);
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // =========================== weight loader (bulk TMA) ===========================
-    if (elect_one()) {
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpack) +
-                            (size_t)blockIdx.y * nchunks * 9 * (size_t)(128 * BN);
-      int sb = 0; uint32_t phb = 0;
-      for (int i = 0; i < nchunks * 9; ++i) {
-        mbar_wait(&empty_B[sb], phb ^ 1);
-        mbar_arrive_expect_tx(&full_B[sb], (uint32_t)B_STAGE);
-        bulk_g2s(b_base + sb * B_STAGE, wsrc + (size_t)i * (128 * BN), (uint32_t)B_STAGE, &full_B[sb]);
-        if (++sb == a.SB) { sb = 0; phb ^= 1; }
-      }
-    }
-    __syncwarp();
-  } else {
-    // =========================== A producers: gather + BN/ReLU/pool/upsample + split ===========
-    const int ftid = tid - 64;
-    const int j = ftid & 3;            // plane (8 channels) this thread fills: fixed, 256 % 4 == 0
-    const int pbase = ftid >> 2;       // first halo pixel; stride 64 pixels
-    for (int c = 0; c < nchunks; ++c) {
-      const int sa = c % a.SA;
-      const uint32_t pha = (c / a.SA) & 1;
-      const int cch = c * 32 + j * 8;
-      const bool second = cch >= V.C0;
-      const SrcDesc& S = second ? V.s[1] : V.s[0];
-      const int cc = second ? cch - V.C0 : cch;
-      float sc[8], sh[8];
-      if (S.mode != SRC_IDENTITY) { ld8(S.scale + cc, sc); ld8(S.shift + cc, sh); }
-      mbar_wait(&empty_A[sa], pha ^ 1);
-      uint8_t* stage = a_base + sa * A_STAGE + j * PLANE;
-      auto run = [&](auto mode_tag, auto batch_tag) {
-        constexpr int MODE = decltype(mode_tag)::value;
-        constexpr int U = decltype(batch_tag)::value;
-        for (int p0 = pbase; p0 < HALO_PX; p0 += 64 * U) {
-          Raw8 raw[U][RawCount<MODE>::value];
-          int off[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int p = p0 + 64 * u;
-            off[u] = -1;
-            if (p < HALO_PX) {
-              const int2 e = table[p];
-              off[u] = second ? e.y : e.x;
-              if (off[u] >= 0) view_issue<MODE>(S, off[u], cc, raw[u]);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int p = p0 + 64 * u;
-            if (p < HALO_PX) {
-              uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-              if (off[u] >= 0) {
-                float v[8];
-                view_finish<MODE>(raw[u], sc, sh, in_mul, v);
-                split8<FMT>(v, hi, lo);
-              }
-              uint8_t* dst = stage + p * 16;
-              *reinterpret_cast<uint4*>(dst) = hi;
-              if (a.nterms > 1) *reinterpret_cast<uint4*>(dst + 4 * PLANE) = lo;
-            }
-          }
-        }
-      };
-      switch (S.mode) {
-        case SRC_IDENTITY: run(std::integral_constant<int, SRC_IDENTITY>{}, std::integral_constant<int, 4>{}); break;
-        case SRC_AFFINE_RELU_POOL: run(std::integral_constant<int, SRC_AFFINE_RELU_POOL>{}, std::integral_constant<int, 2>{}); break;
-        case SRC_AFFINE_RELU_UP: run(std::integral_constant<int, SRC_AFFINE_RELU_UP>{}, std::integral_constant<int, 4>{}); break;
-        default: run(std::integral_constant<int, SRC_AFFINE_RELU>{}, std::integral_constant<int, 4>{}); break;
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(&full_A[sa]);
-    }
-
-    // =========================== epilogue (warps 2..5) ===========================
-    if (warp < 6) {
-      const int q = warp & 3;  // TMEM lane quarter this warp may access
-      mbar_wait(tmem_full, 0);
-      tc_fence_after();
-      float* sstat = reinterpret_cast<float*>(a_base);  // [4 warps][2][BN], A stages are dead by now
-      const int row = 32 * q + lane;
-      const int r = row >> 3, cc = row & 7;
-      for (int col0 = 0; col0 < BN; col0 += 32) {
-        float csum = 0.f, csq = 0.f;
-        for (int mt = 0; mt < MT; ++mt) {
-          const int h = h0 + r, w = w0 + 8 * mt + cc;
-          const bool valid = (h < V.H) && (w < V.W);
-          uint32_t rg[32];
-          tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(mt * BN + col0), rg);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rg[i]) * out_mul;
-          if (valid) {
-            float4* dst = reinterpret_cast<float4*>(a.out + ((size_t)(n * V.H + h) * V.W + w) * a.Cout + n0 + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
-          if (a.stat_part != nullptr) {
-            float s1[32], s2[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float x = valid ? v[i] : 0.f;
-              s1[i] = x;
-              s2[i] = x * x;
-            }
-            csum += warp_transpose_sum(s1, lane);
-            csq += warp_transpose_sum(s2, lane);
-          }
-        }
-        if (a.stat_part != nullptr) {
-          sstat[(q * 2 + 0) * BN + col0 + lane] = csum;
-          sstat[(q * 2 + 1) * BN + col0 + lane] = csq;
-        }
-      }
-      if (a.stat_part != nullptr) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
-        const int et = tid - 64;                        // 0..127
-        for (int j = et; j < 2 * BN; j += 128) {
-          const int which = j / BN, col = j - which * BN;
-          const float s = sstat[(0 * 2 + which) * BN + col] + sstat[(1 * 2 + which) * BN + col] +
-                          sstat[(2 * 2 + which) * BN + col] + sstat[(3 * 2 + which) * BN + col];
-          a.stat_part[((size_t)blockIdx.x * 2 + which) * a.Cout + n0 + col] = s;
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, a.tmem_cols);
-  }
-}
-
-static int pow2_cols(int c) {
-  int p = 32;
-  while (p < c) p <<= 1;
-  return p;
-}
-
-int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* plan) {
-  TNB_REQUIRE(Cin % 32 == 0, "conv3x3: view channels %d must be a multiple of 32", Cin);
-  const int BN = pick_bn(Cout);
-  TNB_REQUIRE(BN >= 32 && BN % 16 == 0, "conv3x3: unsupported output channel count %d", Cout);
-  const int TP = nterms > 1 ? 2 : 1;
-  int MT = 512 / BN;
-  if (MT > 4) MT = 4;
-  while (MT > 1 && 8 * (MT - 1) >= W) --MT;  // do not tile wider than the image
-  int SA = 2, SB = 0;
-  size_t smem = 0;
-  for (;; --MT) {
-    const int pitch = 8 * MT + 2, halo = 18 * pitch;
-    const size_t a_stage = (size_t)TP * 4 * pad_px(halo) * 16;
-    const size_t b_stage = (size_t)TP * 64 * BN;
-    const size_t fixed = kHdrBytes + ((halo * 8 + 127) & ~127) + SA * a_stage;
-    if (fixed + 2 * b_stage <= (size_t)kMaxSmem) {
-      SB = (int)((kMaxSmem - fixed) / b_stage);
-      if (SB > 8) SB = 8;
-      smem = fixed + SB * b_stage;
-      break;
-    }
-    TNB_REQUIRE(MT > 1, "conv3x3: no shared-memory plan for Cin=%d Cout=%d", Cin, Cout);
-  }
-  plan->BN = BN; plan->MT = MT; plan->SA = SA; plan->SB = SB;
-  plan->tmem_cols = pow2_cols(MT * BN);
-  plan->smem_bytes = smem;
-  plan->tiles_h = (H + 15) / 16;
-  plan->tiles_w = (W + 8 * MT - 1) / (8 * MT);
-  (void)N;
-  return 0;
-}
-
-int conv3x3_num_stat_rows(int N, int H, int W, int Cin, int Cout, int nterms) {
-  ConvPlan p;
-  if (conv3x3_plan(N, H, W, Cin, Cout, nterms, &p)) return -1;
-  return N * p.tiles_h * p.tiles_w;
-}
-
-int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout,
-                   int nterms, int fmt, int variant, cudaStream_t st) {
-  ConvPlan p;
-  int rc = conv3x3_plan(view.N, view.H, view.W, view.C, Cout, nterms, &p);
-  if (rc) return rc;
-  ConvArgs a;
-  a.view = view; a.wpack = wpack; a.out = out; a.stat_part = stat_part;
-  a.Cout = Cout; a.BN = p.BN; a.MT = p.MT; a.SA = p.SA; a.SB = p.SB; a.nterms = nterms; a.variant = variant;
-  a.tmem_cols = p.tmem_cols; a.tiles_h = p.tiles_h; a.tiles_w = p.tiles_w;
-  dim3 grid(view.N * p.tiles_h * p.tiles_w, Cout / p.BN);
-  auto kern = fmt == 0 ? conv3x3_kernel<0> : conv3x3_kernel<1>;
-  TNB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-  ProfScope prof((view.s[0].mode == SRC_IDENTITY && view.s[0].scale != nullptr) ? PROF_CONV_DGRAD : PROF_CONV_FWD, st, view.N, view.H, view.W, view.C, Cout);
-  kern<<<grid, kThreads, p.smem_bytes, st>>>(a);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -524,42 +173,45 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   const float out_mul = 1.f / dz_mul;
 
   if (warp == 0) {
-    if (elect_one()) {
+    // whole warp runs the uniform loops (descriptor math in uniform registers); one lane issues
+    {
+      const bool lead = elect_one();
       const uint32_t idesc = make_idesc(128, NT, FMT, 1, 1);
       // MN-major planar tiles: SBO = plane stride (next 8 channels), LBO = 128 B (next 8 pixels).
       uint32_t a_lbo = 128, a_sbo = DZPL, b_lbo = 128, b_sbo = VPL;
       if (a.variant & 1) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; }
       if (a.variant & 2) { uint32_t t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
+      const uint64_t a_desc0 = make_smem_desc(smem_u32(st_base), a_lbo, a_sbo);
+      const uint64_t b_desc0 = make_smem_desc(smem_u32(st_base) + DZ_BYTES, b_lbo, b_sbo);
+      const uint32_t stage16 = STAGE >> 4, a_lo16 = (16 * DZPL) >> 4, b_lo16 = (NPL * VPL) >> 4;
       int it = 0;
       for (int kt = kt0; kt < kt1; ++kt, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t dz_s = smem_u32(st_base + s * STAGE);
-        const uint32_t v_s = dz_s + DZ_BYTES;
+        const uint64_t a_st = a_desc0 + (uint64_t)(s * stage16);
+        const uint64_t b_st = b_desc0 + (uint64_t)(s * stage16);
         for (int r = 0; r < kWgTileH; ++r) {
-          const uint32_t a_addr = dz_s + (r * 16) * 16;
-          const uint64_t a_hi = make_smem_desc(a_addr, a_lbo, a_sbo);
-          const uint64_t a_lo = make_smem_desc(a_addr + 16 * DZPL, a_lbo, a_sbo);
+          const uint64_t a_hi = a_st + (uint64_t)(r * 16);
+          const uint32_t acc = (it | r) != 0;
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             const int dy = t / 3, dx = t % 3;
-            const uint32_t b_addr = v_s + ((r + dy) * kWgHaloW + dx) * 16;
-            const uint64_t b_hi = make_smem_desc(b_addr, b_lbo, b_sbo);
+            const uint64_t b_hi = b_st + (uint64_t)((r + dy) * kWgHaloW + dx);
             const uint32_t d_tmem = tmem_base + t * NT;
-            const uint32_t acc = (it | r) != 0;
-            umma_f16(d_tmem, a_hi, b_hi, idesc, acc);
-            if (a.nterms > 1) {
-              const uint64_t b_lo = make_smem_desc(b_addr + NPL * VPL, b_lbo, b_sbo);
-              umma_f16(d_tmem, a_lo, b_hi, idesc, 1);
-              umma_f16(d_tmem, a_hi, b_lo, idesc, 1);
+            if (lead) {
+              umma_f16(d_tmem, a_hi, b_hi, idesc, acc);
+              if (a.nterms > 1) {
+                umma_f16(d_tmem, a_hi + a_lo16, b_hi, idesc, 1);
+                umma_f16(d_tmem, a_hi, b_hi + b_lo16, idesc, 1);
+              }
             }
           }
         }
-        umma_commit(&empty[s]);
+        if (lead) umma_commit(&empty[s]);
       }
-      umma_commit(tmem_full);
+      if (lead) umma_commit(tmem_full);
     }
     __syncwarp();
   } else if (warp >= 2) {
@@ -651,10 +303,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
           }
         };
         switch (VS.mode) {
-          case SRC_IDENTITY: run(std::integral_constant<int, SRC_IDENTITY>{}, std::integral_constant<int, 4>{}); break;
-          case SRC_AFFINE_RELU_POOL: run(std::integral_constant<int, SRC_AFFINE_RELU_POOL>{}, std::integral_constant<int, 2>{}); break;
-          case SRC_AFFINE_RELU_UP: run(std::integral_constant<int, SRC_AFFINE_RELU_UP>{}, std::integral_constant<int, 4>{}); break;
-          default: run(std::integral_constant<int, SRC_AFFINE_RELU>{}, std::integral_constant<int, 4>{}); break;
+          case SRC_IDENTITY: run(std::integral_constant<int, SRC_IDENTITY>{}, std::integral_constant<int, 2>{}); break;
+          case SRC_AFFINE_RELU_POOL: run(std::integral_constant<int, SRC_AFFINE_RELU_POOL>{}, std::integral_constant<int, 1>{}); break;
+          case SRC_AFFINE_RELU_UP: run(std::integral_constant<int, SRC_AFFINE_RELU_UP>{}, std::integral_constant<int, 2>{}); break;
+          default: run(std::integral_constant<int, SRC_AFFINE_RELU>{}, std::integral_constant<int, 2>{}); break;
         }
       }
       fence_proxy_async_smem();

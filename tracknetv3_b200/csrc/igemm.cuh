@@ -124,8 +124,13 @@ TNB_DEVINL float pow2_scale_for(const float* amax_ptr) {
 }
 
 // ---- host-side launchers (igemm.cu) ----------------------------------------------------------
+__host__ __device__ inline int pad_px(int px) {  // plane stride = 2 (mod 8) pixels -> conflict-free fill stores
+  int r = px & 7;
+  return px + ((2 - r) & 7);
+}
+
 struct ConvPlan {
-  int BN, MT, SA, SB, tmem_cols;
+  int BN, MT, SA, SB, nbuf, tmem_cols;
   size_t smem_bytes;
   int tiles_h, tiles_w;
 };

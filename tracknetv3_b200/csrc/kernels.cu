@@ -260,16 +260,17 @@ template <bool APPLY>
 __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnBwdArgs a) {
   const int CQ = a.C >> 2;
   const int Hw = (a.H + 1) >> 1, Ww = (a.W + 1) >> 1;
-  const long long items = (long long)a.N * Hw * Ww * CQ;
-  const long long stride = (long long)gridDim.x * blockDim.x;
+  const unsigned items = (unsigned)a.N * Hw * Ww * CQ;  // < 2^31, checked by the launcher
+  const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned cq_shift = 31 - __clz(CQ);             // CQ is a power of two (256 % CQ == 0)
   float4 acc1 = make_float4(0, 0, 0, 0), acc2 = make_float4(0, 0, 0, 0);
   float amax = 0.f;
-  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += stride) {
-    const int cq = (int)(it % CQ);
-    long long r = it / CQ;
-    const int ww = (int)(r % Ww); r /= Ww;
-    const int wh = (int)(r % Hw);
-    const int n = (int)(r / Hw);
+  for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += stride) {
+    const int cq = (int)(it & (CQ - 1));
+    unsigned r = it >> cq_shift;
+    const int ww = (int)(r % (unsigned)Ww); r /= (unsigned)Ww;
+    const int wh = (int)(r % (unsigned)Hw);
+    const int n = (int)(r / (unsigned)Hw);
     const int c = cq * 4;
     const float4 sc = ld4(a.scale + c), sh = ld4(a.shift + c), mu = ld4(a.mean + c), is = ld4(a.invstd + c);
     float4 m1 = make_float4(0, 0, 0, 0), m2 = m1;
@@ -387,6 +388,7 @@ int bn_bwd_num_blocks(int N, int H, int W, int C) {
 }
 static int bn_bwd_check(const BnBwdArgs& a) {
   TNB_REQUIRE(a.C % 4 == 0 && 256 % (a.C / 4) == 0, "bn_bwd: unsupported channel count %d", a.C);
+  TNB_REQUIRE((long long)a.N * ((a.H + 1) / 2) * ((a.W + 1) / 2) * (a.C / 4) < (1ll << 31), "bn_bwd: tensor too large");
   return 0;
 }
 int launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t st) {
