@@ -271,8 +271,8 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
-            "dtype": "fp16x3 fwd / bf16x3 bwd split operands, fp32 accumulate (fp32-faithful)" if terms == 3
-            else "fp16 fwd / bf16 bwd single pass, fp32 accumulate (TF32-class)",
+            "dtype": "fp16x3 (3-term hi/lo split operands, fp32 accumulate: fp32-faithful)" if terms == 3
+            else "fp16 single pass, fp32 accumulate (TF32-class)",
             "data": "synthetic",
             "config": {"workload": "TrackNet seq_len=8 bg=concat (27->8 ch) 288x512 fwd+WBCE+bwd, BASELINE configs[1]",
                        "global_batch": BATCH * world, "per_gpu_batch": BATCH, "parallelism": f"dp{world}",
