@@ -29,7 +29,8 @@ extern "C" {
 /* ---- descriptors -------------------------------------------------------------------------- */
 
 /* How one channel-slice of a conv layer's logical input is produced from a stored tensor. */
-enum { TNB_SRC_IDENTITY = 0, TNB_SRC_AFFINE_RELU = 1, TNB_SRC_AFFINE_RELU_POOL = 2, TNB_SRC_AFFINE_RELU_UP = 3 };
+enum { TNB_SRC_IDENTITY = 0, TNB_SRC_AFFINE_RELU = 1, TNB_SRC_AFFINE_RELU_POOL = 2, TNB_SRC_AFFINE_RELU_UP = 3,
+       TNB_SRC_PRESPLIT = 4 /* ptr holds the "pre-split" 16-bit format, see tnb_presplit_bf16 */ };
 typedef struct {
   const float* ptr;   /* [N, Hs, Ws, C] fp32 NHWC */
   const float* scale; /* [C] fused BatchNorm scale (gamma * invstd). IDENTITY: NULL, or a pointer to ONE float =
@@ -64,6 +65,7 @@ typedef struct {
   float* dz;         /* apply:  [N,H,W,C] */
   float inv_count;
   float* amax;       /* apply, optional: device scalar, atomically raised to max|dz| (zero it first) */
+  int dz_format;     /* apply: 0 = fp32 [N,H,W,C]; 1 = pre-split bf16 (same byte size, see tnb_presplit_bf16) */
 } tnb_bnbwd_t;
 
 typedef struct {
@@ -72,7 +74,7 @@ typedef struct {
   int out_dim;
   int training;    /* 1: BatchNorm uses batch statistics and updates running stats (model.train()) */
   int fwd_terms;   /* 3 = fp16 hi/lo split, fp32-faithful (default); 1 = single fp16 pass (TF32-class) */
-  int bwd_terms;   /* 3 = fp16 hi/lo split of power-of-two pre-scaled gradients (default); 1 = single pass */
+  int bwd_terms;   /* 3 = bf16 hi/lo split (default; gradients need fp32's exponent range); 1 = single bf16 pass */
   int variant;     /* bring-up probe bits; 0 in production */
   float bn_eps;    /* 1e-5 */
   float bn_momentum; /* 0.1 */
@@ -87,6 +89,13 @@ int tnb_abi_version(void);
 /* NCHW fp32 -> NHWC fp32 with channels zero-padded to cpad. Replaces the layout the reference feeds
  * to Conv2d directly (train.py:86 `x.float().cuda()`, model.py:58). */
 int tnb_pack_nchw_to_nhwc(const float* x_nchw, float* out_nhwc, int n, int c, int h, int w, int cpad, void* stream);
+
+/* "Pre-split" tensor format: every fp32 value x is stored as two bf16 numbers hi = rn(x), lo = rn(x - hi)
+ * (x ~ hi + lo to 2^-17), laid out [pixel][C/8][2 (hi, lo)][8 channels] so that a (pixel, 8-channel) operand
+ * fragment of both terms is one contiguous 32-byte read. Same byte size as the fp32 tensor. Gradient tensors
+ * (dz) are produced in this format by tnb_bn_relu_bwd_apply(dz_format = 1) and consumed by dgrad
+ * (TNB_SRC_PRESPLIT view) and wgrad without any per-element arithmetic in the consumers. */
+int tnb_presplit_bf16(const float* x_nhwc, void* out, long long npixels, int c, void* stream);
 
 /* Weight pre-packing for the tcgen05 kernels. mode 0: forward operand, mode 1: dgrad operand (rotated,
  * transposed). fmt 0: fp16 split, 1: bf16 split. Source is the reference's canonical OIHW parameter
@@ -103,10 +112,10 @@ int tnb_conv3x3_fwd(const tnb_view_t* view, const uint16_t* wpack, float* out, f
                     int terms, int fmt, int variant, void* stream);
 
 /* Weight gradient of the same convolution (autograd of model.py:13 via train.py:95):
- * dw[cout][cin_real][3][3] += sum dz * view. dw must be zeroed by the caller. dz_amax: optional device scalar
- * max|dz| enabling power-of-two pre-scaling (see tnb_src_t.scale). */
-int tnb_conv3x3_wgrad(const tnb_view_t* view, const float* dz, const float* dz_amax, float* dw_oihw, int cout,
-                      int cin_real, int terms, int fmt, int variant, void* stream);
+ * dw[cout][cin_real][3][3] += sum dz * view. dw must be zeroed by the caller. dz is in the pre-split bf16 format
+ * ([N,H,W,cout] logical); the view operand is split to bf16 on the fly. */
+int tnb_conv3x3_wgrad(const tnb_view_t* view, const void* dz_presplit, float* dw_oihw, int cout, int cin_real,
+                      int terms, int variant, void* stream);
 
 /* BatchNorm2d statistics -> fused affine + running-stat update (model.py:9; torch defaults eps 1e-5,
  * momentum 0.1, unbiased running_var). training==0 uses the running statistics (model.eval()). */

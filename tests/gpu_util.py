@@ -67,13 +67,28 @@ def conv3x3(view, w_oihw, cout, terms=3, fmt=0, variant=0, stats=False, mode=0):
     return out, part
 
 
-def wgrad3x3(view, dz_nhwc, cout, cin_real, terms=3, fmt=0, variant=0, scaled=True):
-    """fmt 0 + scaled: the production configuration (fp16 split of power-of-two pre-scaled dz)."""
+def presplit(t_nhwc):
+    """fp32 NHWC -> the pre-split bf16 format (same byte size); returned as an opaque uint8 tensor."""
+    L = lib()
+    n, h, w, c = t_nhwc.shape
+    out = torch.empty(t_nhwc.numel() * 4, dtype=torch.uint8, device=DEV)
+    _lib.check(L.tnb_presplit_bf16(t_nhwc.data_ptr(), out.data_ptr(), n * h * w, c, st()))
+    return out
+
+
+def unsplit(buf, shape_nhwc):
+    """inverse of presplit (hi + lo) for checking: uint8 buffer -> fp32 NHWC."""
+    n, h, w, c = shape_nhwc
+    v = buf.view(torch.bfloat16).reshape(n, h, w, c // 8, 2, 8).float()
+    return (v[..., 0, :] + v[..., 1, :]).reshape(n, h, w, c)
+
+
+def wgrad3x3(view, dz_nhwc, cout, cin_real, terms=3, variant=0):
+    """production configuration: dz pre-split to bf16, view split on the fly."""
     L = lib()
     dw = torch.zeros((cout, cin_real, 3, 3), device=DEV)
-    amax = dz_nhwc.abs().max().reshape(1).contiguous() if scaled else None
-    _lib.check(L.tnb_conv3x3_wgrad(C.byref(view), dz_nhwc.data_ptr(), amax.data_ptr() if scaled else None,
-                                   dw.data_ptr(), cout, cin_real, terms, fmt, variant, st()))
+    dzs = presplit(dz_nhwc)
+    _lib.check(L.tnb_conv3x3_wgrad(C.byref(view), dzs.data_ptr(), dw.data_ptr(), cout, cin_real, terms, variant, st()))
     torch.cuda.synchronize()
     return dw
 

@@ -91,27 +91,27 @@ def test_conv3x3_fused_views(mode):
     wz = torch.zeros(64, xin.shape[1], 3, 3, requires_grad=True)
     (F.conv2d(xin, wz, padding=1) * dz).sum().backward()
     dw = G.wgrad3x3(G.make_view(srcs, n, h, w), dev(dz.permute(0, 2, 3, 1)), 64, xin.shape[1])
-    assert G.rel_err(dw, wz.grad) < 2e-5
+    assert G.rel_err(dw, wz.grad) < 2e-4
     del keep
 
 
 @pytest.mark.parametrize("terms", [3, 1])
 @pytest.mark.parametrize("n,h,w,cin,cout", [(1, 16, 16, 64, 64), (2, 20, 24, 192, 64), (1, 16, 16, 128, 256)])
 def test_conv3x3_dgrad(n, h, w, cin, cout, terms):
-    """dIn = conv(dz, rot180(W)^T) through the same kernel with mode-1 packed weights; dz (~1e-6) is pre-scaled
-    by a power of two from its device-side max so that the fp16 hi/lo split keeps ~22 bits."""
+    """dIn = conv(dz, rot180(W)^T) through the same kernel: weights packed with mode 1 (bf16), dz (~1e-6, needs
+    fp32's exponent range) supplied in the pre-split bf16 format so that the operand fill is a pure copy."""
     dz = _rand(n, cout, h, w, seed=11, scale=1e-6)
     wt = _rand(cout, cin, 3, 3, seed=12, scale=0.2)
     ref = F.conv_transpose2d(dz, wt, padding=1)
     t = G.nhwc(dz)
-    amax = t.abs().max().reshape(1).contiguous()
-    src = G.make_src(t)
-    src.scale = amax.data_ptr()
-    out, _ = G.conv3x3(G.make_view([src], n, h, w), wt.to(G.DEV), cin, terms=terms, fmt=0, mode=1)
-    assert G.rel_err(G.nchw(out), ref) < (2e-5 if terms == 3 else 4e-3)
-    # bf16 split without scaling is the wide-range alternative: ~16 bits
-    out, _ = G.conv3x3(G.make_view([G.make_src(t)], n, h, w), wt.to(G.DEV), cin, terms=3, fmt=1, mode=1)
-    assert G.rel_err(G.nchw(out), ref) < 2e-4
+    ts = G.presplit(t)
+    assert G.max_abs(G.unsplit(ts, t.shape), t) < 2e-5 * 1e-6  # hi + lo reproduces dz to ~2^-17
+    src = _lib.Src(ptr=ts.data_ptr(), scale=None, shift=None, C=cout, Hs=h, Ws=w, mode=_lib.SRC_PRESPLIT)
+    out, _ = G.conv3x3(G.make_view([src], n, h, w), wt.to(G.DEV), cin, terms=terms, fmt=1, mode=1)
+    assert G.rel_err(G.nchw(out), ref) < (2e-4 if terms == 3 else 2e-2)
+    # identity (fp32) source with on-the-fly bf16 split gives the same numbers
+    out2, _ = G.conv3x3(G.make_view([G.make_src(t)], n, h, w), wt.to(G.DEV), cin, terms=terms, fmt=1, mode=1)
+    assert G.rel_err(out2, out) < 1e-6
 
 
 @pytest.mark.parametrize("terms", [3, 1])
@@ -119,8 +119,9 @@ def test_conv3x3_dgrad(n, h, w, cin, cout, terms):
     (1, 8, 16, 32, 27, 64),      # first layer: 27 real channels, one K tile
     (2, 16, 32, 64, 64, 64),     # Cout 64 (half of the 128 accumulator rows unused)
     (1, 20, 24, 64, 64, 128),    # ragged tiles
-    (1, 16, 16, 192, 192, 64),   # NT = 48
-    (1, 8, 16, 128, 128, 256),   # two co tiles
+    (1, 16, 16, 192, 192, 64),   # NT = 96, two ci tiles
+    (1, 8, 16, 128, 128, 256),   # two co tiles, NT = 128
+    (2, 12, 40, 256, 256, 128),  # ragged 4x16 K tiles, two ci tiles of 128
 ])
 def test_conv3x3_wgrad(n, h, w, cin, cin_real, cout, terms):
     x = _rand(n, cin, h, w, seed=13)
@@ -131,7 +132,7 @@ def test_conv3x3_wgrad(n, h, w, cin, cin_real, cout, terms):
     (F.conv2d(xr, wt, padding=1) * dz).sum().backward()
     t, d = G.nhwc(x), G.nhwc(dz)
     dw = G.wgrad3x3(G.make_view([G.make_src(t)], n, h, w), d, cout, cin_real, terms=terms)
-    assert G.rel_err(dw, wt.grad) < (2e-5 if terms == 3 else 4e-3)
+    assert G.rel_err(dw, wt.grad) < (2e-4 if terms == 3 else 2e-2)
 
 
 def test_conv3x3_full_resolution_layer_vs_torch_cuda():

@@ -208,12 +208,19 @@ def test_bn_relu_backward_with_gradient_routing(consumers):
     args.inv_count = 1.0 / (n * h * w)
     amax = torch.zeros(1, device=G.DEV)
     args.amax = amax.data_ptr()
+    args.dz_format = 0
     _lib.check(L.tnb_bn_relu_bwd_reduce(C.byref(args), G.st()))
     _lib.check(L.tnb_bn_relu_bwd_finalize(part.data_ptr(), rows, c, sums.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), G.st()))
     _lib.check(L.tnb_bn_relu_bwd_apply(C.byref(args), G.st()))
     torch.cuda.synchronize()
     assert G.rel_err(G.nchw(dz), z.grad) < 2e-4
-    assert amax.item() == dz.abs().max().item()  # feeds the power-of-two pre-scaling of dgrad / wgrad
+    assert amax.item() == dz.abs().max().item()
+    # production format: the same dz emitted pre-split (bf16 hi/lo) for the dgrad / wgrad operand fills
+    dzs = torch.zeros(n * h * w * c * 4, dtype=torch.uint8, device=G.DEV)
+    args.dz, args.dz_format, args.amax = dzs.data_ptr(), 1, None
+    _lib.check(L.tnb_bn_relu_bwd_apply(C.byref(args), G.st()))
+    torch.cuda.synchronize()
+    assert G.max_abs(G.unsplit(dzs, (n, h, w, c)), dz) <= 2e-5 * dz.abs().max().item()
     # d gamma / d beta from the same reductions (checked through a second autograd pass)
     z2 = z.detach().clone(); g2 = gamma.clone().requires_grad_(True); b2 = beta.clone().requires_grad_(True)
     a2 = F.relu(F.batch_norm(z2, None, None, g2, b2, True, 0.1, 1e-5))

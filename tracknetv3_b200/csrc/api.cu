@@ -30,6 +30,9 @@ int tnb_pack_nchw_to_nhwc(const float* x, float* out, int n, int c, int h, int w
   TNB_REQUIRE(cpad % 4 == 0 && cpad >= c, "pack_nchw_to_nhwc: bad cpad %d for c %d", cpad, c);
   return launch_pack_input(x, out, n, c, h, w, cpad, ST(stream));
 }
+int tnb_presplit_bf16(const float* x, void* out, long long npixels, int c, void* stream) {
+  return launch_presplit_bf16(x, out, npixels, c, ST(stream));
+}
 size_t tnb_conv3x3_wpack_elems(int k_side, int n_side) { return conv3x3_wpack_elems(k_side, n_side); }
 int tnb_conv3x3_pack_weights(const float* w, uint16_t* out, int cout, int cin, int mode, int fmt, void* stream) {
   // the tile width must match what the conv launcher will pick for this N side
@@ -45,9 +48,9 @@ int tnb_conv3x3_fwd(const tnb_view_t* view, const uint16_t* wpack, float* out, f
                     int fmt, int variant, void* stream) {
   return launch_conv3x3(*view, wpack, out, stat_part, cout, terms, fmt, variant, ST(stream));
 }
-int tnb_conv3x3_wgrad(const tnb_view_t* view, const float* dz, const float* dz_amax, float* dw, int cout,
-                      int cin_real, int terms, int fmt, int variant, void* stream) {
-  return launch_wgrad3x3(*view, dz, dz_amax, dw, cout, cin_real, terms, fmt, variant, ST(stream));
+int tnb_conv3x3_wgrad(const tnb_view_t* view, const void* dz_presplit, float* dw, int cout, int cin_real, int terms,
+                      int variant, void* stream) {
+  return launch_wgrad3x3(*view, dz_presplit, dw, cout, cin_real, terms, variant, ST(stream));
 }
 int tnb_bn_finalize(const float* part, int rows, double count, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, float momentum, float eps, int training, float* scale,

@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
         const SrcDesc& S = second ? V.s[1] : V.s[0];
         const int cc = second ? cch - V.C0 : cch;
         float sc[8], sh[8];
-        if (S.mode != SRC_IDENTITY) { ld8(S.scale + cc, sc); ld8(S.shift + cc, sh); }
+        if (S.mode != SRC_IDENTITY && S.mode != SRC_PRESPLIT) { ld8(S.scale + cc, sc); ld8(S.shift + cc, sh); }
         const bool pf_next = (c + 1 < nchunks) && (cc - (j * 8) + 32 < S.C);  // next chunk comes from the same source
         mbar_wait(&empty_A[sa], pha ^ 1);
         uint8_t* stage = a_base + sa * A_STAGE + j * PLANE;
@@ -346,9 +346,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
               if (p < HALO_PX) {
                 uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
                 if (off[u] >= 0) {
-                  float v[8];
-                  view_finish<MODE>(raw[u], sc, sh, in_mul, v);
-                  split8<FMT>(v, hi, lo);
+                  if (MODE == SRC_PRESPLIT) {  // already (hi, lo): pure copy, no arithmetic
+                    hi = *reinterpret_cast<const uint4*>(&raw[u][0].a);
+                    lo = *reinterpret_cast<const uint4*>(&raw[u][0].b);
+                  } else {
+                    float v[8];
+                    view_finish<MODE>(raw[u], sc, sh, in_mul, v);
+                    split8<FMT>(v, hi, lo);
+                  }
                 }
                 uint8_t* dst = stage + p * 16;
                 *reinterpret_cast<uint4*>(dst) = hi;
@@ -361,6 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
           case SRC_IDENTITY: run(std::integral_constant<int, SRC_IDENTITY>{}, std::integral_constant<int, 4>{}); break;
           case SRC_AFFINE_RELU_POOL: run(std::integral_constant<int, SRC_AFFINE_RELU_POOL>{}, std::integral_constant<int, 1>{}); break;
           case SRC_AFFINE_RELU_UP: run(std::integral_constant<int, SRC_AFFINE_RELU_UP>{}, std::integral_constant<int, 4>{}); break;
+          case SRC_PRESPLIT: run(std::integral_constant<int, SRC_PRESPLIT>{}, std::integral_constant<int, 4>{}); break;
           default: run(std::integral_constant<int, SRC_AFFINE_RELU>{}, std::integral_constant<int, 4>{}); break;
         }
         fence_proxy_async_smem();
@@ -455,7 +461,7 @@ int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, floa
   const int grid = a.nwork < num_sms() ? a.nwork : num_sms();
   auto kern = fmt == 0 ? conv3x3_kernel<0> : conv3x3_kernel<1>;
   TNB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-  ProfScope prof((view.s[0].mode == SRC_IDENTITY && view.s[0].scale != nullptr) ? PROF_CONV_DGRAD : PROF_CONV_FWD, st,
+  ProfScope prof(view.s[0].mode == SRC_PRESPLIT ? PROF_CONV_DGRAD : PROF_CONV_FWD, st,
                  view.N, view.H, view.W, view.C, Cout);
   kern<<<grid, kThreads, p.smem_bytes, st>>>(a);
   TNB_CHECK_CUDA(cudaGetLastError());

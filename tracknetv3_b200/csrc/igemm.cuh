@@ -13,7 +13,8 @@ enum SrcMode : int {
   SRC_IDENTITY = TNB_SRC_IDENTITY,                  // plain NHWC fp32 tensor (packed network input, or dz)
   SRC_AFFINE_RELU = TNB_SRC_AFFINE_RELU,            // relu(z*scale + shift)                  (model.py:12-16)
   SRC_AFFINE_RELU_POOL = TNB_SRC_AFFINE_RELU_POOL,  // maxpool2x2(relu(z*scale+shift)), z is 2H x 2W (model.py:59,61,63)
-  SRC_AFFINE_RELU_UP = TNB_SRC_AFFINE_RELU_UP       // nearest x2 upsample of relu(z*scale+shift)  (model.py:65,67,69)
+  SRC_AFFINE_RELU_UP = TNB_SRC_AFFINE_RELU_UP,      // nearest x2 upsample of relu(z*scale+shift)  (model.py:65,67,69)
+  SRC_PRESPLIT = TNB_SRC_PRESPLIT                   // already (hi, lo) bf16, [pixel][C/8][2][8]: pure copy
 };
 using SrcDesc = tnb_src_t;    // see include/tracknet_b200.h
 using ViewDesc = tnb_view_t;
@@ -80,6 +81,8 @@ TNB_DEVINL void raw_to_arr(const Raw8& r, float (&v)[8]) {
 template <int MODE> struct RawCount { static constexpr int value = (MODE == SRC_AFFINE_RELU_POOL) ? 4 : 1; };
 template <int MODE>
 TNB_DEVINL void view_issue(const SrcDesc& s, int poff, int c, Raw8 (&raw)[RawCount<MODE>::value]) {
+  // fp32 and pre-split tensors have the same 4 bytes per element, and the 8 channels [c, c+8) of one pixel are the
+  // same 32 contiguous bytes in both: raw.a = channels c..c+3 (fp32) or the hi term (pre-split), raw.b = the rest / lo
   const float* p = s.ptr + (size_t)poff * s.C + c;
   raw[0] = ld_raw8(p);
   if (MODE == SRC_AFFINE_RELU_POOL) {
@@ -94,7 +97,7 @@ TNB_DEVINL void view_finish(const Raw8 (&raw)[RawCount<MODE>::value], const floa
                             float mul, float (&v)[8]) {
   float a[8];
   raw_to_arr(raw[0], a);
-  if (MODE == SRC_IDENTITY) {
+  if (MODE == SRC_IDENTITY || MODE == SRC_PRESPLIT) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = a[i] * mul;
     return;
@@ -143,7 +146,7 @@ int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, floa
                    int nterms, int fmt, int variant, cudaStream_t st);
 int conv3x3_num_stat_rows(int N, int H, int W, int Cin, int Cout, int nterms);
 
-int launch_wgrad3x3(const ViewDesc& view, const float* dz, const float* dz_amax, float* dw_oihw, int Cout, int CinReal,
-                    int nterms, int fmt, int variant, cudaStream_t st);
+int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw_oihw, int Cout, int CinReal, int nterms,
+                    int variant, cudaStream_t st);
 
 }  // namespace tnb

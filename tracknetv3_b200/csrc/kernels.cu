@@ -256,7 +256,8 @@ int launch_predictor_bwd(const SrcDesc& src, int N, int H, int W, const float* w
 TNB_DEVINL float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 TNB_DEVINL float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-template <bool APPLY>
+// CFG 0: one GRAD_SAME consumer; CFG 1: {GRAD_POOL, GRAD_SAME}; CFG 2: anything else (generic gather)
+template <bool APPLY, int CFG>
 __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnBwdArgs a) {
   const int CQ = a.C >> 2;
   const int Hw = (a.H + 1) >> 1, Ww = (a.W + 1) >> 1;
@@ -282,56 +283,84 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnB
     }
     float4 z[4], act[4], dy[4];
     bool valid[4];
+    size_t zoff[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int h = 2 * wh + (k >> 1), w = 2 * ww + (k & 1);
       valid[k] = (h < a.H) && (w < a.W);
+      zoff[k] = ((size_t)(n * a.H + h) * a.W + w);
       dy[k] = make_float4(0, 0, 0, 0);
       z[k] = make_float4(0, 0, 0, 0);
-      if (valid[k]) z[k] = ld4(a.z + ((size_t)(n * a.H + h) * a.W + w) * a.C + c);
-      act[k] = make_float4(fmaf(z[k].x, sc.x, sh.x), fmaf(z[k].y, sc.y, sh.y), fmaf(z[k].z, sc.z, sh.z),
-                           fmaf(z[k].w, sc.w, sh.w));
     }
-    for (int gi = 0; gi < a.ng; ++gi) {
-      const GradSrc& g = a.g[gi];
-      if (g.mode == GRAD_SAME) {
+    float4 gp = make_float4(0, 0, 0, 0);
+    bool has_pool = false;
+    if (CFG == 0 || CFG == 1) {
+      // fast paths (one same-resolution consumer, optionally preceded by a max-pool consumer): every global load of
+      // the item is issued before the first use, so one memory latency is paid per item instead of two
+      const GradSrc& gs = a.g[CFG == 1 ? 1 : 0];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int h = 2 * wh + (k >> 1), w = 2 * ww + (k & 1);
-          if (valid[k]) dy[k] = f4add(dy[k], ld4(g.ptr + ((size_t)(n * g.Hs + h) * g.Ws + w) * g.C + g.coff + c));
-        }
-      } else if (g.mode == GRAD_UP) {
+      for (int k = 0; k < 4; ++k)
+        if (valid[k]) z[k] = ld4(a.z + zoff[k] * a.C + c);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int h = 2 * wh + (k >> 1), w = 2 * ww + (k & 1);
-          if (valid[k]) {
+      for (int k = 0; k < 4; ++k)
+        if (valid[k]) dy[k] = ld4(gs.ptr + zoff[k] * gs.C + gs.coff + c);
+      if (CFG == 1) {
+        const GradSrc& g = a.g[0];
+        has_pool = wh < g.Hs && ww < g.Ws && valid[3];
+        if (has_pool) gp = ld4(g.ptr + ((size_t)(n * g.Hs + wh) * g.Ws + ww) * g.C + g.coff + c);
+      }
+    } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int hh = 2 * h + (j >> 1), wv = 2 * w + (j & 1);
-              dy[k] = f4add(dy[k], ld4(g.ptr + ((size_t)(n * g.Hs + hh) * g.Ws + wv) * g.C + g.coff + c));
-            }
-          }
-        }
-      } else {  // GRAD_POOL: the consumer saw maxpool2x2(relu(act)); first maximum in window scan order wins
-        if (wh < g.Hs && ww < g.Ws && valid[3]) {
-          const float4 gp = ld4(g.ptr + ((size_t)(n * g.Hs + wh) * g.Ws + ww) * g.C + g.coff + c);
-          int ix = 0, iy = 0, iz = 0, iw = 0;
-          float bx = act[0].x, by = act[0].y, bz = act[0].z, bw = act[0].w;
-#pragma unroll
-          for (int k = 1; k < 4; ++k) {
-            if (act[k].x > bx) { bx = act[k].x; ix = k; }
-            if (act[k].y > by) { by = act[k].y; iy = k; }
-            if (act[k].z > bz) { bz = act[k].z; iz = k; }
-            if (act[k].w > bw) { bw = act[k].w; iw = k; }
-          }
+      for (int k = 0; k < 4; ++k)
+        if (valid[k]) z[k] = ld4(a.z + zoff[k] * a.C + c);
+      for (int gi = 0; gi < a.ng; ++gi) {
+        const GradSrc& g = a.g[gi];
+        if (g.mode == GRAD_SAME) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            if (ix == k) dy[k].x += gp.x;
-            if (iy == k) dy[k].y += gp.y;
-            if (iz == k) dy[k].z += gp.z;
-            if (iw == k) dy[k].w += gp.w;
+            const int h = 2 * wh + (k >> 1), w = 2 * ww + (k & 1);
+            if (valid[k]) dy[k] = f4add(dy[k], ld4(g.ptr + ((size_t)(n * g.Hs + h) * g.Ws + w) * g.C + g.coff + c));
           }
+        } else if (g.mode == GRAD_UP) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int h = 2 * wh + (k >> 1), w = 2 * ww + (k & 1);
+            if (valid[k]) {
+              float4 t[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int hh = 2 * h + (j >> 1), wv = 2 * w + (j & 1);
+                t[j] = ld4(g.ptr + ((size_t)(n * g.Hs + hh) * g.Ws + wv) * g.C + g.coff + c);
+              }
+              dy[k] = f4add(dy[k], f4add(f4add(t[0], t[1]), f4add(t[2], t[3])));
+            }
+          }
+        } else {  // GRAD_POOL
+          has_pool = wh < g.Hs && ww < g.Ws && valid[3];
+          if (has_pool) gp = ld4(g.ptr + ((size_t)(n * g.Hs + wh) * g.Ws + ww) * g.C + g.coff + c);
         }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      act[k] = make_float4(fmaf(z[k].x, sc.x, sh.x), fmaf(z[k].y, sc.y, sh.y), fmaf(z[k].z, sc.z, sh.z),
+                           fmaf(z[k].w, sc.w, sh.w));
+    if (has_pool) {  // the consumer saw maxpool2x2(relu(act)); first maximum in window scan order wins
+      int ix = 0, iy = 0, iz = 0, iw = 0;
+      float bx = act[0].x, by = act[0].y, bz = act[0].z, bw = act[0].w;
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        if (act[k].x > bx) { bx = act[k].x; ix = k; }
+        if (act[k].y > by) { by = act[k].y; iy = k; }
+        if (act[k].z > bz) { bz = act[k].z; iz = k; }
+        if (act[k].w > bw) { bw = act[k].w; iw = k; }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (ix == k) dy[k].x += gp.x;
+        if (iy == k) dy[k].y += gp.y;
+        if (iz == k) dy[k].z += gp.z;
+        if (iw == k) dy[k].w += gp.w;
       }
     }
 #pragma unroll
@@ -351,7 +380,18 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnB
         o.y = sc.y * (d.y - m1.y - xh.y * m2.y);
         o.z = sc.z * (d.z - m1.z - xh.z * m2.z);
         o.w = sc.w * (d.w - m1.w - xh.w * m2.w);
-        *reinterpret_cast<float4*>(a.dz + ((size_t)(n * a.H + h) * a.W + w) * a.C + c) = o;
+        const size_t pix = (size_t)(n * a.H + h) * a.W + w;
+        if (a.dz_format == 0) {
+          *reinterpret_cast<float4*>(a.dz + pix * a.C + c) = o;
+        } else {
+          // pre-split bf16: [pixel][C/8][2][8]; this thread owns channels c..c+3 = half (cq & 1) of plane cq >> 1
+          uint32_t h01, l01, h23, l23;
+          split2<1>(o.x, o.y, h01, l01);
+          split2<1>(o.z, o.w, h23, l23);
+          uint8_t* base = reinterpret_cast<uint8_t*>(a.dz) + (pix * (a.C >> 3) + (cq >> 1)) * 32 + (cq & 1) * 8;
+          *reinterpret_cast<uint2*>(base) = make_uint2(h01, h23);
+          *reinterpret_cast<uint2*>(base + 16) = make_uint2(l01, l23);
+        }
         amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
       } else {
         acc1 = f4add(acc1, d);
@@ -386,6 +426,12 @@ int bn_bwd_num_blocks(int N, int H, int W, int C) {
   const long long items = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
   return min(cdiv(items, 256), 148 * 8);
 }
+static int bn_bwd_cfg(const BnBwdArgs& a) {
+  const bool same_res0 = a.ng >= 1 && a.g[0].Hs == a.H && a.g[0].Ws == a.W;
+  if (a.ng == 1 && a.g[0].mode == GRAD_SAME && same_res0) return 0;
+  if (a.ng == 2 && a.g[0].mode == GRAD_POOL && a.g[1].mode == GRAD_SAME && a.g[1].Hs == a.H && a.g[1].Ws == a.W) return 1;
+  return 2;
+}
 static int bn_bwd_check(const BnBwdArgs& a) {
   TNB_REQUIRE(a.C % 4 == 0 && 256 % (a.C / 4) == 0, "bn_bwd: unsupported channel count %d", a.C);
   TNB_REQUIRE((long long)a.N * ((a.H + 1) / 2) * ((a.W + 1) / 2) * (a.C / 4) < (1ll << 31), "bn_bwd: tensor too large");
@@ -394,14 +440,24 @@ static int bn_bwd_check(const BnBwdArgs& a) {
 int launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t st) {
   if (int rc = bn_bwd_check(a)) return rc;
   ProfScope prof(PROF_BN_BWD, st, a.N, a.H, a.W, a.C, a.C);
-  bn_bwd_kernel<false><<<bn_bwd_num_blocks(a.N, a.H, a.W, a.C), 256, 0, st>>>(a);
+  const int nb = bn_bwd_num_blocks(a.N, a.H, a.W, a.C);
+  switch (bn_bwd_cfg(a)) {
+    case 0: bn_bwd_kernel<false, 0><<<nb, 256, 0, st>>>(a); break;
+    case 1: bn_bwd_kernel<false, 1><<<nb, 256, 0, st>>>(a); break;
+    default: bn_bwd_kernel<false, 2><<<nb, 256, 0, st>>>(a); break;
+  }
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st) {
   if (int rc = bn_bwd_check(a)) return rc;
   ProfScope prof(PROF_BN_BWD, st, a.N, a.H, a.W, a.C, a.C);
-  bn_bwd_kernel<true><<<bn_bwd_num_blocks(a.N, a.H, a.W, a.C), 256, 0, st>>>(a);
+  const int nb = bn_bwd_num_blocks(a.N, a.H, a.W, a.C);
+  switch (bn_bwd_cfg(a)) {
+    case 0: bn_bwd_kernel<true, 0><<<nb, 256, 0, st>>>(a); break;
+    case 1: bn_bwd_kernel<true, 1><<<nb, 256, 0, st>>>(a); break;
+    default: bn_bwd_kernel<true, 2><<<nb, 256, 0, st>>>(a); break;
+  }
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -442,6 +498,26 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
 int launch_bn_bwd_finalize(const float* part, int rows, int C, float* sums, float* dgamma, float* dbeta,
                            cudaStream_t st) {
   bn_bwd_finalize_kernel<<<cdiv(C, 32), dim3(32, 32), 0, st>>>(part, rows, C, sums, dgamma, dbeta);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// fp32 NHWC -> pre-split bf16 [pixel][C/8][2][8] (see include/tracknet_b200.h)
+__global__ void presplit_bf16_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, long long nchunks) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nchunks;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    ld8(x + i * 8, v);
+    uint4 hi, lo;
+    split8<1>(v, hi, lo);
+    *reinterpret_cast<uint4*>(out + i * 32) = hi;
+    *reinterpret_cast<uint4*>(out + i * 32 + 16) = lo;
+  }
+}
+int launch_presplit_bf16(const float* x, void* out, long long npixels, int C, cudaStream_t st) {
+  TNB_REQUIRE(C % 8 == 0, "presplit: channels %d must be a multiple of 8", C);
+  const long long nchunks = npixels * (C / 8);
+  presplit_bf16_kernel<<<min(cdiv(nchunks, 256), 148 * 16), 256, 0, st>>>(x, (uint8_t*)out, nchunks);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

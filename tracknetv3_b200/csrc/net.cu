@@ -190,7 +190,6 @@ int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float*
   Plan P;
   if (int rc = build_plan(c, ws, &P)) return rc;
   TNB_REQUIRE(ws_bytes >= P.bytes, "tracknet_backward: workspace too small (%zu < %zu)", ws_bytes, P.bytes);
-  TNB_CHECK_CUDA(cudaMemsetAsync(P.amax_all, 0, sizeof(float) * kLayers, st));
   const SrcDesc last = make_src(P, c, kLayers - 1, SRC_AFFINE_RELU);
   if (int rc = launch_predictor_bwd(last, c.n, c.h, c.w, (const float*)params[kLayers * 6 + 0], c.out_dim, dy, y,
                                     P.dA_pred, (float*)grads[kLayers * 3 + 0], (float*)grads[kLayers * 3 + 1], st))
@@ -218,7 +217,7 @@ int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float*
     }
     a.z = B.z; a.scale = B.scale; a.shift = B.shift; a.mean = B.mean; a.invstd = B.invstd;
     a.N = c.n; a.H = B.H; a.W = B.W; a.C = B.cout;
-    a.part = B.bwd_part; a.sums = B.bwd_sums; a.dz = B.dz; a.amax = B.amax;
+    a.part = B.bwd_part; a.sums = B.bwd_sums; a.dz = B.dz; a.amax = nullptr; a.dz_format = 1;  // dz -> pre-split bf16
     a.inv_count = (float)(1.0 / ((double)c.n * B.H * B.W));
     if (int rc = launch_bn_bwd_reduce(a, st)) return rc;
     if (int rc = launch_bn_bwd_finalize(B.bwd_part, B.bwd_rows, B.cout, B.bwd_sums, (float*)grads[l * 3 + 1],
@@ -229,19 +228,18 @@ int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float*
     if (l > 0) {
       ViewDesc dv;
       memset(&dv, 0, sizeof(dv));
-      dv.s[0] = SrcDesc{B.dz, B.amax, nullptr, B.cout, B.H, B.W, SRC_IDENTITY};  // scale slot = max|dz|
+      dv.s[0] = SrcDesc{B.dz, nullptr, nullptr, B.cout, B.H, B.W, SRC_PRESPLIT};
       dv.s[1] = dv.s[0];
       dv.C0 = dv.C = B.cout; dv.N = c.n; dv.H = B.H; dv.W = B.W;
       ConvPlan cp;
       if (int rc = conv3x3_plan(c.n, B.H, B.W, B.cout, B.cin, c.bwd_terms, &cp)) return rc;
-      if (int rc = launch_pack_weights(w, B.wd, B.cout, B.cin, 1, 0, cp.BN, st)) return rc;
-      if (int rc = launch_conv3x3(dv, B.wd, B.din, nullptr, B.cin, c.bwd_terms, 0, c.variant & 3, st)) return rc;
+      if (int rc = launch_pack_weights(w, B.wd, B.cout, B.cin, 1, 1, cp.BN, st)) return rc;
+      if (int rc = launch_conv3x3(dv, B.wd, B.din, nullptr, B.cin, c.bwd_terms, 1, c.variant & 3, st)) return rc;
     }
     float* dw = (float*)grads[l * 3 + 0];
     TNB_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)B.cout * B.cin_real * 9, st));
     const ViewDesc v = make_view(P, c, l);
-    if (int rc = launch_wgrad3x3(v, B.dz, B.amax, dw, B.cout, B.cin_real, c.bwd_terms, 0, (c.variant >> 2) & 3, st))
-      return rc;
+    if (int rc = launch_wgrad3x3(v, B.dz, dw, B.cout, B.cin_real, c.bwd_terms, (c.variant >> 2) & 3, st)) return rc;
   }
   return 0;
 }
