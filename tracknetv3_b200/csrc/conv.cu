@@ -9,12 +9,10 @@
 //   warp 0      one elected thread issues tcgen05.mma (kind::f16, M=128, N=BN, K=16; 3 MMAs per K step in the
 //               fp32-faithful hi/lo split mode) into one of up to two TMEM accumulator buffers
 //   warp 1      weight tiles: 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx) of pre-packed smem images
-//   warps 4-7   epilogue: tcgen05.ld -> fp32 NHWC stores + per-channel (sum, sumsq) partials; overlaps the
+//   warps 2-5   epilogue: tcgen05.ld -> fp32 NHWC stores + per-channel (sum, sumsq) partials; overlaps the
 //               next tile's MMAs when two accumulator buffers fit in TMEM (2*MT*BN <= 512 columns)
-//   warps 8-15  operand producers: batched global gathers -> BN affine/ReLU/pool/upsample/concat ->
+//   warps 6-11  operand producers: batched global gathers -> BN affine/ReLU/pool/upsample/concat ->
 //               16-bit hi/lo split -> planar smem halo tile -> fence.proxy.async -> mbarrier
-// Registers are re-balanced per warpgroup with setmaxnreg (56 / 104 / 176 / 176): the producers need them for
-// deep load batches (memory-level parallelism), the issue warps need almost none.
 // The planar tile [plane = 8 channels][pixel][16 B] is a SWIZZLE_NONE K-major operand in which every 3x3 tap
 // is just a different 16-byte aligned start address: one halo tile serves all 9 taps.
 #include "igemm.cuh"
@@ -23,8 +21,8 @@
 
 namespace tnb {
 
-static constexpr int kThreads = 512;      // 4 warpgroups: {MMA, TMA, -, -} {epilogue x4} {producers x8}
-static constexpr int kFillThreads = 256;
+static constexpr int kThreads = 384;
+static constexpr int kFillThreads = 192;
 static constexpr int kEpiThreads = 128;
 static constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 static constexpr int kHdrBytes = 512;
@@ -42,23 +40,6 @@ struct ConvArgs {
 TNB_DEVINL float warp_transpose_sum(float (&v)[32], int lane) {
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) {
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int i = 0; i < o; ++i) {
-      const float send = up ? v[i] : v[i + o];
-      const float keep = up ? v[i + o] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-    }
-  }
-  return v[0];
-}
-
-// 16-value variant: on return lane j holds the sum over the 32 lanes of v[j & 15].
-TNB_DEVINL float warp_transpose_sum16(float (&v)[16], int lane) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
-#pragma unroll
-  for (int o = 8; o >= 1; o >>= 1) {
     const bool up = (lane & o) != 0;
 #pragma unroll
     for (int i = 0; i < o; ++i) {
@@ -120,10 +101,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
   const float in_mul = (V.s[0].mode == SRC_IDENTITY) ? pow2_scale_for(V.s[0].scale) : 1.f;
   const float out_mul = 1.f / in_mul;
 
-  // warpgroup register re-balancing (512 threads start with 128 registers each): first statement of each role
-  if (warp < 4) {
-   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-   if (warp == 0) {
+  if (warp == 0) {
     // =========================== MMA issuer ===========================
     // The whole warp runs the (warp-uniform) loops so that the descriptor arithmetic stays in uniform
     // registers; only the tcgen05 instructions themselves are predicated on one elected lane.
@@ -187,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
       }
     }
     __syncwarp();
-   } else if (warp == 1) {
+  } else if (warp == 1) {
     // =========================== weight loader (bulk TMA) ===========================
     if (elect_one()) {
       int sb = 0;
@@ -204,14 +182,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
       }
     }
     __syncwarp();
-   }  // warps 2-3: no role (they only lend their registers to the producers)
-  } else if (warp < 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-    // =========================== epilogue (warps 4..7) ===========================
+  } else if (warp < 6) {
+    // =========================== epilogue (warps 2..5) ===========================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = 32 * q + lane;
     const int r = row >> 3, cc = row & 7;
-    const int et = tid - 128;  // 0..127
+    const int et = tid - 64;  // 0..127
     int k = 0;
     for (int work = blockIdx.x; work < a.nwork; work += gridDim.x, ++k) {
       const int nt = work / a.ntiles;
@@ -225,37 +201,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
       const uint32_t use = (uint32_t)(k / a.nbuf);
       mbar_wait(&tmem_full[buf], use & 1);
       tc_fence_after();
-      for (int col0 = 0; col0 < BN; col0 += 16) {
+      for (int col0 = 0; col0 < BN; col0 += 32) {
         float csum = 0.f, csq = 0.f;
         for (int mt = 0; mt < MT; ++mt) {
           const int h = h0 + r, w = w0 + 8 * mt + cc;
           const bool valid = (h < V.H) && (w < V.W);
-          uint32_t rg[16];
-          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * BUFCOLS + mt * BN + col0), rg);
+          uint32_t rg[32];
+          tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * BUFCOLS + mt * BN + col0), rg);
           tmem_ld_wait();
-          float v[16];
+          float v[32];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rg[i]) * out_mul;
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rg[i]) * out_mul;
           if (valid) {
             float4* dst = reinterpret_cast<float4*>(a.out + ((size_t)(n * V.H + h) * V.W + w) * a.Cout + n0 + col0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           }
           if (a.stat_part != nullptr) {
             if (!valid) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = 0.f;
+              for (int i = 0; i < 32; ++i) v[i] = 0.f;
             }
-            float s[16];
+            float s[32];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) s[i] = v[i];
-            csum += warp_transpose_sum16(s, lane);
+            for (int i = 0; i < 32; ++i) s[i] = v[i];
+            csum += warp_transpose_sum(s, lane);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) s[i] = v[i] * v[i];
-            csq += warp_transpose_sum16(s, lane);
+            for (int i = 0; i < 32; ++i) s[i] = v[i] * v[i];
+            csq += warp_transpose_sum(s, lane);
           }
         }
-        if (a.stat_part != nullptr && lane < 16) {
+        if (a.stat_part != nullptr) {
           sstat[(q * 2 + 0) * BN + col0 + lane] = csum;
           sstat[(q * 2 + 1) * BN + col0 + lane] = csq;
         }
@@ -276,9 +252,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
     // =========================== A producers: gather + BN/ReLU/pool/upsample + split ===========
-    const int ftid = tid - 256;
+    const int ftid = tid - 192;
     const int j = ftid & 3;       // plane (8 channels) this thread fills: fixed, kFillThreads % 4 == 0
     const int pbase = ftid >> 2;  // first halo pixel; stride kFillThreads/4 pixels
     int sa = 0;
@@ -290,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
       const int th = tile % a.tiles_h;
       const int n = tile / a.tiles_h;
       const int h0 = th * 16, w0 = tw * 8 * MT;
-      asm volatile("bar.sync 2, 256;" ::: "memory");  // previous tile's table is no longer read
+      asm volatile("bar.sync 2, 192;" ::: "memory");  // previous tile's table is no longer read
       for (int p = ftid; p < HALO_PX; p += kFillThreads) {
         const int hr = p / PITCH, hc = p - hr * PITCH;
         const int h = h0 - 1 + hr, w = w0 - 1 + hc;
@@ -301,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
         }
         table[p] = e;
       }
-      asm volatile("bar.sync 2, 256;" ::: "memory");
+      asm volatile("bar.sync 2, 192;" ::: "memory");
       for (int c = 0; c < nchunks; ++c) {
         const int cch = c * 32 + j * 8;
         const bool second = cch >= V.C0;
@@ -309,7 +284,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
         const int cc = second ? cch - V.C0 : cch;
         float sc[8], sh[8];
         if (S.mode != SRC_IDENTITY && S.mode != SRC_PRESPLIT) { ld8(S.scale + cc, sc); ld8(S.shift + cc, sh); }
-        const bool pf_next = (c + 1 < nchunks) && (cc - (j * 8) + 32 < S.C);  // next chunk comes from the same source
         mbar_wait(&empty_A[sa], pha ^ 1);
         uint8_t* stage = a_base + sa * A_STAGE + j * PLANE;
         auto run = [&](auto mode_tag, auto batch_tag) {
@@ -325,19 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
               if (p < HALO_PX) {
                 const int2 e = table[p];
                 off[u] = second ? e.y : e.x;
-                if (off[u] >= 0) {
-                  view_issue<MODE>(S, off[u], cc, raw[u]);
-                  // pull the NEXT chunk's line of this pixel from HBM into L2 while this one is in flight
-                  if (pf_next && j == 0) {
-                    const float* q = S.ptr + (size_t)off[u] * S.C + cc + 32;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-                    if (MODE == SRC_AFFINE_RELU_POOL) {
-                      asm volatile("prefetch.global.L2 [%0];" ::"l"(q + S.C));
-                      asm volatile("prefetch.global.L2 [%0];" ::"l"(q + (size_t)S.Ws * S.C));
-                      asm volatile("prefetch.global.L2 [%0];" ::"l"(q + (size_t)S.Ws * S.C + S.C));
-                    }
-                  }
-                }
+                if (off[u] >= 0) view_issue<MODE>(S, off[u], cc, raw[u]);
               }
             }
 #pragma unroll

@@ -28,7 +28,6 @@ static constexpr int kFillThreads = 384;
 static constexpr int kHdrBytes = 256;
 static constexpr int kTileH = 4, kTileW = 16;    // 64 pixels per K tile
 static constexpr int kHaloW = kTileW + 2;        // 18
-static constexpr int kViewPx = kTileH * kHaloW;  // 72: only the rows of this CTA's filter row dy are needed
 static constexpr int kStages = 3;
 
 struct WgradArgs {
@@ -36,6 +35,7 @@ struct WgradArgs {
   const uint8_t* dz;  // pre-split bf16 [N,H,W][Cout/8][2][8]
   float* dw;          // [Cout][CinReal][3][3], accumulated with atomics (must be zeroed by the caller)
   int Cout, CinReal, NT, nterms, variant;
+  int ndy;  // filter rows per CTA: 3 when all 9 taps fit in TMEM (9 * NT <= 512), else 1 (grid.x carries dy)
   int tiles_h, tiles_w, ktiles, ktiles_per_cta, ncot, ncit;
 };
 
@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   const int NT = a.NT, NPL = NT / 8;
   const int TP = a.nterms > 1 ? 2 : 1;
   const int DZPL = pad_px(kTileH * kTileW) * 16;  // 66 * 16
-  const int VPL = pad_px(kViewPx) * 16;           // 74 * 16
+  const int kViewPx = (kTileH + a.ndy - 1) * kHaloW;  // 72 (one filter row) or 108 (all three)
+  const int VPL = pad_px(kViewPx) * 16;
   const int DZ_BYTES = TP * 16 * DZPL;
   const int STAGE = DZ_BYTES + TP * NPL * VPL;
   constexpr int S = kStages;
@@ -65,7 +66,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   uint8_t* st_base = smem + kHdrBytes;
 
   int bx = blockIdx.x;
-  const int dy = bx % 3; bx /= 3;
+  const int ndy = a.ndy, ngrp = 3 / ndy;
+  const int dy0 = (bx % ngrp) * ndy; bx /= ngrp;  // first filter row of this CTA
   const int co0 = (bx % a.ncot) * 128;
   const int ci0 = (bx / a.ncot) * NT;
   const int cvalid = min(128, a.Cout - co0);
@@ -123,15 +125,17 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
         for (int r = 0; r < kTileH; ++r) {
           const uint64_t a_hi = a_st + (uint64_t)(r * kTileW);
           const uint32_t acc = (kt != kt0 || r != 0);
+          for (int dyl = 0; dyl < ndy; ++dyl) {
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            const uint64_t b_hi = b_st + (uint64_t)(r * kHaloW + dx);
-            const uint32_t d_tmem = tmem_base + dx * NT;
-            if (lead) {
-              umma_f16(d_tmem, a_hi, b_hi, idesc, acc);
-              if (a.nterms > 1) {
-                umma_f16(d_tmem, a_hi + a_lo16, b_hi, idesc, 1);
-                umma_f16(d_tmem, a_hi, b_hi + b_lo16, idesc, 1);
+            for (int dx = 0; dx < 3; ++dx) {
+              const uint64_t b_hi = b_st + (uint64_t)((r + dyl) * kHaloW + dx);
+              const uint32_t d_tmem = tmem_base + (dyl * 3 + dx) * NT;
+              if (lead) {
+                umma_f16(d_tmem, a_hi, b_hi, idesc, acc);
+                if (a.nterms > 1) {
+                  umma_f16(d_tmem, a_hi + a_lo16, b_hi, idesc, 1);
+                  umma_f16(d_tmem, a_hi, b_hi + b_lo16, idesc, 1);
+                }
               }
             }
           }
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
           for (int u = 0; u < U; ++u) {
             const int p = p0 + u * VG;
             const int hr = p / kHaloW, hc = p - hr * kHaloW;
-            const int h = h0 + hr + dy - 1, w = w0 - 1 + hc;
+            const int h = h0 + hr + dy0 - 1, w = w0 - 1 + hc;
             ok[u] = p < kViewPx && h >= 0 && h < V.H && w >= 0 && w < V.W;
             if (ok[u]) view_issue<MODE>(VS, view_off_t<MODE>(VS, n, h, w), vcc, raw[u]);
           }
@@ -249,17 +253,17 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
       mbar_wait(tmem_full, 0);
       tc_fence_after();
       const int row = 32 * q + lane;
-      for (int dx = 0; dx < 3; ++dx) {
+      for (int t = 0; t < 3 * ndy; ++t) {
         for (int col0 = 0; col0 < NT; col0 += 16) {
           uint32_t rg[16];
-          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(dx * NT + col0), rg);
+          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * NT + col0), rg);
           tmem_ld_wait();
           if (row < cvalid && kt1 > kt0) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int ci = ci0 + col0 + j;
               if (ci < a.CinReal)
-                atomicAdd(a.dw + ((size_t)(co0 + row) * a.CinReal + ci) * 9 + dy * 3 + dx, __uint_as_float(rg[j]));
+                atomicAdd(a.dw + ((size_t)(co0 + row) * a.CinReal + ci) * 9 + dy0 * 3 + t, __uint_as_float(rg[j]));
             }
           }
         }
@@ -274,10 +278,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   }
 }
 
-static int pick_nt(int cin) {
+// input-channel tile: divides Cin and (for concat views) the first source, so that a CTA's channels come from ONE
+// source (one gather mode per CTA: no divergence between the up-sampled and the skip half)
+static int pick_nt(int cin, int c0) {
   const int cand[] = {128, 96, 64, 48, 32};
   for (int c : cand)
-    if (cin % c == 0) return c;
+    if (cin % c == 0 && (c0 == cin || c0 % c == 0)) return c;
   return 0;
 }
 
@@ -287,13 +293,15 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
   WgradArgs a;
   a.view = view; a.dz = (const uint8_t*)dz_presplit; a.dw = dw; a.Cout = Cout; a.CinReal = CinReal;
   a.nterms = nterms; a.variant = variant;
-  a.NT = pick_nt(view.C);
+  a.NT = pick_nt(view.C, view.C0);
+  TNB_REQUIRE(a.NT > 0, "wgrad3x3: no input-channel tile for Cin=%d (first source %d)", view.C, view.C0);
   a.tiles_h = (view.H + kTileH - 1) / kTileH;
   a.tiles_w = (view.W + kTileW - 1) / kTileW;
   a.ktiles = view.N * a.tiles_h * a.tiles_w;
   a.ncot = (Cout + 127) / 128;
   a.ncit = view.C / a.NT;
-  const int gx = a.ncot * a.ncit * 3;
+  a.ndy = (9 * a.NT <= 512) ? 3 : 1;
+  const int gx = a.ncot * a.ncit * (3 / a.ndy);
   // split the pixel (K) range so that the grid is ~1 wave of 148 SMs (every CTA ends with 128 x NT x 3 atomics,
   // so fewer, longer CTAs are better), each CTA owning >= 8 K tiles
   int splits = (148 + gx / 2) / gx;
@@ -303,7 +311,7 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
   splits = (a.ktiles + a.ktiles_per_cta - 1) / a.ktiles_per_cta;
   const int TP = nterms > 1 ? 2 : 1;
   const size_t smem = kHdrBytes + kStages * (size_t)(TP * 16 * pad_px(kTileH * kTileW) * 16 +
-                                                     TP * (a.NT / 8) * pad_px(kViewPx) * 16);
+                                                     TP * (a.NT / 8) * pad_px((kTileH + a.ndy - 1) * kHaloW) * 16);
   TNB_REQUIRE(smem <= 232448, "wgrad3x3: shared memory plan too large (%zu)", smem);
   TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(PROF_WGRAD, st, view.N, view.H, view.W, view.C, Cout);
