@@ -139,19 +139,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
             const uint64_t b_st = b_desc0 + (uint64_t)(sb * b_stage16);
             const int dy = t / 3, dx = t - dy * 3;
             const uint64_t a_tap = a_st + (uint64_t)(dy * PITCH + dx);
-            for (int mt = 0; mt < MT; ++mt) {
-              const uint32_t d_tmem = d_buf + mt * BN;
+            // Issue order: consecutive MMAs go to DIFFERENT accumulators (mt innermost), so a short MMA (N = 64 is
+            // 32 cycles) never waits for the previous accumulation into the same TMEM columns to retire.
 #pragma unroll
-              for (int kk = 0; kk < 2; ++kk) {
-                const uint64_t a_hi = a_tap + (uint64_t)(8 * mt + kk * a_k16);
-                const uint64_t b_hi = b_st + (uint64_t)(kk * b_k16);
-                const uint32_t acc = (c | t | kk) != 0;
-                if (lead) {
-                  umma_f16(d_tmem, a_hi, b_hi, idesc, acc);
-                  if (a.nterms > 1) {
-                    umma_f16(d_tmem, a_hi + a_lo16, b_hi, idesc, 1);
-                    umma_f16(d_tmem, a_hi, b_hi + b_lo16, idesc, 1);
-                  }
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint64_t a_k = a_tap + (uint64_t)(kk * a_k16);
+              const uint64_t b_k = b_st + (uint64_t)(kk * b_k16);
+              for (int term = 0; term < a.nterms; ++term) {
+                const uint64_t a_t = a_k + (uint64_t)(term == 1 ? a_lo16 : 0u);
+                const uint64_t b_t = b_k + (uint64_t)(term == 2 ? b_lo16 : 0u);
+                const uint32_t acc = (c | t | kk | term) != 0;
+                for (int mt = 0; mt < MT; ++mt) {
+                  if (lead) umma_f16(d_buf + mt * BN, a_t + (uint64_t)(8 * mt), b_t, idesc, acc);
                 }
               }
             }
