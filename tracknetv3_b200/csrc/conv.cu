@@ -32,7 +32,7 @@ struct ConvArgs {
   const uint16_t* wpack;
   float* out;        // [N,H,W,Cout]
   float* stat_part;  // [ntiles][2][Cout] per-tile (sum, sumsq) partials, or nullptr
-  int Cout, BN, MT, SA, SB, nbuf, nterms, variant, tmem_cols;
+  int Cout, BN, MT, SA, SB, G, nbuf, nterms, variant, tmem_cols;  // G: filter taps per weight stage (1 or 3)
   int tiles_h, tiles_w, ntiles, nwork;
 };
 
@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
   const int PLANE = pad_px(HALO_PX) * 16;  // bytes
   const int TP = a.nterms > 1 ? 2 : 1;     // operand term planes stored (hi[,lo])
   const int A_STAGE = TP * 4 * PLANE;
-  const int B_STAGE = TP * 64 * BN;        // bytes: [term][4 planes][BN][16B]
+  const int B_TAP = TP * 64 * BN;          // bytes of one tap: [term][4 planes][BN][16B]
+  const int B_STAGE = a.G * B_TAP;         // a stage holds G consecutive taps of one 32-channel chunk
   const int nchunks = V.C / 32;
   const int BUFCOLS = MT * BN;
 
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
       // descriptors are base + (byte offset >> 4): the start-address field never carries into the next field
       const uint64_t a_desc0 = make_smem_desc(smem_u32(a_base), a_lbo, a_sbo);
       const uint64_t b_desc0 = make_smem_desc(smem_u32(b_base), b_lbo, b_sbo);
-      const uint32_t a_stage16 = A_STAGE >> 4, b_stage16 = B_STAGE >> 4;
+      const uint32_t a_stage16 = A_STAGE >> 4, b_stage16 = B_STAGE >> 4, b_tap16 = B_TAP >> 4;
       const uint32_t a_k16 = (2 * PLANE) >> 4, a_lo16 = (4 * PLANE) >> 4;
       const uint32_t b_k16 = (2 * BN * 16) >> 4, b_lo16 = (4 * BN * 16) >> 4;
       int sa = 0, sb = 0;
@@ -133,24 +134,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
           mbar_wait(&full_A[sa], pha);
           tc_fence_after();
           const uint64_t a_st = a_desc0 + (uint64_t)(sa * a_stage16);
-          for (int t = 0; t < 9; ++t) {
+          for (int t0 = 0; t0 < 9; t0 += a.G) {
             mbar_wait(&full_B[sb], phb);
             tc_fence_after();
             const uint64_t b_st = b_desc0 + (uint64_t)(sb * b_stage16);
-            const int dy = t / 3, dx = t - dy * 3;
-            const uint64_t a_tap = a_st + (uint64_t)(dy * PITCH + dx);
-            // Issue order: consecutive MMAs go to DIFFERENT accumulators (mt innermost), so a short MMA (N = 64 is
-            // 32 cycles) never waits for the previous accumulation into the same TMEM columns to retire.
+            // Issue order: ALL MMAs of this tap group that accumulate into one TMEM tile are issued back to back
+            // (G taps x 2 K-steps x nterms), then the next tile. Measured: the tensor pipe retires a chain into one
+            // accumulator at full rate but pays a drain when the accumulator changes, so short chains starve it.
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint32_t d_tmem = d_buf + mt * BN;
+              for (int tg = 0; tg < a.G; ++tg) {
+                const int t = t0 + tg;
+                const int dy = t / 3, dx = t - dy * 3;
+                const uint64_t a_tap = a_st + (uint64_t)(dy * PITCH + dx + 8 * mt);
+                const uint64_t b_tap = b_st + (uint64_t)(tg * b_tap16);
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-              const uint64_t a_k = a_tap + (uint64_t)(kk * a_k16);
-              const uint64_t b_k = b_st + (uint64_t)(kk * b_k16);
-              for (int term = 0; term < a.nterms; ++term) {
-                const uint64_t a_t = a_k + (uint64_t)(term == 1 ? a_lo16 : 0u);
-                const uint64_t b_t = b_k + (uint64_t)(term == 2 ? b_lo16 : 0u);
-                const uint32_t acc = (c | t | kk | term) != 0;
-                for (int mt = 0; mt < MT; ++mt) {
-                  if (lead) umma_f16(d_buf + mt * BN, a_t + (uint64_t)(8 * mt), b_t, idesc, acc);
+                for (int kk = 0; kk < 2; ++kk) {
+                  const uint64_t a_hi = a_tap + (uint64_t)(kk * a_k16);
+                  const uint64_t b_hi = b_tap + (uint64_t)(kk * b_k16);
+                  const uint32_t acc = (c | t | kk) != 0;
+                  if (lead) {
+                    umma_f16(d_tmem, a_hi, b_hi, idesc, acc);
+                    if (a.nterms > 1) {
+                      umma_f16(d_tmem, a_hi + a_lo16, b_hi, idesc, 1);
+                      umma_f16(d_tmem, a_hi, b_hi + b_lo16, idesc, 1);
+                    }
+                  }
                 }
               }
             }
@@ -172,10 +181,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
       for (int work = blockIdx.x; work < a.nwork; work += gridDim.x) {
         const int nt = work / a.ntiles;
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)nt * nchunks * 9 * (size_t)(128 * BN);
-        for (int i = 0; i < nchunks * 9; ++i) {
+        for (int i = 0; i < nchunks * 9; i += a.G) {
           mbar_wait(&empty_B[sb], phb ^ 1);
           mbar_arrive_expect_tx(&full_B[sb], (uint32_t)B_STAGE);
-          bulk_g2s(b_base + sb * B_STAGE, wsrc + (size_t)i * (128 * BN), (uint32_t)B_STAGE, &full_B[sb]);
+          for (int g = 0; g < a.G; ++g)  // each tap image is [hi | lo]; with one term only the hi half is fetched
+            bulk_g2s(b_base + sb * B_STAGE + g * B_TAP, wsrc + (size_t)(i + g) * (128 * BN), (uint32_t)B_TAP, &full_B[sb]);
           if (++sb == a.SB) { sb = 0; phb ^= 1; }
         }
       }
@@ -377,22 +387,32 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
   int MT = 512 / BN;
   if (MT > 4) MT = 4;
   while (MT > 1 && 8 * (MT - 1) >= W) --MT;  // do not tile wider than the image
-  int SA = 2, SB = 0;
+  int SA = 2, SB = 0, G = 1;
   size_t smem = 0;
-  for (;; --MT) {
-    const int pitch = 8 * MT + 2, halo = 18 * pitch;
-    const size_t a_stage = (size_t)TP * 4 * pad_px(halo) * 16;
-    const size_t b_stage = (size_t)TP * 64 * BN;
-    const size_t fixed = kHdrBytes + ((halo * 8 + 127) & ~127) + (size_t)4 * 2 * BN * 4 + SA * a_stage;
-    if (fixed + 2 * b_stage <= (size_t)kMaxSmem) {
-      SB = (int)((kMaxSmem - fixed) / b_stage);
-      if (SB > 8) SB = 8;
-      smem = fixed + SB * b_stage;
-      break;
+  const int mt_max = MT;
+  bool found = false;
+  // pass 0: narrow tiles (BN <= 128) get weight stages holding a whole filter row (3 taps) so that 18+ MMAs chain into
+  // one accumulator; pass 1: one tap per stage, as many stages as fit
+  for (int pass = (BN <= 128 ? 0 : 1); pass < 2 && !found; ++pass) {
+    const int g = pass == 0 ? 3 : 1;
+    for (MT = mt_max; MT >= 1; --MT) {
+      const int pitch = 8 * MT + 2, halo = 18 * pitch;
+      const size_t a_stage = (size_t)TP * 4 * pad_px(halo) * 16;
+      const size_t b_stage = (size_t)g * TP * 64 * BN;
+      const size_t fixed = kHdrBytes + ((halo * 8 + 127) & ~127) + (size_t)4 * 2 * BN * 4 + SA * a_stage;
+      if (fixed + 2 * b_stage <= (size_t)kMaxSmem) {
+        G = g;
+        SB = (int)((kMaxSmem - fixed) / b_stage);
+        const int cap = g == 3 ? 3 : 8;
+        if (SB > cap) SB = cap;
+        smem = fixed + SB * b_stage;
+        found = true;
+        break;
+      }
     }
-    TNB_REQUIRE(MT > 1, "conv3x3: no shared-memory plan for Cin=%d Cout=%d", Cin, Cout);
   }
-  plan->BN = BN; plan->MT = MT; plan->SA = SA; plan->SB = SB;
+  TNB_REQUIRE(found, "conv3x3: no shared-memory plan for Cin=%d Cout=%d", Cin, Cout);
+  plan->BN = BN; plan->MT = MT; plan->SA = SA; plan->SB = SB; plan->G = G;
   plan->nbuf = (2 * MT * BN <= 512) ? 2 : 1;
   plan->tmem_cols = pow2_cols(plan->nbuf * MT * BN);
   plan->smem_bytes = smem;
@@ -415,7 +435,7 @@ int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, floa
   if (rc) return rc;
   ConvArgs a;
   a.view = view; a.wpack = wpack; a.out = out; a.stat_part = stat_part;
-  a.Cout = Cout; a.BN = p.BN; a.MT = p.MT; a.SA = p.SA; a.SB = p.SB; a.nbuf = p.nbuf; a.nterms = nterms;
+  a.Cout = Cout; a.BN = p.BN; a.MT = p.MT; a.SA = p.SA; a.SB = p.SB; a.G = p.G; a.nbuf = p.nbuf; a.nterms = nterms;
   a.variant = variant; a.tmem_cols = p.tmem_cols; a.tiles_h = p.tiles_h; a.tiles_w = p.tiles_w;
   a.ntiles = view.N * p.tiles_h * p.tiles_w;
   a.nwork = a.ntiles * (Cout / p.BN);

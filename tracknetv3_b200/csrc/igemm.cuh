@@ -133,7 +133,7 @@ __host__ __device__ inline int pad_px(int px) {  // plane stride = 2 (mod 8) pix
 }
 
 struct ConvPlan {
-  int BN, MT, SA, SB, nbuf, tmem_cols;
+  int BN, MT, SA, SB, G, nbuf, tmem_cols;
   size_t smem_bytes;
   int tiles_h, tiles_w;
 };

@@ -121,21 +121,23 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
         tc_fence_after();
         const uint64_t a_st = a_desc0 + (uint64_t)(s * stage16);
         const uint64_t b_st = b_desc0 + (uint64_t)(s * stage16);
+        // Issue order: for each tap (= one TMEM accumulator) chain all K steps of this tile (4 rows x nterms) back
+        // to back; the tensor pipe pays a drain whenever the accumulator changes, so chains must be long.
+        for (int dyl = 0; dyl < ndy; ++dyl) {
 #pragma unroll
-        for (int r = 0; r < kTileH; ++r) {
-          const uint64_t a_hi = a_st + (uint64_t)(r * kTileW);
-          const uint32_t acc = (kt != kt0 || r != 0);
-          // consecutive MMAs target different accumulators (taps innermost): a 16..64-cycle MMA never waits for the
-          // previous accumulation into the same TMEM columns
-          for (int term = 0; term < a.nterms; ++term) {
-            const uint64_t a_t = a_hi + (uint64_t)(term == 1 ? a_lo16 : 0u);
-            const uint32_t b_off = term == 2 ? b_lo16 : 0u;
-            const uint32_t acc_t = acc | (uint32_t)(term != 0);
-            for (int dyl = 0; dyl < ndy; ++dyl) {
+          for (int dx = 0; dx < 3; ++dx) {
+            const uint32_t d_tmem = tmem_base + (dyl * 3 + dx) * NT;
 #pragma unroll
-              for (int dx = 0; dx < 3; ++dx) {
-                const uint64_t b_t = b_st + (uint64_t)((r + dyl) * kHaloW + dx + b_off);
-                if (lead) umma_f16(tmem_base + (dyl * 3 + dx) * NT, a_t, b_t, idesc, acc_t);
+            for (int r = 0; r < kTileH; ++r) {
+              const uint64_t a_hi = a_st + (uint64_t)(r * kTileW);
+              const uint64_t b_hi = b_st + (uint64_t)((r + dyl) * kHaloW + dx);
+              const uint32_t acc = (kt != kt0 || r != 0);
+              if (lead) {
+                umma_f16(d_tmem, a_hi, b_hi, idesc, acc);
+                if (a.nterms > 1) {
+                  umma_f16(d_tmem, a_hi + a_lo16, b_hi, idesc, 1);
+                  umma_f16(d_tmem, a_hi, b_hi + b_lo16, idesc, 1);
+                }
               }
             }
           }
