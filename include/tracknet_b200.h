@@ -96,6 +96,10 @@ int tnb_pack_nchw_to_nhwc(const float* x_nchw, float* out_nhwc, int n, int c, in
  * (dz) are produced in this format by tnb_bn_relu_bwd_apply(dz_format = 1) and consumed by dgrad
  * (TNB_SRC_PRESPLIT view) and wgrad without any per-element arithmetic in the consumers. */
 int tnb_presplit_bf16(const float* x_nhwc, void* out, long long npixels, int c, void* stream);
+/* Materialise a whole logical view (BN affine + ReLU + MaxPool / Upsample / cat of the producers) in the pre-split
+ * format: out is [N,H,W][C/8][2][8] 16-bit, fmt 0 = fp16 (values clamped to +-65504), 1 = bf16. Used by the backward
+ * pass so that the weight-gradient kernel's operand fills are plain copies (TNB_SRC_PRESPLIT). */
+int tnb_view_presplit(const tnb_view_t* view, void* out, int fmt, void* stream);
 
 /* Weight pre-packing for the tcgen05 kernels. mode 0: forward operand, mode 1: dgrad operand (rotated,
  * transposed). fmt 0: fp16 split, 1: bf16 split. Source is the reference's canonical OIHW parameter

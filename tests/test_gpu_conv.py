@@ -1,4 +1,6 @@
 """-m gpu: the tcgen05 implicit-GEMM kernels (conv fwd / dgrad / wgrad) against the CPU fp32 oracle ops."""
+import ctypes as C
+
 import numpy as np
 import pytest
 import torch
@@ -92,6 +94,15 @@ def test_conv3x3_fused_views(mode):
     (F.conv2d(xin, wz, padding=1) * dz).sum().backward()
     dw = G.wgrad3x3(G.make_view(srcs, n, h, w), dev(dz.permute(0, 2, 3, 1)), 64, xin.shape[1])
     assert G.rel_err(dw, wz.grad) < 2e-4
+    # production backward: the same view materialised once in the pre-split format, wgrad fills are pure copies
+    L = G.lib()
+    view = G.make_view(srcs, n, h, w)
+    vs = torch.empty(n * h * w * xin.shape[1] * 4, dtype=torch.uint8, device=G.DEV)
+    _lib.check(L.tnb_view_presplit(C.byref(view), vs.data_ptr(), 1, G.st()))
+    assert G.max_abs(G.unsplit(vs, (n, h, w, xin.shape[1])), xin.permute(0, 2, 3, 1)) < 2e-5 * xin.abs().max().item()
+    psrc = _lib.Src(ptr=vs.data_ptr(), scale=None, shift=None, C=xin.shape[1], Hs=h, Ws=w, mode=_lib.SRC_PRESPLIT)
+    dw2 = G.wgrad3x3(G.make_view([psrc], n, h, w), keep[-1], 64, xin.shape[1])
+    assert G.rel_err(dw2, wz.grad) < 2e-4
     del keep
 
 

@@ -189,7 +189,9 @@ def test_backward_is_the_derivative_of_forward():
                 p.add_(eps * d)
         fd = (lp - lm) / (2 * eps)
         print(f"gradcheck trial {trial}: analytic {analytic:.6e} finite-difference {fd:.6e}")
-        errs.append((analytic - fd) / max(abs(fd), abs(analytic)))
+        errs.append((analytic - fd, abs(fd)))
     # the loss is only piecewise smooth (ReLU / max-pool kinks inside the finite-difference interval), so single
-    # directions scatter by a few percent; a wrong backward would be off by O(1) and with a consistent sign
-    assert max(abs(e) for e in errs) < 0.12 and abs(sum(errs) / len(errs)) < 0.05, errs
+    # directions scatter by a few percent of the typical slope; a wrong backward would be off by O(1), consistently
+    scale = sum(f for _, f in errs) / len(errs)
+    assert max(abs(e) for e, _ in errs) < 0.08 * scale, errs
+    assert abs(sum(e for e, _ in errs)) / len(errs) < 0.03 * scale, errs

@@ -33,6 +33,9 @@ int tnb_pack_nchw_to_nhwc(const float* x, float* out, int n, int c, int h, int w
 int tnb_presplit_bf16(const float* x, void* out, long long npixels, int c, void* stream) {
   return launch_presplit_bf16(x, out, npixels, c, ST(stream));
 }
+int tnb_view_presplit(const tnb_view_t* view, void* out, int fmt, void* stream) {
+  return launch_view_presplit(*view, out, fmt, ST(stream));
+}
 size_t tnb_conv3x3_wpack_elems(int k_side, int n_side) { return conv3x3_wpack_elems(k_side, n_side); }
 int tnb_conv3x3_pack_weights(const float* w, uint16_t* out, int cout, int cin, int mode, int fmt, void* stream) {
   // the tile width must match what the conv launcher will pick for this N side

@@ -171,11 +171,16 @@ TNB_DEVINL uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t 
   return d;                // base_offset = 0, lbo_mode = 0, layout_type = 0 (no swizzle)
 }
 // Instruction descriptor for kind::f16: fp32 accumulate, A/B format 0 = fp16 / 1 = bf16.
+TNB_DEVINL uint32_t make_idesc2(int M, int N, int a_format, int b_format, int a_mn_major, int b_mn_major);
 TNB_DEVINL uint32_t make_idesc(int M, int N, int ab_format, int a_mn_major, int b_mn_major) {
+  return make_idesc2(M, N, ab_format, ab_format, a_mn_major, b_mn_major);
+}
+// A and B formats are independent fields of the descriptor (0 = fp16, 1 = bf16)
+TNB_DEVINL uint32_t make_idesc2(int M, int N, int a_format, int b_format, int a_mn_major, int b_mn_major) {
   uint32_t d = 0;
   d |= 1u << 4;                          // D format f32
-  d |= (uint32_t)ab_format << 7;         // A format
-  d |= (uint32_t)ab_format << 10;        // B format
+  d |= (uint32_t)a_format << 7;          // A format
+  d |= (uint32_t)b_format << 10;         // B format
   d |= (uint32_t)(a_mn_major & 1) << 15; // A major
   d |= (uint32_t)(b_mn_major & 1) << 16; // B major
   d |= (uint32_t)(N >> 3) << 17;

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
                   const uint64_t a_hi = a_tap + (uint64_t)(kk * a_k16);
                   const uint64_t b_hi = b_tap + (uint64_t)(kk * b_k16);
                   const uint32_t acc = (c | t | kk) != 0;
-                  if (lead) {
+                  if (lead && !(a.variant & 4)) {
                     umma_f16(d_tmem, a_hi, b_hi, idesc, acc);
                     if (a.nterms > 1) {
                       umma_f16(d_tmem, a_hi + a_lo16, b_hi, idesc, 1);
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
         float csum = 0.f, csq = 0.f;
         for (int mt = 0; mt < MT; ++mt) {
           const int h = h0 + r, w = w0 + 8 * mt + cc;
-          const bool valid = (h < V.H) && (w < V.W);
+          const bool valid = (h < V.H) && (w < V.W) && !(a.variant & 16);
           uint32_t rg[32];
           tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * BUFCOLS + mt * BN + col0), rg);
           tmem_ld_wait();
@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
         auto run = [&](auto mode_tag, auto batch_tag) {
           constexpr int MODE = decltype(mode_tag)::value;
           constexpr int U = decltype(batch_tag)::value;
+          if (a.variant & 8) return;  // ablation: barrier traffic only
           for (int p0 = pbase; p0 < HALO_PX; p0 += (kFillThreads / 4) * U) {
             Raw8 raw[U][RawCount<MODE>::value];
             int off[U];

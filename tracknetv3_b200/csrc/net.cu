@@ -45,6 +45,7 @@ struct LayerBuf {
 };
 struct Plan {
   LayerBuf L[kLayers];
+  uint8_t* vsplit;  // scratch: the current layer's input view materialised as pre-split bf16 (largest: 192 ch @ full res)
   float* amax_all;  // [kLayers] max|dz| per layer, raised atomically by bn_bwd apply
   float* xin;
   float* dA_pred;
@@ -84,6 +85,15 @@ int build_plan(const tnb_tracknet_cfg_t& c, void* ws, Plan* P) {
   P->cpad = (c.in_dim + 31) / 32 * 32;
   const size_t npix0 = (size_t)c.n * c.h * c.w;
   P->amax_all = b.take<float>(kLayers);
+  P->vsplit = nullptr;
+  if (c.training) {
+    size_t vmax = 0;
+    for (int l = 0; l < kLayers; ++l) {
+      const size_t e = (size_t)c.n * (c.h >> kDefs[l].level) * (c.w >> kDefs[l].level) * layer_cin(c, l);
+      vmax = e > vmax ? e : vmax;
+    }
+    P->vsplit = b.take<uint8_t>(vmax * 4);
+  }
   P->xin = b.take<float>(npix0 * P->cpad);
   P->dA_pred = b.take<float>(npix0 * 64);
   for (int l = 0; l < kLayers; ++l) {
@@ -238,15 +248,22 @@ int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float*
     }
     float* dw = (float*)grads[l * 3 + 0];
     TNB_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)B.cout * B.cin_real * 9, st));
+    // materialise the input view once (bf16 hi/lo), then both wgrad operands are plain copies
     const ViewDesc v = make_view(P, c, l);
-    if (int rc = launch_wgrad3x3(v, B.dz, dw, B.cout, B.cin_real, c.bwd_terms, (c.variant >> 2) & 3, st)) return rc;
+    if (int rc = launch_view_presplit(v, P.vsplit, 1, st)) return rc;
+    ViewDesc pv;
+    memset(&pv, 0, sizeof(pv));
+    pv.s[0] = SrcDesc{reinterpret_cast<const float*>(P.vsplit), nullptr, nullptr, B.cin, B.H, B.W, SRC_PRESPLIT};
+    pv.s[1] = pv.s[0];
+    pv.C0 = pv.C = B.cin; pv.N = c.n; pv.H = B.H; pv.W = B.W;
+    if (int rc = launch_wgrad3x3(pv, B.dz, dw, B.cout, B.cin_real, c.bwd_terms, (c.variant >> 2) & 3, st)) return rc;
   }
   return 0;
 }
 
 int tracknet_num_launches(const tnb_tracknet_cfg_t& c, int backward) {
   if (!backward) return 1 + kLayers * 3 + (c.training ? 1 : 0) + 1;  // pack, (wpack, conv, bn_finalize) x17, counters, predictor
-  return 1 + kLayers * 4 + (kLayers - 1) * 2;                         // predictor_bwd, (reduce, finalize, apply, wgrad) x17, (wpack, dgrad) x16
+  return 1 + kLayers * 5 + (kLayers - 1) * 2;  // predictor_bwd, (reduce, finalize, apply, view_presplit, wgrad) x17, (wpack, dgrad) x16
 }
 
 }  // namespace tnb

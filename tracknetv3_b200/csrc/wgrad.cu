@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
     if (warp == 0) {
       // whole warp runs the uniform loops (descriptor math in uniform registers); one lane issues
       const bool lead = elect_one();
-      const uint32_t idesc = make_idesc(128, NT, 1 /*bf16*/, 1, 1);
+            const uint32_t idesc = make_idesc(128, NT, 1 /*bf16: A and B formats must match (mixed = illegal instruction)*/, 1, 1);
       // MN-major planar tiles: SBO = plane stride (next 8 channels), LBO = 128 B (next 8 pixels).
       uint32_t a_lbo = 128, a_sbo = DZPL, b_lbo = 128, b_sbo = VPL;
       if (a.variant & 1) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; }
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
     const SrcDesc& VS = vsecond ? V.s[1] : V.s[0];
     const int vcc = vsecond ? vch - V.C0 : vch;
     float sc[8], sh[8];
-    if (VS.mode != SRC_IDENTITY && vactive) { ld8(VS.scale + vcc, sc); ld8(VS.shift + vcc, sh); }
+    if (VS.mode != SRC_IDENTITY && VS.mode != SRC_PRESPLIT && vactive) { ld8(VS.scale + vcc, sc); ld8(VS.shift + vcc, sh); }
     const uint8_t* dz_base = a.dz + (size_t)(co0 / 8 + dpl) * 32;
     const size_t dz_pix_stride = (size_t)(a.Cout / 8) * 32;
     const int per_img = a.tiles_h * a.tiles_w;
@@ -213,9 +213,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
             if (p < kViewPx) {
               uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
               if (ok[u]) {
-                float v[8];
-                view_finish<MODE>(raw[u], sc, sh, 1.f, v);
-                split8<1>(v, hi, lo);
+                if (MODE == SRC_PRESPLIT) {  // materialised bf16 view (tnb_view_presplit): pure copy
+                  hi = *reinterpret_cast<const uint4*>(&raw[u][0].a);
+                  lo = *reinterpret_cast<const uint4*>(&raw[u][0].b);
+                } else {
+                  float v[8];
+                  view_finish<MODE>(raw[u], sc, sh, 1.f, v);
+                  split8<1>(v, hi, lo);
+                }
               }
               *reinterpret_cast<uint4*>(vwp + p * 16) = hi;
               if (a.nterms > 1) *reinterpret_cast<uint4*>(vwp + p * 16 + NPL * VPL) = lo;
@@ -227,6 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
         switch (VS.mode) {
           case SRC_IDENTITY: view_run(std::integral_constant<int, SRC_IDENTITY>{}, std::integral_constant<int, 3>{}); break;
           case SRC_AFFINE_RELU_UP: view_run(std::integral_constant<int, SRC_AFFINE_RELU_UP>{}, std::integral_constant<int, 3>{}); break;
+          case SRC_PRESPLIT: view_run(std::integral_constant<int, SRC_PRESPLIT>{}, std::integral_constant<int, 3>{}); break;
           case SRC_AFFINE_RELU_POOL: view_run(std::integral_constant<int, SRC_AFFINE_RELU_POOL>{}, std::integral_constant<int, 1>{}); break;
           default: view_run(std::integral_constant<int, SRC_AFFINE_RELU>{}, std::integral_constant<int, 3>{}); break;
         }
