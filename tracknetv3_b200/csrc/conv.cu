@@ -51,7 +51,9 @@ TNB_DEVINL float warp_transpose_sum(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int FMT>
+// M0 / M1: gather modes of the (up to two) concatenated view sources, compile-time so that every instantiation carries
+// only the gather paths it needs (the producers are register-limited; a run-time switch over all modes costs spills)
+template <int FMT, int M0, int M1>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_constant__ ConvArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
@@ -334,13 +336,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
             }
           }
         };
-        switch (S.mode) {
-          case SRC_IDENTITY: run(std::integral_constant<int, SRC_IDENTITY>{}, std::integral_constant<int, 4>{}); break;
-          case SRC_AFFINE_RELU_POOL: run(std::integral_constant<int, SRC_AFFINE_RELU_POOL>{}, std::integral_constant<int, 1>{}); break;
-          case SRC_AFFINE_RELU_UP: run(std::integral_constant<int, SRC_AFFINE_RELU_UP>{}, std::integral_constant<int, 4>{}); break;
-          case SRC_PRESPLIT: run(std::integral_constant<int, SRC_PRESPLIT>{}, std::integral_constant<int, 4>{}); break;
-          default: run(std::integral_constant<int, SRC_AFFINE_RELU>{}, std::integral_constant<int, 4>{}); break;
-        }
+        constexpr int U0 = (M0 == SRC_AFFINE_RELU_POOL) ? 2 : 4, U1 = (M1 == SRC_AFFINE_RELU_POOL) ? 2 : 4;
+        if (second) run(std::integral_constant<int, M1>{}, std::integral_constant<int, U1>{});
+        else        run(std::integral_constant<int, M0>{}, std::integral_constant<int, U0>{});
         fence_proxy_async_smem();
         mbar_arrive(&full_A[sa]);
         if (++sa == a.SA) { sa = 0; pha ^= 1; }
@@ -441,11 +439,26 @@ int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, floa
   a.ntiles = view.N * p.tiles_h * p.tiles_w;
   a.nwork = a.ntiles * (Cout / p.BN);
   const int grid = a.nwork < num_sms() ? a.nwork : num_sms();
-  auto kern = fmt == 0 ? conv3x3_kernel<0> : conv3x3_kernel<1>;
-  TNB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-  ProfScope prof(view.s[0].mode == SRC_PRESPLIT ? PROF_CONV_DGRAD : PROF_CONV_FWD, st,
-                 view.N, view.H, view.W, view.C, Cout);
-  kern<<<grid, kThreads, p.smem_bytes, st>>>(a);
+  const int m0 = view.s[0].mode, m1 = (view.C0 < view.C) ? view.s[1].mode : view.s[0].mode;
+  ProfScope prof(view.s[0].mode == SRC_PRESPLIT ? PROF_CONV_DGRAD : PROF_CONV_FWD, st, view.N, view.H, view.W, view.C, Cout);
+  auto go = [&](auto kern) -> int {
+    TNB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+    kern<<<grid, kThreads, p.smem_bytes, st>>>(a);
+    return 0;
+  };
+  int rc2 = -2;
+#define TNB_CONV_CASE(F, A, B) if (fmt == F && m0 == A && m1 == B) rc2 = go(conv3x3_kernel<F, A, B>); else
+  TNB_CONV_CASE(0, SRC_IDENTITY, SRC_IDENTITY)
+  TNB_CONV_CASE(0, SRC_AFFINE_RELU, SRC_AFFINE_RELU)
+  TNB_CONV_CASE(0, SRC_AFFINE_RELU_POOL, SRC_AFFINE_RELU_POOL)
+  TNB_CONV_CASE(0, SRC_AFFINE_RELU_UP, SRC_AFFINE_RELU)
+  TNB_CONV_CASE(0, SRC_AFFINE_RELU_UP, SRC_AFFINE_RELU_UP)
+  TNB_CONV_CASE(0, SRC_PRESPLIT, SRC_PRESPLIT)
+  TNB_CONV_CASE(1, SRC_IDENTITY, SRC_IDENTITY)
+  TNB_CONV_CASE(1, SRC_PRESPLIT, SRC_PRESPLIT)
+  { tnb::set_last_error("conv3x3: unsupported (fmt %d, source modes %d/%d) combination", fmt, m0, m1); return -2; }
+#undef TNB_CONV_CASE
+  if (rc2) return rc2;
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

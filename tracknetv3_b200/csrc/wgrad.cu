@@ -37,6 +37,7 @@ struct WgradArgs {
   int Cout, CinReal, NT, nterms, variant;
   int ndy;  // filter rows per CTA: 3 when all 9 taps fit in TMEM (9 * NT <= 512), else 1 (grid.x carries dy)
   int tiles_h, tiles_w, ktiles, ktiles_per_cta, ncot, ncit;
+  int ci_tile_base;  // first input-channel tile of this launch (concat views with two gather modes use two launches)
 };
 
 template <int MODE> TNB_DEVINL int view_off_t(const SrcDesc& s, int n, int h, int w) {
@@ -45,6 +46,9 @@ template <int MODE> TNB_DEVINL int view_off_t(const SrcDesc& s, int n, int h, in
   return (n * s.Hs + h) * s.Ws + w;
 }
 
+// VMODE: gather mode of the view operand, compile-time so that every instantiation carries exactly one gather path
+// (the producers are register-limited; a run-time switch over all modes costs spills in the hot loop)
+template <int VMODE>
 __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_constant__ WgradArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
@@ -69,7 +73,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   const int ndy = a.ndy, ngrp = 3 / ndy;
   const int dy0 = (bx % ngrp) * ndy; bx /= ngrp;  // first filter row of this CTA
   const int co0 = (bx % a.ncot) * 128;
-  const int ci0 = (bx / a.ncot) * NT;
+  const int ci0 = (bx / a.ncot + a.ci_tile_base) * NT;
   const int cvalid = min(128, a.Cout - co0);
   const int npld = cvalid / 8;  // dz planes actually filled (8 or 16)
   const int kt0 = blockIdx.y * a.ktiles_per_cta;
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
     const SrcDesc& VS = vsecond ? V.s[1] : V.s[0];
     const int vcc = vsecond ? vch - V.C0 : vch;
     float sc[8], sh[8];
-    if (VS.mode != SRC_IDENTITY && VS.mode != SRC_PRESPLIT && vactive) { ld8(VS.scale + vcc, sc); ld8(VS.shift + vcc, sh); }
+    if (VMODE != SRC_IDENTITY && VMODE != SRC_PRESPLIT && vactive) { ld8(VS.scale + vcc, sc); ld8(VS.shift + vcc, sh); }
     const uint8_t* dz_base = a.dz + (size_t)(co0 / 8 + dpl) * 32;
     const size_t dz_pix_stride = (size_t)(a.Cout / 8) * 32;
     const int per_img = a.tiles_h * a.tiles_w;
@@ -228,15 +232,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
           }
         }
       };
-      if (vactive) {
-        switch (VS.mode) {
-          case SRC_IDENTITY: view_run(std::integral_constant<int, SRC_IDENTITY>{}, std::integral_constant<int, 3>{}); break;
-          case SRC_AFFINE_RELU_UP: view_run(std::integral_constant<int, SRC_AFFINE_RELU_UP>{}, std::integral_constant<int, 3>{}); break;
-          case SRC_PRESPLIT: view_run(std::integral_constant<int, SRC_PRESPLIT>{}, std::integral_constant<int, 3>{}); break;
-          case SRC_AFFINE_RELU_POOL: view_run(std::integral_constant<int, SRC_AFFINE_RELU_POOL>{}, std::integral_constant<int, 1>{}); break;
-          default: view_run(std::integral_constant<int, SRC_AFFINE_RELU>{}, std::integral_constant<int, 3>{}); break;
-        }
-      }
+      if (vactive)
+        view_run(std::integral_constant<int, VMODE>{},
+                 std::integral_constant<int, (VMODE == SRC_AFFINE_RELU_POOL) ? 1 : 3>{});
       // ---- dz: already (hi, lo) bf16 -> two 16-byte stores, no arithmetic ----
 #pragma unroll
       for (int u = 0; u < 3; ++u) {
@@ -300,7 +298,7 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
   TNB_REQUIRE(view.C % 32 == 0 && Cout % 64 == 0, "wgrad3x3: unsupported channels Cin=%d Cout=%d", view.C, Cout);
   WgradArgs a;
   a.view = view; a.dz = (const uint8_t*)dz_presplit; a.dw = dw; a.Cout = Cout; a.CinReal = CinReal;
-  a.nterms = nterms; a.variant = variant;
+  a.nterms = nterms; a.variant = variant; a.ci_tile_base = 0;
   a.NT = pick_nt(view.C, view.C0);
   TNB_REQUIRE(a.NT > 0, "wgrad3x3: no input-channel tile for Cin=%d (first source %d)", view.C, view.C0);
   a.tiles_h = (view.H + kTileH - 1) / kTileH;
@@ -321,9 +319,39 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
   const size_t smem = kHdrBytes + kStages * (size_t)(TP * 16 * pad_px(kTileH * kTileW) * 16 +
                                                      TP * (a.NT / 8) * pad_px((kTileH + a.ndy - 1) * kHaloW) * 16);
   TNB_REQUIRE(smem <= 232448, "wgrad3x3: shared memory plan too large (%zu)", smem);
-  TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // one gather mode per launch: a concat view whose two halves use different modes is split by the channel tiling
+  // (pick_nt keeps every CTA inside one source), but the kernel is instantiated per mode -> require equal modes or
+  // fall back to the first source's mode only when the second source is unused
+  const int mode0 = view.s[0].mode, mode1 = (view.C0 < view.C) ? view.s[1].mode : view.s[0].mode;
+  auto launch = [&](auto tag, const WgradArgs& args, int gx_first, int gx_count) -> int {
+    constexpr int M = decltype(tag)::value;
+    TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    (void)gx_first;
+    wgrad3x3_kernel<M><<<dim3(gx_count, splits), kThreads, smem, st>>>(args);
+    return 0;
+  };
+  auto dispatch = [&](int mode, const WgradArgs& args, int gx_count) -> int {
+    switch (mode) {
+      case SRC_IDENTITY: return launch(std::integral_constant<int, SRC_IDENTITY>{}, args, 0, gx_count);
+      case SRC_AFFINE_RELU: return launch(std::integral_constant<int, SRC_AFFINE_RELU>{}, args, 0, gx_count);
+      case SRC_AFFINE_RELU_POOL: return launch(std::integral_constant<int, SRC_AFFINE_RELU_POOL>{}, args, 0, gx_count);
+      case SRC_AFFINE_RELU_UP: return launch(std::integral_constant<int, SRC_AFFINE_RELU_UP>{}, args, 0, gx_count);
+      case SRC_PRESPLIT: return launch(std::integral_constant<int, SRC_PRESPLIT>{}, args, 0, gx_count);
+      default: tnb::set_last_error("wgrad3x3: bad view mode %d", mode); return -2;
+    }
+  };
   ProfScope prof(PROF_WGRAD, st, view.N, view.H, view.W, view.C, Cout);
-  wgrad3x3_kernel<<<dim3(gx, splits), kThreads, smem, st>>>(a);
+  if (mode0 == mode1) {
+    if (int rc = dispatch(mode0, a, gx)) return rc;
+  } else {
+    // two launches, one per source: ci tiles [0, C0/NT) use mode0, the rest mode1 (ci_base shifts blockIdx.x)
+    WgradArgs a0 = a, a1 = a;
+    const int t0 = view.C0 / a.NT;
+    a0.ncit = t0; a0.ci_tile_base = 0;
+    a1.ncit = a.ncit - t0; a1.ci_tile_base = t0;
+    if (int rc = dispatch(mode0, a0, a.ncot * a0.ncit * (3 / a.ndy))) return rc;
+    if (int rc = dispatch(mode1, a1, a.ncot * a1.ncit * (3 / a.ndy))) return rc;
+  }
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
