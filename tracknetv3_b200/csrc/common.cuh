@@ -100,6 +100,17 @@ TNB_DEVINL void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint6
       : "memory");
 }
 
+// 16-byte asynchronous global->shared copy (LDGSTS). src_bytes = 0 zero-fills the destination without reading.
+TNB_DEVINL void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+// The mbarrier receives one arrival (counted against its initial expected count) once all cp.async operations issued
+// so far by this thread have landed: producers never wait for their own loads.
+TNB_DEVINL void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA issue, commit, TMEM loads
 // ---------------------------------------------------------------------------------------------

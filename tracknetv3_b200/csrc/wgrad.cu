@@ -182,6 +182,41 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
       uint8_t* dzp = stage + dpl * DZPL;
       uint8_t* vwp = stage + DZ_BYTES + vpl * VPL;
 
+      if (VMODE == SRC_PRESPLIT) {
+        // Both operands are already (hi, lo) 16-bit pairs in HBM: the fill is 16-byte cp.async copies straight into
+        // the planar tiles. The thread never waits for its own loads (the stage's mbarrier is armed with a
+        // cp.async-completion arrival), so up to kStages K tiles of HBM latency are in flight per thread.
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int px = dpx0 + u * DG;
+          if (px < kTileH * kTileW) {
+            const int h = h0 + (px >> 4), w = w0 + (px & 15);
+            const bool ok = h < V.H && w < V.W;
+            const uint8_t* q = ok ? dz_base + ((size_t)(n * V.H + h) * V.W + w) * dz_pix_stride : a.dz;
+            cp_async16(dzp + px * 16, q, ok ? 16u : 0u);
+            if (a.nterms > 1) cp_async16(dzp + px * 16 + 16 * DZPL, q + 16, ok ? 16u : 0u);
+          }
+        }
+        if (vactive) {
+          const uint8_t* vbase = reinterpret_cast<const uint8_t*>(VS.ptr) + (size_t)(vcc / 8) * 32;
+          const size_t vstride = (size_t)(VS.C / 8) * 32;
+#pragma unroll
+          for (int u = 0; u < 3; ++u) {
+            const int p = vpx0 + u * VG;
+            if (p < kViewPx) {
+              const int hr = p / kHaloW, hc = p - hr * kHaloW;
+              const int h = h0 + hr + dy0 - 1, w = w0 - 1 + hc;
+              const bool ok = h >= 0 && h < V.H && w >= 0 && w < V.W;
+              const uint8_t* q = ok ? vbase + ((size_t)(n * VS.Hs + h) * VS.Ws + w) * vstride : vbase;
+              cp_async16(vwp + p * 16, q, ok ? 16u : 0u);
+              if (a.nterms > 1) cp_async16(vwp + p * 16 + NPL * VPL, q + 16, ok ? 16u : 0u);
+            }
+          }
+        }
+        cp_async_mbar_arrive_noinc(&full[s]);
+        if (++s == S) { s = 0; ph ^= 1; }
+        continue;
+      }
       // ---- issue every load of this K tile: dz copies first, then the view gathers ----
       Raw8 draw[3];
       bool dok[3];
