@@ -91,13 +91,14 @@ int tnb_abi_version(void);
 int tnb_pack_nchw_to_nhwc(const float* x_nchw, float* out_nhwc, int n, int c, int h, int w, int cpad, void* stream);
 
 /* "Pre-split" tensor format: every fp32 value x is stored as two bf16 numbers hi = rn(x), lo = rn(x - hi)
- * (x ~ hi + lo to 2^-17), laid out [pixel][C/8][2 (hi, lo)][8 channels] so that a (pixel, 8-channel) operand
- * fragment of both terms is one contiguous 32-byte read. Same byte size as the fp32 tensor. Gradient tensors
+ * (x ~ hi + lo to 2^-17), laid out [pixel][2 (hi, lo)][C] 16-bit: the hi terms of a pixel's channels are contiguous
+ * (so 16-byte cp.async copies of neighbouring channel chunks coalesce into full sectors), the lo terms follow at
+ * +2*C bytes. Same byte size as the fp32 tensor. Gradient tensors
  * (dz) are produced in this format by tnb_bn_relu_bwd_apply(dz_format = 1) and consumed by dgrad
  * (TNB_SRC_PRESPLIT view) and wgrad without any per-element arithmetic in the consumers. */
 int tnb_presplit_bf16(const float* x_nhwc, void* out, long long npixels, int c, void* stream);
 /* Materialise a whole logical view (BN affine + ReLU + MaxPool / Upsample / cat of the producers) in the pre-split
- * format: out is [N,H,W][C/8][2][8] 16-bit, fmt 0 = fp16 (values clamped to +-65504), 1 = bf16. Used by the backward
+ * format: out is [N,H,W][2 (hi, lo)][C] 16-bit, fmt 0 = fp16 (values clamped to +-65504), 1 = bf16. Used by the backward
  * pass so that the weight-gradient kernel's operand fills are plain copies (TNB_SRC_PRESPLIT). */
 int tnb_view_presplit(const tnb_view_t* view, void* out, int fmt, void* stream);
 

@@ -79,8 +79,8 @@ def presplit(t_nhwc):
 def unsplit(buf, shape_nhwc):
     """inverse of presplit (hi + lo) for checking: uint8 buffer -> fp32 NHWC."""
     n, h, w, c = shape_nhwc
-    v = buf.view(torch.bfloat16).reshape(n, h, w, c // 8, 2, 8).float()
-    return (v[..., 0, :] + v[..., 1, :]).reshape(n, h, w, c)
+    v = buf.view(torch.bfloat16).reshape(n, h, w, 2, c).float()  # [pixel][2 (hi, lo)][C]
+    return v[..., 0, :] + v[..., 1, :]
 
 
 def wgrad3x3(view, dz_nhwc, cout, cin_real, terms=3, variant=0):

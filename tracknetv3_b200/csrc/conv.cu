@@ -341,14 +341,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
           // 16-byte cp.async copies straight into the planar tile; the stage's mbarrier gets a cp.async-completion
           // arrival, so the thread never waits for its own loads and SA stages of HBM latency stay in flight
           if (!(a.variant & 8)) {
-            const uint8_t* sbase = reinterpret_cast<const uint8_t*>(S.ptr) + (size_t)(cc / 8) * 32;
-            const size_t sstride = (size_t)(S.C / 8) * 32;
+            const uint8_t* sbase = reinterpret_cast<const uint8_t*>(S.ptr) + (size_t)cc * 2;  // [pixel][2][C] 16-bit
+            const size_t sstride = (size_t)S.C * 4;
+            const int lo_off = S.C * 2;
             for (int p = pbase; p < HALO_PX; p += kFillThreads / 4) {
               const int2 e = table[p];
               const int off = second ? e.y : e.x;
               const uint8_t* q = off >= 0 ? sbase + (size_t)off * sstride : sbase;
               cp_async16(stage + p * 16, q, off >= 0 ? 16u : 0u);
-              if (a.nterms > 1) cp_async16(stage + p * 16 + 4 * PLANE, q + 16, off >= 0 ? 16u : 0u);
+              if (a.nterms > 1) cp_async16(stage + p * 16 + 4 * PLANE, q + lo_off, off >= 0 ? 16u : 0u);
             }
           }
           cp_async_mbar_arrive_noinc(&full_A[sa]);

@@ -14,7 +14,7 @@ enum SrcMode : int {
   SRC_AFFINE_RELU = TNB_SRC_AFFINE_RELU,            // relu(z*scale + shift)                  (model.py:12-16)
   SRC_AFFINE_RELU_POOL = TNB_SRC_AFFINE_RELU_POOL,  // maxpool2x2(relu(z*scale+shift)), z is 2H x 2W (model.py:59,61,63)
   SRC_AFFINE_RELU_UP = TNB_SRC_AFFINE_RELU_UP,      // nearest x2 upsample of relu(z*scale+shift)  (model.py:65,67,69)
-  SRC_PRESPLIT = TNB_SRC_PRESPLIT                   // already (hi, lo) bf16, [pixel][C/8][2][8]: pure copy
+  SRC_PRESPLIT = TNB_SRC_PRESPLIT                   // already (hi, lo) 16-bit, [pixel][2][C]: pure copy
 };
 using SrcDesc = tnb_src_t;    // see include/tracknet_b200.h
 using ViewDesc = tnb_view_t;
@@ -81,8 +81,15 @@ TNB_DEVINL void raw_to_arr(const Raw8& r, float (&v)[8]) {
 template <int MODE> struct RawCount { static constexpr int value = (MODE == SRC_AFFINE_RELU_POOL) ? 4 : 1; };
 template <int MODE>
 TNB_DEVINL void view_issue(const SrcDesc& s, int poff, int c, Raw8 (&raw)[RawCount<MODE>::value]) {
-  // fp32 and pre-split tensors have the same 4 bytes per element, and the 8 channels [c, c+8) of one pixel are the
-  // same 32 contiguous bytes in both: raw.a = channels c..c+3 (fp32) or the hi term (pre-split), raw.b = the rest / lo
+  if (MODE == SRC_PRESPLIT) {
+    // [pixel][2 (hi, lo)][C] 16-bit: raw.a = the 8 hi values, raw.b = the 8 lo values of channels [c, c+8)
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(s.ptr) + ((size_t)poff * 2 * s.C + c) * 2;
+    const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(b));
+    const uint4 x1 = __ldg(reinterpret_cast<const uint4*>(b + 2 * s.C));
+    raw[0].a = *reinterpret_cast<const float4*>(&x0);
+    raw[0].b = *reinterpret_cast<const float4*>(&x1);
+    return;
+  }
   const float* p = s.ptr + (size_t)poff * s.C + c;
   raw[0] = ld_raw8(p);
   if (MODE == SRC_AFFINE_RELU_POOL) {

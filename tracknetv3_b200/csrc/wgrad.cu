@@ -32,7 +32,7 @@ static constexpr int kStages = 3;
 
 struct WgradArgs {
   ViewDesc view;
-  const uint8_t* dz;  // pre-split bf16 [N,H,W][Cout/8][2][8]
+  const uint8_t* dz;  // pre-split bf16 [N,H,W][2 (hi, lo)][Cout]
   float* dw;          // [Cout][CinReal][3][3], accumulated with atomics (must be zeroed by the caller)
   int Cout, CinReal, NT, nterms, variant;
   int ndy;  // filter rows per CTA: 3 when all 9 taps fit in TMEM (9 * NT <= 512), else 1 (grid.x carries dy)
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
               const uint64_t a_hi = a_st + (uint64_t)(r * kTileW);
               const uint64_t b_hi = b_st + (uint64_t)((r + dyl) * kHaloW + dx);
               const uint32_t acc = (kt != kt0 || r != 0);
-              if (lead) {
+              if (lead && !(a.variant & 4)) {
                 umma_f16(d_tmem, a_hi, b_hi, idesc, acc);
                 if (a.nterms > 1) {
                   umma_f16(d_tmem, a_hi + a_lo16, b_hi, idesc, 1);
@@ -166,8 +166,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
     const int vcc = vsecond ? vch - V.C0 : vch;
     float sc[8], sh[8];
     if (VMODE != SRC_IDENTITY && VMODE != SRC_PRESPLIT && vactive) { ld8(VS.scale + vcc, sc); ld8(VS.shift + vcc, sh); }
-    const uint8_t* dz_base = a.dz + (size_t)(co0 / 8 + dpl) * 32;
-    const size_t dz_pix_stride = (size_t)(a.Cout / 8) * 32;
+    const uint8_t* dz_base = a.dz + (size_t)(co0 + dpl * 8) * 2;  // dz: [pixel][2 (hi, lo)][Cout] bf16
+    const size_t dz_pix_stride = (size_t)a.Cout * 4;
+    const int dz_lo = a.Cout * 2;
     const int per_img = a.tiles_h * a.tiles_w;
 
     int s = 0;
@@ -182,6 +183,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
       uint8_t* dzp = stage + dpl * DZPL;
       uint8_t* vwp = stage + DZ_BYTES + vpl * VPL;
 
+      if (VMODE == SRC_PRESPLIT && (a.variant & 8)) {  // ablation: barrier traffic only
+        cp_async_mbar_arrive_noinc(&full[s]);
+        if (++s == S) { s = 0; ph ^= 1; }
+        continue;
+      }
       if (VMODE == SRC_PRESPLIT) {
         // Both operands are already (hi, lo) 16-bit pairs in HBM: the fill is 16-byte cp.async copies straight into
         // the planar tiles. The thread never waits for its own loads (the stage's mbarrier is armed with a
@@ -194,12 +200,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
             const bool ok = h < V.H && w < V.W;
             const uint8_t* q = ok ? dz_base + ((size_t)(n * V.H + h) * V.W + w) * dz_pix_stride : a.dz;
             cp_async16(dzp + px * 16, q, ok ? 16u : 0u);
-            if (a.nterms > 1) cp_async16(dzp + px * 16 + 16 * DZPL, q + 16, ok ? 16u : 0u);
+            if (a.nterms > 1) cp_async16(dzp + px * 16 + 16 * DZPL, q + dz_lo, ok ? 16u : 0u);
           }
         }
         if (vactive) {
-          const uint8_t* vbase = reinterpret_cast<const uint8_t*>(VS.ptr) + (size_t)(vcc / 8) * 32;
-          const size_t vstride = (size_t)(VS.C / 8) * 32;
+          const uint8_t* vbase = reinterpret_cast<const uint8_t*>(VS.ptr) + (size_t)vcc * 2;  // [pixel][2][C] 16-bit
+          const size_t vstride = (size_t)VS.C * 4;
+          const int v_lo = VS.C * 2;
 #pragma unroll
           for (int u = 0; u < 3; ++u) {
             const int p = vpx0 + u * VG;
@@ -209,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
               const bool ok = h >= 0 && h < V.H && w >= 0 && w < V.W;
               const uint8_t* q = ok ? vbase + ((size_t)(n * VS.Hs + h) * VS.Ws + w) * vstride : vbase;
               cp_async16(vwp + p * 16, q, ok ? 16u : 0u);
-              if (a.nterms > 1) cp_async16(vwp + p * 16 + NPL * VPL, q + 16, ok ? 16u : 0u);
+              if (a.nterms > 1) cp_async16(vwp + p * 16 + NPL * VPL, q + v_lo, ok ? 16u : 0u);
             }
           }
         }
@@ -226,8 +233,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
         const int h = h0 + (px >> 4), w = w0 + (px & 15);
         dok[u] = px < kTileH * kTileW && h < V.H && w < V.W;
         if (dok[u]) {
-          const uint4* q = reinterpret_cast<const uint4*>(dz_base + ((size_t)(n * V.H + h) * V.W + w) * dz_pix_stride);
-          const uint4 x0 = __ldg(q), x1 = __ldg(q + 1);
+          const uint8_t* q = dz_base + ((size_t)(n * V.H + h) * V.W + w) * dz_pix_stride;
+          const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(q)), x1 = __ldg(reinterpret_cast<const uint4*>(q + dz_lo));
           draw[u].a = *reinterpret_cast<const float4*>(&x0);
           draw[u].b = *reinterpret_cast<const float4*>(&x1);
         }
@@ -299,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
           uint32_t rg[16];
           tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * NT + col0), rg);
           tmem_ld_wait();
-          if (row < cvalid && kt1 > kt0) {
+          if (row < cvalid && kt1 > kt0 && !(a.variant & 16)) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int ci = ci0 + col0 + j;
@@ -345,7 +352,7 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
   const int gx = a.ncot * a.ncit * (3 / a.ndy);
   // split the pixel (K) range so that the grid is ~1 wave of 148 SMs (every CTA ends with 128 x NT x 3 atomics,
   // so fewer, longer CTAs are better), each CTA owning >= 8 K tiles
-  int splits = (148 + gx / 2) / gx;
+  int splits = 148 / gx;  // never more CTAs than SMs: a 149th CTA would cost a whole second wave
   if (splits > (a.ktiles + 7) / 8) splits = (a.ktiles + 7) / 8;
   if (splits < 1) splits = 1;
   a.ktiles_per_cta = (a.ktiles + splits - 1) / splits;
