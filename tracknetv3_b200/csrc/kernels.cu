@@ -518,6 +518,41 @@ __global__ void presplit_bf16_kernel(const float* __restrict__ x, uint8_t* __res
     *reinterpret_cast<uint4*>(dst + 2 * C) = lo;
   }
 }
+// Materialise a layer's logical input view (BN affine + ReLU + MaxPool / Upsample / cat of its producers, exactly what
+// the conv kernels gather on the fly) ONCE in the pre-split 16-bit format, so that kernels which would otherwise each
+// redo that arithmetic several times (wgrad: 3 filter rows x Cout/128 tiles) fill their operands with plain copies.
+template <int FMT>
+__global__ void __launch_bounds__(256) view_presplit_kernel(const __grid_constant__ ViewDesc V, uint8_t* __restrict__ out) {
+  const int nch = V.C >> 3;
+  const long long total = (long long)V.N * V.H * V.W * nch;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % nch);
+    const long long pix = i / nch;
+    const int w = (int)(pix % V.W);
+    const long long r = pix / V.W;
+    const int h = (int)(r % V.H), n = (int)(r / V.H);
+    const int c = ch * 8;
+    float v[8];
+    if (c >= V.C0) view_load8(V.s[1], view_pix_off(V.s[1], n, h, w), c - V.C0, v);
+    else           view_load8(V.s[0], view_pix_off(V.s[0], n, h, w), c, v);
+    uint4 hi, lo;
+    split8<FMT>(v, hi, lo);
+    uint8_t* dst = out + ((size_t)pix * 2 * V.C + c) * 2;  // [pixel][2 (hi, lo)][C] 16-bit
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + 2 * V.C) = lo;
+  }
+}
+int launch_view_presplit(const ViewDesc& view, void* out, int fmt, cudaStream_t st) {
+  TNB_REQUIRE(view.C % 8 == 0 && view.C0 % 8 == 0, "view_presplit: channel counts must be multiples of 8");
+  const long long total = (long long)view.N * view.H * view.W * (view.C / 8);
+  const int blocks = min(cdiv(total, 256), 148 * 16);
+  if (fmt == 0) view_presplit_kernel<0><<<blocks, 256, 0, st>>>(view, (uint8_t*)out);
+  else          view_presplit_kernel<1><<<blocks, 256, 0, st>>>(view, (uint8_t*)out);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_presplit_bf16(const float* x, void* out, long long npixels, int C, cudaStream_t st) {
   TNB_REQUIRE(C % 8 == 0, "presplit: channels %d must be a multiple of 8", C);
   const long long nchunks = npixels * (C / 8);
