@@ -105,8 +105,6 @@ TNB_DEVINL void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
                : "memory");
 }
-TNB_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> TNB_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // The mbarrier receives one arrival (counted against its initial expected count) once all cp.async operations issued
 // so far by this thread have landed: producers never wait for their own loads.
 TNB_DEVINL void cp_async_mbar_arrive_noinc(uint64_t* bar) {

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
   // ---- one-time setup ----
   if (warp == 0) {
     if (elect_one()) {
-      for (int i = 0; i < a.SA; ++i) { mbar_init(&full_A[i], kFillThreads / 32); mbar_init(&empty_A[i], 1); }  // one arrival per producer WARP
+      for (int i = 0; i < a.SA; ++i) { mbar_init(&full_A[i], kFillThreads); mbar_init(&empty_A[i], 1); }
       for (int i = 0; i < a.SB; ++i) { mbar_init(&full_B[i], 1); mbar_init(&empty_B[i], 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
       fence_mbar_init();
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
     const int ftid = tid - 192;
     const int j = ftid & 3;       // plane (8 channels) this thread fills: fixed, kFillThreads % 4 == 0
     const int pbase = ftid >> 2;  // first halo pixel; stride kFillThreads/4 pixels
-    int sa = 0, sap = 0, issued = 0;  // sap / issued: cp.async path publishes a chunk one iteration after issuing it
+    int sa = 0;
     uint32_t pha = 0;
     for (int work = blockIdx.x; work < a.nwork; work += gridDim.x) {
       const int nt = work / a.ntiles;
@@ -352,15 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
               if (a.nterms > 1) cp_async16(stage + p * 16 + 4 * PLANE, q + lo_off, off >= 0 ? 16u : 0u);
             }
           }
-          cp_async_commit();
-          if (issued >= 1) {  // publish the chunk issued one iteration ago (SA = 2 stages: one chunk of latency in flight)
-            cp_async_wait<1>();
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full_A[sap]);
-            if (++sap == a.SA) sap = 0;
-          }
-          ++issued;
+          cp_async_mbar_arrive_noinc(&full_A[sa]);
           if (++sa == a.SA) { sa = 0; pha ^= 1; }
           continue;
         }
@@ -368,16 +360,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
         if (second) run(std::integral_constant<int, M1>{}, std::integral_constant<int, U1>{});
         else        run(std::integral_constant<int, M0>{}, std::integral_constant<int, U0>{});
         fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_A[sa]);
+        mbar_arrive(&full_A[sa]);
         if (++sa == a.SA) { sa = 0; pha ^= 1; }
       }
-    }
-    if (M0 == SRC_PRESPLIT && M1 == SRC_PRESPLIT && issued >= 1) {  // drain the last cp.async chunk
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_A[sap]);
     }
   }
 

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
 
   if (warp == 0) {
     if (elect_one()) {
-      for (int i = 0; i < S; ++i) { mbar_init(&full[i], kFillThreads / 32); mbar_init(&empty[i], 1); }  // one arrival per producer WARP
+      for (int i = 0; i < S; ++i) { mbar_init(&full[i], kFillThreads); mbar_init(&empty[i], 1); }
       mbar_init(tmem_full, 1);
       fence_mbar_init();
     }
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
     const int dz_lo = a.Cout * 2;
     const int per_img = a.tiles_h * a.tiles_w;
 
-    int s = 0, sp = 0;  // s: stage being filled, sp: next stage to publish (cp.async path lags by two tiles)
+    int s = 0;
     uint32_t ph = 0;
     for (int kt = kt0; kt < kt1; ++kt) {
       const int n = kt / per_img;
@@ -183,15 +183,19 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
       uint8_t* dzp = stage + dpl * DZPL;
       uint8_t* vwp = stage + DZ_BYTES + vpl * VPL;
 
+      if (VMODE == SRC_PRESPLIT && (a.variant & 8)) {  // ablation: barrier traffic only
+        cp_async_mbar_arrive_noinc(&full[s]);
+        if (++s == S) { s = 0; ph ^= 1; }
+        continue;
+      }
       if (VMODE == SRC_PRESPLIT) {
         // Both operands are already (hi, lo) 16-bit pairs in HBM: the fill is 16-byte cp.async copies straight into
-        // the planar tiles, one commit group per K tile. A tile is published (ONE mbarrier arrival per warp, not per
-        // thread: 384 arrivals on one mbarrier cost ~1000 cycles per tile) two tiles later, once its group has
-        // landed, so two tiles of HBM latency are always in flight per thread.
+        // the planar tiles. The thread never waits for its own loads (the stage's mbarrier is armed with a
+        // cp.async-completion arrival), so up to kStages K tiles of HBM latency are in flight per thread.
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
           const int px = dpx0 + u * DG;
-          if (px < kTileH * kTileW && !(a.variant & 8)) {
+          if (px < kTileH * kTileW) {
             const int h = h0 + (px >> 4), w = w0 + (px & 15);
             const bool ok = h < V.H && w < V.W;
             const uint8_t* q = ok ? dz_base + ((size_t)(n * V.H + h) * V.W + w) * dz_pix_stride : a.dz;
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
 #pragma unroll
           for (int u = 0; u < 3; ++u) {
             const int p = vpx0 + u * VG;
-            if (p < kViewPx && !(a.variant & 8)) {
+            if (p < kViewPx) {
               const int hr = p / kHaloW, hc = p - hr * kHaloW;
               const int h = h0 + hr + dy0 - 1, w = w0 - 1 + hc;
               const bool ok = h >= 0 && h < V.H && w >= 0 && w < V.W;
@@ -216,14 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
             }
           }
         }
-        cp_async_commit();
-        if (kt - kt0 >= 2) {  // publish the tile issued two iterations ago
-          cp_async_wait<2>();
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full[sp]);
-          if (++sp == S) sp = 0;
-        }
+        cp_async_mbar_arrive_noinc(&full[s]);
         if (++s == S) { s = 0; ph ^= 1; }
         continue;
       }
@@ -295,25 +292,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
         }
       }
       fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[s]);
+      mbar_arrive(&full[s]);
       if (++s == S) { s = 0; ph ^= 1; }
-    }
-    if (VMODE == SRC_PRESPLIT) {  // drain: publish the last (up to two) tiles
-      const int ntiles = kt1 - kt0;
-      if (ntiles >= 2) {
-        cp_async_wait<1>();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[sp]);
-        if (++sp == S) sp = 0;
-      }
-      if (ntiles >= 1) {
-        cp_async_wait<0>();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[sp]);
-      }
     }
 
     if (warp < 8) {
