@@ -180,14 +180,22 @@ def main():
         bucket.allreduce()
         return loss
 
+    # e2e: every step's inputs start in pinned host memory and are copied H2D inside the timed region (side stream,
+    # overlapped with the previous step's compute by the package's DevicePrefetcher); the loss is read back every step
+    e2e_state = {"loader": None}
+
     def step_e2e():
         for p in model.parameters():
             p.grad = None
-        xd, yd = x_pin.cuda(non_blocking=True), y_pin.cuda(non_blocking=True)
+        xd, yd = next(e2e_state["loader"])
         loss = T.WBCELoss(model(xd), yd)
         loss.backward()
         bucket.allreduce()
         return loss.item()  # D2H read of the step result, like train.py:94
+
+    def host_batches(count):
+        for _ in range(count):
+            yield (x_pin, y_pin)
 
     def barrier():
         if world > 1:
@@ -219,8 +227,24 @@ def main():
     desc = (C.c_int * (6 * maxrec))()
     kms = (C.c_float * maxrec)()
     nrec = lib.tnb_profile_collect(maxrec, desc, kms)
-    step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    e2e_state["loader"] = T.DevicePrefetcher(host_batches(1))
+    step_e2e()  # untimed warm-up of the e2e path
+
+    def timed_e2e(steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        e2e_state["loader"] = T.DevicePrefetcher(host_batches(steps))  # the first copy is issued inside the region
+        for _ in range(steps):
+            step_e2e()
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    ms_e2e = timed_e2e(args.steps)
 
     if rank != 0:
         if world > 1:

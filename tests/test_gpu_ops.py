@@ -232,3 +232,11 @@ def test_bn_relu_backward_with_gradient_routing(consumers):
         (F.interpolate(a2, scale_factor=2, mode="nearest") * dup[:, :c]).sum().backward()
     assert G.rel_err(dgamma, g2.grad) < 2e-4 and G.rel_err(dbeta, b2.grad) < 2e-4
     del keep
+
+
+def test_device_prefetcher_yields_batches_in_order():
+    host = [(torch.full((4, 8), float(i)).pin_memory(), torch.arange(4).float().pin_memory() + i) for i in range(5)]
+    got = list(T.DevicePrefetcher(iter(host)))
+    assert len(got) == 5
+    for i, (a, b) in enumerate(got):
+        assert a.is_cuda and torch.equal(a.cpu(), host[i][0]) and torch.equal(b.cpu(), host[i][1])

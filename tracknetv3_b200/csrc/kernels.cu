@@ -158,13 +158,19 @@ __global__ void __launch_bounds__(256) predictor_bwd_kernel(SrcDesc src, int N, 
   constexpr int TP = 64;  // pixels per tile
   __shared__ float sw[kMaxPredO * 64];
   __shared__ float sdl[kMaxPredO][TP];
-  __shared__ float sa[TP][65];
+  __shared__ __align__(16) float sa[TP][68];  // 16-byte aligned rows: the dW pass reads float4
   for (int i = threadIdx.x; i < O * 64; i += 256) sw[i] = wp[i];
   const long long hw = (long long)H * W, npix = (long long)N * hw;
   const long long ntiles = (npix + TP - 1) / TP;
-  float accw[4] = {0.f, 0.f, 0.f, 0.f};  // pairs (o,c) = threadIdx.x + 256*k, k < O*64/256
+  // dW pass: a "unit" = one output map o x 4 consecutive channels; units = O*16; the 256 threads form G pixel groups
+  // of `units` threads, each group reducing its share of the tile's pixels (1 scalar + 1 float4 LDS per 4 FMAs)
+  const int units = O * 16;
+  const int G = units <= 64 ? 4 : units <= 128 ? 2 : 1;
+  const int ugrp = threadIdx.x / units, uidx = threadIdx.x - ugrp * units;
+  const bool uact = ugrp < G;
+  const int uo = uidx >> 4, uc = (uidx & 15) * 4;
+  float accw[4] = {0.f, 0.f, 0.f, 0.f};
   float accb = 0.f;
-  const int npairs = O * 64;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     __syncthreads();
     const long long p0 = tile * TP;
@@ -211,15 +217,16 @@ __global__ void __launch_bounds__(256) predictor_bwd_kernel(SrcDesc src, int N, 
       for (int i = 0; i < 16; ++i) sa[pl][qd * 16 + i] = a[i];
     }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int pair = threadIdx.x + 256 * k;
-      if (pair < npairs) {
-        const int o = pair >> 6, c = pair & 63;
-        float s = accw[k];
-#pragma unroll 8
-        for (int pl = 0; pl < TP; ++pl) s = fmaf(sdl[o][pl], sa[pl][c], s);
-        accw[k] = s;
+    if (uact) {
+      const int per = TP / G;
+#pragma unroll 4
+      for (int pl = ugrp * per; pl < (ugrp + 1) * per; ++pl) {
+        const float d = sdl[uo][pl];
+        const float4 a4 = *reinterpret_cast<const float4*>(&sa[pl][uc]);
+        accw[0] = fmaf(d, a4.x, accw[0]);
+        accw[1] = fmaf(d, a4.y, accw[1]);
+        accw[2] = fmaf(d, a4.z, accw[2]);
+        accw[3] = fmaf(d, a4.w, accw[3]);
       }
     }
     if (threadIdx.x < O) {
@@ -228,10 +235,9 @@ __global__ void __launch_bounds__(256) predictor_bwd_kernel(SrcDesc src, int N, 
       accb = s;
     }
   }
+  if (uact) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int pair = threadIdx.x + 256 * k;
-    if (pair < npairs) atomicAdd(dwp + pair, accw[k]);
+    for (int k = 0; k < 4; ++k) atomicAdd(dwp + uo * 64 + uc + k, accw[k]);
   }
   if (threadIdx.x < O) atomicAdd(dbias + threadIdx.x, accb);
 }
