@@ -273,8 +273,16 @@ def main():
     conv_launches = sum(per_kind.get(k, [0, 0, 0])[2] for k in (0, 1))
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     terms = 3 if args.precision == "fp32x3" else 1
+    traffic, traffic_src = None, None
+    prof = os.path.join(ROOT, "profiles", "kernel_metrics_r1.json")
+    if os.path.exists(prof) and args.precision == "fp32x3":  # dram read+write per conv launch from the committed ncu pass
+        km = json.load(open(prof))
+        conv = [v for k, v in km.items() if k.startswith("conv3x3_kernel")]
+        traffic = sum(v["dram_bytes_per_launch"] * v["launches"] for v in conv) / sum(v["launches"] for v in conv)
+        traffic_src = "profiles/kernel_metrics_r1.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per conv launch)"
     roofline = {"bound": "tensor", "kernel": "conv3x3_kernel (forward + dgrad launches)", "achieved": achieved,
-                "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
+                "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peaks["source"], "avg_launch_ms": conv_ms / max(conv_launches, 1),
                 "algorithmic_flops_per_launch": conv_fl / max(conv_launches, 1),
                 "mma_flops_per_algorithmic_flop": terms,
