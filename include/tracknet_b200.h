@@ -170,6 +170,13 @@ int tnb_heatmap_decode(const void* maps, int is_u8, float thresh, int nmaps, int
 int tnb_inpaintnet_fwd(const float* coords, const float* mask, const void* const* params, int n, int l, float* out,
                        void* stream);
 
+/* Autograd of the above, as train.py:147-166 needs it (loss.backward() through InpaintNet): one kernel that
+ * recomputes the forward in shared memory. dout: (n, l, 2) gradient w.r.t. the output. grads: 18 device pointers
+ * (same order as params) the parameter gradients are ADDED into (caller zeroes them). dcoords: optional (n, l, 2)
+ * gradient w.r.t. coords, may be NULL. l <= 28. */
+int tnb_inpaintnet_bwd(const float* coords, const float* mask, const void* const* params, const float* dout,
+                       void* const* grads, int n, int l, float* dcoords, void* stream);
+
 /* ---- network level: TrackNet.forward / its autograd backward (model.py:57-73) --------------- */
 
 /* params: 104 device pointers in state_dict order: for each of the 17 Conv2DBlocks

@@ -42,10 +42,50 @@ def grad_stats(g):
     return np.concatenate([[g.sum().item(), g.abs().sum().item(), g.abs().max().item()], g[idx].numpy()])
 
 
+def gen_inpaint_train(refmodel):
+    """One InpaintNet train step (reference train.py:147-166) on the REAL reference module, CPU fp32: random
+    Bernoulli mask AND visibility -> zero the masked coordinates -> forward -> MSE on the masked entries ->
+    backward -> clip_grad_norm_(1) -> Adam(lr 1e-3). The RNG draw of the mask (get_random_mask, train.py:42-57,
+    numpy binomial) is made here and stored, the step arithmetic runs on the stored tensors."""
+    torch.manual_seed(5)
+    np.random.seed(5)
+    net = refmodel.InpaintNet().train()
+    n, L = 6, 16
+    coor_gt = torch.rand(n, L, 2)
+    vis_gt = (torch.rand(n, L, 1) < 0.85).float()
+    coor_gt = coor_gt * vis_gt
+    coor_pred = (coor_gt + 0.02 * torch.randn(n, L, 2)).clamp(0, 1) * vis_gt
+    mask = torch.from_numpy(np.random.binomial(1, 0.3, size=(n, L))).float().unsqueeze(-1)
+    inpaint_mask = torch.logical_and(vis_gt, mask).int()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    opt.zero_grad()
+    x_in = coor_pred * (1 - inpaint_mask)
+    refine = net(x_in, inpaint_mask)
+    loss = torch.nn.MSELoss()(refine * inpaint_mask, coor_gt * inpaint_mask)
+    loss.backward()
+    grads = {k: p.grad.detach().clone().numpy() for k, p in net.named_parameters()}
+    total_norm = torch.nn.utils.clip_grad_norm_(net.parameters(), 1)
+    clipped = {k: p.grad.detach().clone().numpy() for k, p in net.named_parameters()}
+    opt.step()
+    after = {k: v.detach().numpy() for k, v in net.state_dict().items()}
+    out = {"seed": 5, "coor_gt": coor_gt.numpy(), "coor_pred": coor_pred.numpy(), "vis_gt": vis_gt.numpy(),
+           "mask": mask.numpy(), "refine": refine.detach().numpy(), "loss": loss.item(),
+           "total_norm": float(total_norm)}
+    for k in grads:  # full gradients; clipped gradients and updated parameters as (sum, |sum|, max, 16 samples)
+        out["grad/" + k] = grads[k]
+        out["clipped/" + k] = grad_stats(torch.from_numpy(clipped[k]))
+        out["after/" + k] = grad_stats(torch.from_numpy(after[k]))
+    np.savez_compressed(f"{OUT}/inpaintnet_train.npz", **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     refmodel = load_module("ref_model", f"{REF}/model.py")
+    if len(sys.argv) > 1 and sys.argv[1] == "inpaint_train":  # regenerate only this fixture
+        gen_inpaint_train(refmodel)
+        print("inpaintnet_train.npz written")
+        return
     refmetric = load_module("ref_metric", f"{REF}/utils/metric.py")
     import cv2
     env = {"np": np, "cv2": cv2, "torch": torch, "math": math}
@@ -142,6 +182,8 @@ def main():
     with torch.no_grad():
         out = net(coor, mask)
     np.savez_compressed(f"{OUT}/inpaintnet.npz", seed=7, coor=coor.numpy(), mask=mask.numpy(), out=out.numpy())
+
+    gen_inpaint_train(refmodel)
 
     # ---- small host-side pieces: ensemble weights, mixup ----
     ew = {f"weight_{L}": env["get_ensemble_weight"](L, "weight").numpy() for L in (1, 4, 7, 8)}

@@ -195,3 +195,27 @@ def inpaint_blend(coor_pred, coor_inpaint, mask):
     out = out.clone()
     out[th] = 0.0
     return out
+
+
+def get_random_mask(mask_size, mask_ratio):
+    """train.py:42-57: Bernoulli(mask_ratio) mask of shape (N, L, 1), 1 = masked; numpy's global RNG, as there."""
+    return torch.from_numpy(np.random.binomial(1, mask_ratio, size=mask_size)).float().unsqueeze(-1)
+
+
+def inpaintnet_loss_and_grads(sd, coor_pred, coor_gt, vis_gt, mask):
+    """The arithmetic of one InpaintNet train step up to the gradients (reference train.py:151-163):
+    inpaint_mask = vis_gt AND mask; masked input coordinates are zeroed; MSE between the masked prediction and
+    the masked ground truth (mean over ALL N*L*2 entries, nn.MSELoss default). Returns refine, loss, {key: grad}."""
+    inpaint_mask = torch.logical_and(vis_gt, mask).int()
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    refine = inpaintnet_forward(params, coor_pred * (1 - inpaint_mask), inpaint_mask.to(coor_pred.dtype))
+    loss = F.mse_loss(refine * inpaint_mask, coor_gt * inpaint_mask)
+    grads = torch.autograd.grad(loss, list(params.values()))
+    return refine.detach(), loss.detach(), dict(zip(params.keys(), grads))
+
+
+def clip_grad_norm(grads, max_norm=1.0):
+    """nn.utils.clip_grad_norm_ (train.py:161): global L2 norm, scale by max_norm / (norm + 1e-6) clamped to 1."""
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).float()
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    return total, {k: g * coef for k, g in grads.items()}

@@ -129,3 +129,21 @@ def test_decode_oracle_matches_live_cv2():
         assert tuple(D.predict_location(mask)) == cv2_ref(mask)
 
     check()
+
+
+def test_inpaintnet_train_step_matches_reference(golden_dir):
+    """oracle restatement of train.py:147-166 vs the real reference module's step (oracle/gen_golden.py)."""
+    g = _load(golden_dir, "inpaintnet_train.npz")
+    sd = O.init_inpaintnet_state(int(g["seed"]))
+    t = lambda k: torch.from_numpy(g[k])
+    refine, loss, grads = O.inpaintnet_loss_and_grads(sd, t("coor_pred"), t("coor_gt"), t("vis_gt"), t("mask"))
+    assert (refine - t("refine")).abs().max() < 1e-6
+    assert abs(loss.item() - float(g["loss"])) < 1e-7
+    for k, gr in grads.items():
+        ref = t("grad/" + k)
+        assert (gr - ref).abs().max() <= 1e-5 * ref.abs().max() + 1e-9, k
+    total, clipped = O.clip_grad_norm(grads, 1.0)
+    assert abs(total.item() - float(g["total_norm"])) < 1e-5 * float(g["total_norm"])
+    for k, gr in clipped.items():
+        st = g["clipped/" + k]
+        assert abs(gr.double().sum().item() - st[0]) <= 1e-5 * st[1] + 1e-9, k

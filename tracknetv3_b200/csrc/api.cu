@@ -108,6 +108,16 @@ int tnb_inpaintnet_fwd(const float* coords, const float* mask, const void* const
   for (int i = 0; i < 9; ++i) { p.w[i] = (const float*)params[2 * i]; p.b[i] = (const float*)params[2 * i + 1]; }
   return launch_inpaint_fwd(coords, mask, p, n, l, out, ST(stream));
 }
+int tnb_inpaintnet_bwd(const float* coords, const float* mask, const void* const* params, const float* dout,
+                       void* const* grads, int n, int l, float* dcoords, void* stream) {
+  InpaintParams p;
+  InpaintGrads g;
+  for (int i = 0; i < 9; ++i) {
+    p.w[i] = (const float*)params[2 * i]; p.b[i] = (const float*)params[2 * i + 1];
+    g.w[i] = (float*)grads[2 * i];        g.b[i] = (float*)grads[2 * i + 1];
+  }
+  return launch_inpaint_bwd(coords, mask, p, dout, g, n, l, dcoords, ST(stream));
+}
 
 size_t tnb_tracknet_workspace_bytes(const tnb_tracknet_cfg_t* cfg) { return tracknet_workspace_bytes(*cfg); }
 int tnb_tracknet_forward(const tnb_tracknet_cfg_t* cfg, const float* x, void* const* params, float* y, void* ws,

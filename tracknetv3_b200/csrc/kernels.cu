@@ -886,4 +886,142 @@ int launch_inpaint_fwd(const float* coords, const float* mask, const InpaintPara
   return 0;
 }
 
+
+// =============================================================================================
+// InpaintNet backward (autograd of reference model.py:113-129 as used by train.py:147-166): ONE kernel,
+// one CTA per trajectory. The forward is recomputed into shared memory (nothing is saved between the
+// two launches), then every layer's activation gradient, weight gradient and bias gradient is formed
+// from the shared-memory activations; parameter gradients are summed over trajectories with
+// red.global.add.f32 into caller-zeroed buffers.
+// =============================================================================================
+TNB_DEVINL void act_bwd(float* g, const float* a, int n, int act) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = a[i];
+    g[i] *= act == 1 ? (v > 0.f ? 1.f : 0.01f) : v * (1.f - v);  // LeakyReLU(0.01) / sigmoid, from the outputs
+  }
+  __syncthreads();
+}
+// dW[co][ci][k] += sum_l dz[co][l] * in[ci][l+k-1];  db[co] += sum_l dz[co][l]
+TNB_DEVINL void conv1d_k3_wgrad(const float* dz, int Cout, const float* inA, int CA, const float* inB, int CB,
+                                float* __restrict__ dw, float* __restrict__ db, int L) {
+  const int Cin = CA + CB, total = Cout * Cin * 3;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int co = idx / (Cin * 3), r = idx - co * Cin * 3, ci = r / 3, k = r - ci * 3;
+    const float* row = ci < CA ? inA + ci * L : inB + (ci - CA) * L;
+    const float* g = dz + co * L;
+    const int lo = k == 0 ? 1 : 0, hi = k == 2 ? L - 1 : L;
+    float s = 0.f;
+    for (int l = lo; l < hi; ++l) s = fmaf(g[l], row[l + k - 1], s);
+    atomicAdd(dw + idx, s);
+  }
+  for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s += dz[co * L + l];
+    atomicAdd(db + co, s);
+  }
+}
+// dIn[ci][l] (+)= sum_co sum_k dz[co][l+1-k] * w[co][ci_off+ci][k] for the C channels starting at ci_off
+TNB_DEVINL void conv1d_k3_dgrad(const float* dz, int Cout, const float* __restrict__ w, int Cin, int ci_off, int C,
+                                float* dIn, int L, bool accumulate) {
+  for (int idx = threadIdx.x; idx < C * L; idx += blockDim.x) {
+    const int ci = idx / L, l = idx - ci * L;
+    const float* wq = w + (size_t)(ci_off + ci) * 3;
+    float s = 0.f;
+    for (int co = 0; co < Cout; ++co) {
+      const float* g = dz + co * L;
+      const float* wr = wq + (size_t)co * Cin * 3;
+      const float gp = l + 1 < L ? g[l + 1] : 0.f, gm = l > 0 ? g[l - 1] : 0.f;
+      s = fmaf(gp, __ldg(wr), s); s = fmaf(g[l], __ldg(wr + 1), s); s = fmaf(gm, __ldg(wr + 2), s);
+    }
+    dIn[idx] = accumulate ? dIn[idx] + s : s;
+  }
+}
+__global__ void __launch_bounds__(512) inpaint_bwd_kernel(const float* __restrict__ coords,
+                                                          const float* __restrict__ mask, InpaintParams P,
+                                                          const float* __restrict__ dout, InpaintGrads G, int L,
+                                                          float* __restrict__ dcoords) {
+  extern __shared__ float sm[];
+  float* in0 = sm;            float* x1 = in0 + 3 * L;   float* x2 = x1 + 32 * L;  float* x3 = x2 + 64 * L;
+  float* t1 = x3 + 128 * L;   float* t2 = t1 + 256 * L;  float* u1 = t2 + 256 * L;  float* u2 = u1 + 128 * L;
+  float* u3 = u2 + 64 * L;    float* o = u3 + 32 * L;
+  float* g_in0 = o + 2 * L;   float* g_x1 = g_in0 + 3 * L; float* g_x2 = g_x1 + 32 * L; float* g_x3 = g_x2 + 64 * L;
+  float* g_t1 = g_x3 + 128 * L; float* g_t2 = g_t1 + 256 * L; float* g_u1 = g_t2 + 256 * L; float* g_u2 = g_u1 + 128 * L;
+  float* g_u3 = g_u2 + 64 * L;  float* g_o = g_u3 + 32 * L;
+  const int n = blockIdx.x;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    in0[0 * L + i] = coords[((size_t)n * L + i) * 2 + 0];
+    in0[1 * L + i] = coords[((size_t)n * L + i) * 2 + 1];
+    in0[2 * L + i] = mask[(size_t)n * L + i];
+  }
+  for (int i = threadIdx.x; i < L * 2; i += blockDim.x) g_o[(i & 1) * L + (i >> 1)] = dout[(size_t)n * L * 2 + i];
+  __syncthreads();
+  conv1d_k3(x1, 32, in0, 3, nullptr, 0, P.w[0], P.b[0], L, 1);
+  conv1d_k3(x2, 64, x1, 32, nullptr, 0, P.w[1], P.b[1], L, 1);
+  conv1d_k3(x3, 128, x2, 64, nullptr, 0, P.w[2], P.b[2], L, 1);
+  conv1d_k3(t1, 256, x3, 128, nullptr, 0, P.w[3], P.b[3], L, 1);
+  conv1d_k3(t2, 256, t1, 256, nullptr, 0, P.w[4], P.b[4], L, 1);
+  conv1d_k3(u1, 128, t2, 256, x3, 128, P.w[5], P.b[5], L, 1);
+  conv1d_k3(u2, 64, u1, 128, x2, 64, P.w[6], P.b[6], L, 1);
+  conv1d_k3(u3, 32, u2, 64, x1, 32, P.w[7], P.b[7], L, 1);
+  conv1d_k3(o, 2, u3, 32, nullptr, 0, P.w[8], P.b[8], L, 2);
+  // predictor
+  act_bwd(g_o, o, 2 * L, 2);
+  conv1d_k3_wgrad(g_o, 2, u3, 32, nullptr, 0, G.w[8], G.b[8], L);
+  conv1d_k3_dgrad(g_o, 2, P.w[8], 32, 0, 32, g_u3, L, false);
+  __syncthreads();
+  // up_3 on cat([u2, x1])
+  act_bwd(g_u3, u3, 32 * L, 1);
+  conv1d_k3_wgrad(g_u3, 32, u2, 64, x1, 32, G.w[7], G.b[7], L);
+  conv1d_k3_dgrad(g_u3, 32, P.w[7], 96, 0, 64, g_u2, L, false);
+  conv1d_k3_dgrad(g_u3, 32, P.w[7], 96, 64, 32, g_x1, L, false);
+  __syncthreads();
+  // up_2 on cat([u1, x2])
+  act_bwd(g_u2, u2, 64 * L, 1);
+  conv1d_k3_wgrad(g_u2, 64, u1, 128, x2, 64, G.w[6], G.b[6], L);
+  conv1d_k3_dgrad(g_u2, 64, P.w[6], 192, 0, 128, g_u1, L, false);
+  conv1d_k3_dgrad(g_u2, 64, P.w[6], 192, 128, 64, g_x2, L, false);
+  __syncthreads();
+  // up_1 on cat([t2, x3])
+  act_bwd(g_u1, u1, 128 * L, 1);
+  conv1d_k3_wgrad(g_u1, 128, t2, 256, x3, 128, G.w[5], G.b[5], L);
+  conv1d_k3_dgrad(g_u1, 128, P.w[5], 384, 0, 256, g_t2, L, false);
+  conv1d_k3_dgrad(g_u1, 128, P.w[5], 384, 256, 128, g_x3, L, false);
+  __syncthreads();
+  // buttleneck.conv_2, conv_1
+  act_bwd(g_t2, t2, 256 * L, 1);
+  conv1d_k3_wgrad(g_t2, 256, t1, 256, nullptr, 0, G.w[4], G.b[4], L);
+  conv1d_k3_dgrad(g_t2, 256, P.w[4], 256, 0, 256, g_t1, L, false);
+  __syncthreads();
+  act_bwd(g_t1, t1, 256 * L, 1);
+  conv1d_k3_wgrad(g_t1, 256, x3, 128, nullptr, 0, G.w[3], G.b[3], L);
+  conv1d_k3_dgrad(g_t1, 256, P.w[3], 128, 0, 128, g_x3, L, true);
+  __syncthreads();
+  // down_3, down_2, down_1
+  act_bwd(g_x3, x3, 128 * L, 1);
+  conv1d_k3_wgrad(g_x3, 128, x2, 64, nullptr, 0, G.w[2], G.b[2], L);
+  conv1d_k3_dgrad(g_x3, 128, P.w[2], 64, 0, 64, g_x2, L, true);
+  __syncthreads();
+  act_bwd(g_x2, x2, 64 * L, 1);
+  conv1d_k3_wgrad(g_x2, 64, x1, 32, nullptr, 0, G.w[1], G.b[1], L);
+  conv1d_k3_dgrad(g_x2, 64, P.w[1], 32, 0, 32, g_x1, L, true);
+  __syncthreads();
+  act_bwd(g_x1, x1, 32 * L, 1);
+  conv1d_k3_wgrad(g_x1, 32, in0, 3, nullptr, 0, G.w[0], G.b[0], L);
+  if (dcoords != nullptr) {  // gradient w.r.t. the (N, L, 2) coordinates (the mask channel gets none)
+    conv1d_k3_dgrad(g_x1, 32, P.w[0], 3, 0, 2, g_in0, L, false);
+    __syncthreads();
+    for (int i = threadIdx.x; i < L * 2; i += blockDim.x) dcoords[(size_t)n * L * 2 + i] = g_in0[(i & 1) * L + (i >> 1)];
+  }
+}
+int launch_inpaint_bwd(const float* coords, const float* mask, const InpaintParams& p, const float* dout,
+                       const InpaintGrads& g, int N, int L, float* dcoords, cudaStream_t st) {
+  if (N == 0) return 0;
+  const size_t smem = (size_t)2 * (3 + 32 + 64 + 128 + 256 + 256 + 128 + 64 + 32 + 2) * L * sizeof(float);
+  TNB_REQUIRE(smem <= 227 * 1024, "inpaint_bwd: sequence length %d too long for the fused kernel (max 28)", L);
+  TNB_CHECK_CUDA(cudaFuncSetAttribute(inpaint_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  inpaint_bwd_kernel<<<N, 512, smem, st>>>(coords, mask, p, dout, g, L, dcoords);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace tnb

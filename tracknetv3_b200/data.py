@@ -8,15 +8,37 @@ class DevicePrefetcher:
 
     The copy of batch k+1 is enqueued on a dedicated CUDA stream as soon as batch k is handed out, so it overlaps
     with the compute of batch k; the consumer's stream waits on the copy's event, no host synchronisation.
+    Two fixed sets of device buffers are cycled (no allocator traffic in the loop): a yielded batch is valid until
+    the next-but-one ``next()`` call, which is what a train / predict loop needs.
     """
 
     def __init__(self, host_batches, device=None):
         self.it = iter(host_batches)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = [None, None]     # device buffers of each slot
+        self.release = [None, None]   # event on the consumer stream after which the slot may be overwritten
+        self.count = 0
         self.next = None
         self.event = None
         self._preload()
+
+    def _buffers(self, slot, batch):
+        bufs = self.slots[slot]
+        ok = bufs is not None and len(bufs) == len(batch) and all(
+            (not torch.is_tensor(t)) or (b.shape == t.shape and b.dtype == t.dtype) for b, t in zip(bufs, batch))
+        if not ok:
+            cur = torch.cuda.current_stream(self.device)
+            bufs = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) if torch.is_tensor(t) else t
+                         for t in batch)
+            for b in bufs:
+                if torch.is_tensor(b):
+                    b.record_stream(self.stream)  # freed memory must also wait for the copy stream
+            ev = torch.cuda.Event()
+            ev.record(cur)                        # allocation-order safety: copy only after `cur` got here
+            self.release[slot] = ev
+            self.slots[slot] = bufs
+        return bufs
 
     def _preload(self):
         try:
@@ -24,10 +46,18 @@ class DevicePrefetcher:
         except StopIteration:
             self.next = None
             return
+        slot = self.count & 1
+        self.count += 1
+        bufs = self._buffers(slot, batch)
         with torch.cuda.stream(self.stream):
-            self.next = tuple(t.to(self.device, non_blocking=True) if torch.is_tensor(t) else t for t in batch)
+            if self.release[slot] is not None:
+                self.stream.wait_event(self.release[slot])
+            for b, t in zip(bufs, batch):
+                if torch.is_tensor(t):
+                    b.copy_(t, non_blocking=True)
             self.event = torch.cuda.Event()
             self.event.record(self.stream)
+        self.next = (slot, bufs)
 
     def __iter__(self):
         return self
@@ -37,9 +67,10 @@ class DevicePrefetcher:
             raise StopIteration
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(self.event)
-        batch = self.next
-        for t in batch:
-            if torch.is_tensor(t):
-                t.record_stream(cur)  # the caching allocator must not recycle it while `cur` still uses it
+        slot, batch = self.next
+        # everything that used the other slot has been enqueued on `cur` by now: it may be refilled after this point
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.release[1 - slot] = ev
         self._preload()
         return batch

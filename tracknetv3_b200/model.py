@@ -166,11 +166,40 @@ class Double1DConv(nn.Module):
         self.conv_2 = Conv1DBlock(out_dim, out_dim)
 
 
-class InpaintNet(nn.Module):
-    """Drop-in for reference ``model.InpaintNet`` (model.py:100-129); forward is one fused kernel.
+class _InpaintNetFunction(torch.autograd.Function):
+    """autograd bridge: forward = tnb_inpaintnet_fwd, backward = tnb_inpaintnet_bwd (recomputes the forward)."""
 
-    Inference only in this round: ``forward`` does not record an autograd graph.
-    """
+    @staticmethod
+    def forward(ctx, x, m, module, *params):
+        lib = _lib.load()
+        n, l = x.shape[0], x.shape[1]
+        out = torch.empty((n, l, 2), dtype=torch.float32, device=x.device)
+        _lib.check(lib.tnb_inpaintnet_fwd(x.data_ptr(), m.data_ptr(), _lib.ptr_array(params), n, l,
+                                          out.data_ptr(), _lib.stream_ptr()))
+        ctx.save_for_backward(x, m, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        x, m, *params = ctx.saved_tensors
+        n, l = x.shape[0], x.shape[1]
+        flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=x.device)
+        grads, off = [], 0
+        for p in params:
+            grads.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dout = dout.contiguous().float()
+        _lib.check(lib.tnb_inpaintnet_bwd(x.data_ptr(), m.data_ptr(), _lib.ptr_array(params), dout.data_ptr(),
+                                          _lib.ptr_array(grads), n, l, dx.data_ptr() if dx is not None else None,
+                                          _lib.stream_ptr()))
+        return (dx, None, None) + tuple(grads)
+
+
+class InpaintNet(nn.Module):
+    """Drop-in for reference ``model.InpaintNet`` (model.py:100-129): forward is one fused kernel, and so is its
+    autograd backward (what ``train.py:147-166`` needs)."""
 
     def __init__(self):
         super(InpaintNet, self).__init__()
@@ -194,17 +223,11 @@ class InpaintNet(nn.Module):
 
     def forward(self, x, m):
         _lib.require_cuda(x, m)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise RuntimeError("tracknet_b200: InpaintNet training (backward) is not implemented; "
-                               "call under torch.no_grad() / model.eval()")
-        lib = _lib.load()
-        n, l = x.shape[0], x.shape[1]
+        if x.dim() != 3 or x.shape[2] != 2 or m.dim() != 3 or m.shape[2] != 1 or m.shape[:2] != x.shape[:2]:
+            raise RuntimeError(f"InpaintNet expects x (N, L, 2) and m (N, L, 1), got {tuple(x.shape)} {tuple(m.shape)}")
         x = x.contiguous().float()
         m = m.contiguous().float()
-        out = torch.empty((n, l, 2), dtype=torch.float32, device=x.device)
         tensors = self._param_tensors()
         for t in tensors:
             _lib.require_cuda(t)
-        _lib.check(lib.tnb_inpaintnet_fwd(x.data_ptr(), m.data_ptr(), _lib.ptr_array(tensors), n, l,
-                                          out.data_ptr(), _lib.stream_ptr()))
-        return out
+        return _InpaintNetFunction.apply(x, m, self, *tensors)

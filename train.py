@@ -1,4 +1,5 @@
-"""Hot-path subset of the reference's train.py: `mixup` (:19-40) and the TrackNet step loop (:59-121).
+"""Hot-path subset of the reference's train.py: `mixup` (:19-40), `get_random_mask` (:42-57), the TrackNet step loop
+(:59-121) and the InpaintNet step loop (:123-177).
 
 Dataset / TensorBoard / checkpoint plumbing of the reference's __main__ is out of scope;
 `train_tracknet` accepts any iterable yielding the reference's (i, x, y, c, _) tuples and runs the step of
@@ -47,6 +48,34 @@ def train_tracknet(model, optimizer, data_loader, param_dict):
         loss = WBCELoss(y_pred, y)
         epoch_loss.append(loss.item())
         loss.backward()
+        optimizer.step()
+    return float(np.mean(epoch_loss))
+
+
+def get_random_mask(mask_size, mask_ratio):
+    """ Generate random mask by binomial distribution (1 = masked): same numpy draw as reference :54, (N, L, 1). """
+    mask = np.random.binomial(1, mask_ratio, size=mask_size)
+    mask = torch.from_numpy(mask).float().cuda().unsqueeze(-1)
+    return mask
+
+
+def train_inpaintnet(model, optimizer, data_loader, param_dict):
+    """ Train InpaintNet model for one epoch (step semantics of reference :147-163): random mask AND visibility,
+        masked coordinates zeroed, MSE on the masked entries, clip_grad_norm_(1), optimizer step. Returns mean loss.
+        The model's forward and backward are one kernel each; the few (N, L, 2)-sized loss ops stay torch ops. """
+    model.train()
+    epoch_loss = []
+    for step, (_, coor_pred, coor_gt, _, vis_gt, _) in enumerate(data_loader):
+        optimizer.zero_grad()
+        coor_pred, coor_gt, vis_gt = coor_pred.float().cuda(), coor_gt.float().cuda(), vis_gt.float().cuda()
+        mask = get_random_mask(mask_size=coor_gt.shape[:2], mask_ratio=param_dict['mask_ratio']).cuda()  # (N, L, 1)
+        inpaint_mask = torch.logical_and(vis_gt, mask).int()  # visible and masked area
+        coor_pred = coor_pred * (1 - inpaint_mask)  # masked area is set to 0
+        refine_coor = model(coor_pred, inpaint_mask)
+        loss = torch.nn.MSELoss()(refine_coor * inpaint_mask, coor_gt * inpaint_mask)
+        epoch_loss.append(loss.item())
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1)
         optimizer.step()
     return float(np.mean(epoch_loss))
 
