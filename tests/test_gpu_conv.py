@@ -146,6 +146,34 @@ def test_conv3x3_wgrad(n, h, w, cin, cin_real, cout, terms):
     assert G.rel_err(dw, wt.grad) < (2e-4 if terms == 3 else 2e-2)
 
 
+@pytest.mark.parametrize("terms", [3, 1])
+@pytest.mark.parametrize("n,h,w,cin,cin_real", [
+    (1, 8, 16, 32, 27),       # first layer: 32-channel tile, rows {dy 0 | 1 | 2 | unused}
+    (2, 16, 32, 64, 64),      # 64-channel tile, rows {dy | dy + 1}
+    (1, 21, 37, 64, 64),      # ragged tiles on both axes
+    (2, 12, 40, 192, 192),    # up_block_3.conv_1: three ci tiles
+    (1, 4, 16, 128, 128),     # a single K tile per CTA
+])
+def test_conv3x3_wgrad_tap_stacked(n, h, w, cin, cin_real, terms):
+    """Cout = 64 with a pre-split view takes the tap-stacked kernel (two filter rows per MMA); the generic kernel on
+    the same operands (variant bit 32) must agree with it and both with the oracle op."""
+    cout = 64
+    x = _rand(n, cin, h, w, seed=23)
+    x[:, cin_real:] = 0
+    dz = _rand(n, cout, h, w, seed=24, scale=1e-5)
+    wt = torch.zeros(cout, cin_real, 3, 3, requires_grad=True)
+    (F.conv2d(x[:, :cin_real], wt, padding=1) * dz).sum().backward()
+    t, d = G.nhwc(x), G.nhwc(dz)
+    ts = G.presplit(t)
+    src = _lib.Src(ptr=ts.data_ptr(), scale=None, shift=None, C=cin, Hs=h, Ws=w, mode=_lib.SRC_PRESPLIT)
+    dw = G.wgrad3x3(G.make_view([src], n, h, w), d, cout, cin_real, terms=terms)
+    tol = 2e-4 if terms == 3 else 2e-2
+    assert G.rel_err(dw, wt.grad) < tol
+    dw_generic = G.wgrad3x3(G.make_view([src], n, h, w), d, cout, cin_real, terms=terms, variant=32)
+    assert G.rel_err(dw_generic, wt.grad) < tol
+    assert G.rel_err(dw, dw_generic) < (1e-5 if terms == 3 else 1e-3)
+
+
 def test_conv3x3_full_resolution_layer_vs_torch_cuda():
     """down_block_1.conv_2 shape at the reference resolution (64->64 @ 288x512), checked on-device against
     torch's fp32 convolution (TF32 disabled) - the oracle op, just executed on the GPU for speed."""

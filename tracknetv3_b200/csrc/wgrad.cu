@@ -326,6 +326,243 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   }
 }
 
+// =============================================================================================
+// Tap-stacked variant for 64 output channels (the full-resolution layers, where the generic kernel wastes half of
+// every MMA's M = 128 rows on zero planes and runs three CTAs - one per filter row - over the same pixels).
+//
+// Roles are swapped: M = input channels, N = 64 output channels, and the input halo tile is stored
+// [halo row][plane = 8 channels][halo column][16 B]. With SBO = one plane (RP bytes) the 16 eight-channel row groups
+// of an M = 128 operand walk 8 planes of halo row r and then - with no gap - the 8 planes of halo row r + 1: ONE
+// tcgen05.mma computes the taps (dy, dx) and (dy + 1, dx) of a 64-channel tile (or dy = 0..3 of a 32-channel tile)
+// from the same shared-memory bytes. A CTA therefore owns all 9 taps: 6 MMAs per K step instead of 9 (3 for the
+// 27(32)-channel first layer), the dz tile and the input tile are fetched once instead of three times.
+// Accumulators (TMEM columns): [dx] = rows {dy 0 | dy 1}, [3 + dx] = rows {dy 2 | unused}; 32-channel tiles: [dx] =
+// rows {dy 0 | 1 | 2 | unused}. Both operands must be pre-split bf16 (tnb_view_presplit / BatchNorm backward).
+// =============================================================================================
+static constexpr int kSStages = 4;
+static constexpr int kSRP = 19 * 16;        // bytes per (halo row, plane): 18 columns + 1 pad (odd -> spread banks)
+static constexpr int kSRows = kTileH + 3;   // 6 halo rows filled + 1 slack row read by the unused half of dy = 2
+
+struct WgradSArgs {
+  const uint8_t* view;  // pre-split bf16 [N,H,W][2][C]
+  const uint8_t* dz;    // pre-split bf16 [N,H,W][2][Cout]
+  float* dw;
+  int N, H, W, C, Cout, CinReal, P /*planes per ci tile: 8 or 4*/, nterms, ncit, ncot;
+  int tiles_h, tiles_w, ktiles, ktiles_per_cta;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __grid_constant__ WgradSArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int P = a.P, CI = P * 8;
+  const int TP = a.nterms > 1 ? 2 : 1;
+  const int DZPL = pad_px(kTileH * kTileW) * 16;
+  const int A_TERM = kSRows * P * kSRP;  // one term of the input tile
+  const int A_BYTES = TP * A_TERM;
+  const int B_TERM = 8 * DZPL;
+  const int STAGE = A_BYTES + TP * B_TERM;
+  constexpr int S = kSStages;
+  const int nacc = P == 8 ? 6 : 3;
+
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + S;
+  uint64_t* tmem_full = full + 2 * S;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(full + 2 * S + 1);
+  uint8_t* st_base = smem + kHdrBytes;
+
+  const int ci0 = (blockIdx.x % a.ncit) * CI;
+  const int co0 = (blockIdx.x / a.ncit) * 64;
+  const int kt0 = blockIdx.y * a.ktiles_per_cta;
+  const int kt1 = min(a.ktiles, kt0 + a.ktiles_per_cta);
+  const int tmem_cols = 512;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int i = 0; i < S; ++i) { mbar_init(&full[i], kFillThreads); mbar_init(&empty[i], 1); }
+      mbar_init(tmem_full, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, tmem_cols);
+  }
+  // the slack halo row is never written by the fill: clear it once (its products land in accumulator rows nobody reads,
+  // but they should not be signalling garbage)
+  for (int i = tid; i < S * TP * P * (kSRP / 16); i += kThreads) {
+    int r = i;
+    const int c = r % (kSRP / 16); r /= (kSRP / 16);
+    const int pl = r % P; r /= P;
+    const int term = r % TP; r /= TP;
+    *reinterpret_cast<uint4*>(st_base + r * STAGE + term * A_TERM + ((kSRows - 1) * P + pl) * kSRP + c * 16) =
+        make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      const bool lead = elect_one();
+      const uint32_t idesc = make_idesc(128, 64, 1, 1, 1);  // bf16 x bf16, both operands MN-major
+      const uint64_t a_desc0 = make_smem_desc(smem_u32(st_base), 128, kSRP);
+      const uint64_t b_desc0 = make_smem_desc(smem_u32(st_base) + A_BYTES, 128, DZPL);
+      const uint32_t stage16 = STAGE >> 4, a_lo16 = A_TERM >> 4, b_lo16 = B_TERM >> 4;
+      const uint32_t row16 = (P * kSRP) >> 4;  // one halo row of the input tile
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kt = kt0; kt < kt1; ++kt) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint64_t a_st = a_desc0 + (uint64_t)(s * stage16);
+        const uint64_t b_st = b_desc0 + (uint64_t)(s * stage16);
+        for (int acc_i = 0; acc_i < nacc; ++acc_i) {  // one accumulator = one chain of 4 rows x nterms MMAs
+          const int dx = acc_i % 3, dyb = (acc_i / 3) * 2;
+          const uint32_t d_tmem = tmem_base + acc_i * 64;
+#pragma unroll
+          for (int r = 0; r < kTileH; ++r) {
+            const uint64_t a_hi = a_st + (uint64_t)((r + dyb) * row16 + dx);
+            const uint64_t b_hi = b_st + (uint64_t)(r * kTileW);
+            const uint32_t acc = (kt != kt0 || r != 0);
+            if (lead) {
+              umma_f16(d_tmem, a_hi, b_hi, idesc, acc);
+              if (a.nterms > 1) {
+                umma_f16(d_tmem, a_hi + a_lo16, b_hi, idesc, 1);
+                umma_f16(d_tmem, a_hi, b_hi + b_lo16, idesc, 1);
+              }
+            }
+          }
+        }
+        if (lead) umma_commit(&empty[s]);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+      if (lead) umma_commit(tmem_full);
+      __syncwarp();
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    const int ftid = tid - 128;
+    // The copy list of a K tile is the same for every tile: item -> (shared offset, pixel offset, channel offset).
+    // dz items: 64 pixels x 8 planes; input items: 6 x 18 halo pixels x P planes. 8 (or P) neighbouring threads copy
+    // the 128 (64) contiguous bytes of one pixel.
+    constexpr int MAXI = 4;
+    const int ndz = kTileH * kTileW * 8, nin = (kTileH + 2) * kHaloW * P;
+    uint32_t soff[MAXI];
+    int dh[MAXI], dwv[MAXI], goff[MAXI];
+    bool isdz[MAXI], act[MAXI];
+#pragma unroll
+    for (int u = 0; u < MAXI; ++u) {
+      const int it = ftid + u * kFillThreads;
+      act[u] = it < ndz + nin;
+      isdz[u] = it < ndz;
+      if (isdz[u]) {
+        const int pl = it & 7, px = it >> 3;
+        soff[u] = A_BYTES + pl * DZPL + px * 16;
+        dh[u] = px >> 4; dwv[u] = px & 15;
+        goff[u] = (co0 + pl * 8) * 2;
+      } else {
+        const int j = it - ndz;
+        const int pl = j % P, hp = j / P;
+        const int hr = hp / kHaloW, hc = hp - hr * kHaloW;
+        soff[u] = (hr * P + pl) * kSRP + hc * 16;
+        dh[u] = hr - 1; dwv[u] = hc - 1;
+        goff[u] = (ci0 + pl * 8) * 2;
+      }
+    }
+    const size_t dz_stride = (size_t)a.Cout * 4, v_stride = (size_t)a.C * 4;
+    const int dz_lo = a.Cout * 2, v_lo = a.C * 2;
+    const int per_img = a.tiles_h * a.tiles_w;
+
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kt = kt0; kt < kt1; ++kt) {
+      const int n = kt / per_img;
+      const int rem = kt - n * per_img;
+      const int th = rem / a.tiles_w;
+      const int h0 = th * kTileH, w0 = (rem - th * a.tiles_w) * kTileW;
+      mbar_wait(&empty[s], ph ^ 1);
+      uint8_t* stage = st_base + s * STAGE;
+#pragma unroll
+      for (int u = 0; u < MAXI; ++u) {
+        if (act[u]) {
+          const int h = h0 + dh[u], w = w0 + dwv[u];
+          const bool ok = h >= 0 && h < a.H && w >= 0 && w < a.W;
+          const size_t pix = (size_t)(n * a.H + h) * a.W + w;
+          const uint8_t* q = isdz[u] ? (ok ? a.dz + pix * dz_stride + goff[u] : a.dz)
+                                     : (ok ? a.view + pix * v_stride + goff[u] : a.view);
+          cp_async16(stage + soff[u], q, ok ? 16u : 0u);
+          if (a.nterms > 1)
+            cp_async16(stage + soff[u] + (isdz[u] ? B_TERM : A_TERM), q + (isdz[u] ? dz_lo : v_lo), ok ? 16u : 0u);
+        }
+      }
+      cp_async_mbar_arrive_noinc(&full[s]);
+      if (++s == S) { s = 0; ph ^= 1; }
+    }
+
+    if (warp < 8) {
+      const int q = warp & 3;
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      const int m = 32 * q + lane;  // accumulator row = (tap slot, input channel)
+      const int slot = m / CI, ci = ci0 + m % CI;
+      for (int acc_i = 0; acc_i < nacc; ++acc_i) {
+        const int dx = acc_i % 3;
+        const int dy = P == 8 ? (acc_i / 3) * 2 + slot : slot;
+        const bool live = (P == 8 ? (acc_i < 3 || slot == 0) : slot < 3) && ci < a.CinReal && kt1 > kt0;
+        for (int col0 = 0; col0 < 64; col0 += 16) {
+          uint32_t rg[16];
+          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc_i * 64 + col0), rg);
+          tmem_ld_wait();
+          if (live) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              atomicAdd(a.dw + ((size_t)(co0 + col0 + j) * a.CinReal + ci) * 9 + dy * 3 + dx, __uint_as_float(rg[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+static bool stacked_applicable(const ViewDesc& view, int Cout) {
+  return Cout == 64 && view.C0 == view.C && view.s[0].mode == SRC_PRESPLIT && (view.C == 32 || view.C % 64 == 0) &&
+         view.s[0].Hs == view.H && view.s[0].Ws == view.W;
+}
+
+static int launch_wgrad3x3_stacked(const ViewDesc& view, const void* dz_presplit, float* dw, int Cout, int CinReal,
+                                   int nterms, cudaStream_t st) {
+  WgradSArgs a;
+  a.view = reinterpret_cast<const uint8_t*>(view.s[0].ptr); a.dz = (const uint8_t*)dz_presplit; a.dw = dw;
+  a.N = view.N; a.H = view.H; a.W = view.W; a.C = view.C; a.Cout = Cout; a.CinReal = CinReal; a.nterms = nterms;
+  a.P = view.C == 32 ? 4 : 8;
+  a.ncit = view.C / (a.P * 8); a.ncot = Cout / 64;
+  a.tiles_h = (view.H + kTileH - 1) / kTileH;
+  a.tiles_w = (view.W + kTileW - 1) / kTileW;
+  a.ktiles = view.N * a.tiles_h * a.tiles_w;
+  const int gx = a.ncit * a.ncot;
+  int splits = 148 / gx;
+  if (splits > (a.ktiles + 7) / 8) splits = (a.ktiles + 7) / 8;
+  if (splits < 1) splits = 1;
+  a.ktiles_per_cta = (a.ktiles + splits - 1) / splits;
+  splits = (a.ktiles + a.ktiles_per_cta - 1) / a.ktiles_per_cta;
+  const int TP = nterms > 1 ? 2 : 1;
+  const size_t smem = kHdrBytes + kSStages * (size_t)(TP * kSRows * a.P * kSRP + TP * 8 * pad_px(kTileH * kTileW) * 16);
+  TNB_REQUIRE(smem <= 232448, "wgrad3x3 (stacked): shared memory plan too large (%zu)", smem);
+  TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_stacked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope prof(PROF_WGRAD, st, view.N, view.H, view.W, view.C, Cout);
+  wgrad3x3_stacked_kernel<<<dim3(gx, splits), kThreads, smem, st>>>(a);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // input-channel tile: divides Cin and (for concat views) the first source, so that a CTA's channels come from ONE
 // source (one gather mode per CTA: no divergence between the up-sampled and the skip half)
 static int pick_nt(int cin, int c0) {
@@ -338,6 +575,8 @@ static int pick_nt(int cin, int c0) {
 int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, int Cout, int CinReal, int nterms,
                     int variant, cudaStream_t st) {
   TNB_REQUIRE(view.C % 32 == 0 && Cout % 64 == 0, "wgrad3x3: unsupported channels Cin=%d Cout=%d", view.C, Cout);
+  if (!(variant & 32) && stacked_applicable(view, Cout))  // variant bit 32: force the generic kernel (tests, ablation)
+    return launch_wgrad3x3_stacked(view, dz_presplit, dw, Cout, CinReal, nterms, st);
   WgradArgs a;
   a.view = view; a.dz = (const uint8_t*)dz_presplit; a.dw = dw; a.Cout = Cout; a.CinReal = CinReal;
   a.nterms = nterms; a.variant = variant; a.ci_tile_base = 0;
