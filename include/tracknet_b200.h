@@ -116,6 +116,16 @@ int tnb_conv3x3_stat_rows(int n, int h, int w, int cin, int cout, int terms);
 int tnb_conv3x3_fwd(const tnb_view_t* view, const uint16_t* wpack, float* out, float* stat_part, int cout,
                     int terms, int fmt, int variant, void* stream);
 
+/* dgrad (view = pre-split dz, weights packed with mode 1, fmt 1) fused with the reduction pass of the BatchNorm
+ * backward of the layer whose activation gradient it produces (autograd of model.py:13-15): `out` = dL/da of that
+ * layer, z/scale/shift/mean/invstd = that layer's raw conv output and BatchNorm constants (cout channels). The
+ * epilogue writes per-tile partials part[row][2][cout] = (sum g, sum g * xhat), g = out * [scale * z + shift > 0],
+ * xhat = (z - mean) * invstd, which tnb_bn_relu_bwd_finalize consumes; rows = tnb_conv3x3_dgrad_bnreduce_rows(). */
+int tnb_conv3x3_dgrad_bnreduce_rows(int n, int h, int w, int cin, int cout, int terms);
+int tnb_conv3x3_dgrad_bnreduce(const tnb_view_t* view, const uint16_t* wpack, float* out, float* part, int cout,
+                               int terms, const float* z, const float* scale, const float* shift, const float* mean,
+                               const float* invstd, void* stream);
+
 /* Weight gradient of the same convolution (autograd of model.py:13 via train.py:95):
  * dw[cout][cin_real][3][3] += sum dz * view. dw must be zeroed by the caller. dz is in the pre-split bf16 format
  * ([N,H,W,cout] logical); the view operand is split to bf16 on the fly. */

@@ -125,6 +125,45 @@ def test_conv3x3_dgrad(n, h, w, cin, cout, terms):
     assert G.rel_err(out2, out) < 1e-6
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 16, 16, 64, 64), (2, 20, 24, 128, 256), (1, 24, 40, 512, 512)])
+def test_conv3x3_dgrad_fused_bn_reduce(n, h, w, cin, cout):
+    """dgrad whose epilogue also produces the BatchNorm-backward reduction of the layer below (sum g, sum g*xhat with
+    g = dL/da masked by that layer's ReLU): the gradient itself is unchanged and the column sums match fp64."""
+    L = G.lib()
+    dz = _rand(n, cout, h, w, seed=31, scale=1e-6)
+    wt = _rand(cout, cin, 3, 3, seed=32, scale=0.2)
+    din = F.conv_transpose2d(dz, wt, padding=1)                 # dL/da of the producing layer (cin channels)
+    z = _rand(n, cin, h, w, seed=33)                            # that layer's raw conv output
+    gen = torch.Generator().manual_seed(34)
+    scale = torch.where(torch.arange(cin) % 5 == 0, -1.0, 1.0) * (torch.rand(cin, generator=gen) + 0.5)
+    shift = _rand(cin, seed=35, scale=0.3)
+    mean = _rand(cin, seed=36, scale=0.2)
+    invstd = torch.rand(cin, generator=gen) + 0.5
+    bc = lambda v: v[None, :, None, None]
+    g = torch.where(z * bc(scale) + bc(shift) > 0, din, torch.zeros_like(din)).double()
+    ref1 = g.sum((0, 2, 3))
+    ref2 = (g * ((z.double() - bc(mean).double()) * bc(invstd).double())).sum((0, 2, 3))
+    ts = G.presplit(G.nhwc(dz))
+    src = _lib.Src(ptr=ts.data_ptr(), scale=None, shift=None, C=cout, Hs=h, Ws=w, mode=_lib.SRC_PRESPLIT)
+    view = G.make_view([src], n, h, w)
+    wp = G.pack_weights(wt.to(G.DEV), 1, 1)
+    rows = L.tnb_conv3x3_dgrad_bnreduce_rows(n, h, w, cout, cin, 3)
+    out = torch.full((n, h, w, cin), float("nan"), device=G.DEV)
+    part = torch.full((rows, 2, cin), float("nan"), device=G.DEV)
+    dev = [t.to(G.DEV).contiguous() for t in (G.nhwc(z).cpu(), scale, shift, mean, invstd)]
+    _lib.check(L.tnb_conv3x3_dgrad_bnreduce(C.byref(view), wp.data_ptr(), out.data_ptr(), part.data_ptr(), cin, 3,
+                                            *[t.data_ptr() for t in dev], G.st()))
+    torch.cuda.synchronize()
+    assert G.rel_err(G.nchw(out), din) < 2e-4
+    sums = part.double().sum(0).cpu()
+    # a few ReLU masks sit within rounding of zero and dL/da carries the 2e-5 dgrad error: compare against the scale
+    # of the absolute column sums
+    tol1 = 3e-4 * g.abs().sum((0, 2, 3)) + 1e-12
+    assert ((sums[0] - ref1).abs() <= tol1).all()
+    tol2 = 3e-4 * (g.abs() * ((z.double() - bc(mean).double()) * bc(invstd).double()).abs()).sum((0, 2, 3)) + 1e-12
+    assert ((sums[1] - ref2).abs() <= tol2).all()
+
+
 @pytest.mark.parametrize("terms", [3, 1])
 @pytest.mark.parametrize("n,h,w,cin,cin_real,cout", [
     (1, 8, 16, 32, 27, 64),      # first layer: 27 real channels, one K tile

@@ -51,6 +51,15 @@ int tnb_conv3x3_fwd(const tnb_view_t* view, const uint16_t* wpack, float* out, f
                     int fmt, int variant, void* stream) {
   return launch_conv3x3(*view, wpack, out, stat_part, cout, terms, fmt, variant, ST(stream));
 }
+int tnb_conv3x3_dgrad_bnreduce_rows(int n, int h, int w, int cin, int cout, int terms) {
+  return conv3x3_num_stat_rows(n, h, w, cin, cout, terms, true);
+}
+int tnb_conv3x3_dgrad_bnreduce(const tnb_view_t* view, const uint16_t* wpack, float* out, float* part, int cout,
+                               int terms, const float* z, const float* scale, const float* shift, const float* mean,
+                               const float* invstd, void* stream) {
+  const BnBwdFuse fuse{z, scale, shift, mean, invstd};
+  return launch_conv3x3(*view, wpack, out, part, cout, terms, 1, 0, ST(stream), &fuse);
+}
 int tnb_conv3x3_wgrad(const tnb_view_t* view, const void* dz_presplit, float* dw, int cout, int cin_real, int terms,
                       int variant, void* stream) {
   return launch_wgrad3x3(*view, dz_presplit, dw, cout, cin_real, terms, variant, ST(stream));

@@ -32,6 +32,9 @@ struct ConvArgs {
   const uint16_t* wpack;
   float* out;        // [N,H,W,Cout]
   float* stat_part;  // [ntiles][2][Cout] per-tile (sum, sumsq) partials, or nullptr
+  // dgrad fused with the BatchNorm-backward reduction of the layer that produced the view this gradient belongs to:
+  // with bz != nullptr the partials are (sum g, sum g * xhat), g = out * [relu'(bsc * z + bsh)], xhat = (z - bmu) * bis
+  const float *bz, *bsc, *bsh, *bmu, *bis;
   int Cout, BN, MT, SA, SB, G, nbuf, nterms, variant, tmem_cols;  // G: filter taps per weight stage (1 or 3)
   int tiles_h, tiles_w, ntiles, nwork;
 };
@@ -53,7 +56,7 @@ TNB_DEVINL float warp_transpose_sum(float (&v)[32], int lane) {
 
 // M0 / M1: gather modes of the (up to two) concatenated view sources, compile-time so that every instantiation carries
 // only the gather paths it needs (the producers are register-limited; a run-time switch over all modes costs spills)
-template <int FMT, int M0, int M1>
+template <int FMT, int M0, int M1, bool BWD = false>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_constant__ ConvArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
@@ -81,7 +84,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
   int2* table = reinterpret_cast<int2*>(smem + kHdrBytes);
   const int table_bytes = (HALO_PX * 8 + 127) & ~127;
   float* sstat = reinterpret_cast<float*>(smem + kHdrBytes + table_bytes);  // [4 warps][2][BN]
-  uint8_t* a_base = smem + kHdrBytes + table_bytes + 4 * 2 * BN * 4;
+  float4* btab = reinterpret_cast<float4*>(sstat + 4 * 2 * BN);  // [BN] (scale, shift, mean, invstd), fused BN-bwd only
+  uint8_t* a_base = smem + kHdrBytes + table_bytes + 4 * 2 * BN * 4 + (BWD ? BN * 16 : 0);
   uint8_t* b_base = a_base + a.SA * A_STAGE;
 
   // ---- one-time setup ----
@@ -200,8 +204,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
     const int r = row >> 3, cc = row & 7;
     const int et = tid - 64;  // 0..127
     int k = 0;
+    int tab_nt = -1;
     for (int work = blockIdx.x; work < a.nwork; work += gridDim.x, ++k) {
       const int nt = work / a.ntiles;
+      if (BWD && nt != tab_nt) {  // per-channel BatchNorm constants of this output-channel tile
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int j = et; j < BN; j += kEpiThreads) {
+          const int c = nt * BN + j;
+          btab[j] = make_float4(a.bsc[c], a.bsh[c], a.bmu[c], a.bis[c]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        tab_nt = nt;
+      }
       int tile = work - nt * a.ntiles;
       const int tile_id = tile;
       const int tw = tile % a.tiles_w; tile /= a.tiles_w;
@@ -234,15 +248,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
               for (int i = 0; i < 32; ++i) v[i] = 0.f;
             }
             float s[32];
+            if (BWD) {
+              // g = dL/da masked by the producer's ReLU (same expression as the forward gather / bn_bwd_kernel);
+              // column sums of g and g * (z - mean), 8 channels of z at a time to keep the live set small
+              const float4* zp =
+                  reinterpret_cast<const float4*>(a.bz + ((size_t)(n * V.H + h) * V.W + w) * a.Cout + n0 + col0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) s[i] = v[i];
-            csum += warp_transpose_sum(s, lane);
+              for (int c8 = 0; c8 < 4; ++c8) {
+                const float4 za = valid ? __ldg(zp + 2 * c8) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 zb = valid ? __ldg(zp + 2 * c8 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float zc[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
 #pragma unroll
-            for (int i = 0; i < 32; ++i) s[i] = v[i] * v[i];
-            csq += warp_transpose_sum(s, lane);
+                for (int i = 0; i < 8; ++i) {
+                  const float4 t = btab[col0 + 8 * c8 + i];
+                  const float g = fmaf(zc[i], t.x, t.y) > 0.f ? v[8 * c8 + i] : 0.f;
+                  v[8 * c8 + i] = g;
+                  s[8 * c8 + i] = g * (zc[i] - t.z);
+                }
+              }
+              csum += warp_transpose_sum(v, lane);
+              csq += warp_transpose_sum(s, lane);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) s[i] = v[i];
+              csum += warp_transpose_sum(s, lane);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) s[i] = v[i] * v[i];
+              csq += warp_transpose_sum(s, lane);
+            }
           }
         }
         if (a.stat_part != nullptr) {
+          if (BWD) csq *= btab[col0 + lane].w;  // sum g * (z - mean) -> sum g * xhat
           sstat[(q * 2 + 0) * BN + col0 + lane] = csum;
           sstat[(q * 2 + 1) * BN + col0 + lane] = csq;
         }
@@ -398,7 +435,7 @@ static int num_sms() {
   return n;
 }
 
-int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* plan) {
+int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* plan, bool bn_bwd_fused) {
   TNB_REQUIRE(Cin % 32 == 0, "conv3x3: view channels %d must be a multiple of 32", Cin);
   const int BN = pick_bn(Cout);
   TNB_REQUIRE(BN >= 32 && BN % 16 == 0, "conv3x3: unsupported output channel count %d", Cout);
@@ -418,7 +455,8 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
       const int pitch = 8 * MT + 2, halo = 18 * pitch;
       const size_t a_stage = (size_t)TP * 4 * pad_px(halo) * 16;
       const size_t b_stage = (size_t)g * TP * 64 * BN;
-      const size_t fixed = kHdrBytes + ((halo * 8 + 127) & ~127) + (size_t)4 * 2 * BN * 4 + SA * a_stage;
+      const size_t fixed = kHdrBytes + ((halo * 8 + 127) & ~127) + (size_t)4 * 2 * BN * 4 + (bn_bwd_fused ? BN * 16 : 0) +
+                           SA * a_stage;
       if (fixed + 2 * b_stage <= (size_t)kMaxSmem) {
         G = g;
         SB = (int)((kMaxSmem - fixed) / b_stage);
@@ -441,25 +479,32 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
   return 0;
 }
 
-int conv3x3_num_stat_rows(int N, int H, int W, int Cin, int Cout, int nterms) {
+int conv3x3_num_stat_rows(int N, int H, int W, int Cin, int Cout, int nterms, bool bn_bwd_fused) {
   ConvPlan p;
-  if (conv3x3_plan(N, H, W, Cin, Cout, nterms, &p)) return -1;
+  if (conv3x3_plan(N, H, W, Cin, Cout, nterms, &p, bn_bwd_fused)) return -1;
   return N * p.tiles_h * p.tiles_w;
 }
 
 int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout,
-                   int nterms, int fmt, int variant, cudaStream_t st) {
+                   int nterms, int fmt, int variant, cudaStream_t st, const BnBwdFuse* fuse) {
   ConvPlan p;
-  int rc = conv3x3_plan(view.N, view.H, view.W, view.C, Cout, nterms, &p);
+  int rc = conv3x3_plan(view.N, view.H, view.W, view.C, Cout, nterms, &p, fuse != nullptr);
   if (rc) return rc;
+  const int m0 = view.s[0].mode, m1 = (view.C0 < view.C) ? view.s[1].mode : view.s[0].mode;
   ConvArgs a;
   a.view = view; a.wpack = wpack; a.out = out; a.stat_part = stat_part;
+  a.bz = a.bsc = a.bsh = a.bmu = a.bis = nullptr;
+  if (fuse != nullptr) {
+    TNB_REQUIRE(stat_part != nullptr, "conv3x3: fused BatchNorm-backward reduction needs a partials buffer");
+    TNB_REQUIRE(fmt == 1 && m0 == SRC_PRESPLIT && m1 == SRC_PRESPLIT,
+                "conv3x3: the fused BatchNorm-backward reduction exists for the dgrad configuration only");
+    a.bz = fuse->z; a.bsc = fuse->scale; a.bsh = fuse->shift; a.bmu = fuse->mean; a.bis = fuse->invstd;
+  }
   a.Cout = Cout; a.BN = p.BN; a.MT = p.MT; a.SA = p.SA; a.SB = p.SB; a.G = p.G; a.nbuf = p.nbuf; a.nterms = nterms;
   a.variant = variant; a.tmem_cols = p.tmem_cols; a.tiles_h = p.tiles_h; a.tiles_w = p.tiles_w;
   a.ntiles = view.N * p.tiles_h * p.tiles_w;
   a.nwork = a.ntiles * (Cout / p.BN);
   const int grid = a.nwork < num_sms() ? a.nwork : num_sms();
-  const int m0 = view.s[0].mode, m1 = (view.C0 < view.C) ? view.s[1].mode : view.s[0].mode;
   ProfScope prof(view.s[0].mode == SRC_PRESPLIT ? PROF_CONV_DGRAD : PROF_CONV_FWD, st, view.N, view.H, view.W, view.C, Cout);
   auto go = [&](auto kern) -> int {
     TNB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
@@ -475,6 +520,9 @@ int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, floa
   TNB_CONV_CASE(0, SRC_AFFINE_RELU_UP, SRC_AFFINE_RELU_UP)
   TNB_CONV_CASE(0, SRC_PRESPLIT, SRC_PRESPLIT)
   TNB_CONV_CASE(1, SRC_IDENTITY, SRC_IDENTITY)
+  if (fmt == 1 && m0 == SRC_PRESPLIT && m1 == SRC_PRESPLIT && fuse != nullptr)
+    rc2 = go(conv3x3_kernel<1, SRC_PRESPLIT, SRC_PRESPLIT, true>);
+  else
   TNB_CONV_CASE(1, SRC_PRESPLIT, SRC_PRESPLIT)
   { tnb::set_last_error("conv3x3: unsupported (fmt %d, source modes %d/%d) combination", fmt, m0, m1); return -2; }
 #undef TNB_CONV_CASE

@@ -145,13 +145,18 @@ struct ConvPlan {
   int tiles_h, tiles_w;
 };
 // fmt: 0 = fp16 split, 1 = bf16 split. nterms: 1 (single pass) or 3 (hi*hi + lo*hi + hi*lo).
-int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* plan);
+// bn_bwd_fused: reserve the per-channel constant table of the fused BatchNorm-backward reduction (dgrad epilogue)
+int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* plan, bool bn_bwd_fused = false);
 size_t conv3x3_wpack_elems(int Kside, int Nside);  // uint16 elements of a packed weight buffer
 int launch_pack_weights(const float* w_oihw, uint16_t* out, int Co, int Ci, int mode /*0 fwd, 1 dgrad*/,
                         int fmt, int BN, cudaStream_t st);
+// Optional fusion for dgrad launches: `out` is dL/d(activation) of a producer layer whose raw conv output is `z`; the
+// per-tile partials become (sum g, sum g * xhat) with g = out masked by that layer's ReLU - the reduction pass of its
+// BatchNorm backward - instead of (sum out, sum out^2).
+struct BnBwdFuse { const float *z, *scale, *shift, *mean, *invstd; };
 int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout,
-                   int nterms, int fmt, int variant, cudaStream_t st);
-int conv3x3_num_stat_rows(int N, int H, int W, int Cin, int Cout, int nterms);
+                   int nterms, int fmt, int variant, cudaStream_t st, const BnBwdFuse* fuse = nullptr);
+int conv3x3_num_stat_rows(int N, int H, int W, int Cin, int Cout, int nterms, bool bn_bwd_fused = false);
 
 int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw_oihw, int Cout, int CinReal, int nterms,
                     int variant, cudaStream_t st);

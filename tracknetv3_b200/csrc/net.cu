@@ -41,8 +41,20 @@ struct LayerBuf {
   int stat_rows;
   float *dz, *din, *bwd_part, *bwd_sums, *amax;
   int bwd_rows;
+  int fused_rows;  // > 0: the BatchNorm-backward reduction of THIS layer is produced by the dgrad epilogue of layer + 1
   uint16_t *wf, *wd;
 };
+
+// The reduction pass of layer p's BatchNorm backward can ride on the dgrad of layer p + 1 when that convolution is
+// the only consumer of p's activation and sees it at the same resolution through a plain BN + ReLU view.
+bool bn_reduce_fusable(int p) {
+  if (p + 1 >= kLayers) return false;
+  const LayerDef& d = kDefs[p + 1];
+  if (d.src0 != p || d.src1 >= 0 || d.mode0 != SRC_AFFINE_RELU) return false;
+  for (int j = 0; j < kLayers; ++j)
+    if (j != p + 1 && (kDefs[j].src0 == p || kDefs[j].src1 == p)) return false;
+  return true;
+}
 struct Plan {
   LayerBuf L[kLayers];
   uint8_t* vsplit;  // scratch: the current layer's input view materialised as pre-split bf16 (largest: 192 ch @ full res)
@@ -113,12 +125,18 @@ int build_plan(const tnb_tracknet_cfg_t& c, void* ws, Plan* P) {
       B.dz = b.take<float>(npix * B.cout);
       B.din = (l > 0) ? b.take<float>(npix * B.cin) : nullptr;
       B.bwd_rows = bn_bwd_num_blocks(c.n, B.H, B.W, B.cout);
-      B.bwd_part = b.take<float>((size_t)B.bwd_rows * 2 * B.cout);
+      B.fused_rows = 0;
+      if (!(c.variant & 64) && bn_reduce_fusable(l)) {  // variant bit 64: keep the stand-alone reduction (ablation)
+        // dgrad of layer l + 1: K side = its cout, N side = its cin = this layer's cout, same resolution
+        B.fused_rows = conv3x3_num_stat_rows(c.n, B.H, B.W, kDefs[l + 1].cout, B.cout, c.bwd_terms, true);
+        if (B.fused_rows < 0) return -2;
+      }
+      B.bwd_part = b.take<float>((size_t)(B.fused_rows > B.bwd_rows ? B.fused_rows : B.bwd_rows) * 2 * B.cout);
       B.bwd_sums = b.take<float>(2 * B.cout);
       B.amax = P->amax_all + l;
       B.wd = (l > 0) ? b.take<uint16_t>(conv3x3_wpack_elems(B.cout, B.cin)) : nullptr;
     } else {
-      B.dz = B.din = B.bwd_part = B.bwd_sums = B.amax = nullptr; B.wd = nullptr; B.bwd_rows = 0;
+      B.dz = B.din = B.bwd_part = B.bwd_sums = B.amax = nullptr; B.wd = nullptr; B.bwd_rows = 0; B.fused_rows = 0;
     }
   }
   P->bytes = (b.off + 255) & ~(size_t)255;
@@ -229,9 +247,10 @@ int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float*
     a.N = c.n; a.H = B.H; a.W = B.W; a.C = B.cout;
     a.part = B.bwd_part; a.sums = B.bwd_sums; a.dz = B.dz; a.amax = nullptr; a.dz_format = 1;  // dz -> pre-split bf16
     a.inv_count = (float)(1.0 / ((double)c.n * B.H * B.W));
-    if (int rc = launch_bn_bwd_reduce(a, st)) return rc;
-    if (int rc = launch_bn_bwd_finalize(B.bwd_part, B.bwd_rows, B.cout, B.bwd_sums, (float*)grads[l * 3 + 1],
-                                        (float*)grads[l * 3 + 2], st))
+    if (B.fused_rows == 0)
+      if (int rc = launch_bn_bwd_reduce(a, st)) return rc;
+    if (int rc = launch_bn_bwd_finalize(B.bwd_part, B.fused_rows > 0 ? B.fused_rows : B.bwd_rows, B.cout, B.bwd_sums,
+                                        (float*)grads[l * 3 + 1], (float*)grads[l * 3 + 2], st))
       return rc;
     if (int rc = launch_bn_bwd_apply(a, st)) return rc;
     const float* w = (const float*)params[l * 6 + 0];
@@ -242,9 +261,14 @@ int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float*
       dv.s[1] = dv.s[0];
       dv.C0 = dv.C = B.cout; dv.N = c.n; dv.H = B.H; dv.W = B.W;
       ConvPlan cp;
-      if (int rc = conv3x3_plan(c.n, B.H, B.W, B.cout, B.cin, c.bwd_terms, &cp)) return rc;
+      const LayerBuf* Pp = (l > 0 && P.L[l - 1].fused_rows > 0) ? &P.L[l - 1] : nullptr;  // producer whose reduction rides along
+      BnBwdFuse fuse{};
+      if (Pp != nullptr) fuse = BnBwdFuse{Pp->z, Pp->scale, Pp->shift, Pp->mean, Pp->invstd};
+      if (int rc = conv3x3_plan(c.n, B.H, B.W, B.cout, B.cin, c.bwd_terms, &cp, Pp != nullptr)) return rc;
       if (int rc = launch_pack_weights(w, B.wd, B.cout, B.cin, 1, 1, cp.BN, st)) return rc;
-      if (int rc = launch_conv3x3(dv, B.wd, B.din, nullptr, B.cin, c.bwd_terms, 1, c.variant & 3, st)) return rc;
+      if (int rc = launch_conv3x3(dv, B.wd, B.din, Pp != nullptr ? Pp->bwd_part : nullptr, B.cin, c.bwd_terms, 1,
+                                  c.variant & 3, st, Pp != nullptr ? &fuse : nullptr))
+        return rc;
     }
     float* dw = (float*)grads[l * 3 + 0];
     TNB_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)B.cout * B.cin_real * 9, st));
@@ -263,7 +287,11 @@ int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float*
 
 int tracknet_num_launches(const tnb_tracknet_cfg_t& c, int backward) {
   if (!backward) return 1 + kLayers * 3 + (c.training ? 1 : 0) + 1;  // pack, (wpack, conv, bn_finalize) x17, counters, predictor
-  return 1 + kLayers * 5 + (kLayers - 1) * 2;  // predictor_bwd, (reduce, finalize, apply, view_presplit, wgrad) x17, (wpack, dgrad) x16
+  int fused = 0;
+  for (int l = 0; l < kLayers; ++l) fused += (!(c.variant & 64) && bn_reduce_fusable(l)) ? 1 : 0;
+  // predictor_bwd, (reduce [unless fused into the next layer's dgrad], finalize, apply, view_presplit, wgrad) x17,
+  // (wpack, dgrad) x16
+  return 1 + kLayers * 5 - fused + (kLayers - 1) * 2;
 }
 
 }  // namespace tnb
