@@ -187,6 +187,14 @@ int tnb_inpaintnet_fwd(const float* coords, const float* mask, const void* const
 int tnb_inpaintnet_bwd(const float* coords, const float* mask, const void* const* params, const float* dout,
                        void* const* grads, int n, int l, float* dcoords, void* stream);
 
+/* Temporal ensemble of sliding-window predictions (predict.py:163-209 heatmaps, :245-301 coordinates). state: the
+ * previous seq_len-1 samples' predictions [(seq_len-1)][seq_len][frame_elems] (zeros before the first batch); pred:
+ * this batch [batch][seq_len][frame_elems]; weight_host: seq_len floats in HOST memory (test.py:25-50). sample_count:
+ * samples consumed before this batch. n_tail = seq_len-1 when this batch contains the last sample (index tail_base in
+ * the batch): the remaining frames are appended, else 0. out: [batch + n_tail][frame_elems]. */
+int tnb_temporal_ensemble(const float* state, const float* pred, float* out, const float* weight_host, int seq_len,
+                          long long frame_elems, int batch, int sample_count, int tail_base, int n_tail, void* stream);
+
 /* ---- network level: TrackNet.forward / its autograd backward (model.py:57-73) --------------- */
 
 /* params: 104 device pointers in state_dict order: for each of the 17 Conv2DBlocks

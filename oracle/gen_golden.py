@@ -78,6 +78,92 @@ def gen_inpaint_train(refmodel):
     np.savez_compressed(f"{OUT}/inpaintnet_train.npz", **out)
 
 
+def _find_stream_loop(tree, names):
+    """The `for step, (<names>) in enumerate(tqdm(data_loader))` loop of predict.py's __main__ whose body holds the
+    per-sample `for b in range(b_size)` ensemble loop."""
+    for node in ast.walk(tree):
+        if isinstance(node, ast.For) and isinstance(node.target, ast.Tuple) and len(node.target.elts) == 2 and \
+                isinstance(node.target.elts[1], ast.Tuple) and \
+                [getattr(e, "id", None) for e in node.target.elts[1].elts] == names and \
+                any(isinstance(n, ast.For) and getattr(n.target, "id", None) == "b" for n in ast.walk(node)):
+            return node
+    raise RuntimeError("ensemble loop not found in the reference")
+
+
+def gen_temporal_ensemble():
+    """EXECUTE the reference's streaming temporal-ensemble loops (predict.py:168-209 heatmaps, :252-301 coordinates)
+    as they are, lifted out of its __main__ with ast, against fake models that return prepared predictions and a fake
+    `predict` that records what the loop hands to the decoder. Small maps (6x10) keep the fixture tiny."""
+    src = open(f"{REF}/predict.py").read()
+    tree = ast.parse(src)
+    env0 = {"torch": torch, "np": np, "math": math, "tqdm": lambda x: x}
+    extract_functions(f"{REF}/test.py", {"get_ensemble_weight"}, env0)
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self  # the loops call .cuda() on their inputs; there is no GPU here
+    out = {}
+    try:
+        for mode in ("weight", "average"):
+            for L, video_len, bs in ((8, 21, 4), (4, 4, 3), (3, 11, 16)):
+                H, W = 6, 10
+                num_sample = video_len - L + 1
+                g = torch.Generator().manual_seed(100 + L + video_len)
+                preds = torch.rand(num_sample, L, H, W, generator=g)
+                idx = torch.stack([torch.stack([torch.zeros(L), torch.arange(s, s + L).float()], 1) for s in range(num_sample)])
+                batches = [(idx[a:a + bs], torch.arange(a, min(a + bs, num_sample))) for a in range(0, num_sample, bs)]
+                rec = []
+                env = dict(env0)
+                env.update(HEIGHT=H, WIDTH=W, seq_len=L, num_sample=num_sample, sample_count=0, buffer_size=L - 1,
+                           batch_i=torch.arange(L), frame_i=torch.arange(L - 1, -1, -1),
+                           y_pred_buffer=torch.zeros((L - 1, L, H, W)), weight=env0["get_ensemble_weight"](L, mode),
+                           data_loader=batches, tracknet=lambda x: preds[x.long()], img_scaler=(1, 1),
+                           tracknet_pred_dict={},
+                           predict=lambda i, y_pred=None, c_pred=None, img_scaler=None: rec.append((i.clone(), y_pred.clone())) or {})
+                loop = _find_stream_loop(tree, ["i", "x"])
+                exec(compile(ast.Module(body=[loop], type_ignores=[]), f"{REF}/predict.py", "exec"), env)
+                key = f"hm_{mode}_{L}_{video_len}_{bs}"
+                out[key + "/preds"] = preds.numpy()
+                out[key + "/ens"] = torch.cat([r[1] for r in rec]).numpy()
+                out[key + "/idx"] = torch.cat([r[0] for r in rec]).numpy()
+                out[key + "/counts"] = np.array([len(r[1]) for r in rec])
+        # coordinate ensemble around InpaintNet (predict.py:252-301): fake inpaintnet returns prepared coordinates
+        for mode in ("weight",):
+            for L, n, bs in ((16, 40, 16), (5, 5, 2)):
+                g = torch.Generator().manual_seed(200 + L + n)
+                coor = torch.rand(n, L, 2, generator=g)
+                coor[torch.rand(n, L, generator=g) < 0.2] = 0.01  # some below COOR_TH
+                pred_in = torch.rand(n, L, 2, generator=g)
+                msk = (torch.rand(n, L, 1, generator=g) < 0.4).float()
+                idx = torch.stack([torch.stack([torch.zeros(L), torch.arange(s, s + L).float()], 1) for s in range(n)])
+                order = iter(range(0, n, bs))
+                batches = [(idx[a:a + bs], pred_in[a:a + bs], msk[a:a + bs]) for a in range(0, n, bs)]
+                calls = {"a": 0}
+
+                def fake_inpaint(c, m, _c=calls, _coor=coor, _bs=bs):
+                    a = _c["a"]; _c["a"] += _bs
+                    return _coor[a:a + c.shape[0]]
+                rec = []
+
+                class _DS:
+                    def __len__(self):
+                        return n
+                env = dict(env0)
+                env.update(seq_len=L, COOR_TH=50 / math.sqrt(288 ** 2 + 512 ** 2), data_loader=batches, dataset=_DS(),
+                           num_sample=n, sample_count=0, buffer_size=L - 1, batch_i=torch.arange(L),
+                           frame_i=torch.arange(L - 1, -1, -1), coor_inpaint_buffer=torch.zeros((L - 1, L, 2)),
+                           weight=env0["get_ensemble_weight"](L, mode), inpaintnet=fake_inpaint, img_scaler=(1, 1),
+                           inpaint_pred_dict={},
+                           predict=lambda i, y_pred=None, c_pred=None, img_scaler=None: rec.append((i.clone(), c_pred.clone())) or {})
+                loop = _find_stream_loop(tree, ["i", "coor_pred", "inpaint_mask"])
+                exec(compile(ast.Module(body=[loop], type_ignores=[]), f"{REF}/predict.py", "exec"), env)
+                key = f"co_{mode}_{L}_{n}_{bs}"
+                out[key + "/coor"] = coor.numpy(); out[key + "/pred_in"] = pred_in.numpy(); out[key + "/mask"] = msk.numpy()
+                out[key + "/ens"] = torch.cat([r[1] for r in rec]).numpy()
+                out[key + "/counts"] = np.array([len(r[1]) for r in rec])
+    finally:
+        torch.Tensor.cuda = real_cuda
+    np.savez_compressed(f"{OUT}/temporal_ensemble.npz", **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -85,6 +171,10 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "inpaint_train":  # regenerate only this fixture
         gen_inpaint_train(refmodel)
         print("inpaintnet_train.npz written")
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "temporal_ensemble":
+        gen_temporal_ensemble()
+        print("temporal_ensemble.npz written")
         return
     refmetric = load_module("ref_metric", f"{REF}/utils/metric.py")
     import cv2
@@ -184,6 +274,7 @@ def main():
     np.savez_compressed(f"{OUT}/inpaintnet.npz", seed=7, coor=coor.numpy(), mask=mask.numpy(), out=out.numpy())
 
     gen_inpaint_train(refmodel)
+    gen_temporal_ensemble()
 
     # ---- small host-side pieces: ensemble weights, mixup ----
     ew = {f"weight_{L}": env["get_ensemble_weight"](L, "weight").numpy() for L in (1, 4, 7, 8)}

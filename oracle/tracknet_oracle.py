@@ -219,3 +219,37 @@ def clip_grad_norm(grads, max_norm=1.0):
     total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).float()
     coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
     return total, {k: g * coef for k, g in grads.items()}
+
+
+class TemporalEnsemble:
+    """Streaming temporal ensemble of overlapping predictions (reference predict.py:163-209 for heatmaps, :245-301
+    for InpaintNet coordinates). Sample s predicts frames s..s+L-1; frame t is the combination of the L samples that
+    contain it: uniform mean while fewer than L samples have been seen (:181-183), `weight` afterwards (:184-186),
+    and plain means over the remaining samples for the last L-1 frames once `num_sample` is reached (:192-201).
+    push(pred (B, L, ...)) returns the ensembled frames this batch completes, (B [+ L-1 at the end], ...)."""
+
+    def __init__(self, seq_len, eval_mode, num_sample):
+        self.L, self.num_sample, self.count = seq_len, num_sample, 0
+        self.weight = get_ensemble_weight(seq_len, eval_mode)
+        self.buffer = None
+
+    def push(self, pred):
+        L = self.L
+        if self.buffer is None:
+            self.buffer = torch.zeros((L - 1,) + tuple(pred.shape[1:]), dtype=pred.dtype)
+        buf = torch.cat((self.buffer, pred), dim=0)
+        batch_i, frame_i = torch.arange(L), torch.arange(L - 1, -1, -1)
+        w = self.weight.reshape((L,) + (1,) * (pred.dim() - 2))
+        out = []
+        for b in range(pred.shape[0]):
+            if self.count < L - 1:
+                out.append(buf[batch_i + b, frame_i].sum(0) / (self.count + 1))
+            else:
+                out.append((buf[batch_i + b, frame_i] * w).sum(0))
+            self.count += 1
+            if self.count == self.num_sample:
+                buf = torch.cat((buf, torch.zeros_like(buf[:L - 1])), dim=0)
+                for f in range(1, L):
+                    out.append(buf[batch_i + b + f, frame_i].sum(0) / (L - f))
+        self.buffer = buf[-(L - 1):] if L > 1 else buf[:0]
+        return torch.stack(out)

@@ -8,6 +8,7 @@ import numpy as np
 import torch
 
 from tracknetv3_b200.decode import decode_heatmaps
+from tracknetv3_b200.ensemble import TemporalEnsemble
 from utils.general import HEIGHT, WIDTH
 
 
@@ -57,3 +58,35 @@ def predict(indices, y_pred=None, c_pred=None, img_scaler=(1, 1)):
             pred_dict['Visibility'].append(vis_pred)
             prev_f_i = f_i
     return pred_dict
+
+
+def predict_ensemble(ensemble, indices, y_pred=None, c_pred=None, img_scaler=(1, 1)):
+    """ One iteration of the reference's temporal-ensemble loops (predict.py:168-209 with ``y_pred``, :252-301 with
+        ``c_pred``) with the ensemble and the heatmap decode on the GPU: no heatmap leaves the device.
+
+        Args:
+            ensemble (TemporalEnsemble): created once per video with (seq_len, eval_mode, num_sample)
+            indices (torch.Tensor): indices of this batch's input sequences, (N, L, 2)
+            y_pred (torch.Tensor, optional): CUDA heatmaps of this batch, (N, L, H, W)
+            c_pred (torch.Tensor, optional): CUDA inpainted + blended + thresholded coordinates, (N, L, 2)
+
+        Returns:
+            pred_dict (Dict): what ``predict()`` returns for the frames this batch completes
+    """
+    from utils.general import COOR_TH
+    seq_len = indices.shape[1]
+    b_size = indices.shape[0]
+    last = ensemble.sample_count + b_size == ensemble.num_sample
+    ens_i = [indices[b][0].reshape(1, 1, 2) for b in range(b_size)]
+    if last:
+        ens_i += [indices[-1][f].reshape(1, 1, 2) for f in range(1, seq_len)]
+    ens_i = torch.cat([torch.as_tensor(t) for t in ens_i], dim=0)
+    if y_pred is not None:
+        ens = ensemble.push(y_pred)                       # (n_out, H, W)
+        return predict(ens_i, y_pred=ens.unsqueeze(1), img_scaler=img_scaler)
+    if c_pred is not None:
+        ens = ensemble.push(c_pred)                       # (n_out, 2)
+        th_mask = (ens[:, 0] < COOR_TH) & (ens[:, 1] < COOR_TH)
+        ens = ens.masked_fill(th_mask[:, None], 0.)
+        return predict(ens_i, c_pred=ens.unsqueeze(1), img_scaler=img_scaler)
+    raise ValueError('Invalid input')

@@ -304,3 +304,67 @@ def test_device_prefetcher_yields_batches_in_order():
         assert acc.item() == host[i][0].sum().item() + host[i][1].sum().item()
         seen += 1
     assert seen == len(host)
+
+
+def test_temporal_ensemble_vs_reference_loops(golden_dir):
+    """GPU TemporalEnsemble vs the reference's streaming loops (fixture produced by executing predict.py's own
+    loops, oracle/gen_golden.py): same frames per batch, values within 1 ulp-ish, decoded boxes identical."""
+    g = _load(golden_dir, "temporal_ensemble.npz")
+    keys = sorted({k.split("/")[0] for k in g.files})
+    for key in keys:
+        kind, mode, L, n, bs = key.split("_")
+        L, n, bs = int(L), int(n), int(bs)
+        if kind == "hm":
+            preds = torch.from_numpy(g[key + "/preds"])
+            num_sample = preds.shape[0]
+        else:
+            coor, pred_in, msk = (torch.from_numpy(g[key + "/" + k]) for k in ("coor", "pred_in", "mask"))
+            preds = O.inpaint_blend(pred_in, coor, msk)
+            num_sample = n
+        ens = T.TemporalEnsemble(L, mode, num_sample)
+        outs = [ens.push(preds[a:a + bs].to(G.DEV)) for a in range(0, num_sample, bs)]
+        assert [len(o) for o in outs] == list(g[key + "/counts"])
+        out = torch.cat(outs).cpu()
+        ref = torch.from_numpy(g[key + "/ens"]).reshape(out.shape)
+        if kind == "co":
+            th = (out[:, 0] < O.COOR_TH) & (out[:, 1] < O.COOR_TH)
+            out[th] = 0.0
+        assert (out - ref).abs().max().item() <= 1.2e-7, key
+        print(f"temporal ensemble {key}: bit-exact={torch.equal(out, ref)}")
+    with pytest.raises(RuntimeError):
+        ens.push(preds[:1].to(G.DEV))  # more samples than num_sample
+
+
+def test_temporal_ensemble_full_size_and_predict_ensemble():
+    """288x512 heatmaps, seq_len 8, bs 32 batches through predict.predict_ensemble: frames, coordinates and
+    visibility equal the oracle's ensemble + OpenCV-rule decode."""
+    import predict as P
+    L, H, W, num_sample, bs = 8, 288, 512, 40, 32
+    gen = torch.Generator().manual_seed(9)
+    # blobs that move one pixel per frame so that the ensemble of the 8 overlapping predictions stays above 0.5
+    preds = torch.zeros(num_sample, L, H, W)
+    for s in range(num_sample):
+        for f in range(L):
+            t = s + f
+            cx, cy = 20 + 5 * t, 30 + 3 * t
+            preds[s, f, cy - 3:cy + 4, cx - 3:cx + 4] = 0.6 + 0.4 * torch.rand(7, 7, generator=gen)
+    idx = torch.stack([torch.stack([torch.zeros(L), torch.arange(s, s + L).float()], 1) for s in range(num_sample)])
+    oracle = O.TemporalEnsemble(L, "weight", num_sample)
+    ens = T.TemporalEnsemble(L, "weight", num_sample)
+    got = {"Frame": [], "X": [], "Y": [], "Visibility": []}
+    want = {"Frame": [], "X": [], "Y": [], "Visibility": []}
+    for a in range(0, num_sample, bs):
+        d = P.predict_ensemble(ens, idx[a:a + bs], y_pred=preds[a:a + bs].to(G.DEV))
+        for k in got:
+            got[k] += d[k]
+        o = oracle.push(preds[a:a + bs])
+        boxes = D.decode_batch(o.unsqueeze(1).numpy())
+        last = a + bs >= num_sample
+        frames = list(range(a, min(a + bs, num_sample))) + (list(range(num_sample, num_sample + L - 1)) if last else [])
+        for j, fr in enumerate(frames):
+            x, y, w, h = (int(v) for v in boxes[j][0])
+            cx, cy = int(x + w / 2), int(y + h / 2)
+            want["Frame"].append(fr); want["X"].append(cx); want["Y"].append(cy)
+            want["Visibility"].append(0 if cx == 0 and cy == 0 else 1)
+    assert got == want
+    assert len(got["Frame"]) == num_sample + L - 1 and sum(got["Visibility"]) > 30

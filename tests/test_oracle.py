@@ -147,3 +147,29 @@ def test_inpaintnet_train_step_matches_reference(golden_dir):
     for k, gr in clipped.items():
         st = g["clipped/" + k]
         assert abs(gr.double().sum().item() - st[0]) <= 1e-5 * st[1] + 1e-9, k
+
+
+def test_temporal_ensemble_matches_reference_loops(golden_dir):
+    """oracle TemporalEnsemble vs the reference's own streaming loops executed by oracle/gen_golden.py."""
+    g = _load(golden_dir, "temporal_ensemble.npz")
+    keys = sorted({k.split("/")[0] for k in g.files})
+    assert len(keys) == 8
+    for key in keys:
+        kind, mode, L, n, bs = key.split("_")
+        L, n, bs = int(L), int(n), int(bs)
+        if kind == "hm":
+            preds = torch.from_numpy(g[key + "/preds"])
+            num_sample = preds.shape[0]
+        else:
+            coor, pred_in, msk = (torch.from_numpy(g[key + "/" + k]) for k in ("coor", "pred_in", "mask"))
+            preds = O.inpaint_blend(pred_in, coor, msk)   # predict.py:257-261 happens before buffering
+            num_sample = n
+        ens = O.TemporalEnsemble(L, mode, num_sample)
+        outs = [ens.push(preds[a:a + bs]) for a in range(0, num_sample, bs)]
+        assert [len(o) for o in outs] == list(g[key + "/counts"])
+        out = torch.cat(outs)
+        ref = torch.from_numpy(g[key + "/ens"]).reshape(out.shape)
+        if kind == "co":  # predict.py:289-291: the ensembled coordinates are thresholded again
+            th = (out[:, 0] < O.COOR_TH) & (out[:, 1] < O.COOR_TH)
+            out[th] = 0.0
+        assert torch.equal(out, ref), key

@@ -128,6 +128,12 @@ int tnb_inpaintnet_bwd(const float* coords, const float* mask, const void* const
   return launch_inpaint_bwd(coords, mask, p, dout, g, n, l, dcoords, ST(stream));
 }
 
+int tnb_temporal_ensemble(const float* state, const float* pred, float* out, const float* weight_host, int seq_len,
+                          long long frame_elems, int batch, int sample_count, int tail_base, int n_tail, void* stream) {
+  return launch_temporal_ensemble(state, pred, out, weight_host, seq_len, frame_elems, batch, sample_count, tail_base,
+                                  n_tail, ST(stream));
+}
+
 size_t tnb_tracknet_workspace_bytes(const tnb_tracknet_cfg_t* cfg) { return tracknet_workspace_bytes(*cfg); }
 int tnb_tracknet_forward(const tnb_tracknet_cfg_t* cfg, const float* x, void* const* params, float* y, void* ws,
                          size_t ws_bytes, void* stream) {

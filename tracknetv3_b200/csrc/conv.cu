@@ -224,6 +224,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
       const int h0 = th * 16, w0 = tw * 8 * MT, n0 = nt * BN;
       const int buf = k % a.nbuf;
       const uint32_t use = (uint32_t)(k / a.nbuf);
+      if (BWD) {  // pull this tile's slice of the producer's z towards L2 while the MMAs of the tile are still running
+        for (int mt = 0; mt < MT; ++mt) {
+          const int h = h0 + r, w = w0 + 8 * mt + cc;
+          if (h < V.H && w < V.W) {
+            const float* zp = a.bz + ((size_t)(n * V.H + h) * V.W + w) * a.Cout + n0;
+            for (int col0 = 0; col0 < BN; col0 += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(zp + col0));
+          }
+        }
+      }
       mbar_wait(&tmem_full[buf], use & 1);
       tc_fence_after();
       for (int col0 = 0; col0 < BN; col0 += 32) {
@@ -231,6 +240,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
         for (int mt = 0; mt < MT; ++mt) {
           const int h = h0 + r, w = w0 + 8 * mt + cc;
           const bool valid = (h < V.H) && (w < V.W) && !(a.variant & 16);
+          float zz[BWD ? 32 : 1];
+          if (BWD) {  // the producer's z for these 32 channels: issued before the TMEM load so the latencies overlap
+            const float4* zp =
+                reinterpret_cast<const float4*>(a.bz + ((size_t)(n * V.H + h) * V.W + w) * a.Cout + n0 + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 t = valid ? __ldg(zp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+              zz[4 * i] = t.x; zz[4 * i + 1] = t.y; zz[4 * i + 2] = t.z; zz[4 * i + 3] = t.w;
+            }
+          }
           uint32_t rg[32];
           tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * BUFCOLS + mt * BN + col0), rg);
           tmem_ld_wait();
@@ -250,21 +269,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
             float s[32];
             if (BWD) {
               // g = dL/da masked by the producer's ReLU (same expression as the forward gather / bn_bwd_kernel);
-              // column sums of g and g * (z - mean), 8 channels of z at a time to keep the live set small
-              const float4* zp =
-                  reinterpret_cast<const float4*>(a.bz + ((size_t)(n * V.H + h) * V.W + w) * a.Cout + n0 + col0);
+              // column sums of g and g * (z - mean)
 #pragma unroll
-              for (int c8 = 0; c8 < 4; ++c8) {
-                const float4 za = valid ? __ldg(zp + 2 * c8) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 zb = valid ? __ldg(zp + 2 * c8 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float zc[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float4 t = btab[col0 + 8 * c8 + i];
-                  const float g = fmaf(zc[i], t.x, t.y) > 0.f ? v[8 * c8 + i] : 0.f;
-                  v[8 * c8 + i] = g;
-                  s[8 * c8 + i] = g * (zc[i] - t.z);
-                }
+              for (int i = 0; i < 32; ++i) {
+                const float4 t = btab[col0 + i];
+                const float g = fmaf(zz[i], t.x, t.y) > 0.f ? v[i] : 0.f;
+                v[i] = g;
+                s[i] = g * (zz[i] - t.z);
               }
               csum += warp_transpose_sum(v, lane);
               csq += warp_transpose_sum(s, lane);

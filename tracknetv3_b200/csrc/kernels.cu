@@ -1,6 +1,7 @@
 // HBM-bound sm_100a kernels of the TrackNet / InpaintNet hot path. Each cites the reference lines it
 // replaces; none of them falls back to a library.
 #include "kernels.cuh"
+#include <algorithm>
 #include "prof.cuh"
 #include <limits.h>
 
@@ -1020,6 +1021,64 @@ int launch_inpaint_bwd(const float* coords, const float* mask, const InpaintPara
   TNB_REQUIRE(smem <= 227 * 1024, "inpaint_bwd: sequence length %d too long for the fused kernel (max 28)", L);
   TNB_CHECK_CUDA(cudaFuncSetAttribute(inpaint_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   inpaint_bwd_kernel<<<N, 512, smem, st>>>(coords, mask, p, dout, g, L, dcoords);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+// =============================================================================================
+// Temporal ensemble of overlapping sliding-window predictions (reference predict.py:163-209 for heatmaps and
+// :245-301 for InpaintNet coordinates, where it is a per-frame Python loop over a growing torch.cat buffer on the
+// CPU after a full D2H of the heatmaps). Sample s predicts frames s..s+L-1; output frame j of this batch combines
+// element [row0 + k][L-1-k] for k = 0..L-1 of the logical buffer cat(state (L-1 rows), pred (B rows), zeros).
+// One pass: every prediction element is read once per output frame that uses it (HBM-bound).
+// =============================================================================================
+struct EnsembleArgs {
+  const float* state;  // [(L-1)][L][E]  predictions of the previous L-1 samples (zeros before the first batch)
+  const float* pred;   // [B][L][E]
+  float* out;          // [B + n_tail][E]
+  float weight[16];
+  int L, B, count0, tail_base, n_tail;
+  long long E;
+};
+__global__ void __launch_bounds__(256) temporal_ensemble_kernel(const __grid_constant__ EnsembleArgs a) {
+  const int j = blockIdx.y;
+  const int L = a.L, S = L - 1;
+  int row0;
+  float div = 0.f;  // > 0: plain sum divided by `div`; 0: weighted sum
+  if (j < a.B) {
+    row0 = j;
+    const int s = a.count0 + j;
+    if (s < S) div = (float)(s + 1);               // incomplete buffer, predict.py:181-183
+  } else {
+    const int f = j - a.B + 1;                     // last input sequence, predict.py:197-201
+    row0 = a.tail_base + f;
+    div = (float)(L - f);
+  }
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < a.E; e += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < L; ++k) {
+      const int r = row0 + k;
+      float v = 0.f;
+      if (r < S) v = a.state[((size_t)r * L + (L - 1 - k)) * a.E + e];
+      else if (r < S + a.B) v = a.pred[((size_t)(r - S) * L + (L - 1 - k)) * a.E + e];
+      // torch evaluates (buffer * weight).sum(0): a rounded product, then a rounded add - no fused multiply-add
+      acc = __fadd_rn(acc, div > 0.f ? v : __fmul_rn(v, a.weight[k]));
+    }
+    a.out[(size_t)j * a.E + e] = div > 0.f ? __fdiv_rn(acc, div) : acc;
+  }
+}
+int launch_temporal_ensemble(const float* state, const float* pred, float* out, const float* weight_host, int L,
+                             long long E, int B, int count0, int tail_base, int n_tail, cudaStream_t st) {
+  TNB_REQUIRE(L >= 1 && L <= 16, "temporal_ensemble: sequence length %d not in 1..16", L);
+  TNB_REQUIRE(B >= 0 && E > 0 && (n_tail == 0 || n_tail == L - 1), "temporal_ensemble: bad batch / tail (%d, %d)", B, n_tail);
+  if (B + n_tail == 0) return 0;
+  EnsembleArgs a;
+  a.state = state; a.pred = pred; a.out = out; a.L = L; a.B = B; a.count0 = count0; a.tail_base = tail_base;
+  a.n_tail = n_tail; a.E = E;
+  for (int k = 0; k < 16; ++k) a.weight[k] = k < L ? weight_host[k] : 0.f;
+  const int bx = (int)std::min<long long>((E + 255) / 256, 148 * 4);
+  temporal_ensemble_kernel<<<dim3(bx, B + n_tail), 256, 0, st>>>(a);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
