@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="fp32x3", choices=["fp32x3", "tf32like"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", type=int, default=0, help="kernel experiment bits (tnb_tracknet_cfg_t.variant)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -165,6 +166,7 @@ def main():
 
     torch.manual_seed(13)  # reference train.py:195 default seed
     model = T.TrackNet(IN_DIM, OUT_DIM, precision=args.precision).cuda().train()
+    model._variant = args.variant
     if world > 1:
         broadcast_module(model)
     bucket = GradBucket(model)
@@ -289,7 +291,7 @@ def main():
                 "whole_step_frac": (84.78e9 * value / world) / (peaks["tflops"] * 1e12)}
 
     cfg = _lib.TrackNetCfg(n=BATCH, h=H, w=W, in_dim=IN_DIM, out_dim=OUT_DIM, training=1, fwd_terms=terms,
-                           bwd_terms=terms, variant=0, bn_eps=1e-5, bn_momentum=0.1)
+                           bwd_terms=terms, variant=args.variant, bn_eps=1e-5, bn_momentum=0.1)
     launches = (lib.tnb_tracknet_num_launches(C.byref(cfg), 0) + lib.tnb_tracknet_num_launches(C.byref(cfg), 1)
                 + 3) * args.steps  # + WBCE forward (2 kernels) and backward (1)
 

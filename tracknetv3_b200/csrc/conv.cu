@@ -16,6 +16,7 @@
 // The planar tile [plane = 8 channels][pixel][16 B] is a SWIZZLE_NONE K-major operand in which every 3x3 tap
 // is just a different 16-byte aligned start address: one halo tile serves all 9 taps.
 #include "igemm.cuh"
+#include <cstdlib>
 #include "prof.cuh"
 #include <type_traits>
 
@@ -453,6 +454,9 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
   const int TP = nterms > 1 ? 2 : 1;
   int MT = 512 / BN;
   if (MT > 4) MT = 4;
+  // experiment switch (tools/ablate_plan.py): TNB_CONV_PLAN=1 halves the tile so that the accumulator double-buffers
+  static const int plan_mode = [] { const char* e = getenv("TNB_CONV_PLAN"); return e ? atoi(e) : 0; }();
+  if (plan_mode == 1) while (MT > 1 && 2 * MT * BN > 512) MT >>= 1;
   while (MT > 1 && 8 * (MT - 1) >= W) --MT;  // do not tile wider than the image
   int SA = 2, SB = 0, G = 1;
   size_t smem = 0;
