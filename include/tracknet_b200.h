@@ -30,7 +30,8 @@ extern "C" {
 
 /* How one channel-slice of a conv layer's logical input is produced from a stored tensor. */
 enum { TNB_SRC_IDENTITY = 0, TNB_SRC_AFFINE_RELU = 1, TNB_SRC_AFFINE_RELU_POOL = 2, TNB_SRC_AFFINE_RELU_UP = 3,
-       TNB_SRC_PRESPLIT = 4 /* ptr holds the "pre-split" 16-bit format, see tnb_presplit_bf16 */ };
+       TNB_SRC_PRESPLIT = 4 /* ptr holds the "pre-split" 16-bit format, see tnb_presplit_bf16 */,
+       TNB_SRC_PRESPLIT_UP = 5 /* pre-split tensor at HALF resolution read through nearest x2 upsampling (wgrad only) */ };
 typedef struct {
   const float* ptr;   /* [N, Hs, Ws, C] fp32 NHWC */
   const float* scale; /* [C] fused BatchNorm scale (gamma * invstd). IDENTITY: NULL, or a pointer to ONE float =
@@ -66,6 +67,8 @@ typedef struct {
   float inv_count;
   float* amax;       /* apply, optional: device scalar, atomically raised to max|dz| (zero it first) */
   int dz_format;     /* apply: 0 = fp32 [N,H,W,C]; 1 = pre-split bf16 (same byte size, see tnb_presplit_bf16) */
+  void* act_presplit; /* apply, optional: also write relu(scale*z+shift) - this layer's activation, the wgrad operand of
+                         the next layer - in the pre-split bf16 format (saves a tnb_view_presplit pass); NULL = off */
 } tnb_bnbwd_t;
 
 typedef struct {

@@ -213,6 +213,28 @@ def test_conv3x3_wgrad_tap_stacked(n, h, w, cin, cin_real, terms):
     assert G.rel_err(dw, dw_generic) < (1e-5 if terms == 3 else 1e-3)
 
 
+@pytest.mark.parametrize("c_up,c_skip,cout", [(128, 64, 64), (64, 64, 64), (256, 128, 128), (512, 256, 256)])
+def test_conv3x3_wgrad_concat_of_half_resolution_source(c_up, c_skip, cout):
+    """Decoder concat view [upsample(x), skip] given as two pre-split sources, the first one at half resolution
+    (TNB_SRC_PRESPLIT_UP: the fill reads pixel (h/2, w/2)): Cout 64 runs the tap-stacked kernel with per-tile source
+    selection, larger Cout the generic kernel (one launch per source)."""
+    n, h, w = 2, 12, 24
+    lo = _rand(n, c_up, h // 2, w // 2, seed=41)
+    sk = _rand(n, c_skip, h, w, seed=42)
+    xin = torch.cat([F.interpolate(lo, scale_factor=2, mode="nearest"), sk], 1)
+    dz = _rand(n, cout, h, w, seed=43, scale=1e-5)
+    wt = torch.zeros(cout, c_up + c_skip, 3, 3, requires_grad=True)
+    (F.conv2d(xin, wt, padding=1) * dz).sum().backward()
+    ps_lo, ps_sk = G.presplit(G.nhwc(lo)), G.presplit(G.nhwc(sk))
+    s0 = _lib.Src(ptr=ps_lo.data_ptr(), scale=None, shift=None, C=c_up, Hs=h // 2, Ws=w // 2, mode=_lib.SRC_PRESPLIT_UP)
+    s1 = _lib.Src(ptr=ps_sk.data_ptr(), scale=None, shift=None, C=c_skip, Hs=h, Ws=w, mode=_lib.SRC_PRESPLIT)
+    dw = G.wgrad3x3(G.make_view([s0, s1], n, h, w), G.nhwc(dz), cout, c_up + c_skip)
+    assert G.rel_err(dw, wt.grad) < 2e-4
+    if cout == 64:  # the generic kernel on the same operands
+        dw2 = G.wgrad3x3(G.make_view([s0, s1], n, h, w), G.nhwc(dz), cout, c_up + c_skip, variant=32)
+        assert G.rel_err(dw2, wt.grad) < 2e-4
+
+
 def test_conv3x3_full_resolution_layer_vs_torch_cuda():
     """down_block_1.conv_2 shape at the reference resolution (64->64 @ 288x512), checked on-device against
     torch's fp32 convolution (TF32 disabled) - the oracle op, just executed on the GPU for speed."""

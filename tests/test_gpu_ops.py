@@ -274,9 +274,14 @@ def test_bn_relu_backward_with_gradient_routing(consumers):
     # production format: the same dz emitted pre-split (bf16 hi/lo) for the dgrad / wgrad operand fills
     dzs = torch.zeros(n * h * w * c * 4, dtype=torch.uint8, device=G.DEV)
     args.dz, args.dz_format, args.amax = dzs.data_ptr(), 1, None
+    # ... and, in the same pass, the layer's own activation relu(bn(z)) pre-split: the next layer's wgrad operand
+    acts = torch.zeros(n * h * w * c * 4, dtype=torch.uint8, device=G.DEV)
+    args.act_presplit = acts.data_ptr()
     _lib.check(L.tnb_bn_relu_bwd_apply(C.byref(args), G.st()))
     torch.cuda.synchronize()
     assert G.max_abs(G.unsplit(dzs, (n, h, w, c)), dz) <= 2e-5 * dz.abs().max().item()
+    act_ref = F.relu(z.detach() * scale[None, :, None, None] + shift[None, :, None, None])
+    assert G.max_abs(G.unsplit(acts, (n, h, w, c)), G.nhwc(act_ref)) <= 2e-5 * act_ref.abs().max().item()
     # d gamma / d beta from the same reductions (checked through a second autograd pass)
     z2 = z.detach().clone(); g2 = gamma.clone().requires_grad_(True); b2 = beta.clone().requires_grad_(True)
     a2 = F.relu(F.batch_norm(z2, None, None, g2, b2, True, 0.1, 1e-5))

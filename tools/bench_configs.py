@@ -34,7 +34,12 @@ def inference_path(bs=32, seq_len=8, h=288, w=512, steps=10):
     with torch.no_grad():
         y = net(x)
         out["tracknet_fwd_ms"] = timed(lambda: net(x), steps, 3)
-        out["decode_ms"] = timed(lambda: T.decode_heatmaps(y), steps, 3)
+        # decode cost depends on the amount of foreground: time it on heatmaps as a trained model emits them (one small
+        # blob per frame, ~15 % empty) and on the random-init output (about half the pixels above 0.5: worst case)
+        xb, yb = B.synthetic_batch(bs, 3)
+        blobs = (yb.cuda() * 0.9 + 0.02)
+        out["decode_ms"] = timed(lambda: T.decode_heatmaps(blobs), steps, 3)
+        out["decode_dense_random_ms"] = timed(lambda: T.decode_heatmaps(y), steps, 3)
 
         def ens_step():
             e = T.TemporalEnsemble(seq_len, "weight", 10 ** 9)

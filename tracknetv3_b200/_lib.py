@@ -33,7 +33,7 @@ class BnBwd(C.Structure):  # tnb_bnbwd_t
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
                 ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
                 ("part", C.c_void_p), ("sums", C.c_void_p), ("dz", C.c_void_p), ("inv_count", C.c_float),
-                ("amax", C.c_void_p), ("dz_format", C.c_int)]
+                ("amax", C.c_void_p), ("dz_format", C.c_int), ("act_presplit", C.c_void_p)]
 
 
 class TrackNetCfg(C.Structure):  # tnb_tracknet_cfg_t
@@ -42,7 +42,7 @@ class TrackNetCfg(C.Structure):  # tnb_tracknet_cfg_t
                 ("bn_eps", C.c_float), ("bn_momentum", C.c_float)]
 
 
-SRC_IDENTITY, SRC_AFFINE_RELU, SRC_AFFINE_RELU_POOL, SRC_AFFINE_RELU_UP, SRC_PRESPLIT = 0, 1, 2, 3, 4
+SRC_IDENTITY, SRC_AFFINE_RELU, SRC_AFFINE_RELU_POOL, SRC_AFFINE_RELU_UP, SRC_PRESPLIT, SRC_PRESPLIT_UP = 0, 1, 2, 3, 4, 5
 GRAD_SAME, GRAD_POOL, GRAD_UP = 0, 1, 2
 
 vp, i32, i64, f32, f64, sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double, C.c_size_t

@@ -454,9 +454,12 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
   const int TP = nterms > 1 ? 2 : 1;
   int MT = 512 / BN;
   if (MT > 4) MT = 4;
-  // experiment switch (tools/ablate_plan.py): TNB_CONV_PLAN=1 halves the tile so that the accumulator double-buffers
-  static const int plan_mode = [] { const char* e = getenv("TNB_CONV_PLAN"); return e ? atoi(e) : 0; }();
-  if (plan_mode == 1) while (MT > 1 && 2 * MT * BN > 512) MT >>= 1;
+  // Two accumulator buffers in TMEM (2 * MT * BN <= 512 columns) let the epilogue of tile i overlap the MMAs of tile
+  // i + 1; with one buffer it is exposed (7-17 % of the layer, measured: profiles/r1_summary.md 6). Narrower tiles
+  // re-stream the weights twice as often, which only pays while the weight set is small: Cin <= 512.
+  // TNB_CONV_PLAN=0 restores the widest tile (tools/ablate_plan.py).
+  static const int plan_mode = [] { const char* e = getenv("TNB_CONV_PLAN"); return e ? atoi(e) : 1; }();
+  if (plan_mode == 1 && Cin <= 512) while (MT > 1 && 2 * MT * BN > 512) MT >>= 1;
   while (MT > 1 && 8 * (MT - 1) >= W) --MT;  // do not tile wider than the image
   int SA = 2, SB = 0, G = 1;
   size_t smem = 0;

@@ -14,7 +14,8 @@ enum SrcMode : int {
   SRC_AFFINE_RELU = TNB_SRC_AFFINE_RELU,            // relu(z*scale + shift)                  (model.py:12-16)
   SRC_AFFINE_RELU_POOL = TNB_SRC_AFFINE_RELU_POOL,  // maxpool2x2(relu(z*scale+shift)), z is 2H x 2W (model.py:59,61,63)
   SRC_AFFINE_RELU_UP = TNB_SRC_AFFINE_RELU_UP,      // nearest x2 upsample of relu(z*scale+shift)  (model.py:65,67,69)
-  SRC_PRESPLIT = TNB_SRC_PRESPLIT                   // already (hi, lo) 16-bit, [pixel][2][C]: pure copy
+  SRC_PRESPLIT = TNB_SRC_PRESPLIT,                  // already (hi, lo) 16-bit, [pixel][2][C]: pure copy
+  SRC_PRESPLIT_UP = TNB_SRC_PRESPLIT_UP             // the same at half resolution, read as its nearest x2 upsampling (wgrad)
 };
 using SrcDesc = tnb_src_t;    // see include/tracknet_b200.h
 using ViewDesc = tnb_view_t;

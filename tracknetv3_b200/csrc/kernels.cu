@@ -399,6 +399,14 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnB
           *reinterpret_cast<uint2*>(base) = make_uint2(h01, h23);
           *reinterpret_cast<uint2*>(base + 2 * a.C) = make_uint2(l01, l23);
         }
+        if (a.act_presplit != nullptr) {  // the activation itself, pre-split: the next layer's wgrad operand
+          uint32_t h01, l01, h23, l23;
+          split2<1>(fmaxf(act[k].x, 0.f), fmaxf(act[k].y, 0.f), h01, l01);
+          split2<1>(fmaxf(act[k].z, 0.f), fmaxf(act[k].w, 0.f), h23, l23);
+          uint8_t* base = reinterpret_cast<uint8_t*>(a.act_presplit) + (pix * 2 * a.C + c) * 2;
+          *reinterpret_cast<uint2*>(base) = make_uint2(h01, h23);
+          *reinterpret_cast<uint2*>(base + 2 * a.C) = make_uint2(l01, l23);
+        }
         amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
       } else {
         acc1 = f4add(acc1, d);
@@ -823,12 +831,14 @@ TNB_DEVINL void conv1d_k3(float* out, int Cout, const float* inA, int CA, const 
     const int l = idx % L, co = idx / L;
     const float* wr = w + (size_t)co * Cin * 3;
     float s = b[co];
+#pragma unroll 4
     for (int ci = 0; ci < CA; ++ci) {
       const float* row = inA + ci * L;
       const float w0 = __ldg(wr + ci * 3), w1 = __ldg(wr + ci * 3 + 1), w2 = __ldg(wr + ci * 3 + 2);
       const float xm = l > 0 ? row[l - 1] : 0.f, xp = l + 1 < L ? row[l + 1] : 0.f;
       s = fmaf(w0, xm, s); s = fmaf(w1, row[l], s); s = fmaf(w2, xp, s);
     }
+#pragma unroll 4
     for (int ci = 0; ci < CB; ++ci) {
       const float* row = inB + ci * L;
       const float* wq = wr + (size_t)(CA + ci) * 3;
@@ -842,7 +852,7 @@ TNB_DEVINL void conv1d_k3(float* out, int Cout, const float* inA, int CA, const 
   }
   __syncthreads();
 }
-__global__ void __launch_bounds__(256) inpaint_fwd_kernel(const float* __restrict__ coords,
+__global__ void __launch_bounds__(1024) inpaint_fwd_kernel(const float* __restrict__ coords,
                                                           const float* __restrict__ mask, InpaintParams P, int L,
                                                           float* __restrict__ out) {
   extern __shared__ float sm[];
@@ -882,7 +892,8 @@ int launch_inpaint_fwd(const float* coords, const float* mask, const InpaintPara
   const size_t smem = (size_t)(3 + 32 + 64 + 128 + 256 + 256 + 128 + 64 + 32 + 2) * L * sizeof(float);
   TNB_REQUIRE(smem <= 227 * 1024, "inpaint_fwd: sequence length %d too long for the fused kernel", L);
   TNB_CHECK_CUDA(cudaFuncSetAttribute(inpaint_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  inpaint_fwd_kernel<<<N, 256, smem, st>>>(coords, mask, p, L, out);
+  // latency-bound: one CTA per trajectory, as many warps as the SM takes to hide the L2 latency of the weight reads
+  inpaint_fwd_kernel<<<N, 1024, smem, st>>>(coords, mask, p, L, out);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -937,7 +948,7 @@ TNB_DEVINL void conv1d_k3_dgrad(const float* dz, int Cout, const float* __restri
     dIn[idx] = accumulate ? dIn[idx] + s : s;
   }
 }
-__global__ void __launch_bounds__(512) inpaint_bwd_kernel(const float* __restrict__ coords,
+__global__ void __launch_bounds__(1024) inpaint_bwd_kernel(const float* __restrict__ coords,
                                                           const float* __restrict__ mask, InpaintParams P,
                                                           const float* __restrict__ dout, InpaintGrads G, int L,
                                                           float* __restrict__ dcoords) {
@@ -1020,7 +1031,7 @@ int launch_inpaint_bwd(const float* coords, const float* mask, const InpaintPara
   const size_t smem = (size_t)2 * (3 + 32 + 64 + 128 + 256 + 256 + 128 + 64 + 32 + 2) * L * sizeof(float);
   TNB_REQUIRE(smem <= 227 * 1024, "inpaint_bwd: sequence length %d too long for the fused kernel (max 28)", L);
   TNB_CHECK_CUDA(cudaFuncSetAttribute(inpaint_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  inpaint_bwd_kernel<<<N, 512, smem, st>>>(coords, mask, p, dout, g, L, dcoords);
+  inpaint_bwd_kernel<<<N, 1024, smem, st>>>(coords, mask, p, dout, g, L, dcoords);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -77,6 +77,14 @@ struct Bump {
   }
 };
 
+// Layer l reads the activation of layer l - 1 as it is (BN + ReLU, same resolution, no concat): its wgrad operand can
+// be written by the BatchNorm-backward apply pass of layer l - 1 (which recomputes that activation anyway) instead of
+// a separate view pass; the wgrad of layer l is then launched right after that pass.
+bool wgrad_operand_from_bn_bwd(const tnb_tracknet_cfg_t& c, int l) {
+  if (c.variant & 128) return false;  // variant bit 128: always materialise with tnb_view_presplit (ablation)
+  return l > 0 && kDefs[l].src0 == l - 1 && kDefs[l].src1 < 0 && kDefs[l].mode0 == SRC_AFFINE_RELU;
+}
+
 int layer_cin(const tnb_tracknet_cfg_t& c, int l) {
   if (l == 0) return (c.in_dim + 31) / 32 * 32;
   const LayerDef& d = kDefs[l];
@@ -126,7 +134,9 @@ int build_plan(const tnb_tracknet_cfg_t& c, void* ws, Plan* P) {
       B.din = (l > 0) ? b.take<float>(npix * B.cin) : nullptr;
       B.bwd_rows = bn_bwd_num_blocks(c.n, B.H, B.W, B.cout);
       B.fused_rows = 0;
-      if (!(c.variant & 64) && bn_reduce_fusable(l)) {  // variant bit 64: keep the stand-alone reduction (ablation)
+      // variant bit 64 switches the fusion ON. It is off by default: measured neutral on the bs-10 step (the dgrad
+      // epilogue gets slower by about what the stand-alone reduction pass costs, profiles/r1_summary.md 6)
+      if ((c.variant & 64) && bn_reduce_fusable(l)) {
         // dgrad of layer l + 1: K side = its cout, N side = its cin = this layer's cout, same resolution
         B.fused_rows = conv3x3_num_stat_rows(c.n, B.H, B.W, kDefs[l + 1].cout, B.cout, c.bwd_terms, true);
         if (B.fused_rows < 0) return -2;
@@ -222,6 +232,22 @@ int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float*
   if (int rc = launch_predictor_bwd(last, c.n, c.h, c.w, (const float*)params[kLayers * 6 + 0], c.out_dim, dy, y,
                                     P.dA_pred, (float*)grads[kLayers * 3 + 0], (float*)grads[kLayers * 3 + 1], st))
     return rc;
+  auto run_wgrad = [&](int layer, const ViewDesc& pv) -> int {
+    LayerBuf& W = P.L[layer];
+    float* dw = (float*)grads[layer * 3 + 0];
+    TNB_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)W.cout * W.cin_real * 9, st));
+    return launch_wgrad3x3(pv, W.dz, dw, W.cout, W.cin_real, c.bwd_terms, (c.variant >> 2) & 3, st);
+  };
+  auto plain_presplit_view = [&](int layer) {
+    const LayerBuf& W = P.L[layer];
+    ViewDesc pv;
+    memset(&pv, 0, sizeof(pv));
+    pv.N = c.n; pv.H = W.H; pv.W = W.W; pv.C = pv.C0 = W.cin;
+    pv.s[0] = SrcDesc{reinterpret_cast<const float*>(P.vsplit), nullptr, nullptr, W.cin, W.H, W.W, SRC_PRESPLIT};
+    pv.s[1] = pv.s[0];
+    return pv;
+  };
+  int pending = -1;  // layer whose wgrad waits for its operand from the next BatchNorm-backward apply pass
   for (int l = kLayers - 1; l >= 0; --l) {
     LayerBuf& B = P.L[l];
     BnBwdArgs a;
@@ -252,7 +278,12 @@ int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float*
     if (int rc = launch_bn_bwd_finalize(B.bwd_part, B.fused_rows > 0 ? B.fused_rows : B.bwd_rows, B.cout, B.bwd_sums,
                                         (float*)grads[l * 3 + 1], (float*)grads[l * 3 + 2], st))
       return rc;
+    a.act_presplit = (pending == l + 1) ? P.vsplit : nullptr;
     if (int rc = launch_bn_bwd_apply(a, st)) return rc;
+    if (pending == l + 1) {
+      if (int rc = run_wgrad(pending, plain_presplit_view(pending))) return rc;
+      pending = -1;
+    }
     const float* w = (const float*)params[l * 6 + 0];
     if (l > 0) {
       ViewDesc dv;
@@ -270,17 +301,32 @@ int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float*
                                   c.variant & 3, st, Pp != nullptr ? &fuse : nullptr))
         return rc;
     }
-    float* dw = (float*)grads[l * 3 + 0];
-    TNB_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)B.cout * B.cin_real * 9, st));
+    if (wgrad_operand_from_bn_bwd(c, l)) { pending = l; continue; }
     // materialise the input view once (bf16 hi/lo), then both wgrad operands are plain copies
     const ViewDesc v = make_view(P, c, l);
-    if (int rc = launch_view_presplit(v, P.vsplit, 1, st)) return rc;
     ViewDesc pv;
     memset(&pv, 0, sizeof(pv));
-    pv.s[0] = SrcDesc{reinterpret_cast<const float*>(P.vsplit), nullptr, nullptr, B.cin, B.H, B.W, SRC_PRESPLIT};
-    pv.s[1] = pv.s[0];
-    pv.C0 = pv.C = B.cin; pv.N = c.n; pv.H = B.H; pv.W = B.W;
-    if (int rc = launch_wgrad3x3(pv, B.dz, dw, B.cout, B.cin_real, c.bwd_terms, (c.variant >> 2) & 3, st)) return rc;
+    pv.N = c.n; pv.H = B.H; pv.W = B.W; pv.C = B.cin;
+    if (v.C0 < v.C && v.s[0].mode == SRC_AFFINE_RELU_UP && v.s[1].mode == SRC_AFFINE_RELU) {
+      // decoder concat [up(x), skip]: the up-sampled half is materialised at ITS OWN (half) resolution and read by
+      // the wgrad fill through (h/2, w/2) addressing - a quarter of the bytes of the up-sampled tensor
+      ViewDesc v0 = v, v1 = v;
+      v0.s[0].mode = SRC_AFFINE_RELU; v0.s[1] = v0.s[0]; v0.C0 = v0.C = v.C0; v0.H = v.s[0].Hs; v0.W = v.s[0].Ws;
+      v1.s[0] = v.s[1]; v1.s[1] = v.s[1]; v1.C0 = v1.C = v.C - v.C0;
+      uint8_t* up = P.vsplit;
+      uint8_t* skip = P.vsplit + (size_t)c.n * v0.H * v0.W * v0.C * 4;
+      if (int rc = launch_view_presplit(v0, up, 1, st)) return rc;
+      if (int rc = launch_view_presplit(v1, skip, 1, st)) return rc;
+      pv.s[0] = SrcDesc{reinterpret_cast<const float*>(up), nullptr, nullptr, v0.C, v0.H, v0.W, SRC_PRESPLIT_UP};
+      pv.s[1] = SrcDesc{reinterpret_cast<const float*>(skip), nullptr, nullptr, v1.C, B.H, B.W, SRC_PRESPLIT};
+      pv.C0 = v0.C;
+    } else {
+      if (int rc = launch_view_presplit(v, P.vsplit, 1, st)) return rc;
+      pv.s[0] = SrcDesc{reinterpret_cast<const float*>(P.vsplit), nullptr, nullptr, B.cin, B.H, B.W, SRC_PRESPLIT};
+      pv.s[1] = pv.s[0];
+      pv.C0 = B.cin;
+    }
+    if (int rc = run_wgrad(l, pv)) return rc;
   }
   return 0;
 }
@@ -288,10 +334,13 @@ int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float*
 int tracknet_num_launches(const tnb_tracknet_cfg_t& c, int backward) {
   if (!backward) return 1 + kLayers * 3 + (c.training ? 1 : 0) + 1;  // pack, (wpack, conv, bn_finalize) x17, counters, predictor
   int fused = 0;
-  for (int l = 0; l < kLayers; ++l) fused += (!(c.variant & 64) && bn_reduce_fusable(l)) ? 1 : 0;
+  for (int l = 0; l < kLayers; ++l) fused += ((c.variant & 64) && bn_reduce_fusable(l)) ? 1 : 0;
   // predictor_bwd, (reduce [unless fused into the next layer's dgrad], finalize, apply, view_presplit, wgrad) x17,
   // (wpack, dgrad) x16
-  return 1 + kLayers * 5 - fused + (kLayers - 1) * 2;
+  int emitted = 0;  // wgrad operands written by the BatchNorm-backward apply pass: no view_presplit launch
+  for (int l = 0; l < kLayers; ++l) emitted += wgrad_operand_from_bn_bwd(c, l) ? 1 : 0;
+  // + second view_presplit of the 3 decoder concat layers, + one memset per weight gradient is not a kernel
+  return 1 + kLayers * 5 - fused - emitted + (kLayers - 1) * 2 + 3;
 }
 
 }  // namespace tnb

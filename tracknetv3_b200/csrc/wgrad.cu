@@ -165,7 +165,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
     const SrcDesc& VS = vsecond ? V.s[1] : V.s[0];
     const int vcc = vsecond ? vch - V.C0 : vch;
     float sc[8], sh[8];
-    if (VMODE != SRC_IDENTITY && VMODE != SRC_PRESPLIT && vactive) { ld8(VS.scale + vcc, sc); ld8(VS.shift + vcc, sh); }
+    if (VMODE != SRC_IDENTITY && VMODE != SRC_PRESPLIT && VMODE != SRC_PRESPLIT_UP && vactive) {
+      ld8(VS.scale + vcc, sc); ld8(VS.shift + vcc, sh);
+    }
     const uint8_t* dz_base = a.dz + (size_t)(co0 + dpl * 8) * 2;  // dz: [pixel][2 (hi, lo)][Cout] bf16
     const size_t dz_pix_stride = (size_t)a.Cout * 4;
     const int dz_lo = a.Cout * 2;
@@ -183,12 +185,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
       uint8_t* dzp = stage + dpl * DZPL;
       uint8_t* vwp = stage + DZ_BYTES + vpl * VPL;
 
-      if (VMODE == SRC_PRESPLIT && (a.variant & 8)) {  // ablation: barrier traffic only
+      constexpr bool kCopy = (VMODE == SRC_PRESPLIT || VMODE == SRC_PRESPLIT_UP);  // both operands are plain copies
+      if (kCopy && (a.variant & 8)) {  // ablation: barrier traffic only
         cp_async_mbar_arrive_noinc(&full[s]);
         if (++s == S) { s = 0; ph ^= 1; }
         continue;
       }
-      if (VMODE == SRC_PRESPLIT) {
+      if (kCopy) {
         // Both operands are already (hi, lo) 16-bit pairs in HBM: the fill is 16-byte cp.async copies straight into
         // the planar tiles. The thread never waits for its own loads (the stage's mbarrier is armed with a
         // cp.async-completion arrival), so up to kStages K tiles of HBM latency are in flight per thread.
@@ -214,7 +217,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
               const int hr = p / kHaloW, hc = p - hr * kHaloW;
               const int h = h0 + hr + dy0 - 1, w = w0 - 1 + hc;
               const bool ok = h >= 0 && h < V.H && w >= 0 && w < V.W;
-              const uint8_t* q = ok ? vbase + ((size_t)(n * VS.Hs + h) * VS.Ws + w) * vstride : vbase;
+              // PRESPLIT_UP: the source is the half-resolution tensor, pixel (h, w) of the view is its (h/2, w/2)
+              const int hs = VMODE == SRC_PRESPLIT_UP ? h >> 1 : h, wsrc = VMODE == SRC_PRESPLIT_UP ? w >> 1 : w;
+              const uint8_t* q = ok ? vbase + ((size_t)(n * VS.Hs + hs) * VS.Ws + wsrc) * vstride : vbase;
               cp_async16(vwp + p * 16, q, ok ? 16u : 0u);
               if (a.nterms > 1) cp_async16(vwp + p * 16 + NPL * VPL, q + v_lo, ok ? 16u : 0u);
             }
@@ -344,7 +349,10 @@ static constexpr int kSRP = 19 * 16;        // bytes per (halo row, plane): 18 c
 static constexpr int kSRows = kTileH + 3;   // 6 halo rows filled + 1 slack row read by the unused half of dy = 2
 
 struct WgradSArgs {
-  const uint8_t* view;  // pre-split bf16 [N,H,W][2][C]
+  const uint8_t* view;  // pre-split bf16 [N,H,W][2][C] (first source: channels [0, C0))
+  const uint8_t* view1; // second source of a concat view, channels [C0, C)
+  int C0, Cs0, Cs1;     // channels of the first source in the view; channel strides of the two source tensors
+  int up0, Hs0, Ws0;    // first source is at half resolution (SRC_PRESPLIT_UP) with these dimensions
   const uint8_t* dz;    // pre-split bf16 [N,H,W][2][Cout]
   float* dw;
   int N, H, W, C, Cout, CinReal, P /*planes per ci tile: 8 or 4*/, nterms, ncit, ncot;
@@ -468,11 +476,17 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __g
         const int hr = hp / kHaloW, hc = hp - hr * kHaloW;
         soff[u] = (hr * P + pl) * kSRP + hc * 16;
         dh[u] = hr - 1; dwv[u] = hc - 1;
-        goff[u] = (ci0 + pl * 8) * 2;
+        goff[u] = (ci0 - (ci0 >= a.C0 ? a.C0 : 0) + pl * 8) * 2;
       }
     }
-    const size_t dz_stride = (size_t)a.Cout * 4, v_stride = (size_t)a.C * 4;
-    const int dz_lo = a.Cout * 2, v_lo = a.C * 2;
+    // a CTA's 64 (32) input channels come from ONE source of the view (launcher: C0 is a multiple of the tile)
+    const bool second = ci0 >= a.C0;
+    const uint8_t* vsrc = second ? a.view1 : a.view;
+    const int vC = second ? a.Cs1 : a.Cs0;
+    const int vshift = (!second && a.up0) ? 1 : 0;
+    const int vH = vshift ? a.Hs0 : a.H, vW = vshift ? a.Ws0 : a.W;
+    const size_t dz_stride = (size_t)a.Cout * 4, v_stride = (size_t)vC * 4;
+    const int dz_lo = a.Cout * 2, v_lo = vC * 2;
     const int per_img = a.tiles_h * a.tiles_w;
 
     int s = 0;
@@ -490,8 +504,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __g
           const int h = h0 + dh[u], w = w0 + dwv[u];
           const bool ok = h >= 0 && h < a.H && w >= 0 && w < a.W;
           const size_t pix = (size_t)(n * a.H + h) * a.W + w;
+          const size_t vpix = (size_t)(n * vH + (h >> vshift)) * vW + (w >> vshift);
           const uint8_t* q = isdz[u] ? (ok ? a.dz + pix * dz_stride + goff[u] : a.dz)
-                                     : (ok ? a.view + pix * v_stride + goff[u] : a.view);
+                                     : (ok ? vsrc + vpix * v_stride + goff[u] : vsrc);
           cp_async16(stage + soff[u], q, ok ? 16u : 0u);
           if (a.nterms > 1)
             cp_async16(stage + soff[u] + (isdz[u] ? B_TERM : A_TERM), q + (isdz[u] ? dz_lo : v_lo), ok ? 16u : 0u);
@@ -533,14 +548,23 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __g
 }
 
 static bool stacked_applicable(const ViewDesc& view, int Cout) {
-  return Cout == 64 && view.C0 == view.C && view.s[0].mode == SRC_PRESPLIT && (view.C == 32 || view.C % 64 == 0) &&
-         view.s[0].Hs == view.H && view.s[0].Ws == view.W;
+  if (Cout != 64 || !(view.C == 32 || view.C % 64 == 0)) return false;
+  const bool two = view.C0 < view.C;
+  if (two && view.C0 % 64 != 0) return false;
+  const SrcDesc& s0 = view.s[0];
+  const bool ok0 = (s0.mode == SRC_PRESPLIT && s0.Hs == view.H && s0.Ws == view.W) ||
+                   (s0.mode == SRC_PRESPLIT_UP && s0.Hs * 2 == view.H && s0.Ws * 2 == view.W);
+  const bool ok1 = !two || (view.s[1].mode == SRC_PRESPLIT && view.s[1].Hs == view.H && view.s[1].Ws == view.W);
+  return ok0 && ok1;
 }
 
 static int launch_wgrad3x3_stacked(const ViewDesc& view, const void* dz_presplit, float* dw, int Cout, int CinReal,
                                    int nterms, cudaStream_t st) {
   WgradSArgs a;
   a.view = reinterpret_cast<const uint8_t*>(view.s[0].ptr); a.dz = (const uint8_t*)dz_presplit; a.dw = dw;
+  a.view1 = reinterpret_cast<const uint8_t*>(view.C0 < view.C ? view.s[1].ptr : view.s[0].ptr);
+  a.C0 = view.C0; a.Cs0 = view.s[0].C; a.Cs1 = view.C0 < view.C ? view.s[1].C : view.s[0].C;
+  a.up0 = view.s[0].mode == SRC_PRESPLIT_UP ? 1 : 0; a.Hs0 = view.s[0].Hs; a.Ws0 = view.s[0].Ws;
   a.N = view.N; a.H = view.H; a.W = view.W; a.C = view.C; a.Cout = Cout; a.CinReal = CinReal; a.nterms = nterms;
   a.P = view.C == 32 ? 4 : 8;
   a.ncit = view.C / (a.P * 8); a.ncot = Cout / 64;
@@ -618,6 +642,7 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
       case SRC_AFFINE_RELU_POOL: return launch(std::integral_constant<int, SRC_AFFINE_RELU_POOL>{}, args, 0, gx_count);
       case SRC_AFFINE_RELU_UP: return launch(std::integral_constant<int, SRC_AFFINE_RELU_UP>{}, args, 0, gx_count);
       case SRC_PRESPLIT: return launch(std::integral_constant<int, SRC_PRESPLIT>{}, args, 0, gx_count);
+      case SRC_PRESPLIT_UP: return launch(std::integral_constant<int, SRC_PRESPLIT_UP>{}, args, 0, gx_count);
       default: tnb::set_last_error("wgrad3x3: bad view mode %d", mode); return -2;
     }
   };
