@@ -4,6 +4,7 @@
 // Nothing here is derived from the reference (which has no native code);
 // descriptor bit layouts follow the PTX ISA tcgen05 matrix / instruction descriptor tables.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -101,9 +102,19 @@ TNB_DEVINL void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint6
 }
 
 // 16-byte asynchronous global->shared copy (LDGSTS). src_bytes = 0 zero-fills the destination without reading.
-TNB_DEVINL void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
-               : "memory");
+// ca = true allocates the line in L1 (.ca) instead of bypassing it (.cg): neighbouring threads that copy the two
+// 16-byte halves of one 32-byte sector to non-adjacent shared-memory addresses then share one sector fetch.
+TNB_DEVINL void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes, bool ca = false) {
+  if (ca)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+                 : "memory");
+  else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+                 : "memory");
+}
+inline int cp_async_ca_env() {  // experiment switch TNB_CPASYNC_CA=1
+  static const int v = [] { const char* e = getenv("TNB_CPASYNC_CA"); return e ? atoi(e) : 0; }();
+  return v;
 }
 // The mbarrier receives one arrival (counted against its initial expected count) once all cp.async operations issued
 // so far by this thread have landed: producers never wait for their own loads.

@@ -393,12 +393,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
             const uint8_t* sbase = reinterpret_cast<const uint8_t*>(S.ptr) + (size_t)cc * 2;  // [pixel][2][C] 16-bit
             const size_t sstride = (size_t)S.C * 4;
             const int lo_off = S.C * 2;
+            const bool ca = (a.variant & 256) != 0;
             for (int p = pbase; p < HALO_PX; p += kFillThreads / 4) {
               const int2 e = table[p];
               const int off = second ? e.y : e.x;
               const uint8_t* q = off >= 0 ? sbase + (size_t)off * sstride : sbase;
-              cp_async16(stage + p * 16, q, off >= 0 ? 16u : 0u);
-              if (a.nterms > 1) cp_async16(stage + p * 16 + 4 * PLANE, q + lo_off, off >= 0 ? 16u : 0u);
+              cp_async16(stage + p * 16, q, off >= 0 ? 16u : 0u, ca);
+              if (a.nterms > 1) cp_async16(stage + p * 16 + 4 * PLANE, q + lo_off, off >= 0 ? 16u : 0u, ca);
             }
           }
           cp_async_mbar_arrive_noinc(&full_A[sa]);
@@ -519,7 +520,7 @@ int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, floa
     a.bz = fuse->z; a.bsc = fuse->scale; a.bsh = fuse->shift; a.bmu = fuse->mean; a.bis = fuse->invstd;
   }
   a.Cout = Cout; a.BN = p.BN; a.MT = p.MT; a.SA = p.SA; a.SB = p.SB; a.G = p.G; a.nbuf = p.nbuf; a.nterms = nterms;
-  a.variant = variant; a.tmem_cols = p.tmem_cols; a.tiles_h = p.tiles_h; a.tiles_w = p.tiles_w;
+  a.variant = variant | (cp_async_ca_env() ? 256 : 0); a.tmem_cols = p.tmem_cols; a.tiles_h = p.tiles_h; a.tiles_w = p.tiles_w;
   a.ntiles = view.N * p.tiles_h * p.tiles_w;
   a.nwork = a.ntiles * (Cout / p.BN);
   const int grid = a.nwork < num_sms() ? a.nwork : num_sms();

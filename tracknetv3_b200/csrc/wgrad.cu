@@ -165,14 +165,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
     const SrcDesc& VS = vsecond ? V.s[1] : V.s[0];
     const int vcc = vsecond ? vch - V.C0 : vch;
     float sc[8], sh[8];
-    if (VMODE != SRC_IDENTITY && VMODE != SRC_PRESPLIT && VMODE != SRC_PRESPLIT_UP && vactive) {
-      ld8(VS.scale + vcc, sc); ld8(VS.shift + vcc, sh);
-    }
+    if (VMODE != SRC_IDENTITY && VMODE != SRC_PRESPLIT && vactive) { ld8(VS.scale + vcc, sc); ld8(VS.shift + vcc, sh); }
     const uint8_t* dz_base = a.dz + (size_t)(co0 + dpl * 8) * 2;  // dz: [pixel][2 (hi, lo)][Cout] bf16
     const size_t dz_pix_stride = (size_t)a.Cout * 4;
     const int dz_lo = a.Cout * 2;
     const int per_img = a.tiles_h * a.tiles_w;
 
+    const bool ca = (a.variant & 256) != 0;
     int s = 0;
     uint32_t ph = 0;
     for (int kt = kt0; kt < kt1; ++kt) {
@@ -185,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
       uint8_t* dzp = stage + dpl * DZPL;
       uint8_t* vwp = stage + DZ_BYTES + vpl * VPL;
 
-      constexpr bool kCopy = (VMODE == SRC_PRESPLIT || VMODE == SRC_PRESPLIT_UP);  // both operands are plain copies
+      constexpr bool kCopy = (VMODE == SRC_PRESPLIT);  // both operands are plain copies
       if (kCopy && (a.variant & 8)) {  // ablation: barrier traffic only
         cp_async_mbar_arrive_noinc(&full[s]);
         if (++s == S) { s = 0; ph ^= 1; }
@@ -202,14 +201,15 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
             const int h = h0 + (px >> 4), w = w0 + (px & 15);
             const bool ok = h < V.H && w < V.W;
             const uint8_t* q = ok ? dz_base + ((size_t)(n * V.H + h) * V.W + w) * dz_pix_stride : a.dz;
-            cp_async16(dzp + px * 16, q, ok ? 16u : 0u);
-            if (a.nterms > 1) cp_async16(dzp + px * 16 + 16 * DZPL, q + dz_lo, ok ? 16u : 0u);
+            cp_async16(dzp + px * 16, q, ok ? 16u : 0u, ca);
+            if (a.nterms > 1) cp_async16(dzp + px * 16 + 16 * DZPL, q + dz_lo, ok ? 16u : 0u, ca);
           }
         }
         if (vactive) {
           const uint8_t* vbase = reinterpret_cast<const uint8_t*>(VS.ptr) + (size_t)vcc * 2;  // [pixel][2][C] 16-bit
           const size_t vstride = (size_t)VS.C * 4;
           const int v_lo = VS.C * 2;
+          const int vup = VS.mode == SRC_PRESPLIT_UP ? 1 : 0;
 #pragma unroll
           for (int u = 0; u < 3; ++u) {
             const int p = vpx0 + u * VG;
@@ -218,10 +218,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
               const int h = h0 + hr + dy0 - 1, w = w0 - 1 + hc;
               const bool ok = h >= 0 && h < V.H && w >= 0 && w < V.W;
               // PRESPLIT_UP: the source is the half-resolution tensor, pixel (h, w) of the view is its (h/2, w/2)
-              const int hs = VMODE == SRC_PRESPLIT_UP ? h >> 1 : h, wsrc = VMODE == SRC_PRESPLIT_UP ? w >> 1 : w;
-              const uint8_t* q = ok ? vbase + ((size_t)(n * VS.Hs + hs) * VS.Ws + wsrc) * vstride : vbase;
-              cp_async16(vwp + p * 16, q, ok ? 16u : 0u);
-              if (a.nterms > 1) cp_async16(vwp + p * 16 + NPL * VPL, q + v_lo, ok ? 16u : 0u);
+              const uint8_t* q = ok ? vbase + ((size_t)(n * VS.Hs + (h >> vup)) * VS.Ws + (w >> vup)) * vstride : vbase;
+              cp_async16(vwp + p * 16, q, ok ? 16u : 0u, ca);
+              if (a.nterms > 1) cp_async16(vwp + p * 16 + NPL * VPL, q + v_lo, ok ? 16u : 0u, ca);
             }
           }
         }
@@ -357,6 +356,7 @@ struct WgradSArgs {
   float* dw;
   int N, H, W, C, Cout, CinReal, P /*planes per ci tile: 8 or 4*/, nterms, ncit, ncot;
   int tiles_h, tiles_w, ktiles, ktiles_per_cta;
+  int ca;  // cp.async.ca instead of .cg (experiment)
 };
 
 __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __grid_constant__ WgradSArgs a) {
@@ -507,9 +507,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __g
           const size_t vpix = (size_t)(n * vH + (h >> vshift)) * vW + (w >> vshift);
           const uint8_t* q = isdz[u] ? (ok ? a.dz + pix * dz_stride + goff[u] : a.dz)
                                      : (ok ? vsrc + vpix * v_stride + goff[u] : vsrc);
-          cp_async16(stage + soff[u], q, ok ? 16u : 0u);
+          cp_async16(stage + soff[u], q, ok ? 16u : 0u, a.ca != 0);
           if (a.nterms > 1)
-            cp_async16(stage + soff[u] + (isdz[u] ? B_TERM : A_TERM), q + (isdz[u] ? dz_lo : v_lo), ok ? 16u : 0u);
+            cp_async16(stage + soff[u] + (isdz[u] ? B_TERM : A_TERM), q + (isdz[u] ? dz_lo : v_lo), ok ? 16u : 0u,
+                       a.ca != 0);
         }
       }
       cp_async_mbar_arrive_noinc(&full[s]);
@@ -567,6 +568,7 @@ static int launch_wgrad3x3_stacked(const ViewDesc& view, const void* dz_presplit
   a.up0 = view.s[0].mode == SRC_PRESPLIT_UP ? 1 : 0; a.Hs0 = view.s[0].Hs; a.Ws0 = view.s[0].Ws;
   a.N = view.N; a.H = view.H; a.W = view.W; a.C = view.C; a.Cout = Cout; a.CinReal = CinReal; a.nterms = nterms;
   a.P = view.C == 32 ? 4 : 8;
+  a.ca = cp_async_ca_env();
   a.ncit = view.C / (a.P * 8); a.ncot = Cout / 64;
   a.tiles_h = (view.H + kTileH - 1) / kTileH;
   a.tiles_w = (view.W + kTileW - 1) / kTileW;
@@ -603,7 +605,7 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
     return launch_wgrad3x3_stacked(view, dz_presplit, dw, Cout, CinReal, nterms, st);
   WgradArgs a;
   a.view = view; a.dz = (const uint8_t*)dz_presplit; a.dw = dw; a.Cout = Cout; a.CinReal = CinReal;
-  a.nterms = nterms; a.variant = variant; a.ci_tile_base = 0;
+  a.nterms = nterms; a.variant = variant | (cp_async_ca_env() ? 256 : 0); a.ci_tile_base = 0;
   a.NT = pick_nt(view.C, view.C0);
   TNB_REQUIRE(a.NT > 0, "wgrad3x3: no input-channel tile for Cin=%d (first source %d)", view.C, view.C0);
   a.tiles_h = (view.H + kTileH - 1) / kTileH;
@@ -627,7 +629,9 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
   // one gather mode per launch: a concat view whose two halves use different modes is split by the channel tiling
   // (pick_nt keeps every CTA inside one source), but the kernel is instantiated per mode -> require equal modes or
   // fall back to the first source's mode only when the second source is unused
-  const int mode0 = view.s[0].mode, mode1 = (view.C0 < view.C) ? view.s[1].mode : view.s[0].mode;
+  // a half-resolution pre-split source differs from a full-resolution one by an address shift only: same instantiation
+  auto canon = [](int m) { return m == SRC_PRESPLIT_UP ? (int)SRC_PRESPLIT : m; };
+  const int mode0 = canon(view.s[0].mode), mode1 = canon((view.C0 < view.C) ? view.s[1].mode : view.s[0].mode);
   auto launch = [&](auto tag, const WgradArgs& args, int gx_first, int gx_count) -> int {
     constexpr int M = decltype(tag)::value;
     TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -642,7 +646,6 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
       case SRC_AFFINE_RELU_POOL: return launch(std::integral_constant<int, SRC_AFFINE_RELU_POOL>{}, args, 0, gx_count);
       case SRC_AFFINE_RELU_UP: return launch(std::integral_constant<int, SRC_AFFINE_RELU_UP>{}, args, 0, gx_count);
       case SRC_PRESPLIT: return launch(std::integral_constant<int, SRC_PRESPLIT>{}, args, 0, gx_count);
-      case SRC_PRESPLIT_UP: return launch(std::integral_constant<int, SRC_PRESPLIT_UP>{}, args, 0, gx_count);
       default: tnb::set_last_error("wgrad3x3: bad view mode %d", mode); return -2;
     }
   };
@@ -651,6 +654,8 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
     if (int rc = dispatch(mode0, a, gx)) return rc;
   } else {
     // two launches, one per source: ci tiles [0, C0/NT) use mode0, the rest mode1 (ci_base shifts blockIdx.x)
+    // (each launch under-fills the GPU: the K split was chosen for the combined grid. Only views whose two halves need
+    // different on-the-fly gathers come here; the network's backward pass materialises both halves pre-split.)
     WgradArgs a0 = a, a1 = a;
     const int t0 = view.C0 / a.NT;
     a0.ncit = t0; a0.ci_tile_base = 0;
