@@ -102,8 +102,10 @@ TNB_DEVINL void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint6
 }
 
 // 16-byte asynchronous global->shared copy (LDGSTS). src_bytes = 0 zero-fills the destination without reading.
-// ca = true allocates the line in L1 (.ca) instead of bypassing it (.cg): neighbouring threads that copy the two
-// 16-byte halves of one 32-byte sector to non-adjacent shared-memory addresses then share one sector fetch.
+// ca = true allocates the line in L1 (.ca) instead of bypassing it (.cg). With .cg every 16-byte copy fetches its own
+// 32-byte sector from L2 even when the neighbouring thread copies the other half (measured with ncu on the wgrad fill:
+// 31.7 sectors per 512-byte warp request, 2.38 GB moved for 1.19 GB used); with .ca the two halves share one fetch.
+// wgrad 7.72 -> 6.52 ms per step, dgrad 5.80 -> 5.63 (profiles/r1_summary.md 6).
 TNB_DEVINL void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes, bool ca = false) {
   if (ca)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
@@ -112,8 +114,8 @@ TNB_DEVINL void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes,
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
                  : "memory");
 }
-inline int cp_async_ca_env() {  // experiment switch TNB_CPASYNC_CA=1
-  static const int v = [] { const char* e = getenv("TNB_CPASYNC_CA"); return e ? atoi(e) : 0; }();
+inline int cp_async_ca_env() {  // TNB_CPASYNC_CA=0 restores the L1-bypassing copies (ablation)
+  static const int v = [] { const char* e = getenv("TNB_CPASYNC_CA"); return e ? atoi(e) : 1; }();
   return v;
 }
 // The mbarrier receives one arrival (counted against its initial expected count) once all cp.async operations issued

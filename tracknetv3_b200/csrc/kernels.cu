@@ -44,38 +44,58 @@ int launch_pack_input(const float* x, float* out, int N, int C, int H, int W, in
 // (deterministic), combines in fp64, emits the fused affine (scale, shift) used by every consumer,
 // and updates the running statistics exactly like torch (biased var to normalise, unbiased to track).
 // =============================================================================================
-__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ part, int rows, double count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* running_mean, float* running_var, float momentum, float eps, int training,
-                                   float* scale, float* shift, float* mean_out, float* invstd_out, int C) {
-  __shared__ double s1[32][33], s2[32][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
+// Column sums of a [rows][2][C] partials buffer in fp64 for the kFinCh channels of this block: thread (x = channel,
+// y = row lane of kFinLanes); fixed summation order (deterministic). Few channels per block so that a 64-channel layer
+// still spreads over 8 SMs, many row lanes so that the serial part is short: these kernels sit between every pair of
+// convolutions and are pure latency.
+static constexpr int kFinCh = 8, kFinLanes = 128;
+struct FinalizeSmem { double s1[kFinLanes][kFinCh + 1], s2[kFinLanes][kFinCh + 1]; };
+// returns the two column sums in thread (x, y = 0); other threads get garbage
+TNB_DEVINL void finalize_column_sums(const float* __restrict__ part, int rows, int C, int c, bool active,
+                                     FinalizeSmem& sm, double& out1, double& out2) {
   double a = 0.0, b = 0.0;
-  if (training && c < C) {
-    float fa[4] = {0.f, 0.f, 0.f, 0.f}, fb[4] = {0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    float fa[4], fb[4];
     int r = threadIdx.y;
-    for (; r + 96 < rows; r += 128) {  // 4 independent loads in flight per thread
+    for (; r + 3 * kFinLanes < rows; r += 4 * kFinLanes) {  // 8 independent loads in flight per thread
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        fa[u] = part[((size_t)(r + 32 * u) * 2 + 0) * C + c];
-        fb[u] = part[((size_t)(r + 32 * u) * 2 + 1) * C + c];
+        fa[u] = part[((size_t)(r + kFinLanes * u) * 2 + 0) * C + c];
+        fb[u] = part[((size_t)(r + kFinLanes * u) * 2 + 1) * C + c];
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) { a += (double)fa[u]; b += (double)fb[u]; }
     }
-    for (; r < rows; r += 32) {
+    for (; r < rows; r += kFinLanes) {
       a += (double)part[((size_t)r * 2 + 0) * C + c];
       b += (double)part[((size_t)r * 2 + 1) * C + c];
     }
   }
-  s1[threadIdx.y][threadIdx.x] = a;
-  s2[threadIdx.y][threadIdx.x] = b;
+  sm.s1[threadIdx.y][threadIdx.x] = a;
+  sm.s2[threadIdx.y][threadIdx.x] = b;
   __syncthreads();
+  double sa = 0.0, sb = 0.0;
+  if (threadIdx.y < 16)  // 128 -> 16 lanes
+    for (int i = threadIdx.y; i < kFinLanes; i += 16) { sa += sm.s1[i][threadIdx.x]; sb += sm.s2[i][threadIdx.x]; }
+  __syncthreads();
+  if (threadIdx.y < 16) { sm.s1[threadIdx.y][threadIdx.x] = sa; sm.s2[threadIdx.y][threadIdx.x] = sb; }
+  __syncthreads();
+  out1 = out2 = 0.0;
+  if (threadIdx.y == 0)
+    for (int i = 0; i < 16; ++i) { out1 += sm.s1[i][threadIdx.x]; out2 += sm.s2[i][threadIdx.x]; }
+}
+
+__global__ void __launch_bounds__(kFinCh * kFinLanes) bn_finalize_kernel(const float* __restrict__ part, int rows, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* running_mean, float* running_var, float momentum, float eps, int training,
+                                   float* scale, float* shift, float* mean_out, float* invstd_out, int C) {
+  __shared__ FinalizeSmem sm;
+  const int c = blockIdx.x * kFinCh + threadIdx.x;
+  double sa, sb;
+  finalize_column_sums(part, rows, C, c, training && c < C, sm, sa, sb);
   if (threadIdx.y == 0 && c < C) {
     float mean, invstd;
     if (training) {
-      double sa = 0.0, sb = 0.0;
-      for (int i = 0; i < 32; ++i) { sa += s1[i][threadIdx.x]; sb += s2[i][threadIdx.x]; }
       const double m = sa / count;
       double var = sb / count - m * m;
       if (var < 0.0) var = 0.0;
@@ -98,7 +118,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
 int launch_bn_finalize(const float* part, int rows, double count, const float* gamma, const float* beta,
                        float* running_mean, float* running_var, float momentum, float eps, int training,
                        float* scale, float* shift, float* mean, float* invstd, int C, cudaStream_t st) {
-  bn_finalize_kernel<<<cdiv(C, 32), dim3(32, 32), 0, st>>>(part, rows, count, gamma, beta, running_mean,
+  bn_finalize_kernel<<<cdiv(C, kFinCh), dim3(kFinCh, kFinLanes), 0, st>>>(part, rows, count, gamma, beta, running_mean,
                                                            running_var, momentum, eps, training, scale, shift, mean,
                                                            invstd, C);
   TNB_CHECK_CUDA(cudaGetLastError());
@@ -151,7 +171,7 @@ int launch_predictor_fwd(const SrcDesc& src, int N, int H, int W, const float* w
 
 // backward of sigmoid + 1x1 conv: dl = dy*y*(1-y); dA[p][c] = sum_o dl[o] W[o][c];
 // dW[o][c] = sum_p dl[p][o] a[p][c]; db[o] = sum_p dl[p][o]   (autograd of model.py:71-72)
-__global__ void __launch_bounds__(256) predictor_bwd_kernel(SrcDesc src, int N, int H, int W,
+__global__ void __launch_bounds__(256, 4) predictor_bwd_kernel(SrcDesc src, int N, int H, int W,
                                                             const float* __restrict__ wp, int O,
                                                             const float* __restrict__ dy,
                                                             const float* __restrict__ y, float* __restrict__ dA,
@@ -249,6 +269,8 @@ int launch_predictor_bwd(const SrcDesc& src, int N, int H, int W, const float* w
   TNB_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * O * 64, st));
   TNB_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * O, st));
   ProfScope prof(PROF_PRED, st, N, H, W, 64, O);
+  // 4 resident CTAs per SM (__launch_bounds__(256, 4) caps the registers): every 64-pixel tile is a
+  // load -> barrier -> compute chain, so it is the other CTAs that hide the load latency
   predictor_bwd_kernel<<<min(cdiv(npix, 64), 148 * 4), 256, 0, st>>>(src, N, H, W, wp, O, dy, y, dA, dwp, dbias);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -476,34 +498,13 @@ int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st) {
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
-__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ part, int rows, int C,
+__global__ void __launch_bounds__(kFinCh * kFinLanes) bn_bwd_finalize_kernel(const float* __restrict__ part, int rows, int C,
                                                                float* sums, float* dgamma, float* dbeta) {
-  __shared__ double s1[32][33], s2[32][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  double a = 0.0, b = 0.0;
-  if (c < C) {
-    float fa[4], fb[4];
-    int r = threadIdx.y;
-    for (; r + 96 < rows; r += 128) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        fa[u] = part[((size_t)(r + 32 * u) * 2 + 0) * C + c];
-        fb[u] = part[((size_t)(r + 32 * u) * 2 + 1) * C + c];
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { a += (double)fa[u]; b += (double)fb[u]; }
-    }
-    for (; r < rows; r += 32) {
-      a += (double)part[((size_t)r * 2 + 0) * C + c];
-      b += (double)part[((size_t)r * 2 + 1) * C + c];
-    }
-  }
-  s1[threadIdx.y][threadIdx.x] = a;
-  s2[threadIdx.y][threadIdx.x] = b;
-  __syncthreads();
+  __shared__ FinalizeSmem sm;
+  const int c = blockIdx.x * kFinCh + threadIdx.x;
+  double sa, sb;
+  finalize_column_sums(part, rows, C, c, c < C, sm, sa, sb);
   if (threadIdx.y == 0 && c < C) {
-    double sa = 0.0, sb = 0.0;
-    for (int i = 0; i < 32; ++i) { sa += s1[i][threadIdx.x]; sb += s2[i][threadIdx.x]; }
     sums[c] = (float)sa;
     sums[C + c] = (float)sb;
     dbeta[c] = (float)sa;   // d/dbeta  = sum dy
@@ -512,7 +513,7 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
 }
 int launch_bn_bwd_finalize(const float* part, int rows, int C, float* sums, float* dgamma, float* dbeta,
                            cudaStream_t st) {
-  bn_bwd_finalize_kernel<<<cdiv(C, 32), dim3(32, 32), 0, st>>>(part, rows, C, sums, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<cdiv(C, kFinCh), dim3(kFinCh, kFinLanes), 0, st>>>(part, rows, C, sums, dgamma, dbeta);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
