@@ -211,6 +211,10 @@ int tnb_tracknet_forward(const tnb_tracknet_cfg_t* cfg, const float* x_nchw, voi
 int tnb_tracknet_backward(const tnb_tracknet_cfg_t* cfg, const float* dy_nchw, const float* y_nchw,
                           void* const* params, void* const* grads, void* workspace, size_t workspace_bytes,
                           void* stream);
+/* tnb_tracknet_forward / tnb_tracknet_backward replay their launch sequence from a CUDA graph once the same
+ * argument set (cfg and every pointer) is seen again; per-launch profiling and a caller-side stream capture bypass it.
+ * This switch turns the replay off (0) or on (1, default; env TNB_GRAPHS=0 also disables); returns the old value. */
+int tnb_set_graph_replay(int on);
 /* number of kernels launched by one forward / backward call (for bench.py's gpu_launches) */
 int tnb_tracknet_num_launches(const tnb_tracknet_cfg_t* cfg, int backward);
 

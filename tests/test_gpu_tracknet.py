@@ -195,3 +195,39 @@ def test_backward_is_the_derivative_of_forward():
     scale = sum(f for _, f in errs) / len(errs)
     assert max(abs(e) for e, _ in errs) < 0.08 * scale, errs
     assert abs(sum(e for e, _ in errs)) / len(errs) < 0.03 * scale, errs
+
+
+def test_cuda_graph_replay_equals_eager_launches():
+    """The library replays the forward / backward launch sequence from a CUDA graph from the third identical call on.
+    A replayed step must read the CURRENT contents of its buffers and give what the eager launches give."""
+    from tracknetv3_b200 import _lib
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 12, 32, 64, generator=gen).to(G.DEV)
+    y = (torch.rand(2, 4, 32, 64, generator=gen) > 0.99).float().to(G.DEV)
+    xs = [torch.rand(2, 12, 32, 64, generator=gen).to(G.DEV) for _ in range(5)]
+
+    def run(graphs):
+        prev = lib.tnb_set_graph_replay(1 if graphs else 0)
+        try:
+            m = _model(7, 12, 4).train()
+            xbuf = torch.empty_like(x)
+            out = []
+            for xi in xs:                      # same buffers every step, new contents
+                xbuf.copy_(xi)
+                for p in m.parameters():
+                    p.grad = None
+                yp = m(xbuf)
+                T.WBCELoss(yp, y).backward()
+                out.append((yp.detach().clone(), [p.grad.detach().clone() for p in m.parameters()],
+                            m.state_dict()["down_block_1.conv_1.bn.running_mean"].clone()))
+            return out
+        finally:
+            lib.tnb_set_graph_replay(prev)
+
+    eager, graphed = run(False), run(True)
+    for step, ((y0, g0, r0), (y1, g1, r1)) in enumerate(zip(eager, graphed)):
+        assert torch.equal(y0, y1), step                      # forward is deterministic
+        assert torch.equal(r0, r1), step                      # running statistics advance on every replay
+        for a, b in zip(g0, g1):                              # wgrad accumulates with float atomics: order-dependent
+            assert (a - b).abs().max() <= 1e-5 * a.abs().max() + 1e-12, step

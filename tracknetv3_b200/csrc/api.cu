@@ -16,6 +16,7 @@ int tracknet_forward(const tnb_tracknet_cfg_t& c, const float* x, void* const* p
 int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float* y, void* const* params,
                       void* const* grads, void* ws, size_t ws_bytes, cudaStream_t st);
 int tracknet_num_launches(const tnb_tracknet_cfg_t& c, int backward);
+int set_graph_replay(int on);
 }  // namespace tnb
 
 using namespace tnb;
@@ -143,6 +144,7 @@ int tnb_tracknet_backward(const tnb_tracknet_cfg_t* cfg, const float* dy, const 
                           void* const* grads, void* ws, size_t ws_bytes, void* stream) {
   return tracknet_backward(*cfg, dy, y, params, grads, ws, ws_bytes, ST(stream));
 }
+int tnb_set_graph_replay(int on) { return set_graph_replay(on); }
 int tnb_tracknet_num_launches(const tnb_tracknet_cfg_t* cfg, int backward) {
   return tracknet_num_launches(*cfg, backward);
 }

@@ -16,6 +16,8 @@ cudaEvent_t get_event() {
 }
 }  // namespace
 
+bool prof_enabled() { return g_on; }
+
 ProfScope::ProfScope(int kind, cudaStream_t s, int n, int h, int w, int cin, int cout) : idx(-1), st(s) {
   if (!g_on) return;
   Rec r{get_event(), get_event(), kind, n, h, w, cin, cout};

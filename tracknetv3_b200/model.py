@@ -79,7 +79,13 @@ class _TrackNetFunction(torch.autograd.Function):
         if not ctx.cfg.training:
             raise RuntimeError("tracknet_b200: backward through an eval()-mode TrackNet is not implemented")
         params = list(module.parameters())
-        grads = [torch.empty_like(p) for p in params]
+        # one block for all 53 gradients: a single allocation whose address repeats from step to step, which is what
+        # lets the library replay its captured launch sequence (the pointers are part of the CUDA-graph key)
+        flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=dy.device)
+        grads, off = [], 0
+        for p in params:
+            grads.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
         dy = dy.contiguous()
         _lib.check(lib.tnb_tracknet_backward(C.byref(ctx.cfg), dy.data_ptr(), y.data_ptr(),
                                              _lib.ptr_array(module._state_tensors()), _lib.ptr_array(grads),
