@@ -14,5 +14,5 @@ try:
     for k,v in d["kernel_breakdown"].items(): print("   ",k, round(v["ms_per_step"],3), v["tflops"] and round(v["tflops"],1))
 except Exception as e: print("bench parse failed", e)
 PY
-timeout -k 5 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv python tools/profile_step.py 1 1 > $OUT/ncu_launches.log 2>&1; echo "ncu launches rc=$?" >> $OUT/summary.txt
+TNB_GRAPHS=0 timeout -k 5 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv python tools/profile_step.py 1 1 > $OUT/ncu_launches.log 2>&1; echo "ncu launches rc=$?" >> $OUT/summary.txt
 cat $OUT/summary.txt
