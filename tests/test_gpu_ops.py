@@ -75,6 +75,43 @@ def test_fused_adam_matches_torch_adam():
         assert G.max_abs(mp, rp) < 2e-6
 
 
+
+def test_fused_adam_checkpoint_interchanges_with_torch_adam():
+    """optimizer.state_dict() round trip in both directions (reference train.py:258-259 saves it, :286-301 resumes):
+    two steps with one optimizer, load its state into the other kind, two more steps - same parameters as four steps of
+    torch.optim.Adam."""
+    shapes = [(64, 27, 3, 3), (64,), (8, 64, 1, 1)]
+
+    def grads(step):
+        return [torch.randn(s, generator=torch.Generator().manual_seed(100 * step + i)) * 0.1 for i, s in enumerate(shapes)]
+
+    torch.manual_seed(1)
+    init = [torch.randn(s) for s in shapes]
+    ref_p = [p.clone().requires_grad_(True) for p in init]
+    ref = torch.optim.Adam(ref_p, lr=1e-3)
+    for step in range(4):
+        for p, g in zip(ref_p, grads(step)):
+            p.grad = g
+        ref.step()
+    for first_fused in (True, False):
+        pa = [p.clone().to(G.DEV).requires_grad_(True) for p in init]
+        make = lambda fused, ps: T.FusedAdam(ps, lr=1e-3) if fused else torch.optim.Adam(ps, lr=1e-3)
+        opt = make(first_fused, pa)
+        for step in range(2):
+            for p, g in zip(pa, grads(step)):
+                p.grad = g.to(G.DEV)
+            opt.step()
+        ckpt = opt.state_dict()
+        pb = [p.detach().clone().requires_grad_(True) for p in pa]
+        opt2 = make(not first_fused, pb)
+        opt2.load_state_dict(ckpt)
+        for step in range(2, 4):
+            for p, g in zip(pb, grads(step)):
+                p.grad = g.to(G.DEV)
+            opt2.step()
+        for rp, mp in zip(ref_p, pb):
+            assert G.max_abs(mp, rp) < 2e-6, first_fused
+
 def test_decode_vs_cv2_fixture_and_oracle(golden_dir):
     g = _load(golden_dir, "decode_golden.npz")
     masks = torch.from_numpy(g["masks"]).to(G.DEV)

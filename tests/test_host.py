@@ -82,6 +82,16 @@ def _worker(rank, world, port, q):
         p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
     GradBucket(net).allreduce()
     g = torch.cat([p.grad.flatten() for p in net.parameters()])
+    # gradients handed out as slices of one allocation (what TrackNet's backward does): reduced in place, no copies
+    flat = torch.cat([torch.full((p.numel(),), float(rank + 1) * (i + 1)) for i, p in enumerate(net.parameters())])
+    off = 0
+    for p in net.parameters():
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    bucket = GradBucket(net)
+    assert bucket._shared_flat([p.grad for p in net.parameters()]) is not None
+    bucket.allreduce()
+    assert torch.equal(flat, g) and torch.equal(torch.cat([p.grad.flatten() for p in net.parameters()]), g)
     q.put((rank, w0.numpy(), g.numpy()))
     dist.destroy_process_group()
 

@@ -11,7 +11,12 @@ class _Entry(C.Structure):
 
 
 class FusedAdam(torch.optim.Optimizer):
-    """Same update rule and defaults as ``torch.optim.Adam`` (amsgrad=False), one launch per step."""
+    """Same update rule and defaults as ``torch.optim.Adam`` (amsgrad=False), one launch per step.
+
+    The per-parameter state uses torch's keys (``step``, ``exp_avg``, ``exp_avg_sq``), so ``state_dict()`` /
+    ``load_state_dict()`` interchange with ``torch.optim.Adam`` checkpoints (reference train.py:258-259, 286-301):
+    ``step`` may arrive as a python int (torch 1.10, the reference's pin) or as a tensor (current torch).
+    """
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
@@ -36,8 +41,9 @@ class FusedAdam(torch.optim.Optimizer):
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p)
                     st["exp_avg_sq"] = torch.zeros_like(p)
-                st["step"] += 1
-            key = (gi,) + tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
+                st["step"] = st["step"] + 1
+            key = (gi,) + tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
+                                 self.state[p]["exp_avg_sq"].data_ptr()) for p in ps)
             if key != self._table_key:
                 arr = (_Entry * len(ps))()
                 for i, p in enumerate(ps):
@@ -50,5 +56,5 @@ class FusedAdam(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             _lib.check(lib.tnb_adam_multi(self._table.data_ptr(), len(ps), max(p.numel() for p in ps),
                                           group["lr"], b1, b2, group["eps"], group["weight_decay"],
-                                          self.state[ps[0]]["step"], _lib.stream_ptr()))
+                                          int(self.state[ps[0]]["step"]), _lib.stream_ptr()))
         return loss

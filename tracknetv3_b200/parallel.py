@@ -22,10 +22,30 @@ class GradBucket:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
 
+    @staticmethod
+    def _shared_flat(grads):
+        """The gradients as ONE tensor without copying, if they already are back-to-back slices of one allocation in
+        parameter order (TrackNet's backward hands them out that way), else None."""
+        if not grads or any(not g.is_contiguous() for g in grads):
+            return None
+        st = grads[0].untyped_storage()
+        off = grads[0].storage_offset()
+        first = off
+        for g in grads:
+            if g.dtype != grads[0].dtype or g.untyped_storage().data_ptr() != st.data_ptr() or g.storage_offset() != off:
+                return None
+            off += g.numel()
+        return torch.empty(0, dtype=grads[0].dtype, device=grads[0].device).set_(st, first, (off - first,))
+
     def allreduce(self):
         if self.world == 1:
             return
         grads = [p.grad for p in self.params if p.grad is not None]
+        flat = self._shared_flat(grads)
+        if flat is not None:  # in place: no flatten / copy-back passes around the collective
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.div_(self.world)
+            return
         flat = _flatten_dense_tensors(grads)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
         flat.div_(self.world)
