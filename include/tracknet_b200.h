@@ -190,6 +190,12 @@ int tnb_inpaintnet_fwd(const float* coords, const float* mask, const void* const
 int tnb_inpaintnet_bwd(const float* coords, const float* mask, const void* const* params, const float* dout,
                        void* const* grads, int n, int l, float* dcoords, void* stream);
 
+/* Per-map statistics of the evaluation bookkeeping (test.py:159-169): conf[m] = max of y_pred map m inside
+ * boxes[m] = (x, y, w, h) (0 for an empty box); true_any[m] = 1 iff map m of y_true has a value > 0 (y_true and
+ * true_any may be NULL). boxes: int32 as written by tnb_heatmap_decode. */
+int tnb_eval_stats(const float* y_pred, const float* y_true, const int* boxes_xywh, int nmaps, int h, int w,
+                   float* conf, int* true_any, void* stream);
+
 /* Temporal ensemble of sliding-window predictions (predict.py:163-209 heatmaps, :245-301 coordinates). state: the
  * previous seq_len-1 samples' predictions [(seq_len-1)][seq_len][frame_elems] (zeros before the first batch); pred:
  * this batch [batch][seq_len][frame_elems]; weight_host: seq_len floats in HOST memory (test.py:25-50). sample_count:

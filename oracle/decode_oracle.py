@@ -7,6 +7,8 @@ box: cv2.findContours(RETR_EXTERNAL) + boundingRect + "largest w*h, first wins" 
 Pinned against real OpenCV by tests/test_oracle.py (hypothesis masks, when cv2 is importable) and by the
 cv2-generated fixtures in tests/golden/decode_golden.npz.
 """
+import math
+
 import numpy as np
 
 
@@ -70,3 +72,76 @@ def decode_batch(y_pred, threshold=0.5):
     for i, m in enumerate(maps):
         out[i] = predict_location(to_img(m > threshold))
     return out.reshape(lead + (4,))
+
+
+PRED_TYPES = ['TP', 'TN', 'FP1', 'FP2', 'FN']           # reference test.py:20-21
+PRED_TYPES_MAP = {t: i for i, t in enumerate(PRED_TYPES)}
+
+
+def classify(pred_any, true_any, cx_pred, cy_pred, cx_true, cy_true, tolerance):
+    """Outcome of one frame (reference test.py:135-157 / :171-192): TN / FP2 / FN by presence, else FP1 when the
+    predicted centre is farther than `tolerance` from the true one, else TP."""
+    if not pred_any and not true_any:
+        return PRED_TYPES_MAP['TN']
+    if pred_any and not true_any:
+        return PRED_TYPES_MAP['FP2']
+    if not pred_any and true_any:
+        return PRED_TYPES_MAP['FN']
+    dist = math.sqrt(pow(cx_pred - cx_true, 2) + pow(cy_pred - cy_true, 2))
+    return PRED_TYPES_MAP['FP1'] if dist > tolerance else PRED_TYPES_MAP['TP']
+
+
+def evaluate(indices, y_true=None, y_pred=None, c_true=None, c_pred=None, tolerance=4., img_scaler=(1, 1),
+             output_bbox=False, output_gt=False, height=288, width=512):
+    """Per-frame evaluation (reference test.py:81-221) on numpy arrays: heatmap mode decodes prediction (> 0.5) and
+    ground truth (to_img != 0) with predict_location, confidence = max of the heatmap inside the predicted box;
+    coordinate mode scales normalised coordinates by (width, height). Frames repeat at the end of a padded sample:
+    the first repeated index ends that sample (:130-133, :211-212)."""
+    d = {'Frame': [], 'X': [], 'Y': [], 'Visibility': [], 'Type': [], 'BBox': [], 'Confidence': [], 'X_GT': [],
+         'Y_GT': [], 'Visibility_GT': []}
+    indices = np.asarray(indices).tolist()
+    heat = y_true is not None and y_pred is not None
+    if heat:
+        y_true, y_pred = np.asarray(y_true), np.asarray(y_pred)
+        h_pred = y_pred > 0.5
+    else:
+        c_true = np.asarray(c_true, dtype=np.float32) * np.array([width, height], dtype=np.float32)
+        c_pred = np.asarray(c_pred, dtype=np.float32) * np.array([width, height], dtype=np.float32)
+    for n in range(len(indices)):
+        prev = [-1, -1]
+        for f in range(len(indices[n])):
+            d_i = indices[n][f]
+            if d_i == prev:
+                break
+            if heat:
+                bt = predict_location(to_img(y_true[n][f]))
+                cx_true, cy_true = int(bt[0] + bt[2] / 2), int(bt[1] + bt[3] / 2)
+                bp = predict_location(to_img(h_pred[n][f]))
+                cx_pred, cy_pred = int(bp[0] + bp[2] / 2), int(bp[1] + bp[3] / 2)
+                conf = float(np.amax(y_pred[n][f][bp[1]:bp[1] + bp[3], bp[0]:bp[0] + bp[2]])) if max(bp) > 0 else 0.
+                typ = classify(np.amax(h_pred[n][f]) > 0, np.amax(y_true[n][f]) > 0, cx_pred, cy_pred, cx_true, cy_true,
+                               tolerance)
+            else:
+                c_t, c_p = c_true[n][f], c_pred[n][f]
+                cx_true, cy_true = int(c_t[0]), int(c_t[1])
+                cx_pred, cy_pred = int(c_p[0]), int(c_p[1])
+                typ = classify(np.amax(c_p) > 0, np.amax(c_t) > 0, cx_pred, cy_pred, cx_true, cy_true, tolerance)
+            d['Type'].append(typ)
+            d['Frame'].append(int(d_i[1]))
+            d['X'].append(int(cx_pred * img_scaler[0]))
+            d['Y'].append(int(cy_pred * img_scaler[1]))
+            d['Visibility'].append(0 if cx_pred == 0 and cy_pred == 0 else 1)
+            if output_bbox:
+                d['BBox'].append([int(bp[0] * img_scaler[0]), int(bp[1] * img_scaler[1]), int(bp[2] * img_scaler[0]),
+                                  int(bp[3] * img_scaler[1])])
+                d['Confidence'].append(conf)
+            if output_gt:
+                d['X_GT'].append(int(cx_true * img_scaler[0]))
+                d['Y_GT'].append(int(cy_true * img_scaler[1]))
+                d['Visibility_GT'].append(0 if cx_true == 0 and cy_true == 0 else 1)
+            prev = d_i
+    if not output_bbox:
+        del d['BBox'], d['Confidence']
+    if not output_gt:
+        del d['X_GT'], d['Y_GT'], d['Visibility_GT']
+    return d

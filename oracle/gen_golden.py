@@ -164,6 +164,64 @@ def gen_temporal_ensemble():
     np.savez_compressed(f"{OUT}/temporal_ensemble.npz", **out)
 
 
+def gen_evaluate():
+    """EXECUTE the reference's `evaluate` (test.py:81-221) - lifted out with ast, together with the helpers it calls
+    (`predict_location`, utils.general `to_img` / `to_img_format`) - on small synthetic heatmap and coordinate batches
+    that hit every outcome: TP, TN, FP1 (too far), FP2 (ball predicted, none there), FN, padded duplicate frames."""
+    import cv2
+    env = {"np": np, "cv2": cv2, "torch": torch, "math": math, "HEIGHT": 288, "WIDTH": 512}
+    extract_functions(f"{REF}/utils/general.py", {"to_img", "to_img_format"}, env)
+    extract_functions(f"{REF}/test.py", {"predict_location", "evaluate"}, env)
+    env["pred_types"] = ['TP', 'TN', 'FP1', 'FP2', 'FN']
+    env["pred_types_map"] = {t: i for i, t in enumerate(env["pred_types"])}
+    H, W, N, L = 36, 64, 3, 4
+    rng = np.random.default_rng(21)
+    y_true = np.zeros((N, L, H, W), np.float32)
+    y_pred = rng.random((N, L, H, W)).astype(np.float32) * 0.4          # background below the 0.5 threshold
+
+    def disc(a, cx, cy, r, v):
+        yy, xx = np.ogrid[:H, :W]
+        a[(yy - cy) ** 2 + (xx - cx) ** 2 <= r * r] = v
+    centres = [(10, 8), (30, 20), (50, 12), (20, 30)]
+    for n in range(N):
+        for f in range(L):
+            k = (n * L + f) % 6
+            cx, cy = centres[(n + f) % 4]
+            if k in (0, 1, 2, 4):
+                disc(y_true[n, f], cx, cy, 2, 1.0)
+            if k in (0, 1):
+                disc(y_pred[n, f], cx + (1 if k else 0), cy, 2, 0.9)     # TP (0 or 1 px off)
+            elif k == 2:
+                disc(y_pred[n, f], (cx + 20) % W, cy, 2, 0.8)            # FP1: far from the truth
+            elif k == 3:
+                disc(y_pred[n, f], cx, cy, 3, 0.7)                       # FP2: nothing there
+            # k == 4: FN, k == 5: TN
+    y_pred[0, 1][2:4, 40:43] = 0.95                                      # a second, smaller blob: largest bbox wins
+    idx = np.zeros((N, L, 2), np.int64)
+    for n in range(N):
+        for f in range(L):
+            idx[n, f] = (0, min(n * L + f, N * L - 3))                   # last sample repeats frames: padded -> break
+    out = {"y_true": y_true, "y_pred": y_pred, "indices": idx}
+    for name, kw in (("plain", {}), ("bbox_gt", {"output_bbox": True, "output_gt": True}),
+                     ("scaled", {"img_scaler": (2.5, 2.5), "tolerance": 1.0, "output_gt": True})):
+        d = env["evaluate"](torch.from_numpy(idx), y_true=torch.from_numpy(y_true.copy()),
+                            y_pred=torch.from_numpy(y_pred.copy()), **kw)
+        for k, v in d.items():
+            out[f"hm_{name}/{k}"] = np.asarray(v, dtype=np.float64)
+    c_true = rng.random((N, L, 2)).astype(np.float32)
+    c_pred = c_true + rng.normal(0, 0.004, (N, L, 2)).astype(np.float32)
+    c_true[0, 0] = 0; c_pred[0, 0] = 0          # TN
+    c_true[0, 1] = 0                            # FP2
+    c_pred[0, 2] = 0                            # FN
+    c_pred[1, 0] += 0.2                         # FP1
+    out["c_true"], out["c_pred"] = c_true.copy(), c_pred.copy()
+    d = env["evaluate"](torch.from_numpy(idx), c_true=torch.from_numpy(c_true.copy()),
+                        c_pred=torch.from_numpy(c_pred.copy()), output_gt=True)
+    for k, v in d.items():
+        out[f"co/{k}"] = np.asarray(v, dtype=np.float64)
+    np.savez_compressed(f"{OUT}/evaluate.npz", **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -171,6 +229,10 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "inpaint_train":  # regenerate only this fixture
         gen_inpaint_train(refmodel)
         print("inpaintnet_train.npz written")
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "evaluate":
+        gen_evaluate()
+        print("evaluate.npz written")
         return
     if len(sys.argv) > 1 and sys.argv[1] == "temporal_ensemble":
         gen_temporal_ensemble()
@@ -275,6 +337,7 @@ def main():
 
     gen_inpaint_train(refmodel)
     gen_temporal_ensemble()
+    gen_evaluate()
 
     # ---- small host-side pieces: ensemble weights, mixup ----
     ew = {f"weight_{L}": env["get_ensemble_weight"](L, "weight").numpy() for L in (1, 4, 7, 8)}

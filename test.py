@@ -2,3 +2,110 @@
 The evaluation drivers of the reference (dataset loops, COCO export) are out of scope."""
 from tracknetv3_b200.decode import predict_location, decode_heatmaps  # noqa: F401
 from tracknetv3_b200.ensemble import get_ensemble_weight, TemporalEnsemble  # noqa: F401
+
+import math  # noqa: E402
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from tracknetv3_b200 import _lib  # noqa: E402
+from utils.general import HEIGHT, WIDTH  # noqa: E402
+
+pred_types = ['TP', 'TN', 'FP1', 'FP2', 'FN']
+pred_types_map = {pred_type: i for i, pred_type in enumerate(pred_types)}
+
+
+def _frame_stats(y_true, y_pred):
+    """Everything `evaluate` needs per frame, computed on the GPU: predicted / true bounding boxes (the OpenCV-rule
+    decode), confidence, ground-truth presence. 44 bytes per frame come back instead of two full heatmaps."""
+    lib = _lib.load()
+    y_pred = y_pred.cuda().contiguous().float()
+    y_true = y_true.cuda().contiguous().float()
+    boxes_pred = decode_heatmaps(y_pred, threshold=0.5)                       # predict_location(to_img(y_pred > 0.5))
+    boxes_true = decode_heatmaps((y_true * 255).to(torch.uint8))              # predict_location(to_img(y_true))
+    nmaps = y_pred.numel() // (y_pred.shape[-2] * y_pred.shape[-1])
+    conf = torch.empty(nmaps, dtype=torch.float32, device=y_pred.device)
+    true_any = torch.empty(nmaps, dtype=torch.int32, device=y_pred.device)
+    _lib.check(lib.tnb_eval_stats(y_pred.data_ptr(), y_true.data_ptr(), boxes_pred.data_ptr(), nmaps, y_pred.shape[-2],
+                                  y_pred.shape[-1], conf.data_ptr(), true_any.data_ptr(), _lib.stream_ptr()))
+    lead = y_pred.shape[:-2]
+    return (boxes_pred.cpu().numpy(), boxes_true.cpu().numpy(), conf.reshape(lead).cpu().numpy(),
+            true_any.reshape(lead).cpu().numpy())
+
+
+def evaluate(indices, y_true=None, y_pred=None, c_true=None, c_pred=None, tolerance=4., img_scaler=(1, 1),
+             output_bbox=False, output_gt=False):
+    """ Predict and output the result of each frame (drop-in for reference test.py:81-221; same arguments and the
+        same dictionary). Heatmap inputs are decoded on the GPU; the outcome logic (TP / TN / FP1 / FP2 / FN) runs on
+        the few integers per frame that come back. Unlike the reference, the caller's tensors are not modified.
+    """
+    pred_dict = {'Frame': [], 'X': [], 'Y': [], 'Visibility': [], 'Type': [], 'BBox': [], 'Confidence': [],
+                 'X_GT': [], 'Y_GT': [], 'Visibility_GT': []}
+    batch_size, seq_len = indices.shape[0], indices.shape[1]
+    indices = indices.detach().cpu().numpy().tolist() if torch.is_tensor(indices) else np.asarray(indices).tolist()
+
+    heat = y_true is not None and y_pred is not None
+    if heat:
+        assert c_true is None and c_pred is None, 'Invalid input'
+        y_true = y_true if torch.is_tensor(y_true) else torch.as_tensor(np.asarray(y_true))
+        y_pred = y_pred if torch.is_tensor(y_pred) else torch.as_tensor(np.asarray(y_pred))
+        boxes_pred, boxes_true, conf_all, true_any = _frame_stats(y_true, y_pred)
+    elif c_true is not None and c_pred is not None:
+        assert y_true is None and y_pred is None, 'Invalid input'
+        assert output_bbox == False, 'Coordinate prediction cannot output detection'  # noqa: E712
+        scale = np.array([WIDTH, HEIGHT], dtype=np.float32)
+        c_true = (c_true.detach().cpu().numpy() if torch.is_tensor(c_true) else np.asarray(c_true)).astype(np.float32) * scale
+        c_pred = (c_pred.detach().cpu().numpy() if torch.is_tensor(c_pred) else np.asarray(c_pred)).astype(np.float32) * scale
+
+    for n in range(batch_size):
+        prev_d_i = [-1, -1]  # for ignoring the same frame in sequence
+        for f in range(seq_len):
+            d_i = indices[n][f]
+            if d_i == prev_d_i:
+                break
+            if heat:
+                bbox_true, bbox_pred = boxes_true[n][f], boxes_pred[n][f]
+                cx_true, cy_true = int(bbox_true[0] + bbox_true[2] / 2), int(bbox_true[1] + bbox_true[3] / 2)
+                cx_pred, cy_pred = int(bbox_pred[0] + bbox_pred[2] / 2), int(bbox_pred[1] + bbox_pred[3] / 2)
+                conf = float(conf_all[n][f]) if np.amax(bbox_pred) > 0 else 0.
+                p_any, t_any = bool(np.amax(bbox_pred) > 0), bool(true_any[n][f])
+            elif c_true is not None and c_pred is not None:
+                c_t, c_p = c_true[n][f], c_pred[n][f]
+                cx_true, cy_true = int(c_t[0]), int(c_t[1])
+                cx_pred, cy_pred = int(c_p[0]), int(c_p[1])
+                p_any, t_any = bool(np.amax(c_p) > 0), bool(np.amax(c_t) > 0)
+            else:
+                raise ValueError('Invalid input')
+            vis_pred = 0 if cx_pred == 0 and cy_pred == 0 else 1
+            if not p_any and not t_any:
+                pred_dict['Type'].append(pred_types_map['TN'])
+            elif p_any and not t_any:
+                pred_dict['Type'].append(pred_types_map['FP2'])
+            elif not p_any and t_any:
+                pred_dict['Type'].append(pred_types_map['FN'])
+            else:
+                dist = math.sqrt(pow(cx_pred - cx_true, 2) + pow(cy_pred - cy_true, 2))
+                pred_dict['Type'].append(pred_types_map['FP1'] if dist > tolerance else pred_types_map['TP'])
+            pred_dict['Frame'].append(int(d_i[1]))
+            pred_dict['X'].append(int(cx_pred * img_scaler[0]))
+            pred_dict['Y'].append(int(cy_pred * img_scaler[1]))
+            pred_dict['Visibility'].append(vis_pred)
+            if output_bbox:
+                pred_dict['BBox'].append([int(bbox_pred[0] * img_scaler[0]), int(bbox_pred[1] * img_scaler[1]),
+                                          int(bbox_pred[2] * img_scaler[0]), int(bbox_pred[3] * img_scaler[1])])
+                pred_dict['Confidence'].append(float(conf))
+            if output_gt:
+                vis_gt = 0 if cx_true == 0 and cy_true == 0 else 1
+                pred_dict['X_GT'].append(int(cx_true * img_scaler[0]))
+                pred_dict['Y_GT'].append(int(cy_true * img_scaler[1]))
+                pred_dict['Visibility_GT'].append(vis_gt)
+            prev_d_i = d_i
+
+    if not output_bbox:
+        del pred_dict['BBox']
+        del pred_dict['Confidence']
+    if not output_gt:
+        del pred_dict['X_GT']
+        del pred_dict['Y_GT']
+        del pred_dict['Visibility_GT']
+    return pred_dict

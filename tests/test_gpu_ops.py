@@ -410,3 +410,28 @@ def test_temporal_ensemble_full_size_and_predict_ensemble():
             want["Visibility"].append(0 if cx == 0 and cy == 0 else 1)
     assert got == want
     assert len(got["Frame"]) == num_sample + L - 1 and sum(got["Visibility"]) > 30
+
+
+def test_evaluate_on_gpu_vs_reference_fixture(golden_dir):
+    """test.evaluate (GPU decode + eval_stats kernel) vs the reference's evaluate run by oracle/gen_golden.py: all
+    outcome types, bbox / confidence / ground-truth outputs, scaling; plus a full-size batch against the oracle."""
+    import test as TT
+    g = _load(golden_dir, "evaluate.npz")
+    cases = {"hm_plain": {}, "hm_bbox_gt": {"output_bbox": True, "output_gt": True},
+             "hm_scaled": {"img_scaler": (2.5, 2.5), "tolerance": 1.0, "output_gt": True}}
+    for name, kw in cases.items():
+        d = TT.evaluate(torch.from_numpy(g["indices"]), y_true=torch.from_numpy(g["y_true"]).to(G.DEV),
+                        y_pred=torch.from_numpy(g["y_pred"]).to(G.DEV), **kw)
+        keys = sorted(k.split("/")[1] for k in g.files if k.startswith(name + "/"))
+        assert sorted(d.keys()) == keys
+        for k in keys:
+            assert np.array_equal(np.asarray(d[k], dtype=np.float64), g[f"{name}/{k}"]), (name, k)
+    # 288x512, 2 x 8 frames: blobs, empties, a prediction without ground truth
+    xb, yb = __import__("bench").synthetic_batch(2, 5)
+    gen = torch.Generator().manual_seed(6)
+    yp = yb * (0.6 + 0.4 * torch.rand(yb.shape, generator=gen)) + 0.3 * torch.rand(yb.shape, generator=gen)
+    yp[0, 0] = 0.1; yp[1, 7, 100:104, 200:205] = 0.97
+    idx = torch.stack([torch.stack([torch.zeros(8), torch.arange(8 * s, 8 * s + 8).float()], 1) for s in range(2)])
+    got = TT.evaluate(idx, y_true=yb.to(G.DEV), y_pred=yp.to(G.DEV), output_bbox=True, output_gt=True)
+    want = D.evaluate(idx.numpy(), y_true=yb.numpy(), y_pred=yp.numpy(), output_bbox=True, output_gt=True)
+    assert got == want

@@ -173,3 +173,22 @@ def test_temporal_ensemble_matches_reference_loops(golden_dir):
             th = (out[:, 0] < O.COOR_TH) & (out[:, 1] < O.COOR_TH)
             out[th] = 0.0
         assert torch.equal(out, ref), key
+
+
+def test_evaluate_matches_reference(golden_dir):
+    """oracle evaluate() vs the reference's own evaluate executed by oracle/gen_golden.py (all five outcome types,
+    padded duplicate frames, bbox / confidence / ground-truth outputs, image scaling)."""
+    from oracle import decode_oracle as D
+    g = _load(golden_dir, "evaluate.npz")
+    cases = {"hm_plain": {}, "hm_bbox_gt": {"output_bbox": True, "output_gt": True},
+             "hm_scaled": {"img_scaler": (2.5, 2.5), "tolerance": 1.0, "output_gt": True}}
+    for name, kw in cases.items():
+        d = D.evaluate(g["indices"], y_true=g["y_true"], y_pred=g["y_pred"], **kw)
+        keys = sorted(k.split("/")[1] for k in g.files if k.startswith(name + "/"))
+        assert sorted(d.keys()) == keys
+        for k in keys:
+            assert np.array_equal(np.asarray(d[k], dtype=np.float64), g[f"{name}/{k}"]), (name, k)
+    d = D.evaluate(g["indices"], c_true=g["c_true"], c_pred=g["c_pred"], output_gt=True)
+    for k in d:
+        assert np.array_equal(np.asarray(d[k], dtype=np.float64), g[f"co/{k}"]), k
+    assert set(g["hm_plain/Type"].tolist()) == {0.0, 1.0, 2.0, 3.0, 4.0}

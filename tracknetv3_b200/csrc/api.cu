@@ -129,6 +129,10 @@ int tnb_inpaintnet_bwd(const float* coords, const float* mask, const void* const
   return launch_inpaint_bwd(coords, mask, p, dout, g, n, l, dcoords, ST(stream));
 }
 
+int tnb_eval_stats(const float* y_pred, const float* y_true, const int* boxes_xywh, int nmaps, int h, int w,
+                   float* conf, int* true_any, void* stream) {
+  return launch_eval_stats(y_pred, y_true, boxes_xywh, nmaps, h, w, conf, true_any, ST(stream));
+}
 int tnb_temporal_ensemble(const float* state, const float* pred, float* out, const float* weight_host, int seq_len,
                           long long frame_elems, int batch, int sample_count, int tail_base, int n_tail, void* stream) {
   return launch_temporal_ensemble(state, pred, out, weight_host, seq_len, frame_elems, batch, sample_count, tail_base,

@@ -1095,4 +1095,41 @@ int launch_temporal_ensemble(const float* state, const float* pred, float* out, 
   return 0;
 }
 
+
+// =============================================================================================
+// Per-map statistics for the evaluation bookkeeping (reference test.py:159-169): the detection confidence = maximum
+// of the heatmap inside the predicted bounding box (0 when the box is empty), and whether the ground-truth map has
+// any non-zero value (np.amax(y_t) > 0). One CTA per map; replaces a D2H copy of both full heatmaps.
+// =============================================================================================
+__global__ void __launch_bounds__(256) eval_stats_kernel(const float* __restrict__ y_pred, const float* __restrict__ y_true,
+                                                         const int* __restrict__ boxes, int H, int W,
+                                                         float* __restrict__ conf, int* __restrict__ true_any) {
+  const int m = blockIdx.x;
+  const int bx = boxes[m * 4 + 0], by = boxes[m * 4 + 1], bw = boxes[m * 4 + 2], bh = boxes[m * 4 + 3];
+  const float* yp = y_pred + (size_t)m * H * W;
+  float best = -INFINITY;
+  for (int i = threadIdx.x; i < bw * bh; i += blockDim.x) best = fmaxf(best, yp[(size_t)(by + i / bw) * W + bx + i % bw]);
+  float tmax = -INFINITY;
+  if (y_true != nullptr) {
+    const float* yt = y_true + (size_t)m * H * W;
+    for (int i = threadIdx.x; i < H * W; i += blockDim.x) tmax = fmaxf(tmax, yt[i]);
+  }
+  __shared__ float s1[8], s2[8];
+  best = warp_max(best); tmax = warp_max(tmax);
+  if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = best; s2[threadIdx.x >> 5] = tmax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) { best = fmaxf(best, s1[i]); tmax = fmaxf(tmax, s2[i]); }
+    conf[m] = (bw > 0 && bh > 0) ? fmaxf(best, s1[0]) : 0.f;
+    if (true_any != nullptr) true_any[m] = fmaxf(tmax, s2[0]) > 0.f ? 1 : 0;
+  }
+}
+int launch_eval_stats(const float* y_pred, const float* y_true, const int* boxes, int nmaps, int H, int W, float* conf,
+                      int* true_any, cudaStream_t st) {
+  if (nmaps == 0) return 0;
+  eval_stats_kernel<<<nmaps, 256, 0, st>>>(y_pred, y_true, boxes, H, W, conf, true_any);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace tnb

@@ -43,6 +43,8 @@ int launch_decode(const void* maps, int is_u8, float thresh, int nmaps, int H, i
 struct InpaintParams { const float* w[9]; const float* b[9]; };
 int launch_inpaint_fwd(const float* coords, const float* mask, const InpaintParams& p, int N, int L, float* out,
                        cudaStream_t st);
+int launch_eval_stats(const float* y_pred, const float* y_true, const int* boxes, int nmaps, int H, int W, float* conf,
+                      int* true_any, cudaStream_t st);
 int launch_temporal_ensemble(const float* state, const float* pred, float* out, const float* weight_host, int L,
                              long long E, int B, int count0, int tail_base, int n_tail, cudaStream_t st);
 struct InpaintGrads { float* w[9]; float* b[9]; };
