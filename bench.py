@@ -308,6 +308,8 @@ def main():
         cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": "bs=1 of the bs=10 workload, 3 timed + 1 warm-up train steps, torch CPU fp32 (oracle port)"}
 
+    gs = (C.c_longlong * 4)()
+    lib.tnb_graph_stats(gs)
     nbytes_in = x_pin.numel() * 4 + y_pin.numel() * 4
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -322,7 +324,9 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "roofline": roofline, "kernel_breakdown": breakdown, "cpu_baseline": cpu}
+            "gpu_launches": launches,
+            "cuda_graphs": {"captured": gs[0], "replayed_calls": gs[1], "stream_launched_calls": gs[2], "capture_failures": gs[3]},
+            "roofline": roofline, "kernel_breakdown": breakdown, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -221,6 +221,8 @@ int tnb_tracknet_backward(const tnb_tracknet_cfg_t* cfg, const float* dy_nchw, c
  * argument set (cfg and every pointer) is seen again; per-launch profiling and a caller-side stream capture bypass it.
  * This switch turns the replay off (0) or on (1, default; env TNB_GRAPHS=0 also disables); returns the old value. */
 int tnb_set_graph_replay(int on);
+/* out4 = {graphs captured, graph replays, eager (stream-launched) calls while replay was allowed, capture failures} */
+int tnb_graph_stats(long long* out4);
 /* number of kernels launched by one forward / backward call (for bench.py's gpu_launches) */
 int tnb_tracknet_num_launches(const tnb_tracknet_cfg_t* cfg, int backward);
 

@@ -83,6 +83,7 @@ SIGNATURES = {
     "tnb_tracknet_forward": (i32, [C.POINTER(TrackNetCfg), vp, C.POINTER(vp), vp, vp, sz, vp]),
     "tnb_tracknet_backward": (i32, [C.POINTER(TrackNetCfg), vp, vp, C.POINTER(vp), C.POINTER(vp), vp, sz, vp]),
     "tnb_set_graph_replay": (i32, [i32]),
+    "tnb_graph_stats": (i32, [C.POINTER(C.c_longlong)]),
     "tnb_tracknet_num_launches": (i32, [C.POINTER(TrackNetCfg), i32]),
     "tnb_profile_enable": (i32, [i32]),
     "tnb_profile_collect": (i32, [i32, vp, vp]),

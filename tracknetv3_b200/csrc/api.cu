@@ -17,6 +17,7 @@ int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float*
                       void* const* grads, void* ws, size_t ws_bytes, cudaStream_t st);
 int tracknet_num_launches(const tnb_tracknet_cfg_t& c, int backward);
 int set_graph_replay(int on);
+void graph_stats(long long* out4);
 }  // namespace tnb
 
 using namespace tnb;
@@ -149,6 +150,7 @@ int tnb_tracknet_backward(const tnb_tracknet_cfg_t* cfg, const float* dy, const 
   return tracknet_backward(*cfg, dy, y, params, grads, ws, ws_bytes, ST(stream));
 }
 int tnb_set_graph_replay(int on) { return set_graph_replay(on); }
+int tnb_graph_stats(long long* out4) { graph_stats(out4); return 0; }
 int tnb_tracknet_num_launches(const tnb_tracknet_cfg_t* cfg, int backward) {
   return tracknet_num_launches(*cfg, backward);
 }

@@ -352,6 +352,9 @@ struct GraphCache {
   std::vector<uint64_t> seen;        // keys that ran eagerly once (ring)
   uint64_t clock = 0;
   int failures = 0;                  // capture failures: after a few, stop trying
+  long long captures = 0, replays = 0, eager = 0;
+  cudaStream_t side = nullptr;       // capture stream (the caller's stream may be the legacy default stream, which
+                                     // cannot be captured); the instantiated graph is launched into the caller's stream
 };
 constexpr int kMaxGraphs = 8, kMaxSeen = 32;
 GraphCache g_graphs;
@@ -365,15 +368,20 @@ uint64_t fnv(uint64_t h, const void* data, size_t n) {
 }
 template <typename F>
 int run_maybe_graphed(uint64_t key, cudaStream_t st, F&& enqueue) {
-  if (!graphs_enabled()) return enqueue();
+  if (!graphs_enabled()) return enqueue(st);
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return enqueue();  // caller captures
+  if (st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread &&
+      (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)) {
+    cudaGetLastError();
+    return enqueue(st);  // the caller is capturing this stream itself
+  }
   std::lock_guard<std::mutex> lock(g_graphs.mu);
   GraphCache& G = g_graphs;
   ++G.clock;
   for (auto& e : G.entries)
     if (e.key == key) {
       e.stamp = G.clock;
+      ++G.replays;
       TNB_CHECK_CUDA(cudaGraphLaunch(e.exec, st));
       return 0;
     }
@@ -381,27 +389,35 @@ int run_maybe_graphed(uint64_t key, cudaStream_t st, F&& enqueue) {
   for (uint64_t k : G.seen) second |= (k == key);
   if (!second) {
     if ((int)G.seen.size() < kMaxSeen) G.seen.push_back(key); else G.seen[G.clock % kMaxSeen] = key;
-    return enqueue();
+    ++G.eager;
+    return enqueue(st);
   }
-  // second sighting: capture, instantiate, launch
-  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-    cudaGetLastError(); ++G.failures;
-    return enqueue();
+  // second sighting: capture on the side stream, instantiate, launch into the caller's stream
+  if (G.side == nullptr && cudaStreamCreateWithFlags(&G.side, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError(); ++G.failures; ++G.eager;
+    return enqueue(st);
   }
-  const int rc = enqueue();
+  if (cudaStreamBeginCapture(G.side, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError(); ++G.failures; ++G.eager;
+    return enqueue(st);
+  }
+  const int rc = enqueue(G.side);
   cudaGraph_t graph = nullptr;
-  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  const cudaError_t ce = cudaStreamEndCapture(G.side, &graph);
   if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
     cudaGetLastError(); ++G.failures;
     if (graph) cudaGraphDestroy(graph);
-    return rc != 0 ? rc : enqueue();  // nothing was executed during the failed capture
+    if (rc != 0) return rc;
+    ++G.eager;
+    return enqueue(st);  // nothing was executed during the failed capture
   }
   cudaGraphExec_t exec = nullptr;
   if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
-    cudaGetLastError(); ++G.failures;
+    cudaGetLastError(); ++G.failures; ++G.eager;
     cudaGraphDestroy(graph);
-    return enqueue();
+    return enqueue(st);
   }
+  ++G.captures;
   cudaGraphDestroy(graph);
   if ((int)G.entries.size() >= kMaxGraphs) {
     size_t lru = 0;
@@ -428,7 +444,7 @@ int tracknet_forward(const tnb_tracknet_cfg_t& c, const float* x, void* const* p
   uint64_t key = key_common(c, 0, ws, ws_bytes);
   key = fnv(key, &x, sizeof(x)); key = fnv(key, &y, sizeof(y));
   key = fnv(key, params, sizeof(void*) * (kLayers * 6 + 2));
-  return run_maybe_graphed(key, st, [&] { return forward_enqueue(c, x, params, y, ws, ws_bytes, st); });
+  return run_maybe_graphed(key, st, [&](cudaStream_t s) { return forward_enqueue(c, x, params, y, ws, ws_bytes, s); });
 }
 
 int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float* y, void* const* params,
@@ -437,7 +453,13 @@ int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float*
   key = fnv(key, &dy, sizeof(dy)); key = fnv(key, &y, sizeof(y));
   key = fnv(key, params, sizeof(void*) * (kLayers * 6 + 2));
   key = fnv(key, grads, sizeof(void*) * (kLayers * 3 + 2));
-  return run_maybe_graphed(key, st, [&] { return backward_enqueue(c, dy, y, params, grads, ws, ws_bytes, st); });
+  return run_maybe_graphed(key, st,
+                           [&](cudaStream_t s) { return backward_enqueue(c, dy, y, params, grads, ws, ws_bytes, s); });
+}
+
+void graph_stats(long long* out4) {
+  std::lock_guard<std::mutex> lock(g_graphs.mu);
+  out4[0] = g_graphs.captures; out4[1] = g_graphs.replays; out4[2] = g_graphs.eager; out4[3] = g_graphs.failures;
 }
 
 int set_graph_replay(int on) {
