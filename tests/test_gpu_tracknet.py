@@ -241,3 +241,29 @@ def test_cuda_graph_replay_equals_eager_launches():
         assert torch.equal(r0, r1), step                      # running statistics advance on every replay
         for a, b in zip(g0, g1):                              # wgrad accumulates with float atomics: order-dependent
             assert (a - b).abs().max() <= 1e-5 * a.abs().max() + 1e-12, step
+
+
+@pytest.mark.parametrize("h,w", [(360, 640), (544, 960)])
+def test_resolution_sweep_forward_parity(h, w):
+    """BASELINE configs[4]: seq_len 8 / bg concat at the other resolutions of the sweep (540 is not poolable three
+    times - the reference's torch.cat raises there, ours too - 544 is the nearest valid height): forward heatmaps in
+    train and eval mode against the oracle, and a train step's loss."""
+    m = _model(21, 27, 8)
+    sd = O.init_tracknet_state(21, 27, 8)
+    gen = torch.Generator().manual_seed(22)
+    x = torch.rand(1, 27, h, w, generator=gen)
+    y = torch.zeros(1, 8, h, w)
+    for f in range(8):
+        y[0, f] = torch.from_numpy(O.label_disc(37 * f + 11, 23 * f + 9, h=h, w=w))
+    m.train()
+    y_pred = m(x.to(G.DEV))
+    loss = T.WBCELoss(y_pred, y.to(G.DEV))
+    loss.backward()
+    r_pred, r_loss, _ = O.tracknet_loss_and_grads(sd, x, y, True)
+    assert G.max_abs(y_pred, r_pred) < HEAT_TOL
+    assert abs(loss.item() - r_loss.item()) < 1e-4 * abs(r_loss.item())
+    with torch.no_grad():
+        m.eval()
+        assert G.max_abs(m(x.to(G.DEV)), O.tracknet_forward(sd, x, False)) < HEAT_TOL
+    with pytest.raises(RuntimeError, match="divisible by 8"):
+        m(torch.zeros(1, 27, 540, 960, device=G.DEV))
