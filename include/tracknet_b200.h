@@ -190,6 +190,17 @@ int tnb_inpaintnet_fwd(const float* coords, const float* mask, const void* const
 int tnb_inpaintnet_bwd(const float* coords, const float* mask, const void* const* params, const float* dout,
                        void* const* grads, int n, int l, float* dcoords, void* stream);
 
+/* Frame preprocessing (dataset.py:435-461, 783-812): Pillow's antialiased BICUBIC `img.resize((wd, hd))` of nimg uint8
+ * images [nimg][hs][ws][c] (22-bit fixed point, horizontal pass then vertical pass, bit-exact against Pillow), then
+ * HWC -> CHW, / 255 and stacking: image i lands in out + (i / per_sample) * sample_stride +
+ * ((i % per_sample) * c + chan_off) * hd * wd, as float planes. Coefficient tables (device memory) as Pillow's
+ * precompute_coeffs / normalize_coeffs_8bpc build them: bounds = (first tap, tap count) per output sample, kk = ksize
+ * ints per output sample; hbounds/hkk NULL when ws == wd (Pillow skips that pass); the vertical table must always
+ * be given (identity table when hs == hd). tmp: nimg * hs * wd * c bytes of scratch. */
+int tnb_resize_frames(const uint8_t* src, int nimg, int hs, int ws, int c, const int* hbounds, const int* hkk, int hksize,
+                      const int* vbounds, const int* vkk, int vksize, int hd, int wd, uint8_t* tmp, float* out,
+                      int per_sample, long long sample_stride, int chan_off, void* stream);
+
 /* Per-map statistics of the evaluation bookkeeping (test.py:159-169): conf[m] = max of y_pred map m inside
  * boxes[m] = (x, y, w, h) (0 for an empty box); true_any[m] = 1 iff map m of y_true has a value > 0 (y_true and
  * true_any may be NULL). boxes: int32 as written by tnb_heatmap_decode. */

@@ -222,6 +222,37 @@ def gen_evaluate():
     np.savez_compressed(f"{OUT}/evaluate.npz", **out)
 
 
+def gen_input_pipeline():
+    """EXECUTE the reference's frame preprocessing - `Video_IterableDataset.__process__` (dataset.py:783-812), lifted
+    out of its class with ast and run against the real Pillow of this image - for bg_mode '' and 'concat', plus the
+    median preparation of dataset.py:102-107. Small frames keep the fixture small; the resize arithmetic does not
+    depend on the size (tests/test_oracle.py also pins the restatement against Pillow at 720p -> 288x512)."""
+    from PIL import Image
+    tree = ast.parse(open(f"{REF}/dataset.py").read())
+    fn = None
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == "__process__":
+            fn = node
+    env = {"np": np, "Image": Image}
+    fn.name = "process"
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), f"{REF}/dataset.py", "exec"), env)
+    rng = np.random.default_rng(31)
+    out = {}
+    for name, (h0, w0, H, W, L) in {"down": (90, 160, 36, 64, 3), "odd": (77, 123, 40, 56, 2), "up": (20, 30, 36, 64, 2)}.items():
+        imgs = rng.integers(0, 256, (L, h0, w0, 3), dtype=np.uint8)
+        imgs[0, 10:30, 20:50] = 255; imgs[1, :, ::2] = 0          # hard edges: over/undershoot gets clipped
+        med_src = np.median(imgs, 0)
+        med = np.moveaxis(np.array(Image.fromarray(med_src.astype('uint8')).resize(size=(W, H))), -1, 0)  # dataset.py:104-107
+
+        class S:  # stand-in for the dataset object
+            pass
+        for bg in ("", "concat"):
+            s_ = S(); s_.bg_mode, s_.median, s_.HEIGHT, s_.WIDTH, s_.seq_len = bg, med, H, W, L
+            out[f"{name}/{bg or 'none'}"] = env["process"](s_, imgs)
+        out[f"{name}/imgs"], out[f"{name}/median_src"], out[f"{name}/median"] = imgs, med_src, med
+    np.savez_compressed(f"{OUT}/input_pipeline.npz", **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -229,6 +260,10 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "inpaint_train":  # regenerate only this fixture
         gen_inpaint_train(refmodel)
         print("inpaintnet_train.npz written")
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "input_pipeline":
+        gen_input_pipeline()
+        print("input_pipeline.npz written")
         return
     if len(sys.argv) > 1 and sys.argv[1] == "evaluate":
         gen_evaluate()
@@ -338,6 +373,7 @@ def main():
     gen_inpaint_train(refmodel)
     gen_temporal_ensemble()
     gen_evaluate()
+    gen_input_pipeline()
 
     # ---- small host-side pieces: ensemble weights, mixup ----
     ew = {f"weight_{L}": env["get_ensemble_weight"](L, "weight").numpy() for L in (1, 4, 7, 8)}

@@ -435,3 +435,31 @@ def test_evaluate_on_gpu_vs_reference_fixture(golden_dir):
     got = TT.evaluate(idx, y_true=yb.to(G.DEV), y_pred=yp.to(G.DEV), output_bbox=True, output_gt=True)
     want = D.evaluate(idx.numpy(), y_true=yb.numpy(), y_pred=yp.numpy(), output_bbox=True, output_gt=True)
     assert got == want
+
+
+def test_frame_preprocessing_vs_reference_fixture_and_pillow_oracle(golden_dir):
+    """GPU resize + normalise + stack vs (i) the reference's `__process__` run with real Pillow (fixture),
+    (ii) the oracle restatement of Pillow at the real sizes (720p -> 288x512, identity, 360x640): bit-exact uint8
+    resampling, outputs equal to float32(frames / 255.)."""
+    from oracle import pil_resize_oracle as P
+    g = _load(golden_dir, "input_pipeline.npz")
+    for name in ("down", "odd", "up"):
+        imgs, med = g[f"{name}/imgs"], g[f"{name}/median"]
+        H, W = med.shape[1:]
+        fp = T.FramePreprocessor(imgs.shape[1], imgs.shape[2], H, W)
+        x = torch.from_numpy(imgs).to(G.DEV).unsqueeze(0)                  # (1, L, Hs, Ws, 3)
+        assert torch.equal(fp.process(x).cpu()[0], torch.from_numpy(g[f"{name}/none"]).float())
+        m = fp.prepare_median(g[f"{name}/median_src"])
+        assert torch.equal(m.cpu(), torch.from_numpy(med))
+        assert torch.equal(fp.process(x, m).cpu()[0], torch.from_numpy(g[f"{name}/concat"]).float())
+    rng = np.random.default_rng(8)
+    for hs, ws, h, w, n, l in ((720, 1280, 288, 512, 2, 3), (288, 512, 288, 512, 1, 2), (720, 1280, 360, 640, 1, 2),
+                               (288, 400, 288, 512, 1, 1)):
+        imgs = rng.integers(0, 256, (n, l, hs, ws, 3), dtype=np.uint8)
+        fp = T.FramePreprocessor(hs, ws, h, w)
+        got = fp.process(torch.from_numpy(imgs).to(G.DEV)).cpu()
+        for i in range(n):
+            want = torch.from_numpy(P.process_frames(imgs[i], None, w, h)).float()
+            assert torch.equal(got[i], want), (hs, ws, h, w, i)
+    with pytest.raises(RuntimeError):
+        fp.process(torch.zeros(1, 1, 10, 10, 3, dtype=torch.uint8, device=G.DEV))

@@ -192,3 +192,22 @@ def test_evaluate_matches_reference(golden_dir):
     for k in d:
         assert np.array_equal(np.asarray(d[k], dtype=np.float64), g[f"co/{k}"]), k
     assert set(g["hm_plain/Type"].tolist()) == {0.0, 1.0, 2.0, 3.0, 4.0}
+
+
+def test_input_pipeline_matches_reference_and_pillow(golden_dir):
+    """oracle restatement of Pillow's bicubic resize + the reference's frame stacking vs (i) the reference's own
+    `__process__` executed with real Pillow by oracle/gen_golden.py, (ii) real Pillow itself when importable."""
+    from oracle import pil_resize_oracle as P
+    g = _load(golden_dir, "input_pipeline.npz")
+    for name in ("down", "odd", "up"):
+        imgs, med = g[f"{name}/imgs"], g[f"{name}/median"]
+        H, W = med.shape[1:]
+        assert np.array_equal(P.process_frames(imgs, None, W, H), g[f"{name}/none"])
+        assert np.array_equal(P.process_frames(imgs, med, W, H), g[f"{name}/concat"])
+        med2 = np.moveaxis(P.resize_bicubic_u8(g[f"{name}/median_src"].astype("uint8"), W, H), -1, 0)
+        assert np.array_equal(med2, med)
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(5)
+    for h, w, oh, ow in ((720, 1280, 288, 512), (97, 131, 40, 64), (50, 70, 100, 90)):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(P.resize_bicubic_u8(img, ow, oh), np.array(Image.fromarray(img).resize(size=(ow, oh))))

@@ -5,6 +5,7 @@ from .decode import decode_heatmaps, predict_location, bbox_to_center  # noqa: F
 from .optim import FusedAdam  # noqa: F401
 from .data import DevicePrefetcher  # noqa: F401
 from .ensemble import TemporalEnsemble, get_ensemble_weight  # noqa: F401
+from .frames import FramePreprocessor, resample_table  # noqa: F401
 from . import _lib  # noqa: F401
 
 __all__ = ["TrackNet", "InpaintNet", "WBCELoss", "get_metric", "decode_heatmaps", "predict_location",

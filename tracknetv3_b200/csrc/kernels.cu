@@ -1132,4 +1132,83 @@ int launch_eval_stats(const float* y_pred, const float* y_true, const int* boxes
   return 0;
 }
 
+
+// =============================================================================================
+// Frame preprocessing (reference dataset.py:435-461, 611-647, 783-812): `img.resize((W, H))` of every uint8 frame -
+// Pillow's antialiased BICUBIC in 22-bit fixed point, horizontal pass first, rounded to uint8 between the passes
+// (Pillow 10.0.0 src/libImaging/Resample.c, the reference's pinned dependency) - then HWC -> CHW, / 255 and stacking
+// into the (N, C, H, W) float tensor the network consumes. Integer arithmetic throughout: bit-exact against Pillow.
+// The coefficient tables are built on the host exactly as Resample.c builds them (tracknetv3_b200/frames.py).
+// =============================================================================================
+TNB_DEVINL int clip8_fixed(int acc) {
+  const int v = acc >> 22;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+// horizontal pass: src [nimg][hs][ws][C] u8 -> tmp [nimg][hs][wd][C] u8
+__global__ void __launch_bounds__(256) resize_h_kernel(const uint8_t* __restrict__ src, int nimg, int hs, int ws, int wd, int C,
+                                                       const int* __restrict__ bounds, const int* __restrict__ kk, int ksize,
+                                                       uint8_t* __restrict__ tmp) {
+  const long long total = (long long)nimg * hs * wd;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % wd);
+    const long long row = i / wd;  // image * hs + y
+    const int xmin = bounds[2 * xx], cnt = bounds[2 * xx + 1];
+    const uint8_t* p = src + (row * ws + xmin) * C;
+    const int* k = kk + (size_t)xx * ksize;
+    int acc[4] = {1 << 21, 1 << 21, 1 << 21, 1 << 21};
+    for (int x = 0; x < cnt; ++x) {
+      const int w = k[x];
+      for (int c = 0; c < C; ++c) acc[c] += (int)p[x * C + c] * w;
+    }
+    for (int c = 0; c < C; ++c) tmp[i * C + c] = (uint8_t)clip8_fixed(acc[c]);
+  }
+}
+// vertical pass fused with HWC -> CHW, / 255 and the channel stacking: tmp [nimg][hs][wd][C] u8 ->
+// out[(img / per_sample) * sample_stride + ((img % per_sample) * C + chan_off + c) * hd * wd + yy * wd + xx] float
+__global__ void __launch_bounds__(256) resize_v_stack_kernel(const uint8_t* __restrict__ tmp, int nimg, int hs, int wd, int hd,
+                                                             int C, const int* __restrict__ bounds, const int* __restrict__ kk,
+                                                             int ksize, float* __restrict__ out, int per_sample,
+                                                             long long sample_stride, int chan_off) {
+  const long long total = (long long)nimg * hd * wd;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % wd);
+    const long long r = i / wd;
+    const int yy = (int)(r % hd);
+    const int img = (int)(r / hd);
+    const int ymin = bounds[2 * yy], cnt = bounds[2 * yy + 1];
+    const uint8_t* p = tmp + (((long long)img * hs + ymin) * wd + xx) * C;
+    const int* k = kk + (size_t)yy * ksize;
+    int acc[4] = {1 << 21, 1 << 21, 1 << 21, 1 << 21};
+    for (int y = 0; y < cnt; ++y) {
+      const int w = k[y];
+      for (int c = 0; c < C; ++c) acc[c] += (int)p[(long long)y * wd * C + c] * w;
+    }
+    float* o = out + (long long)(img / per_sample) * sample_stride +
+               ((long long)(img % per_sample) * C + chan_off) * hd * wd + (long long)yy * wd + xx;
+    // the reference divides the float64 array by 255. and casts to float32 at train.py:86 / predict.py:171
+    for (int c = 0; c < C; ++c) o[(long long)c * hd * wd] = __double2float_rn((double)clip8_fixed(acc[c]) / 255.0);
+  }
+}
+int launch_resize_frames(const uint8_t* src, int nimg, int hs, int ws, int C, const int* hbounds, const int* hkk, int hksize,
+                         const int* vbounds, const int* vkk, int vksize, int hd, int wd, uint8_t* tmp, float* out,
+                         int per_sample, long long sample_stride, int chan_off, cudaStream_t st) {
+  TNB_REQUIRE(C >= 1 && C <= 4 && per_sample >= 1, "resize_frames: channels %d / frames per sample %d", C, per_sample);
+  if (nimg == 0) return 0;
+  const uint8_t* vsrc = src;
+  if (hbounds != nullptr) {  // widths differ: horizontal pass first (Resample.c ImagingResampleInner)
+    const long long total = (long long)nimg * hs * wd;
+    resize_h_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(src, nimg, hs, ws, wd, C,
+                                                                                           hbounds, hkk, hksize, tmp);
+    TNB_CHECK_CUDA(cudaGetLastError());
+    vsrc = tmp;
+  } else {
+    TNB_REQUIRE(ws == wd, "resize_frames: no horizontal table but widths differ (%d vs %d)", ws, wd);
+  }
+  const long long total = (long long)nimg * hd * wd;
+  resize_v_stack_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(
+      vsrc, nimg, hs, wd, hd, C, vbounds, vkk, vksize, out, per_sample, sample_stride, chan_off);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace tnb

@@ -43,6 +43,9 @@ int launch_decode(const void* maps, int is_u8, float thresh, int nmaps, int H, i
 struct InpaintParams { const float* w[9]; const float* b[9]; };
 int launch_inpaint_fwd(const float* coords, const float* mask, const InpaintParams& p, int N, int L, float* out,
                        cudaStream_t st);
+int launch_resize_frames(const uint8_t* src, int nimg, int hs, int ws, int C, const int* hbounds, const int* hkk, int hksize,
+                         const int* vbounds, const int* vkk, int vksize, int hd, int wd, uint8_t* tmp, float* out,
+                         int per_sample, long long sample_stride, int chan_off, cudaStream_t st);
 int launch_eval_stats(const float* y_pred, const float* y_true, const int* boxes, int nmaps, int H, int W, float* conf,
                       int* true_any, cudaStream_t st);
 int launch_temporal_ensemble(const float* state, const float* pred, float* out, const float* weight_host, int L,
