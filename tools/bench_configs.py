@@ -50,6 +50,12 @@ def inference_path(bs=32, seq_len=8, h=288, w=512, steps=10):
         ens = ens_step()
         out["ensemble_decode_ms"] = timed(lambda: T.decode_heatmaps(ens.unsqueeze(1)), steps, 3)
         out["inpaintnet_fwd_ms"] = timed(lambda: inp(coor * (1 - mask), mask), steps, 3)
+    # GPU input pipeline: bs x seq_len 720p RGB frames -> Pillow-exact 288x512 -> (bs, 27, H, W)
+    fp = T.FramePreprocessor(720, 1280, h, w)
+    frames = torch.randint(0, 256, (bs, seq_len, 720, 1280, 3), dtype=torch.uint8, device="cuda")
+    med = fp.prepare_median(frames[0, 0].cpu().numpy())
+    out["frame_preprocess_720p_ms"] = timed(lambda: fp.process(frames, med), steps, 3)
+    out["frame_preprocess_input_GBps"] = frames.numel() / (out["frame_preprocess_720p_ms"] * 1e-3) / 1e9
     total = out["tracknet_fwd_ms"] + out["decode_ms"] + out["inpaintnet_fwd_ms"]
     out.update(config="configs[3]: predict path bs=32 seq_len=8 288x512 (nonoverlap: fwd + decode + InpaintNet)",
                frames_per_s=bs * seq_len / total * 1e3,
