@@ -108,3 +108,30 @@ def test_gradient_bucket_allreduce_gloo_world2():
     assert np.array_equal(res[0][2], res[1][2])              # identical averaged gradients
     # rank grads were (r+1)*(i+1): mean over ranks = 1.5*(i+1)
     assert np.allclose(np.unique(res[0][2]), [1.5, 3.0, 4.5, 6.0])
+
+
+def test_resample_tables_match_pillow_restatement():
+    """Host-side coefficient tables of the GPU resize (tracknetv3_b200.frames) == the oracle's restatement of
+    Pillow's precompute_coeffs / normalize_coeffs_8bpc, which tests/test_oracle.py pins against real Pillow."""
+    import tracknetv3_b200 as T
+    from oracle import pil_resize_oracle as P
+    for a, b in ((720, 288), (1280, 512), (1080, 288), (50, 100), (31, 5), (97, 40)):
+        b1, k1 = T.resample_table(a, b)
+        b2, k2 = P.precompute_coeffs(a, b)
+        assert np.array_equal(b1, b2) and np.array_equal(k1, k2), (a, b)
+        assert (k1.sum(1) - (1 << 22)).__abs__().max() <= k1.shape[1]      # weights sum to 1 in 22-bit fixed point
+    b, k = T.resample_table(288, 288)                                      # identity pass
+    assert np.array_equal(b[:, 0], np.arange(288)) and (b[:, 1] == 1).all() and (k == 1 << 22).all()
+
+
+def test_evaluate_coordinate_mode_matches_reference_fixture():
+    """test.evaluate in coordinate mode is host arithmetic on (N, L, 2) arrays (no GPU involved): check it against the
+    reference's evaluate (fixture) here; the heatmap mode is a -m gpu test."""
+    import test as TT
+    g = np.load(os.path.join(ROOT, "tests", "golden", "evaluate.npz"))
+    d = TT.evaluate(torch.from_numpy(g["indices"]), c_true=torch.from_numpy(g["c_true"]),
+                    c_pred=torch.from_numpy(g["c_pred"]), output_gt=True)
+    for k in d:
+        assert np.array_equal(np.asarray(d[k], dtype=np.float64), g["co/" + k]), k
+    with pytest.raises(ValueError):
+        TT.evaluate(torch.from_numpy(g["indices"]))
