@@ -251,6 +251,32 @@ def test_bn_finalize_and_predictor():
     assert G.rel_err(dwp, wp.grad.reshape(o, c)) < 1e-4 and G.rel_err(dbp, bp.grad) < 1e-4
 
 
+@pytest.mark.parametrize("n,h,w,o,affine", [(2, 8, 12, 8, True), (1, 7, 9, 4, True), (3, 5, 11, 12, False), (1, 40, 72, 8, True)])
+def test_predictor_backward_shapes(n, h, w, o, affine):
+    """sigmoid + 1x1 conv backward (two streaming kernels): pixel counts that are not multiples of the 32-pixel warp
+    chunk, out_dim 4 / 8 / 12 (both template instances), BN+ReLU and identity activation sources."""
+    L = G.lib()
+    gen = torch.Generator().manual_seed(60 + o)
+    z = torch.randn(n, 64, h, w, generator=gen)
+    sc, sh = torch.rand(64, generator=gen) + 0.5, torch.randn(64, generator=gen) * 0.3
+    a = F.relu(z * sc[None, :, None, None] + sh[None, :, None, None]) if affine else z
+    wp = (torch.rand(o, 64, 1, 1, generator=gen) - 0.5).requires_grad_(True)
+    bp = (torch.rand(o, generator=gen) - 0.5).requires_grad_(True)
+    a_leaf = a.detach().clone().requires_grad_(True)
+    y_ref = torch.sigmoid(F.conv2d(a_leaf, wp, bp))
+    dy = torch.randn(n, o, h, w, generator=gen)
+    y_ref.backward(dy)
+    zt, scd, shd = G.nhwc(z), sc.to(G.DEV), sh.to(G.DEV)
+    src = G.make_src(zt, _lib.SRC_AFFINE_RELU, scd, shd) if affine else G.make_src(zt)
+    yd, dyd, wd = y_ref.detach().to(G.DEV).contiguous(), dy.to(G.DEV), wp.detach().to(G.DEV)
+    dA = torch.full((n, h, w, 64), float("nan"), device=G.DEV)
+    dwp = torch.full((o, 64), float("nan"), device=G.DEV); dbp = torch.full((o,), float("nan"), device=G.DEV)
+    _lib.check(L.tnb_conv1x1_bias_sigmoid_bwd(C.byref(src), n, h, w, wd.data_ptr(), o, dyd.data_ptr(), yd.data_ptr(),
+                                              dA.data_ptr(), dwp.data_ptr(), dbp.data_ptr(), G.st()))
+    assert G.rel_err(G.nchw(dA), a_leaf.grad) < 1e-4
+    assert G.rel_err(dwp, wp.grad.reshape(o, 64)) < 1e-4 and G.rel_err(dbp, bp.grad) < 1e-4
+
+
 @pytest.mark.parametrize("consumers", ["same", "pool+skip", "up"])
 def test_bn_relu_backward_with_gradient_routing(consumers):
     """BN+ReLU backward fused with MaxPool / Upsample / cat gradient routing vs torch autograd (CPU fp32)."""

@@ -171,107 +171,117 @@ int launch_predictor_fwd(const SrcDesc& src, int N, int H, int W, const float* w
 
 // backward of sigmoid + 1x1 conv: dl = dy*y*(1-y); dA[p][c] = sum_o dl[o] W[o][c];
 // dW[o][c] = sum_p dl[p][o] a[p][c]; db[o] = sum_p dl[p][o]   (autograd of model.py:71-72)
-__global__ void __launch_bounds__(256, 4) predictor_bwd_kernel(SrcDesc src, int N, int H, int W,
-                                                            const float* __restrict__ wp, int O,
-                                                            const float* __restrict__ dy,
-                                                            const float* __restrict__ y, float* __restrict__ dA,
-                                                            float* dwp, float* dbias) {
-  constexpr int TP = 64;  // pixels per tile
+// Two streaming kernels without block-level barriers (a single tiled kernel with load -> barrier -> compute phases ran
+// at 1.7 TB/s): dA needs only dl and W; dW / db need dl and the activation, reduced in registers along the pixels.
+__global__ void __launch_bounds__(256) predictor_bwd_da_kernel(long long npix, long long hw, const float* __restrict__ wp,
+                                                               int O, const float* __restrict__ dy,
+                                                               const float* __restrict__ y, float* __restrict__ dA) {
   __shared__ float sw[kMaxPredO * 64];
-  __shared__ float sdl[kMaxPredO][TP];
-  __shared__ __align__(16) float sa[TP][68];  // 16-byte aligned rows: the dW pass reads float4
-  for (int i = threadIdx.x; i < O * 64; i += 256) sw[i] = wp[i];
-  const long long hw = (long long)H * W, npix = (long long)N * hw;
-  const long long ntiles = (npix + TP - 1) / TP;
-  // dW pass: a "unit" = one output map o x 4 consecutive channels; units = O*16; the 256 threads form G pixel groups
-  // of `units` threads, each group reducing its share of the tile's pixels (1 scalar + 1 float4 LDS per 4 FMAs)
-  const int units = O * 16;
-  const int G = units <= 64 ? 4 : units <= 128 ? 2 : 1;
-  const int ugrp = threadIdx.x / units, uidx = threadIdx.x - ugrp * units;
-  const bool uact = ugrp < G;
-  const int uo = uidx >> 4, uc = (uidx & 15) * 4;
-  float accw[4] = {0.f, 0.f, 0.f, 0.f};
-  float accb = 0.f;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    __syncthreads();
-    const long long p0 = tile * TP;
-    for (int i = threadIdx.x; i < TP * O; i += 256) {
-      const int pl = i % TP, o = i / TP;
-      const long long p = p0 + pl;
-      float d = 0.f;
-      if (p < npix) {
+  for (int i = threadIdx.x; i < O * 64; i += blockDim.x) sw[i] = wp[i];
+  __syncthreads();
+  // 4 threads per pixel, 16 channels each: a warp writes 8 pixels x 256 B = 2 KB contiguous
+  const long long total = npix * 4;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < total; it += (long long)gridDim.x * blockDim.x) {
+    const long long p = it >> 2;
+    const int qd = (int)(it & 3);
+    const long long n = p / hw, r = p - n * hw;
+    float g[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) g[i] = 0.f;
+    for (int o = 0; o < O; ++o) {
+      const float yy = __ldg(y + (n * O + o) * hw + r);
+      const float d = __ldg(dy + (n * O + o) * hw + r) * yy * (1.f - yy);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) g[i] = fmaf(d, sw[o * 64 + qd * 16 + i], g[i]);
+    }
+    float4* dst = reinterpret_cast<float4*>(dA + p * 64 + qd * 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = make_float4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
+  }
+}
+// one warp per chunk of 32 consecutive pixels: lane l first computes dl of pixel p0 + l (coalesced plane reads), then
+// the warp walks the 32 pixels - lane l owns channels 2l, 2l+1 of the activation (256 B coalesced per pixel) and the
+// dl values arrive by shuffle; acc[o][2] lives in registers for the whole grid-stride loop
+template <int O_MAX>
+__global__ void __launch_bounds__(256) predictor_bwd_dw_kernel(SrcDesc src, long long npix, long long hw, int O,
+                                                               const float* __restrict__ dy, const float* __restrict__ y,
+                                                               float* dwp, float* dbias) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool affine = src.mode != SRC_IDENTITY;
+  float2 sc = make_float2(1.f, 1.f), sh = make_float2(0.f, 0.f);
+  if (affine) {
+    sc = *reinterpret_cast<const float2*>(src.scale + 2 * lane);
+    sh = *reinterpret_cast<const float2*>(src.shift + 2 * lane);
+  }
+  float acc[O_MAX][2], dsum[O_MAX];
+#pragma unroll
+  for (int o = 0; o < O_MAX; ++o) { acc[o][0] = acc[o][1] = 0.f; dsum[o] = 0.f; }
+  const long long nchunks = (npix + 31) / 32;
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long ch = blockIdx.x * (long long)(blockDim.x >> 5) + warp; ch < nchunks; ch += wstride) {
+    const long long p0 = ch * 32, p = p0 + lane;
+    float d[O_MAX];
+#pragma unroll
+    for (int o = 0; o < O_MAX; ++o) {
+      d[o] = 0.f;
+      if (o < O && p < npix) {
         const long long n = p / hw, r = p - n * hw;
-        const float yy = y[(n * O + o) * hw + r];
-        d = dy[(n * O + o) * hw + r] * yy * (1.f - yy);
+        const float yy = __ldg(y + (n * O + o) * hw + r);
+        d[o] = __ldg(dy + (n * O + o) * hw + r) * yy * (1.f - yy);
       }
-      sdl[o][pl] = d;
+      dsum[o] += d[o];
     }
-    __syncthreads();
-    {
-      const int pl = threadIdx.x >> 2, qd = threadIdx.x & 3;
-      const long long p = p0 + pl;
-      float a[16];
-      if (p < npix) {
-        float v[8];
-        view_load8(src, (int)p, qd * 16, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = v[i];
-        view_load8(src, (int)p, qd * 16 + 8, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[8 + i] = v[i];
-        float g[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) g[i] = 0.f;
-        for (int o = 0; o < O; ++o) {
-          const float d = sdl[o][pl];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) g[i] = fmaf(d, sw[o * 64 + qd * 16 + i], g[i]);
-        }
-        float4* dst = reinterpret_cast<float4*>(dA + p * 64 + qd * 16);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = make_float4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) a[i] = 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) sa[pl][qd * 16 + i] = a[i];
-    }
-    __syncthreads();
-    if (uact) {
-      const int per = TP / G;
+    const int cnt = (int)min((long long)32, npix - p0);
 #pragma unroll 4
-      for (int pl = ugrp * per; pl < (ugrp + 1) * per; ++pl) {
-        const float d = sdl[uo][pl];
-        const float4 a4 = *reinterpret_cast<const float4*>(&sa[pl][uc]);
-        accw[0] = fmaf(d, a4.x, accw[0]);
-        accw[1] = fmaf(d, a4.y, accw[1]);
-        accw[2] = fmaf(d, a4.z, accw[2]);
-        accw[3] = fmaf(d, a4.w, accw[3]);
+    for (int j = 0; j < cnt; ++j) {
+      float2 a = __ldg(reinterpret_cast<const float2*>(src.ptr + (p0 + j) * 64 + 2 * lane));
+      if (affine) { a.x = fmaxf(fmaf(a.x, sc.x, sh.x), 0.f); a.y = fmaxf(fmaf(a.y, sc.y, sh.y), 0.f); }
+#pragma unroll
+      for (int o = 0; o < O_MAX; ++o) {
+        const float dj = __shfl_sync(0xffffffffu, d[o], j);
+        acc[o][0] = fmaf(dj, a.x, acc[o][0]);
+        acc[o][1] = fmaf(dj, a.y, acc[o][1]);
       }
     }
-    if (threadIdx.x < O) {
-      float s = accb;
-      for (int pl = 0; pl < TP; ++pl) s += sdl[threadIdx.x][pl];
-      accb = s;
-    }
   }
-  if (uact) {
+  // block reduction over the 8 warps, then one atomic per (o, channel) and per o
+  __shared__ float red[8][O_MAX][64];
+  __shared__ float redb[8][O_MAX];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) atomicAdd(dwp + uo * 64 + uc + k, accw[k]);
+  for (int o = 0; o < O_MAX; ++o) {
+    red[warp][o][2 * lane] = acc[o][0];
+    red[warp][o][2 * lane + 1] = acc[o][1];
+    const float s = warp_sum(dsum[o]);
+    if (lane == 0) redb[warp][o] = s;
   }
-  if (threadIdx.x < O) atomicAdd(dbias + threadIdx.x, accb);
+  __syncthreads();
+  for (int i = threadIdx.x; i < O * 64; i += blockDim.x) {
+    const int o = i >> 6, c = i & 63;
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][o][c];
+    atomicAdd(dwp + i, s);
+  }
+  if (threadIdx.x < O) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += redb[w][threadIdx.x];
+    atomicAdd(dbias + threadIdx.x, s);
+  }
 }
 int launch_predictor_bwd(const SrcDesc& src, int N, int H, int W, const float* wp, int O, const float* dy,
                          const float* y, float* dA, float* dwp, float* dbias, cudaStream_t st) {
   TNB_REQUIRE(src.C == 64 && O <= kMaxPredO, "predictor_bwd: expects 64 channels, out_dim <= %d", kMaxPredO);
-  const long long npix = (long long)N * H * W;
+  TNB_REQUIRE((src.mode == SRC_IDENTITY || src.mode == SRC_AFFINE_RELU) && src.Hs == H && src.Ws == W,
+              "predictor_bwd: the activation must be a same-resolution identity / BN+ReLU source (mode %d)", src.mode);
+  const long long npix = (long long)N * H * W, hw = (long long)H * W;
   TNB_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * O * 64, st));
   TNB_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * O, st));
   ProfScope prof(PROF_PRED, st, N, H, W, 64, O);
-  // 4 resident CTAs per SM (__launch_bounds__(256, 4) caps the registers): every 64-pixel tile is a
-  // load -> barrier -> compute chain, so it is the other CTAs that hide the load latency
-  predictor_bwd_kernel<<<min(cdiv(npix, 64), 148 * 4), 256, 0, st>>>(src, N, H, W, wp, O, dy, y, dA, dwp, dbias);
+  const long long blocks_a = (npix * 4 + 255) / 256, blocks_w = ((npix + 31) / 32 + 7) / 8;
+  predictor_bwd_da_kernel<<<(int)std::min<long long>(blocks_a, 148 * 8), 256, 0, st>>>(npix, hw, wp, O, dy, y, dA);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  const int gridw = (int)std::min<long long>(blocks_w, 148 * 4);
+  if (O <= 8) predictor_bwd_dw_kernel<8><<<gridw, 256, 0, st>>>(src, npix, hw, O, dy, y, dwp, dbias);
+  else        predictor_bwd_dw_kernel<kMaxPredO><<<gridw, 256, 0, st>>>(src, npix, hw, O, dy, y, dwp, dbias);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
