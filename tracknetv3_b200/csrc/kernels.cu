@@ -173,84 +173,104 @@ int launch_predictor_fwd(const SrcDesc& src, int N, int H, int W, const float* w
 // dW[o][c] = sum_p dl[p][o] a[p][c]; db[o] = sum_p dl[p][o]   (autograd of model.py:71-72)
 // Two streaming kernels without block-level barriers (a single tiled kernel with load -> barrier -> compute phases ran
 // at 1.7 TB/s): dA needs only dl and W; dW / db need dl and the activation, reduced in registers along the pixels.
+template <int O_MAX>
 __global__ void __launch_bounds__(256) predictor_bwd_da_kernel(long long npix, long long hw, const float* __restrict__ wp,
                                                                int O, const float* __restrict__ dy,
                                                                const float* __restrict__ y, float* __restrict__ dA) {
   __shared__ float sw[kMaxPredO * 64];
   for (int i = threadIdx.x; i < O * 64; i += blockDim.x) sw[i] = wp[i];
   __syncthreads();
-  // 4 threads per pixel, 16 channels each: a warp writes 8 pixels x 256 B = 2 KB contiguous
+  // 4 threads per pixel, 16 channels each, interleaved in float4 units (thread qd owns channels 16*i + 4*qd .. +3,
+  // i = 0..3): every store instruction of a warp then writes whole 32-byte sectors (64 contiguous bytes per pixel)
   const long long total = npix * 4;
   for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < total; it += (long long)gridDim.x * blockDim.x) {
     const long long p = it >> 2;
     const int qd = (int)(it & 3);
     const long long n = p / hw, r = p - n * hw;
-    float g[16];
+    float g[16], yv[O_MAX], dv[O_MAX];
 #pragma unroll
     for (int i = 0; i < 16; ++i) g[i] = 0.f;
-    for (int o = 0; o < O; ++o) {
-      const float yy = __ldg(y + (n * O + o) * hw + r);
-      const float d = __ldg(dy + (n * O + o) * hw + r) * yy * (1.f - yy);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) g[i] = fmaf(d, sw[o * 64 + qd * 16 + i], g[i]);
+    for (int o = 0; o < O_MAX; ++o) {  // all 2 * O loads of the item in flight together
+      yv[o] = o < O ? __ldg(y + (n * O + o) * hw + r) : 0.f;
+      dv[o] = o < O ? __ldg(dy + (n * O + o) * hw + r) : 0.f;
     }
-    float4* dst = reinterpret_cast<float4*>(dA + p * 64 + qd * 16);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) dst[i] = make_float4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
+    for (int o = 0; o < O_MAX; ++o) {
+      if (o < O) {
+        const float d = dv[o] * yv[o] * (1.f - yv[o]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) g[i] = fmaf(d, sw[o * 64 + (i >> 2) * 16 + qd * 4 + (i & 3)], g[i]);
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(dA + p * 64 + qd * 4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[4 * i] = make_float4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
   }
 }
 // one warp per chunk of 32 consecutive pixels: lane l first computes dl of pixel p0 + l (coalesced plane reads), then
-// the warp walks the 32 pixels - lane l owns channels 2l, 2l+1 of the activation (256 B coalesced per pixel) and the
-// dl values arrive by shuffle; acc[o][2] lives in registers for the whole grid-stride loop
+// the warp walks the chunk two pixels at a time - half-warp h takes pixel 2j + h, lane owns 4 channels of the
+// activation (one 16-byte load; 512 contiguous bytes per warp instruction, 8 of them in flight) and the dl values
+// arrive by shuffle; acc[o][4] lives in registers for the whole grid-stride loop
 template <int O_MAX>
 __global__ void __launch_bounds__(256) predictor_bwd_dw_kernel(SrcDesc src, long long npix, long long hw, int O,
                                                                const float* __restrict__ dy, const float* __restrict__ y,
                                                                float* dwp, float* dbias) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = lane >> 4, c4 = (lane & 15) * 4;
   const bool affine = src.mode != SRC_IDENTITY;
-  float2 sc = make_float2(1.f, 1.f), sh = make_float2(0.f, 0.f);
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
   if (affine) {
-    sc = *reinterpret_cast<const float2*>(src.scale + 2 * lane);
-    sh = *reinterpret_cast<const float2*>(src.shift + 2 * lane);
+    sc = *reinterpret_cast<const float4*>(src.scale + c4);
+    sh = *reinterpret_cast<const float4*>(src.shift + c4);
   }
-  float acc[O_MAX][2], dsum[O_MAX];
+  float acc[O_MAX][4], dsum[O_MAX];
 #pragma unroll
-  for (int o = 0; o < O_MAX; ++o) { acc[o][0] = acc[o][1] = 0.f; dsum[o] = 0.f; }
+  for (int o = 0; o < O_MAX; ++o) { acc[o][0] = acc[o][1] = acc[o][2] = acc[o][3] = 0.f; dsum[o] = 0.f; }
   const long long nchunks = (npix + 31) / 32;
   const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long ch = blockIdx.x * (long long)(blockDim.x >> 5) + warp; ch < nchunks; ch += wstride) {
     const long long p0 = ch * 32, p = p0 + lane;
-    float d[O_MAX];
+    float d[O_MAX], yv[O_MAX];
+    const long long n = p < npix ? p / hw : 0, r = p < npix ? p - n * hw : 0;
 #pragma unroll
     for (int o = 0; o < O_MAX; ++o) {
-      d[o] = 0.f;
-      if (o < O && p < npix) {
-        const long long n = p / hw, r = p - n * hw;
-        const float yy = __ldg(y + (n * O + o) * hw + r);
-        d[o] = __ldg(dy + (n * O + o) * hw + r) * yy * (1.f - yy);
-      }
-      dsum[o] += d[o];
+      const bool ok = o < O && p < npix;
+      yv[o] = ok ? __ldg(y + (n * O + o) * hw + r) : 0.f;
+      d[o] = ok ? __ldg(dy + (n * O + o) * hw + r) : 0.f;
     }
-    const int cnt = (int)min((long long)32, npix - p0);
-#pragma unroll 4
-    for (int j = 0; j < cnt; ++j) {
-      float2 a = __ldg(reinterpret_cast<const float2*>(src.ptr + (p0 + j) * 64 + 2 * lane));
-      if (affine) { a.x = fmaxf(fmaf(a.x, sc.x, sh.x), 0.f); a.y = fmaxf(fmaf(a.y, sc.y, sh.y), 0.f); }
+#pragma unroll
+    for (int o = 0; o < O_MAX; ++o) { d[o] = d[o] * yv[o] * (1.f - yv[o]); dsum[o] += d[o]; }
+#pragma unroll 8
+    for (int j = 0; j < 16; ++j) {
+      const int pj = 2 * j + half;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p0 + pj < npix) {
+        a = __ldg(reinterpret_cast<const float4*>(src.ptr + (p0 + pj) * 64 + c4));
+        if (affine) {
+          a.x = fmaxf(fmaf(a.x, sc.x, sh.x), 0.f); a.y = fmaxf(fmaf(a.y, sc.y, sh.y), 0.f);
+          a.z = fmaxf(fmaf(a.z, sc.z, sh.z), 0.f); a.w = fmaxf(fmaf(a.w, sc.w, sh.w), 0.f);
+        }
+      }
 #pragma unroll
       for (int o = 0; o < O_MAX; ++o) {
-        const float dj = __shfl_sync(0xffffffffu, d[o], j);
-        acc[o][0] = fmaf(dj, a.x, acc[o][0]);
-        acc[o][1] = fmaf(dj, a.y, acc[o][1]);
+        const float dj = __shfl_sync(0xffffffffu, d[o], pj);  // dl of the pixel this half-warp is on (0 beyond npix)
+        acc[o][0] = fmaf(dj, a.x, acc[o][0]); acc[o][1] = fmaf(dj, a.y, acc[o][1]);
+        acc[o][2] = fmaf(dj, a.z, acc[o][2]); acc[o][3] = fmaf(dj, a.w, acc[o][3]);
       }
     }
   }
-  // block reduction over the 8 warps, then one atomic per (o, channel) and per o
+  // fold the two half-warps, then block reduction over the 8 warps, then one atomic per (o, channel) and per o
   __shared__ float red[8][O_MAX][64];
   __shared__ float redb[8][O_MAX];
 #pragma unroll
   for (int o = 0; o < O_MAX; ++o) {
-    red[warp][o][2 * lane] = acc[o][0];
-    red[warp][o][2 * lane + 1] = acc[o][1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[o][k] += __shfl_xor_sync(0xffffffffu, acc[o][k], 16);
+    if (half == 0) {
+      red[warp][o][c4] = acc[o][0]; red[warp][o][c4 + 1] = acc[o][1];
+      red[warp][o][c4 + 2] = acc[o][2]; red[warp][o][c4 + 3] = acc[o][3];
+    }
     const float s = warp_sum(dsum[o]);
     if (lane == 0) redb[warp][o] = s;
   }
@@ -277,7 +297,9 @@ int launch_predictor_bwd(const SrcDesc& src, int N, int H, int W, const float* w
   TNB_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * O, st));
   ProfScope prof(PROF_PRED, st, N, H, W, 64, O);
   const long long blocks_a = (npix * 4 + 255) / 256, blocks_w = ((npix + 31) / 32 + 7) / 8;
-  predictor_bwd_da_kernel<<<(int)std::min<long long>(blocks_a, 148 * 8), 256, 0, st>>>(npix, hw, wp, O, dy, y, dA);
+  const int grida = (int)std::min<long long>(blocks_a, 148 * 8);
+  if (O <= 8) predictor_bwd_da_kernel<8><<<grida, 256, 0, st>>>(npix, hw, wp, O, dy, y, dA);
+  else        predictor_bwd_da_kernel<kMaxPredO><<<grida, 256, 0, st>>>(npix, hw, wp, O, dy, y, dA);
   TNB_CHECK_CUDA(cudaGetLastError());
   const int gridw = (int)std::min<long long>(blocks_w, 148 * 4);
   if (O <= 8) predictor_bwd_dw_kernel<8><<<gridw, 256, 0, st>>>(src, npix, hw, O, dy, y, dwp, dbias);
