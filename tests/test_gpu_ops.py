@@ -269,6 +269,10 @@ def test_predictor_backward_shapes(n, h, w, o, affine):
     zt, scd, shd = G.nhwc(z), sc.to(G.DEV), sh.to(G.DEV)
     src = G.make_src(zt, _lib.SRC_AFFINE_RELU, scd, shd) if affine else G.make_src(zt)
     yd, dyd, wd = y_ref.detach().to(G.DEV).contiguous(), dy.to(G.DEV), wp.detach().to(G.DEV)
+    yf = torch.full((n, o, h, w), float("nan"), device=G.DEV)
+    bd = bp.detach().to(G.DEV)
+    _lib.check(L.tnb_conv1x1_bias_sigmoid_fwd(C.byref(src), n, h, w, wd.data_ptr(), bd.data_ptr(), o, yf.data_ptr(), G.st()))
+    assert G.max_abs(yf, y_ref) < 1e-5
     dA = torch.full((n, h, w, 64), float("nan"), device=G.DEV)
     dwp = torch.full((o, 64), float("nan"), device=G.DEV); dbp = torch.full((o,), float("nan"), device=G.DEV)
     _lib.check(L.tnb_conv1x1_bias_sigmoid_bwd(C.byref(src), n, h, w, wd.data_ptr(), o, dyd.data_ptr(), yd.data_ptr(),

@@ -131,6 +131,10 @@ int launch_bn_finalize(const float* part, int rows, double count, const float* g
 // Output is NCHW fp32, the layout the reference's callers consume (train.py:93, predict.py:140).
 // =============================================================================================
 static constexpr int kMaxPredO = 16;
+// 4 threads per pixel, 16 channels each, interleaved in float4 units (thread qd owns channels 16*i + 4*qd .. +3):
+// every load instruction of a warp reads whole 32-byte sectors (64 contiguous bytes per pixel); the 4 partial dot
+// products are folded with two shuffles and thread qd stores outputs o = qd, qd + 4, ...
+template <int O_MAX>
 __global__ void __launch_bounds__(256) predictor_fwd_kernel(SrcDesc src, int N, int H, int W,
                                                             const float* __restrict__ wp,
                                                             const float* __restrict__ bias, int O,
@@ -139,32 +143,55 @@ __global__ void __launch_bounds__(256) predictor_fwd_kernel(SrcDesc src, int N, 
   for (int i = threadIdx.x; i < O * 64; i += blockDim.x) sw[i] = wp[i];
   for (int i = threadIdx.x; i < O; i += blockDim.x) sw[kMaxPredO * 64 + i] = bias[i];
   __syncthreads();
+  const bool affine = src.mode != SRC_IDENTITY;
   const long long hw = (long long)H * W, npix = (long long)N * hw;
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix;
-       p += (long long)gridDim.x * blockDim.x) {
-    float a[64];
+  const long long total = (npix * 4 + 31) / 32 * 32;  // whole warps: the shuffles below need every lane
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < total; it += (long long)gridDim.x * blockDim.x) {
+    const long long p = it >> 2;
+    const int qd = (int)(it & 3);
+    const bool ok = p < npix;
+    float a[16];
 #pragma unroll
-    for (int c8 = 0; c8 < 8; ++c8) {
-      float v[8];
-      view_load8(src, (int)p, c8 * 8, v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) a[c8 * 8 + i] = v[i];
+    for (int i = 0; i < 4; ++i) {
+      const int c = 16 * i + 4 * qd;
+      float4 v = ok ? __ldg(reinterpret_cast<const float4*>(src.ptr + p * 64 + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (affine) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(src.scale + c));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(src.shift + c));
+        v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f); v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+        v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f); v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+      }
+      a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
     }
-    const long long n = p / hw, r = p - n * hw;
-    for (int o = 0; o < O; ++o) {
-      float s = sw[kMaxPredO * 64 + o];
+    float s[O_MAX];
 #pragma unroll
-      for (int c = 0; c < 64; ++c) s = fmaf(a[c], sw[o * 64 + c], s);
-      y[(n * O + o) * hw + r] = 1.f / (1.f + expf(-s));
+    for (int o = 0; o < O_MAX; ++o) {
+      s[o] = 0.f;
+      if (o < O) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s[o] = fmaf(a[i], sw[o * 64 + (i >> 2) * 16 + qd * 4 + (i & 3)], s[o]);
+      }
+      s[o] += __shfl_xor_sync(0xffffffffu, s[o], 1);
+      s[o] += __shfl_xor_sync(0xffffffffu, s[o], 2);
+    }
+    if (ok) {
+      const long long n = p / hw, r = p - n * hw;
+#pragma unroll
+      for (int o = 0; o < O_MAX; ++o)
+        if ((o & 3) == qd && o < O) y[(n * O + o) * hw + r] = 1.f / (1.f + expf(-(s[o] + sw[kMaxPredO * 64 + o])));
     }
   }
 }
 int launch_predictor_fwd(const SrcDesc& src, int N, int H, int W, const float* wp, const float* bias, int O,
                          float* y, cudaStream_t st) {
   TNB_REQUIRE(src.C == 64 && O <= kMaxPredO, "predictor: expects 64 input channels and out_dim <= %d", kMaxPredO);
+  TNB_REQUIRE((src.mode == SRC_IDENTITY || src.mode == SRC_AFFINE_RELU) && src.Hs == H && src.Ws == W,
+              "predictor: the activation must be a same-resolution identity / BN+ReLU source (mode %d)", src.mode);
   const long long npix = (long long)N * H * W;
   ProfScope prof(PROF_PRED, st, N, H, W, 64, O);
-  predictor_fwd_kernel<<<min(cdiv(npix, 256), 148 * 8), 256, 0, st>>>(src, N, H, W, wp, bias, O, y);
+  const int grid = (int)std::min<long long>((npix * 4 + 255) / 256, 148 * 8);
+  if (O <= 8) predictor_fwd_kernel<8><<<grid, 256, 0, st>>>(src, N, H, W, wp, bias, O, y);
+  else        predictor_fwd_kernel<kMaxPredO><<<grid, 256, 0, st>>>(src, N, H, W, wp, bias, O, y);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
