@@ -353,8 +353,8 @@ struct GraphCache {
   uint64_t clock = 0;
   int failures = 0;                  // capture failures: after a few, stop trying
   long long captures = 0, replays = 0, eager = 0;
-  cudaStream_t side = nullptr;       // capture stream (the caller's stream may be the legacy default stream, which
-                                     // cannot be captured); the instantiated graph is launched into the caller's stream
+  cudaStream_t side[64] = {};        // per-device capture stream (the caller's stream may be the legacy default stream,
+                                     // which cannot be captured); the instantiated graph is launched into the caller's
 };
 constexpr int kMaxGraphs = 8, kMaxSeen = 32;
 GraphCache g_graphs;
@@ -392,18 +392,21 @@ int run_maybe_graphed(uint64_t key, cudaStream_t st, F&& enqueue) {
     ++G.eager;
     return enqueue(st);
   }
-  // second sighting: capture on the side stream, instantiate, launch into the caller's stream
-  if (G.side == nullptr && cudaStreamCreateWithFlags(&G.side, cudaStreamNonBlocking) != cudaSuccess) {
+  // second sighting: capture on this device's side stream, instantiate, launch into the caller's stream
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); ++G.eager; return enqueue(st); }
+  cudaStream_t& side = G.side[dev];
+  if (side == nullptr && cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError(); ++G.failures; ++G.eager; side = nullptr;
+    return enqueue(st);
+  }
+  if (cudaStreamBeginCapture(side, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
     cudaGetLastError(); ++G.failures; ++G.eager;
     return enqueue(st);
   }
-  if (cudaStreamBeginCapture(G.side, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-    cudaGetLastError(); ++G.failures; ++G.eager;
-    return enqueue(st);
-  }
-  const int rc = enqueue(G.side);
+  const int rc = enqueue(side);
   cudaGraph_t graph = nullptr;
-  const cudaError_t ce = cudaStreamEndCapture(G.side, &graph);
+  const cudaError_t ce = cudaStreamEndCapture(side, &graph);
   if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
     cudaGetLastError(); ++G.failures;
     if (graph) cudaGraphDestroy(graph);
