@@ -134,6 +134,11 @@ int tnb_conv3x3_dgrad_bnreduce(const tnb_view_t* view, const uint16_t* wpack, fl
  * ([N,H,W,cout] logical); the view operand is split to bf16 on the fly. */
 int tnb_conv3x3_wgrad(const tnb_view_t* view, const void* dz_presplit, float* dw_oihw, int cout, int cin_real,
                       int terms, int variant, void* stream);
+/* The same with a scratch buffer of 9 * cout * view->C floats: the split-K partials are reduced tap-major (coalesced
+ * 128-byte reductions instead of 32 scattered ones per warp instruction) and a second small kernel writes dw_oihw with
+ * plain stores (dw need not be zeroed; the scratch is zeroed by the call). What tnb_tracknet_backward uses. */
+int tnb_conv3x3_wgrad_ws(const tnb_view_t* view, const void* dz_presplit, float* dw_oihw, int cout, int cin_real,
+                         int terms, int variant, float* scratch, void* stream);
 
 /* BatchNorm2d statistics -> fused affine + running-stat update (model.py:9; torch defaults eps 1e-5,
  * momentum 0.1, unbiased running_var). training==0 uses the running statistics (model.eval()). */

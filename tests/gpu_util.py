@@ -83,11 +83,19 @@ def unsplit(buf, shape_nhwc):
     return v[..., 0, :] + v[..., 1, :]
 
 
-def wgrad3x3(view, dz_nhwc, cout, cin_real, terms=3, variant=0):
-    """production configuration: dz pre-split to bf16, view split on the fly."""
+def wgrad3x3(view, dz_nhwc, cout, cin_real, terms=3, variant=0, scratch=False):
+    """production configuration: dz pre-split to bf16, view split on the fly. scratch=True: the tap-major accumulation
+    buffer + scatter path that tnb_tracknet_backward uses (dw starts as NaN: every element must be written)."""
     L = lib()
-    dw = torch.zeros((cout, cin_real, 3, 3), device=DEV)
     dzs = presplit(dz_nhwc)
+    if scratch:
+        dw = torch.full((cout, cin_real, 3, 3), float("nan"), device=DEV)
+        ws = torch.full((9 * cout * view.C,), float("nan"), device=DEV)
+        _lib.check(L.tnb_conv3x3_wgrad_ws(C.byref(view), dzs.data_ptr(), dw.data_ptr(), cout, cin_real, terms, variant,
+                                          ws.data_ptr(), st()))
+        torch.cuda.synchronize()
+        return dw
+    dw = torch.zeros((cout, cin_real, 3, 3), device=DEV)
     _lib.check(L.tnb_conv3x3_wgrad(C.byref(view), dzs.data_ptr(), dw.data_ptr(), cout, cin_real, terms, variant, st()))
     torch.cuda.synchronize()
     return dw

@@ -183,6 +183,8 @@ def test_conv3x3_wgrad(n, h, w, cin, cin_real, cout, terms):
     t, d = G.nhwc(x), G.nhwc(dz)
     dw = G.wgrad3x3(G.make_view([G.make_src(t)], n, h, w), d, cout, cin_real, terms=terms)
     assert G.rel_err(dw, wt.grad) < (2e-4 if terms == 3 else 2e-2)
+    dw_ws = G.wgrad3x3(G.make_view([G.make_src(t)], n, h, w), d, cout, cin_real, terms=terms, scratch=True)
+    assert G.rel_err(dw_ws, wt.grad) < (2e-4 if terms == 3 else 2e-2)
 
 
 @pytest.mark.parametrize("terms", [3, 1])
@@ -211,6 +213,10 @@ def test_conv3x3_wgrad_tap_stacked(n, h, w, cin, cin_real, terms):
     dw_generic = G.wgrad3x3(G.make_view([src], n, h, w), d, cout, cin_real, terms=terms, variant=32)
     assert G.rel_err(dw_generic, wt.grad) < tol
     assert G.rel_err(dw, dw_generic) < (1e-5 if terms == 3 else 1e-3)
+    # tap-major accumulation buffer + scatter (what the network's backward pass uses), both kernels
+    for variant in (0, 32):
+        dw_ws = G.wgrad3x3(G.make_view([src], n, h, w), d, cout, cin_real, terms=terms, variant=variant, scratch=True)
+        assert G.rel_err(dw_ws, wt.grad) < tol
 
 
 @pytest.mark.parametrize("c_up,c_skip,cout", [(128, 64, 64), (64, 64, 64), (256, 128, 128), (512, 256, 256)])

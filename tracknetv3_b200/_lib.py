@@ -59,6 +59,7 @@ SIGNATURES = {
     "tnb_conv3x3_dgrad_bnreduce_rows": (i32, [i32, i32, i32, i32, i32, i32]),
     "tnb_conv3x3_dgrad_bnreduce": (i32, [C.POINTER(View), vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
     "tnb_conv3x3_wgrad": (i32, [C.POINTER(View), vp, vp, i32, i32, i32, i32, vp]),
+    "tnb_conv3x3_wgrad_ws": (i32, [C.POINTER(View), vp, vp, i32, i32, i32, i32, vp, vp]),
     "tnb_presplit_bf16": (i32, [vp, vp, i64, i32, vp]),
     "tnb_view_presplit": (i32, [C.POINTER(View), vp, i32, vp]),
     "tnb_bn_finalize": (i32, [vp, i32, f64, vp, vp, vp, vp, f32, f32, i32, vp, vp, vp, vp, i32, vp]),

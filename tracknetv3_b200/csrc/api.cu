@@ -66,6 +66,10 @@ int tnb_conv3x3_wgrad(const tnb_view_t* view, const void* dz_presplit, float* dw
                       int variant, void* stream) {
   return launch_wgrad3x3(*view, dz_presplit, dw, cout, cin_real, terms, variant, ST(stream));
 }
+int tnb_conv3x3_wgrad_ws(const tnb_view_t* view, const void* dz_presplit, float* dw, int cout, int cin_real, int terms,
+                         int variant, float* scratch, void* stream) {
+  return launch_wgrad3x3(*view, dz_presplit, dw, cout, cin_real, terms, variant, ST(stream), scratch);
+}
 int tnb_bn_finalize(const float* part, int rows, double count, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, float momentum, float eps, int training, float* scale,
                     float* shift, float* mean, float* invstd, int c, void* stream) {

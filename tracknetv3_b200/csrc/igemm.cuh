@@ -159,7 +159,11 @@ int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, floa
                    int nterms, int fmt, int variant, cudaStream_t st, const BnBwdFuse* fuse = nullptr);
 int conv3x3_num_stat_rows(int N, int H, int W, int Cin, int Cout, int nterms, bool bn_bwd_fused = false);
 
+// ws: optional scratch of 9 * Cout * view.C floats. With it the split-K partials are reduced tap-major, where the lanes of a
+// warp hit consecutive addresses (one 128-byte reduction per instruction instead of 32 scattered ones), and a small
+// kernel then writes dw_oihw (plain stores: dw need not be zeroed). Without it the partials are added into dw_oihw
+// directly (the caller zeroes it).
 int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw_oihw, int Cout, int CinReal, int nterms,
-                    int variant, cudaStream_t st);
+                    int variant, cudaStream_t st, float* ws = nullptr);
 
 }  // namespace tnb

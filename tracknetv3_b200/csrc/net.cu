@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 #include "prof.cuh"
 #include <string.h>
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 #include <vector>
@@ -61,6 +62,7 @@ bool bn_reduce_fusable(int p) {
 }
 struct Plan {
   LayerBuf L[kLayers];
+  float* wgrad_ws;  // scratch: tap-major split-K accumulation buffer of the current layer's weight gradient
   uint8_t* vsplit;  // scratch: the current layer's input view materialised as pre-split bf16 (largest: 192 ch @ full res)
   float* amax_all;  // [kLayers] max|dz| per layer, raised atomically by bn_bwd apply
   float* xin;
@@ -117,6 +119,9 @@ int build_plan(const tnb_tracknet_cfg_t& c, void* ws, Plan* P) {
       vmax = e > vmax ? e : vmax;
     }
     P->vsplit = b.take<uint8_t>(vmax * 4);
+    size_t wmax = 0;
+    for (int l = 0; l < kLayers; ++l) wmax = std::max(wmax, (size_t)9 * kDefs[l].cout * layer_cin(c, l));
+    P->wgrad_ws = b.take<float>(wmax);
   }
   P->xin = b.take<float>(npix0 * P->cpad);
   P->dA_pred = b.take<float>(npix0 * 64);
@@ -239,8 +244,11 @@ static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const 
   auto run_wgrad = [&](int layer, const ViewDesc& pv) -> int {
     LayerBuf& W = P.L[layer];
     float* dw = (float*)grads[layer * 3 + 0];
-    TNB_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)W.cout * W.cin_real * 9, st));
-    return launch_wgrad3x3(pv, W.dz, dw, W.cout, W.cin_real, c.bwd_terms, (c.variant >> 2) & 3, st);
+    if (c.variant & 512) {  // variant bit 512: add the split-K partials straight into dw (ablation of the tap-major buffer)
+      TNB_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)W.cout * W.cin_real * 9, st));
+      return launch_wgrad3x3(pv, W.dz, dw, W.cout, W.cin_real, c.bwd_terms, (c.variant >> 2) & 3, st);
+    }
+    return launch_wgrad3x3(pv, W.dz, dw, W.cout, W.cin_real, c.bwd_terms, (c.variant >> 2) & 3, st, P.wgrad_ws);
   };
   auto plain_presplit_view = [&](int layer) {
     const LayerBuf& W = P.L[layer];
@@ -480,7 +488,9 @@ int tracknet_num_launches(const tnb_tracknet_cfg_t& c, int backward) {
   int emitted = 0;  // wgrad operands written by the BatchNorm-backward apply pass: no view_presplit launch
   for (int l = 0; l < kLayers; ++l) emitted += wgrad_operand_from_bn_bwd(c, l) ? 1 : 0;
   // + second view_presplit of the 3 decoder concat layers, + one memset per weight gradient is not a kernel
-  return 1 + kLayers * 5 - fused - emitted + (kLayers - 1) * 2 + 3;
+  const int scatter = (c.variant & 512) ? 0 : kLayers;  // tap-major weight-gradient buffer -> OIHW, one per layer
+  // predictor backward is two kernels
+  return 2 + kLayers * 5 - fused - emitted + (kLayers - 1) * 2 + 3 + scatter;
 }
 
 }  // namespace tnb

@@ -20,6 +20,7 @@
 #include "igemm.cuh"
 #include "prof.cuh"
 #include <type_traits>
+#include <algorithm>
 
 namespace tnb {
 
@@ -38,6 +39,7 @@ struct WgradArgs {
   int ndy;  // filter rows per CTA: 3 when all 9 taps fit in TMEM (9 * NT <= 512), else 1 (grid.x carries dy)
   int tiles_h, tiles_w, ktiles, ktiles_per_cta, ncot, ncit;
   int ci_tile_base;  // first input-channel tile of this launch (concat views with two gather modes use two launches)
+  float* ws;         // optional tap-major accumulation buffer [9][Cin_view][Cout] (see launch_wgrad_scatter); nullptr: dw
 };
 
 template <int MODE> TNB_DEVINL int view_off_t(const SrcDesc& s, int n, int h, int w) {
@@ -314,7 +316,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int ci = ci0 + col0 + j;
-              if (ci < a.CinReal)
+              if (a.ws != nullptr)  // lanes = consecutive output channels: one 128-byte reduction per warp instruction
+                atomicAdd(a.ws + ((size_t)(dy0 * 3 + t) * V.C + ci) * a.Cout + co0 + row, __uint_as_float(rg[j]));
+              else if (ci < a.CinReal)
                 atomicAdd(a.dw + ((size_t)(co0 + row) * a.CinReal + ci) * 9 + dy0 * 3 + t, __uint_as_float(rg[j]));
             }
           }
@@ -357,6 +361,7 @@ struct WgradSArgs {
   int N, H, W, C, Cout, CinReal, P /*planes per ci tile: 8 or 4*/, nterms, ncit, ncot;
   int tiles_h, tiles_w, ktiles, ktiles_per_cta;
   int ca;  // cp.async.ca instead of .cg (experiment)
+  float* ws;  // optional tap-major accumulation buffer [9][Cout][C] (see launch_wgrad_scatter); nullptr: dw
 };
 
 __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __grid_constant__ WgradSArgs a) {
@@ -533,8 +538,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __g
           tmem_ld_wait();
           if (live) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              atomicAdd(a.dw + ((size_t)(co0 + col0 + j) * a.CinReal + ci) * 9 + dy * 3 + dx, __uint_as_float(rg[j]));
+            for (int j = 0; j < 16; ++j) {
+              if (a.ws != nullptr)  // lanes = consecutive input channels: one 128-byte reduction per warp instruction
+                atomicAdd(a.ws + ((size_t)(dy * 3 + dx) * a.Cout + co0 + col0 + j) * a.C + ci, __uint_as_float(rg[j]));
+              else
+                atomicAdd(a.dw + ((size_t)(co0 + col0 + j) * a.CinReal + ci) * 9 + dy * 3 + dx, __uint_as_float(rg[j]));
+            }
           }
         }
       }
@@ -559,9 +568,30 @@ static bool stacked_applicable(const ViewDesc& view, int Cout) {
   return ok0 && ok1;
 }
 
+// dw[co][ci][tap] = ws[...]: the tap-major accumulation buffer back to the reference's OIHW layout (plain stores).
+// layout 0: ws[tap][ci][co] (generic kernel), layout 1: ws[tap][co][ci] (stacked kernel); ci over the padded view channels.
+__global__ void __launch_bounds__(256) wgrad_scatter_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cout,
+                                                            int Cin, int CinReal, int layout) {
+  const long long total = (long long)9 * Cout * Cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i / ((long long)Cout * Cin));
+    const int r = (int)(i - (long long)tap * Cout * Cin);
+    const int co = layout == 0 ? r % Cout : r / Cin, ci = layout == 0 ? r / Cout : r % Cin;
+    if (ci < CinReal) dw[((size_t)co * CinReal + ci) * 9 + tap] = ws[i];
+  }
+}
+static int launch_wgrad_scatter(const float* ws, float* dw, int Cout, int Cin, int CinReal, int layout, cudaStream_t st) {
+  const long long total = (long long)9 * Cout * Cin;
+  wgrad_scatter_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 8), 256, 0, st>>>(ws, dw, Cout, Cin, CinReal,
+                                                                                              layout);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static int launch_wgrad3x3_stacked(const ViewDesc& view, const void* dz_presplit, float* dw, int Cout, int CinReal,
-                                   int nterms, cudaStream_t st) {
+                                   int nterms, cudaStream_t st, float* ws) {
   WgradSArgs a;
+  a.ws = ws;
   a.view = reinterpret_cast<const uint8_t*>(view.s[0].ptr); a.dz = (const uint8_t*)dz_presplit; a.dw = dw;
   a.view1 = reinterpret_cast<const uint8_t*>(view.C0 < view.C ? view.s[1].ptr : view.s[0].ptr);
   a.C0 = view.C0; a.Cs0 = view.s[0].C; a.Cs1 = view.C0 < view.C ? view.s[1].C : view.s[0].C;
@@ -584,8 +614,10 @@ static int launch_wgrad3x3_stacked(const ViewDesc& view, const void* dz_presplit
   TNB_REQUIRE(smem <= 232448, "wgrad3x3 (stacked): shared memory plan too large (%zu)", smem);
   TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_stacked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(PROF_WGRAD, st, view.N, view.H, view.W, view.C, Cout);
+  if (ws != nullptr) TNB_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 9 * (size_t)Cout * view.C, st));
   wgrad3x3_stacked_kernel<<<dim3(gx, splits), kThreads, smem, st>>>(a);
   TNB_CHECK_CUDA(cudaGetLastError());
+  if (ws != nullptr) return launch_wgrad_scatter(ws, dw, Cout, view.C, CinReal, 1, st);
   return 0;
 }
 
@@ -599,11 +631,13 @@ static int pick_nt(int cin, int c0) {
 }
 
 int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, int Cout, int CinReal, int nterms,
-                    int variant, cudaStream_t st) {
+                    int variant, cudaStream_t st, float* ws) {
   TNB_REQUIRE(view.C % 32 == 0 && Cout % 64 == 0, "wgrad3x3: unsupported channels Cin=%d Cout=%d", view.C, Cout);
   if (!(variant & 32) && stacked_applicable(view, Cout))  // variant bit 32: force the generic kernel (tests, ablation)
-    return launch_wgrad3x3_stacked(view, dz_presplit, dw, Cout, CinReal, nterms, st);
+    return launch_wgrad3x3_stacked(view, dz_presplit, dw, Cout, CinReal, nterms, st, ws);
   WgradArgs a;
+  a.ws = ws;
+  if (ws != nullptr) TNB_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 9 * (size_t)Cout * view.C, st));
   a.view = view; a.dz = (const uint8_t*)dz_presplit; a.dw = dw; a.Cout = Cout; a.CinReal = CinReal;
   a.nterms = nterms; a.variant = variant | (cp_async_ca_env() ? 256 : 0); a.ci_tile_base = 0;
   a.NT = pick_nt(view.C, view.C0);
@@ -664,6 +698,7 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
     if (int rc = dispatch(mode1, a1, a.ncot * a1.ncit * (3 / a.ndy))) return rc;
   }
   TNB_CHECK_CUDA(cudaGetLastError());
+  if (ws != nullptr) return launch_wgrad_scatter(ws, dw, Cout, view.C, CinReal, 0, st);
   return 0;
 }
 
