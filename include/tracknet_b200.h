@@ -198,13 +198,20 @@ int tnb_inpaintnet_bwd(const float* coords, const float* mask, const void* const
 /* Frame preprocessing (dataset.py:435-461, 783-812): Pillow's antialiased BICUBIC `img.resize((wd, hd))` of nimg uint8
  * images [nimg][hs][ws][c] (22-bit fixed point, horizontal pass then vertical pass, bit-exact against Pillow), then
  * HWC -> CHW, / 255 and stacking: image i lands in out + (i / per_sample) * sample_stride +
- * ((i % per_sample) * c + chan_off) * hd * wd, as float planes. Coefficient tables (device memory) as Pillow's
+ * ((i % per_sample) * frame_stride + chan_off) * hd * wd, as c float planes (frame_stride = channels every frame
+ * occupies in the stack: c, or 4 for bg_mode 'subtract_concat'). Coefficient tables (device memory) as Pillow's
  * precompute_coeffs / normalize_coeffs_8bpc build them: bounds = (first tap, tap count) per output sample, kk = ksize
  * ints per output sample; hbounds/hkk NULL when ws == wd (Pillow skips that pass); the vertical table must always
  * be given (identity table when hs == hd). tmp: nimg * hs * wd * c bytes of scratch. */
 int tnb_resize_frames(const uint8_t* src, int nimg, int hs, int ws, int c, const int* hbounds, const int* hkk, int hksize,
                       const int* vbounds, const int* vkk, int vksize, int hd, int wd, uint8_t* tmp, float* out,
-                      int per_sample, long long sample_stride, int chan_off, void* stream);
+                      int per_sample, long long sample_stride, int chan_off, int frame_stride, void* stream);
+
+/* Background-difference image of bg_mode 'subtract' / 'subtract_concat' (dataset.py:438, 442):
+ * out[i][y][x] = uint8 cast (numpy semantics: truncate, wrap modulo 256) of sum_c |frames[i][y][x][c] - median[y][x][c]|,
+ * frames uint8 [nimg][hs][ws][3], median float64 [hs][ws][3]. The result goes through tnb_resize_frames with c = 1. */
+int tnb_bg_subtract_u8(const uint8_t* frames, const double* median, long long nimg, int hs, int ws, uint8_t* out,
+                       void* stream);
 
 /* Per-map statistics of the evaluation bookkeeping (test.py:159-169): conf[m] = max of y_pred map m inside
  * boxes[m] = (x, y, w, h) (0 for an empty box); true_any[m] = 1 iff map m of y_true has a value > 0 (y_true and

@@ -246,9 +246,11 @@ def gen_input_pipeline():
 
         class S:  # stand-in for the dataset object
             pass
-        for bg in ("", "concat"):
-            s_ = S(); s_.bg_mode, s_.median, s_.HEIGHT, s_.WIDTH, s_.seq_len = bg, med, H, W, L
-            out[f"{name}/{bg or 'none'}"] = env["process"](s_, imgs)
+        for bg in ("", "concat", "subtract", "subtract_concat"):
+            s_ = S(); s_.bg_mode, s_.HEIGHT, s_.WIDTH, s_.seq_len = bg, H, W, L
+            s_.median = med if bg == "concat" else med_src      # dataset.py:103-109: resized CHW only for 'concat'
+            with np.errstate(invalid="ignore"):
+                out[f"{name}/{bg or 'none'}"] = env["process"](s_, imgs)
         out[f"{name}/imgs"], out[f"{name}/median_src"], out[f"{name}/median"] = imgs, med_src, med
     np.savez_compressed(f"{OUT}/input_pipeline.npz", **out)
 

@@ -87,14 +87,32 @@ def resize_bicubic_u8(img, out_w, out_h):
     return a[:, :, 0] if img.ndim == 2 else a
 
 
-def process_frames(imgs, median_chw=None, width=512, height=288):
-    """`Video_IterableDataset.__process__` / the frame branch of `Shuttlecock_Trajectory_Dataset.__getitem__` for
-    bg_mode '' and 'concat' (reference dataset.py:435-461, 783-812): every frame resized, HWC -> CHW, stacked along the
-    channel axis, the (already resized, CHW) median image first when given, divided by 255 in float64."""
+def process_frames(imgs, median_chw=None, width=512, height=288, bg_mode=None, median_src=None):
+    """`Video_IterableDataset.__process__` / the frame branch of `Shuttlecock_Trajectory_Dataset.__getitem__`
+    (reference dataset.py:435-461, 783-812): every frame resized, HWC -> CHW, stacked along the channel axis, divided by
+    255 in float64. bg_mode (default: 'concat' when median_chw is given, else ''):
+      ''                plain RGB frames;
+      'concat'          the (already resized, CHW, uint8) median image first, then the frames;
+      'subtract'        one channel per frame: sum_c |frame - median_src| cast to uint8 (numpy's wrap-around cast of the
+                        float64 sum, as the reference does it), then resized as an 8-bit grey image;
+      'subtract_concat' per frame R, G, B, difference.
+    median_src: float64 (Hs, Ws, 3) median at the source resolution (dataset.py:108-109) for the subtract modes."""
+    if bg_mode is None:
+        bg_mode = 'concat' if median_chw is not None else ''
     frames = np.array([]).reshape(0, height, width)
     for img in imgs:
-        frames = np.concatenate((frames, np.moveaxis(resize_bicubic_u8(img, width, height), -1, 0)), axis=0)
-    if median_chw is not None:
+        if bg_mode in ('subtract', 'subtract_concat'):
+            with np.errstate(invalid='ignore'):
+                diff = np.sum(np.absolute(img - median_src), 2).astype('uint8')
+            diff = resize_bicubic_u8(diff, width, height).reshape(1, height, width)
+        if bg_mode == 'subtract':
+            img = diff
+        else:
+            img = np.moveaxis(resize_bicubic_u8(img, width, height), -1, 0)
+            if bg_mode == 'subtract_concat':
+                img = np.concatenate((img, diff), axis=0)
+        frames = np.concatenate((frames, img), axis=0)
+    if bg_mode == 'concat':
         frames = np.concatenate((median_chw, frames), axis=0)
     frames /= 255.
     return frames

@@ -482,6 +482,9 @@ def test_frame_preprocessing_vs_reference_fixture_and_pillow_oracle(golden_dir):
         m = fp.prepare_median(g[f"{name}/median_src"])
         assert torch.equal(m.cpu(), torch.from_numpy(med))
         assert torch.equal(fp.process(x, m).cpu()[0], torch.from_numpy(g[f"{name}/concat"]).float())
+        for bg in ("subtract", "subtract_concat"):   # difference image incl. numpy's wrap-around uint8 cast
+            got = fp.process(x, g[f"{name}/median_src"], bg_mode=bg).cpu()[0]
+            assert torch.equal(got, torch.from_numpy(g[f"{name}/{bg}"]).float()), (name, bg)
     rng = np.random.default_rng(8)
     for hs, ws, h, w, n, l in ((720, 1280, 288, 512, 2, 3), (288, 512, 288, 512, 1, 2), (720, 1280, 360, 640, 1, 2),
                                (288, 400, 288, 512, 1, 1)):
@@ -493,3 +496,5 @@ def test_frame_preprocessing_vs_reference_fixture_and_pillow_oracle(golden_dir):
             assert torch.equal(got[i], want), (hs, ws, h, w, i)
     with pytest.raises(RuntimeError):
         fp.process(torch.zeros(1, 1, 10, 10, 3, dtype=torch.uint8, device=G.DEV))
+    with pytest.raises(ValueError):
+        fp.process(torch.zeros(1, 1, 288, 400, 3, dtype=torch.uint8, device=G.DEV), bg_mode="subtract")

@@ -204,6 +204,9 @@ def test_input_pipeline_matches_reference_and_pillow(golden_dir):
         H, W = med.shape[1:]
         assert np.array_equal(P.process_frames(imgs, None, W, H), g[f"{name}/none"])
         assert np.array_equal(P.process_frames(imgs, med, W, H), g[f"{name}/concat"])
+        for bg in ("subtract", "subtract_concat"):
+            got = P.process_frames(imgs, None, W, H, bg_mode=bg, median_src=g[f"{name}/median_src"])
+            assert np.array_equal(got, g[f"{name}/{bg}"]), (name, bg)
         med2 = np.moveaxis(P.resize_bicubic_u8(g[f"{name}/median_src"].astype("uint8"), W, H), -1, 0)
         assert np.array_equal(med2, med)
     Image = pytest.importorskip("PIL.Image")

@@ -78,7 +78,8 @@ SIGNATURES = {
     "tnb_heatmap_decode": (i32, [vp, i32, f32, i32, i32, i32, vp, vp, vp]),
     "tnb_inpaintnet_fwd": (i32, [vp, vp, C.POINTER(vp), i32, i32, vp, vp]),
     "tnb_inpaintnet_bwd": (i32, [vp, vp, C.POINTER(vp), vp, C.POINTER(vp), i32, i32, vp, vp]),
-    "tnb_resize_frames": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, i32, i32, i32, vp, vp, i32, C.c_longlong, i32, vp]),
+    "tnb_resize_frames": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, i32, i32, i32, vp, vp, i32, C.c_longlong, i32, i32, vp]),
+    "tnb_bg_subtract_u8": (i32, [vp, vp, C.c_longlong, i32, i32, vp, vp]),
     "tnb_eval_stats": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp]),
     "tnb_temporal_ensemble": (i32, [vp, vp, vp, C.POINTER(C.c_float), i32, C.c_longlong, i32, i32, i32, i32, vp]),
     "tnb_tracknet_workspace_bytes": (sz, [C.POINTER(TrackNetCfg)]),

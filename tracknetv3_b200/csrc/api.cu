@@ -136,9 +136,13 @@ int tnb_inpaintnet_bwd(const float* coords, const float* mask, const void* const
 
 int tnb_resize_frames(const uint8_t* src, int nimg, int hs, int ws, int c, const int* hbounds, const int* hkk, int hksize,
                       const int* vbounds, const int* vkk, int vksize, int hd, int wd, uint8_t* tmp, float* out,
-                      int per_sample, long long sample_stride, int chan_off, void* stream) {
+                      int per_sample, long long sample_stride, int chan_off, int frame_stride, void* stream) {
   return launch_resize_frames(src, nimg, hs, ws, c, hbounds, hkk, hksize, vbounds, vkk, vksize, hd, wd, tmp, out, per_sample,
-                              sample_stride, chan_off, ST(stream));
+                              sample_stride, chan_off, frame_stride, ST(stream));
+}
+int tnb_bg_subtract_u8(const uint8_t* frames, const double* median, long long nimg, int hs, int ws, uint8_t* out,
+                       void* stream) {
+  return launch_bg_subtract(frames, median, nimg, hs, ws, out, ST(stream));
 }
 int tnb_eval_stats(const float* y_pred, const float* y_true, const int* boxes_xywh, int nmaps, int h, int w,
                    float* conf, int* true_any, void* stream) {

@@ -1223,11 +1223,11 @@ __global__ void __launch_bounds__(256) resize_h_kernel(const uint8_t* __restrict
   }
 }
 // vertical pass fused with HWC -> CHW, / 255 and the channel stacking: tmp [nimg][hs][wd][C] u8 ->
-// out[(img / per_sample) * sample_stride + ((img % per_sample) * C + chan_off + c) * hd * wd + yy * wd + xx] float
+// out[(img / per_sample) * sample_stride + ((img % per_sample) * frame_stride + chan_off + c) * hd * wd + yy * wd + xx]
 __global__ void __launch_bounds__(256) resize_v_stack_kernel(const uint8_t* __restrict__ tmp, int nimg, int hs, int wd, int hd,
                                                              int C, const int* __restrict__ bounds, const int* __restrict__ kk,
                                                              int ksize, float* __restrict__ out, int per_sample,
-                                                             long long sample_stride, int chan_off) {
+                                                             long long sample_stride, int chan_off, int frame_stride) {
   const long long total = (long long)nimg * hd * wd;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int xx = (int)(i % wd);
@@ -1243,15 +1243,39 @@ __global__ void __launch_bounds__(256) resize_v_stack_kernel(const uint8_t* __re
       for (int c = 0; c < C; ++c) acc[c] += (int)p[(long long)y * wd * C + c] * w;
     }
     float* o = out + (long long)(img / per_sample) * sample_stride +
-               ((long long)(img % per_sample) * C + chan_off) * hd * wd + (long long)yy * wd + xx;
+               ((long long)(img % per_sample) * frame_stride + chan_off) * hd * wd + (long long)yy * wd + xx;
     // the reference divides the float64 array by 255. and casts to float32 at train.py:86 / predict.py:171
     for (int c = 0; c < C; ++c) o[(long long)c * hd * wd] = __double2float_rn((double)clip8_fixed(acc[c]) / 255.0);
   }
 }
+// Background subtraction of bg_mode 'subtract' / 'subtract_concat' (dataset.py:438, 442, 797, 801):
+// np.sum(np.absolute(img - median), 2).astype('uint8') - float64 arithmetic, truncation toward zero, and the wrap-around
+// of numpy's double -> uint8 cast for sums above 255 (the reference feeds that image to PIL as it is).
+__global__ void __launch_bounds__(256) bg_subtract_kernel(const uint8_t* __restrict__ frames, const double* __restrict__ median,
+                                                          long long nimg, long long hw, uint8_t* __restrict__ out) {
+  const long long total = nimg * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i % hw;
+    double v = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v += fabs((double)frames[i * 3 + c] - median[p * 3 + c]);
+    out[i] = (uint8_t)((long long)v & 0xff);
+  }
+}
+int launch_bg_subtract(const uint8_t* frames, const double* median, long long nimg, int hs, int ws, uint8_t* out,
+                       cudaStream_t st) {
+  if (nimg == 0) return 0;
+  const long long total = nimg * hs * ws;
+  bg_subtract_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(frames, median, nimg,
+                                                                                            (long long)hs * ws, out);
+  TNB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 int launch_resize_frames(const uint8_t* src, int nimg, int hs, int ws, int C, const int* hbounds, const int* hkk, int hksize,
                          const int* vbounds, const int* vkk, int vksize, int hd, int wd, uint8_t* tmp, float* out,
-                         int per_sample, long long sample_stride, int chan_off, cudaStream_t st) {
-  TNB_REQUIRE(C >= 1 && C <= 4 && per_sample >= 1, "resize_frames: channels %d / frames per sample %d", C, per_sample);
+                         int per_sample, long long sample_stride, int chan_off, int frame_stride, cudaStream_t st) {
+  TNB_REQUIRE(C >= 1 && C <= 4 && per_sample >= 1 && frame_stride >= C, "resize_frames: channels %d / frames per sample %d / stride %d",
+              C, per_sample, frame_stride);
   if (nimg == 0) return 0;
   const uint8_t* vsrc = src;
   if (hbounds != nullptr) {  // widths differ: horizontal pass first (Resample.c ImagingResampleInner)
@@ -1265,7 +1289,7 @@ int launch_resize_frames(const uint8_t* src, int nimg, int hs, int ws, int C, co
   }
   const long long total = (long long)nimg * hd * wd;
   resize_v_stack_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(
-      vsrc, nimg, hs, wd, hd, C, vbounds, vkk, vksize, out, per_sample, sample_stride, chan_off);
+      vsrc, nimg, hs, wd, hd, C, vbounds, vkk, vksize, out, per_sample, sample_stride, chan_off, frame_stride);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -45,7 +45,9 @@ int launch_inpaint_fwd(const float* coords, const float* mask, const InpaintPara
                        cudaStream_t st);
 int launch_resize_frames(const uint8_t* src, int nimg, int hs, int ws, int C, const int* hbounds, const int* hkk, int hksize,
                          const int* vbounds, const int* vkk, int vksize, int hd, int wd, uint8_t* tmp, float* out,
-                         int per_sample, long long sample_stride, int chan_off, cudaStream_t st);
+                         int per_sample, long long sample_stride, int chan_off, int frame_stride, cudaStream_t st);
+int launch_bg_subtract(const uint8_t* frames, const double* median, long long nimg, int hs, int ws, uint8_t* out,
+                       cudaStream_t st);
 int launch_eval_stats(const float* y_pred, const float* y_true, const int* boxes, int nmaps, int H, int W, float* conf,
                       int* true_any, cudaStream_t st);
 int launch_temporal_ensemble(const float* state, const float* pred, float* out, const float* weight_host, int L,

@@ -72,7 +72,7 @@ class FramePreprocessor:
         self.hb, self.hk = (dev(hb), dev(hk)) if src_w != width else (None, None)
         self.vb, self.vk = dev(vb), dev(vk)
 
-    def _run(self, imgs, out, per_sample, chan_off):
+    def _run(self, imgs, out, per_sample, chan_off, frame_stride=None):
         lib = _lib.load()
         _lib.require_cuda(imgs, out)
         if imgs.dtype != torch.uint8 or imgs.dim() != 4 or imgs.shape[1] != self.src_h or imgs.shape[2] != self.src_w:
@@ -84,7 +84,8 @@ class FramePreprocessor:
             imgs.data_ptr(), n, self.src_h, self.src_w, c,
             self.hb.data_ptr() if self.hb is not None else None, self.hk.data_ptr() if self.hk is not None else None,
             self.hk.shape[1] if self.hk is not None else 0, self.vb.data_ptr(), self.vk.data_ptr(), self.vk.shape[1],
-            self.h, self.w, tmp.data_ptr(), out.data_ptr(), per_sample, out.stride(0), chan_off, _lib.stream_ptr()))
+            self.h, self.w, tmp.data_ptr(), out.data_ptr(), per_sample, out.stride(0), chan_off,
+            c if frame_stride is None else frame_stride, _lib.stream_ptr()))
 
     def prepare_median(self, median_hwc):
         """dataset.py:104-107 / :776-779: the median frame (any float or uint8 (Hs, Ws, 3)) as uint8, resized, CHW."""
@@ -94,11 +95,37 @@ class FramePreprocessor:
         self._run(m.unsqueeze(0), out, 1, 0)
         return torch.round(out[0] * 255).to(torch.uint8)
 
-    def process(self, imgs, median=None):
+    def _difference(self, flat, median_src):
+        """np.sum(np.absolute(img - median), 2).astype('uint8') for every frame (dataset.py:438, 442): (n, Hs, Ws, 1)."""
+        lib = _lib.load()
+        med = torch.as_tensor(np.asarray(median_src, dtype=np.float64)).to(self.device).contiguous()
+        if tuple(med.shape) != (self.src_h, self.src_w, 3):
+            raise RuntimeError(f"median must be ({self.src_h}, {self.src_w}, 3) at the source resolution, got {tuple(med.shape)}")
+        diff = torch.empty((flat.shape[0], self.src_h, self.src_w, 1), dtype=torch.uint8, device=self.device)
+        _lib.check(lib.tnb_bg_subtract_u8(flat.data_ptr(), med.data_ptr(), flat.shape[0], self.src_h, self.src_w,
+                                          diff.data_ptr(), _lib.stream_ptr()))
+        return diff
+
+    def process(self, imgs, median=None, bg_mode=None):
+        """bg_mode: '' | 'concat' (median = prepare_median(...) output) | 'subtract' | 'subtract_concat' (median = the
+        float64 (Hs, Ws, 3) median at the source resolution, dataset.py:108-109). Default: 'concat' if a median is
+        given, else ''. Output channels: 3L, 3L + 3, L, 4L (utils/general.py:66-74 get_model's in_dim)."""
+        if bg_mode is None:
+            bg_mode = 'concat' if median is not None else ''
+        if bg_mode not in ('', 'concat', 'subtract', 'subtract_concat'):
+            raise ValueError(f"unknown bg_mode {bg_mode!r}")
+        if bg_mode != '' and median is None:
+            raise ValueError(f"bg_mode {bg_mode!r} needs the median image")
+        _lib.require_cuda(imgs)
         n, l = imgs.shape[0], imgs.shape[1]
-        extra = 3 if median is not None else 0
-        out = torch.empty((n, 3 * l + extra, self.h, self.w), dtype=torch.float32, device=self.device)
-        self._run(imgs.reshape(n * l, *imgs.shape[2:]), out, l, extra)
-        if median is not None:
+        flat = imgs.reshape(n * l, *imgs.shape[2:]).contiguous()
+        per_frame = {'': 3, 'concat': 3, 'subtract': 1, 'subtract_concat': 4}[bg_mode]
+        extra = 3 if bg_mode == 'concat' else 0
+        out = torch.empty((n, per_frame * l + extra, self.h, self.w), dtype=torch.float32, device=self.device)
+        if bg_mode in ('subtract', 'subtract_concat'):
+            self._run(self._difference(flat, median), out, l, per_frame - 1, per_frame)
+        if bg_mode != 'subtract':
+            self._run(flat, out, l, extra, per_frame)
+        if bg_mode == 'concat':
             out[:, :3] = (median.to(self.device).double() / 255.0).float()
         return out
