@@ -90,3 +90,83 @@ def predict_ensemble(ensemble, indices, y_pred=None, c_pred=None, img_scaler=(1,
         ens = ens.masked_fill(th_mask[:, None], 0.)
         return predict(ens_i, c_pred=ens.unsqueeze(1), img_scaler=img_scaler)
     raise ValueError('Invalid input')
+
+
+def run_video(frames_u8, tracknet, inpaintnet=None, seq_len=8, bg_mode='concat', batch_size=16, eval_mode='weight',
+              img_scaler=(1, 1)):
+    """ The data path of the reference's `predict.py` __main__ (:110-301) for one video held in memory, entirely on the
+        GPU: frames -> Pillow-exact resize / stack (FramePreprocessor) -> TrackNet -> temporal ensemble -> heatmap decode
+        [-> InpaintNet on the decoded trajectory -> temporal ensemble]. Video file decoding, the csv / video writers and
+        `generate_inpaint_mask` of the reference stay what they are (host code around this function).
+
+        Args:
+            frames_u8 (torch.Tensor): (T, Hs, Ws, 3) uint8 RGB frames of the video (CUDA or host)
+            tracknet, inpaintnet: models from utils.general.get_model, already .cuda().eval()
+        Returns:
+            (tracknet_pred_dict, inpaint_pred_dict or None)
+    """
+    import tracknetv3_b200 as T
+    frames_u8 = torch.as_tensor(frames_u8).cuda()
+    t, hs, ws = frames_u8.shape[0], frames_u8.shape[1], frames_u8.shape[2]
+    fp = T.FramePreprocessor(hs, ws, HEIGHT, WIDTH)
+    median = None
+    if bg_mode:
+        med_src = torch.median(frames_u8.float(), dim=0).values.cpu().numpy()   # the reference: np.median(frame_arr, 0)
+        median = fp.prepare_median(med_src) if bg_mode == 'concat' else med_src
+    num_sample = t - seq_len + 1
+    ens = TemporalEnsemble(seq_len, eval_mode, num_sample)
+    pred = {'Frame': [], 'X': [], 'Y': [], 'Visibility': []}
+    with torch.no_grad():
+        for s0 in range(0, num_sample, batch_size):
+            ids = list(range(s0, min(s0 + batch_size, num_sample)))
+            imgs = torch.stack([frames_u8[s:s + seq_len] for s in ids])           # sliding_step 1, (B, L, Hs, Ws, 3)
+            idx = torch.tensor([[[0, s + f] for f in range(seq_len)] for s in ids])
+            y = tracknet(fp.process(imgs, median, bg_mode=bg_mode))
+            d = predict_ensemble(ens, idx, y_pred=y, img_scaler=img_scaler)
+            for k in pred:
+                pred[k].extend(d[k])
+    if inpaintnet is None:
+        return pred, None
+    # InpaintNet pass over the decoded trajectory (predict.py:214-301); every missing detection is inpainted here, the
+    # reference narrows that down with generate_inpaint_mask (host logic, out of this function's scope)
+    w_, h_ = WIDTH * img_scaler[0], HEIGHT * img_scaler[1]
+    coor = torch.tensor([[x / w_, y_ / h_] for x, y_ in zip(pred['X'], pred['Y'])], dtype=torch.float32).cuda()
+    mask = torch.tensor([[1.0 - v] for v in pred['Visibility']], dtype=torch.float32).cuda()
+    li = 16 if t >= 16 else t
+    n_in = t - li + 1
+    ens_c = TemporalEnsemble(li, eval_mode, n_in)
+    out = {'Frame': [], 'X': [], 'Y': [], 'Visibility': []}
+    from utils.general import COOR_TH
+    with torch.no_grad():
+        for s0 in range(0, n_in, batch_size):
+            ids = list(range(s0, min(s0 + batch_size, n_in)))
+            c = torch.stack([coor[s:s + li] for s in ids])
+            m = torch.stack([mask[s:s + li] for s in ids])
+            idx = torch.tensor([[[0, s + f] for f in range(li)] for s in ids])
+            ci = inpaintnet(c, m)
+            ci = ci * m + c * (1 - m)
+            ci = ci.masked_fill(((ci[:, :, 0] < COOR_TH) & (ci[:, :, 1] < COOR_TH))[:, :, None], 0.)
+            d = predict_ensemble(ens_c, idx, c_pred=ci, img_scaler=img_scaler)
+            for k in out:
+                out[k].extend(d[k])
+    return pred, out
+
+
+if __name__ == '__main__':
+    import argparse
+    from utils.general import get_model
+    parser = argparse.ArgumentParser(description='synthetic end-to-end run of the GPU predict path (no checkpoints / video files)')
+    parser.add_argument('--frames', type=int, default=40)
+    parser.add_argument('--batch_size', type=int, default=16)
+    parser.add_argument('--eval_mode', type=str, default='weight', choices=['weight', 'average'])
+    args = parser.parse_args()
+    torch.manual_seed(0)
+    video = torch.randint(0, 40, (args.frames, 360, 640, 3), dtype=torch.uint8)
+    for i in range(args.frames):                                       # a bright ball crossing a dark noisy court
+        video[i, 100 + 3 * i:108 + 3 * i, 50 + 10 * i:58 + 10 * i] = 250
+    tracknet = get_model('TrackNet', 8, 'concat').cuda().eval()
+    inpaintnet = get_model('InpaintNet').cuda().eval()
+    p1, p2 = run_video(video, tracknet, inpaintnet, batch_size=args.batch_size, eval_mode=args.eval_mode,
+                       img_scaler=(640 / WIDTH, 360 / HEIGHT))
+    print(f"TrackNet: {len(p1['Frame'])} frames, {sum(p1['Visibility'])} visible (random weights); "
+          f"InpaintNet: {len(p2['Frame'])} frames")
