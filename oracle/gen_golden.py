@@ -255,6 +255,32 @@ def gen_input_pipeline():
     np.savez_compressed(f"{OUT}/input_pipeline.npz", **out)
 
 
+def gen_inpaint_mask():
+    """EXECUTE the reference's `generate_inpaint_mask` (test.py:223-258) on random trajectories: visibility runs of
+    random length (gaps at the start, in the middle, at the end, gaps of length 1, all visible, none visible) with
+    y coordinates on both sides of the height threshold."""
+    env = {"np": np}
+    extract_functions(f"{REF}/test.py", {"generate_inpaint_mask"}, env)
+    rng = np.random.default_rng(41)
+    ys, vs, ms, ths = [], [], [], []
+    for case in range(300):
+        n = int(rng.integers(1, 40))
+        vis = np.ones(n, dtype=np.int64)
+        pos = 0
+        while pos < n:
+            run = int(rng.integers(1, 8))
+            vis[pos:pos + run] = rng.integers(0, 2)
+            pos += run
+        if case % 17 == 0:
+            vis[:] = case % 2
+        y = rng.integers(0, 288, n) * vis
+        th = float(rng.choice([30.0, 14.4, 100.0]))
+        m = env["generate_inpaint_mask"]({"Y": y.tolist(), "Visibility": vis.tolist()}, th_h=th)
+        pad = lambda a: np.pad(np.asarray(a), (0, 40 - n), constant_values=-1)
+        ys.append(pad(y)); vs.append(pad(vis)); ms.append(pad(m)); ths.append(th)
+    np.savez_compressed(f"{OUT}/inpaint_mask.npz", y=np.stack(ys), vis=np.stack(vs), mask=np.stack(ms), th=np.array(ths))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -262,6 +288,10 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "inpaint_train":  # regenerate only this fixture
         gen_inpaint_train(refmodel)
         print("inpaintnet_train.npz written")
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "inpaint_mask":
+        gen_inpaint_mask()
+        print("inpaint_mask.npz written")
         return
     if len(sys.argv) > 1 and sys.argv[1] == "input_pipeline":
         gen_input_pipeline()
@@ -376,6 +406,7 @@ def main():
     gen_temporal_ensemble()
     gen_evaluate()
     gen_input_pipeline()
+    gen_inpaint_mask()
 
     # ---- small host-side pieces: ensemble weights, mixup ----
     ew = {f"weight_{L}": env["get_ensemble_weight"](L, "weight").numpy() for L in (1, 4, 7, 8)}

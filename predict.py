@@ -96,8 +96,8 @@ def run_video(frames_u8, tracknet, inpaintnet=None, seq_len=8, bg_mode='concat',
               img_scaler=(1, 1)):
     """ The data path of the reference's `predict.py` __main__ (:110-301) for one video held in memory, entirely on the
         GPU: frames -> Pillow-exact resize / stack (FramePreprocessor) -> TrackNet -> temporal ensemble -> heatmap decode
-        [-> InpaintNet on the decoded trajectory -> temporal ensemble]. Video file decoding, the csv / video writers and
-        `generate_inpaint_mask` of the reference stay what they are (host code around this function).
+        [-> generate_inpaint_mask -> InpaintNet on the decoded trajectory -> temporal ensemble]. Video file decoding
+        and the csv / video writers of the reference stay what they are (host code around this function).
 
         Args:
             frames_u8 (torch.Tensor): (T, Hs, Ws, 3) uint8 RGB frames of the video (CUDA or host)
@@ -127,11 +127,12 @@ def run_video(frames_u8, tracknet, inpaintnet=None, seq_len=8, bg_mode='concat',
                 pred[k].extend(d[k])
     if inpaintnet is None:
         return pred, None
-    # InpaintNet pass over the decoded trajectory (predict.py:214-301); every missing detection is inpainted here, the
-    # reference narrows that down with generate_inpaint_mask (host logic, out of this function's scope)
+    # InpaintNet pass over the decoded trajectory (predict.py:214-301): gaps selected by generate_inpaint_mask with the
+    # reference's threshold of 5 % of the image height (:216)
+    from test import generate_inpaint_mask
     w_, h_ = WIDTH * img_scaler[0], HEIGHT * img_scaler[1]
     coor = torch.tensor([[x / w_, y_ / h_] for x, y_ in zip(pred['X'], pred['Y'])], dtype=torch.float32).cuda()
-    mask = torch.tensor([[1.0 - v] for v in pred['Visibility']], dtype=torch.float32).cuda()
+    mask = torch.tensor(generate_inpaint_mask(pred, th_h=h_ * 0.05), dtype=torch.float32).reshape(-1, 1).cuda()
     li = 16 if t >= 16 else t
     n_in = t - li + 1
     ens_c = TemporalEnsemble(li, eval_mode, n_in)

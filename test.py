@@ -109,3 +109,37 @@ def evaluate(indices, y_true=None, y_pred=None, c_true=None, c_pred=None, tolera
         del pred_dict['Y_GT']
         del pred_dict['Visibility_GT']
     return pred_dict
+
+
+def generate_inpaint_mask(pred_dict, th_h=30):
+    """ Generate inpaint mask from a predicted trajectory (drop-in for reference test.py:223-258): a run of invisible
+        frames is marked for inpainting when the ball was inside the court on both sides of it - y above `th_h` at the
+        last visible frame before the run (the run must start after index 1) and at the first visible frame after it - or,
+        for a run at the very start, at the first visible frame after it. A run that reaches the last frame is never
+        marked, like in the reference, whose scan treats the last index as the end of every run.
+
+        Args:
+            pred_dict (Dict): {'Frame': [], 'X': [], 'Y': [], 'Visibility': []}
+            th_h (float): height threshold (pixels) for the y coordinate
+        Returns:
+            inpaint_mask (List[int])
+    """
+    y = np.asarray(pred_dict['Y'])
+    vis = np.asarray(pred_dict['Visibility'])
+    n = len(vis)
+    mask = np.zeros_like(y)
+    start = 0
+    while n > 0:
+        gone = np.flatnonzero(vis[start:n - 1] != 1)          # first invisible frame; the last index stands in for "none"
+        i = start + int(gone[0]) if len(gone) else n - 1
+        back = np.flatnonzero(vis[i:n - 1] != 0)              # first visible frame after it; ditto
+        j = i + int(back[0]) if len(back) else n - 1
+        if j == i:
+            break
+        if i == 0:
+            if y[j] > th_h:
+                mask[:j] = 1
+        elif i > 1 and y[i - 1] > th_h and y[j] > th_h:
+            mask[i:j] = 1
+        start = j
+    return mask.tolist()

@@ -135,3 +135,15 @@ def test_evaluate_coordinate_mode_matches_reference_fixture():
         assert np.array_equal(np.asarray(d[k], dtype=np.float64), g["co/" + k]), k
     with pytest.raises(ValueError):
         TT.evaluate(torch.from_numpy(g["indices"]))
+
+
+def test_generate_inpaint_mask_matches_reference_fixture():
+    """test.generate_inpaint_mask (host logic between the TrackNet and InpaintNet passes, predict.py:216) vs the
+    reference's function executed on 300 random trajectories by oracle/gen_golden.py."""
+    import test as TT
+    g = np.load(os.path.join(ROOT, "tests", "golden", "inpaint_mask.npz"))
+    for y, vis, mask, th in zip(g["y"], g["vis"], g["mask"], g["th"]):
+        n = int((vis >= 0).sum())
+        got = TT.generate_inpaint_mask({"Y": y[:n].tolist(), "Visibility": vis[:n].tolist()}, th_h=float(th))
+        assert got == mask[:n].tolist(), (y[:n], vis[:n])
+    assert g["mask"].max() == 1 and (g["mask"] == 1).sum() > 200      # the fixture does exercise marked runs
