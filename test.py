@@ -143,3 +143,59 @@ def generate_inpaint_mask(pred_dict, th_h=30):
             mask[i:j] = 1
         start = j
     return mask.tolist()
+
+
+inpaintnet_eval_types = ['inpaint', 'reconstruct', 'baseline']
+
+
+def get_eval_res(pred_dict):
+    """ np.array([TP, TN, FP1, FP2, FN]) counted from pred_dict['Type'] (reference test.py:289-306). """
+    type_res = np.asarray(pred_dict['Type'])
+    return np.array([float((type_res == pred_types_map[t]).sum()) for t in pred_types])
+
+
+def _res_dict(confusion):
+    from utils.metric import get_metric
+    TP, TN, FP1, FP2, FN = confusion
+    accuracy, precision, recall, f1, miss_rate = get_metric(TP, TN, FP1, FP2, FN)
+    return {'TP': TP, 'TN': TN, 'FP1': FP1, 'FP2': FP2, 'FN': FN, 'accuracy': accuracy, 'precision': precision,
+            'recall': recall, 'f1': f1, 'miss_rate': miss_rate}
+
+
+def eval_tracknet(model, data_loader, param_dict):
+    """ Evaluate TrackNet (validation loop of reference test.py:308-368, called from train.py:276): mean WBCE loss and
+        the TP/TN/FP1/FP2/FN counts with derived metrics. Forward, loss and the heatmap decode inside `evaluate` run on the
+        GPU; per batch one loss scalar and 44 B per frame come back to the host. """
+    from utils.metric import WBCELoss
+    model.eval()
+    losses = []
+    confusion = np.zeros(5)
+    for step, (i, x, y, _, _) in enumerate(data_loader):
+        x, y = x.float().cuda(), y.float().cuda()
+        with torch.no_grad():
+            y_pred = model(x)
+            losses.append(WBCELoss(y_pred, y).item())
+        confusion += get_eval_res(evaluate(i, y_true=y, y_pred=y_pred, tolerance=param_dict['tolerance']))
+    return float(np.mean(losses)), _res_dict(confusion)
+
+
+def eval_inpaintnet(model, data_loader, param_dict):
+    """ Evaluate InpaintNet (reference test.py:370-443): masked MSE loss and, for the three comparisons of the reference
+        ('inpaint': refined vs truth, 'reconstruct': refined vs TrackNet's prediction, 'baseline': prediction vs truth),
+        the TP/TN/FP1/FP2/FN counts with derived metrics. """
+    from utils.general import COOR_TH
+    model.eval()
+    losses = []
+    confusion = {t: np.zeros(5) for t in inpaintnet_eval_types}
+    for step, (i, coor_pred, coor, _, _, inpaint_mask) in enumerate(data_loader):
+        coor_pred, coor, inpaint_mask = coor_pred.float().cuda(), coor.float().cuda(), inpaint_mask.float().cuda()
+        with torch.no_grad():
+            coor_inpaint = model(coor_pred, inpaint_mask)
+            coor_inpaint = coor_inpaint * inpaint_mask + coor_pred * (1 - inpaint_mask)
+            losses.append(torch.nn.MSELoss()(coor_inpaint * inpaint_mask, coor * inpaint_mask).item())
+            th_mask = (coor_inpaint[:, :, 0] < COOR_TH) & (coor_inpaint[:, :, 1] < COOR_TH)
+            coor_inpaint = coor_inpaint.masked_fill(th_mask[:, :, None], 0.)
+        pairs = {'inpaint': (coor, coor_inpaint), 'reconstruct': (coor_pred, coor_inpaint), 'baseline': (coor, coor_pred)}
+        for t, (c_true, c_pred) in pairs.items():
+            confusion[t] += get_eval_res(evaluate(i, c_true=c_true, c_pred=c_pred, tolerance=param_dict['tolerance']))
+    return float(np.mean(losses)), {t: _res_dict(confusion[t]) for t in inpaintnet_eval_types}

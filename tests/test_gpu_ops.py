@@ -517,3 +517,43 @@ def test_run_video_end_to_end_flow():
     p3, none = P.run_video(video, get_model('TrackNet', 8, 'subtract_concat').to(G.DEV).eval(), None,
                            bg_mode='subtract_concat', batch_size=3)
     assert none is None and p3['Frame'] == list(range(t))
+
+
+def test_eval_loops_vs_oracle():
+    """test.eval_tracknet / eval_inpaintnet (validation loops of the reference, test.py:308-443) on prepared
+    predictions: loss = mean of the per-batch losses, confusion counts = the oracle's evaluate() over all frames."""
+    import test as TT
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "evaluate.npz"))
+    y_true, y_pred, idx = (torch.from_numpy(g[k]) for k in ("y_true", "y_pred", "indices"))
+
+    class Stub(torch.nn.Module):  # a "model" that returns the prepared heatmaps of the batch it is given
+        def forward(self, x):
+            return y_pred[x[:, 0, 0, 0].long().cpu()].to(G.DEV)
+    batches = [(idx[a:a + 2], torch.arange(a, min(a + 2, 3)).float().reshape(-1, 1, 1, 1), y_true[a:a + 2], None, None)
+               for a in (0, 2)]
+    loss, res = TT.eval_tracknet(Stub(), batches, {"tolerance": 4, "verbose": False})
+    want = np.zeros(5); losses = []
+    for i, x, y, _, _ in batches:
+        sel = x[:, 0, 0, 0].long()
+        want += TT.get_eval_res(D.evaluate(i.numpy(), y_true=y.numpy(), y_pred=y_pred[sel].numpy(), tolerance=4))
+        losses.append(O.wbce_loss(y_pred[sel], y).item())
+    assert [res[k] for k in ("TP", "TN", "FP1", "FP2", "FN")] == want.tolist()
+    assert abs(loss - np.mean(losses)) < 1e-6
+    assert res["accuracy"] == (want[0] + want[1]) / want.sum()
+    # InpaintNet loop with the real module (random weights) against the oracle forward + oracle evaluate
+    torch.manual_seed(2)
+    net = T.InpaintNet().to(G.DEV)
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    gen = torch.Generator().manual_seed(3)
+    coor = torch.rand(4, 16, 2, generator=gen)
+    mask = (torch.rand(4, 16, 1, generator=gen) < 0.3).float()
+    coor_pred = (coor + 0.003 * torch.randn(4, 16, 2, generator=gen)) * (1 - mask)
+    idx2 = torch.stack([torch.stack([torch.zeros(16), torch.arange(16 * s, 16 * s + 16).float()], 1) for s in range(4)])
+    loss2, res2 = TT.eval_inpaintnet(net, [(idx2, coor_pred, coor, None, None, mask)], {"tolerance": 4, "verbose": False})
+    ci = O.inpaintnet_forward(sd, coor_pred, mask)
+    ci = ci * mask + coor_pred * (1 - mask)
+    assert abs(loss2 - F.mse_loss(ci * mask, coor * mask).item()) < 1e-6
+    ci = O.inpaint_blend(coor_pred, O.inpaintnet_forward(sd, coor_pred, mask), mask)
+    for t, (ct, cp) in {"inpaint": (coor, ci), "reconstruct": (coor_pred, ci), "baseline": (coor, coor_pred)}.items():
+        w = TT.get_eval_res(D.evaluate(idx2.numpy(), c_true=ct.numpy(), c_pred=cp.numpy(), tolerance=4))
+        assert [res2[t][k] for k in ("TP", "TN", "FP1", "FP2", "FN")] == w.tolist(), t
