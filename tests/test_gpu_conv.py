@@ -28,6 +28,9 @@ def _rand(*shape, seed=0, scale=1.0):
     (1, 16, 16, 256, 512),   # two N tiles
     (1, 16, 32, 64, 192),    # BN = 192
     (1, 16, 16, 96, 384),    # 2 x BN 192
+    (1, 36, 64, 256, 512),   # bottleneck shape: 8-row x 16-column tiles (36 = 4.5 of them), two N tiles
+    (1, 40, 16, 64, 64),     # 32-row x 16-column tiles (MT = 4 stacked down the image), ragged rows
+    (1, 8, 32, 128, 256),    # one row of 8 x 16 tiles
 ])
 def test_conv3x3_forward_identity_view(n, h, w, cin, cout, terms):
     x = _rand(n, cin, h, w, seed=1)

@@ -38,6 +38,8 @@ struct ConvArgs {
   const float *bz, *bsc, *bsh, *bmu, *bis;
   int Cout, BN, MT, SA, SB, G, nbuf, nterms, variant, tmem_cols;  // G: filter taps per weight stage (1 or 3)
   int tiles_h, tiles_w, ntiles, nwork;
+  int tall;  // tile orientation: 0 = 16 rows x 8*MT columns (halo tile row-major), 1 = 8*MT rows x 16 columns
+             // (halo tile column-major: the 8-pixel core-matrix groups then run down the image)
 };
 
 // 31-shuffle transpose-reduce: on return lane j holds the sum over the 32 lanes of v[j].
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
               for (int tg = 0; tg < a.G; ++tg) {
                 const int t = t0 + tg;
                 const int dy = t / 3, dx = t - dy * 3;
-                const uint64_t a_tap = a_st + (uint64_t)(dy * PITCH + dx + 8 * mt);
+                const uint64_t a_tap = a_st + (uint64_t)((a.tall ? dx * PITCH + dy : dy * PITCH + dx) + 8 * mt);
                 const uint64_t b_tap = b_st + (uint64_t)(tg * b_tap16);
 #pragma unroll
                 for (int kk = 0; kk < 2; ++kk) {
@@ -222,12 +224,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
       const int tw = tile % a.tiles_w; tile /= a.tiles_w;
       const int th = tile % a.tiles_h;
       const int n = tile / a.tiles_h;
-      const int h0 = th * 16, w0 = tw * 8 * MT, n0 = nt * BN;
+      const int h0 = a.tall ? th * 8 * MT : th * 16, w0 = a.tall ? tw * 16 : tw * 8 * MT, n0 = nt * BN;
       const int buf = k % a.nbuf;
       const uint32_t use = (uint32_t)(k / a.nbuf);
       if (BWD) {  // pull this tile's slice of the producer's z towards L2 while the MMAs of the tile are still running
         for (int mt = 0; mt < MT; ++mt) {
-          const int h = h0 + r, w = w0 + 8 * mt + cc;
+          const int h = a.tall ? h0 + 8 * mt + cc : h0 + r, w = a.tall ? w0 + r : w0 + 8 * mt + cc;
           if (h < V.H && w < V.W) {
             const float* zp = a.bz + ((size_t)(n * V.H + h) * V.W + w) * a.Cout + n0;
             for (int col0 = 0; col0 < BN; col0 += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(zp + col0));
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
       for (int col0 = 0; col0 < BN; col0 += 32) {
         float csum = 0.f, csq = 0.f;
         for (int mt = 0; mt < MT; ++mt) {
-          const int h = h0 + r, w = w0 + 8 * mt + cc;
+          const int h = a.tall ? h0 + 8 * mt + cc : h0 + r, w = a.tall ? w0 + r : w0 + 8 * mt + cc;
           const bool valid = (h < V.H) && (w < V.W) && !(a.variant & 16);
           float zz[BWD ? 32 : 1];
           if (BWD) {  // the producer's z for these 32 channels: issued before the TMEM load so the latencies overlap
@@ -324,10 +326,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
       const int tw = tile % a.tiles_w; tile /= a.tiles_w;
       const int th = tile % a.tiles_h;
       const int n = tile / a.tiles_h;
-      const int h0 = th * 16, w0 = tw * 8 * MT;
+      const int h0 = a.tall ? th * 8 * MT : th * 16, w0 = a.tall ? tw * 16 : tw * 8 * MT;
       asm volatile("bar.sync 2, 192;" ::: "memory");  // previous tile's table is no longer read
       for (int p = ftid; p < HALO_PX; p += kFillThreads) {
-        const int hr = p / PITCH, hc = p - hr * PITCH;
+        const int major = p / PITCH, minor = p - major * PITCH;  // halo pixel index = major * PITCH + minor
+        const int hr = a.tall ? minor : major, hc = a.tall ? major : minor;
         const int h = h0 - 1 + hr, w = w0 - 1 + hc;
         int2 e = make_int2(-1, -1);
         if (h >= 0 && h < V.H && w >= 0 && w < V.W) {
@@ -460,8 +463,18 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
   // re-stream the weights twice as often, which only pays while the weight set is small: Cin <= 512.
   // TNB_CONV_PLAN=0 restores the widest tile (tools/ablate_plan.py).
   static const int plan_mode = [] { const char* e = getenv("TNB_CONV_PLAN"); return e ? atoi(e) : 1; }();
-  if (plan_mode == 1 && Cin <= 512) while (MT > 1 && 2 * MT * BN > 512) MT >>= 1;
-  while (MT > 1 && 8 * (MT - 1) >= W) --MT;  // do not tile wider than the image
+  if (plan_mode != 0 && Cin <= 512) while (MT > 1 && 2 * MT * BN > 512) MT >>= 1;
+  // Orientation: M = 128 rows of the MMA are 16 groups of 8 consecutive pixels. Groups along W stacked over 16 image rows
+  // give a 16 x 8*MT tile; groups along H stacked over 16 image columns give an 8*MT x 16 tile. Take the one that pads
+  // the image less: at 72 x 128 and 36 x 64 (H = 4.5 and 2.25 tiles of 16 rows) the tall-group tile wastes 0 / 10 %
+  // of the MMAs instead of 10 / 25 %. TNB_CONV_PLAN=2 forces the first form.
+  auto padded = [&](int mt, bool tall) {
+    const long long th = tall ? (H + 8 * mt - 1) / (8 * mt) * (8 * mt) : (H + 15) / 16 * 16;
+    const long long tw = tall ? (W + 15) / 16 * 16 : (W + 8 * mt - 1) / (8 * mt) * (8 * mt);
+    return th * tw;
+  };
+  const bool tall = plan_mode != 2 && padded(MT, true) < padded(MT, false);
+  while (MT > 1 && 8 * (MT - 1) >= (tall ? H : W)) --MT;  // do not tile wider (taller) than the image
   int SA = 2, SB = 0, G = 1;
   size_t smem = 0;
   const int mt_max = MT;
@@ -492,8 +505,9 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
   plan->nbuf = (2 * MT * BN <= 512) ? 2 : 1;
   plan->tmem_cols = pow2_cols(plan->nbuf * MT * BN);
   plan->smem_bytes = smem;
-  plan->tiles_h = (H + 15) / 16;
-  plan->tiles_w = (W + 8 * MT - 1) / (8 * MT);
+  plan->tall = tall ? 1 : 0;
+  plan->tiles_h = tall ? (H + 8 * MT - 1) / (8 * MT) : (H + 15) / 16;
+  plan->tiles_w = tall ? (W + 15) / 16 : (W + 8 * MT - 1) / (8 * MT);
   (void)N;
   return 0;
 }
@@ -520,7 +534,7 @@ int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, floa
     a.bz = fuse->z; a.bsc = fuse->scale; a.bsh = fuse->shift; a.bmu = fuse->mean; a.bis = fuse->invstd;
   }
   a.Cout = Cout; a.BN = p.BN; a.MT = p.MT; a.SA = p.SA; a.SB = p.SB; a.G = p.G; a.nbuf = p.nbuf; a.nterms = nterms;
-  a.variant = variant | (cp_async_ca_env() ? 256 : 0); a.tmem_cols = p.tmem_cols; a.tiles_h = p.tiles_h; a.tiles_w = p.tiles_w;
+  a.variant = variant | (cp_async_ca_env() ? 256 : 0); a.tmem_cols = p.tmem_cols; a.tiles_h = p.tiles_h; a.tiles_w = p.tiles_w; a.tall = p.tall;
   a.ntiles = view.N * p.tiles_h * p.tiles_w;
   a.nwork = a.ntiles * (Cout / p.BN);
   const int grid = a.nwork < num_sms() ? a.nwork : num_sms();

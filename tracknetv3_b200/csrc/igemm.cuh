@@ -144,6 +144,7 @@ struct ConvPlan {
   int BN, MT, SA, SB, G, nbuf, tmem_cols;
   size_t smem_bytes;
   int tiles_h, tiles_w;
+  int tall;  // tile orientation, see conv3x3_plan
 };
 // fmt: 0 = fp16 split, 1 = bf16 split. nterms: 1 (single pass) or 3 (hi*hi + lo*hi + hi*lo).
 // bn_bwd_fused: reserve the per-channel constant table of the fused BatchNorm-backward reduction (dgrad epilogue)
