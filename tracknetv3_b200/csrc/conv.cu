@@ -463,7 +463,7 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
   // re-stream the weights twice as often, which only pays while the weight set is small: Cin <= 512.
   // TNB_CONV_PLAN=0 restores the widest tile (tools/ablate_plan.py).
   static const int plan_mode = [] { const char* e = getenv("TNB_CONV_PLAN"); return e ? atoi(e) : 1; }();
-  if (plan_mode != 0 && Cin <= 512) while (MT > 1 && 2 * MT * BN > 512) MT >>= 1;
+  if (plan_mode != 0 && (Cin <= 512 || plan_mode == 3)) while (MT > 1 && 2 * MT * BN > 512) MT >>= 1;
   // Orientation: M = 128 rows of the MMA are 16 groups of 8 consecutive pixels. Groups along W stacked over 16 image rows
   // give a 16 x 8*MT tile; groups along H stacked over 16 image columns give an 8*MT x 16 tile. Take the one that pads
   // the image less: at 72 x 128 and 36 x 64 (H = 4.5 and 2.25 tiles of 16 rows) the tall-group tile wastes 0 / 10 %
