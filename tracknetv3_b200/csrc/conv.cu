@@ -460,10 +460,11 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
   if (MT > 4) MT = 4;
   // Two accumulator buffers in TMEM (2 * MT * BN <= 512 columns) let the epilogue of tile i overlap the MMAs of tile
   // i + 1; with one buffer it is exposed (7-17 % of the layer, measured: profiles/r1_summary.md 6). Narrower tiles
-  // re-stream the weights twice as often, which only pays while the weight set is small: Cin <= 512.
-  // TNB_CONV_PLAN=0 restores the widest tile (tools/ablate_plan.py).
+  // re-stream the weights twice as often; with the tile orientation below removing the padded tile rows that still
+  // pays even for the 768-channel layer (0.669 -> 0.604 ms). TNB_CONV_PLAN=0 restores the widest tile, =2 keeps the
+  // double buffering but forces the row-major orientation (tools/ablate_plan.py).
   static const int plan_mode = [] { const char* e = getenv("TNB_CONV_PLAN"); return e ? atoi(e) : 1; }();
-  if (plan_mode != 0 && (Cin <= 512 || plan_mode == 3)) while (MT > 1 && 2 * MT * BN > 512) MT >>= 1;
+  if (plan_mode != 0) while (MT > 1 && 2 * MT * BN > 512) MT >>= 1;
   // Orientation: M = 128 rows of the MMA are 16 groups of 8 consecutive pixels. Groups along W stacked over 16 image rows
   // give a 16 x 8*MT tile; groups along H stacked over 16 image columns give an 8*MT x 16 tile. Take the one that pads
   // the image less: at 72 x 128 and 36 x 64 (H = 4.5 and 2.25 tiles of 16 rows) the tall-group tile wastes 0 / 10 %
