@@ -14,29 +14,25 @@ COOR_TH = DELTA_T * 50
 IMG_FORMAT = 'png'
 
 
+# input channels of TrackNet per bg_mode: (channels per frame, extra channels for the median image)
+_FRAME_CHANNELS = {'subtract': (1, 0), 'subtract_concat': (4, 0), 'concat': (3, 3)}
+
+
 def get_model(model_name, seq_len=None, bg_mode=None):
-    """ Create model by name and the configuration parameter (same table as reference :66-78). """
-    if model_name == 'TrackNet':
-        if bg_mode == 'subtract':
-            model = TrackNet(in_dim=seq_len, out_dim=seq_len)
-        elif bg_mode == 'subtract_concat':
-            model = TrackNet(in_dim=seq_len * 4, out_dim=seq_len)
-        elif bg_mode == 'concat':
-            model = TrackNet(in_dim=(seq_len + 1) * 3, out_dim=seq_len)
-        else:
-            model = TrackNet(in_dim=seq_len * 3, out_dim=seq_len)
-    elif model_name == 'InpaintNet':
-        model = InpaintNet()
-    else:
+    """ Create a model by name (same choices and input-channel table as reference :66-78): 'TrackNet' with L x 3 input
+        channels for RGB frames, L x 1 for 'subtract', L x 4 for 'subtract_concat', (L + 1) x 3 for 'concat', and L
+        heatmaps out; 'InpaintNet'; anything else raises ValueError('Invalid model name.'). """
+    if model_name == 'InpaintNet':
+        return InpaintNet()
+    if model_name != 'TrackNet':
         raise ValueError('Invalid model name.')
-    return model
+    per_frame, extra = _FRAME_CHANNELS.get(bg_mode, (3, 0))
+    return TrackNet(in_dim=seq_len * per_frame + extra, out_dim=seq_len)
 
 
 def to_img(image):
     """ [0, 1] -> uint8 [0, 255] (reference :110-122). """
-    image = image * 255
-    image = image.astype('uint8')
-    return image
+    return (image * 255).astype('uint8')
 
 
 def to_img_format(input, num_ch=1):
