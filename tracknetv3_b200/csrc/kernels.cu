@@ -788,9 +788,14 @@ int launch_adam(const AdamTensor* tab, int ntensors, long long max_n, float lr, 
 // Components nested inside a hole of another component are dropped by RETR_EXTERNAL, but their bbox is
 // strictly inside the enclosing one, so they can never win or tie the maximum.
 // =============================================================================================
+// parents always point to a smaller (raster-earlier) index, so concurrent path halving only ever shortens chains
 TNB_DEVINL int uf_find(volatile int* parent, int x) {
   int p = parent[x];
-  while (p != x) { x = p; p = parent[x]; }
+  while (p != x) {
+    const int g = parent[p];
+    if (g != p) parent[x] = g;  // halve the path
+    x = p; p = g;
+  }
   return x;
 }
 TNB_DEVINL void uf_union(int* parent, int a, int b) {
@@ -828,23 +833,34 @@ __global__ void __launch_bounds__(512) decode_kernel(const void* __restrict__ ma
     if (threadIdx.x < 4) out[blockIdx.x * 4 + threadIdx.x] = 0;
     return;
   }
+  // 8-connectivity with the minimal set of unions per pixel: the already-visited neighbours are W, NW, N, NE. N is
+  // adjacent to all the others, so when N is foreground one union suffices; otherwise NE and one of {NW, W} (NW and W
+  // are adjacent to each other) cover every case.
   for (int p = threadIdx.x; p < HW; p += blockDim.x) {
     if (parent[p] < 0) continue;
     const int y = p / W, x = p - y * W;
-    if (x > 0 && ((volatile int*)parent)[p - 1] >= 0) uf_union(parent, p, p - 1);
-    if (y > 0) {
-      if (((volatile int*)parent)[p - W] >= 0) uf_union(parent, p, p - W);
-      if (x > 0 && ((volatile int*)parent)[p - W - 1] >= 0) uf_union(parent, p, p - W - 1);
-      if (x + 1 < W && ((volatile int*)parent)[p - W + 1] >= 0) uf_union(parent, p, p - W + 1);
+    volatile int* vp = parent;
+    const bool fw = x > 0 && vp[p - 1] >= 0;
+    if (y == 0) {
+      if (fw) uf_union(parent, p, p - 1);
+      continue;
     }
+    if (vp[p - W] >= 0) { uf_union(parent, p, p - W); continue; }
+    if (x + 1 < W && vp[p - W + 1] >= 0) uf_union(parent, p, p - W + 1);
+    if (x > 0 && vp[p - W - 1] >= 0) uf_union(parent, p, p - W - 1);
+    else if (fw) uf_union(parent, p, p - 1);
   }
   __syncthreads();
+  // bounding boxes from the horizontal runs: only a run's first pixel can lower min x, only its last can raise max x,
+  // and one pixel per run suffices for the rows
   for (int p = threadIdx.x; p < HW; p += blockDim.x) {
     if (parent[p] < 0) continue;
-    const int r = uf_find(parent, p);
     const int y = p / W, x = p - y * W;
-    atomicMin(minx + r, x); atomicMax(maxx + r, x);
-    atomicMin(miny + r, y); atomicMax(maxy + r, y);
+    const bool first = x == 0 || parent[p - 1] < 0, last = x + 1 == W || parent[p + 1] < 0;
+    if (!first && !last) continue;
+    const int r = uf_find(parent, p);
+    if (first) { atomicMin(minx + r, x); atomicMin(miny + r, y); atomicMax(maxy + r, y); }
+    if (last) atomicMax(maxx + r, x);
   }
   __syncthreads();
   unsigned long long best = 0ull;
