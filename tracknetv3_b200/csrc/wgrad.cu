@@ -30,6 +30,10 @@ static constexpr int kHdrBytes = 256;
 static constexpr int kTileH = 4, kTileW = 16;    // 64 pixels per K tile
 static constexpr int kHaloW = kTileW + 2;        // 18
 static constexpr int kStages = 3;
+static int wgrad_map_env() {  // TNB_WGRAD_MAP = 4 | 8 | 16: planes per warp copy instruction of the pre-split fills (experiment)
+  static const int v = [] { const char* e = getenv("TNB_WGRAD_MAP"); const int m = e ? atoi(e) : 0; return (m == 4 || m == 8 || m == 16) ? m : 0; }();
+  return v;
+}
 
 struct WgradArgs {
   ViewDesc view;
@@ -188,6 +192,50 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
 
       constexpr bool kCopy = (VMODE == SRC_PRESPLIT);  // both operands are plain copies
       if (kCopy && (a.variant & 8)) {  // ablation: barrier traffic only
+        cp_async_mbar_arrive_noinc(&full[s]);
+        if (++s == S) { s = 0; ph ^= 1; }
+        continue;
+      }
+      if (kCopy && (a.variant & 512)) {
+        // experiment (variant bits 512 | 1024 | 2048): a warp instruction covers PLW planes x 32/PLW consecutive pixels
+        // instead of all 16 planes of 2 pixels
+        const int PLW = (a.variant & 2048) ? 16 : (a.variant & 1024) ? 8 : 4, PXW = 32 / PLW;
+        const int fw = ftid >> 5, pl_sub = lane % PLW, px_sub = lane / PLW;
+        {
+          const int npg = max(npld / PLW, 1), nunits = npg * (kTileH * kTileW / PXW);
+          for (int unit = fw; unit < nunits; unit += kFillThreads / 32) {
+            const int pl = (unit % npg) * PLW + pl_sub, px = (unit / npg) * PXW + px_sub;
+            if (pl < npld) {
+              const int h = h0 + (px >> 4), w = w0 + (px & 15);
+              const bool ok = h < V.H && w < V.W;
+              const uint8_t* q = ok ? a.dz + (size_t)(co0 + pl * 8) * 2 + ((size_t)(n * V.H + h) * V.W + w) * dz_pix_stride : a.dz;
+              uint8_t* d = stage + pl * DZPL + px * 16;
+              cp_async16(d, q, ok ? 16u : 0u, ca);
+              if (a.nterms > 1) cp_async16(d + 16 * DZPL, q + dz_lo, ok ? 16u : 0u, ca);
+            }
+          }
+        }
+        {
+          const SrcDesc& S2 = (ci0 >= V.C0) ? V.s[1] : V.s[0];
+          const int cbase = (ci0 >= V.C0) ? ci0 - V.C0 : ci0;
+          const size_t vstride = (size_t)S2.C * 4;
+          const int v_lo = S2.C * 2;
+          const int vup = S2.mode == SRC_PRESPLIT_UP ? 1 : 0;
+          const int npg = max(NPL / PLW, 1), nblk = (kViewPx + PXW - 1) / PXW, nunits = npg * nblk;
+          for (int unit = fw; unit < nunits; unit += kFillThreads / 32) {
+            const int pl = (unit % npg) * PLW + pl_sub, p = (unit / npg) * PXW + px_sub;
+            if (pl < NPL && p < kViewPx) {
+              const int hr = p / kHaloW, hc = p - hr * kHaloW;
+              const int h = h0 + hr + dy0 - 1, w = w0 - 1 + hc;
+              const bool ok = h >= 0 && h < V.H && w >= 0 && w < V.W;
+              const uint8_t* vb = reinterpret_cast<const uint8_t*>(S2.ptr) + (size_t)(cbase + pl * 8) * 2;
+              const uint8_t* q = ok ? vb + ((size_t)(n * S2.Hs + (h >> vup)) * S2.Ws + (w >> vup)) * vstride : vb;
+              uint8_t* d = stage + DZ_BYTES + pl * VPL + p * 16;
+              cp_async16(d, q, ok ? 16u : 0u, ca);
+              if (a.nterms > 1) cp_async16(d + NPL * VPL, q + v_lo, ok ? 16u : 0u, ca);
+            }
+          }
+        }
         cp_async_mbar_arrive_noinc(&full[s]);
         if (++s == S) { s = 0; ph ^= 1; }
         continue;
@@ -361,6 +409,7 @@ struct WgradSArgs {
   int N, H, W, C, Cout, CinReal, P /*planes per ci tile: 8 or 4*/, nterms, ncit, ncot;
   int tiles_h, tiles_w, ktiles, ktiles_per_cta;
   int ca;  // cp.async.ca instead of .cg (experiment)
+  int map; // 0: 8 planes x 4 pixels per warp copy instruction; 4 / 8: experiment mapping (TNB_WGRAD_MAP)
   float* ws;  // optional tap-major accumulation buffer [9][Cout][C] (see launch_wgrad_scatter); nullptr: dw
 };
 
@@ -467,6 +516,30 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __g
     bool isdz[MAXI], act[MAXI];
 #pragma unroll
     for (int u = 0; u < MAXI; ++u) {
+      if (a.map) {  // experiment (TNB_WGRAD_MAP): a warp instruction covers PLW planes x 32/PLW consecutive pixels
+        const int PLW = a.map, PXW = 32 / PLW;
+        const int pl_sub = lane % PLW, px_sub = lane / PLW;
+        const int ndzu = (8 / PLW) * (kTileH * kTileW / PXW);
+        const int npgv = max(P / PLW, 1), nblk = ((kTileH + 2) * kHaloW + PXW - 1) / PXW;
+        const int unit = (ftid >> 5) + u * (kFillThreads / 32);
+        isdz[u] = unit < ndzu;
+        if (isdz[u]) {
+          const int pl = (unit % (8 / PLW)) * PLW + pl_sub, px = (unit / (8 / PLW)) * PXW + px_sub;
+          act[u] = true;
+          soff[u] = A_BYTES + pl * DZPL + px * 16;
+          dh[u] = px >> 4; dwv[u] = px & 15;
+          goff[u] = (co0 + pl * 8) * 2;
+        } else {
+          const int j = unit - ndzu;
+          const int pl = (j % npgv) * PLW + pl_sub, hp = (j / npgv) * PXW + px_sub;
+          act[u] = j < npgv * nblk && pl < P && hp < (kTileH + 2) * kHaloW;
+          const int hr = hp / kHaloW, hc = hp - hr * kHaloW;
+          soff[u] = (hr * P + pl) * kSRP + hc * 16;
+          dh[u] = hr - 1; dwv[u] = hc - 1;
+          goff[u] = (ci0 - (ci0 >= a.C0 ? a.C0 : 0) + pl * 8) * 2;
+        }
+        continue;
+      }
       const int it = ftid + u * kFillThreads;
       act[u] = it < ndz + nin;
       isdz[u] = it < ndz;
@@ -599,6 +672,7 @@ static int launch_wgrad3x3_stacked(const ViewDesc& view, const void* dz_presplit
   a.N = view.N; a.H = view.H; a.W = view.W; a.C = view.C; a.Cout = Cout; a.CinReal = CinReal; a.nterms = nterms;
   a.P = view.C == 32 ? 4 : 8;
   a.ca = cp_async_ca_env();
+  a.map = wgrad_map_env() == 16 ? 0 : wgrad_map_env();
   a.ncit = view.C / (a.P * 8); a.ncot = Cout / 64;
   a.tiles_h = (view.H + kTileH - 1) / kTileH;
   a.tiles_w = (view.W + kTileW - 1) / kTileW;
@@ -640,6 +714,7 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
   if (ws != nullptr) TNB_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 9 * (size_t)Cout * view.C, st));
   a.view = view; a.dz = (const uint8_t*)dz_presplit; a.dw = dw; a.Cout = Cout; a.CinReal = CinReal;
   a.nterms = nterms; a.variant = variant | (cp_async_ca_env() ? 256 : 0); a.ci_tile_base = 0;
+  if (const int m = wgrad_map_env()) a.variant |= 512 | (m == 8 ? 1024 : m == 16 ? 2048 : 0);
   a.NT = pick_nt(view.C, view.C0);
   TNB_REQUIRE(a.NT > 0, "wgrad3x3: no input-channel tile for Cin=%d (first source %d)", view.C, view.C0);
   a.tiles_h = (view.H + kTileH - 1) / kTileH;
