@@ -1,20 +1,16 @@
 #!/bin/bash
-# usage: tools/gpu_exp.sh <outdir-name>: wgrad fill-mapping experiment (tools/exp_wgrad_map.py) + tests and bench per mapping
+# usage: tools/gpu_exp.sh <outdir-name>: wgrad kernels alone (tools/ablate_wgrad.py), conv parity tests, bench
 cd "$(dirname "$0")/.."
 OUT=gpurun_out/$1
 mkdir -p $OUT
-timeout -k 5 150 python tools/exp_wgrad_map.py generic > $OUT/generic.log 2>&1; echo "generic rc=$?" > $OUT/summary.txt
-for m in 0 4 8; do TNB_WGRAD_MAP=$m timeout -k 5 60 python tools/exp_wgrad_map.py stacked >> $OUT/stacked.log 2>&1; done
-for m in 4 8; do
-  TNB_WGRAD_MAP=$m timeout -k 5 120 python -m pytest tests/test_gpu_conv.py -x -q -k wgrad > $OUT/pytest_map$m.log 2>&1; echo "pytest map$m rc=$?" >> $OUT/summary.txt
-  tail -1 $OUT/pytest_map$m.log >> $OUT/summary.txt
-done
-for m in 0 4 8; do
-  TNB_WGRAD_MAP=$m timeout -k 5 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench_map$m.log 2>&1
-  tail -1 $OUT/bench_map$m.log | python -c "
+timeout -k 5 200 python -m pytest tests/test_gpu_conv.py tests/test_gpu_tracknet.py -x -q > $OUT/pytest.log 2>&1; echo "pytest rc=$?" > $OUT/summary.txt
+tail -3 $OUT/pytest.log >> $OUT/summary.txt
+timeout -k 5 150 python tools/ablate_wgrad.py > $OUT/ablate_wgrad.log 2>&1; echo "ablate rc=$?" >> $OUT/summary.txt
+grep -E "shape|full|no-MMA|no-fill" $OUT/ablate_wgrad.log | grep -E "shape|terms=3" >> $OUT/summary.txt
+timeout -k 5 120 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $OUT/bench.log 2>&1
+tail -1 $OUT/bench.log | python -c "
 import json,sys
 try:
-    d=json.loads(sys.stdin.read()); print('map $m: ms',round(d['ms_per_step'],3),'wgrad',round(d['kernel_breakdown']['conv3x3 wgrad']['ms_per_step'],3),'clk',d['clocks']['sm_mhz'])
+    d=json.loads(sys.stdin.read()); print('bench: ms',round(d['ms_per_step'],3),'fps',round(d['value'],1),{k:round(v['ms_per_step'],3) for k,v in d['kernel_breakdown'].items()},'clk',d['clocks'])
 except Exception as e: print('parse failed',e)" >> $OUT/summary.txt
-done
-cat $OUT/generic.log $OUT/stacked.log $OUT/summary.txt
+cat $OUT/summary.txt

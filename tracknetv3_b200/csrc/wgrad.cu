@@ -30,10 +30,6 @@ static constexpr int kHdrBytes = 256;
 static constexpr int kTileH = 4, kTileW = 16;    // 64 pixels per K tile
 static constexpr int kHaloW = kTileW + 2;        // 18
 static constexpr int kStages = 3;
-static int wgrad_map_env() {  // TNB_WGRAD_MAP = 4 | 8 | 16: planes per warp copy instruction of the pre-split fills (experiment)
-  static const int v = [] { const char* e = getenv("TNB_WGRAD_MAP"); const int m = e ? atoi(e) : 0; return (m == 4 || m == 8 || m == 16) ? m : 0; }();
-  return v;
-}
 
 struct WgradArgs {
   ViewDesc view;
@@ -177,14 +173,38 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
     const int dz_lo = a.Cout * 2;
     const int per_img = a.tiles_h * a.tiles_w;
 
-    const bool ca = (a.variant & 256) != 0;
+    // tile-independent part of this thread's (up to) 3 + 3 copies of a K tile (pre-split operands only): shared-memory
+    // offset inside the stage (-1 = no copy), pixel offset (dh, dw) from the tile origin for the bounds test, and byte
+    // offset from the tile origin's address. A half-resolution source (SRC_PRESPLIT_UP) is addressed at (h >> 1, w >> 1);
+    // tile origins are even, so (h0 + dh) >> 1 = (h0 >> 1) + (dh >> 1) with an arithmetic shift.
+    struct CopyItem { int soff, dh, dw, goff; };
+    CopyItem cdz[3], cvw[3];
+    const int cvup = VS.mode == SRC_PRESPLIT_UP ? 1 : 0;
+    const int cvHs = VS.Hs, cvWs = VS.Ws;
+    const size_t cvstride = (size_t)VS.C * 4;  // [pixel][2][C] 16-bit
+    const int cv_lo = VS.C * 2;
+    const uint8_t* cvbase = reinterpret_cast<const uint8_t*>(VS.ptr);
+    if (VMODE == SRC_PRESPLIT) {
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int px = dpx0 + u * DG;
+        cdz[u].soff = px < kTileH * kTileW ? dpl * DZPL + px * 16 : -1;
+        cdz[u].dh = px >> 4; cdz[u].dw = px & 15;
+        cdz[u].goff = (cdz[u].dh * V.W + cdz[u].dw) * (int)dz_pix_stride + (co0 + dpl * 8) * 2;
+        const int p = vpx0 + u * VG;
+        const int hr = p / kHaloW, hc = p - hr * kHaloW;
+        cvw[u].soff = (vactive && p < kViewPx) ? DZ_BYTES + vpl * VPL + p * 16 : -1;
+        cvw[u].dh = hr + dy0 - 1; cvw[u].dw = hc - 1;
+        cvw[u].goff = ((cvw[u].dh >> cvup) * cvWs + (cvw[u].dw >> cvup)) * (int)cvstride + vcc * 2;
+      }
+    }
     int s = 0;
     uint32_t ph = 0;
+    // (n, h0, w0) of the K tile advance incrementally: no divisions in the loop
+    int n_i = kt0 / per_img, th_i = (kt0 - n_i * per_img) / a.tiles_w, tw_i = kt0 - n_i * per_img - th_i * a.tiles_w;
     for (int kt = kt0; kt < kt1; ++kt) {
-      const int n = kt / per_img;
-      const int rem = kt - n * per_img;
-      const int th = rem / a.tiles_w;
-      const int h0 = th * kTileH, w0 = (rem - th * a.tiles_w) * kTileW;
+      const int n = n_i, h0 = th_i * kTileH, w0 = tw_i * kTileW;
+      if (++tw_i == a.tiles_w) { tw_i = 0; if (++th_i == a.tiles_h) { th_i = 0; ++n_i; } }
       mbar_wait(&empty[s], ph ^ 1);
       uint8_t* stage = st_base + s * STAGE;
       uint8_t* dzp = stage + dpl * DZPL;
@@ -196,82 +216,31 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
         if (++s == S) { s = 0; ph ^= 1; }
         continue;
       }
-      if (kCopy && (a.variant & 512)) {
-        // experiment (variant bits 512 | 1024 | 2048): a warp instruction covers PLW planes x 32/PLW consecutive pixels
-        // instead of all 16 planes of 2 pixels
-        const int PLW = (a.variant & 2048) ? 16 : (a.variant & 1024) ? 8 : 4, PXW = 32 / PLW;
-        const int fw = ftid >> 5, pl_sub = lane % PLW, px_sub = lane / PLW;
-        {
-          const int npg = max(npld / PLW, 1), nunits = npg * (kTileH * kTileW / PXW);
-          for (int unit = fw; unit < nunits; unit += kFillThreads / 32) {
-            const int pl = (unit % npg) * PLW + pl_sub, px = (unit / npg) * PXW + px_sub;
-            if (pl < npld) {
-              const int h = h0 + (px >> 4), w = w0 + (px & 15);
-              const bool ok = h < V.H && w < V.W;
-              const uint8_t* q = ok ? a.dz + (size_t)(co0 + pl * 8) * 2 + ((size_t)(n * V.H + h) * V.W + w) * dz_pix_stride : a.dz;
-              uint8_t* d = stage + pl * DZPL + px * 16;
-              cp_async16(d, q, ok ? 16u : 0u, ca);
-              if (a.nterms > 1) cp_async16(d + 16 * DZPL, q + dz_lo, ok ? 16u : 0u, ca);
-            }
-          }
-        }
-        {
-          const SrcDesc& S2 = (ci0 >= V.C0) ? V.s[1] : V.s[0];
-          const int cbase = (ci0 >= V.C0) ? ci0 - V.C0 : ci0;
-          const size_t vstride = (size_t)S2.C * 4;
-          const int v_lo = S2.C * 2;
-          const int vup = S2.mode == SRC_PRESPLIT_UP ? 1 : 0;
-          const int npg = max(NPL / PLW, 1), nblk = (kViewPx + PXW - 1) / PXW, nunits = npg * nblk;
-          for (int unit = fw; unit < nunits; unit += kFillThreads / 32) {
-            const int pl = (unit % npg) * PLW + pl_sub, p = (unit / npg) * PXW + px_sub;
-            if (pl < NPL && p < kViewPx) {
-              const int hr = p / kHaloW, hc = p - hr * kHaloW;
-              const int h = h0 + hr + dy0 - 1, w = w0 - 1 + hc;
-              const bool ok = h >= 0 && h < V.H && w >= 0 && w < V.W;
-              const uint8_t* vb = reinterpret_cast<const uint8_t*>(S2.ptr) + (size_t)(cbase + pl * 8) * 2;
-              const uint8_t* q = ok ? vb + ((size_t)(n * S2.Hs + (h >> vup)) * S2.Ws + (w >> vup)) * vstride : vb;
-              uint8_t* d = stage + DZ_BYTES + pl * VPL + p * 16;
-              cp_async16(d, q, ok ? 16u : 0u, ca);
-              if (a.nterms > 1) cp_async16(d + NPL * VPL, q + v_lo, ok ? 16u : 0u, ca);
-            }
-          }
-        }
-        cp_async_mbar_arrive_noinc(&full[s]);
-        if (++s == S) { s = 0; ph ^= 1; }
-        continue;
-      }
       if (kCopy) {
         // Both operands are already (hi, lo) 16-bit pairs in HBM: the fill is 16-byte cp.async copies straight into
         // the planar tiles. The thread never waits for its own loads (the stage's mbarrier is armed with a
         // cp.async-completion arrival), so up to kStages K tiles of HBM latency are in flight per thread.
+        // The producers are bound by their own instruction stream (12 warps, ~30 instructions per copy when every
+        // address is rebuilt from (n, h, w)), so everything that does not depend on the tile is hoisted into
+        // CopyItem: per K tile a copy costs one bounds test, one 64-bit add and the LDGSTS pair.
+        const uint8_t* dzt = a.dz + ((size_t)(n * V.H + h0) * V.W + w0) * dz_pix_stride;  // warp-uniform tile origins
+        const uint8_t* vwt = cvbase + ((ptrdiff_t)(n * cvHs + (h0 >> cvup)) * cvWs + (w0 >> cvup)) * (ptrdiff_t)cvstride;
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
-          const int px = dpx0 + u * DG;
-          if (px < kTileH * kTileW) {
-            const int h = h0 + (px >> 4), w = w0 + (px & 15);
-            const bool ok = h < V.H && w < V.W;
-            const uint8_t* q = ok ? dz_base + ((size_t)(n * V.H + h) * V.W + w) * dz_pix_stride : a.dz;
-            cp_async16(dzp + px * 16, q, ok ? 16u : 0u, ca);
-            if (a.nterms > 1) cp_async16(dzp + px * 16 + 16 * DZPL, q + dz_lo, ok ? 16u : 0u, ca);
+          if (cdz[u].soff >= 0) {
+            const bool ok = h0 + cdz[u].dh < V.H && w0 + cdz[u].dw < V.W;
+            const uint8_t* q = ok ? dzt + cdz[u].goff : a.dz;
+            cp_async16(stage + cdz[u].soff, q, ok ? 16u : 0u, true);
+            if (a.nterms > 1) cp_async16(stage + cdz[u].soff + 16 * DZPL, q + dz_lo, ok ? 16u : 0u, true);
           }
         }
-        if (vactive) {
-          const uint8_t* vbase = reinterpret_cast<const uint8_t*>(VS.ptr) + (size_t)vcc * 2;  // [pixel][2][C] 16-bit
-          const size_t vstride = (size_t)VS.C * 4;
-          const int v_lo = VS.C * 2;
-          const int vup = VS.mode == SRC_PRESPLIT_UP ? 1 : 0;
 #pragma unroll
-          for (int u = 0; u < 3; ++u) {
-            const int p = vpx0 + u * VG;
-            if (p < kViewPx) {
-              const int hr = p / kHaloW, hc = p - hr * kHaloW;
-              const int h = h0 + hr + dy0 - 1, w = w0 - 1 + hc;
-              const bool ok = h >= 0 && h < V.H && w >= 0 && w < V.W;
-              // PRESPLIT_UP: the source is the half-resolution tensor, pixel (h, w) of the view is its (h/2, w/2)
-              const uint8_t* q = ok ? vbase + ((size_t)(n * VS.Hs + (h >> vup)) * VS.Ws + (w >> vup)) * vstride : vbase;
-              cp_async16(vwp + p * 16, q, ok ? 16u : 0u, ca);
-              if (a.nterms > 1) cp_async16(vwp + p * 16 + NPL * VPL, q + v_lo, ok ? 16u : 0u, ca);
-            }
+        for (int u = 0; u < 3; ++u) {
+          if (cvw[u].soff >= 0) {
+            const bool ok = (unsigned)(h0 + cvw[u].dh) < (unsigned)V.H && (unsigned)(w0 + cvw[u].dw) < (unsigned)V.W;
+            const uint8_t* q = ok ? vwt + cvw[u].goff : cvbase;
+            cp_async16(stage + cvw[u].soff, q, ok ? 16u : 0u, true);
+            if (a.nterms > 1) cp_async16(stage + cvw[u].soff + NPL * VPL, q + cv_lo, ok ? 16u : 0u, true);
           }
         }
         cp_async_mbar_arrive_noinc(&full[s]);
@@ -408,8 +377,6 @@ struct WgradSArgs {
   float* dw;
   int N, H, W, C, Cout, CinReal, P /*planes per ci tile: 8 or 4*/, nterms, ncit, ncot;
   int tiles_h, tiles_w, ktiles, ktiles_per_cta;
-  int ca;  // cp.async.ca instead of .cg (experiment)
-  int map; // 0: 8 planes x 4 pixels per warp copy instruction; 4 / 8: experiment mapping (TNB_WGRAD_MAP)
   float* ws;  // optional tap-major accumulation buffer [9][Cout][C] (see launch_wgrad_scatter); nullptr: dw
 };
 
@@ -509,86 +476,59 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __g
     // The copy list of a K tile is the same for every tile: item -> (shared offset, pixel offset, channel offset).
     // dz items: 64 pixels x 8 planes; input items: 6 x 18 halo pixels x P planes. 8 (or P) neighbouring threads copy
     // the 128 (64) contiguous bytes of one pixel.
+    // The producers are bound by their own instruction stream, so everything tile-independent is hoisted: per item the
+    // shared-memory offsets of both terms, the pixel offset from the tile origin (bounds test) and the byte offset from
+    // the tile origin's address; per K tile the two (warp-uniform) tile-origin addresses.
     constexpr int MAXI = 4;
     const int ndz = kTileH * kTileW * 8, nin = (kTileH + 2) * kHaloW * P;
-    uint32_t soff[MAXI];
-    int dh[MAXI], dwv[MAXI], goff[MAXI];
-    bool isdz[MAXI], act[MAXI];
-#pragma unroll
-    for (int u = 0; u < MAXI; ++u) {
-      if (a.map) {  // experiment (TNB_WGRAD_MAP): a warp instruction covers PLW planes x 32/PLW consecutive pixels
-        const int PLW = a.map, PXW = 32 / PLW;
-        const int pl_sub = lane % PLW, px_sub = lane / PLW;
-        const int ndzu = (8 / PLW) * (kTileH * kTileW / PXW);
-        const int npgv = max(P / PLW, 1), nblk = ((kTileH + 2) * kHaloW + PXW - 1) / PXW;
-        const int unit = (ftid >> 5) + u * (kFillThreads / 32);
-        isdz[u] = unit < ndzu;
-        if (isdz[u]) {
-          const int pl = (unit % (8 / PLW)) * PLW + pl_sub, px = (unit / (8 / PLW)) * PXW + px_sub;
-          act[u] = true;
-          soff[u] = A_BYTES + pl * DZPL + px * 16;
-          dh[u] = px >> 4; dwv[u] = px & 15;
-          goff[u] = (co0 + pl * 8) * 2;
-        } else {
-          const int j = unit - ndzu;
-          const int pl = (j % npgv) * PLW + pl_sub, hp = (j / npgv) * PXW + px_sub;
-          act[u] = j < npgv * nblk && pl < P && hp < (kTileH + 2) * kHaloW;
-          const int hr = hp / kHaloW, hc = hp - hr * kHaloW;
-          soff[u] = (hr * P + pl) * kSRP + hc * 16;
-          dh[u] = hr - 1; dwv[u] = hc - 1;
-          goff[u] = (ci0 - (ci0 >= a.C0 ? a.C0 : 0) + pl * 8) * 2;
-        }
-        continue;
-      }
-      const int it = ftid + u * kFillThreads;
-      act[u] = it < ndz + nin;
-      isdz[u] = it < ndz;
-      if (isdz[u]) {
-        const int pl = it & 7, px = it >> 3;
-        soff[u] = A_BYTES + pl * DZPL + px * 16;
-        dh[u] = px >> 4; dwv[u] = px & 15;
-        goff[u] = (co0 + pl * 8) * 2;
-      } else {
-        const int j = it - ndz;
-        const int pl = j % P, hp = j / P;
-        const int hr = hp / kHaloW, hc = hp - hr * kHaloW;
-        soff[u] = (hr * P + pl) * kSRP + hc * 16;
-        dh[u] = hr - 1; dwv[u] = hc - 1;
-        goff[u] = (ci0 - (ci0 >= a.C0 ? a.C0 : 0) + pl * 8) * 2;
-      }
-    }
     // a CTA's 64 (32) input channels come from ONE source of the view (launcher: C0 is a multiple of the tile)
     const bool second = ci0 >= a.C0;
     const uint8_t* vsrc = second ? a.view1 : a.view;
     const int vC = second ? a.Cs1 : a.Cs0;
-    const int vshift = (!second && a.up0) ? 1 : 0;
+    const int vshift = (!second && a.up0) ? 1 : 0;  // half-resolution source: pixel (h, w) of the view is its (h/2, w/2)
     const int vH = vshift ? a.Hs0 : a.H, vW = vshift ? a.Ws0 : a.W;
     const size_t dz_stride = (size_t)a.Cout * 4, v_stride = (size_t)vC * 4;
     const int dz_lo = a.Cout * 2, v_lo = vC * 2;
     const int per_img = a.tiles_h * a.tiles_w;
+    int soff[MAXI], slo[MAXI], dh[MAXI], dwv[MAXI], goff[MAXI], glo[MAXI];  // soff < 0: no item
+    bool isdz[MAXI];
+#pragma unroll
+    for (int u = 0; u < MAXI; ++u) {
+      const int it = ftid + u * kFillThreads;
+      isdz[u] = it < ndz;
+      if (isdz[u]) {
+        const int pl = it & 7, px = it >> 3;
+        soff[u] = A_BYTES + pl * DZPL + px * 16; slo[u] = B_TERM; glo[u] = dz_lo;
+        dh[u] = px >> 4; dwv[u] = px & 15;
+        goff[u] = (dh[u] * a.W + dwv[u]) * (int)dz_stride + (co0 + pl * 8) * 2;
+      } else {
+        const int j = it - ndz;
+        const int pl = j % P, hp = j / P;
+        const int hr = hp / kHaloW, hc = hp - hr * kHaloW;
+        soff[u] = it < ndz + nin ? (hr * P + pl) * kSRP + hc * 16 : -1; slo[u] = A_TERM; glo[u] = v_lo;
+        dh[u] = hr - 1; dwv[u] = hc - 1;
+        // tile origins are even, so (h0 + dh) >> 1 = (h0 >> 1) + (dh >> 1) with an arithmetic shift
+        goff[u] = ((dh[u] >> vshift) * vW + (dwv[u] >> vshift)) * (int)v_stride + (ci0 - (second ? a.C0 : 0) + pl * 8) * 2;
+      }
+    }
 
     int s = 0;
     uint32_t ph = 0;
+    int n_i = kt0 / per_img, th_i = (kt0 - n_i * per_img) / a.tiles_w, tw_i = kt0 - n_i * per_img - th_i * a.tiles_w;
     for (int kt = kt0; kt < kt1; ++kt) {
-      const int n = kt / per_img;
-      const int rem = kt - n * per_img;
-      const int th = rem / a.tiles_w;
-      const int h0 = th * kTileH, w0 = (rem - th * a.tiles_w) * kTileW;
+      const int n = n_i, h0 = th_i * kTileH, w0 = tw_i * kTileW;
+      if (++tw_i == a.tiles_w) { tw_i = 0; if (++th_i == a.tiles_h) { th_i = 0; ++n_i; } }
       mbar_wait(&empty[s], ph ^ 1);
       uint8_t* stage = st_base + s * STAGE;
+      const uint8_t* dzt = a.dz + ((size_t)(n * a.H + h0) * a.W + w0) * dz_stride;
+      const uint8_t* vwt = vsrc + ((size_t)(n * vH + (h0 >> vshift)) * vW + (w0 >> vshift)) * v_stride;
 #pragma unroll
       for (int u = 0; u < MAXI; ++u) {
-        if (act[u]) {
-          const int h = h0 + dh[u], w = w0 + dwv[u];
-          const bool ok = h >= 0 && h < a.H && w >= 0 && w < a.W;
-          const size_t pix = (size_t)(n * a.H + h) * a.W + w;
-          const size_t vpix = (size_t)(n * vH + (h >> vshift)) * vW + (w >> vshift);
-          const uint8_t* q = isdz[u] ? (ok ? a.dz + pix * dz_stride + goff[u] : a.dz)
-                                     : (ok ? vsrc + vpix * v_stride + goff[u] : vsrc);
-          cp_async16(stage + soff[u], q, ok ? 16u : 0u, a.ca != 0);
-          if (a.nterms > 1)
-            cp_async16(stage + soff[u] + (isdz[u] ? B_TERM : A_TERM), q + (isdz[u] ? dz_lo : v_lo), ok ? 16u : 0u,
-                       a.ca != 0);
+        if (soff[u] >= 0) {
+          const bool ok = (unsigned)(h0 + dh[u]) < (unsigned)a.H && (unsigned)(w0 + dwv[u]) < (unsigned)a.W;
+          const uint8_t* q = ok ? (isdz[u] ? dzt : vwt) + goff[u] : a.dz;
+          cp_async16(stage + soff[u], q, ok ? 16u : 0u, true);
+          if (a.nterms > 1) cp_async16(stage + soff[u] + slo[u], q + glo[u], ok ? 16u : 0u, true);
         }
       }
       cp_async_mbar_arrive_noinc(&full[s]);
@@ -671,8 +611,6 @@ static int launch_wgrad3x3_stacked(const ViewDesc& view, const void* dz_presplit
   a.up0 = view.s[0].mode == SRC_PRESPLIT_UP ? 1 : 0; a.Hs0 = view.s[0].Hs; a.Ws0 = view.s[0].Ws;
   a.N = view.N; a.H = view.H; a.W = view.W; a.C = view.C; a.Cout = Cout; a.CinReal = CinReal; a.nterms = nterms;
   a.P = view.C == 32 ? 4 : 8;
-  a.ca = cp_async_ca_env();
-  a.map = wgrad_map_env() == 16 ? 0 : wgrad_map_env();
   a.ncit = view.C / (a.P * 8); a.ncot = Cout / 64;
   a.tiles_h = (view.H + kTileH - 1) / kTileH;
   a.tiles_w = (view.W + kTileW - 1) / kTileW;
@@ -713,8 +651,7 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
   a.ws = ws;
   if (ws != nullptr) TNB_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 9 * (size_t)Cout * view.C, st));
   a.view = view; a.dz = (const uint8_t*)dz_presplit; a.dw = dw; a.Cout = Cout; a.CinReal = CinReal;
-  a.nterms = nterms; a.variant = variant | (cp_async_ca_env() ? 256 : 0); a.ci_tile_base = 0;
-  if (const int m = wgrad_map_env()) a.variant |= 512 | (m == 8 ? 1024 : m == 16 ? 2048 : 0);
+  a.nterms = nterms; a.variant = variant; a.ci_tile_base = 0;
   a.NT = pick_nt(view.C, view.C0);
   TNB_REQUIRE(a.NT > 0, "wgrad3x3: no input-channel tile for Cin=%d (first source %d)", view.C, view.C0);
   a.tiles_h = (view.H + kTileH - 1) / kTileH;
