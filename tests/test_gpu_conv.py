@@ -222,6 +222,34 @@ def test_conv3x3_wgrad_tap_stacked(n, h, w, cin, cin_real, terms):
         assert G.rel_err(dw_ws, wt.grad) < tol
 
 
+@pytest.mark.parametrize("terms", [3, 1])
+@pytest.mark.parametrize("n,h,w,cin,cout", [
+    (1, 8, 16, 128, 256),     # one pair per filter row, two K tiles
+    (2, 12, 40, 256, 256),    # ragged 4x16 K tiles, two input-channel tiles
+    (1, 20, 24, 128, 512),    # two pairs along the output channels
+    (3, 16, 48, 384, 256),    # three input-channel tiles, K range split over several CTAs
+])
+def test_conv3x3_wgrad_cta_pair(n, h, w, cin, cout, terms):
+    """Cout % 256 == 0 with pre-split operands and a 128-channel input tile runs on CTA pairs (tcgen05 cta_group::2:
+    each CTA loads its own 128 dz rows and half of the view tile); the single-CTA kernel on the same operands (variant
+    bit 64) must agree with it and both with the oracle op."""
+    x = _rand(n, cin, h, w, seed=33)
+    dz = _rand(n, cout, h, w, seed=34, scale=1e-5)
+    wt = torch.zeros(cout, cin, 3, 3, requires_grad=True)
+    (F.conv2d(x, wt, padding=1) * dz).sum().backward()
+    t, d = G.nhwc(x), G.nhwc(dz)
+    ts = G.presplit(t)
+    src = _lib.Src(ptr=ts.data_ptr(), scale=None, shift=None, C=cin, Hs=h, Ws=w, mode=_lib.SRC_PRESPLIT)
+    tol = 2e-4 if terms == 3 else 2e-2
+    dw = G.wgrad3x3(G.make_view([src], n, h, w), d, cout, cin, terms=terms)
+    assert G.rel_err(dw, wt.grad) < tol
+    dw_single = G.wgrad3x3(G.make_view([src], n, h, w), d, cout, cin, terms=terms, variant=64)
+    assert G.rel_err(dw_single, wt.grad) < tol
+    assert G.rel_err(dw, dw_single) < (1e-5 if terms == 3 else 1e-3)
+    dw_ws = G.wgrad3x3(G.make_view([src], n, h, w), d, cout, cin, terms=terms, scratch=True)
+    assert G.rel_err(dw_ws, wt.grad) < tol
+
+
 @pytest.mark.parametrize("c_up,c_skip,cout", [(128, 64, 64), (64, 64, 64), (256, 128, 128), (512, 256, 256)])
 def test_conv3x3_wgrad_concat_of_half_resolution_source(c_up, c_skip, cout):
     """Decoder concat view [upsample(x), skip] given as two pre-split sources, the first one at half resolution

@@ -1,4 +1,6 @@
-"""Bottleneck ablation of the wgrad kernel (pre-split operands): variant bits 4 = no MMA, 8 = no fill, 16 = no atomics."""
+"""Bottleneck ablation of the wgrad kernels (pre-split operands). variant 0 = what the network runs (CTA pairs where
+Cout % 256 == 0, the tap-stacked kernel for Cout = 64); bit 64 = single-CTA kernel, on which the ablation bits act:
+4 = no MMA, 8 = no fill, 16 = no atomics."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -26,12 +28,12 @@ def time_wgrad(n, h, w, cin, cout, variant, terms=3, reps=5):
 
 if __name__ == "__main__":
     shapes = [(10, 72, 128, 256, 256), (10, 144, 256, 128, 128), (10, 288, 512, 64, 64), (10, 288, 512, 192, 64), (10, 36, 64, 512, 512)]
-    names = {0: "full", 4: "no-MMA", 8: "no-fill", 16: "no-atomics", 12: "barriers+epilogue", 28: "barriers only"}
+    names = {0: "full (as shipped)", 64: "single-CTA full", 68: "single-CTA no-MMA", 72: "single-CTA no-fill", 80: "single-CTA no-atomics"}
     for shp in shapes:
         n, h, w, cin, cout = shp
         gf = 2.0 * n * h * w * cin * cout * 9 / 1e9
         print(f"shape {shp}: {gf:.1f} GFLOP algorithmic")
         for v, nm in names.items():
-            for terms in (3, 1):
+            for terms in (3,):
                 ms = time_wgrad(n, h, w, cin, cout, v, terms)
                 print(f"   {nm:20s} terms={terms}: {ms:7.3f} ms  ({gf / ms:8.1f} TFLOP/s-alg)")

@@ -21,6 +21,7 @@
 #include "prof.cuh"
 #include <type_traits>
 #include <algorithm>
+#include <cstdlib>
 
 namespace tnb {
 
@@ -352,6 +353,267 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
 }
 
 // =============================================================================================
+// CTA-pair variant (tcgen05 cta_group::2) for Cout % 256 == 0 with a 128-channel input tile and pre-split operands.
+//
+// The single-CTA kernel above is bound by what it has to move, not by the tensor pipe: an M = 128, N = 128 MMA reads
+// (128 + 128) x 32 B of shared memory per K step - 64 clocks at 128 B/clk, exactly its math time - and every K tile
+// costs 68 KB of L2 -> SM traffic (the fill alone runs at ~6.7 TB/s chip-wide). Two CTAs of a cluster (the two SMs
+// of a TPC) computing 256 output channels x the SAME 128 input channels share the view operand: each CTA loads its
+// own 128 dz rows and HALF of the view tile (64 channels), the pair's tensor cores read both halves through
+// distributed shared memory. Per CTA: 50 KB per K tile instead of 68, (128 + 64) x 32 B per MMA instead of 256 x 32
+// (48 clocks < 64 of math), and the smaller stage buys a fourth pipeline stage.
+//
+// Protocol: rank 0 issues every tcgen05.mma.cta_group::2 (M = 256: TMEM lanes 0-127 of each CTA hold that CTA's 128
+// output channels) and multicasts the commits to both CTAs' empty / tmem_full barriers. Rank 1's producers arrive on
+// rank 1's own full barrier; its warp 0 relays each completed phase to rank 0's full barrier (expected count
+// kFillThreads + 1) with a cluster-scope release arrive.
+// =============================================================================================
+static constexpr int kPStages = 4;
+
+TNB_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+TNB_DEVINL void cluster_sync_all() {  // every thread of both CTAs
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+TNB_DEVINL void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {  // the barrier at the same offset in CTA `cta`
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+TNB_DEVINL void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // acquire at cluster scope (remote arrivals)
+  uint32_t spins = 0;
+  while (true) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins > (1u << 26)) {
+      printf("tnb: cluster mbarrier wait timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+TNB_DEVINL void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {  // warp 0 of BOTH CTAs, same smem offset
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+TNB_DEVINL void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+TNB_DEVINL void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+TNB_DEVINL void umma_commit_pair(uint64_t* bar) {  // arrives on the barrier at this offset in both CTAs of the pair
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    wgrad3x3_pair_kernel(const __grid_constant__ WgradArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const ViewDesc& V = a.view;
+  const uint32_t rank = cluster_ctarank();
+  constexpr int NPLC = 8;  // view planes per CTA: 64 of the pair's 128 input channels
+  const int TP = a.nterms > 1 ? 2 : 1;
+  const int DZPL = pad_px(kTileH * kTileW) * 16;
+  const int kViewPx = kTileH * kHaloW;  // one filter row per CTA pair: 4 x 18 halo pixels
+  const int VPL = pad_px(kViewPx) * 16;
+  const int DZ_BYTES = TP * 16 * DZPL;
+  const int STAGE = DZ_BYTES + TP * NPLC * VPL;
+  constexpr int S = kPStages;
+
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + S;
+  uint64_t* tmem_full = full + 2 * S;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(full + 2 * S + 1);
+  uint8_t* st_base = smem + kHdrBytes;
+
+  int bx = blockIdx.x >> 1;  // the two CTAs of a pair are neighbours in x
+  const int dy0 = bx % 3; bx /= 3;
+  const int npair = a.ncot >> 1;
+  const int co0 = ((bx % npair) * 2 + (int)rank) * 128;
+  const int ci0 = (bx / npair) * 128;
+  const int kt0 = blockIdx.y * a.ktiles_per_cta;
+  const int kt1 = min(a.ktiles, kt0 + a.ktiles_per_cta);
+  const int tmem_cols = 512;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int i = 0; i < S; ++i) { mbar_init(&full[i], kFillThreads + (rank == 0 ? 1 : 0)); mbar_init(&empty[i], 1); }
+      mbar_init(tmem_full, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc_pair(tmem_ptr, tmem_cols);
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0 && rank == 0) {
+      const bool lead = elect_one();
+      const uint32_t idesc = make_idesc(256, 128, 1, 1, 1);  // bf16 x bf16, both operands MN-major, M = 2 x 128
+      const uint64_t a_desc0 = make_smem_desc(smem_u32(st_base), 128, DZPL);
+      const uint64_t b_desc0 = make_smem_desc(smem_u32(st_base) + DZ_BYTES, 128, VPL);
+      const uint32_t stage16 = STAGE >> 4, a_lo16 = (16 * DZPL) >> 4, b_lo16 = (NPLC * VPL) >> 4;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kt = kt0; kt < kt1; ++kt) {
+        mbar_wait_cluster(&full[s], ph);
+        tc_fence_after();
+        const uint64_t a_st = a_desc0 + (uint64_t)(s * stage16);
+        const uint64_t b_st = b_desc0 + (uint64_t)(s * stage16);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const uint32_t d_tmem = tmem_base + dx * 128;
+#pragma unroll
+          for (int r = 0; r < kTileH; ++r) {
+            const uint64_t a_hi = a_st + (uint64_t)(r * kTileW);
+            const uint64_t b_hi = b_st + (uint64_t)(r * kHaloW + dx);
+            const uint32_t acc = (kt != kt0 || r != 0);
+            if (lead) {
+              umma_f16_pair(d_tmem, a_hi, b_hi, idesc, acc);
+              if (a.nterms > 1) {
+                umma_f16_pair(d_tmem, a_hi + a_lo16, b_hi, idesc, 1);
+                umma_f16_pair(d_tmem, a_hi, b_hi + b_lo16, idesc, 1);
+              }
+            }
+          }
+        }
+        if (lead) umma_commit_pair(&empty[s]);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+      if (lead) umma_commit_pair(tmem_full);
+      __syncwarp();
+    } else if (warp == 0) {
+      // rank 1: forward every completed fill phase of this CTA to the MMA issuer's barrier
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kt = kt0; kt < kt1; ++kt) {
+        mbar_wait(&full[s], ph);
+        fence_proxy_async_smem();
+        if (lane == 0) mbar_arrive_remote(&full[s], 0);
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    const int ftid = tid - 128;
+    const int dpl = ftid & 15, dpx0 = ftid >> 4, DG = kFillThreads / 16;      // dz: 16 planes x 64 pixels
+    const int vpl = ftid & (NPLC - 1), vpx0 = ftid / NPLC, VG = kFillThreads / NPLC;  // view: 8 planes x 72 pixels
+    const bool vsecond = ci0 >= V.C0;  // a 128-channel tile never straddles the two sources (pick_nt)
+    const SrcDesc& VS = vsecond ? V.s[1] : V.s[0];
+    const int vcc = (vsecond ? ci0 - V.C0 : ci0) + (int)rank * 64 + vpl * 8;
+    const size_t dz_pix_stride = (size_t)a.Cout * 4;  // dz: [pixel][2 (hi, lo)][Cout] bf16
+    const int dz_lo = a.Cout * 2;
+    const int per_img = a.tiles_h * a.tiles_w;
+    struct CopyItem { int soff, dh, dw, goff; };  // see wgrad3x3_kernel
+    CopyItem cdz[3], cvw[3];
+    const int cvup = VS.mode == SRC_PRESPLIT_UP ? 1 : 0;
+    const int cvHs = VS.Hs, cvWs = VS.Ws;
+    const size_t cvstride = (size_t)VS.C * 4;
+    const int cv_lo = VS.C * 2;
+    const uint8_t* cvbase = reinterpret_cast<const uint8_t*>(VS.ptr);
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int px = dpx0 + u * DG;
+      cdz[u].soff = px < kTileH * kTileW ? dpl * DZPL + px * 16 : -1;
+      cdz[u].dh = px >> 4; cdz[u].dw = px & 15;
+      cdz[u].goff = (cdz[u].dh * V.W + cdz[u].dw) * (int)dz_pix_stride + (co0 + dpl * 8) * 2;
+      const int p = vpx0 + u * VG;
+      const int hr = p / kHaloW, hc = p - hr * kHaloW;
+      cvw[u].soff = p < kViewPx ? DZ_BYTES + vpl * VPL + p * 16 : -1;
+      cvw[u].dh = hr + dy0 - 1; cvw[u].dw = hc - 1;
+      cvw[u].goff = ((cvw[u].dh >> cvup) * cvWs + (cvw[u].dw >> cvup)) * (int)cvstride + vcc * 2;
+    }
+    int s = 0;
+    uint32_t ph = 0;
+    int n_i = kt0 / per_img, th_i = (kt0 - n_i * per_img) / a.tiles_w, tw_i = kt0 - n_i * per_img - th_i * a.tiles_w;
+    for (int kt = kt0; kt < kt1; ++kt) {
+      const int n = n_i, h0 = th_i * kTileH, w0 = tw_i * kTileW;
+      if (++tw_i == a.tiles_w) { tw_i = 0; if (++th_i == a.tiles_h) { th_i = 0; ++n_i; } }
+      mbar_wait(&empty[s], ph ^ 1);
+      uint8_t* stage = st_base + s * STAGE;
+      const uint8_t* dzt = a.dz + ((size_t)(n * V.H + h0) * V.W + w0) * dz_pix_stride;
+      const uint8_t* vwt = cvbase + ((ptrdiff_t)(n * cvHs + (h0 >> cvup)) * cvWs + (w0 >> cvup)) * (ptrdiff_t)cvstride;
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        if (cdz[u].soff >= 0) {
+          const bool ok = h0 + cdz[u].dh < V.H && w0 + cdz[u].dw < V.W;
+          const uint8_t* q = ok ? dzt + cdz[u].goff : a.dz;
+          cp_async16(stage + cdz[u].soff, q, ok ? 16u : 0u, true);
+          if (a.nterms > 1) cp_async16(stage + cdz[u].soff + 16 * DZPL, q + dz_lo, ok ? 16u : 0u, true);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        if (cvw[u].soff >= 0) {
+          const bool ok = (unsigned)(h0 + cvw[u].dh) < (unsigned)V.H && (unsigned)(w0 + cvw[u].dw) < (unsigned)V.W;
+          const uint8_t* q = ok ? vwt + cvw[u].goff : cvbase;
+          cp_async16(stage + cvw[u].soff, q, ok ? 16u : 0u, true);
+          if (a.nterms > 1) cp_async16(stage + cvw[u].soff + NPLC * VPL, q + cv_lo, ok ? 16u : 0u, true);
+        }
+      }
+      cp_async_mbar_arrive_noinc(&full[s]);
+      if (++s == S) { s = 0; ph ^= 1; }
+    }
+
+    if (warp < 8) {
+      const int q = warp & 3;
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      const int row = 32 * q + lane;  // TMEM lane = output channel co0 + row of THIS CTA
+      for (int t = 0; t < 3; ++t) {
+        for (int col0 = 0; col0 < 128; col0 += 16) {
+          uint32_t rg[16];
+          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 128 + col0), rg);
+          tmem_ld_wait();
+          if (kt1 > kt0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int ci = ci0 + col0 + j;
+              if (a.ws != nullptr)  // lanes = consecutive output channels: one 128-byte reduction per warp instruction
+                atomicAdd(a.ws + ((size_t)(dy0 * 3 + t) * V.C + ci) * a.Cout + co0 + row, __uint_as_float(rg[j]));
+              else if (ci < a.CinReal)
+                atomicAdd(a.dw + ((size_t)(co0 + row) * a.CinReal + ci) * 9 + dy0 * 3 + t, __uint_as_float(rg[j]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();  // the peer's tensor core reads this CTA's shared memory until the last commit has landed
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, tmem_cols);
+  }
+}
+
+// =============================================================================================
 // Tap-stacked variant for 64 output channels (the full-resolution layers, where the generic kernel wastes half of
 // every MMA's M = 128 rows on zero planes and runs three CTAs - one per filter row - over the same pixels).
 //
@@ -669,6 +931,23 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
   a.ktiles_per_cta = (a.ktiles + splits - 1) / splits;
   splits = (a.ktiles + a.ktiles_per_cta - 1) / a.ktiles_per_cta;
   const int TP = nterms > 1 ? 2 : 1;
+  auto canon = [](int m) { return m == SRC_PRESPLIT_UP ? (int)SRC_PRESPLIT : m; };
+  const int mode0 = canon(view.s[0].mode), mode1 = canon((view.C0 < view.C) ? view.s[1].mode : view.s[0].mode);
+  ProfScope prof(PROF_WGRAD, st, view.N, view.H, view.W, view.C, Cout);
+  // CTA pairs (cta_group::2) share the view operand: 256 output channels x one 128-channel input tile per pair.
+  // variant bit 64 / TNB_WGRAD_PAIR=0 force the single-CTA kernel (tests, ablation).
+  static const int pair_env = [] { const char* e = getenv("TNB_WGRAD_PAIR"); return e ? atoi(e) : 1; }();
+  if (pair_env && !(variant & 64) && Cout % 256 == 0 && a.NT == 128 && a.ndy == 1 && mode0 == SRC_PRESPLIT &&
+      mode1 == SRC_PRESPLIT) {
+    const size_t psmem = kHdrBytes + kPStages * (size_t)(TP * 16 * pad_px(kTileH * kTileW) * 16 +
+                                                         TP * 8 * pad_px(kTileH * kHaloW) * 16);
+    TNB_REQUIRE(psmem <= 232448, "wgrad3x3 (pair): shared memory plan too large (%zu)", psmem);
+    TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+    wgrad3x3_pair_kernel<<<dim3(gx, splits), kThreads, psmem, st>>>(a);  // gx = ncot * ncit * 3 with ncot even
+    TNB_CHECK_CUDA(cudaGetLastError());
+    if (ws != nullptr) return launch_wgrad_scatter(ws, dw, Cout, view.C, CinReal, 0, st);
+    return 0;
+  }
   const size_t smem = kHdrBytes + kStages * (size_t)(TP * 16 * pad_px(kTileH * kTileW) * 16 +
                                                      TP * (a.NT / 8) * pad_px((kTileH + a.ndy - 1) * kHaloW) * 16);
   TNB_REQUIRE(smem <= 232448, "wgrad3x3: shared memory plan too large (%zu)", smem);
@@ -676,8 +955,6 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
   // (pick_nt keeps every CTA inside one source), but the kernel is instantiated per mode -> require equal modes or
   // fall back to the first source's mode only when the second source is unused
   // a half-resolution pre-split source differs from a full-resolution one by an address shift only: same instantiation
-  auto canon = [](int m) { return m == SRC_PRESPLIT_UP ? (int)SRC_PRESPLIT : m; };
-  const int mode0 = canon(view.s[0].mode), mode1 = canon((view.C0 < view.C) ? view.s[1].mode : view.s[0].mode);
   auto launch = [&](auto tag, const WgradArgs& args, int gx_first, int gx_count) -> int {
     constexpr int M = decltype(tag)::value;
     TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -695,7 +972,6 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
       default: tnb::set_last_error("wgrad3x3: bad view mode %d", mode); return -2;
     }
   };
-  ProfScope prof(PROF_WGRAD, st, view.N, view.H, view.W, view.C, Cout);
   if (mode0 == mode1) {
     if (int rc = dispatch(mode0, a, gx)) return rc;
   } else {
