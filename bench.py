@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="fp32x3", choices=["fp32x3", "tf32like"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-launch", action="store_true", help="print the mean duration of every profiled launch to stderr")
     ap.add_argument("--variant", type=int, default=0, help="kernel experiment bits (tnb_tracknet_cfg_t.variant)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -271,6 +272,15 @@ def main():
             fl = 2.0 * n * hh * ww * cin_alg * cout * 9
         e = per_kind.setdefault(k, [0.0, 0.0, 0])
         e[0] += kms[i]; e[1] += fl; e[2] += 1
+    if args.per_launch:  # diagnosis: median duration of every profiled launch of a step, in launch order (stderr)
+        per_step = max(nrec, 0) // prof_steps
+        for j in range(per_step):
+            k, n, hh, ww, cin, cout = (desc[6 * j + t] for t in range(6))
+            runs = sorted(kms[j + per_step * r] for r in range(prof_steps))
+            ms = runs[len(runs) // 2]  # median over the profiled steps
+            fl = 2.0 * n * hh * ww * (IN_DIM if (k != 1 and cin == 32) else cin) * cout * 9 if k in (0, 1, 2) else 0.0
+            print(f"launch {j:3d} {kinds.get(k, k):14s} n={n} {hh}x{ww} {cin}->{cout}: {ms:.4f} ms (min {runs[0]:.4f} max {runs[-1]:.4f})"
+                  + (f"  {fl / ms / 1e9:7.1f} TFLOP/s-alg" if fl else ""), file=sys.stderr)
     breakdown = {kinds.get(k, str(k)): {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[2] / prof_steps,
                                         "tflops": (v[1] / (v[0] * 1e-3) / 1e12) if v[0] > 0 and v[1] > 0 else None}
                  for k, v in sorted(per_kind.items())}

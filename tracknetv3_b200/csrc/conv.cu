@@ -38,6 +38,7 @@ struct ConvArgs {
   const float *bz, *bsc, *bsh, *bmu, *bis;
   int Cout, BN, MT, SA, SB, G, nbuf, nterms, variant, tmem_cols;  // G: filter taps per weight stage (1 or 3)
   int tiles_h, tiles_w, ntiles, nwork;
+  int merged;  // weights packed [plane][hi | lo][BN rows]: x_hi * [w_hi | w_lo] is ONE MMA of width 2 * BN (see conv3x3_merged)
   int tall;  // tile orientation: 0 = 16 rows x 8*MT columns (halo tile row-major), 1 = 8*MT rows x 16 columns
              // (halo tile column-major: the 8-pixel core-matrix groups then run down the image)
 };
@@ -72,10 +73,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
   const int PLANE = pad_px(HALO_PX) * 16;  // bytes
   const int TP = a.nterms > 1 ? 2 : 1;     // operand term planes stored (hi[,lo])
   const int A_STAGE = TP * 4 * PLANE;
-  const int B_TAP = TP * 64 * BN;          // bytes of one tap: [term][4 planes][BN][16B]
+  const bool MG = a.merged != 0;
+  const int B_TAP = (MG ? 2 : TP) * 64 * BN;  // bytes of one tap: [term][4 planes][BN][16B], merged: [4 planes][term][BN][16B]
   const int B_STAGE = a.G * B_TAP;         // a stage holds G consecutive taps of one 32-channel chunk
   const int nchunks = V.C / 32;
-  const int BUFCOLS = MT * BN;
+  const int ACCW = (MG && a.nterms > 1) ? 2 * BN : BN;  // TMEM columns per M tile (merged: [x*w_hi + x_lo*w_hi | x_hi*w_lo])
+  const int BUFCOLS = MT * ACCW;
 
   uint64_t* full_A = reinterpret_cast<uint64_t*>(smem);       // [4]
   uint64_t* empty_A = full_A + 4;                             // [4]
@@ -121,7 +124,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
       // A: K-major planar halo tile. LBO = plane stride (next 8 channels), SBO = halo row pitch (next 8 output
       // pixels = next image row of the 16x8 tile). B: K-major packed weights. variant bits swap them (probe).
       uint32_t a_lbo = PLANE, a_sbo = PITCH * 16;
-      uint32_t b_lbo = BN * 16, b_sbo = 128;
+      uint32_t b_lbo = (MG ? 2 : 1) * BN * 16, b_sbo = 128;
+      const uint32_t idesc2 = make_idesc(128, 2 * BN, FMT, 0, 0);  // merged: B = [w_hi | w_lo], 2 * BN rows per plane
       if (a.variant & 1) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; }
       if (a.variant & 2) { uint32_t t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
       // descriptors are base + (byte offset >> 4): the start-address field never carries into the next field
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
       const uint64_t b_desc0 = make_smem_desc(smem_u32(b_base), b_lbo, b_sbo);
       const uint32_t a_stage16 = A_STAGE >> 4, b_stage16 = B_STAGE >> 4, b_tap16 = B_TAP >> 4;
       const uint32_t a_k16 = (2 * PLANE) >> 4, a_lo16 = (4 * PLANE) >> 4;
-      const uint32_t b_k16 = (2 * BN * 16) >> 4, b_lo16 = (4 * BN * 16) >> 4;
+      const uint32_t b_k16 = (2 * b_lbo) >> 4, b_lo16 = MG ? (uint32_t)(BN * 16) >> 4 : (uint32_t)(4 * BN * 16) >> 4;
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       int k = 0;
@@ -151,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
             // (G taps x 2 K-steps x nterms), then the next tile. Measured: the tensor pipe retires a chain into one
             // accumulator at full rate but pays a drain when the accumulator changes, so short chains starve it.
             for (int mt = 0; mt < MT; ++mt) {
-              const uint32_t d_tmem = d_buf + mt * BN;
+              const uint32_t d_tmem = d_buf + mt * ACCW;
               for (int tg = 0; tg < a.G; ++tg) {
                 const int t = t0 + tg;
                 const int dy = t / 3, dx = t - dy * 3;
@@ -163,10 +167,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
                   const uint64_t b_hi = b_tap + (uint64_t)(kk * b_k16);
                   const uint32_t acc = (c | t | kk) != 0;
                   if (lead && !(a.variant & 4)) {
-                    umma_f16(d_tmem, a_hi, b_hi, idesc, acc);
-                    if (a.nterms > 1) {
+                    if (MG && a.nterms > 1) {
+                      // x_hi * [w_hi | w_lo] in one MMA of width 2 * BN (the A tile is read once for both products),
+                      // then x_lo * w_hi into the first half; the epilogue adds the two halves
+                      umma_f16(d_tmem, a_hi, b_hi, idesc2, acc);
                       umma_f16(d_tmem, a_hi + a_lo16, b_hi, idesc, 1);
-                      umma_f16(d_tmem, a_hi, b_hi + b_lo16, idesc, 1);
+                    } else {
+                      umma_f16(d_tmem, a_hi, b_hi, idesc, acc);
+                      if (a.nterms > 1) {
+                        umma_f16(d_tmem, a_hi + a_lo16, b_hi, idesc, 1);
+                        umma_f16(d_tmem, a_hi, b_hi + b_lo16, idesc, 1);
+                      }
                     }
                   }
                 }
@@ -254,11 +265,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
             }
           }
           uint32_t rg[32];
-          tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * BUFCOLS + mt * BN + col0), rg);
+          tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * BUFCOLS + mt * ACCW + col0), rg);
           tmem_ld_wait();
           float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rg[i]) * out_mul;
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rg[i]);
+          if (ACCW != BN) {  // merged weights: the x_hi * w_lo products sit BN columns further
+            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * BUFCOLS + mt * ACCW + BN + col0), rg);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(rg[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= out_mul;
           if (valid) {
             float4* dst = reinterpret_cast<float4*>(a.out + ((size_t)(n * V.H + h) * V.W + w) * a.Cout + n0 + col0);
 #pragma unroll
@@ -451,12 +470,24 @@ static int num_sms() {
   return n;
 }
 
+// 64-wide output tiles: an M = 128, N = 64 MMA reads (128 + 64) x 32 B of shared memory (48 clocks at 128 B/clk) for 32
+// clocks of math, so the three MMAs of a split product cost 144 clocks per K step. With the weights packed
+// [plane][hi | lo][64 rows], x_hi * [w_hi | w_lo] is ONE MMA of width 128 (64 clocks of math = 64 of operand reads)
+// and x_lo * w_hi a second one: 112 clocks, at the price of 2 x 64 accumulator columns per tile (MT <= 2).
+// TNB_CONV_MERGE=0 restores the three-MMA form (ablation).
+bool conv3x3_merged(int BN) {
+  static const int on = [] { const char* e = getenv("TNB_CONV_MERGE"); return e ? atoi(e) : 1; }();
+  return on && BN == 64;
+}
+
 int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* plan, bool bn_bwd_fused) {
   TNB_REQUIRE(Cin % 32 == 0, "conv3x3: view channels %d must be a multiple of 32", Cin);
   const int BN = pick_bn(Cout);
   TNB_REQUIRE(BN >= 32 && BN % 16 == 0, "conv3x3: unsupported output channel count %d", Cout);
   const int TP = nterms > 1 ? 2 : 1;
-  int MT = 512 / BN;
+  const bool merged = conv3x3_merged(BN);
+  const int ACCW = (merged && nterms > 1) ? 2 * BN : BN;  // accumulator columns per M tile
+  int MT = 512 / ACCW;
   if (MT > 4) MT = 4;
   // Two accumulator buffers in TMEM (2 * MT * BN <= 512 columns) let the epilogue of tile i overlap the MMAs of tile
   // i + 1; with one buffer it is exposed (7-17 % of the layer, measured: profiles/r1_summary.md 6). Narrower tiles
@@ -464,7 +495,7 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
   // pays even for the 768-channel layer (0.669 -> 0.604 ms). TNB_CONV_PLAN=0 restores the widest tile, =2 keeps the
   // double buffering but forces the row-major orientation (tools/ablate_plan.py).
   static const int plan_mode = [] { const char* e = getenv("TNB_CONV_PLAN"); return e ? atoi(e) : 1; }();
-  if (plan_mode != 0) while (MT > 1 && 2 * MT * BN > 512) MT >>= 1;
+  if (plan_mode != 0) while (MT > 1 && 2 * MT * ACCW > 512) MT >>= 1;
   // Orientation: M = 128 rows of the MMA are 16 groups of 8 consecutive pixels. Groups along W stacked over 16 image rows
   // give a 16 x 8*MT tile; groups along H stacked over 16 image columns give an 8*MT x 16 tile. Take the one that pads
   // the image less: at 72 x 128 and 36 x 64 (H = 4.5 and 2.25 tiles of 16 rows) the tall-group tile wastes 0 / 10 %
@@ -487,7 +518,7 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
     for (MT = mt_max; MT >= 1; --MT) {
       const int pitch = 8 * MT + 2, halo = 18 * pitch;
       const size_t a_stage = (size_t)TP * 4 * pad_px(halo) * 16;
-      const size_t b_stage = (size_t)g * TP * 64 * BN;
+      const size_t b_stage = (size_t)g * (merged ? 2 : TP) * 64 * BN;
       const size_t fixed = kHdrBytes + ((halo * 8 + 127) & ~127) + (size_t)4 * 2 * BN * 4 + (bn_bwd_fused ? BN * 16 : 0) +
                            SA * a_stage;
       if (fixed + 2 * b_stage <= (size_t)kMaxSmem) {
@@ -503,8 +534,9 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
   }
   TNB_REQUIRE(found, "conv3x3: no shared-memory plan for Cin=%d Cout=%d", Cin, Cout);
   plan->BN = BN; plan->MT = MT; plan->SA = SA; plan->SB = SB; plan->G = G;
-  plan->nbuf = (2 * MT * BN <= 512) ? 2 : 1;
-  plan->tmem_cols = pow2_cols(plan->nbuf * MT * BN);
+  plan->nbuf = (2 * MT * ACCW <= 512) ? 2 : 1;
+  plan->tmem_cols = pow2_cols(plan->nbuf * MT * ACCW);
+  plan->merged = merged ? 1 : 0;
   plan->smem_bytes = smem;
   plan->tall = tall ? 1 : 0;
   plan->tiles_h = tall ? (H + 8 * MT - 1) / (8 * MT) : (H + 15) / 16;
@@ -535,7 +567,7 @@ int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, floa
     a.bz = fuse->z; a.bsc = fuse->scale; a.bsh = fuse->shift; a.bmu = fuse->mean; a.bis = fuse->invstd;
   }
   a.Cout = Cout; a.BN = p.BN; a.MT = p.MT; a.SA = p.SA; a.SB = p.SB; a.G = p.G; a.nbuf = p.nbuf; a.nterms = nterms;
-  a.variant = variant | (cp_async_ca_env() ? 256 : 0); a.tmem_cols = p.tmem_cols; a.tiles_h = p.tiles_h; a.tiles_w = p.tiles_w; a.tall = p.tall;
+  a.variant = variant | (cp_async_ca_env() ? 256 : 0); a.tmem_cols = p.tmem_cols; a.tiles_h = p.tiles_h; a.tiles_w = p.tiles_w; a.tall = p.tall; a.merged = p.merged;
   a.ntiles = view.N * p.tiles_h * p.tiles_w;
   a.nwork = a.ntiles * (Cout / p.BN);
   const int grid = a.nwork < num_sms() ? a.nwork : num_sms();

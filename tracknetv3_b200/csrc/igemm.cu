@@ -30,12 +30,13 @@ namespace tnb {
 
 // =============================================================================================
 // weight packing: OIHW fp32 -> per (n-tile, k-chunk, tap) smem images [term][plane(4)][BN][8] (uint16)
+// (64-wide tiles: [plane(4)][term][BN][8], see conv3x3_merged)
 // mode 0 (forward):  B[n = co][k = ci] = W[co][ci][dy][dx]
 // mode 1 (dgrad):    B[n = ci][k = co] = W[co][ci][2-dy][2-dx]      (180-degree rotated, transposed)
 // =============================================================================================
 template <int FMT>
 __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Co, int Ci,
-                                    int Nside, int Kpad, int BN, int mode) {
+                                    int Nside, int Kpad, int BN, int mode, int merged) {
   const int nchunks = Kpad / 32;
   const long long total = (long long)(Nside / BN) * nchunks * 9 * 4 * BN;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -64,8 +65,11 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __res
     split8<FMT>(v, hi, lo);
     // stage base (uint16 elements): ((ntile*nchunks + chunk)*9 + tap) * (2*4*BN*8)
     const size_t stage = (((size_t)ntile * nchunks + chunk) * 9 + tap) * (size_t)(64 * BN);
-    uint4* dst_hi = reinterpret_cast<uint4*>(out + stage + ((size_t)plane * BN + nl) * 8);
-    uint4* dst_lo = reinterpret_cast<uint4*>(out + stage + (size_t)32 * BN + ((size_t)plane * BN + nl) * 8);
+    // [term][plane][BN rows][8], or for the merged 64-wide tiles [plane][term][BN rows][8] (conv3x3_merged): hi and lo
+    // rows of a plane are then one operand of 2 * BN rows
+    uint4* dst_hi = reinterpret_cast<uint4*>(out + stage + (merged ? ((size_t)plane * 2 * BN + nl) * 8 : ((size_t)plane * BN + nl) * 8));
+    uint4* dst_lo = reinterpret_cast<uint4*>(out + stage + (merged ? ((size_t)(plane * 2 + 1) * BN + nl) * 8
+                                                                   : (size_t)32 * BN + ((size_t)plane * BN + nl) * 8));
     *dst_hi = hi;
     *dst_lo = lo;
   }
@@ -85,10 +89,11 @@ int launch_pack_weights(const float* w, uint16_t* out, int Co, int Ci, int mode,
   const long long total = (long long)(Nside / BN) * (Kpad / 32) * 9 * 4 * BN;
   const int threads = 256;
   const int blocks = (int)((total + threads - 1) / threads);
+  const int merged = conv3x3_merged(BN) ? 1 : 0;  // the layout is a function of the tile width alone
   if (fmt == 0)
-    pack_weights_kernel<0><<<blocks, threads, 0, st>>>(w, out, Co, Ci, Nside, Kpad, BN, mode);
+    pack_weights_kernel<0><<<blocks, threads, 0, st>>>(w, out, Co, Ci, Nside, Kpad, BN, mode, merged);
   else
-    pack_weights_kernel<1><<<blocks, threads, 0, st>>>(w, out, Co, Ci, Nside, Kpad, BN, mode);
+    pack_weights_kernel<1><<<blocks, threads, 0, st>>>(w, out, Co, Ci, Nside, Kpad, BN, mode, merged);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -141,13 +141,14 @@ __host__ __device__ inline int pad_px(int px) {  // plane stride = 2 (mod 8) pix
 }
 
 struct ConvPlan {
-  int BN, MT, SA, SB, G, nbuf, tmem_cols;
+  int BN, MT, SA, SB, G, nbuf, tmem_cols, merged;
   size_t smem_bytes;
   int tiles_h, tiles_w;
   int tall;  // tile orientation, see conv3x3_plan
 };
 // fmt: 0 = fp16 split, 1 = bf16 split. nterms: 1 (single pass) or 3 (hi*hi + lo*hi + hi*lo).
 // bn_bwd_fused: reserve the per-channel constant table of the fused BatchNorm-backward reduction (dgrad epilogue)
+bool conv3x3_merged(int BN);  // weights of this tile width are packed [plane][hi | lo][BN] (one MMA for x_hi * [w_hi | w_lo])
 int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* plan, bool bn_bwd_fused = false);
 size_t conv3x3_wpack_elems(int Kside, int Nside);  // uint16 elements of a packed weight buffer
 int launch_pack_weights(const float* w_oihw, uint16_t* out, int Co, int Ci, int mode /*0 fwd, 1 dgrad*/,

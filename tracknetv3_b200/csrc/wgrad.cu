@@ -369,6 +369,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
 // kFillThreads + 1) with a cluster-scope release arrive.
 // =============================================================================================
 static constexpr int kPStages = 4;
+// plane stride in pixels: 0 = pad_px (2 mod 8), 1 = multiple of 8 (128-byte aligned planes), 2 = 1 mod 8, 3 = 4 mod 8
+__host__ __device__ inline int pad_sel(int px, int mode) {
+  if (mode == 0) return pad_px(px);
+  const int r = px & 7, want = mode == 1 ? 0 : mode == 2 ? 1 : 4;
+  return px + ((want - r) & 7);
+}
 
 TNB_DEVINL uint32_t cluster_ctarank() {
   uint32_t r;
@@ -434,9 +440,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   const uint32_t rank = cluster_ctarank();
   constexpr int NPLC = 8;  // view planes per CTA: 64 of the pair's 128 input channels
   const int TP = a.nterms > 1 ? 2 : 1;
-  const int DZPL = pad_px(kTileH * kTileW) * 16;
+  const int padm = (a.variant >> 7) & 3;  // experiment: plane stride padding (0 = pad_px)
+  const int DZPL = pad_sel(kTileH * kTileW, padm) * 16;
   const int kViewPx = kTileH * kHaloW;  // one filter row per CTA pair: 4 x 18 halo pixels
-  const int VPL = pad_px(kViewPx) * 16;
+  const int VPL = pad_sel(kViewPx, padm) * 16;
   const int DZ_BYTES = TP * 16 * DZPL;
   const int STAGE = DZ_BYTES + TP * NPLC * VPL;
   constexpr int S = kPStages;
@@ -493,7 +500,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             const uint64_t a_hi = a_st + (uint64_t)(r * kTileW);
             const uint64_t b_hi = b_st + (uint64_t)(r * kHaloW + dx);
             const uint32_t acc = (kt != kt0 || r != 0);
-            if (lead) {
+            if (lead && !(a.variant & 4)) {
               umma_f16_pair(d_tmem, a_hi, b_hi, idesc, acc);
               if (a.nterms > 1) {
                 umma_f16_pair(d_tmem, a_hi + a_lo16, b_hi, idesc, 1);
@@ -559,6 +566,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       uint8_t* stage = st_base + s * STAGE;
       const uint8_t* dzt = a.dz + ((size_t)(n * V.H + h0) * V.W + w0) * dz_pix_stride;
       const uint8_t* vwt = cvbase + ((ptrdiff_t)(n * cvHs + (h0 >> cvup)) * cvWs + (w0 >> cvup)) * (ptrdiff_t)cvstride;
+      if (!(a.variant & 8)) {  // (ablation bit 8: barrier traffic only)
 #pragma unroll
       for (int u = 0; u < 3; ++u) {
         if (cdz[u].soff >= 0) {
@@ -576,6 +584,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           cp_async16(stage + cvw[u].soff, q, ok ? 16u : 0u, true);
           if (a.nterms > 1) cp_async16(stage + cvw[u].soff + NPLC * VPL, q + cv_lo, ok ? 16u : 0u, true);
         }
+      }
       }
       cp_async_mbar_arrive_noinc(&full[s]);
       if (++s == S) { s = 0; ph ^= 1; }
@@ -939,8 +948,9 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
   static const int pair_env = [] { const char* e = getenv("TNB_WGRAD_PAIR"); return e ? atoi(e) : 1; }();
   if (pair_env && !(variant & 64) && Cout % 256 == 0 && a.NT == 128 && a.ndy == 1 && mode0 == SRC_PRESPLIT &&
       mode1 == SRC_PRESPLIT) {
-    const size_t psmem = kHdrBytes + kPStages * (size_t)(TP * 16 * pad_px(kTileH * kTileW) * 16 +
-                                                         TP * 8 * pad_px(kTileH * kHaloW) * 16);
+    const int padm = (variant >> 7) & 3;
+    const size_t psmem = kHdrBytes + kPStages * (size_t)(TP * 16 * pad_sel(kTileH * kTileW, padm) * 16 +
+                                                         TP * 8 * pad_sel(kTileH * kHaloW, padm) * 16);
     TNB_REQUIRE(psmem <= 232448, "wgrad3x3 (pair): shared memory plan too large (%zu)", psmem);
     TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
     wgrad3x3_pair_kernel<<<dim3(gx, splits), kThreads, psmem, st>>>(a);  // gx = ncot * ncit * 3 with ncot even
