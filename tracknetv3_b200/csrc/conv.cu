@@ -524,7 +524,7 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
       if (fixed + 2 * b_stage <= (size_t)kMaxSmem) {
         G = g;
         SB = (int)((kMaxSmem - fixed) / b_stage);
-        const int cap = g == 3 ? 3 : 8;
+        const int cap = g == 3 ? 3 : 8;  // deeper rings measured no better (cap 5), one tap per slot clearly worse
         if (SB > cap) SB = cap;
         smem = fixed + SB * b_stage;
         found = true;

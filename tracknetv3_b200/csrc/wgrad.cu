@@ -369,10 +369,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
 // kFillThreads + 1) with a cluster-scope release arrive.
 // =============================================================================================
 static constexpr int kPStages = 4;
-// plane stride in pixels: 0 = pad_px (2 mod 8), 1 = multiple of 8 (128-byte aligned planes), 2 = 1 mod 8, 3 = 4 mod 8
+// plane stride in pixels: mode 0 = 1 (mod 8) pixels, the fastest fill measured (256->256: 0.221 ms; 2 (mod 8) = pad_px
+// 0.226, 4 (mod 8) 0.248, 128-byte aligned planes 0.338: the cp.async stores of neighbouring planes then collide).
+// Modes 1-3 (variant bits 7-8) keep the other strides reachable for tools/ablate_pair.py.
 __host__ __device__ inline int pad_sel(int px, int mode) {
-  if (mode == 0) return pad_px(px);
-  const int r = px & 7, want = mode == 1 ? 0 : mode == 2 ? 1 : 4;
+  const int r = px & 7, want = mode == 0 ? 1 : mode == 1 ? 0 : mode == 2 ? 2 : 4;
   return px + ((want - r) & 7);
 }
 
