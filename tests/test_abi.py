@@ -44,7 +44,10 @@ def test_workspace_and_plan_queries():
     eval_bytes = lib.tnb_tracknet_workspace_bytes(C.byref(cfg))
     assert 0 < eval_bytes < train_bytes < 16 * 2 ** 30
     assert lib.tnb_conv3x3_wpack_elems(27, 64) == 64 * 32 * 9 * 2
-    assert lib.tnb_conv3x3_stat_rows(10, 288, 512, 64, 64, 3) == 10 * 18 * 16  # 16x32-pixel CTA tiles
+    # 64-wide tiles keep two accumulator halves per M tile (x_hi * [w_hi | w_lo] in one MMA): 16x16-pixel CTA tiles;
+    # 128-wide tiles: 16x16 as well (2 buffers x 2 M tiles x 128 columns)
+    assert lib.tnb_conv3x3_stat_rows(10, 288, 512, 64, 64, 3) == 10 * 18 * 32
+    assert lib.tnb_conv3x3_stat_rows(10, 144, 256, 128, 128, 3) == 10 * 9 * 16
     assert lib.tnb_tracknet_num_launches(C.byref(cfg), 0) == 53
     assert lib.tnb_heatmap_decode_workspace_bytes(256, 288, 512) == 256 * 5 * 288 * 512 * 4
 
