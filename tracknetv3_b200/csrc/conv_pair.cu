@@ -1,20 +1,19 @@
-// Persistent tcgen05 implicit-GEMM 3x3 convolution (forward and dgrad) for sm_100a.
+// CTA-pair variant of the persistent tcgen05 implicit-GEMM 3x3 convolution (forward and dgrad) - EXPERIMENTAL, off by
+// default (TNB_CONV_PAIR=1), not yet run on a GPU. conv.cu holds the validated single-CTA kernel; this file is the same
+// kernel body with the pair protocol of wgrad3x3_pair_kernel (wgrad.cu) added, kept in its own translation unit so that
+// the shipped kernel's code stays byte-identical until the pair version has been measured:
 //
-// Replaces cuDNN's nn.Conv2d(3x3, padding='same', bias=False) forward (reference model.py:8,13) and its
-// autograd dgrad (reference train.py:95), with BatchNorm-apply + ReLU (model.py:14-15), MaxPool2d
-// (model.py:59,61,63) and Upsample + torch.cat (model.py:65,67,69) of the producing layers fused into the
-// operand gather, and the BatchNorm statistics of the output fused into the epilogue.
-//
-// One CTA per SM loops over (pixel tile, channel tile) work items:
-//   warp 0      one elected thread issues tcgen05.mma (kind::f16, M=128, N=BN, K=16; 3 MMAs per K step in the
-//               fp32-faithful hi/lo split mode) into one of up to two TMEM accumulator buffers
-//   warp 1      weight tiles: 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx) of pre-packed smem images
-//   warps 2-5   epilogue: tcgen05.ld -> fp32 NHWC stores + per-channel (sum, sumsq) partials; overlaps the
-//               next tile's MMAs when two accumulator buffers fit in TMEM (2*MT*BN <= 512 columns)
-//   warps 6-11  operand producers: batched global gathers -> BN affine/ReLU/pool/upsample/concat ->
-//               16-bit hi/lo split -> planar smem halo tile -> fence.proxy.async -> mbarrier
-// The planar tile [plane = 8 channels][pixel][16 B] is a SWIZZLE_NONE K-major operand in which every 3x3 tap
-// is just a different 16-byte aligned start address: one halo tile serves all 9 taps.
+//   * clusters of two CTAs (the two SMs of a TPC) work on two M tiles of the same output-channel tile; each CTA
+//     gathers its own halo tile and loads HALF of every weight stage (output-channel rows [rank * BN/2, +BN/2) of each
+//     plane; tap images packed [rank][term][plane][BN/2 rows][8], launch_pack_weights layout 2);
+//   * rank 0 issues every MMA as tcgen05.mma.cta_group::2 with M = 256 (TMEM lanes 0-127 of each CTA = that CTA's 128
+//     pixels) and multicasts the commits to both CTAs' empty_A / empty_B / tmem_full barriers;
+//   * rank 1's warp 0 relays its full_A / full_B phases to rank 0's barriers (expected counts + 1), rank 1's epilogue
+//     warps arrive on rank 0's tmem_empty (count 8);
+//   * an odd number of M tiles leaves rank 1 of the last pair a duplicate of the last tile with all stores off.
+// Why: the weights are the larger part of the L2 -> SM traffic of these kernels (590 KB per 256-pixel tile on a
+// 128 -> 128 layer against 166 KB of activations), an N = 128 MMA reads 64 clocks of operands for 64 of math, and the
+// 64-wide layers are bound by per-stage handshakes (profiles/r1_final.md section 10): a pair halves all three per SM.
 #include "igemm.cuh"
 #include <cstdlib>
 #include "prof.cuh"
@@ -28,7 +27,7 @@ static constexpr int kEpiThreads = 128;
 static constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 static constexpr int kHdrBytes = 512;
 
-struct ConvArgs {
+struct ConvPairArgs {
   ViewDesc view;
   const uint16_t* wpack;
   float* out;        // [N,H,W,Cout]
@@ -38,6 +37,7 @@ struct ConvArgs {
   const float *bz, *bsc, *bsh, *bmu, *bis;
   int Cout, BN, MT, SA, SB, G, nbuf, nterms, variant, tmem_cols;  // G: filter taps per weight stage (1 or 3)
   int tiles_h, tiles_w, ntiles, nwork;
+  int ntiles_p, nwork_p;  // CTA-pair kernel: pairs of M tiles per n-tile, pair work items (see conv3x3_kernel<..., PAIR>)
   int merged;  // weights packed [plane][hi | lo][BN rows]: x_hi * [w_hi | w_lo] is ONE MMA of width 2 * BN (see conv3x3_merged)
   int tall;  // tile orientation: 0 = 16 rows x 8*MT columns (halo tile row-major), 1 = 8*MT rows x 16 columns
              // (halo tile column-major: the 8-pixel core-matrix groups then run down the image)
@@ -60,11 +60,37 @@ TNB_DEVINL float warp_transpose_sum(float (&v)[32], int lane) {
 
 // M0 / M1: gather modes of the (up to two) concatenated view sources, compile-time so that every instantiation carries
 // only the gather paths it needs (the producers are register-limited; a run-time switch over all modes costs spills)
-template <int FMT, int M0, int M1, bool BWD = false>
-__global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_constant__ ConvArgs a) {
+//
+// PAIR (experimental, TNB_CONV_PAIR=1; launched as clusters of two CTAs): the two CTAs of a pair work on two M tiles of
+// the same output-channel tile and share the weight operand through tcgen05 cta_group::2 - each CTA gathers its own
+// halo tile and loads HALF of every weight stage (rows [rank * BN/2, +BN/2) of each plane), rank 0 issues every MMA
+// with M = 256 and multicasts the commits; rank 1's warp 0 relays its full_A / full_B phases to rank 0's barriers and
+// rank 1's epilogue warps arrive on rank 0's tmem_empty. Same protocol as wgrad3x3_pair_kernel (wgrad.cu).
+template <int FMT, int M0, int M1>
+__global__ void __launch_bounds__(kThreads, 1) conv3x3_pair_kernel(const __grid_constant__ ConvPairArgs a) {
+  constexpr bool PAIR = true, BWD = false;  // the body is conv3x3_kernel's (conv.cu) with the pair protocol switched on
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  // persistent loop over work items: (M tile, n-tile), or for PAIR (pair of M tiles, n-tile) per pair of CTAs
+  const int wstart = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int wstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int wcount = PAIR ? a.nwork_p : a.nwork;
+  // work item -> (n-tile, M tile of THIS CTA, dummy): an odd tile count leaves rank 1 of the last pair without a tile;
+  // it then repeats the last one (the pair must stay in lock step) with every global store switched off
+  auto decode_work = [&](int work, int& nt, int& tile, bool& dummy) {
+    if (PAIR) {
+      nt = work / a.ntiles_p;
+      tile = 2 * (work - nt * a.ntiles_p) + rank;
+      dummy = tile >= a.ntiles;
+      if (dummy) tile = a.ntiles - 1;
+    } else {
+      nt = work / a.ntiles;
+      tile = work - nt * a.ntiles;
+      dummy = false;
+    }
+  };
 
   const ViewDesc& V = a.view;
   const int MT = a.MT, BN = a.BN;
@@ -74,7 +100,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
   const int TP = a.nterms > 1 ? 2 : 1;     // operand term planes stored (hi[,lo])
   const int A_STAGE = TP * 4 * PLANE;
   const bool MG = a.merged != 0;
-  const int B_TAP = (MG ? 2 : TP) * 64 * BN;  // bytes of one tap: [term][4 planes][BN][16B], merged: [4 planes][term][BN][16B]
+  const int BROWS = PAIR ? BN / 2 : BN;    // weight rows (output channels) held by THIS CTA
+  const int B_TAP = (MG ? 2 : TP) * 64 * BROWS;  // bytes of one tap: [term][4 planes][rows][16B], merged: [4 planes][term][rows][16B]
   const int B_STAGE = a.G * B_TAP;         // a stage holds G consecutive taps of one 32-channel chunk
   const int nchunks = V.C / 32;
   const int ACCW = (MG && a.nterms > 1) ? 2 * BN : BN;  // TMEM columns per M tile (merged: [x*w_hi + x_lo*w_hi | x_hi*w_lo])
@@ -97,16 +124,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
   // ---- one-time setup ----
   if (warp == 0) {
     if (elect_one()) {
-      for (int i = 0; i < a.SA; ++i) { mbar_init(&full_A[i], kFillThreads); mbar_init(&empty_A[i], 1); }
-      for (int i = 0; i < a.SB; ++i) { mbar_init(&full_B[i], 1); mbar_init(&empty_B[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+      // PAIR, rank 0: one extra arrival per phase from rank 1's relay (full_A, full_B) / 4 more from its epilogue warps
+      const int extra = (PAIR && rank == 0) ? 1 : 0;
+      for (int i = 0; i < a.SA; ++i) { mbar_init(&full_A[i], kFillThreads + extra); mbar_init(&empty_A[i], 1); }
+      for (int i = 0; i < a.SB; ++i) { mbar_init(&full_B[i], 1 + extra); mbar_init(&empty_B[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 + 4 * extra); }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr, a.tmem_cols);
+    if (PAIR) tmem_alloc_pair(tmem_ptr, a.tmem_cols); else tmem_alloc(tmem_ptr, a.tmem_cols);
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // both CTAs' barriers initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   // dgrad: dz is multiplied by a power of two on the way in (so that its fp16 hi/lo split keeps ~22 bits) and
@@ -114,17 +144,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
   const float in_mul = (V.s[0].mode == SRC_IDENTITY) ? pow2_scale_for(V.s[0].scale) : 1.f;
   const float out_mul = 1.f / in_mul;
 
-  if (warp == 0) {
+  if (PAIR && warp == 0 && rank != 0) {
+    // =========================== rank 1 of a pair: relay ===========================
+    // forward every completed fill phase of this CTA (halo tile, weight half) to the MMA issuer's barriers, in the
+    // order in which the issuer waits for them
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
+    for (int work = wstart; work < wcount; work += wstep) {
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(&full_A[sa], pha);
+        fence_proxy_async_smem();
+        if (lane == 0) mbar_arrive_remote(&full_A[sa], 0);
+        __syncwarp();
+        for (int t0 = 0; t0 < 9; t0 += a.G) {
+          mbar_wait(&full_B[sb], phb);
+          if (lane == 0) mbar_arrive_remote(&full_B[sb], 0);
+          __syncwarp();
+          if (++sb == a.SB) { sb = 0; phb ^= 1; }
+        }
+        if (++sa == a.SA) { sa = 0; pha ^= 1; }
+      }
+    }
+  } else if (warp == 0) {
     // =========================== MMA issuer ===========================
     // The whole warp runs the (warp-uniform) loops so that the descriptor arithmetic stays in uniform
     // registers; only the tcgen05 instructions themselves are predicated on one elected lane.
     {
       const bool lead = elect_one();
-      const uint32_t idesc = make_idesc(128, BN, FMT, 0, 0);
+      const uint32_t idesc = make_idesc(PAIR ? 256 : 128, BN, FMT, 0, 0);
+      auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t acc) {
+        if (PAIR) umma_f16_pair(d, da, db, id, acc); else umma_f16(d, da, db, id, acc);
+      };
+      auto commit = [&](uint64_t* bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
+      auto wait = [&](uint64_t* bar, uint32_t parity) { if (PAIR) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity); };
       // A: K-major planar halo tile. LBO = plane stride (next 8 channels), SBO = halo row pitch (next 8 output
       // pixels = next image row of the 16x8 tile). B: K-major packed weights. variant bits swap them (probe).
       uint32_t a_lbo = PLANE, a_sbo = PITCH * 16;
-      uint32_t b_lbo = (MG ? 2 : 1) * BN * 16, b_sbo = 128;
+      uint32_t b_lbo = (MG ? 2 : 1) * BROWS * 16, b_sbo = 128;
       const uint32_t idesc2 = make_idesc(128, 2 * BN, FMT, 0, 0);  // merged: B = [w_hi | w_lo], 2 * BN rows per plane
       if (a.variant & 1) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; }
       if (a.variant & 2) { uint32_t t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
@@ -133,22 +189,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
       const uint64_t b_desc0 = make_smem_desc(smem_u32(b_base), b_lbo, b_sbo);
       const uint32_t a_stage16 = A_STAGE >> 4, b_stage16 = B_STAGE >> 4, b_tap16 = B_TAP >> 4;
       const uint32_t a_k16 = (2 * PLANE) >> 4, a_lo16 = (4 * PLANE) >> 4;
-      const uint32_t b_k16 = (2 * b_lbo) >> 4, b_lo16 = MG ? (uint32_t)(BN * 16) >> 4 : (uint32_t)(4 * BN * 16) >> 4;
+      const uint32_t b_k16 = (2 * b_lbo) >> 4, b_lo16 = MG ? (uint32_t)(BROWS * 16) >> 4 : (uint32_t)(4 * BROWS * 16) >> 4;
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       int k = 0;
-      for (int work = blockIdx.x; work < a.nwork; work += gridDim.x, ++k) {
+      for (int work = wstart; work < wcount; work += wstep, ++k) {
         const int buf = k % a.nbuf;
         const uint32_t use = (uint32_t)(k / a.nbuf);
-        mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);  // epilogue has drained this accumulator buffer
+        wait(&tmem_empty[buf], (use & 1) ^ 1);  // epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t d_buf = tmem_base + buf * BUFCOLS;
         for (int c = 0; c < nchunks; ++c) {
-          mbar_wait(&full_A[sa], pha);
+          wait(&full_A[sa], pha);
           tc_fence_after();
           const uint64_t a_st = a_desc0 + (uint64_t)(sa * a_stage16);
           for (int t0 = 0; t0 < 9; t0 += a.G) {
-            mbar_wait(&full_B[sb], phb);
+            wait(&full_B[sb], phb);
             tc_fence_after();
             const uint64_t b_st = b_desc0 + (uint64_t)(sb * b_stage16);
             // Issue order: ALL MMAs of this tap group that accumulate into one TMEM tile are issued back to back
@@ -170,26 +226,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
                     if (MG && a.nterms > 1) {
                       // x_hi * [w_hi | w_lo] in one MMA of width 2 * BN (the A tile is read once for both products),
                       // then x_lo * w_hi into the first half; the epilogue adds the two halves
-                      umma_f16(d_tmem, a_hi, b_hi, idesc2, acc);
-                      umma_f16(d_tmem, a_hi + a_lo16, b_hi, idesc, 1);
+                      mma(d_tmem, a_hi, b_hi, idesc2, acc);
+                      mma(d_tmem, a_hi + a_lo16, b_hi, idesc, 1);
                     } else {
-                      umma_f16(d_tmem, a_hi, b_hi, idesc, acc);
+                      mma(d_tmem, a_hi, b_hi, idesc, acc);
                       if (a.nterms > 1) {
-                        umma_f16(d_tmem, a_hi + a_lo16, b_hi, idesc, 1);
-                        umma_f16(d_tmem, a_hi, b_hi + b_lo16, idesc, 1);
+                        mma(d_tmem, a_hi + a_lo16, b_hi, idesc, 1);
+                        mma(d_tmem, a_hi, b_hi + b_lo16, idesc, 1);
                       }
                     }
                   }
                 }
               }
             }
-            if (lead) umma_commit(&empty_B[sb]);
+            if (lead) commit(&empty_B[sb]);
             if (++sb == a.SB) { sb = 0; phb ^= 1; }
           }
-          if (lead) umma_commit(&empty_A[sa]);
+          if (lead) commit(&empty_A[sa]);
           if (++sa == a.SA) { sa = 0; pha ^= 1; }
         }
-        if (lead) umma_commit(&tmem_full[buf]);
+        if (lead) commit(&tmem_full[buf]);
       }
     }
     __syncwarp();
@@ -198,9 +254,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
     if (elect_one()) {
       int sb = 0;
       uint32_t phb = 0;
-      for (int work = blockIdx.x; work < a.nwork; work += gridDim.x) {
-        const int nt = work / a.ntiles;
-        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)nt * nchunks * 9 * (size_t)(128 * BN);
+      for (int work = wstart; work < wcount; work += wstep) {
+        int nt, tile_unused; bool dummy_unused;
+        decode_work(work, nt, tile_unused, dummy_unused);
+        // PAIR: a tap image is [rank][term][4 planes][BN/2 rows][16 B]; this CTA fetches its own half
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)nt * nchunks * 9 * (size_t)(128 * BN) +
+                              (PAIR ? (size_t)rank * (size_t)(64 * BN) : 0);
         for (int i = 0; i < nchunks * 9; i += a.G) {
           mbar_wait(&empty_B[sb], phb ^ 1);
           mbar_arrive_expect_tx(&full_B[sb], (uint32_t)B_STAGE);
@@ -219,8 +278,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
     const int et = tid - 64;  // 0..127
     int k = 0;
     int tab_nt = -1;
-    for (int work = blockIdx.x; work < a.nwork; work += gridDim.x, ++k) {
-      const int nt = work / a.ntiles;
+    for (int work = wstart; work < wcount; work += wstep, ++k) {
+      int nt, tile; bool dummy;
+      decode_work(work, nt, tile, dummy);
       if (BWD && nt != tab_nt) {  // per-channel BatchNorm constants of this output-channel tile
         asm volatile("bar.sync 1, 128;" ::: "memory");
         for (int j = et; j < BN; j += kEpiThreads) {
@@ -230,7 +290,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
         asm volatile("bar.sync 1, 128;" ::: "memory");
         tab_nt = nt;
       }
-      int tile = work - nt * a.ntiles;
       const int tile_id = tile;
       const int tw = tile % a.tiles_w; tile /= a.tiles_w;
       const int th = tile % a.tiles_h;
@@ -253,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
         float csum = 0.f, csq = 0.f;
         for (int mt = 0; mt < MT; ++mt) {
           const int h = a.tall ? h0 + 8 * mt + cc : h0 + r, w = a.tall ? w0 + r : w0 + 8 * mt + cc;
-          const bool valid = (h < V.H) && (w < V.W) && !(a.variant & 16);
+          const bool valid = (h < V.H) && (w < V.W) && !(a.variant & 16) && !dummy;
           float zz[BWD ? 32 : 1];
           if (BWD) {  // the producer's z for these 32 channels: issued before the TMEM load so the latencies overlap
             const float4* zp =
@@ -320,14 +379,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
       // all TMEM reads of this buffer are complete: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (lane == 0) {  // PAIR: the MMA issuer (rank 0) waits for the epilogue warps of both CTAs
+        if (PAIR && rank != 0) mbar_arrive_remote(&tmem_empty[buf], 0); else mbar_arrive(&tmem_empty[buf]);
+      }
       if (a.stat_part != nullptr) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         for (int j = et; j < 2 * BN; j += kEpiThreads) {
           const int which = j / BN, col = j - which * BN;
           const float s = sstat[(0 * 2 + which) * BN + col] + sstat[(1 * 2 + which) * BN + col] +
                           sstat[(2 * 2 + which) * BN + col] + sstat[(3 * 2 + which) * BN + col];
-          a.stat_part[((size_t)tile_id * 2 + which) * a.Cout + n0 + col] = s;
+          if (!dummy) a.stat_part[((size_t)tile_id * 2 + which) * a.Cout + n0 + col] = s;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");  // sstat is reused by the next tile
       }
@@ -339,9 +400,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
     const int pbase = ftid >> 2;  // first halo pixel; stride kFillThreads/4 pixels
     int sa = 0;
     uint32_t pha = 0;
-    for (int work = blockIdx.x; work < a.nwork; work += gridDim.x) {
-      const int nt = work / a.ntiles;
-      int tile = work - nt * a.ntiles;
+    for (int work = wstart; work < wcount; work += wstep) {
+      int nt, tile; bool dummy;
+      decode_work(work, nt, tile, dummy);
       const int tw = tile % a.tiles_w; tile /= a.tiles_w;
       const int th = tile % a.tiles_h;
       const int n = tile / a.tiles_h;
@@ -440,168 +501,55 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's tensor core reads this CTA's weight half until the last commit has landed
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, a.tmem_cols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, a.tmem_cols); else tmem_dealloc(tmem_base, a.tmem_cols);
   }
 }
 
-static int pick_bn(int nside) {
-  if (nside % 256 == 0) return 256;
-  if (nside % 192 == 0) return 192;
-  if (nside % 128 == 0) return 128;
-  if (nside % 64 == 0) return 64;
-  if (nside % 32 == 0) return 32;
-  return 0;
-}
-static int pow2_cols(int c) {
-  int p = 32;
-  while (p < c) p <<= 1;
-  return p;
-}
-static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-        n <= 0)
-      n = 148;
-  }
-  return n;
-}
 
-// 64-wide output tiles: an M = 128, N = 64 MMA reads (128 + 64) x 32 B of shared memory (48 clocks at 128 B/clk) for 32
-// clocks of math, so the three MMAs of a split product cost 144 clocks per K step. With the weights packed
-// [plane][hi | lo][64 rows], x_hi * [w_hi | w_lo] is ONE MMA of width 128 (64 clocks of math = 64 of operand reads)
-// and x_lo * w_hi a second one: 112 clocks, at the price of 2 x 64 accumulator columns per tile (MT <= 2).
-// TNB_CONV_MERGE=0 restores the three-MMA form (ablation).
-bool conv3x3_merged(int BN) {
-  static const int on = [] { const char* e = getenv("TNB_CONV_MERGE"); return e ? atoi(e) : 1; }();
-  return on && BN == 64 && !conv3x3_pair_enabled();
-}
-// TNB_CONV_PAIR=1: forward / dgrad on CTA pairs (conv_pair.cu; experimental, off by default). The weight layout follows it.
-bool conv3x3_pair_enabled() {
-  static const int on = [] { const char* e = getenv("TNB_CONV_PAIR"); return e ? atoi(e) : 0; }();
-  return on != 0;
-}
-int conv3x3_weight_layout(int BN) { return conv3x3_pair_enabled() ? 2 : conv3x3_merged(BN) ? 1 : 0; }
-
-int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* plan, bool bn_bwd_fused) {
-  TNB_REQUIRE(Cin % 32 == 0, "conv3x3: view channels %d must be a multiple of 32", Cin);
-  const int BN = pick_bn(Cout);
-  TNB_REQUIRE(BN >= 32 && BN % 16 == 0, "conv3x3: unsupported output channel count %d", Cout);
-  const int TP = nterms > 1 ? 2 : 1;
-  const bool merged = conv3x3_merged(BN);
-  const bool pair = conv3x3_pair_enabled();  // each CTA of a pair holds half of every weight stage
-  TNB_REQUIRE(!(pair && bn_bwd_fused), "conv3x3: the CTA-pair kernel has no fused BatchNorm-backward reduction");
-  const int ACCW = (merged && nterms > 1) ? 2 * BN : BN;  // accumulator columns per M tile
-  int MT = 512 / ACCW;
-  if (MT > 4) MT = 4;
-  // Two accumulator buffers in TMEM (2 * MT * BN <= 512 columns) let the epilogue of tile i overlap the MMAs of tile
-  // i + 1; with one buffer it is exposed (7-17 % of the layer, measured: profiles/r1_summary.md 6). Narrower tiles
-  // re-stream the weights twice as often; with the tile orientation below removing the padded tile rows that still
-  // pays even for the 768-channel layer (0.669 -> 0.604 ms). TNB_CONV_PLAN=0 restores the widest tile, =2 keeps the
-  // double buffering but forces the row-major orientation (tools/ablate_plan.py).
-  static const int plan_mode = [] { const char* e = getenv("TNB_CONV_PLAN"); return e ? atoi(e) : 1; }();
-  if (plan_mode != 0) while (MT > 1 && 2 * MT * ACCW > 512) MT >>= 1;
-  // Orientation: M = 128 rows of the MMA are 16 groups of 8 consecutive pixels. Groups along W stacked over 16 image rows
-  // give a 16 x 8*MT tile; groups along H stacked over 16 image columns give an 8*MT x 16 tile. Take the one that pads
-  // the image less: at 72 x 128 and 36 x 64 (H = 4.5 and 2.25 tiles of 16 rows) the tall-group tile wastes 0 / 10 %
-  // of the MMAs instead of 10 / 25 %. TNB_CONV_PLAN=2 forces the first form.
-  auto padded = [&](int mt, bool tall) {
-    const long long th = tall ? (H + 8 * mt - 1) / (8 * mt) * (8 * mt) : (H + 15) / 16 * 16;
-    const long long tw = tall ? (W + 15) / 16 * 16 : (W + 8 * mt - 1) / (8 * mt) * (8 * mt);
-    return th * tw;
-  };
-  const bool tall = plan_mode != 2 && padded(MT, true) < padded(MT, false);
-  while (MT > 1 && 8 * (MT - 1) >= (tall ? H : W)) --MT;  // do not tile wider (taller) than the image
-  int SA = 2, SB = 0, G = 1;
-  size_t smem = 0;
-  const int mt_max = MT;
-  bool found = false;
-  // pass 0: narrow tiles (BN <= 128) get weight stages holding a whole filter row (3 taps) so that 18+ MMAs chain into
-  // one accumulator; pass 1: one tap per stage, as many stages as fit
-  for (int pass = (BN <= 128 ? 0 : 1); pass < 2 && !found; ++pass) {
-    const int g = pass == 0 ? 3 : 1;
-    for (MT = mt_max; MT >= 1; --MT) {
-      const int pitch = 8 * MT + 2, halo = 18 * pitch;
-      const size_t a_stage = (size_t)TP * 4 * pad_px(halo) * 16;
-      const size_t b_stage = (size_t)g * (merged ? 2 : TP) * 64 * BN / (pair ? 2 : 1);
-      const size_t fixed = kHdrBytes + ((halo * 8 + 127) & ~127) + (size_t)4 * 2 * BN * 4 + (bn_bwd_fused ? BN * 16 : 0) +
-                           SA * a_stage;
-      if (fixed + 2 * b_stage <= (size_t)kMaxSmem) {
-        G = g;
-        SB = (int)((kMaxSmem - fixed) / b_stage);
-        const int cap = g == 3 ? 3 : 8;  // deeper rings measured no better (cap 5), one tap per slot clearly worse
-        if (SB > cap) SB = cap;
-        smem = fixed + SB * b_stage;
-        found = true;
-        break;
-      }
-    }
-  }
-  TNB_REQUIRE(found, "conv3x3: no shared-memory plan for Cin=%d Cout=%d", Cin, Cout);
-  plan->BN = BN; plan->MT = MT; plan->SA = SA; plan->SB = SB; plan->G = G;
-  plan->nbuf = (2 * MT * ACCW <= 512) ? 2 : 1;
-  plan->tmem_cols = pow2_cols(plan->nbuf * MT * ACCW);
-  plan->merged = merged ? 1 : 0;
-  plan->pair = pair ? 1 : 0;
-  plan->smem_bytes = smem;
-  plan->tall = tall ? 1 : 0;
-  plan->tiles_h = tall ? (H + 8 * MT - 1) / (8 * MT) : (H + 15) / 16;
-  plan->tiles_w = tall ? (W + 15) / 16 : (W + 8 * MT - 1) / (8 * MT);
-  (void)N;
-  return 0;
-}
-
-int conv3x3_num_stat_rows(int N, int H, int W, int Cin, int Cout, int nterms, bool bn_bwd_fused) {
-  ConvPlan p;
-  if (conv3x3_plan(N, H, W, Cin, Cout, nterms, &p, bn_bwd_fused)) return -1;
-  return N * p.tiles_h * p.tiles_w;
-}
-
-int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout,
-                   int nterms, int fmt, int variant, cudaStream_t st, const BnBwdFuse* fuse) {
-  ConvPlan p;
-  int rc = conv3x3_plan(view.N, view.H, view.W, view.C, Cout, nterms, &p, fuse != nullptr);
-  if (rc) return rc;
-  if (p.pair) return launch_conv3x3_pair(view, wpack, out, stat_part, Cout, nterms, fmt, variant, p, st);
+int launch_conv3x3_pair(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout, int nterms,
+                        int fmt, int variant, const ConvPlan& p, cudaStream_t st) {
   const int m0 = view.s[0].mode, m1 = (view.C0 < view.C) ? view.s[1].mode : view.s[0].mode;
-  ConvArgs a;
+  ConvPairArgs a;
   a.view = view; a.wpack = wpack; a.out = out; a.stat_part = stat_part;
   a.bz = a.bsc = a.bsh = a.bmu = a.bis = nullptr;
-  if (fuse != nullptr) {
-    TNB_REQUIRE(stat_part != nullptr, "conv3x3: fused BatchNorm-backward reduction needs a partials buffer");
-    TNB_REQUIRE(fmt == 1 && m0 == SRC_PRESPLIT && m1 == SRC_PRESPLIT,
-                "conv3x3: the fused BatchNorm-backward reduction exists for the dgrad configuration only");
-    a.bz = fuse->z; a.bsc = fuse->scale; a.bsh = fuse->shift; a.bmu = fuse->mean; a.bis = fuse->invstd;
-  }
   a.Cout = Cout; a.BN = p.BN; a.MT = p.MT; a.SA = p.SA; a.SB = p.SB; a.G = p.G; a.nbuf = p.nbuf; a.nterms = nterms;
-  a.variant = variant | (cp_async_ca_env() ? 256 : 0); a.tmem_cols = p.tmem_cols; a.tiles_h = p.tiles_h; a.tiles_w = p.tiles_w; a.tall = p.tall; a.merged = p.merged;
+  a.variant = variant | (cp_async_ca_env() ? 256 : 0); a.tmem_cols = p.tmem_cols; a.tiles_h = p.tiles_h; a.tiles_w = p.tiles_w;
+  a.tall = p.tall; a.merged = 0;
   a.ntiles = view.N * p.tiles_h * p.tiles_w;
   a.nwork = a.ntiles * (Cout / p.BN);
-  const int grid = a.nwork < num_sms() ? a.nwork : num_sms();
+  a.ntiles_p = (a.ntiles + 1) / 2;
+  a.nwork_p = a.ntiles_p * (Cout / p.BN);
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int pairs = a.nwork_p < sms / 2 ? a.nwork_p : sms / 2;
   ProfScope prof(view.s[0].mode == SRC_PRESPLIT ? PROF_CONV_DGRAD : PROF_CONV_FWD, st, view.N, view.H, view.W, view.C, Cout);
   auto go = [&](auto kern) -> int {
     TNB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-    kern<<<grid, kThreads, p.smem_bytes, st>>>(a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = p.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    TNB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     return 0;
   };
   int rc2 = -2;
-#define TNB_CONV_CASE(F, A, B) if (fmt == F && m0 == A && m1 == B) rc2 = go(conv3x3_kernel<F, A, B>); else
-  TNB_CONV_CASE(0, SRC_IDENTITY, SRC_IDENTITY)
-  TNB_CONV_CASE(0, SRC_AFFINE_RELU, SRC_AFFINE_RELU)
-  TNB_CONV_CASE(0, SRC_AFFINE_RELU_POOL, SRC_AFFINE_RELU_POOL)
-  TNB_CONV_CASE(0, SRC_AFFINE_RELU_UP, SRC_AFFINE_RELU)
-  TNB_CONV_CASE(0, SRC_AFFINE_RELU_UP, SRC_AFFINE_RELU_UP)
-  TNB_CONV_CASE(0, SRC_PRESPLIT, SRC_PRESPLIT)
-  TNB_CONV_CASE(1, SRC_IDENTITY, SRC_IDENTITY)
-  if (fmt == 1 && m0 == SRC_PRESPLIT && m1 == SRC_PRESPLIT && fuse != nullptr)
-    rc2 = go(conv3x3_kernel<1, SRC_PRESPLIT, SRC_PRESPLIT, true>);
-  else
-  TNB_CONV_CASE(1, SRC_PRESPLIT, SRC_PRESPLIT)
-  { tnb::set_last_error("conv3x3: unsupported (fmt %d, source modes %d/%d) combination", fmt, m0, m1); return -2; }
-#undef TNB_CONV_CASE
+#define TNB_CONVP_CASE(F, A, B) if (fmt == F && m0 == A && m1 == B) rc2 = go(conv3x3_pair_kernel<F, A, B>); else
+  TNB_CONVP_CASE(0, SRC_IDENTITY, SRC_IDENTITY)
+  TNB_CONVP_CASE(0, SRC_AFFINE_RELU, SRC_AFFINE_RELU)
+  TNB_CONVP_CASE(0, SRC_AFFINE_RELU_POOL, SRC_AFFINE_RELU_POOL)
+  TNB_CONVP_CASE(0, SRC_AFFINE_RELU_UP, SRC_AFFINE_RELU)
+  TNB_CONVP_CASE(1, SRC_PRESPLIT, SRC_PRESPLIT)
+  { tnb::set_last_error("conv3x3 (pair): unsupported (fmt %d, source modes %d/%d) combination", fmt, m0, m1); return -2; }
+#undef TNB_CONVP_CASE
   if (rc2) return rc2;
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;

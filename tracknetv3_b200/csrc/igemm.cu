@@ -36,7 +36,7 @@ namespace tnb {
 // =============================================================================================
 template <int FMT>
 __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Co, int Ci,
-                                    int Nside, int Kpad, int BN, int mode, int merged) {
+                                    int Nside, int Kpad, int BN, int mode, int layout) {
   const int nchunks = Kpad / 32;
   const long long total = (long long)(Nside / BN) * nchunks * 9 * 4 * BN;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -67,9 +67,21 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __res
     const size_t stage = (((size_t)ntile * nchunks + chunk) * 9 + tap) * (size_t)(64 * BN);
     // [term][plane][BN rows][8], or for the merged 64-wide tiles [plane][term][BN rows][8] (conv3x3_merged): hi and lo
     // rows of a plane are then one operand of 2 * BN rows
-    uint4* dst_hi = reinterpret_cast<uint4*>(out + stage + (merged ? ((size_t)plane * 2 * BN + nl) * 8 : ((size_t)plane * BN + nl) * 8));
-    uint4* dst_lo = reinterpret_cast<uint4*>(out + stage + (merged ? ((size_t)(plane * 2 + 1) * BN + nl) * 8
-                                                                   : (size_t)32 * BN + ((size_t)plane * BN + nl) * 8));
+    // CTA-pair kernel (layout 2): [rank][term][plane][BN/2 rows][8] - each CTA of a pair fetches one contiguous half
+    size_t off_hi, off_lo;
+    if (layout == 2) {
+      const int half = BN / 2, rk = nl / half, nh = nl - rk * half;
+      off_hi = (size_t)rk * 32 * BN + ((size_t)plane * half + nh) * 8;
+      off_lo = off_hi + (size_t)16 * BN;
+    } else if (layout == 1) {
+      off_hi = ((size_t)plane * 2 * BN + nl) * 8;
+      off_lo = ((size_t)(plane * 2 + 1) * BN + nl) * 8;
+    } else {
+      off_hi = ((size_t)plane * BN + nl) * 8;
+      off_lo = (size_t)32 * BN + off_hi;
+    }
+    uint4* dst_hi = reinterpret_cast<uint4*>(out + stage + off_hi);
+    uint4* dst_lo = reinterpret_cast<uint4*>(out + stage + off_lo);
     *dst_hi = hi;
     *dst_lo = lo;
   }
@@ -89,11 +101,11 @@ int launch_pack_weights(const float* w, uint16_t* out, int Co, int Ci, int mode,
   const long long total = (long long)(Nside / BN) * (Kpad / 32) * 9 * 4 * BN;
   const int threads = 256;
   const int blocks = (int)((total + threads - 1) / threads);
-  const int merged = conv3x3_merged(BN) ? 1 : 0;  // the layout is a function of the tile width alone
+  const int layout = conv3x3_weight_layout(BN);  // a function of the tile width (and the experiment switches) alone
   if (fmt == 0)
-    pack_weights_kernel<0><<<blocks, threads, 0, st>>>(w, out, Co, Ci, Nside, Kpad, BN, mode, merged);
+    pack_weights_kernel<0><<<blocks, threads, 0, st>>>(w, out, Co, Ci, Nside, Kpad, BN, mode, layout);
   else
-    pack_weights_kernel<1><<<blocks, threads, 0, st>>>(w, out, Co, Ci, Nside, Kpad, BN, mode, merged);
+    pack_weights_kernel<1><<<blocks, threads, 0, st>>>(w, out, Co, Ci, Nside, Kpad, BN, mode, layout);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

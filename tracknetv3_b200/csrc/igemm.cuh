@@ -141,13 +141,15 @@ __host__ __device__ inline int pad_px(int px) {  // plane stride = 2 (mod 8) pix
 }
 
 struct ConvPlan {
-  int BN, MT, SA, SB, G, nbuf, tmem_cols, merged;
+  int BN, MT, SA, SB, G, nbuf, tmem_cols, merged, pair;
   size_t smem_bytes;
   int tiles_h, tiles_w;
   int tall;  // tile orientation, see conv3x3_plan
 };
 // fmt: 0 = fp16 split, 1 = bf16 split. nterms: 1 (single pass) or 3 (hi*hi + lo*hi + hi*lo).
 // bn_bwd_fused: reserve the per-channel constant table of the fused BatchNorm-backward reduction (dgrad epilogue)
+bool conv3x3_pair_enabled();          // TNB_CONV_PAIR=1: forward / dgrad on CTA pairs (conv_pair.cu, experimental)
+int conv3x3_weight_layout(int BN);    // 0 plain [term][plane][BN], 1 merged [plane][term][BN], 2 pair [rank][term][plane][BN/2]
 bool conv3x3_merged(int BN);  // weights of this tile width are packed [plane][hi | lo][BN] (one MMA for x_hi * [w_hi | w_lo])
 int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* plan, bool bn_bwd_fused = false);
 size_t conv3x3_wpack_elems(int Kside, int Nside);  // uint16 elements of a packed weight buffer
@@ -157,6 +159,9 @@ int launch_pack_weights(const float* w_oihw, uint16_t* out, int Co, int Ci, int 
 // per-tile partials become (sum g, sum g * xhat) with g = out masked by that layer's ReLU - the reduction pass of its
 // BatchNorm backward - instead of (sum out, sum out^2).
 struct BnBwdFuse { const float *z, *scale, *shift, *mean, *invstd; };
+// CTA-pair variant (conv_pair.cu), selected by launch_conv3x3 when the plan says so
+int launch_conv3x3_pair(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout, int nterms,
+                        int fmt, int variant, const ConvPlan& plan, cudaStream_t st);
 int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout,
                    int nterms, int fmt, int variant, cudaStream_t st, const BnBwdFuse* fuse = nullptr);
 int conv3x3_num_stat_rows(int N, int H, int W, int Cin, int Cout, int nterms, bool bn_bwd_fused = false);
