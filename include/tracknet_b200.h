@@ -107,7 +107,11 @@ int tnb_view_presplit(const tnb_view_t* view, void* out, int fmt, void* stream);
 
 /* Weight pre-packing for the tcgen05 kernels. mode 0: forward operand, mode 1: dgrad operand (rotated,
  * transposed). fmt 0: fp16 split, 1: bf16 split. Source is the reference's canonical OIHW parameter
- * (`<block>.conv.weight`, model.py:8). */
+ * (`<block>.conv.weight`, model.py:8). The packed buffer is opaque: it is the shared-memory image the consuming
+ * tnb_conv3x3_fwd launch streams with bulk TMA, one image per (output-channel tile, 32-channel chunk, filter tap), and
+ * its inner layout follows the tile width the launcher will pick for this N side ([hi | lo][plane][rows], or
+ * [plane][hi | lo][rows] for the 64-wide tiles whose two weight terms feed one MMA). Pack and convolve in the same
+ * process (the layout also follows the TNB_CONV_MERGE / TNB_CONV_PAIR experiment switches). */
 size_t tnb_conv3x3_wpack_elems(int k_side, int n_side); /* number of uint16 elements */
 int tnb_conv3x3_pack_weights(const float* w_oihw, uint16_t* out, int cout, int cin, int mode, int fmt, void* stream);
 
@@ -131,7 +135,9 @@ int tnb_conv3x3_dgrad_bnreduce(const tnb_view_t* view, const uint16_t* wpack, fl
 
 /* Weight gradient of the same convolution (autograd of model.py:13 via train.py:95):
  * dw[cout][cin_real][3][3] += sum dz * view. dw must be zeroed by the caller. dz is in the pre-split bf16 format
- * ([N,H,W,cout] logical); the view operand is split to bf16 on the fly. */
+ * ([N,H,W,cout] logical); the view operand is split to bf16 on the fly. With a pre-split view three kernels exist:
+ * CTA pairs (tcgen05 cta_group::2) when cout % 256 == 0 and the input tile is 128 channels, the tap-stacked kernel for
+ * cout == 64, the single-CTA kernel otherwise; variant bit 32 forces the generic kernels, bit 64 the single-CTA one. */
 int tnb_conv3x3_wgrad(const tnb_view_t* view, const void* dz_presplit, float* dw_oihw, int cout, int cin_real,
                       int terms, int variant, void* stream);
 /* The same with a scratch buffer of 9 * cout * view->C floats: the split-K partials are reduced tap-major (coalesced
