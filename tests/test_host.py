@@ -147,3 +147,79 @@ def test_generate_inpaint_mask_matches_reference_fixture():
         got = TT.generate_inpaint_mask({"Y": y[:n].tolist(), "Visibility": vis[:n].tolist()}, th_h=float(th))
         assert got == mask[:n].tolist(), (y[:n], vis[:n])
     assert g["mask"].max() == 1 and (g["mask"] == 1).sum() > 200      # the fixture does exercise marked runs
+
+
+def test_train_main_plumbing_optimizer_scheduler_checkpoint_resume(tmp_path):
+    """Host side of the reference's train.py __main__ (:236-305): optimizer / scheduler choices, checkpoint layout,
+    best / current checkpoint policy and resume. Runs on CPU with stand-in train / eval functions."""
+    import train as TR
+    import tracknetv3_b200 as T
+    net = torch.nn.Linear(4, 2)
+    assert isinstance(TR.make_optimizer(net, "Adam", 1e-3), T.FusedAdam)
+    assert type(TR.make_optimizer(net, "Adam", 1e-3, fused=False)) is torch.optim.Adam
+    sgd = TR.make_optimizer(net, "SGD", 0.1)
+    assert type(sgd) is torch.optim.SGD and sgd.defaults["momentum"] == 0.9 and sgd.defaults["lr"] == 0.1
+    assert type(TR.make_optimizer(net, "Adadelta", 1.0)) is torch.optim.Adadelta
+    with pytest.raises(ValueError, match="Invalid optimizer"):
+        TR.make_optimizer(net, "LAMB", 1e-3)
+    assert TR.make_scheduler(sgd, "", 30) is None
+    sch = TR.make_scheduler(sgd, "StepLR", 7)
+    assert sch.step_size == 2 and sch.gamma == 0.1  # int(epochs / 3), reference :250
+
+    ck = TR.checkpoint_dict(3, 0.5, net, sgd, None, {"model_name": "TrackNet"})
+    assert set(ck) == {"epoch", "max_val_acc", "model", "optimizer", "scheduler", "param_dict"} and ck["scheduler"] is None
+
+    # epoch loop: accuracy 0.2, 0.6, 0.6, 0.4 -> best is rewritten at epochs 0, 1, 2 (>=), not at 3; cur every epoch
+    accs = [0.2, 0.6, 0.6, 0.4, 0.9, 0.1]
+    calls = {"train": 0, "eval": 0}
+
+    def train_fn(model, optimizer, loader, param_dict):
+        calls["train"] += 1
+        optimizer.zero_grad()
+        model(torch.ones(1, 4)).sum().backward()
+        optimizer.step()
+        return 1.0 / calls["train"]
+
+    def eval_fn(model, loader, param_dict):
+        acc = accs[calls["eval"]]
+        calls["eval"] += 1
+        return 0.5, {"accuracy": acc}
+
+    pd = {"model_name": "TrackNet", "epochs": 4, "tolerance": 4}
+    opt = TR.make_optimizer(net, "SGD", 0.1)
+    sch = TR.make_scheduler(opt, "StepLR", 4)  # step_size 1: lr x0.1 per epoch
+    best, hist = TR.fit(net, opt, sch, lambda: [], lambda: [], pd, train_fn, eval_fn, save_dir=str(tmp_path), log=lambda s: None)
+    assert best == 0.6 and [h[0] for h in hist] == [0, 1, 2, 3]
+    cur = torch.load(tmp_path / "TrackNet_cur.pt", weights_only=False)
+    bst = torch.load(tmp_path / "TrackNet_best.pt", weights_only=False)
+    assert cur["epoch"] == 3 and bst["epoch"] == 2 and cur["max_val_acc"] == 0.6 and bst["max_val_acc"] == 0.6
+    assert abs(opt.param_groups[0]["lr"] - 0.1 * 0.1 ** 4) < 1e-12
+
+    # resume: a fresh model / optimizer / scheduler continue at epoch 4 with the restored weights, momentum and lr
+    net2 = torch.nn.Linear(4, 2)
+    opt2 = TR.make_optimizer(net2, "SGD", 0.1)
+    sch2 = TR.make_scheduler(opt2, "StepLR", 4)
+    start, mx = TR.resume_from(cur, net2, opt2, sch2)
+    assert (start, mx) == (4, 0.6)
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), net2.state_dict().values()))
+    assert abs(opt2.param_groups[0]["lr"] - opt.param_groups[0]["lr"]) < 1e-15 and sch2.last_epoch == sch.last_epoch
+    mb = [opt.state[p]["momentum_buffer"] for p in net.parameters()]
+    mb2 = [opt2.state[p]["momentum_buffer"] for p in net2.parameters()]
+    assert all(torch.equal(a, b) for a, b in zip(mb, mb2))
+    pd["epochs"] = 6
+    best2, hist2 = TR.fit(net2, opt2, sch2, lambda: [], lambda: [], pd, train_fn, eval_fn, start, mx, str(tmp_path), log=lambda s: None)
+    assert [h[0] for h in hist2] == [4, 5] and best2 == 0.9
+    assert torch.load(tmp_path / "TrackNet_best.pt", weights_only=False)["epoch"] == 4
+
+
+def test_synthetic_tracknet_loader_matches_the_reference_batch_layout():
+    import train as TR
+    from oracle.tracknet_oracle import label_disc
+    batches = list(TR._synthetic_tracknet_loader(2, 3, 4, "concat", h=32, w=64, seed=1))
+    assert len(batches) == 2
+    idx, x, y, c, _ = batches[1]
+    assert idx.shape == (3, 4, 2) and x.shape == (3, 15, 32, 64) and y.shape == (3, 4, 32, 64) and c.shape == (3, 4, 2)
+    assert len({int(v) for v in idx[..., 1].flatten()}) == 12  # distinct frame ids inside a batch
+    cx, cy = int(round(float(c[1, 2, 0]) * 64)), int(round(float(c[1, 2, 1]) * 32))
+    assert np.array_equal(y[1, 2].numpy(), label_disc(cx, cy, h=32, w=64))  # the label rule of dataset.py:401-410
+    assert 0 < y[1, 2].sum() <= 21  # a radius-2.5 disc has 21 pixels, fewer when clipped by the border

@@ -1,9 +1,11 @@
 """Hot-path subset of the reference's train.py: `mixup` (:19-40), `get_random_mask` (:42-57), the TrackNet step loop
 (:59-121) and the InpaintNet step loop (:123-177).
 
-Dataset / TensorBoard / checkpoint plumbing of the reference's __main__ is out of scope;
-`train_tracknet` accepts any iterable yielding the reference's (i, x, y, c, _) tuples and runs the step of
-train.py:85-96 on the B200 kernels. `python train.py --synthetic` runs a few steps on random frames.
+The reference's datasets and TensorBoard writer are out of scope; `train_tracknet` accepts any iterable
+yielding the reference's (i, x, y, c, _) tuples and runs the step of train.py:85-96 on the B200 kernels. The optimizer /
+scheduler choices, the checkpoint layout and the resume logic of the reference's __main__ (:236-305) are here as
+`make_optimizer`, `make_scheduler`, `checkpoint_dict`, `resume_from` and `fit`; `python train.py` takes the reference's
+command line and trains on synthetic batches.
 """
 import argparse
 
@@ -80,31 +82,136 @@ def train_inpaintnet(model, optimizer, data_loader, param_dict):
     return float(np.mean(epoch_loss))
 
 
-def _synthetic_loader(steps, batch_size, seq_len, bg_mode, h=288, w=512):
+def make_optimizer(model, optim, learning_rate, fused=True):
+    """ Optimizer choices of reference :238-246: 'Adam' (lr), 'SGD' (lr, momentum 0.9), 'Adadelta' (lr); anything else raises
+        ValueError('Invalid optimizer.'). With fused=True 'Adam' is the one-launch FusedAdam, whose state_dict interchanges
+        with torch.optim.Adam's (same keys), so checkpoints written either way resume either way. """
+    if optim == 'Adam':
+        if fused:
+            from tracknetv3_b200 import FusedAdam
+            return FusedAdam(model.parameters(), lr=learning_rate)
+        return torch.optim.Adam(model.parameters(), lr=learning_rate)
+    if optim == 'SGD':
+        return torch.optim.SGD(model.parameters(), lr=learning_rate, momentum=0.9)
+    if optim == 'Adadelta':
+        return torch.optim.Adadelta(model.parameters(), lr=learning_rate)
+    raise ValueError('Invalid optimizer.')
+
+
+def make_scheduler(optimizer, lr_scheduler, epochs):
+    """ 'StepLR' -> StepLR(step_size=int(epochs / 3), gamma=0.1), '' -> None (reference :248-252). """
+    if lr_scheduler == 'StepLR':
+        return torch.optim.lr_scheduler.StepLR(optimizer, step_size=int(epochs / 3), gamma=0.1)
+    return None
+
+
+def checkpoint_dict(epoch, max_val_acc, model, optimizer, scheduler, param_dict):
+    """ The reference's checkpoint layout (:283-301): epoch, max_val_acc, model, optimizer, scheduler (None without one),
+        param_dict - what `--resume_training` and predict.py (:99-108: ckpt['model'], ckpt['param_dict']) read. """
+    return dict(epoch=epoch, max_val_acc=max_val_acc, model=model.state_dict(), optimizer=optimizer.state_dict(),
+                scheduler=scheduler.state_dict() if scheduler is not None else None, param_dict=param_dict)
+
+
+def resume_from(ckpt, model, optimizer, scheduler):
+    """ Restore model / optimizer / scheduler from a checkpoint dict written by this file or by the reference
+        (:255-262). Returns (start_epoch, max_val_acc). """
+    model.load_state_dict(ckpt['model'])
+    optimizer.load_state_dict(ckpt['optimizer'])
+    if scheduler is not None and ckpt.get('scheduler') is not None:
+        scheduler.load_state_dict(ckpt['scheduler'])
+    return ckpt['epoch'] + 1, ckpt['max_val_acc']
+
+
+def fit(model, optimizer, scheduler, train_loader_fn, val_loader_fn, param_dict, train_fn, eval_fn,
+        start_epoch=0, max_val_acc=0., save_dir=None, log=print):
+    """ Epoch loop of reference :268-305 without the TensorBoard writer: train, evaluate, scheduler step, `<model>_best.pt`
+        when the validation accuracy does not drop, `<model>_cur.pt` every epoch. The loaders are given as callables
+        returning a fresh iterable per epoch. Returns (max_val_acc, history). """
+    import os
+    name = param_dict['model_name']
+    history = []
+    for epoch in range(start_epoch, param_dict['epochs']):
+        train_loss = train_fn(model, optimizer, train_loader_fn(), param_dict)
+        val_loss, val_res = eval_fn(model, val_loader_fn(), param_dict)
+        if scheduler is not None:
+            scheduler.step()
+        cur_val_acc = val_res['accuracy'] if name == 'TrackNet' else val_res['inpaint']['accuracy']
+        history.append((epoch, train_loss, val_loss, cur_val_acc))
+        log(f'Epoch [{epoch + 1} / {param_dict["epochs"]}] train loss {train_loss:.6f} val loss {val_loss:.6f} '
+            f'val accuracy {cur_val_acc:.4f}')
+        if save_dir is not None:
+            if cur_val_acc >= max_val_acc:
+                max_val_acc = cur_val_acc
+                torch.save(checkpoint_dict(epoch, max_val_acc, model, optimizer, scheduler, param_dict),
+                           os.path.join(save_dir, f'{name}_best.pt'))
+            torch.save(checkpoint_dict(epoch, max_val_acc, model, optimizer, scheduler, param_dict),
+                       os.path.join(save_dir, f'{name}_cur.pt'))
+        else:
+            max_val_acc = max(max_val_acc, cur_val_acc)
+    return max_val_acc, history
+
+
+def _synthetic_tracknet_loader(steps, batch_size, seq_len, bg_mode, h=288, w=512, seed=0):
+    """ Batches in the layout of the reference's heatmap-mode dataset (dataset.py:611-647): (index, x, y, coordinates,
+        visibility-unused); y = one radius-2.5 disc per frame (dataset.py:401-410), coordinates normalised to [0, 1]. """
     in_dim = get_model('TrackNet', seq_len, bg_mode).in_dim
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.arange(1, h + 1), torch.arange(1, w + 1), indexing='ij')
     for i in range(steps):
-        x = torch.rand(batch_size, in_dim, h, w)
-        y = (torch.rand(batch_size, seq_len, h, w) > 0.999).float()
-        yield i, x, y, torch.zeros(batch_size, seq_len, 2), None
+        x = torch.rand(batch_size, in_dim, h, w, generator=g)
+        cx = torch.randint(0, w, (batch_size, seq_len), generator=g)
+        cy = torch.randint(0, h, (batch_size, seq_len), generator=g)
+        y = (((xx - (cx[..., None, None] + 1)) ** 2 + (yy - (cy[..., None, None] + 1)) ** 2) <= 2.5 ** 2).float()
+        y = y * ((cx != 0) | (cy != 0))[..., None, None]  # (0, 0) is the reference's "no shuttlecock": an empty map
+        c = torch.stack([cx / w, cy / h], -1).float()
+        idx = torch.stack([torch.full((batch_size, seq_len), i), torch.arange(seq_len).expand(batch_size, seq_len)
+                           + i * batch_size * seq_len + torch.arange(batch_size)[:, None] * seq_len], -1)
+        yield idx, x, y, c, None
 
 
 if __name__ == '__main__':
+    import os
+    # the reference's command line (:180-199); datasets are out of scope here (SURVEY.md 2), so the loaders are either the
+    # reference's own `dataset.Shuttlecock_Trajectory_Dataset` when it is importable, or --synthetic_steps random batches
     parser = argparse.ArgumentParser()
-    parser.add_argument('--model_name', type=str, default='TrackNet', choices=['TrackNet'])
-    parser.add_argument('--seq_len', type=int, default=8)
-    parser.add_argument('--batch_size', type=int, default=10)
-    parser.add_argument('--learning_rate', type=float, default=0.001)
-    parser.add_argument('--bg_mode', type=str, default='concat', choices=['', 'subtract', 'subtract_concat', 'concat'])
-    parser.add_argument('--alpha', type=float, default=0.5)
+    parser.add_argument('--model_name', type=str, default='TrackNet', choices=['TrackNet'], help='model type')
+    parser.add_argument('--seq_len', type=int, default=8, help='sequence length of input')
+    parser.add_argument('--epochs', type=int, default=3, help='number of epochs')
+    parser.add_argument('--batch_size', type=int, default=10, help='batch size of training')
+    parser.add_argument('--optim', type=str, default='Adam', choices=['Adam', 'SGD', 'Adadelta'], help='optimizer')
+    parser.add_argument('--learning_rate', type=float, default=0.001, help='initial learning rate')
+    parser.add_argument('--lr_scheduler', type=str, default='', choices=['', 'StepLR'], help='learning rate scheduler')
+    parser.add_argument('--bg_mode', type=str, default='', choices=['', 'subtract', 'subtract_concat', 'concat'])
+    parser.add_argument('--alpha', type=float, default=-1, help='alpha of sample mixup, -1 means no mixup')
+    parser.add_argument('--frame_alpha', type=float, default=-1)
+    parser.add_argument('--mask_ratio', type=float, default=0.3)
+    parser.add_argument('--tolerance', type=float, default=4)
+    parser.add_argument('--resume_training', action='store_true', default=False)
     parser.add_argument('--seed', type=int, default=13)
-    parser.add_argument('--steps', type=int, default=5)
-    parser.add_argument('--synthetic', action='store_true', default=True)
+    parser.add_argument('--save_dir', type=str, default='exp')
+    parser.add_argument('--debug', action='store_true', default=False)
+    parser.add_argument('--verbose', action='store_true', default=False)
+    parser.add_argument('--synthetic_steps', type=int, default=5, help='random batches per epoch (no dataset in this repo)')
     args = parser.parse_args()
+    param_dict = vars(args)
     np.random.seed(args.seed)
     torch.manual_seed(args.seed)
-    from tracknetv3_b200 import FusedAdam
-    model = get_model(args.model_name, args.seq_len, args.bg_mode).cuda()
-    optimizer = FusedAdam(model.parameters(), lr=args.learning_rate)
-    loss = train_tracknet(model, optimizer, _synthetic_loader(args.steps, args.batch_size, args.seq_len, args.bg_mode),
-                          vars(args))
-    print(f'mean loss over {args.steps} synthetic steps: {loss:.6f}')
+    os.makedirs(args.save_dir, exist_ok=True)
+    ckpt = None
+    if args.resume_training:
+        path = os.path.join(args.save_dir, f'{args.model_name}_cur.pt')
+        assert os.path.exists(path), f'No checkpoint found in {args.save_dir}'
+        ckpt = torch.load(path, weights_only=False)
+        param_dict = dict(ckpt['param_dict'], resume_training=True, epochs=args.epochs, verbose=args.verbose)
+        param_dict.setdefault('synthetic_steps', args.synthetic_steps)
+    P = argparse.Namespace(**param_dict)
+    print(f'Parameters: {param_dict}')
+    from test import eval_tracknet
+    model = get_model(P.model_name, P.seq_len, P.bg_mode).cuda()
+    optimizer = make_optimizer(model, P.optim, P.learning_rate)
+    scheduler = make_scheduler(optimizer, P.lr_scheduler, P.epochs)
+    start_epoch, max_val_acc = resume_from(ckpt, model, optimizer, scheduler) if ckpt is not None else (0, 0.)
+    loaders = lambda seed: (lambda: _synthetic_tracknet_loader(P.synthetic_steps, P.batch_size, P.seq_len, P.bg_mode, seed=seed))
+    best, _ = fit(model, optimizer, scheduler, loaders(P.seed), loaders(P.seed + 1), param_dict, train_tracknet,
+                  eval_tracknet, start_epoch, max_val_acc, P.save_dir)
+    print(f'best validation accuracy {best:.4f}; checkpoints in {P.save_dir}')
