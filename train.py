@@ -169,12 +169,32 @@ def _synthetic_tracknet_loader(steps, batch_size, seq_len, bg_mode, h=288, w=512
         yield idx, x, y, c, None
 
 
+def _synthetic_inpaintnet_loader(steps, batch_size, seq_len, seed=0):
+    """ Batches in the layout of the reference's coordinate-mode dataset (dataset.py:649-690): (index, predicted
+        coordinates, true coordinates, predicted visibility, true visibility, inpaint mask); smooth parabolic
+        trajectories in [0, 1]^2, the prediction = truth + noise with ~20 % of the frames lost (set to 0), and the
+        inpaint mask of `generate_inpaint_mask`'s kind: lost frames between visible ones. """
+    g = torch.Generator().manual_seed(seed)
+    t = torch.linspace(0, 1, seq_len)
+    for i in range(steps):
+        x0, vx = torch.rand(batch_size, 1, generator=g) * 0.4 + 0.1, torch.rand(batch_size, 1, generator=g) * 0.4
+        y0, vy = torch.rand(batch_size, 1, generator=g) * 0.3 + 0.5, -torch.rand(batch_size, 1, generator=g) * 1.2
+        coor = torch.stack([x0 + vx * t, (y0 + vy * t + 1.2 * t * t).clamp(0.1, 0.95)], -1)
+        lost = torch.rand(batch_size, seq_len, generator=g) < 0.2
+        lost[:, 0] = lost[:, -1] = False
+        coor_pred = (coor + 0.003 * torch.randn(coor.shape, generator=g)) * (~lost)[..., None]
+        vis = torch.ones(batch_size, seq_len, 1)
+        idx = torch.stack([torch.full((batch_size, seq_len), i), torch.arange(seq_len).expand(batch_size, seq_len)
+                           + i * batch_size * seq_len + torch.arange(batch_size)[:, None] * seq_len], -1)
+        yield idx, coor_pred, coor, (~lost)[..., None].float(), vis, lost[..., None].float()
+
+
 if __name__ == '__main__':
     import os
     # the reference's command line (:180-199); datasets are out of scope here (SURVEY.md 2), so the loaders are either the
     # reference's own `dataset.Shuttlecock_Trajectory_Dataset` when it is importable, or --synthetic_steps random batches
     parser = argparse.ArgumentParser()
-    parser.add_argument('--model_name', type=str, default='TrackNet', choices=['TrackNet'], help='model type')
+    parser.add_argument('--model_name', type=str, default='TrackNet', choices=['TrackNet', 'InpaintNet'], help='model type')
     parser.add_argument('--seq_len', type=int, default=8, help='sequence length of input')
     parser.add_argument('--epochs', type=int, default=3, help='number of epochs')
     parser.add_argument('--batch_size', type=int, default=10, help='batch size of training')
@@ -206,12 +226,17 @@ if __name__ == '__main__':
         param_dict.setdefault('synthetic_steps', args.synthetic_steps)
     P = argparse.Namespace(**param_dict)
     print(f'Parameters: {param_dict}')
-    from test import eval_tracknet
-    model = get_model(P.model_name, P.seq_len, P.bg_mode).cuda()
+    from test import eval_tracknet, eval_inpaintnet
+    tracknet = P.model_name == 'TrackNet'
+    model = get_model(P.model_name, P.seq_len, P.bg_mode).cuda() if tracknet else get_model(P.model_name).cuda()
     optimizer = make_optimizer(model, P.optim, P.learning_rate)
     scheduler = make_scheduler(optimizer, P.lr_scheduler, P.epochs)
     start_epoch, max_val_acc = resume_from(ckpt, model, optimizer, scheduler) if ckpt is not None else (0, 0.)
-    loaders = lambda seed: (lambda: _synthetic_tracknet_loader(P.synthetic_steps, P.batch_size, P.seq_len, P.bg_mode, seed=seed))
-    best, _ = fit(model, optimizer, scheduler, loaders(P.seed), loaders(P.seed + 1), param_dict, train_tracknet,
-                  eval_tracknet, start_epoch, max_val_acc, P.save_dir)
+    if tracknet:
+        loaders = lambda seed: (lambda: _synthetic_tracknet_loader(P.synthetic_steps, P.batch_size, P.seq_len, P.bg_mode, seed=seed))
+    else:
+        loaders = lambda seed: (lambda: _synthetic_inpaintnet_loader(P.synthetic_steps, P.batch_size, P.seq_len, seed=seed))
+    best, _ = fit(model, optimizer, scheduler, loaders(P.seed), loaders(P.seed + 1), param_dict,
+                  train_tracknet if tracknet else train_inpaintnet, eval_tracknet if tracknet else eval_inpaintnet,
+                  start_epoch, max_val_acc, P.save_dir)
     print(f'best validation accuracy {best:.4f}; checkpoints in {P.save_dir}')
