@@ -153,21 +153,83 @@ def run_video(frames_u8, tracknet, inpaintnet=None, seq_len=8, bg_mode='concat',
     return pred, out
 
 
+def generate_frames(video_file):
+    """ All frames of an .mp4 as a list of BGR arrays (reference utils/general.py:202-226; cv2.VideoCapture on the host). """
+    import cv2
+    assert video_file[-4:] == '.mp4', 'Invalid video file format.'
+    cap = cv2.VideoCapture(video_file)
+    frame_list = []
+    while True:
+        success, frame = cap.read()
+        if not success:
+            break
+        frame_list.append(frame)
+    cap.release()
+    return frame_list
+
+
+def write_pred_csv(pred_dict, save_file):
+    """ Frame, Visibility, X, Y - the csv the reference's `write_pred_csv` (utils/general.py:322-354) writes for a
+        prediction (same header, column order and integer formatting as its pandas `to_csv(index=False)`). """
+    import csv
+    with open(save_file, 'w', newline='') as f:
+        wr = csv.writer(f, lineterminator='\n')
+        wr.writerow(['Frame', 'Visibility', 'X', 'Y'])
+        for row in zip(pred_dict['Frame'], pred_dict['Visibility'], pred_dict['X'], pred_dict['Y']):
+            wr.writerow([int(v) for v in row])
+
+
+def load_models(tracknet_file, inpaintnet_file=''):
+    """ Models from checkpoints in the reference's layout (predict.py:99-108): ckpt['model'] and
+        ckpt['param_dict']['seq_len' / 'bg_mode']. Returns (tracknet, inpaintnet or None, seq_len, bg_mode). """
+    from utils.general import get_model
+    ckpt = torch.load(tracknet_file, map_location='cpu', weights_only=False)
+    seq_len, bg_mode = ckpt['param_dict']['seq_len'], ckpt['param_dict']['bg_mode']
+    tracknet = get_model('TrackNet', seq_len, bg_mode)
+    tracknet.load_state_dict(ckpt['model'])
+    inpaintnet = None
+    if inpaintnet_file:
+        ickpt = torch.load(inpaintnet_file, map_location='cpu', weights_only=False)
+        inpaintnet = get_model('InpaintNet')
+        inpaintnet.load_state_dict(ickpt['model'])
+    return tracknet, inpaintnet, seq_len, bg_mode
+
+
 if __name__ == '__main__':
     import argparse
+    import os
     from utils.general import get_model
-    parser = argparse.ArgumentParser(description='synthetic end-to-end run of the GPU predict path (no checkpoints / video files)')
-    parser.add_argument('--frames', type=int, default=40)
-    parser.add_argument('--batch_size', type=int, default=16)
-    parser.add_argument('--eval_mode', type=str, default='weight', choices=['weight', 'average'])
+    # the reference's command line (predict.py:72-83) for the in-memory path; without --video_file a synthetic clip
+    # and random weights exercise the same GPU data path
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--video_file', type=str, default='', help='file path of the video (.mp4)')
+    parser.add_argument('--tracknet_file', type=str, default='', help='file path of the TrackNet model checkpoint')
+    parser.add_argument('--inpaintnet_file', type=str, default='', help='file path of the InpaintNet model checkpoint')
+    parser.add_argument('--batch_size', type=int, default=16, help='batch size for inference')
+    parser.add_argument('--eval_mode', type=str, default='weight', choices=['average', 'weight'], help='evaluation mode')
+    parser.add_argument('--save_dir', type=str, default='pred_result', help='directory to save the prediction result')
+    parser.add_argument('--frames', type=int, default=40, help='length of the synthetic clip (no --video_file)')
     args = parser.parse_args()
-    torch.manual_seed(0)
-    video = torch.randint(0, 40, (args.frames, 360, 640, 3), dtype=torch.uint8)
-    for i in range(args.frames):                                       # a bright ball crossing a dark noisy court
-        video[i, 100 + 3 * i:108 + 3 * i, 50 + 10 * i:58 + 10 * i] = 250
-    tracknet = get_model('TrackNet', 8, 'concat').cuda().eval()
-    inpaintnet = get_model('InpaintNet').cuda().eval()
-    p1, p2 = run_video(video, tracknet, inpaintnet, batch_size=args.batch_size, eval_mode=args.eval_mode,
-                       img_scaler=(640 / WIDTH, 360 / HEIGHT))
-    print(f"TrackNet: {len(p1['Frame'])} frames, {sum(p1['Visibility'])} visible (random weights); "
-          f"InpaintNet: {len(p2['Frame'])} frames")
+    if args.video_file:
+        assert args.tracknet_file, 'a TrackNet checkpoint is required with --video_file'
+        tracknet, inpaintnet, seq_len, bg_mode = load_models(args.tracknet_file, args.inpaintnet_file)
+        frames = np.array(generate_frames(args.video_file))[:, :, :, ::-1]      # BGR -> RGB, as predict.py:128
+        video = torch.from_numpy(np.ascontiguousarray(frames))
+        name = os.path.basename(args.video_file)[:-4]
+    else:
+        torch.manual_seed(0)
+        seq_len, bg_mode, name = 8, 'concat', 'synthetic'
+        video = torch.randint(0, 40, (args.frames, 360, 640, 3), dtype=torch.uint8)
+        for i in range(args.frames):                                   # a bright ball crossing a dark noisy court
+            video[i, 100 + 3 * i:108 + 3 * i, 50 + 10 * i:58 + 10 * i] = 250
+        tracknet, inpaintnet = get_model('TrackNet', seq_len, bg_mode), get_model('InpaintNet')
+    tracknet = tracknet.cuda().eval()
+    inpaintnet = inpaintnet.cuda().eval() if inpaintnet is not None else None
+    h, w = video.shape[1], video.shape[2]
+    p1, p2 = run_video(video, tracknet, inpaintnet, seq_len=seq_len, bg_mode=bg_mode, batch_size=args.batch_size,
+                       eval_mode=args.eval_mode, img_scaler=(w / WIDTH, h / HEIGHT))
+    os.makedirs(args.save_dir, exist_ok=True)
+    out_csv = os.path.join(args.save_dir, f'{name}_ball.csv')
+    write_pred_csv(p2 if p2 is not None else p1, out_csv)
+    print(f"TrackNet: {len(p1['Frame'])} frames, {sum(p1['Visibility'])} visible"
+          + (f"; InpaintNet: {len(p2['Frame'])} frames" if p2 is not None else '') + f"; wrote {out_csv}")

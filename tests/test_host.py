@@ -223,3 +223,44 @@ def test_synthetic_tracknet_loader_matches_the_reference_batch_layout():
     cx, cy = int(round(float(c[1, 2, 0]) * 64)), int(round(float(c[1, 2, 1]) * 32))
     assert np.array_equal(y[1, 2].numpy(), label_disc(cx, cy, h=32, w=64))  # the label rule of dataset.py:401-410
     assert 0 < y[1, 2].sum() <= 21  # a radius-2.5 disc has 21 pixels, fewer when clipped by the border
+
+
+def test_predict_csv_writer_and_frame_reader(tmp_path):
+    """Host IO around predict.run_video: the csv equals what the reference's pandas writer produces; an .mp4 written with
+    OpenCV comes back frame by frame (skipped when this OpenCV build has no mp4 encoder)."""
+    import pandas as pd
+    import predict as P
+    d = {"Frame": [0, 1, 2], "X": [640, 0, 17], "Y": [360, 0, 5], "Visibility": [1, 0, 1]}
+    P.write_pred_csv(d, str(tmp_path / "a.csv"))
+    ref = pd.DataFrame({"Frame": d["Frame"], "Visibility": d["Visibility"], "X": d["X"], "Y": d["Y"]}).to_csv(index=False)
+    assert open(tmp_path / "a.csv").read() == ref
+    with pytest.raises(AssertionError, match="Invalid video file format"):
+        P.generate_frames("clip.avi")
+    import cv2
+    path = str(tmp_path / "clip.mp4")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 25, (64, 48))
+    if not wr.isOpened():
+        pytest.skip("no mp4 encoder in this OpenCV build")
+    for i in range(5):
+        wr.write(np.full((48, 64, 3), 40 * i, np.uint8))
+    wr.release()
+    frames = P.generate_frames(path)
+    assert len(frames) == 5 and frames[0].shape == (48, 64, 3)
+    assert abs(int(frames[3].mean()) - 120) <= 3
+
+
+def test_predict_load_models_reads_the_reference_checkpoint_layout(tmp_path):
+    import predict as P
+    import train as TR
+    from utils.general import get_model
+    torch.manual_seed(3)
+    tn, ip = get_model("TrackNet", 4, "subtract"), get_model("InpaintNet")
+    pd_t = {"model_name": "TrackNet", "seq_len": 4, "bg_mode": "subtract"}
+    pd_i = {"model_name": "InpaintNet", "seq_len": 16, "bg_mode": ""}
+    torch.save(TR.checkpoint_dict(0, 0.1, tn, torch.optim.SGD(tn.parameters(), lr=0.1), None, pd_t), tmp_path / "t.pt")
+    torch.save(TR.checkpoint_dict(0, 0.1, ip, torch.optim.SGD(ip.parameters(), lr=0.1), None, pd_i), tmp_path / "i.pt")
+    t2, i2, seq_len, bg_mode = P.load_models(str(tmp_path / "t.pt"), str(tmp_path / "i.pt"))
+    assert (seq_len, bg_mode, t2.in_dim, t2.out_dim) == (4, "subtract", 4, 4)
+    assert all(torch.equal(a, b) for a, b in zip(tn.state_dict().values(), t2.state_dict().values()))
+    assert all(torch.equal(a, b) for a, b in zip(ip.state_dict().values(), i2.state_dict().values()))
+    assert P.load_models(str(tmp_path / "t.pt"))[1] is None
