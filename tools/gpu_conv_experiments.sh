@@ -1,0 +1,24 @@
+#!/bin/bash
+# usage: tools/gpu_conv_experiments.sh <outdir-name>: first GPU run of the two experimental forward/dgrad kernels
+# (conv_lean.cu: TNB_CONV_LEAN=1, conv_pair.cu: TNB_CONV_PAIR=1) - parity tests under each switch, then bench.py with the
+# per-launch table for the shipped kernel and each experiment on the same box.
+cd "$(dirname "$0")/.."
+OUT=gpurun_out/$1
+mkdir -p $OUT
+: > $OUT/summary.txt
+for sw in TNB_CONV_LEAN TNB_CONV_PAIR; do
+  env $sw=1 timeout -k 5 200 python -m pytest tests/test_gpu_conv.py -x -q -k "not wgrad and not bn_reduce" > $OUT/pytest_conv_$sw.log 2>&1; echo "pytest conv ($sw) rc=$?" >> $OUT/summary.txt
+  tail -12 $OUT/pytest_conv_$sw.log | cut -c1-300 >> $OUT/summary.txt
+  env $sw=1 timeout -k 5 200 python -m pytest tests/test_gpu_tracknet.py -x -q > $OUT/pytest_net_$sw.log 2>&1; echo "pytest tracknet ($sw) rc=$?" >> $OUT/summary.txt
+  tail -4 $OUT/pytest_net_$sw.log | cut -c1-300 >> $OUT/summary.txt
+done
+for sw in NONE TNB_CONV_LEAN TNB_CONV_PAIR; do
+  env $sw=1 timeout -k 5 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --per-launch > $OUT/bench_$sw.log 2> $OUT/launches_$sw.txt
+  tail -1 $OUT/bench_$sw.log | python -c "
+import json,sys
+try:
+    d=json.loads(sys.stdin.read()); print('bench $sw: ms',round(d['ms_per_step'],3),{k:round(v['ms_per_step'],3) for k,v in d['kernel_breakdown'].items()},'clk',d['clocks'])
+except Exception as e: print('parse failed',e)" >> $OUT/summary.txt
+done
+cat $OUT/summary.txt
+paste -d'|' <(grep "^launch" $OUT/launches_NONE.txt | cut -c1-100) <(grep "^launch" $OUT/launches_TNB_CONV_LEAN.txt | awk '{print $8}') <(grep "^launch" $OUT/launches_TNB_CONV_PAIR.txt | awk '{print $8}') | grep -E "fwd|dgrad"

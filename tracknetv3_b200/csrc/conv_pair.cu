@@ -24,6 +24,7 @@ namespace tnb {
 #define TNB_CK_NAME conv3x3_pair_kernel
 #define TNB_CK_ARGS ConvPairArgs
 #define TNB_CK_PAIR 1
+#define TNB_CK_LEAN 0
 #include "conv_kernel.inc"
 
 int launch_conv3x3_pair(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout, int nterms,

@@ -159,6 +159,9 @@ int launch_pack_weights(const float* w_oihw, uint16_t* out, int Co, int Ci, int 
 // per-tile partials become (sum g, sum g * xhat) with g = out masked by that layer's ReLU - the reduction pass of its
 // BatchNorm backward - instead of (sum out, sum out^2).
 struct BnBwdFuse { const float *z, *scale, *shift, *mean, *invstd; };
+// lean-issue variant (conv_lean.cu, TNB_CONV_LEAN=1)
+int launch_conv3x3_lean(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout, int nterms,
+                        int fmt, int variant, const ConvPlan& plan, cudaStream_t st);
 // CTA-pair variant (conv_pair.cu), selected by launch_conv3x3 when the plan says so
 int launch_conv3x3_pair(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout, int nterms,
                         int fmt, int variant, const ConvPlan& plan, cudaStream_t st);
