@@ -345,7 +345,10 @@ TNB_DEVINL float4 ld4(const float* p) { return __ldg(reinterpret_cast<const floa
 TNB_DEVINL float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 // CFG 0: one GRAD_SAME consumer; CFG 1: {GRAD_POOL, GRAD_SAME}; CFG 2: anything else (generic gather)
-template <bool APPLY, int CFG>
+// REV (experiment, TNB_BN_REVERSE=1): the reduction pass walks the tensor in descending address order, so that it starts on
+// the tail of dy the dgrad kernel has just written and the apply pass (ascending) starts on what the reduction read last -
+// the 126 MB L2 then serves part of the second read. A pure permutation of the item -> thread assignment.
+template <bool APPLY, int CFG, bool REV = false>
 __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnBwdArgs a) {
   const int CQ = a.C >> 2;
   const int Hw = (a.H + 1) >> 1, Ww = (a.W + 1) >> 1;
@@ -354,7 +357,8 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnB
   const unsigned cq_shift = 31 - __clz(CQ);             // CQ is a power of two (256 % CQ == 0)
   float4 acc1 = make_float4(0, 0, 0, 0), acc2 = make_float4(0, 0, 0, 0);
   float amax = 0.f;
-  for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += stride) {
+  for (unsigned it0 = blockIdx.x * blockDim.x + threadIdx.x; it0 < items; it0 += stride) {
+    const unsigned it = REV ? items - 1 - it0 : it0;
     const int cq = (int)(it & (CQ - 1));
     unsigned r = it >> cq_shift;
     const int ww = (int)(r % (unsigned)Ww); r /= (unsigned)Ww;
@@ -537,6 +541,14 @@ int launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t st) {
   if (int rc = bn_bwd_check(a)) return rc;
   ProfScope prof(PROF_BN_BWD, st, a.N, a.H, a.W, a.C, a.C);
   const int nb = bn_bwd_num_blocks(a.N, a.H, a.W, a.C);
+  static const int reverse = [] { const char* e = getenv("TNB_BN_REVERSE"); return e ? atoi(e) : 0; }();
+  if (reverse) {
+    switch (bn_bwd_cfg(a)) {
+      case 0: bn_bwd_kernel<false, 0, true><<<nb, 256, 0, st>>>(a); break;
+      case 1: bn_bwd_kernel<false, 1, true><<<nb, 256, 0, st>>>(a); break;
+      default: bn_bwd_kernel<false, 2, true><<<nb, 256, 0, st>>>(a); break;
+    }
+  } else
   switch (bn_bwd_cfg(a)) {
     case 0: bn_bwd_kernel<false, 0><<<nb, 256, 0, st>>>(a); break;
     case 1: bn_bwd_kernel<false, 1><<<nb, 256, 0, st>>>(a); break;
