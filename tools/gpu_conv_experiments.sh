@@ -23,5 +23,13 @@ try:
     d=json.loads(sys.stdin.read()); print('bench $sw: ms',round(d['ms_per_step'],3),{k:round(v['ms_per_step'],3) for k,v in d['kernel_breakdown'].items()},'clk',d['clocks'])
 except Exception as e: print('parse failed',e)" >> $OUT/summary.txt
 done
+TNB_CONV_PAIR=1 TNB_CONV_LEAN=1 timeout -k 5 200 python -m pytest tests/test_gpu_conv.py tests/test_gpu_tracknet.py -x -q -k "not wgrad and not bn_reduce" > $OUT/pytest_pair_lean.log 2>&1; echo "pytest (pair + lean) rc=$?" >> $OUT/summary.txt
+tail -3 $OUT/pytest_pair_lean.log | cut -c1-300 >> $OUT/summary.txt
+TNB_CONV_PAIR=1 TNB_CONV_LEAN=1 timeout -k 5 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --per-launch > $OUT/bench_PAIR_LEAN.log 2> $OUT/launches_PAIR_LEAN.txt
+tail -1 $OUT/bench_PAIR_LEAN.log | python -c "
+import json,sys
+try:
+    d=json.loads(sys.stdin.read()); print('bench pair+lean: ms',round(d['ms_per_step'],3),{k:round(v['ms_per_step'],3) for k,v in d['kernel_breakdown'].items()},'clk',d['clocks'])
+except Exception as e: print('parse failed',e)" >> $OUT/summary.txt
 cat $OUT/summary.txt
 paste -d'|' <(grep "^launch" $OUT/launches_NONE.txt | cut -c1-100) <(grep "^launch" $OUT/launches_TNB_CONV_LEAN.txt | awk '{print $8}') <(grep "^launch" $OUT/launches_TNB_CONV_PAIR.txt | awk '{print $8}') | grep -E "fwd|dgrad"

@@ -147,9 +147,10 @@ int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, floa
   ConvPlan p;
   int rc = conv3x3_plan(view.N, view.H, view.W, view.C, Cout, nterms, &p, fuse != nullptr);
   if (rc) return rc;
-  if (p.pair) return launch_conv3x3_pair(view, wpack, out, stat_part, Cout, nterms, fmt, variant, p, st);
   // TNB_CONV_LEAN=1: experimental lean MMA-issue loop (conv_lean.cu), same plan and weight layout as the shipped kernel
   static const int lean_env = [] { const char* e = getenv("TNB_CONV_LEAN"); return e ? atoi(e) : 0; }();
+  if (p.pair && lean_env) return launch_conv3x3_pair_lean(view, wpack, out, stat_part, Cout, nterms, fmt, variant, p, st);
+  if (p.pair) return launch_conv3x3_pair(view, wpack, out, stat_part, Cout, nterms, fmt, variant, p, st);
   if (lean_env && fuse == nullptr) return launch_conv3x3_lean(view, wpack, out, stat_part, Cout, nterms, fmt, variant, p, st);
   const int m0 = view.s[0].mode, m1 = (view.C0 < view.C) ? view.s[1].mode : view.s[0].mode;
   ConvArgs a;

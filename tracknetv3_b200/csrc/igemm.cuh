@@ -162,6 +162,8 @@ struct BnBwdFuse { const float *z, *scale, *shift, *mean, *invstd; };
 // lean-issue variant (conv_lean.cu, TNB_CONV_LEAN=1)
 int launch_conv3x3_lean(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout, int nterms,
                         int fmt, int variant, const ConvPlan& plan, cudaStream_t st);
+int launch_conv3x3_pair_lean(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout, int nterms,
+                             int fmt, int variant, const ConvPlan& plan, cudaStream_t st);  // both experiments (conv_pair_lean.cu)
 // CTA-pair variant (conv_pair.cu), selected by launch_conv3x3 when the plan says so
 int launch_conv3x3_pair(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout, int nterms,
                         int fmt, int variant, const ConvPlan& plan, cudaStream_t st);
