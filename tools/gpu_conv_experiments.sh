@@ -2,20 +2,22 @@
 # usage: tools/gpu_conv_experiments.sh <outdir-name>: first GPU run of the two experimental forward/dgrad kernels
 # (conv_lean.cu: TNB_CONV_LEAN=1, conv_pair.cu: TNB_CONV_PAIR=1) - parity tests under each switch, then bench.py with the
 # per-launch table for the shipped kernel and each experiment on the same box (plus TNB_BN_REVERSE=1: descending-order
-# BatchNorm-backward reduction pass, covered by tests/test_gpu_ops.py under that switch).
+# BatchNorm-backward reduction pass, and TNB_WGRAD_LEAN=1: lean issue loop of the tap-stacked wgrad kernel).
 cd "$(dirname "$0")/.."
 OUT=gpurun_out/$1
 mkdir -p $OUT
 : > $OUT/summary.txt
 TNB_BN_REVERSE=1 timeout -k 5 200 python -m pytest tests/test_gpu_ops.py tests/test_gpu_tracknet.py -x -q -k "bn or train_step or backward" > $OUT/pytest_bnrev.log 2>&1; echo "pytest (TNB_BN_REVERSE) rc=$?" >> $OUT/summary.txt
 tail -3 $OUT/pytest_bnrev.log | cut -c1-300 >> $OUT/summary.txt
+TNB_WGRAD_LEAN=1 timeout -k 5 200 python -m pytest tests/test_gpu_conv.py -x -q -k "wgrad" > $OUT/pytest_wgrad_lean.log 2>&1; echo "pytest wgrad (TNB_WGRAD_LEAN) rc=$?" >> $OUT/summary.txt
+tail -3 $OUT/pytest_wgrad_lean.log | cut -c1-300 >> $OUT/summary.txt
 for sw in TNB_CONV_LEAN TNB_CONV_PAIR; do
   env $sw=1 timeout -k 5 200 python -m pytest tests/test_gpu_conv.py -x -q -k "not wgrad and not bn_reduce" > $OUT/pytest_conv_$sw.log 2>&1; echo "pytest conv ($sw) rc=$?" >> $OUT/summary.txt
   tail -12 $OUT/pytest_conv_$sw.log | cut -c1-300 >> $OUT/summary.txt
   env $sw=1 timeout -k 5 200 python -m pytest tests/test_gpu_tracknet.py -x -q > $OUT/pytest_net_$sw.log 2>&1; echo "pytest tracknet ($sw) rc=$?" >> $OUT/summary.txt
   tail -4 $OUT/pytest_net_$sw.log | cut -c1-300 >> $OUT/summary.txt
 done
-for sw in NONE TNB_CONV_LEAN TNB_CONV_PAIR TNB_BN_REVERSE; do
+for sw in NONE TNB_CONV_LEAN TNB_CONV_PAIR TNB_BN_REVERSE TNB_WGRAD_LEAN; do
   env $sw=1 timeout -k 5 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --per-launch > $OUT/bench_$sw.log 2> $OUT/launches_$sw.txt
   tail -1 $OUT/bench_$sw.log | python -c "
 import json,sys

@@ -597,6 +597,10 @@ struct WgradSArgs {
   float* ws;  // optional tap-major accumulation buffer [9][Cout][C] (see launch_wgrad_scatter); nullptr: dw
 };
 
+// LEAN (experiment, TNB_WGRAD_LEAN=1, not yet run on a GPU): the issue loop of the elected thread with the term count
+// compile-time, one branch per K tile and 32-bit descriptor stepping (see the lean path of conv_kernel.inc) - the N = 64
+// MMAs of this kernel last 48 clocks, the generic loop spends ~7 instructions on each.
+template <bool LEAN>
 __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __grid_constant__ WgradSArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
@@ -664,6 +668,35 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __g
         tc_fence_after();
         const uint64_t a_st = a_desc0 + (uint64_t)(s * stage16);
         const uint64_t b_st = b_desc0 + (uint64_t)(s * stage16);
+        if (LEAN) {
+          const uint32_t a_w_st = (uint32_t)a_st, b_w_st = (uint32_t)b_st;  // low descriptor words: start address | LBO << 16
+          const uint32_t a_hi32 = (uint32_t)(a_desc0 >> 32), b_hi32 = (uint32_t)(b_desc0 >> 32);
+          const uint32_t first_acc = kt != kt0 ? 1u : 0u;
+          auto issue = [&](auto terms_tag) {
+            constexpr int TERMS = decltype(terms_tag)::value;
+            if (lead) {
+              for (int g = 0; g < nacc; g += 3) {  // filter-row group {dy, dy + 1}: halo rows r + dyb
+                const uint32_t a_g = a_w_st + (uint32_t)((g / 3) * 2) * row16;
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                  const uint32_t d_tmem = tmem_base + (uint32_t)(g + dx) * 64;
+#pragma unroll
+                  for (int r = 0; r < kTileH; ++r) {
+                    const uint32_t a_w = a_g + (uint32_t)r * row16 + (uint32_t)dx;
+                    const uint32_t b_w = b_w_st + (uint32_t)(r * kTileW);
+                    const uint32_t acc = r != 0 ? 1u : first_acc;
+                    umma_f16_w(d_tmem, a_w, a_hi32, b_w, b_hi32, idesc, acc);
+                    if (TERMS > 1) {
+                      umma_f16_w(d_tmem, a_w + a_lo16, a_hi32, b_w, b_hi32, idesc, 1);
+                      umma_f16_w(d_tmem, a_w, a_hi32, b_w + b_lo16, b_hi32, idesc, 1);
+                    }
+                  }
+                }
+              }
+            }
+          };
+          if (a.nterms > 1) issue(std::integral_constant<int, 3>{}); else issue(std::integral_constant<int, 1>{});
+        } else
         for (int acc_i = 0; acc_i < nacc; ++acc_i) {  // one accumulator = one chain of 4 rows x nterms MMAs
           const int dx = acc_i % 3, dyb = (acc_i / 3) * 2;
           const uint32_t d_tmem = tmem_base + acc_i * 64;
@@ -841,10 +874,13 @@ static int launch_wgrad3x3_stacked(const ViewDesc& view, const void* dz_presplit
   const int TP = nterms > 1 ? 2 : 1;
   const size_t smem = kHdrBytes + kSStages * (size_t)(TP * kSRows * a.P * kSRP + TP * 8 * pad_px(kTileH * kTileW) * 16);
   TNB_REQUIRE(smem <= 232448, "wgrad3x3 (stacked): shared memory plan too large (%zu)", smem);
-  TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_stacked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static const int lean_env = [] { const char* e = getenv("TNB_WGRAD_LEAN"); return e ? atoi(e) : 0; }();
+  TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_stacked_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_stacked_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(PROF_WGRAD, st, view.N, view.H, view.W, view.C, Cout);
   if (ws != nullptr) TNB_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 9 * (size_t)Cout * view.C, st));
-  wgrad3x3_stacked_kernel<<<dim3(gx, splits), kThreads, smem, st>>>(a);
+  if (lean_env) wgrad3x3_stacked_kernel<true><<<dim3(gx, splits), kThreads, smem, st>>>(a);
+  else          wgrad3x3_stacked_kernel<false><<<dim3(gx, splits), kThreads, smem, st>>>(a);
   TNB_CHECK_CUDA(cudaGetLastError());
   if (ws != nullptr) return launch_wgrad_scatter(ws, dw, Cout, view.C, CinReal, 1, st);
   return 0;
