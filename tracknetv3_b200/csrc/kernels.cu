@@ -537,12 +537,12 @@ static int bn_bwd_check(const BnBwdArgs& a) {
   TNB_REQUIRE((long long)a.N * ((a.H + 1) / 2) * ((a.W + 1) / 2) * (a.C / 4) < (1ll << 31), "bn_bwd: tensor too large");
   return 0;
 }
-int launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t st) {
+int launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t st, int rev) {
   if (int rc = bn_bwd_check(a)) return rc;
   ProfScope prof(PROF_BN_BWD, st, a.N, a.H, a.W, a.C, a.C);
   const int nb = bn_bwd_num_blocks(a.N, a.H, a.W, a.C);
   static const int reverse = [] { const char* e = getenv("TNB_BN_REVERSE"); return e ? atoi(e) : 0; }();
-  if (reverse) {
+  if (rev < 0 ? reverse != 0 : rev != 0) {  // rev < 0: no per-call direction, the environment switch decides
     switch (bn_bwd_cfg(a)) {
       case 0: bn_bwd_kernel<false, 0, true><<<nb, 256, 0, st>>>(a); break;
       case 1: bn_bwd_kernel<false, 1, true><<<nb, 256, 0, st>>>(a); break;
@@ -557,10 +557,17 @@ int launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t st) {
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
-int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st) {
+int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st, int rev) {
   if (int rc = bn_bwd_check(a)) return rc;
   ProfScope prof(PROF_BN_BWD, st, a.N, a.H, a.W, a.C, a.C);
   const int nb = bn_bwd_num_blocks(a.N, a.H, a.W, a.C);
+  if (rev > 0) {  // descending traversal (TNB_PINGPONG experiment, net.cu)
+    switch (bn_bwd_cfg(a)) {
+      case 0: bn_bwd_kernel<true, 0, true><<<nb, 256, 0, st>>>(a); break;
+      case 1: bn_bwd_kernel<true, 1, true><<<nb, 256, 0, st>>>(a); break;
+      default: bn_bwd_kernel<true, 2, true><<<nb, 256, 0, st>>>(a); break;
+    }
+  } else
   switch (bn_bwd_cfg(a)) {
     case 0: bn_bwd_kernel<true, 0><<<nb, 256, 0, st>>>(a); break;
     case 1: bn_bwd_kernel<true, 1><<<nb, 256, 0, st>>>(a); break;

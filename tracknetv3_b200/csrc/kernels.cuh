@@ -19,10 +19,11 @@ int launch_predictor_fwd(const SrcDesc& src, int N, int H, int W, const float* w
 int launch_predictor_bwd(const SrcDesc& src, int N, int H, int W, const float* wp, int O, const float* dy,
                          const float* y, float* dA, float* dwp, float* dbias, cudaStream_t st);
 int bn_bwd_num_blocks(int N, int H, int W, int C);
-int launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t st);
+// rev: traversal direction of the pass (experiments): < 0 = TNB_BN_REVERSE decides (reduce pass only), 0 = ascending, 1 = descending
+int launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t st, int rev = -1);
 int launch_bn_bwd_finalize(const float* part, int rows, int C, float* sums, float* dgamma, float* dbeta,
                            cudaStream_t st);
-int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st);
+int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st, int rev = -1);
 
 int wbce_num_blocks(long long per_sample);
 int launch_wbce_fwd(const float* p, const float* y, int nsamples, long long per_sample, int reduce,

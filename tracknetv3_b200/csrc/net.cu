@@ -198,6 +198,14 @@ size_t tracknet_workspace_bytes(const tnb_tracknet_cfg_t& c) {
   return P.bytes;
 }
 
+// TNB_PINGPONG=1 (experiment, needs TNB_CONV_LEAN=1 for the convolutions to follow): every kernel walks its tensor in the
+// direction opposite to the kernel that produced its input, so that it starts on what is still in the 126 MB L2.
+// Forward: conv(l) descending for odd l. Backward: reduce(l) and dgrad(l) descending for even (16 - l), apply(l) the opposite.
+static int pingpong_env() {
+  static const int v = [] { const char* e = getenv("TNB_PINGPONG"); return e ? atoi(e) : 0; }();
+  return v;
+}
+
 static int forward_enqueue(const tnb_tracknet_cfg_t& c, const float* x, void* const* params, float* y, void* ws,
                            size_t ws_bytes, cudaStream_t st) {
   Plan P;
@@ -212,7 +220,7 @@ static int forward_enqueue(const tnb_tracknet_cfg_t& c, const float* x, void* co
     if (int rc = launch_pack_weights(w, B.wf, B.cout, B.cin_real, 0, 0, cp.BN, st)) return rc;
     const ViewDesc v = make_view(P, c, l);
     if (int rc = launch_conv3x3(v, B.wf, B.z, c.training ? B.stat_part : nullptr, B.cout, c.fwd_terms, 0,
-                                c.variant & 3, st))
+                                (c.variant & 3) | ((pingpong_env() && (l & 1)) ? 1024 : 0), st))
       return rc;
     if (int rc = launch_bn_finalize(B.stat_part, B.stat_rows, (double)c.n * B.H * B.W, (const float*)params[l * 6 + 1],
                                     (const float*)params[l * 6 + 2], (float*)params[l * 6 + 3],
@@ -285,13 +293,15 @@ static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const 
     a.N = c.n; a.H = B.H; a.W = B.W; a.C = B.cout;
     a.part = B.bwd_part; a.sums = B.bwd_sums; a.dz = B.dz; a.amax = nullptr; a.dz_format = 1;  // dz -> pre-split bf16
     a.inv_count = (float)(1.0 / ((double)c.n * B.H * B.W));
+    const int pp = pingpong_env();
+    const int red_rev = pp ? (((kLayers - 1 - l) & 1) == 0 ? 1 : 0) : -1;  // -1: TNB_BN_REVERSE decides
     if (B.fused_rows == 0)
-      if (int rc = launch_bn_bwd_reduce(a, st)) return rc;
+      if (int rc = launch_bn_bwd_reduce(a, st, red_rev)) return rc;
     if (int rc = launch_bn_bwd_finalize(B.bwd_part, B.fused_rows > 0 ? B.fused_rows : B.bwd_rows, B.cout, B.bwd_sums,
                                         (float*)grads[l * 3 + 1], (float*)grads[l * 3 + 2], st))
       return rc;
     a.act_presplit = (pending == l + 1) ? P.vsplit : nullptr;
-    if (int rc = launch_bn_bwd_apply(a, st)) return rc;
+    if (int rc = launch_bn_bwd_apply(a, st, pp ? 1 - red_rev : -1)) return rc;
     if (pending == l + 1) {
       if (int rc = run_wgrad(pending, plain_presplit_view(pending))) return rc;
       pending = -1;
@@ -310,7 +320,7 @@ static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const 
       if (int rc = conv3x3_plan(c.n, B.H, B.W, B.cout, B.cin, c.bwd_terms, &cp, Pp != nullptr)) return rc;
       if (int rc = launch_pack_weights(w, B.wd, B.cout, B.cin, 1, 1, cp.BN, st)) return rc;
       if (int rc = launch_conv3x3(dv, B.wd, B.din, Pp != nullptr ? Pp->bwd_part : nullptr, B.cin, c.bwd_terms, 1,
-                                  c.variant & 3, st, Pp != nullptr ? &fuse : nullptr))
+                                  (c.variant & 3) | ((pp && red_rev == 1) ? 1024 : 0), st, Pp != nullptr ? &fuse : nullptr))
         return rc;
     }
     if (wgrad_operand_from_bn_bwd(c, l)) { pending = l; continue; }
