@@ -65,3 +65,58 @@ def test_no_oracle_or_torch_fallback_in_product():
         m(torch.zeros(1, 12, 32, 32))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         T.WBCELoss(torch.rand(1, 1, 4, 4), torch.rand(1, 1, 4, 4))
+
+
+_LAYER_SHAPES = [(27, 64, 0), (64, 64, 0), (64, 128, 1), (128, 128, 1), (128, 256, 2), (256, 256, 2), (256, 512, 3),
+                 (512, 512, 3), (768, 256, 2), (384, 128, 1), (192, 64, 0)]  # (cin, cout, level) of TrackNet's 3x3 layers
+
+
+def _plans(lib, hw_list=((288, 512), (360, 640), (544, 960), (64, 96)), terms_list=(3, 1)):
+    out = (C.c_int * 12)()
+    for h, w in hw_list:
+        for cin, cout, level in _LAYER_SHAPES:
+            for side in ((cin, cout), (cout, cin)):  # forward, and dgrad (K side = cout, N side = cin)
+                if side[1] == 27:
+                    continue  # the first layer has no dgrad
+                for terms in terms_list:
+                    assert lib.tnb_conv3x3_plan_query(10, h >> level, w >> level, side[0], side[1], terms, out) == 0
+                    yield (h, w, side, terms), list(out)
+
+
+def test_conv_plans_fit_the_sm_for_every_layer_and_resolution():
+    """Launch plans of every TrackNet layer (forward and dgrad orientation) at the reference resolution, the sweep
+    resolutions and the smoke size: shared memory within the 227 KB opt-in limit, TMEM within 512 columns (a power of
+    two), at least two slots in every ring, two accumulator buffers whenever they fit, 64-wide tiles merged."""
+    lib = _lib.load()
+    n = 0
+    for key, (bn, mt, sa, sb, g, nbuf, tmem, smem, merged, tall, pair, layout) in _plans(lib):
+        n += 1
+        assert key[2][1] % bn == 0 and bn in (32, 64, 128, 192, 256), key
+        assert 0 < smem <= 232448, (key, smem)
+        accw = 2 * bn if (merged and key[3] > 1) else bn
+        assert nbuf * mt * accw <= tmem <= 512 and tmem & (tmem - 1) == 0, key
+        assert nbuf == (2 if 2 * mt * accw <= 512 else 1), key
+        assert sa >= 2 and sb >= 2 and g in (1, 3) and sb <= 8, key
+        assert merged == (1 if bn == 64 else 0) and pair == 0 and layout == merged, key  # experiments are off by default
+        assert tall in (0, 1)
+    assert n == (len(_LAYER_SHAPES) * 2 - 1) * 2 * 4
+
+
+def test_conv_plans_under_the_pair_switch_subprocess():
+    """TNB_CONV_PAIR=1 (read once per process): every plan asks for the per-rank weight layout, never the merged one, and
+    still fits; a fused BatchNorm-backward reduction is refused together with it."""
+    import subprocess
+    import sys
+    code = (
+        "import ctypes as C, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from tracknetv3_b200 import _lib\n"
+        "from tests.test_abi import _plans\n"
+        "lib = _lib.load()\n"
+        "for key, p in _plans(lib, hw_list=((288, 512),), terms_list=(3,)):\n"
+        "    assert p[10] == 1 and p[11] == 2 and p[8] == 0 and 0 < p[7] <= 232448 and p[3] >= 2, (key, p)\n"
+        "assert lib.tnb_conv3x3_dgrad_bnreduce_rows(10, 288, 512, 64, 64, 3) < 0\n"
+        "print('ok')\n" % ROOT)
+    env = dict(os.environ, TNB_CONV_PAIR="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr

@@ -55,6 +55,7 @@ SIGNATURES = {
     "tnb_conv3x3_wpack_elems": (sz, [i32, i32]),
     "tnb_conv3x3_pack_weights": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "tnb_conv3x3_stat_rows": (i32, [i32, i32, i32, i32, i32, i32]),
+    "tnb_conv3x3_plan_query": (i32, [i32, i32, i32, i32, i32, i32, vp]),
     "tnb_conv3x3_fwd": (i32, [C.POINTER(View), vp, vp, vp, i32, i32, i32, i32, vp]),
     "tnb_conv3x3_dgrad_bnreduce_rows": (i32, [i32, i32, i32, i32, i32, i32]),
     "tnb_conv3x3_dgrad_bnreduce": (i32, [C.POINTER(View), vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
