@@ -377,6 +377,9 @@ __host__ __device__ inline int pad_sel(int px, int mode) {
   return px + ((want - r) & 7);
 }
 
+// LEAN (experiment, TNB_WGRAD_LEAN=1): lean issue loop, see wgrad3x3_stacked_kernel / conv_kernel.inc - the issuing warp of
+// this kernel is busy all the time too (ncu source page: ~10 instructions and ~78 clocks per 64-clock MMA).
+template <bool LEAN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     wgrad3x3_pair_kernel(const __grid_constant__ WgradArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -438,6 +441,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         tc_fence_after();
         const uint64_t a_st = a_desc0 + (uint64_t)(s * stage16);
         const uint64_t b_st = b_desc0 + (uint64_t)(s * stage16);
+        if (LEAN) {
+          const uint32_t a_w_st = (uint32_t)a_st, b_w_st = (uint32_t)b_st;  // low descriptor words: start address | LBO << 16
+          const uint32_t a_hi32 = (uint32_t)(a_desc0 >> 32), b_hi32 = (uint32_t)(b_desc0 >> 32);
+          const uint32_t first_acc = kt != kt0 ? 1u : 0u;
+          auto issue = [&](auto terms_tag) {
+            constexpr int TERMS = decltype(terms_tag)::value;
+            if (lead) {
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                const uint32_t d_tmem = tmem_base + dx * 128;
+#pragma unroll
+                for (int r = 0; r < kTileH; ++r) {
+                  const uint32_t a_w = a_w_st + (uint32_t)(r * kTileW);
+                  const uint32_t b_w = b_w_st + (uint32_t)(r * kHaloW + dx);
+                  const uint32_t acc = r != 0 ? 1u : first_acc;
+                  umma_f16_w_pair(d_tmem, a_w, a_hi32, b_w, b_hi32, idesc, acc);
+                  if (TERMS > 1) {
+                    umma_f16_w_pair(d_tmem, a_w + a_lo16, a_hi32, b_w, b_hi32, idesc, 1);
+                    umma_f16_w_pair(d_tmem, a_w, a_hi32, b_w + b_lo16, b_hi32, idesc, 1);
+                  }
+                }
+              }
+            }
+          };
+          if (a.nterms > 1) issue(std::integral_constant<int, 3>{}); else issue(std::integral_constant<int, 1>{});
+        } else
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
           const uint32_t d_tmem = tmem_base + dx * 128;
@@ -934,8 +963,12 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
     const size_t psmem = kHdrBytes + kPStages * (size_t)(TP * 16 * pad_sel(kTileH * kTileW, padm) * 16 +
                                                          TP * 8 * pad_sel(kTileH * kHaloW, padm) * 16);
     TNB_REQUIRE(psmem <= 232448, "wgrad3x3 (pair): shared memory plan too large (%zu)", psmem);
-    TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-    wgrad3x3_pair_kernel<<<dim3(gx, splits), kThreads, psmem, st>>>(a);  // gx = ncot * ncit * 3 with ncot even
+    static const int lean_env = [] { const char* e = getenv("TNB_WGRAD_LEAN"); return e ? atoi(e) : 0; }();
+    TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+    TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+    // gx = ncot * ncit * 3 with ncot even
+    if (lean_env) wgrad3x3_pair_kernel<true><<<dim3(gx, splits), kThreads, psmem, st>>>(a);
+    else          wgrad3x3_pair_kernel<false><<<dim3(gx, splits), kThreads, psmem, st>>>(a);
     TNB_CHECK_CUDA(cudaGetLastError());
     if (ws != nullptr) return launch_wgrad_scatter(ws, dw, Cout, view.C, CinReal, 0, st);
     return 0;
