@@ -151,7 +151,7 @@ int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, floa
   static const int lean_env = [] { const char* e = getenv("TNB_CONV_LEAN"); return e ? atoi(e) : 0; }();
   if (p.pair && lean_env) return launch_conv3x3_pair_lean(view, wpack, out, stat_part, Cout, nterms, fmt, variant, p, st);
   if (p.pair) return launch_conv3x3_pair(view, wpack, out, stat_part, Cout, nterms, fmt, variant, p, st);
-  if (lean_env && fuse == nullptr) return launch_conv3x3_lean(view, wpack, out, stat_part, Cout, nterms, fmt, variant, p, st);
+  if (lean_env) return launch_conv3x3_lean(view, wpack, out, stat_part, Cout, nterms, fmt, variant, p, st, fuse);
   const int m0 = view.s[0].mode, m1 = (view.C0 < view.C) ? view.s[1].mode : view.s[0].mode;
   ConvArgs a;
   a.view = view; a.wpack = wpack; a.out = out; a.stat_part = stat_part;

@@ -161,12 +161,12 @@ int launch_pack_weights(const float* w_oihw, uint16_t* out, int Co, int Ci, int 
 struct BnBwdFuse { const float *z, *scale, *shift, *mean, *invstd; };
 // lean-issue variant (conv_lean.cu, TNB_CONV_LEAN=1)
 int launch_conv3x3_lean(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout, int nterms,
-                        int fmt, int variant, const ConvPlan& plan, cudaStream_t st);
+                        int fmt, int variant, const ConvPlan& plan, cudaStream_t st, const BnBwdFuse* fuse = nullptr);
 int launch_conv3x3_pair_lean(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout, int nterms,
-                             int fmt, int variant, const ConvPlan& plan, cudaStream_t st);  // both experiments (conv_pair_lean.cu)
+                             int fmt, int variant, const ConvPlan& plan, cudaStream_t st, const BnBwdFuse* fuse = nullptr);  // both experiments (conv_pair_lean.cu)
 // CTA-pair variant (conv_pair.cu), selected by launch_conv3x3 when the plan says so
 int launch_conv3x3_pair(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout, int nterms,
-                        int fmt, int variant, const ConvPlan& plan, cudaStream_t st);
+                        int fmt, int variant, const ConvPlan& plan, cudaStream_t st, const BnBwdFuse* fuse = nullptr);
 int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout,
                    int nterms, int fmt, int variant, cudaStream_t st, const BnBwdFuse* fuse = nullptr);
 int conv3x3_num_stat_rows(int N, int H, int W, int Cin, int Cout, int nterms, bool bn_bwd_fused = false);
