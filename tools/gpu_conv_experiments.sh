@@ -33,6 +33,12 @@ import json,sys
 try:
     d=json.loads(sys.stdin.read()); print('bench pair+lean: ms',round(d['ms_per_step'],3),{k:round(v['ms_per_step'],3) for k,v in d['kernel_breakdown'].items()},'clk',d['clocks'])
 except Exception as e: print('parse failed',e)" >> $OUT/summary.txt
+TNB_CONV_LEAN=1 TNB_CONV_BACKOFF=1 timeout -k 5 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench_LEAN_BACKOFF.log 2>/dev/null
+tail -1 $OUT/bench_LEAN_BACKOFF.log | python -c "
+import json,sys
+try:
+    d=json.loads(sys.stdin.read()); print('bench lean + sleeping waits (TNB_CONV_BACKOFF): ms',round(d['ms_per_step'],3),{k:round(v['ms_per_step'],3) for k,v in d['kernel_breakdown'].items()},'clk',d['clocks'])
+except Exception as e: print('parse failed',e)" >> $OUT/summary.txt
 TNB_CONV_LEAN=1 timeout -k 5 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --variant 64 > $OUT/bench_LEAN_FUSED.log 2>/dev/null
 tail -1 $OUT/bench_LEAN_FUSED.log | python -c "
 import json,sys

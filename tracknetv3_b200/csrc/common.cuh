@@ -89,6 +89,19 @@ TNB_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same with a sleep between polls (sleep_ns = 0: plain spin): for roles that have slack in the pipeline.
+TNB_DEVINL void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t sleep_ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (sleep_ns) __nanosleep(sleep_ns);
+    if (++spins > (1u << 26)) {
+      printf("tnb: mbarrier wait timeout (block %d,%d thread %d bar %p parity %u)\n", blockIdx.x, blockIdx.y,
+             threadIdx.x, (void*)bar, parity);
+      __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // async-proxy fences and bulk TMA (1-D cp.async.bulk; SASS: UBLKCP)
 // ---------------------------------------------------------------------------------------------
