@@ -264,3 +264,25 @@ def test_predict_load_models_reads_the_reference_checkpoint_layout(tmp_path):
     assert all(torch.equal(a, b) for a, b in zip(tn.state_dict().values(), t2.state_dict().values()))
     assert all(torch.equal(a, b) for a, b in zip(ip.state_dict().values(), i2.state_dict().values()))
     assert P.load_models(str(tmp_path / "t.pt"))[1] is None
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line with the contract's keys, the
+    same metric / unit / config family as the GPU arm, zero transfer bytes, and a cpu_baseline that describes itself."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    import bench
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == "frames/s"
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["n_gpus"] == 1
+    assert d["value"] > 0 and abs(d["value"] - 8 / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]  # bs 1 x seq_len 8 per step
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "bs=1" in cb["sample"]
+    # non-zero ranks of a torchrun launch stay silent
+    r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1"],
+                        capture_output=True, text=True, cwd=ROOT, timeout=600, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r2.returncode == 0 and r2.stdout.strip() == ""
