@@ -199,6 +199,12 @@ int tnb_heatmap_decode(const void* maps, int is_u8, float thresh, int nmaps, int
 int tnb_inpaintnet_fwd(const float* coords, const float* mask, const void* const* params, int n, int l, float* out,
                        void* stream);
 
+/* The rectified trajectory of the InpaintNet inference loops (predict.py:256-261, test.py:401,406-408) in the same
+ * launch: out = InpaintNet(coords, mask) * mask + coords * (1 - mask), then both coordinates of a point set to 0 where
+ * both are < coor_th (COOR_TH, utils/general.py:19). Operation order and roundings are torch's (no fused multiply-add). */
+int tnb_inpaintnet_rectify(const float* coords, const float* mask, const void* const* params, int n, int l, float coor_th,
+                           float* out, void* stream);
+
 /* Autograd of the above, as train.py:147-166 needs it (loss.backward() through InpaintNet): one kernel that
  * recomputes the forward in shared memory. dout: (n, l, 2) gradient w.r.t. the output. grads: 18 device pointers
  * (same order as params) the parameter gradients are ADDED into (caller zeroes them). dcoords: optional (n, l, 2)
@@ -217,6 +223,18 @@ int tnb_inpaintnet_bwd(const float* coords, const float* mask, const void* const
 int tnb_resize_frames(const uint8_t* src, int nimg, int hs, int ws, int c, const int* hbounds, const int* hkk, int hksize,
                       const int* vbounds, const int* vkk, int vksize, int hd, int wd, uint8_t* tmp, float* out,
                       int per_sample, long long sample_stride, int chan_off, int frame_stride, void* stream);
+
+/* Median background of a clip (dataset.py:102-107: `np.median(self.frame_arr, 0)`): frames uint8 [nframes][frame_bytes]
+ * (frame_bytes = hs * ws * 3). Per byte position the two middle order statistics a <= b of the nframes values;
+ * out_f64[p] = (a + b) / 2 - numpy's float64 median, kept by bg_mode 'subtract' / 'subtract_concat' (dataset.py:108-109) -
+ * and out_u8[p] = floor((a + b) / 2) = `median.astype('uint8')` (bg_mode 'concat', dataset.py:105). Either may be NULL. */
+int tnb_median_u8(const uint8_t* frames, int nframes, long long frame_bytes, double* out_f64, uint8_t* out_u8,
+                  void* stream);
+
+/* Training labels (dataset.py:400-410 `_get_heatmap`, called with integer centres at :632): map m = 1 where
+ * (i - cx)^2 + (j - cy)^2 <= sigma^2 for pixel (row j, column i), all zeros when cx == cy == 0. centers_xy: device int32
+ * [nmaps][2]. out: [nmaps][h][w] fp32, w % 4 == 0. */
+int tnb_label_discs(const int* centers_xy, int nmaps, int h, int w, float sigma, float* out, void* stream);
 
 /* Background-difference image of bg_mode 'subtract' / 'subtract_concat' (dataset.py:438, 442):
  * out[i][y][x] = uint8 cast (numpy semantics: truncate, wrap modulo 256) of sum_c |frames[i][y][x][c] - median[y][x][c]|,

@@ -45,8 +45,10 @@ def predict(indices, y_pred=None, c_pred=None, img_scaler=(1, 1)):
             if f_i == prev_f_i:
                 break
             if c_pred is not None:
-                c_p = c_pred[n][f]
-                cx_pred, cy_pred = int(c_p[0] * WIDTH * img_scaler[0]), int(c_p[1] * HEIGHT * img_scaler[1])
+                # fp32 products like the reference's 0-dim tensor arithmetic (python scalars do not promote a tensor)
+                c_p = c_pred[n][f].astype(np.float32)
+                cx_pred = int(c_p[0] * np.float32(WIDTH) * np.float32(img_scaler[0]))
+                cy_pred = int(c_p[1] * np.float32(HEIGHT) * np.float32(img_scaler[1]))
             else:
                 x, y, w, h = (int(v) for v in boxes[n][f])
                 cx_pred, cy_pred = int(x + w / 2), int(y + h / 2)
@@ -92,64 +94,113 @@ def predict_ensemble(ensemble, indices, y_pred=None, c_pred=None, img_scaler=(1,
     raise ValueError('Invalid input')
 
 
+def _windows(n_frames, seq_len, sliding_step, padding):
+    """ Frame indices of every input sequence the reference's dataset builds over ``n_frames`` frames
+        (dataset.py:329-355 `_gen_input_from_frame_arr`, :357-395 `_gen_input_from_pred_dict`): windows start every
+        ``sliding_step`` frames; a window running past the end is dropped, or - with ``padding``, which the dataset only
+        honours for non-overlapping sampling (:92) - completed by repeating the last frame seen so far. (N, L) int64. """
+    padding = padding and sliding_step == seq_len
+    out, last = [], -1
+    for i in range(0, n_frames, sliding_step):
+        idx = []
+        for f in range(seq_len):
+            if i + f < n_frames:
+                idx.append(i + f)
+                last = i + f
+            elif padding:
+                idx.append(last)
+            else:
+                break
+        if len(idx) == seq_len:
+            out.append(idx)
+    return torch.tensor(out, dtype=torch.int64).reshape(-1, seq_len)
+
+
+def _as_indices(win):
+    """ (N, L) frame numbers -> the (N, L, 2) `(rally, frame)` index tensor the reference's datasets return. """
+    return torch.stack([torch.zeros_like(win), win], dim=-1)
+
+
+def _extend(dst, src):
+    for k in src:
+        dst[k].extend(src[k])
+
+
 def run_video(frames_u8, tracknet, inpaintnet=None, seq_len=8, bg_mode='concat', batch_size=16, eval_mode='weight',
-              img_scaler=(1, 1)):
-    """ The data path of the reference's `predict.py` __main__ (:110-301) for one video held in memory, entirely on the
-        GPU: frames -> Pillow-exact resize / stack (FramePreprocessor) -> TrackNet -> temporal ensemble -> heatmap decode
-        [-> generate_inpaint_mask -> InpaintNet on the decoded trajectory -> temporal ensemble]. Video file decoding
-        and the csv / video writers of the reference stay what they are (host code around this function).
+              img_scaler=None, inpaintnet_seq_len=16):
+    """ The data path of the reference's `predict.py` __main__ (:110-301, small-video branch) for one video held in
+        memory, entirely on the GPU: median background over all frames (dataset.py:102-107) -> Pillow-exact resize /
+        stack (FramePreprocessor) -> TrackNet -> [temporal ensemble ->] heatmap decode -> generate_inpaint_mask ->
+        InpaintNet + blend + threshold on the decoded trajectory [-> temporal ensemble]. All three ``eval_mode``s:
+        'nonoverlap' (windows every seq_len frames, the last one padded, :123-145, :224-238), 'average' / 'weight'
+        (windows every frame + temporal ensemble, :146-209, :239-301). Video file decoding and the csv / video writers
+        stay host code around this function. Pinned bit for bit to the reference's own __main__ by
+        tests/golden/predict_flow.npz (oracle/gen_predict_flow.py).
 
         Args:
             frames_u8 (torch.Tensor): (T, Hs, Ws, 3) uint8 RGB frames of the video (CUDA or host)
             tracknet, inpaintnet: models from utils.general.get_model, already .cuda().eval()
+            seq_len, bg_mode: the TrackNet checkpoint's param_dict values (predict.py:100-101)
+            inpaintnet_seq_len: the InpaintNet checkpoint's param_dict['seq_len'] (predict.py:106)
+            img_scaler: (w_scaler, h_scaler); default (Ws / WIDTH, Hs / HEIGHT) as predict.py:114
         Returns:
-            (tracknet_pred_dict, inpaint_pred_dict or None)
+            (tracknet_pred_dict incl. 'Inpaint_Mask' when inpaintnet is given, inpaint_pred_dict or None)
     """
     import tracknetv3_b200 as T
+    from utils.general import COOR_TH
+    if eval_mode not in ('nonoverlap', 'average', 'weight'):
+        raise ValueError(f'invalid eval_mode {eval_mode!r}')
     frames_u8 = torch.as_tensor(frames_u8).cuda()
     t, hs, ws = frames_u8.shape[0], frames_u8.shape[1], frames_u8.shape[2]
+    if img_scaler is None:
+        img_scaler = (ws / WIDTH, hs / HEIGHT)
     fp = T.FramePreprocessor(hs, ws, HEIGHT, WIDTH)
     median = None
-    if bg_mode:
-        med_src = torch.median(frames_u8.float(), dim=0).values.cpu().numpy()   # the reference: np.median(frame_arr, 0)
-        median = fp.prepare_median(med_src) if bg_mode == 'concat' else med_src
-    num_sample = t - seq_len + 1
-    ens = TemporalEnsemble(seq_len, eval_mode, num_sample)
+    if bg_mode == 'concat':
+        median = fp.prepare_median(fp.median(frames_u8))
+    elif bg_mode:
+        median = fp.median(frames_u8, as_float=True)
+    ensemble = eval_mode != 'nonoverlap'
+    win = _windows(t, seq_len, 1 if ensemble else seq_len, padding=True)
     pred = {'Frame': [], 'X': [], 'Y': [], 'Visibility': []}
+    ens = TemporalEnsemble(seq_len, eval_mode, len(win)) if ensemble and len(win) else None
+    dev_win = win.cuda()
     with torch.no_grad():
-        for s0 in range(0, num_sample, batch_size):
-            ids = list(range(s0, min(s0 + batch_size, num_sample)))
-            imgs = torch.stack([frames_u8[s:s + seq_len] for s in ids])           # sliding_step 1, (B, L, Hs, Ws, 3)
-            idx = torch.tensor([[[0, s + f] for f in range(seq_len)] for s in ids])
+        for s0 in range(0, len(win), batch_size):
+            w_b = win[s0:s0 + batch_size]
+            imgs = frames_u8[dev_win[s0:s0 + batch_size]]                      # (B, L, Hs, Ws, 3) gathered on the device
             y = tracknet(fp.process(imgs, median, bg_mode=bg_mode))
-            d = predict_ensemble(ens, idx, y_pred=y, img_scaler=img_scaler)
-            for k in pred:
-                pred[k].extend(d[k])
+            if ensemble:
+                _extend(pred, predict_ensemble(ens, _as_indices(w_b), y_pred=y, img_scaler=img_scaler))
+            else:
+                _extend(pred, predict(_as_indices(w_b), y_pred=y, img_scaler=img_scaler))
     if inpaintnet is None:
         return pred, None
-    # InpaintNet pass over the decoded trajectory (predict.py:214-301): gaps selected by generate_inpaint_mask with the
-    # reference's threshold of 5 % of the image height (:216)
+
+    # InpaintNet pass over the decoded trajectory (predict.py:211-301): gaps selected by generate_inpaint_mask with the
+    # reference's threshold of 5 % of the image height (:216); coordinates normalised by the image shape
+    # (dataset.py:469-470)
     from test import generate_inpaint_mask
-    w_, h_ = WIDTH * img_scaler[0], HEIGHT * img_scaler[1]
-    coor = torch.tensor([[x / w_, y_ / h_] for x, y_ in zip(pred['X'], pred['Y'])], dtype=torch.float32).cuda()
-    mask = torch.tensor(generate_inpaint_mask(pred, th_h=h_ * 0.05), dtype=torch.float32).reshape(-1, 1).cuda()
-    li = 16 if t >= 16 else t
-    n_in = t - li + 1
-    ens_c = TemporalEnsemble(li, eval_mode, n_in)
+    L = inpaintnet_seq_len
+    pred['Inpaint_Mask'] = generate_inpaint_mask(pred, th_h=hs * 0.05)
+    n_pred = len(pred['Frame'])
+    # float64 quotient, then .float(): the dataset's coordinate array is float64 (np.concatenate of a float32 array with
+    # python ints promotes, dataset.py:391) and predict.py:253 casts the batch to fp32
+    coor = torch.stack([torch.tensor(pred['X'], dtype=torch.float64) / ws,
+                        torch.tensor(pred['Y'], dtype=torch.float64) / hs], dim=1).reshape(-1, 2).float().cuda()
+    mask = torch.tensor(pred['Inpaint_Mask'], dtype=torch.float32).reshape(-1, 1).cuda()
+    win = _windows(n_pred, L, 1 if ensemble else L, padding=True)
     out = {'Frame': [], 'X': [], 'Y': [], 'Visibility': []}
-    from utils.general import COOR_TH
-    with torch.no_grad():
-        for s0 in range(0, n_in, batch_size):
-            ids = list(range(s0, min(s0 + batch_size, n_in)))
-            c = torch.stack([coor[s:s + li] for s in ids])
-            m = torch.stack([mask[s:s + li] for s in ids])
-            idx = torch.tensor([[[0, s + f] for f in range(li)] for s in ids])
-            ci = inpaintnet(c, m)
-            ci = ci * m + c * (1 - m)
-            ci = ci.masked_fill(((ci[:, :, 0] < COOR_TH) & (ci[:, :, 1] < COOR_TH))[:, :, None], 0.)
-            d = predict_ensemble(ens_c, idx, c_pred=ci, img_scaler=img_scaler)
-            for k in out:
-                out[k].extend(d[k])
+    ens_c = TemporalEnsemble(L, eval_mode, len(win)) if ensemble and len(win) else None
+    dev_win = win.cuda()
+    for s0 in range(0, len(win), batch_size):
+        w_b = win[s0:s0 + batch_size]
+        gather = dev_win[s0:s0 + batch_size]
+        ci = inpaintnet.rectify(coor[gather], mask[gather], COOR_TH)           # forward + blend + threshold, one launch
+        if ensemble:
+            _extend(out, predict_ensemble(ens_c, _as_indices(w_b), c_pred=ci, img_scaler=img_scaler))
+        else:
+            _extend(out, predict(_as_indices(w_b), c_pred=ci, img_scaler=img_scaler))
     return pred, out
 
 
@@ -181,18 +232,20 @@ def write_pred_csv(pred_dict, save_file):
 
 def load_models(tracknet_file, inpaintnet_file=''):
     """ Models from checkpoints in the reference's layout (predict.py:99-108): ckpt['model'] and
-        ckpt['param_dict']['seq_len' / 'bg_mode']. Returns (tracknet, inpaintnet or None, seq_len, bg_mode). """
+        ckpt['param_dict']['seq_len' / 'bg_mode']. Returns (tracknet, inpaintnet or None, seq_len, bg_mode,
+        inpaintnet_seq_len or None). """
     from utils.general import get_model
     ckpt = torch.load(tracknet_file, map_location='cpu', weights_only=False)
     seq_len, bg_mode = ckpt['param_dict']['seq_len'], ckpt['param_dict']['bg_mode']
     tracknet = get_model('TrackNet', seq_len, bg_mode)
     tracknet.load_state_dict(ckpt['model'])
-    inpaintnet = None
+    inpaintnet, inpaintnet_seq_len = None, None
     if inpaintnet_file:
         ickpt = torch.load(inpaintnet_file, map_location='cpu', weights_only=False)
+        inpaintnet_seq_len = ickpt['param_dict']['seq_len']
         inpaintnet = get_model('InpaintNet')
         inpaintnet.load_state_dict(ickpt['model'])
-    return tracknet, inpaintnet, seq_len, bg_mode
+    return tracknet, inpaintnet, seq_len, bg_mode, inpaintnet_seq_len
 
 
 if __name__ == '__main__':
@@ -206,19 +259,19 @@ if __name__ == '__main__':
     parser.add_argument('--tracknet_file', type=str, default='', help='file path of the TrackNet model checkpoint')
     parser.add_argument('--inpaintnet_file', type=str, default='', help='file path of the InpaintNet model checkpoint')
     parser.add_argument('--batch_size', type=int, default=16, help='batch size for inference')
-    parser.add_argument('--eval_mode', type=str, default='weight', choices=['average', 'weight'], help='evaluation mode')
+    parser.add_argument('--eval_mode', type=str, default='weight', choices=['nonoverlap', 'average', 'weight'], help='evaluation mode')
     parser.add_argument('--save_dir', type=str, default='pred_result', help='directory to save the prediction result')
     parser.add_argument('--frames', type=int, default=40, help='length of the synthetic clip (no --video_file)')
     args = parser.parse_args()
     if args.video_file:
         assert args.tracknet_file, 'a TrackNet checkpoint is required with --video_file'
-        tracknet, inpaintnet, seq_len, bg_mode = load_models(args.tracknet_file, args.inpaintnet_file)
+        tracknet, inpaintnet, seq_len, bg_mode, inpaint_seq_len = load_models(args.tracknet_file, args.inpaintnet_file)
         frames = np.array(generate_frames(args.video_file))[:, :, :, ::-1]      # BGR -> RGB, as predict.py:128
         video = torch.from_numpy(np.ascontiguousarray(frames))
         name = os.path.basename(args.video_file)[:-4]
     else:
         torch.manual_seed(0)
-        seq_len, bg_mode, name = 8, 'concat', 'synthetic'
+        seq_len, bg_mode, name, inpaint_seq_len = 8, 'concat', 'synthetic', 16
         video = torch.randint(0, 40, (args.frames, 360, 640, 3), dtype=torch.uint8)
         for i in range(args.frames):                                   # a bright ball crossing a dark noisy court
             video[i, 100 + 3 * i:108 + 3 * i, 50 + 10 * i:58 + 10 * i] = 250
@@ -227,7 +280,8 @@ if __name__ == '__main__':
     inpaintnet = inpaintnet.cuda().eval() if inpaintnet is not None else None
     h, w = video.shape[1], video.shape[2]
     p1, p2 = run_video(video, tracknet, inpaintnet, seq_len=seq_len, bg_mode=bg_mode, batch_size=args.batch_size,
-                       eval_mode=args.eval_mode, img_scaler=(w / WIDTH, h / HEIGHT))
+                       eval_mode=args.eval_mode, img_scaler=(w / WIDTH, h / HEIGHT),
+                       inpaintnet_seq_len=inpaint_seq_len or 16)
     os.makedirs(args.save_dir, exist_ok=True)
     out_csv = os.path.join(args.save_dir, f'{name}_ball.csv')
     write_pred_csv(p2 if p2 is not None else p1, out_csv)

@@ -500,23 +500,18 @@ def test_frame_preprocessing_vs_reference_fixture_and_pillow_oracle(golden_dir):
         fp.process(torch.zeros(1, 1, 288, 400, 3, dtype=torch.uint8, device=G.DEV), bg_mode="subtract")
 
 
-def test_run_video_end_to_end_flow():
-    """predict.run_video: frames -> resize/stack -> TrackNet -> temporal ensemble -> decode -> InpaintNet -> ensemble.
-    Every frame of the video gets exactly one prediction from each stage (the stages themselves are pinned above)."""
+def test_run_video_all_bg_modes_cover_every_frame():
+    """predict.run_video with the two subtract modes (float64 median with x.5 values from the GPU median kernel): every
+    frame of the video gets exactly one prediction. (The composition itself is pinned bit for bit to the reference's
+    __main__ in tests/test_gpu_predict_flow.py.)"""
     import predict as P
     from utils.general import get_model
     torch.manual_seed(0)
     t = 12
     video = torch.randint(0, 40, (t, 90, 160, 3), dtype=torch.uint8)
-    tracknet = get_model('TrackNet', 8, 'concat').to(G.DEV).eval()
-    inpaintnet = get_model('InpaintNet').to(G.DEV).eval()
-    p1, p2 = P.run_video(video, tracknet, inpaintnet, batch_size=4, img_scaler=(160 / 512, 90 / 288))
-    assert p1['Frame'] == list(range(t)) and p2['Frame'] == list(range(t))
-    assert all(len(p1[k]) == t and len(p2[k]) == t for k in ('X', 'Y', 'Visibility'))
-    assert all(0 <= x <= 160 and 0 <= y <= 90 for x, y in zip(p1['X'], p1['Y']))
-    p3, none = P.run_video(video, get_model('TrackNet', 8, 'subtract_concat').to(G.DEV).eval(), None,
-                           bg_mode='subtract_concat', batch_size=3)
-    assert none is None and p3['Frame'] == list(range(t))
+    for bg_mode in ('subtract', 'subtract_concat'):
+        p3, none = P.run_video(video, get_model('TrackNet', 8, bg_mode).to(G.DEV).eval(), None, bg_mode=bg_mode, batch_size=3)
+        assert none is None and p3['Frame'] == list(range(t))
 
 
 def test_eval_loops_vs_oracle():

@@ -259,8 +259,10 @@ def test_predict_load_models_reads_the_reference_checkpoint_layout(tmp_path):
     pd_i = {"model_name": "InpaintNet", "seq_len": 16, "bg_mode": ""}
     torch.save(TR.checkpoint_dict(0, 0.1, tn, torch.optim.SGD(tn.parameters(), lr=0.1), None, pd_t), tmp_path / "t.pt")
     torch.save(TR.checkpoint_dict(0, 0.1, ip, torch.optim.SGD(ip.parameters(), lr=0.1), None, pd_i), tmp_path / "i.pt")
-    t2, i2, seq_len, bg_mode = P.load_models(str(tmp_path / "t.pt"), str(tmp_path / "i.pt"))
-    assert (seq_len, bg_mode, t2.in_dim, t2.out_dim) == (4, "subtract", 4, 4)
+    pd_i["seq_len"] = 12
+    torch.save(TR.checkpoint_dict(0, 0.1, ip, torch.optim.SGD(ip.parameters(), lr=0.1), None, pd_i), tmp_path / "i.pt")
+    t2, i2, seq_len, bg_mode, inpaint_seq_len = P.load_models(str(tmp_path / "t.pt"), str(tmp_path / "i.pt"))
+    assert (seq_len, bg_mode, t2.in_dim, t2.out_dim, inpaint_seq_len) == (4, "subtract", 4, 4, 12)
     assert all(torch.equal(a, b) for a, b in zip(tn.state_dict().values(), t2.state_dict().values()))
     assert all(torch.equal(a, b) for a, b in zip(ip.state_dict().values(), i2.state_dict().values()))
     assert P.load_models(str(tmp_path / "t.pt"))[1] is None
@@ -286,3 +288,18 @@ def test_bench_reference_arm_prints_the_contract_line():
     r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1"],
                         capture_output=True, text=True, cwd=ROOT, timeout=600, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r2.returncode == 0 and r2.stdout.strip() == ""
+
+
+def test_predict_windows_match_the_reference_dataset():
+    """predict._windows (the sampling of input sequences over a clip / a trajectory) against the index tables the
+    reference's Shuttlecock_Trajectory_Dataset built for the same arguments (tests/golden/predict_windows.npz,
+    oracle/gen_predict_flow.py): sliding step 1 and seq_len, with and without padding, clips shorter than a window."""
+    import predict as P
+    g = np.load(os.path.join(ROOT, "tests", "golden", "predict_windows.npz"))
+    assert len(g.files) == 48
+    for key in g.files:
+        n, L, step, pad = (int(v) for v in key.split("_"))
+        win = P._windows(n, L, step, bool(pad))
+        want = g[key]
+        assert tuple(win.shape) == want.shape[:2], key
+        assert np.array_equal(P._as_indices(win).numpy(), want), key

@@ -78,6 +78,9 @@ SIGNATURES = {
     "tnb_heatmap_decode_workspace_bytes": (sz, [i32, i32, i32]),
     "tnb_heatmap_decode": (i32, [vp, i32, f32, i32, i32, i32, vp, vp, vp]),
     "tnb_inpaintnet_fwd": (i32, [vp, vp, C.POINTER(vp), i32, i32, vp, vp]),
+    "tnb_inpaintnet_rectify": (i32, [vp, vp, C.POINTER(vp), i32, i32, f32, vp, vp]),
+    "tnb_median_u8": (i32, [vp, i32, i64, vp, vp, vp]),
+    "tnb_label_discs": (i32, [vp, i32, i32, i32, f32, vp, vp]),
     "tnb_inpaintnet_bwd": (i32, [vp, vp, C.POINTER(vp), vp, C.POINTER(vp), i32, i32, vp, vp]),
     "tnb_resize_frames": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, i32, i32, i32, vp, vp, i32, C.c_longlong, i32, i32, vp]),
     "tnb_bg_subtract_u8": (i32, [vp, vp, C.c_longlong, i32, i32, vp, vp]),

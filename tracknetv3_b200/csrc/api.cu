@@ -129,7 +129,21 @@ int tnb_inpaintnet_fwd(const float* coords, const float* mask, const void* const
                        void* stream) {
   InpaintParams p;
   for (int i = 0; i < 9; ++i) { p.w[i] = (const float*)params[2 * i]; p.b[i] = (const float*)params[2 * i + 1]; }
-  return launch_inpaint_fwd(coords, mask, p, n, l, out, ST(stream));
+  return launch_inpaint_fwd(coords, mask, p, n, l, out, -1.f, ST(stream));
+}
+int tnb_inpaintnet_rectify(const float* coords, const float* mask, const void* const* params, int n, int l, float coor_th,
+                           float* out, void* stream) {
+  TNB_REQUIRE(coor_th >= 0.f, "inpaintnet_rectify: negative threshold %f", coor_th);
+  InpaintParams p;
+  for (int i = 0; i < 9; ++i) { p.w[i] = (const float*)params[2 * i]; p.b[i] = (const float*)params[2 * i + 1]; }
+  return launch_inpaint_fwd(coords, mask, p, n, l, out, coor_th, ST(stream));
+}
+int tnb_median_u8(const uint8_t* frames, int nframes, long long frame_bytes, double* out_f64, uint8_t* out_u8,
+                  void* stream) {
+  return launch_median_u8(frames, nframes, frame_bytes, out_f64, out_u8, ST(stream));
+}
+int tnb_label_discs(const int* centers_xy, int nmaps, int h, int w, float sigma, float* out, void* stream) {
+  return launch_label_discs(centers_xy, nmaps, h, w, sigma, out, ST(stream));
 }
 int tnb_inpaintnet_bwd(const float* coords, const float* mask, const void* const* params, const float* dout,
                        void* const* grads, int n, int l, float* dcoords, void* stream) {

@@ -949,7 +949,7 @@ TNB_DEVINL void conv1d_k3(float* out, int Cout, const float* inA, int CA, const 
 }
 __global__ void __launch_bounds__(1024) inpaint_fwd_kernel(const float* __restrict__ coords,
                                                           const float* __restrict__ mask, InpaintParams P, int L,
-                                                          float* __restrict__ out) {
+                                                          float* __restrict__ out, float coor_th) {
   extern __shared__ float sm[];
   float* in0 = sm;            // [3][L]   cat(x, m) permuted (model.py:114-115)
   float* x1 = in0 + 3 * L;    // [32][L]
@@ -977,18 +977,31 @@ __global__ void __launch_bounds__(1024) inpaint_fwd_kernel(const float* __restri
   conv1d_k3(u2, 64, u1, 128, x2, 64, P.w[6], P.b[6], L, 1);    // cat([x, x2]) model.py:122
   conv1d_k3(u3, 32, u2, 64, x1, 32, P.w[7], P.b[7], L, 1);     // cat([x, x1]) model.py:124
   conv1d_k3(o, 2, u3, 32, nullptr, 0, P.w[8], P.b[8], L, 2);
-  for (int i = threadIdx.x; i < L * 2; i += blockDim.x) {
-    const int l = i >> 1, c = i & 1;
-    out[((size_t)n * L + l) * 2 + c] = o[c * L + l];
+  if (coor_th < 0.f) {
+    for (int i = threadIdx.x; i < L * 2; i += blockDim.x) {
+      const int l = i >> 1, c = i & 1;
+      out[((size_t)n * L + l) * 2 + c] = o[c * L + l];
+    }
+    return;
+  }
+  // Rectification epilogue (predict.py:256-261 = test.py:401,406-408), one thread per point:
+  // coor_inpaint * mask + coor_pred * (1 - mask) with torch's operation order (every product and the sum rounded to fp32,
+  // no fused multiply-add), then both coordinates -> 0 where both are below COOR_TH.
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    const float m = in0[2 * L + l], om = __fsub_rn(1.f, m);
+    const float x = __fadd_rn(__fmul_rn(o[l], m), __fmul_rn(in0[l], om));
+    const float y = __fadd_rn(__fmul_rn(o[L + l], m), __fmul_rn(in0[L + l], om));
+    const bool zero = x < coor_th && y < coor_th;
+    *reinterpret_cast<float2*>(out + ((size_t)n * L + l) * 2) = zero ? make_float2(0.f, 0.f) : make_float2(x, y);
   }
 }
 int launch_inpaint_fwd(const float* coords, const float* mask, const InpaintParams& p, int N, int L, float* out,
-                       cudaStream_t st) {
+                       float coor_th, cudaStream_t st) {
   const size_t smem = (size_t)(3 + 32 + 64 + 128 + 256 + 256 + 128 + 64 + 32 + 2) * L * sizeof(float);
   TNB_REQUIRE(smem <= 227 * 1024, "inpaint_fwd: sequence length %d too long for the fused kernel", L);
   TNB_CHECK_CUDA(cudaFuncSetAttribute(inpaint_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // latency-bound: one CTA per trajectory, as many warps as the SM takes to hide the L2 latency of the weight reads
-  inpaint_fwd_kernel<<<N, 1024, smem, st>>>(coords, mask, p, L, out);
+  inpaint_fwd_kernel<<<N, 1024, smem, st>>>(coords, mask, p, L, out, coor_th);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

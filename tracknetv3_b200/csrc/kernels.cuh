@@ -42,8 +42,12 @@ int launch_decode(const void* maps, int is_u8, float thresh, int nmaps, int H, i
                   cudaStream_t st);
 
 struct InpaintParams { const float* w[9]; const float* b[9]; };
+// coor_th < 0: out = InpaintNet(coords, mask); coor_th >= 0: the rectified trajectory of predict.py:256-261 (blend with the
+// input where mask == 0, zero the points below the threshold)
 int launch_inpaint_fwd(const float* coords, const float* mask, const InpaintParams& p, int N, int L, float* out,
-                       cudaStream_t st);
+                       float coor_th, cudaStream_t st);
+int launch_median_u8(const uint8_t* frames, int T, long long P, double* out_f64, uint8_t* out_u8, cudaStream_t st);
+int launch_label_discs(const int* centers, int nmaps, int H, int W, float sigma, float* out, cudaStream_t st);
 int launch_resize_frames(const uint8_t* src, int nimg, int hs, int ws, int C, const int* hbounds, const int* hkk, int hksize,
                          const int* vbounds, const int* vkk, int vksize, int hd, int wd, uint8_t* tmp, float* out,
                          int per_sample, long long sample_stride, int chan_off, int frame_stride, cudaStream_t st);

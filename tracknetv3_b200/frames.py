@@ -87,9 +87,25 @@ class FramePreprocessor:
             self.h, self.w, tmp.data_ptr(), out.data_ptr(), per_sample, out.stride(0), chan_off,
             c if frame_stride is None else frame_stride, _lib.stream_ptr()))
 
+    def median(self, frames_u8, as_float=False):
+        """`np.median(frame_arr, 0)` of a whole clip (dataset.py:102-103) on the GPU: ``frames_u8`` uint8 CUDA
+        ``(T, Hs, Ws, 3)``. Returns the uint8 image ``median.astype('uint8')`` that bg_mode 'concat' resizes (:105; pass it
+        to ``prepare_median``), or with ``as_float`` numpy's float64 median, x.5 values included, that the subtract modes
+        keep (:108-109; pass it to ``process`` as it is)."""
+        lib = _lib.load()
+        _lib.require_cuda(frames_u8)
+        if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or tuple(frames_u8.shape[1:3]) != (self.src_h, self.src_w):
+            raise RuntimeError(f"median expects uint8 (T, {self.src_h}, {self.src_w}, C), got {tuple(frames_u8.shape)}")
+        frames_u8 = frames_u8.contiguous()
+        t, per = frames_u8.shape[0], frames_u8[0].numel()
+        out = torch.empty(frames_u8.shape[1:], dtype=torch.float64 if as_float else torch.uint8, device=frames_u8.device)
+        _lib.check(lib.tnb_median_u8(frames_u8.data_ptr(), t, per, out.data_ptr() if as_float else None,
+                                     None if as_float else out.data_ptr(), _lib.stream_ptr()))
+        return out
+
     def prepare_median(self, median_hwc):
         """dataset.py:104-107 / :776-779: the median frame (any float or uint8 (Hs, Ws, 3)) as uint8, resized, CHW."""
-        m = torch.as_tensor(np.asarray(median_hwc)).to(self.device)
+        m = median_hwc.to(self.device) if torch.is_tensor(median_hwc) else torch.as_tensor(np.asarray(median_hwc)).to(self.device)
         m = m.to(torch.uint8) if m.dtype != torch.uint8 else m   # .astype('uint8') of values in [0, 255]: truncation
         out = torch.empty((1, 3, self.h, self.w), dtype=torch.float32, device=self.device)
         self._run(m.unsqueeze(0), out, 1, 0)
@@ -98,7 +114,10 @@ class FramePreprocessor:
     def _difference(self, flat, median_src):
         """np.sum(np.absolute(img - median), 2).astype('uint8') for every frame (dataset.py:438, 442): (n, Hs, Ws, 1)."""
         lib = _lib.load()
-        med = torch.as_tensor(np.asarray(median_src, dtype=np.float64)).to(self.device).contiguous()
+        if torch.is_tensor(median_src):
+            med = median_src.to(self.device, torch.float64).contiguous()
+        else:
+            med = torch.as_tensor(np.asarray(median_src, dtype=np.float64)).to(self.device).contiguous()
         if tuple(med.shape) != (self.src_h, self.src_w, 3):
             raise RuntimeError(f"median must be ({self.src_h}, {self.src_w}, 3) at the source resolution, got {tuple(med.shape)}")
         diff = torch.empty((flat.shape[0], self.src_h, self.src_w, 1), dtype=torch.uint8, device=self.device)

@@ -7,6 +7,7 @@ checkpoints (104 entries for TrackNet, 20 for InpaintNet). ``for
 them: the whole network runs through ``tnb_tracknet_forward`` / ``tnb_tracknet_backward`` (C ABI).
 """
 import ctypes as C
+import weakref
 
 import torch
 import torch.nn as nn
@@ -53,7 +54,7 @@ class _TrackNetFunction(torch.autograd.Function):
     """autograd bridge: forward = tnb_tracknet_forward, backward = tnb_tracknet_backward."""
 
     @staticmethod
-    def forward(ctx, x, module, *params):
+    def forward(ctx, x, module, saves_state, *params):
         lib = _lib.load()
         n, _, h, w = x.shape
         cfg = _cfg(n, h, w, module.in_dim, module.out_dim, module.training, module.precision, module._variant)
@@ -61,7 +62,7 @@ class _TrackNetFunction(torch.autograd.Function):
         if nbytes == 0:
             # mirror the reference's failure for sizes its pooling / concat cannot handle (model.py:59-69)
             raise RuntimeError(lib.tnb_last_error().decode())
-        ws = module._workspace(nbytes, x.device)
+        ws, ctx.token = module._workspace(nbytes, x.device, saves_state)
         y = torch.empty((n, module.out_dim, h, w), dtype=torch.float32, device=x.device)
         tensors = module._state_tensors()
         _lib.check(lib.tnb_tracknet_forward(C.byref(cfg), x.data_ptr(), _lib.ptr_array(tensors), y.data_ptr(),
@@ -78,6 +79,13 @@ class _TrackNetFunction(torch.autograd.Function):
         module = ctx.module
         if not ctx.cfg.training:
             raise RuntimeError("tracknet_b200: backward through an eval()-mode TrackNet is not implemented")
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("tracknet_b200: the gradient w.r.t. the input frames is not computed (the reference's "
+                               "train step never asks for it, train.py:86-95); pass x without requires_grad")
+        if ctx.token is None or ctx.token.done:
+            # the workspace holds this forward's activations and BatchNorm statistics; the backward kernels consume them
+            raise RuntimeError("tracknet_b200: backward called twice on the same forward (retain_graph is not supported)")
+        ctx.token.done = True
         params = list(module.parameters())
         # one block for all 53 gradients: a single allocation whose address repeats from step to step, which is what
         # lets the library replay its captured launch sequence (the pointers are part of the CUDA-graph key)
@@ -90,7 +98,15 @@ class _TrackNetFunction(torch.autograd.Function):
         _lib.check(lib.tnb_tracknet_backward(C.byref(ctx.cfg), dy.data_ptr(), y.data_ptr(),
                                              _lib.ptr_array(module._state_tensors()), _lib.ptr_array(grads),
                                              ctx.ws.data_ptr(), ctx.nbytes, _lib.stream_ptr()))
-        return (None, None) + tuple(grads)
+        return (None, None, None) + tuple(grads)
+
+
+class _WorkspaceToken:
+    """Alive and not ``done`` while a forward's saved-for-backward state sits in the workspace it was handed."""
+    __slots__ = ("done", "__weakref__")
+
+    def __init__(self):
+        self.done = False
 
 
 class TrackNet(nn.Module):
@@ -117,7 +133,9 @@ class TrackNet(nn.Module):
             raise ValueError("precision must be 'fp32x3' or 'tf32like'")
         self.precision = precision
         self._variant = 0
-        self._ws = None
+        self._ws_scratch = None   # forwards that keep nothing for a backward (eval(), no_grad)
+        self._ws_saved = None     # the newest training forward's activations until its backward has run
+        self._ws_saved_token = None
 
     def _blocks(self):
         for blk in (self.down_block_1, self.down_block_2, self.down_block_3, self.bottleneck, self.up_block_1,
@@ -135,23 +153,41 @@ class TrackNet(nn.Module):
         out += [self.predictor.weight, self.predictor.bias]
         return out
 
-    def _workspace(self, nbytes, device):
-        # In training the workspace holds the saved-for-backward tensors of THIS forward, so every
-        # forward gets its own buffer; in inference one buffer is reused.
-        if self.training and torch.is_grad_enabled():
-            return torch.empty(nbytes, dtype=torch.uint8, device=device)
-        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != device:
-            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        return self._ws
+    def _workspace(self, nbytes, device, saves_state):
+        """(buffer, token). A forward whose backward may follow (``saves_state``) leaves its activations, BatchNorm
+        statistics and packed weights in the workspace, so that buffer must not be handed out again before the backward
+        has consumed it. The common train loop (forward, backward, forward, ...) reuses ONE cached buffer - a stable
+        address is also what lets the library replay its CUDA graphs; a second forward before the first one's backward
+        (gradient accumulation over micro-batches, an evaluation in between) gets a private buffer instead."""
+        fits = lambda t: t is not None and t.numel() >= nbytes and t.device == device
+        if not saves_state:
+            if not fits(self._ws_scratch):
+                self._ws_scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            return self._ws_scratch, None
+        token = _WorkspaceToken()
+        held = self._ws_saved_token() if self._ws_saved_token is not None else None
+        if held is not None and not held.done:
+            return torch.empty(nbytes, dtype=torch.uint8, device=device), token
+        if not fits(self._ws_saved):
+            self._ws_saved = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self._ws_saved_token = weakref.ref(token)
+        return self._ws_saved, token
 
     def forward(self, x):
         _lib.require_cuda(x)
         if x.dim() != 4 or x.shape[1] != self.in_dim:
             raise RuntimeError(f"TrackNet expects input (N, {self.in_dim}, H, W), got {tuple(x.shape)}")
+        dev = x.device
         for t in self._state_tensors():
             _lib.require_cuda(t)
+            if t.device != dev or not t.is_contiguous() or t.dtype != (torch.int64 if t.dim() == 0 else torch.float32):
+                raise RuntimeError("tracknet_b200: parameters and buffers must be contiguous fp32 tensors on the input's "
+                                   f"device (found {t.dtype} on {t.device}, input on {dev}); .half() / .double() models "
+                                   "are not supported")
         x = x.contiguous().float()
-        return _TrackNetFunction.apply(x, self, *self.parameters())
+        # decided HERE: inside autograd.Function.forward grad mode is always off
+        saves_state = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        return _TrackNetFunction.apply(x, self, saves_state, *self.parameters())
 
 
 class Conv1DBlock(nn.Module):
@@ -227,13 +263,26 @@ class InpaintNet(nn.Module):
             out += [c.weight, c.bias]
         return out
 
-    def forward(self, x, m):
+    def _check(self, x, m):
         _lib.require_cuda(x, m)
         if x.dim() != 3 or x.shape[2] != 2 or m.dim() != 3 or m.shape[2] != 1 or m.shape[:2] != x.shape[:2]:
             raise RuntimeError(f"InpaintNet expects x (N, L, 2) and m (N, L, 1), got {tuple(x.shape)} {tuple(m.shape)}")
-        x = x.contiguous().float()
-        m = m.contiguous().float()
         tensors = self._param_tensors()
         for t in tensors:
             _lib.require_cuda(t)
+        return x.contiguous().float(), m.contiguous().float(), tensors
+
+    def forward(self, x, m):
+        x, m, tensors = self._check(x, m)
         return _InpaintNetFunction.apply(x, m, self, *tensors)
+
+    @torch.no_grad()
+    def rectify(self, coor_pred, inpaint_mask, coor_th):
+        """The inference step of reference predict.py:256-261 / test.py:400-408 in ONE launch:
+        ``c = self(coor_pred, mask); c = c * mask + coor_pred * (1 - mask); c[(c[..., 0] < th) & (c[..., 1] < th)] = 0``."""
+        x, m, tensors = self._check(coor_pred, inpaint_mask)
+        lib = _lib.load()
+        out = torch.empty_like(x)
+        _lib.check(lib.tnb_inpaintnet_rectify(x.data_ptr(), m.data_ptr(), _lib.ptr_array(tensors), x.shape[0], x.shape[1],
+                                              float(coor_th), out.data_ptr(), _lib.stream_ptr()))
+        return out
