@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TNB_ABI_VERSION 1
+#define TNB_ABI_VERSION 2
 
 /* ---- descriptors -------------------------------------------------------------------------- */
 
@@ -111,7 +111,7 @@ int tnb_view_presplit(const tnb_view_t* view, void* out, int fmt, void* stream);
  * tnb_conv3x3_fwd launch streams with bulk TMA, one image per (output-channel tile, 32-channel chunk, filter tap), and
  * its inner layout follows the tile width the launcher will pick for this N side ([hi | lo][plane][rows], or
  * [plane][hi | lo][rows] for the 64-wide tiles whose two weight terms feed one MMA). Pack and convolve in the same
- * process (the layout also follows the TNB_CONV_MERGE / TNB_CONV_PAIR experiment switches). */
+ * process (the layout also follows the TNB_CONV_MERGE ablation switch). */
 size_t tnb_conv3x3_wpack_elems(int k_side, int n_side); /* number of uint16 elements */
 int tnb_conv3x3_pack_weights(const float* w_oihw, uint16_t* out, int cout, int cin, int mode, int fmt, void* stream);
 
@@ -122,8 +122,8 @@ int tnb_conv3x3_pack_weights(const float* w_oihw, uint16_t* out, int cout, int c
 int tnb_conv3x3_stat_rows(int n, int h, int w, int cin, int cout, int terms);
 /* The launch plan tnb_conv3x3_fwd will use for this shape (pure host arithmetic, no device needed): out[0..11] = output-
  * channel tile BN, M tiles per CTA tile MT, halo-tile stages, weight-ring slots, taps per weight stage, TMEM accumulator
- * buffers, TMEM columns, dynamic shared memory in bytes, merged-weights flag, tile orientation, CTA-pair flag,
- * weight-pack layout (0 [term][plane][rows], 1 [plane][term][rows], 2 per-rank halves). Returns 0 or an error code. */
+ * buffers, TMEM columns, dynamic shared memory in bytes, merged-weights flag, tile orientation, 0 (reserved),
+ * weight-pack layout (0 [term][plane][rows], 1 [plane][term][rows]). Returns 0 or an error code. */
 int tnb_conv3x3_plan_query(int n, int h, int w, int cin, int cout, int terms, int* out12);
 int tnb_conv3x3_fwd(const tnb_view_t* view, const uint16_t* wpack, float* out, float* stat_part, int cout,
                     int terms, int fmt, int variant, void* stream);
@@ -145,9 +145,12 @@ int tnb_conv3x3_dgrad_bnreduce(const tnb_view_t* view, const uint16_t* wpack, fl
  * cout == 64, the single-CTA kernel otherwise; variant bit 32 forces the generic kernels, bit 64 the single-CTA one. */
 int tnb_conv3x3_wgrad(const tnb_view_t* view, const void* dz_presplit, float* dw_oihw, int cout, int cin_real,
                       int terms, int variant, void* stream);
-/* The same with a scratch buffer of 9 * cout * view->C floats: the split-K partials are reduced tap-major (coalesced
- * 128-byte reductions instead of 32 scattered ones per warp instruction) and a second small kernel writes dw_oihw with
- * plain stores (dw need not be zeroed; the scratch is zeroed by the call). What tnb_tracknet_backward uses. */
+/* The same, DETERMINISTIC, with a scratch buffer of tnb_conv3x3_wgrad_ws_elems(view, cout) floats: every split-K CTA
+ * stores its partial tap-major into its own slab (plain coalesced stores, no atomics) and a second small kernel sums the
+ * slabs in split order into dw_oihw (dw need not be zeroed). Gradients are bit-identical from run to run, which is what
+ * the reference asks of cuDNN with `torch.backends.cudnn.deterministic = True` (train.py:205). What
+ * tnb_tracknet_backward uses. */
+size_t tnb_conv3x3_wgrad_ws_elems(const tnb_view_t* view, int cout);
 int tnb_conv3x3_wgrad_ws(const tnb_view_t* view, const void* dz_presplit, float* dw_oihw, int cout, int cin_real,
                          int terms, int variant, float* scratch, void* stream);
 
@@ -163,12 +166,16 @@ int tnb_bn_relu_bwd_reduce(const tnb_bnbwd_t* args, void* stream);
 int tnb_bn_relu_bwd_finalize(const float* part, int rows, int c, float* sums, float* dgamma, float* dbeta, void* stream);
 int tnb_bn_relu_bwd_apply(const tnb_bnbwd_t* args, void* stream);
 
-/* predictor: 1x1 conv + bias + sigmoid (model.py:54-55,71-72). y / dy are NCHW [n,out_dim,h,w]. */
+/* predictor: 1x1 conv + bias + sigmoid (model.py:54-55,71-72). y / dy are NCHW [n,out_dim,h,w]; any out_dim >= 1 (the
+ * reference takes any seq_len, utils/general.py:66-74). The backward needs a workspace of
+ * tnb_conv1x1_bias_sigmoid_bwd_workspace_bytes() bytes: per-block partial sums of dweight / dbias, added in block order
+ * (deterministic; dweight and dbias are overwritten, not accumulated). */
 int tnb_conv1x1_bias_sigmoid_fwd(const tnb_src_t* src, int n, int h, int w, const float* weight, const float* bias,
                                  int out_dim, float* y_nchw, void* stream);
+size_t tnb_conv1x1_bias_sigmoid_bwd_workspace_bytes(int n, int h, int w, int out_dim);
 int tnb_conv1x1_bias_sigmoid_bwd(const tnb_src_t* src, int n, int h, int w, const float* weight, int out_dim,
                                  const float* dy_nchw, const float* y_nchw, float* d_act_nhwc, float* dweight,
-                                 float* dbias, void* stream);
+                                 float* dbias, void* workspace, void* stream);
 
 /* WBCELoss(y_pred, y, reduce) (utils/metric.py:3-20). out: 1 float (reduce) or nsamples floats.
  * part: workspace of tnb_wbce_workspace_bytes(nsamples) bytes. gout: upstream gradient (1 or nsamples). */

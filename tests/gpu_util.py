@@ -84,13 +84,13 @@ def unsplit(buf, shape_nhwc):
 
 
 def wgrad3x3(view, dz_nhwc, cout, cin_real, terms=3, variant=0, scratch=False):
-    """production configuration: dz pre-split to bf16, view split on the fly. scratch=True: the tap-major accumulation
-    buffer + scatter path that tnb_tracknet_backward uses (dw starts as NaN: every element must be written)."""
+    """production configuration: dz pre-split to bf16, view split on the fly. scratch=True: the deterministic split-K
+    slab + ordered-sum path that tnb_tracknet_backward uses (slabs and dw start as NaN: every element must be written)."""
     L = lib()
     dzs = presplit(dz_nhwc)
     if scratch:
         dw = torch.full((cout, cin_real, 3, 3), float("nan"), device=DEV)
-        ws = torch.full((9 * cout * view.C,), float("nan"), device=DEV)
+        ws = torch.full((L.tnb_conv3x3_wgrad_ws_elems(C.byref(view), cout),), float("nan"), device=DEV)
         _lib.check(L.tnb_conv3x3_wgrad_ws(C.byref(view), dzs.data_ptr(), dw.data_ptr(), cout, cin_real, terms, variant,
                                           ws.data_ptr(), st()))
         torch.cuda.synchronize()
@@ -108,3 +108,11 @@ def rel_err(a, b):
 
 def max_abs(a, b):
     return (a.detach().double().cpu() - b.detach().double().cpu()).abs().max().item()
+
+
+def predictor_bwd(src, n, h, w, wd, o, dyd, yd, dA, dwp, dbp):
+    """tnb_conv1x1_bias_sigmoid_bwd with its workspace (NaN-filled: every partial the final sum reads must be written)."""
+    L = lib()
+    ws = torch.full((L.tnb_conv1x1_bias_sigmoid_bwd_workspace_bytes(n, h, w, o) // 4,), float("nan"), device=DEV)
+    _lib.check(L.tnb_conv1x1_bias_sigmoid_bwd(C.byref(src), n, h, w, wd.data_ptr(), o, dyd.data_ptr(), yd.data_ptr(),
+                                              dA.data_ptr(), dwp.data_ptr(), dbp.data_ptr(), ws.data_ptr(), st()))

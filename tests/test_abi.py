@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_channel():
     lib = _lib.load()
-    assert lib.tnb_abi_version() == 1
+    assert lib.tnb_abi_version() == 2
     cfg = _lib.TrackNetCfg(n=1, h=540, w=960, in_dim=27, out_dim=8, training=1, fwd_terms=3, bwd_terms=3,
                            variant=0, bn_eps=1e-5, bn_momentum=0.1)
     assert lib.tnb_tracknet_workspace_bytes(C.byref(cfg)) == 0  # 540 is not divisible by 8: the reference raises too
@@ -48,7 +48,15 @@ def test_workspace_and_plan_queries():
     # 128-wide tiles: 16x16 as well (2 buffers x 2 M tiles x 128 columns)
     assert lib.tnb_conv3x3_stat_rows(10, 288, 512, 64, 64, 3) == 10 * 18 * 32
     assert lib.tnb_conv3x3_stat_rows(10, 144, 256, 128, 128, 3) == 10 * 9 * 16
-    assert lib.tnb_tracknet_num_launches(C.byref(cfg), 0) == 53
+    # eval forward: pack_input, ONE weight-pack launch, (conv, bn_finalize) x 17, predictor
+    assert lib.tnb_tracknet_num_launches(C.byref(cfg), 0) == 37
+    cfg.training = 1
+    assert lib.tnb_tracknet_num_launches(C.byref(cfg), 0) == 38       # + the num_batches_tracked counters
+    # backward: predictor (dA, dW, final sum) 3, (reduce, finalize, apply, wgrad) x 17, view_presplit 7 + 3, dgrad 16,
+    # ordered split-K sums 17
+    assert lib.tnb_tracknet_num_launches(C.byref(cfg), 1) == 114
+    cfg.out_dim = 20                                                   # predictor kernels take 16 output channels per launch
+    assert lib.tnb_tracknet_num_launches(C.byref(cfg), 0) == 39
     assert lib.tnb_heatmap_decode_workspace_bytes(256, 288, 512) == 256 * 5 * 288 * 512 * 4
 
 
@@ -100,23 +108,3 @@ def test_conv_plans_fit_the_sm_for_every_layer_and_resolution():
         assert merged == (1 if bn == 64 else 0) and pair == 0 and layout == merged, key  # experiments are off by default
         assert tall in (0, 1)
     assert n == (len(_LAYER_SHAPES) * 2 - 1) * 2 * 4
-
-
-def test_conv_plans_under_the_pair_switch_subprocess():
-    """TNB_CONV_PAIR=1 (read once per process): every plan asks for the per-rank weight layout, never the merged one, and
-    still fits; a fused BatchNorm-backward reduction is refused together with it."""
-    import subprocess
-    import sys
-    code = (
-        "import ctypes as C, sys\n"
-        "sys.path.insert(0, %r)\n"
-        "from tracknetv3_b200 import _lib\n"
-        "from tests.test_abi import _plans\n"
-        "lib = _lib.load()\n"
-        "for key, p in _plans(lib, hw_list=((288, 512),), terms_list=(3,)):\n"
-        "    assert p[10] == 1 and p[11] == 2 and p[8] == 0 and 0 < p[7] <= 232448 and p[3] >= 2, (key, p)\n"
-        "assert lib.tnb_conv3x3_dgrad_bnreduce_rows(10, 288, 512, 64, 64, 3) < 0\n"
-        "print('ok')\n" % ROOT)
-    env = dict(os.environ, TNB_CONV_PAIR="1")
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT)
-    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr

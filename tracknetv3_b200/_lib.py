@@ -60,6 +60,7 @@ SIGNATURES = {
     "tnb_conv3x3_dgrad_bnreduce_rows": (i32, [i32, i32, i32, i32, i32, i32]),
     "tnb_conv3x3_dgrad_bnreduce": (i32, [C.POINTER(View), vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
     "tnb_conv3x3_wgrad": (i32, [C.POINTER(View), vp, vp, i32, i32, i32, i32, vp]),
+    "tnb_conv3x3_wgrad_ws_elems": (sz, [C.POINTER(View), i32]),
     "tnb_conv3x3_wgrad_ws": (i32, [C.POINTER(View), vp, vp, i32, i32, i32, i32, vp, vp]),
     "tnb_presplit_bf16": (i32, [vp, vp, i64, i32, vp]),
     "tnb_view_presplit": (i32, [C.POINTER(View), vp, i32, vp]),
@@ -69,7 +70,8 @@ SIGNATURES = {
     "tnb_bn_relu_bwd_finalize": (i32, [vp, i32, i32, vp, vp, vp, vp]),
     "tnb_bn_relu_bwd_apply": (i32, [C.POINTER(BnBwd), vp]),
     "tnb_conv1x1_bias_sigmoid_fwd": (i32, [C.POINTER(Src), i32, i32, i32, vp, vp, i32, vp, vp]),
-    "tnb_conv1x1_bias_sigmoid_bwd": (i32, [C.POINTER(Src), i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp]),
+    "tnb_conv1x1_bias_sigmoid_bwd_workspace_bytes": (sz, [i32, i32, i32, i32]),
+    "tnb_conv1x1_bias_sigmoid_bwd": (i32, [C.POINTER(Src), i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp]),
     "tnb_wbce_workspace_bytes": (sz, [i32]),
     "tnb_wbce_fwd": (i32, [vp, vp, i32, i64, i32, vp, vp, vp]),
     "tnb_wbce_bwd": (i32, [vp, vp, vp, i32, i64, i32, vp, vp]),
@@ -114,7 +116,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.tnb_abi_version() != 1:
+    if lib.tnb_abi_version() != 2:
         raise TnbError("libtracknet_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -49,7 +49,7 @@ int tnb_conv3x3_pack_weights(const float* w, uint16_t* out, int cout, int cin, i
 int tnb_conv3x3_plan_query(int n, int h, int w, int cin, int cout, int terms, int* out12) {
   ConvPlan p;
   if (int rc = conv3x3_plan(n, h, w, (cin + 31) / 32 * 32, cout, terms, &p)) return rc;
-  const int v[12] = {p.BN, p.MT, p.SA, p.SB, p.G, p.nbuf, p.tmem_cols, (int)p.smem_bytes, p.merged, p.tall, p.pair,
+  const int v[12] = {p.BN, p.MT, p.SA, p.SB, p.G, p.nbuf, p.tmem_cols, (int)p.smem_bytes, p.merged, p.tall, 0 /* (was: CTA-pair flag) */,
                      conv3x3_weight_layout(p.BN)};
   for (int i = 0; i < 12; ++i) out12[i] = v[i];
   return 0;
@@ -74,6 +74,7 @@ int tnb_conv3x3_wgrad(const tnb_view_t* view, const void* dz_presplit, float* dw
                       int variant, void* stream) {
   return launch_wgrad3x3(*view, dz_presplit, dw, cout, cin_real, terms, variant, ST(stream));
 }
+size_t tnb_conv3x3_wgrad_ws_elems(const tnb_view_t* view, int cout) { return wgrad3x3_ws_floats(*view, cout); }
 int tnb_conv3x3_wgrad_ws(const tnb_view_t* view, const void* dz_presplit, float* dw, int cout, int cin_real, int terms,
                          int variant, float* scratch, void* stream) {
   return launch_wgrad3x3(*view, dz_presplit, dw, cout, cin_real, terms, variant, ST(stream), scratch);
@@ -96,10 +97,13 @@ int tnb_conv1x1_bias_sigmoid_fwd(const tnb_src_t* src, int n, int h, int w, cons
                                  int out_dim, float* y, void* stream) {
   return launch_predictor_fwd(*src, n, h, w, weight, bias, out_dim, y, ST(stream));
 }
+size_t tnb_conv1x1_bias_sigmoid_bwd_workspace_bytes(int n, int h, int w, int out_dim) {
+  return predictor_bwd_workspace_bytes(n, h, w, out_dim);
+}
 int tnb_conv1x1_bias_sigmoid_bwd(const tnb_src_t* src, int n, int h, int w, const float* weight, int out_dim,
                                  const float* dy, const float* y, float* d_act, float* dweight, float* dbias,
-                                 void* stream) {
-  return launch_predictor_bwd(*src, n, h, w, weight, out_dim, dy, y, d_act, dweight, dbias, ST(stream));
+                                 void* workspace, void* stream) {
+  return launch_predictor_bwd(*src, n, h, w, weight, out_dim, dy, y, d_act, dweight, dbias, (float*)workspace, ST(stream));
 }
 
 size_t tnb_wbce_workspace_bytes(int nsamples) { return sizeof(double) * (size_t)nsamples * wbce_num_blocks(0); }

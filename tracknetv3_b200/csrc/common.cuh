@@ -37,6 +37,35 @@ void set_last_error(const char* fmt, ...);
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (griddepcontrol). The network's passes are ~60 + ~110 dependent launches of 5-900 us
+// kernels; launched back to back each one pays its launch latency and its prologue (barrier init, TMEM allocation,
+// table build) after the predecessor's last CTA has retired. With the launch attribute below the NEXT kernel's CTAs
+// are scheduled as soon as every CTA of this one has passed pdl_launch_dependents() and an SM has room for them; they
+// run their prologue and then block in pdl_wait() until this grid has completed and its memory is visible.
+// Contract: a kernel launched through launch_pdl() calls pdl_wait() before its first global-memory access (reads of
+// a predecessor's output AND writes to anything a predecessor may still read). Both instructions are no-ops in a kernel
+// launched without the attribute. TNB_PDL=0 launches everything fully serialised (ablation).
+// ---------------------------------------------------------------------------------------------
+TNB_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+TNB_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_enabled() {
+  static const int v = [] { const char* e = getenv("TNB_PDL"); return e ? atoi(e) : 1; }();
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+inline int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  TNB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // small utilities
 // ---------------------------------------------------------------------------------------------
 TNB_DEVINL uint32_t smem_u32(const void* p) {

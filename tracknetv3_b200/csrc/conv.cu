@@ -24,7 +24,7 @@ namespace tnb {
 
 #define TNB_CK_NAME conv3x3_kernel
 #define TNB_CK_ARGS ConvArgs
-#define TNB_CK_PAIR 0
+#define TNB_CK_LAUNCH launch_conv3x3_generic
 #define TNB_CK_LEAN 0
 #include "conv_kernel.inc"
 
@@ -41,7 +41,7 @@ static int pow2_cols(int c) {
   while (p < c) p <<= 1;
   return p;
 }
-static int num_sms() {
+int num_sms() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -59,14 +59,9 @@ static int num_sms() {
 // TNB_CONV_MERGE=0 restores the three-MMA form (ablation).
 bool conv3x3_merged(int BN) {
   static const int on = [] { const char* e = getenv("TNB_CONV_MERGE"); return e ? atoi(e) : 1; }();
-  return on && BN == 64 && !conv3x3_pair_enabled();
+  return on && BN == 64;
 }
-// TNB_CONV_PAIR=1: forward / dgrad on CTA pairs (conv_pair.cu; experimental, off by default). The weight layout follows it.
-bool conv3x3_pair_enabled() {
-  static const int on = [] { const char* e = getenv("TNB_CONV_PAIR"); return e ? atoi(e) : 0; }();
-  return on != 0;
-}
-int conv3x3_weight_layout(int BN) { return conv3x3_pair_enabled() ? 2 : conv3x3_merged(BN) ? 1 : 0; }
+int conv3x3_weight_layout(int BN) { return conv3x3_merged(BN) ? 1 : 0; }
 
 int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* plan, bool bn_bwd_fused) {
   TNB_REQUIRE(Cin % 32 == 0, "conv3x3: view channels %d must be a multiple of 32", Cin);
@@ -74,8 +69,6 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
   TNB_REQUIRE(BN >= 32 && BN % 16 == 0, "conv3x3: unsupported output channel count %d", Cout);
   const int TP = nterms > 1 ? 2 : 1;
   const bool merged = conv3x3_merged(BN);
-  const bool pair = conv3x3_pair_enabled();  // each CTA of a pair holds half of every weight stage
-  TNB_REQUIRE(!(pair && bn_bwd_fused), "conv3x3: the CTA-pair kernel has no fused BatchNorm-backward reduction");
   const int ACCW = (merged && nterms > 1) ? 2 * BN : BN;  // accumulator columns per M tile
   int MT = 512 / ACCW;
   if (MT > 4) MT = 4;
@@ -108,7 +101,7 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
     for (MT = mt_max; MT >= 1; --MT) {
       const int pitch = 8 * MT + 2, halo = 18 * pitch;
       const size_t a_stage = (size_t)TP * 4 * pad_px(halo) * 16;
-      const size_t b_stage = (size_t)g * (merged ? 2 : TP) * 64 * BN / (pair ? 2 : 1);
+      const size_t b_stage = (size_t)g * (merged ? 2 : TP) * 64 * BN;
       const size_t fixed = kHdrBytes + ((halo * 8 + 127) & ~127) + (size_t)4 * 2 * BN * 4 + (bn_bwd_fused ? BN * 16 : 0) +
                            SA * a_stage;
       if (fixed + 2 * b_stage <= (size_t)kMaxSmem) {
@@ -127,7 +120,6 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
   plan->nbuf = (2 * MT * ACCW <= 512) ? 2 : 1;
   plan->tmem_cols = pow2_cols(plan->nbuf * MT * ACCW);
   plan->merged = merged ? 1 : 0;
-  plan->pair = pair ? 1 : 0;
   plan->smem_bytes = smem;
   plan->tall = tall ? 1 : 0;
   plan->tiles_h = tall ? (H + 8 * MT - 1) / (8 * MT) : (H + 15) / 16;
@@ -147,50 +139,13 @@ int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, floa
   ConvPlan p;
   int rc = conv3x3_plan(view.N, view.H, view.W, view.C, Cout, nterms, &p, fuse != nullptr);
   if (rc) return rc;
-  // TNB_CONV_LEAN=1: experimental lean MMA-issue loop (conv_lean.cu), same plan and weight layout as the shipped kernel
-  static const int lean_env = [] { const char* e = getenv("TNB_CONV_LEAN"); return e ? atoi(e) : 0; }();
-  if (p.pair && lean_env) return launch_conv3x3_pair_lean(view, wpack, out, stat_part, Cout, nterms, fmt, variant, p, st);
-  if (p.pair) return launch_conv3x3_pair(view, wpack, out, stat_part, Cout, nterms, fmt, variant, p, st);
-  if (lean_env) return launch_conv3x3_lean(view, wpack, out, stat_part, Cout, nterms, fmt, variant, p, st, fuse);
-  const int m0 = view.s[0].mode, m1 = (view.C0 < view.C) ? view.s[1].mode : view.s[0].mode;
-  ConvArgs a;
-  a.view = view; a.wpack = wpack; a.out = out; a.stat_part = stat_part;
-  a.bz = a.bsc = a.bsh = a.bmu = a.bis = nullptr;
-  if (fuse != nullptr) {
-    TNB_REQUIRE(stat_part != nullptr, "conv3x3: fused BatchNorm-backward reduction needs a partials buffer");
-    TNB_REQUIRE(fmt == 1 && m0 == SRC_PRESPLIT && m1 == SRC_PRESPLIT,
-                "conv3x3: the fused BatchNorm-backward reduction exists for the dgrad configuration only");
-    a.bz = fuse->z; a.bsc = fuse->scale; a.bsh = fuse->shift; a.bmu = fuse->mean; a.bis = fuse->invstd;
-  }
-  a.Cout = Cout; a.BN = p.BN; a.MT = p.MT; a.SA = p.SA; a.SB = p.SB; a.G = p.G; a.nbuf = p.nbuf; a.nterms = nterms;
-  a.variant = variant | (cp_async_ca_env() ? 256 : 0); a.tmem_cols = p.tmem_cols; a.tiles_h = p.tiles_h; a.tiles_w = p.tiles_w; a.tall = p.tall; a.merged = p.merged;
-  a.ntiles = view.N * p.tiles_h * p.tiles_w;
-  a.nwork = a.ntiles * (Cout / p.BN);
-  const int grid = a.nwork < num_sms() ? a.nwork : num_sms();
-  ProfScope prof(view.s[0].mode == SRC_PRESPLIT ? PROF_CONV_DGRAD : PROF_CONV_FWD, st, view.N, view.H, view.W, view.C, Cout);
-  auto go = [&](auto kern) -> int {
-    TNB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-    kern<<<grid, kThreads, p.smem_bytes, st>>>(a);
-    return 0;
-  };
-  int rc2 = -2;
-#define TNB_CONV_CASE(F, A, B) if (fmt == F && m0 == A && m1 == B) rc2 = go(conv3x3_kernel<F, A, B>); else
-  TNB_CONV_CASE(0, SRC_IDENTITY, SRC_IDENTITY)
-  TNB_CONV_CASE(0, SRC_AFFINE_RELU, SRC_AFFINE_RELU)
-  TNB_CONV_CASE(0, SRC_AFFINE_RELU_POOL, SRC_AFFINE_RELU_POOL)
-  TNB_CONV_CASE(0, SRC_AFFINE_RELU_UP, SRC_AFFINE_RELU)
-  TNB_CONV_CASE(0, SRC_AFFINE_RELU_UP, SRC_AFFINE_RELU_UP)
-  TNB_CONV_CASE(0, SRC_PRESPLIT, SRC_PRESPLIT)
-  TNB_CONV_CASE(1, SRC_IDENTITY, SRC_IDENTITY)
-  if (fmt == 1 && m0 == SRC_PRESPLIT && m1 == SRC_PRESPLIT && fuse != nullptr)
-    rc2 = go(conv3x3_kernel<1, SRC_PRESPLIT, SRC_PRESPLIT, true>);
-  else
-  TNB_CONV_CASE(1, SRC_PRESPLIT, SRC_PRESPLIT)
-  { tnb::set_last_error("conv3x3: unsupported (fmt %d, source modes %d/%d) combination", fmt, m0, m1); return -2; }
-#undef TNB_CONV_CASE
-  if (rc2) return rc2;
-  TNB_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  // Which MMA-issue loop (conv_kernel.inc): the lean one for the forward pass and wherever the tile is 64 wide (short MMAs:
+  // the generic loop's ~20 instructions per MMA fall behind), the generic one on the wide dgrad tiles, where it measured
+  // ~5 % faster (per-launch A/B on one box, profiles/r2_experiments.md). TNB_CONV_LEAN=0 / 1 forces one of them (ablation).
+  static const int lean_env = [] { const char* e = getenv("TNB_CONV_LEAN"); return e ? atoi(e) : -1; }();
+  const bool lean = lean_env >= 0 ? lean_env != 0 : (fmt == 0 || p.BN == 64);
+  return lean ? launch_conv3x3_lean(view, wpack, out, stat_part, Cout, nterms, fmt, variant, p, st, fuse)
+              : launch_conv3x3_generic(view, wpack, out, stat_part, Cout, nterms, fmt, variant, p, st, fuse);
 }
 
 }  // namespace tnb

@@ -24,6 +24,7 @@
 #include "prof.cuh"
 #include <stdio.h>
 #include <type_traits>
+#include <algorithm>
 
 namespace tnb {
 
@@ -34,14 +35,18 @@ namespace tnb {
 // mode 0 (forward):  B[n = co][k = ci] = W[co][ci][dy][dx]
 // mode 1 (dgrad):    B[n = ci][k = co] = W[co][ci][2-dy][2-dx]      (180-degree rotated, transposed)
 // =============================================================================================
-template <int FMT>
-__global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Co, int Ci,
-                                    int Nside, int Kpad, int BN, int mode, int layout) {
-  const int nchunks = Kpad / 32;
-  const long long total = (long long)(Nside / BN) * nchunks * 9 * 4 * BN;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+// One launch packs every tensor of a table (the 17 forward operands and, when training, the 16 dgrad operands of a
+// TrackNet step): 33 launches of 3-7 us collapse into one.
+__global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant__ PackTable t) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < t.total;
        i += (long long)gridDim.x * blockDim.x) {
-    long long r = i;
+    int ei = 0;
+    while (ei + 1 < t.n && i >= t.e[ei + 1].first) ++ei;
+    const PackEntry& E = t.e[ei];
+    const int BN = E.BN, nchunks = E.Kpad / 32;
+    long long r = i - E.first;
     const int nl = (int)(r % BN); r /= BN;
     const int plane = (int)(r % 4); r /= 4;
     const int tap = (int)(r % 9); r /= 9;
@@ -54,36 +59,29 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __res
     for (int e = 0; e < 8; ++e) {
       const int k = chunk * 32 + plane * 8 + e;
       float x = 0.f;
-      if (mode == 0) {
-        if (n < Co && k < Ci) x = w[(((size_t)n * Ci + k) * 3 + dy) * 3 + dx];
+      if (E.mode == 0) {
+        if (n < E.Co && k < E.Ci) x = E.w[(((size_t)n * E.Ci + k) * 3 + dy) * 3 + dx];
       } else {
-        if (n < Ci && k < Co) x = w[(((size_t)k * Ci + n) * 3 + (2 - dy)) * 3 + (2 - dx)];
+        if (n < E.Ci && k < E.Co) x = E.w[(((size_t)k * E.Ci + n) * 3 + (2 - dy)) * 3 + (2 - dx)];
       }
       v[e] = x;
     }
     uint4 hi, lo;
-    split8<FMT>(v, hi, lo);
+    if (E.fmt == 0) split8<0>(v, hi, lo); else split8<1>(v, hi, lo);
     // stage base (uint16 elements): ((ntile*nchunks + chunk)*9 + tap) * (2*4*BN*8)
     const size_t stage = (((size_t)ntile * nchunks + chunk) * 9 + tap) * (size_t)(64 * BN);
     // [term][plane][BN rows][8], or for the merged 64-wide tiles [plane][term][BN rows][8] (conv3x3_merged): hi and lo
     // rows of a plane are then one operand of 2 * BN rows
-    // CTA-pair kernel (layout 2): [rank][term][plane][BN/2 rows][8] - each CTA of a pair fetches one contiguous half
     size_t off_hi, off_lo;
-    if (layout == 2) {
-      const int half = BN / 2, rk = nl / half, nh = nl - rk * half;
-      off_hi = (size_t)rk * 32 * BN + ((size_t)plane * half + nh) * 8;
-      off_lo = off_hi + (size_t)16 * BN;
-    } else if (layout == 1) {
+    if (E.layout == 1) {
       off_hi = ((size_t)plane * 2 * BN + nl) * 8;
       off_lo = ((size_t)(plane * 2 + 1) * BN + nl) * 8;
     } else {
       off_hi = ((size_t)plane * BN + nl) * 8;
       off_lo = (size_t)32 * BN + off_hi;
     }
-    uint4* dst_hi = reinterpret_cast<uint4*>(out + stage + off_hi);
-    uint4* dst_lo = reinterpret_cast<uint4*>(out + stage + off_lo);
-    *dst_hi = hi;
-    *dst_lo = lo;
+    *reinterpret_cast<uint4*>(E.out + stage + off_hi) = hi;
+    *reinterpret_cast<uint4*>(E.out + stage + off_lo) = lo;
   }
 }
 
@@ -92,22 +90,30 @@ size_t conv3x3_wpack_elems(int Kside, int Nside) {
   return (size_t)Nside * Kpad * 9 * 2;
 }
 
-int launch_pack_weights(const float* w, uint16_t* out, int Co, int Ci, int mode, int fmt, int BN,
-                        cudaStream_t st) {
+int pack_table_add(PackTable* t, const float* w, uint16_t* out, int Co, int Ci, int mode, int fmt, int BN) {
+  TNB_REQUIRE(t->n < kMaxPack, "pack_weights: more than %d tensors in one table", kMaxPack);
   const int Nside = mode == 0 ? Co : Ci;
   const int Kside = mode == 0 ? Ci : Co;
   const int Kpad = (Kside + 31) / 32 * 32;
   TNB_REQUIRE(BN > 0 && Nside % BN == 0, "pack_weights: N side %d not divisible by BN %d", Nside, BN);
-  const long long total = (long long)(Nside / BN) * (Kpad / 32) * 9 * 4 * BN;
-  const int threads = 256;
-  const int blocks = (int)((total + threads - 1) / threads);
-  const int layout = conv3x3_weight_layout(BN);  // a function of the tile width (and the experiment switches) alone
-  if (fmt == 0)
-    pack_weights_kernel<0><<<blocks, threads, 0, st>>>(w, out, Co, Ci, Nside, Kpad, BN, mode, layout);
-  else
-    pack_weights_kernel<1><<<blocks, threads, 0, st>>>(w, out, Co, Ci, Nside, Kpad, BN, mode, layout);
-  TNB_CHECK_CUDA(cudaGetLastError());
+  PackEntry& E = t->e[t->n++];
+  E.w = w; E.out = out; E.Co = Co; E.Ci = Ci; E.Kpad = Kpad; E.BN = BN; E.mode = mode; E.fmt = fmt;
+  E.layout = conv3x3_weight_layout(BN);  // a function of the tile width alone
+  E.first = t->total;
+  t->total += (long long)(Nside / BN) * (Kpad / 32) * 9 * 4 * BN;
   return 0;
+}
+int launch_pack_table(const PackTable& t, cudaStream_t st) {
+  if (t.n == 0) return 0;
+  const int blocks = (int)std::min<long long>((t.total + 255) / 256, 148 * 16);
+  return launch_pdl(pack_weights_kernel, dim3(blocks), dim3(256), 0, st, t);
+}
+int launch_pack_weights(const float* w, uint16_t* out, int Co, int Ci, int mode, int fmt, int BN,
+                        cudaStream_t st) {
+  PackTable t;
+  t.n = 0; t.total = 0;
+  if (int rc = pack_table_add(&t, w, out, Co, Ci, mode, fmt, BN)) return rc;
+  return launch_pack_table(t, st);
 }
 
 }  // namespace tnb

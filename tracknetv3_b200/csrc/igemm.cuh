@@ -141,40 +141,44 @@ __host__ __device__ inline int pad_px(int px) {  // plane stride = 2 (mod 8) pix
 }
 
 struct ConvPlan {
-  int BN, MT, SA, SB, G, nbuf, tmem_cols, merged, pair;
+  int BN, MT, SA, SB, G, nbuf, tmem_cols, merged;
   size_t smem_bytes;
   int tiles_h, tiles_w;
   int tall;  // tile orientation, see conv3x3_plan
 };
 // fmt: 0 = fp16 split, 1 = bf16 split. nterms: 1 (single pass) or 3 (hi*hi + lo*hi + hi*lo).
 // bn_bwd_fused: reserve the per-channel constant table of the fused BatchNorm-backward reduction (dgrad epilogue)
-bool conv3x3_pair_enabled();          // TNB_CONV_PAIR=1: forward / dgrad on CTA pairs (conv_pair.cu, experimental)
-int conv3x3_weight_layout(int BN);    // 0 plain [term][plane][BN], 1 merged [plane][term][BN], 2 pair [rank][term][plane][BN/2]
+int conv3x3_weight_layout(int BN);    // 0 plain [term][plane][BN], 1 merged [plane][term][BN]
 bool conv3x3_merged(int BN);  // weights of this tile width are packed [plane][hi | lo][BN] (one MMA for x_hi * [w_hi | w_lo])
 int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* plan, bool bn_bwd_fused = false);
 size_t conv3x3_wpack_elems(int Kside, int Nside);  // uint16 elements of a packed weight buffer
 int launch_pack_weights(const float* w_oihw, uint16_t* out, int Co, int Ci, int mode /*0 fwd, 1 dgrad*/,
                         int fmt, int BN, cudaStream_t st);
+// many tensors in one launch: pack_table_add() each, then launch_pack_table()
+struct PackEntry { const float* w; uint16_t* out; long long first; int Co, Ci, Kpad, BN, mode, fmt, layout; };
+constexpr int kMaxPack = 36;
+struct PackTable { PackEntry e[kMaxPack]; long long total; int n; };
+int pack_table_add(PackTable* t, const float* w_oihw, uint16_t* out, int Co, int Ci, int mode, int fmt, int BN);
+int launch_pack_table(const PackTable& t, cudaStream_t st);
 // Optional fusion for dgrad launches: `out` is dL/d(activation) of a producer layer whose raw conv output is `z`; the
 // per-tile partials become (sum g, sum g * xhat) with g = out masked by that layer's ReLU - the reduction pass of its
 // BatchNorm backward - instead of (sum out, sum out^2).
 struct BnBwdFuse { const float *z, *scale, *shift, *mean, *invstd; };
-// lean-issue variant (conv_lean.cu, TNB_CONV_LEAN=1)
+// the two MMA-issue-loop variants of the kernel (conv.cu / conv_lean.cu); launch_conv3x3 plans and picks
+int launch_conv3x3_generic(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout, int nterms,
+                           int fmt, int variant, const ConvPlan& plan, cudaStream_t st, const BnBwdFuse* fuse = nullptr);
 int launch_conv3x3_lean(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout, int nterms,
                         int fmt, int variant, const ConvPlan& plan, cudaStream_t st, const BnBwdFuse* fuse = nullptr);
-int launch_conv3x3_pair_lean(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout, int nterms,
-                             int fmt, int variant, const ConvPlan& plan, cudaStream_t st, const BnBwdFuse* fuse = nullptr);  // both experiments (conv_pair_lean.cu)
-// CTA-pair variant (conv_pair.cu), selected by launch_conv3x3 when the plan says so
-int launch_conv3x3_pair(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout, int nterms,
-                        int fmt, int variant, const ConvPlan& plan, cudaStream_t st, const BnBwdFuse* fuse = nullptr);
+int num_sms();
 int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout,
                    int nterms, int fmt, int variant, cudaStream_t st, const BnBwdFuse* fuse = nullptr);
 int conv3x3_num_stat_rows(int N, int H, int W, int Cin, int Cout, int nterms, bool bn_bwd_fused = false);
 
-// ws: optional scratch of 9 * Cout * view.C floats. With it the split-K partials are reduced tap-major, where the lanes of a
-// warp hit consecutive addresses (one 128-byte reduction per instruction instead of 32 scattered ones), and a small
-// kernel then writes dw_oihw (plain stores: dw need not be zeroed). Without it the partials are added into dw_oihw
-// directly (the caller zeroes it).
+// ws: optional scratch of wgrad3x3_ws_floats(view, Cout) floats. With it every split-K CTA stores its partial tap-major
+// into its own slab (lanes of a warp hit consecutive addresses) and a small kernel sums the slabs in split order into
+// dw_oihw: deterministic, plain stores, dw need not be zeroed. Without it the partials are added into dw_oihw with
+// atomics (the caller zeroes it; summation order, hence the last bits, vary from run to run).
+size_t wgrad3x3_ws_floats(const ViewDesc& view, int Cout);
 int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw_oihw, int Cout, int CinReal, int nterms,
                     int variant, cudaStream_t st, float* ws = nullptr);
 

@@ -14,6 +14,8 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 // =============================================================================================
 __global__ void pack_input_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int C, int H, int W,
                                   int Cpad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long npix = (long long)N * H * W;
   const long long hw = (long long)H * W;
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix;
@@ -33,7 +35,7 @@ __global__ void pack_input_kernel(const float* __restrict__ x, float* __restrict
 }
 int launch_pack_input(const float* x, float* out, int N, int C, int H, int W, int Cpad, cudaStream_t st) {
   const long long npix = (long long)N * H * W;
-  pack_input_kernel<<<min(cdiv(npix, 256), 148 * 16), 256, 0, st>>>(x, out, N, C, H, W, Cpad);
+  if (int rc = launch_pdl(pack_input_kernel, dim3(min(cdiv(npix, 256), 148 * 16)), dim3(256), 0, st, x, out, N, C, H, W, Cpad)) return rc;
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -89,6 +91,8 @@ __global__ void __launch_bounds__(kFinCh * kFinLanes) bn_finalize_kernel(const f
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* running_mean, float* running_var, float momentum, float eps, int training,
                                    float* scale, float* shift, float* mean_out, float* invstd_out, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ FinalizeSmem sm;
   const int c = blockIdx.x * kFinCh + threadIdx.x;
   double sa, sb;
@@ -118,11 +122,8 @@ __global__ void __launch_bounds__(kFinCh * kFinLanes) bn_finalize_kernel(const f
 int launch_bn_finalize(const float* part, int rows, double count, const float* gamma, const float* beta,
                        float* running_mean, float* running_var, float momentum, float eps, int training,
                        float* scale, float* shift, float* mean, float* invstd, int C, cudaStream_t st) {
-  bn_finalize_kernel<<<cdiv(C, kFinCh), dim3(kFinCh, kFinLanes), 0, st>>>(part, rows, count, gamma, beta, running_mean,
-                                                           running_var, momentum, eps, training, scale, shift, mean,
-                                                           invstd, C);
-  TNB_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return launch_pdl(bn_finalize_kernel, dim3(cdiv(C, kFinCh)), dim3(kFinCh, kFinLanes), 0, st, part, rows, count, gamma, beta,
+                    running_mean, running_var, momentum, eps, training, scale, shift, mean, invstd, C);
 }
 
 // =============================================================================================
@@ -137,8 +138,11 @@ static constexpr int kMaxPredO = 16;
 template <int O_MAX>
 __global__ void __launch_bounds__(256) predictor_fwd_kernel(SrcDesc src, int N, int H, int W,
                                                             const float* __restrict__ wp,
-                                                            const float* __restrict__ bias, int O,
+                                                            const float* __restrict__ bias, int O, int o0, int OT,
                                                             float* __restrict__ y) {
+  // this launch computes output channels [o0, o0 + O) of OT (wp / bias already point at channel o0)
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sw[kMaxPredO * 64 + kMaxPredO];
   for (int i = threadIdx.x; i < O * 64; i += blockDim.x) sw[i] = wp[i];
   for (int i = threadIdx.x; i < O; i += blockDim.x) sw[kMaxPredO * 64 + i] = bias[i];
@@ -178,21 +182,27 @@ __global__ void __launch_bounds__(256) predictor_fwd_kernel(SrcDesc src, int N, 
       const long long n = p / hw, r = p - n * hw;
 #pragma unroll
       for (int o = 0; o < O_MAX; ++o)
-        if ((o & 3) == qd && o < O) y[(n * O + o) * hw + r] = 1.f / (1.f + expf(-(s[o] + sw[kMaxPredO * 64 + o])));
+        if ((o & 3) == qd && o < O) y[(n * OT + o0 + o) * hw + r] = 1.f / (1.f + expf(-(s[o] + sw[kMaxPredO * 64 + o])));
     }
   }
 }
 int launch_predictor_fwd(const SrcDesc& src, int N, int H, int W, const float* wp, const float* bias, int O,
                          float* y, cudaStream_t st) {
-  TNB_REQUIRE(src.C == 64 && O <= kMaxPredO, "predictor: expects 64 input channels and out_dim <= %d", kMaxPredO);
+  TNB_REQUIRE(src.C == 64 && O >= 1, "predictor: expects 64 input channels and out_dim >= 1 (got %d, %d)", src.C, O);
   TNB_REQUIRE((src.mode == SRC_IDENTITY || src.mode == SRC_AFFINE_RELU) && src.Hs == H && src.Ws == W,
               "predictor: the activation must be a same-resolution identity / BN+ReLU source (mode %d)", src.mode);
   const long long npix = (long long)N * H * W;
   ProfScope prof(PROF_PRED, st, N, H, W, 64, O);
   const int grid = (int)std::min<long long>((npix * 4 + 255) / 256, 148 * 8);
-  if (O <= 8) predictor_fwd_kernel<8><<<grid, 256, 0, st>>>(src, N, H, W, wp, bias, O, y);
-  else        predictor_fwd_kernel<kMaxPredO><<<grid, 256, 0, st>>>(src, N, H, W, wp, bias, O, y);
-  TNB_CHECK_CUDA(cudaGetLastError());
+  // any out_dim (the reference accepts any seq_len, utils/general.py:66-74): groups of up to 16 output channels per launch
+  for (int o0 = 0; o0 < O; o0 += kMaxPredO) {
+    const int og = std::min(O - o0, kMaxPredO);
+    if (int rc = og <= 8 ? launch_pdl(predictor_fwd_kernel<8>, dim3(grid), dim3(256), 0, st, src, N, H, W, wp + o0 * 64,
+                                      bias + o0, og, o0, O, y)
+                         : launch_pdl(predictor_fwd_kernel<kMaxPredO>, dim3(grid), dim3(256), 0, st, src, N, H, W,
+                                      wp + o0 * 64, bias + o0, og, o0, O, y))
+      return rc;
+  }
   return 0;
 }
 
@@ -202,8 +212,11 @@ int launch_predictor_fwd(const SrcDesc& src, int N, int H, int W, const float* w
 // at 1.7 TB/s): dA needs only dl and W; dW / db need dl and the activation, reduced in registers along the pixels.
 template <int O_MAX>
 __global__ void __launch_bounds__(256) predictor_bwd_da_kernel(long long npix, long long hw, const float* __restrict__ wp,
-                                                               int O, const float* __restrict__ dy,
+                                                               int O, int o0, int OT, const float* __restrict__ dy,
                                                                const float* __restrict__ y, float* __restrict__ dA) {
+  // output channels [o0, o0 + O) of OT; groups after the first (o0 > 0) add to what the earlier launches wrote
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sw[kMaxPredO * 64];
   for (int i = threadIdx.x; i < O * 64; i += blockDim.x) sw[i] = wp[i];
   __syncthreads();
@@ -219,8 +232,16 @@ __global__ void __launch_bounds__(256) predictor_bwd_da_kernel(long long npix, l
     for (int i = 0; i < 16; ++i) g[i] = 0.f;
 #pragma unroll
     for (int o = 0; o < O_MAX; ++o) {  // all 2 * O loads of the item in flight together
-      yv[o] = o < O ? __ldg(y + (n * O + o) * hw + r) : 0.f;
-      dv[o] = o < O ? __ldg(dy + (n * O + o) * hw + r) : 0.f;
+      yv[o] = o < O ? __ldg(y + (n * OT + o0 + o) * hw + r) : 0.f;
+      dv[o] = o < O ? __ldg(dy + (n * OT + o0 + o) * hw + r) : 0.f;
+    }
+    float4* dst = reinterpret_cast<float4*>(dA + p * 64 + qd * 4);
+    if (o0 > 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 t = dst[4 * i];
+        g[4 * i] = t.x; g[4 * i + 1] = t.y; g[4 * i + 2] = t.z; g[4 * i + 3] = t.w;
+      }
     }
 #pragma unroll
     for (int o = 0; o < O_MAX; ++o) {
@@ -230,7 +251,6 @@ __global__ void __launch_bounds__(256) predictor_bwd_da_kernel(long long npix, l
         for (int i = 0; i < 16; ++i) g[i] = fmaf(d, sw[o * 64 + (i >> 2) * 16 + qd * 4 + (i & 3)], g[i]);
       }
     }
-    float4* dst = reinterpret_cast<float4*>(dA + p * 64 + qd * 4);
 #pragma unroll
     for (int i = 0; i < 4; ++i) dst[4 * i] = make_float4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
   }
@@ -240,9 +260,13 @@ __global__ void __launch_bounds__(256) predictor_bwd_da_kernel(long long npix, l
 // activation (one 16-byte load; 512 contiguous bytes per warp instruction, 8 of them in flight) and the dl values
 // arrive by shuffle; acc[o][4] lives in registers for the whole grid-stride loop
 template <int O_MAX>
-__global__ void __launch_bounds__(256) predictor_bwd_dw_kernel(SrcDesc src, long long npix, long long hw, int O,
-                                                               const float* __restrict__ dy, const float* __restrict__ y,
-                                                               float* dwp, float* dbias) {
+__global__ void __launch_bounds__(256) predictor_bwd_dw_kernel(SrcDesc src, long long npix, long long hw, int O, int o0,
+                                                               int OT, const float* __restrict__ dy,
+                                                               const float* __restrict__ y, float* __restrict__ part) {
+  // output channels [o0, o0 + O) of OT. part: [gridDim.x][OT * 65] per-block partial sums (dW rows of 64, then db),
+  // summed in block order by predictor_dw_final_kernel - no atomics, the gradient is bit-identical from run to run
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int half = lane >> 4, c4 = (lane & 15) * 4;
   const bool affine = src.mode != SRC_IDENTITY;
@@ -263,8 +287,8 @@ __global__ void __launch_bounds__(256) predictor_bwd_dw_kernel(SrcDesc src, long
 #pragma unroll
     for (int o = 0; o < O_MAX; ++o) {
       const bool ok = o < O && p < npix;
-      yv[o] = ok ? __ldg(y + (n * O + o) * hw + r) : 0.f;
-      d[o] = ok ? __ldg(dy + (n * O + o) * hw + r) : 0.f;
+      yv[o] = ok ? __ldg(y + (n * OT + o0 + o) * hw + r) : 0.f;
+      d[o] = ok ? __ldg(dy + (n * OT + o0 + o) * hw + r) : 0.f;
     }
 #pragma unroll
     for (int o = 0; o < O_MAX; ++o) { d[o] = d[o] * yv[o] * (1.f - yv[o]); dsum[o] += d[o]; }
@@ -287,7 +311,7 @@ __global__ void __launch_bounds__(256) predictor_bwd_dw_kernel(SrcDesc src, long
       }
     }
   }
-  // fold the two half-warps, then block reduction over the 8 warps, then one atomic per (o, channel) and per o
+  // fold the two half-warps, then block reduction over the 8 warps, then one partial per (o, channel) and per o
   __shared__ float red[8][O_MAX][64];
   __shared__ float redb[8][O_MAX];
 #pragma unroll
@@ -302,37 +326,63 @@ __global__ void __launch_bounds__(256) predictor_bwd_dw_kernel(SrcDesc src, long
     if (lane == 0) redb[warp][o] = s;
   }
   __syncthreads();
+  float* mine = part + (size_t)blockIdx.x * OT * 65;
   for (int i = threadIdx.x; i < O * 64; i += blockDim.x) {
     const int o = i >> 6, c = i & 63;
     float s = 0.f;
     for (int w = 0; w < 8; ++w) s += red[w][o][c];
-    atomicAdd(dwp + i, s);
+    mine[(o0 + o) * 64 + c] = s;
   }
   if (threadIdx.x < O) {
     float s = 0.f;
     for (int w = 0; w < 8; ++w) s += redb[w][threadIdx.x];
-    atomicAdd(dbias + threadIdx.x, s);
+    mine[OT * 64 + o0 + threadIdx.x] = s;
   }
 }
+// dW[o][c] / db[o] = sum over the blocks' partials in block order (fp64 accumulation, fixed order)
+__global__ void __launch_bounds__(256) predictor_dw_final_kernel(const float* __restrict__ part, int nblocks, int OT,
+                                                                 float* __restrict__ dwp, float* __restrict__ dbias) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= OT * 65) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += (double)part[(size_t)b * OT * 65 + i];
+  if (i < OT * 64) dwp[i] = (float)s; else dbias[i - OT * 64] = (float)s;
+}
+static int predictor_dw_blocks(long long npix) {
+  const long long blocks_w = ((npix + 31) / 32 + 7) / 8;
+  return (int)std::min<long long>(blocks_w, 148 * 4);
+}
+size_t predictor_bwd_workspace_bytes(int N, int H, int W, int O) {
+  return sizeof(float) * (size_t)predictor_dw_blocks((long long)N * H * W) * O * 65;
+}
 int launch_predictor_bwd(const SrcDesc& src, int N, int H, int W, const float* wp, int O, const float* dy,
-                         const float* y, float* dA, float* dwp, float* dbias, cudaStream_t st) {
-  TNB_REQUIRE(src.C == 64 && O <= kMaxPredO, "predictor_bwd: expects 64 channels, out_dim <= %d", kMaxPredO);
+                         const float* y, float* dA, float* dwp, float* dbias, float* part, cudaStream_t st) {
+  TNB_REQUIRE(src.C == 64 && O >= 1, "predictor_bwd: expects 64 channels and out_dim >= 1 (got %d, %d)", src.C, O);
   TNB_REQUIRE((src.mode == SRC_IDENTITY || src.mode == SRC_AFFINE_RELU) && src.Hs == H && src.Ws == W,
               "predictor_bwd: the activation must be a same-resolution identity / BN+ReLU source (mode %d)", src.mode);
+  TNB_REQUIRE(part != nullptr, "predictor_bwd: needs a workspace of predictor_bwd_workspace_bytes()");
   const long long npix = (long long)N * H * W, hw = (long long)H * W;
-  TNB_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * O * 64, st));
-  TNB_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * O, st));
   ProfScope prof(PROF_PRED, st, N, H, W, 64, O);
-  const long long blocks_a = (npix * 4 + 255) / 256, blocks_w = ((npix + 31) / 32 + 7) / 8;
+  const long long blocks_a = (npix * 4 + 255) / 256;
   const int grida = (int)std::min<long long>(blocks_a, 148 * 8);
-  if (O <= 8) predictor_bwd_da_kernel<8><<<grida, 256, 0, st>>>(npix, hw, wp, O, dy, y, dA);
-  else        predictor_bwd_da_kernel<kMaxPredO><<<grida, 256, 0, st>>>(npix, hw, wp, O, dy, y, dA);
-  TNB_CHECK_CUDA(cudaGetLastError());
-  const int gridw = (int)std::min<long long>(blocks_w, 148 * 4);
-  if (O <= 8) predictor_bwd_dw_kernel<8><<<gridw, 256, 0, st>>>(src, npix, hw, O, dy, y, dwp, dbias);
-  else        predictor_bwd_dw_kernel<kMaxPredO><<<gridw, 256, 0, st>>>(src, npix, hw, O, dy, y, dwp, dbias);
-  TNB_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  const int gridw = predictor_dw_blocks(npix);
+  for (int o0 = 0; o0 < O; o0 += kMaxPredO) {  // groups of up to 16 output channels, see launch_predictor_fwd
+    const int og = std::min(O - o0, kMaxPredO);
+    if (int rc = og <= 8 ? launch_pdl(predictor_bwd_da_kernel<8>, dim3(grida), dim3(256), 0, st, npix, hw, wp + o0 * 64, og, o0,
+                                      O, dy, y, dA)
+                         : launch_pdl(predictor_bwd_da_kernel<kMaxPredO>, dim3(grida), dim3(256), 0, st, npix, hw,
+                                      wp + o0 * 64, og, o0, O, dy, y, dA))
+      return rc;
+    if (int rc = og <= 8 ? launch_pdl(predictor_bwd_dw_kernel<8>, dim3(gridw), dim3(256), 0, st, src, npix, hw, og, o0, O, dy, y,
+                                      part)
+                         : launch_pdl(predictor_bwd_dw_kernel<kMaxPredO>, dim3(gridw), dim3(256), 0, st, src, npix, hw, og, o0,
+                                      O, dy, y, part))
+      return rc;
+  }
+  return launch_pdl(predictor_dw_final_kernel, dim3((O * 65 + 255) / 256), dim3(256), 0, st, (const float*)part, gridw, O, dwp,
+                    dbias);
 }
 
 // =============================================================================================
@@ -345,11 +395,10 @@ TNB_DEVINL float4 ld4(const float* p) { return __ldg(reinterpret_cast<const floa
 TNB_DEVINL float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 // CFG 0: one GRAD_SAME consumer; CFG 1: {GRAD_POOL, GRAD_SAME}; CFG 2: anything else (generic gather)
-// REV (experiment, TNB_BN_REVERSE=1): the reduction pass walks the tensor in descending address order, so that it starts on
-// the tail of dy the dgrad kernel has just written and the apply pass (ascending) starts on what the reduction read last -
-// the 126 MB L2 then serves part of the second read. A pure permutation of the item -> thread assignment.
-template <bool APPLY, int CFG, bool REV = false>
+template <bool APPLY, int CFG>
 __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnBwdArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int CQ = a.C >> 2;
   const int Hw = (a.H + 1) >> 1, Ww = (a.W + 1) >> 1;
   const unsigned items = (unsigned)a.N * Hw * Ww * CQ;  // < 2^31, checked by the launcher
@@ -358,7 +407,7 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnB
   float4 acc1 = make_float4(0, 0, 0, 0), acc2 = make_float4(0, 0, 0, 0);
   float amax = 0.f;
   for (unsigned it0 = blockIdx.x * blockDim.x + threadIdx.x; it0 < items; it0 += stride) {
-    const unsigned it = REV ? items - 1 - it0 : it0;
+    const unsigned it = it0;
     const int cq = (int)(it & (CQ - 1));
     unsigned r = it >> cq_shift;
     const int ww = (int)(r % (unsigned)Ww); r /= (unsigned)Ww;
@@ -537,47 +586,30 @@ static int bn_bwd_check(const BnBwdArgs& a) {
   TNB_REQUIRE((long long)a.N * ((a.H + 1) / 2) * ((a.W + 1) / 2) * (a.C / 4) < (1ll << 31), "bn_bwd: tensor too large");
   return 0;
 }
-int launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t st, int rev) {
+int launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t st) {
   if (int rc = bn_bwd_check(a)) return rc;
   ProfScope prof(PROF_BN_BWD, st, a.N, a.H, a.W, a.C, a.C);
   const int nb = bn_bwd_num_blocks(a.N, a.H, a.W, a.C);
-  static const int reverse = [] { const char* e = getenv("TNB_BN_REVERSE"); return e ? atoi(e) : 0; }();
-  if (rev < 0 ? reverse != 0 : rev != 0) {  // rev < 0: no per-call direction, the environment switch decides
-    switch (bn_bwd_cfg(a)) {
-      case 0: bn_bwd_kernel<false, 0, true><<<nb, 256, 0, st>>>(a); break;
-      case 1: bn_bwd_kernel<false, 1, true><<<nb, 256, 0, st>>>(a); break;
-      default: bn_bwd_kernel<false, 2, true><<<nb, 256, 0, st>>>(a); break;
-    }
-  } else
   switch (bn_bwd_cfg(a)) {
-    case 0: bn_bwd_kernel<false, 0><<<nb, 256, 0, st>>>(a); break;
-    case 1: bn_bwd_kernel<false, 1><<<nb, 256, 0, st>>>(a); break;
-    default: bn_bwd_kernel<false, 2><<<nb, 256, 0, st>>>(a); break;
+    case 0: return launch_pdl(bn_bwd_kernel<false, 0>, dim3(nb), dim3(256), 0, st, a);
+    case 1: return launch_pdl(bn_bwd_kernel<false, 1>, dim3(nb), dim3(256), 0, st, a);
+    default: return launch_pdl(bn_bwd_kernel<false, 2>, dim3(nb), dim3(256), 0, st, a);
   }
-  TNB_CHECK_CUDA(cudaGetLastError());
-  return 0;
 }
-int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st, int rev) {
+int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st) {
   if (int rc = bn_bwd_check(a)) return rc;
   ProfScope prof(PROF_BN_BWD, st, a.N, a.H, a.W, a.C, a.C);
   const int nb = bn_bwd_num_blocks(a.N, a.H, a.W, a.C);
-  if (rev > 0) {  // descending traversal (TNB_PINGPONG experiment, net.cu)
-    switch (bn_bwd_cfg(a)) {
-      case 0: bn_bwd_kernel<true, 0, true><<<nb, 256, 0, st>>>(a); break;
-      case 1: bn_bwd_kernel<true, 1, true><<<nb, 256, 0, st>>>(a); break;
-      default: bn_bwd_kernel<true, 2, true><<<nb, 256, 0, st>>>(a); break;
-    }
-  } else
   switch (bn_bwd_cfg(a)) {
-    case 0: bn_bwd_kernel<true, 0><<<nb, 256, 0, st>>>(a); break;
-    case 1: bn_bwd_kernel<true, 1><<<nb, 256, 0, st>>>(a); break;
-    default: bn_bwd_kernel<true, 2><<<nb, 256, 0, st>>>(a); break;
+    case 0: return launch_pdl(bn_bwd_kernel<true, 0>, dim3(nb), dim3(256), 0, st, a);
+    case 1: return launch_pdl(bn_bwd_kernel<true, 1>, dim3(nb), dim3(256), 0, st, a);
+    default: return launch_pdl(bn_bwd_kernel<true, 2>, dim3(nb), dim3(256), 0, st, a);
   }
-  TNB_CHECK_CUDA(cudaGetLastError());
-  return 0;
 }
 __global__ void __launch_bounds__(kFinCh * kFinLanes) bn_bwd_finalize_kernel(const float* __restrict__ part, int rows, int C,
                                                                float* sums, float* dgamma, float* dbeta) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ FinalizeSmem sm;
   const int c = blockIdx.x * kFinCh + threadIdx.x;
   double sa, sb;
@@ -591,7 +623,7 @@ __global__ void __launch_bounds__(kFinCh * kFinLanes) bn_bwd_finalize_kernel(con
 }
 int launch_bn_bwd_finalize(const float* part, int rows, int C, float* sums, float* dgamma, float* dbeta,
                            cudaStream_t st) {
-  bn_bwd_finalize_kernel<<<cdiv(C, kFinCh), dim3(kFinCh, kFinLanes), 0, st>>>(part, rows, C, sums, dgamma, dbeta);
+  if (int rc = launch_pdl(bn_bwd_finalize_kernel, dim3(cdiv(C, kFinCh)), dim3(kFinCh, kFinLanes), 0, st, part, rows, C, sums, dgamma, dbeta)) return rc;
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -617,6 +649,8 @@ __global__ void presplit_bf16_kernel(const float* __restrict__ x, uint8_t* __res
 // redo that arithmetic several times (wgrad: 3 filter rows x Cout/128 tiles) fill their operands with plain copies.
 template <int FMT>
 __global__ void __launch_bounds__(256) view_presplit_kernel(const __grid_constant__ ViewDesc V, uint8_t* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nch = V.C >> 3;
   const long long total = (long long)V.N * V.H * V.W * nch;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -641,8 +675,9 @@ int launch_view_presplit(const ViewDesc& view, void* out, int fmt, cudaStream_t 
   TNB_REQUIRE(view.C % 8 == 0 && view.C0 % 8 == 0, "view_presplit: channel counts must be multiples of 8");
   const long long total = (long long)view.N * view.H * view.W * (view.C / 8);
   const int blocks = min(cdiv(total, 256), 148 * 16);
-  if (fmt == 0) view_presplit_kernel<0><<<blocks, 256, 0, st>>>(view, (uint8_t*)out);
-  else          view_presplit_kernel<1><<<blocks, 256, 0, st>>>(view, (uint8_t*)out);
+  if (int rc = fmt == 0 ? launch_pdl(view_presplit_kernel<0>, dim3(blocks), dim3(256), 0, st, view, (uint8_t*)out)
+                        : launch_pdl(view_presplit_kernel<1>, dim3(blocks), dim3(256), 0, st, view, (uint8_t*)out))
+    return rc;
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -678,6 +713,8 @@ int wbce_num_blocks(long long) { return kWbceBlocks; }
 
 __global__ void __launch_bounds__(256) wbce_fwd_kernel(const float* __restrict__ p, const float* __restrict__ y,
                                                        long long per_sample, double* part) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float* ps = p + (size_t)blockIdx.y * per_sample;
   const float* ys = y + (size_t)blockIdx.y * per_sample;
   float acc = 0.f;
@@ -700,6 +737,8 @@ __global__ void __launch_bounds__(256) wbce_fwd_kernel(const float* __restrict__
 }
 __global__ void __launch_bounds__(256) wbce_final_kernel(const double* part, int nsamples, int nblocks,
                                                          long long per_sample, int reduce, float* out) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one block; fixed summation order => deterministic. sample sums first, then the batch total.
   __shared__ double sd[256];
   double total = 0.0;
@@ -722,15 +761,17 @@ __global__ void __launch_bounds__(256) wbce_final_kernel(const double* part, int
 }
 int launch_wbce_fwd(const float* p, const float* y, int nsamples, long long per_sample, int reduce, double* part,
                     float* out, cudaStream_t st) {
-  wbce_fwd_kernel<<<dim3(kWbceBlocks, nsamples), 256, 0, st>>>(p, y, per_sample, part);
+  if (int rc = launch_pdl(wbce_fwd_kernel, dim3(kWbceBlocks, nsamples), dim3(256), 0, st, p, y, per_sample, part)) return rc;
   TNB_CHECK_CUDA(cudaGetLastError());
-  wbce_final_kernel<<<1, 256, 0, st>>>(part, nsamples, kWbceBlocks, per_sample, reduce, out);
+  if (int rc = launch_pdl(wbce_final_kernel, dim3(1), dim3(256), 0, st, (const double*)part, nsamples, kWbceBlocks, per_sample, reduce, out)) return rc;
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 __global__ void __launch_bounds__(256) wbce_bwd_kernel(const float* __restrict__ p, const float* __restrict__ y,
                                                        const float* __restrict__ gout, long long per_sample,
                                                        int nsamples, int reduce, float* __restrict__ dp) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = per_sample * nsamples;
   const float inv = reduce ? (float)(1.0 / (double)total) : (float)(1.0 / (double)per_sample);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -741,7 +782,7 @@ __global__ void __launch_bounds__(256) wbce_bwd_kernel(const float* __restrict__
 }
 int launch_wbce_bwd(const float* p, const float* y, const float* gout, int nsamples, long long per_sample,
                     int reduce, float* dp, cudaStream_t st) {
-  wbce_bwd_kernel<<<148 * 8, 256, 0, st>>>(p, y, gout, per_sample, nsamples, reduce, dp);
+  if (int rc = launch_pdl(wbce_bwd_kernel, dim3(148 * 8), dim3(256), 0, st, p, y, gout, per_sample, nsamples, reduce, dp)) return rc;
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

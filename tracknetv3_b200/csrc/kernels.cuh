@@ -16,14 +16,14 @@ int launch_bn_finalize(const float* part, int rows, double count, const float* g
                        float* scale, float* shift, float* mean, float* invstd, int C, cudaStream_t st);
 int launch_predictor_fwd(const SrcDesc& src, int N, int H, int W, const float* wp, const float* bias, int O,
                          float* y_nchw, cudaStream_t st);
+size_t predictor_bwd_workspace_bytes(int N, int H, int W, int O);
 int launch_predictor_bwd(const SrcDesc& src, int N, int H, int W, const float* wp, int O, const float* dy,
-                         const float* y, float* dA, float* dwp, float* dbias, cudaStream_t st);
+                         const float* y, float* dA, float* dwp, float* dbias, float* part, cudaStream_t st);
 int bn_bwd_num_blocks(int N, int H, int W, int C);
-// rev: traversal direction of the pass (experiments): < 0 = TNB_BN_REVERSE decides (reduce pass only), 0 = ascending, 1 = descending
-int launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t st, int rev = -1);
+int launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t st);
 int launch_bn_bwd_finalize(const float* part, int rows, int C, float* sums, float* dgamma, float* dbeta,
                            cudaStream_t st);
-int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st, int rev = -1);
+int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st);
 
 int wbce_num_blocks(long long per_sample);
 int launch_wbce_fwd(const float* p, const float* y, int nsamples, long long per_sample, int reduce,

@@ -62,7 +62,8 @@ bool bn_reduce_fusable(int p) {
 }
 struct Plan {
   LayerBuf L[kLayers];
-  float* wgrad_ws;  // scratch: tap-major split-K accumulation buffer of the current layer's weight gradient
+  float* wgrad_ws;  // scratch: split-K slabs of the current layer's weight gradient (deterministic ordered sum)
+  float* pred_ws;   // scratch: per-block partials of the predictor's weight / bias gradient
   uint8_t* vsplit;  // scratch: the current layer's input view materialised as pre-split bf16 (largest: 192 ch @ full res)
   float* amax_all;  // [kLayers] max|dz| per layer, raised atomically by bn_bwd apply
   float* xin;
@@ -99,12 +100,34 @@ int layer_cin(const tnb_tracknet_cfg_t& c, int l) {
   return cin;
 }
 
+// The weight-gradient kernel's view of layer l's input, materialised pre-split (bf16 hi/lo) in `vsplit`: one tensor, or
+// for a decoder concat [up(x), skip] the up-sampled half at ITS OWN (half) resolution - read by the wgrad fill through
+// (h/2, w/2) addressing, a quarter of the bytes of the up-sampled tensor - followed by the skip half.
+ViewDesc wgrad_view(const tnb_tracknet_cfg_t& c, int l, const uint8_t* vsplit) {
+  const LayerDef& d = kDefs[l];
+  const int H = c.h >> d.level, W = c.w >> d.level, cin = layer_cin(c, l);
+  ViewDesc pv;
+  memset(&pv, 0, sizeof(pv));
+  pv.N = c.n; pv.H = H; pv.W = W; pv.C = cin;
+  if (d.src1 >= 0 && d.mode0 == SRC_AFFINE_RELU_UP && d.mode1 == SRC_AFFINE_RELU) {
+    const int c0 = kDefs[d.src0].cout, hs = c.h >> kDefs[d.src0].level, ws = c.w >> kDefs[d.src0].level;
+    const uint8_t* skip = vsplit + (size_t)c.n * hs * ws * c0 * 4;
+    pv.s[0] = SrcDesc{reinterpret_cast<const float*>(vsplit), nullptr, nullptr, c0, hs, ws, SRC_PRESPLIT_UP};
+    pv.s[1] = SrcDesc{reinterpret_cast<const float*>(skip), nullptr, nullptr, cin - c0, H, W, SRC_PRESPLIT};
+    pv.C0 = c0;
+  } else {
+    pv.s[0] = SrcDesc{reinterpret_cast<const float*>(vsplit), nullptr, nullptr, cin, H, W, SRC_PRESPLIT};
+    pv.s[1] = pv.s[0];
+    pv.C0 = cin;
+  }
+  return pv;
+}
+
 int build_plan(const tnb_tracknet_cfg_t& c, void* ws, Plan* P) {
   TNB_REQUIRE(c.n > 0 && c.h > 0 && c.w > 0 && c.h % 8 == 0 && c.w % 8 == 0,
               "tracknet: input %dx%d must be divisible by 8 (reference model.py:59-69 pools 3x then concatenates)",
               c.h, c.w);
-  TNB_REQUIRE(c.in_dim > 0 && c.out_dim > 0 && c.out_dim <= 16, "tracknet: bad in_dim/out_dim %d/%d", c.in_dim,
-              c.out_dim);
+  TNB_REQUIRE(c.in_dim > 0 && c.out_dim > 0, "tracknet: bad in_dim/out_dim %d/%d", c.in_dim, c.out_dim);
   TNB_REQUIRE((c.fwd_terms == 1 || c.fwd_terms == 3) && (c.bwd_terms == 1 || c.bwd_terms == 3),
               "tracknet: terms must be 1 or 3");
   Bump b{reinterpret_cast<uint8_t*>(ws), 0};
@@ -120,8 +143,14 @@ int build_plan(const tnb_tracknet_cfg_t& c, void* ws, Plan* P) {
     }
     P->vsplit = b.take<uint8_t>(vmax * 4);
     size_t wmax = 0;
-    for (int l = 0; l < kLayers; ++l) wmax = std::max(wmax, (size_t)9 * kDefs[l].cout * layer_cin(c, l));
+    for (int l = 0; l < kLayers; ++l) {
+      const ViewDesc pv = wgrad_view(c, l, nullptr);
+      const size_t e = wgrad3x3_ws_floats(pv, kDefs[l].cout);
+      if (e == 0) return -2;
+      wmax = std::max(wmax, e);
+    }
     P->wgrad_ws = b.take<float>(wmax);
+    P->pred_ws = b.take<float>(predictor_bwd_workspace_bytes(c.n, c.h, c.w, c.out_dim) / sizeof(float));
   }
   P->xin = b.take<float>(npix0 * P->cpad);
   P->dA_pred = b.take<float>(npix0 * 64);
@@ -187,6 +216,8 @@ ViewDesc make_view(const Plan& P, const tnb_tracknet_cfg_t& c, int l) {
 
 struct CounterTable { long long* p[kLayers]; };
 __global__ void inc_counters_kernel2(CounterTable t) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x < kLayers) *t.p[threadIdx.x] += 1;
 }
 
@@ -198,29 +229,33 @@ size_t tracknet_workspace_bytes(const tnb_tracknet_cfg_t& c) {
   return P.bytes;
 }
 
-// TNB_PINGPONG=1 (experiment, needs TNB_CONV_LEAN=1 for the convolutions to follow): every kernel walks its tensor in the
-// direction opposite to the kernel that produced its input, so that it starts on what is still in the 126 MB L2.
-// Forward: conv(l) descending for odd l. Backward: reduce(l) and dgrad(l) descending for even (16 - l), apply(l) the opposite.
-static int pingpong_env() {
-  static const int v = [] { const char* e = getenv("TNB_PINGPONG"); return e ? atoi(e) : 0; }();
-  return v;
-}
-
 static int forward_enqueue(const tnb_tracknet_cfg_t& c, const float* x, void* const* params, float* y, void* ws,
                            size_t ws_bytes, cudaStream_t st) {
   Plan P;
   if (int rc = build_plan(c, ws, &P)) return rc;
   TNB_REQUIRE(ws_bytes >= P.bytes, "tracknet_forward: workspace too small (%zu < %zu)", ws_bytes, P.bytes);
   if (int rc = launch_pack_input(x, P.xin, c.n, c.in_dim, c.h, c.w, P.cpad, st)) return rc;
+  // every weight operand of the step in ONE launch: the 17 forward images (fp16 hi/lo) and, when a backward will
+  // follow, the 16 dgrad images (bf16 hi/lo, rotated / transposed) - the parameters do not change in between
+  PackTable pt;
+  pt.n = 0; pt.total = 0;
   for (int l = 0; l < kLayers; ++l) {
     LayerBuf& B = P.L[l];
     const float* w = (const float*)params[l * 6 + 0];
     ConvPlan cp;
     if (int rc = conv3x3_plan(c.n, B.H, B.W, B.cin, B.cout, c.fwd_terms, &cp)) return rc;
-    if (int rc = launch_pack_weights(w, B.wf, B.cout, B.cin_real, 0, 0, cp.BN, st)) return rc;
+    if (int rc = pack_table_add(&pt, w, B.wf, B.cout, B.cin_real, 0, 0, cp.BN)) return rc;
+    if (c.training && l > 0) {
+      const bool fused = P.L[l - 1].fused_rows > 0;
+      if (int rc = conv3x3_plan(c.n, B.H, B.W, B.cout, B.cin, c.bwd_terms, &cp, fused)) return rc;
+      if (int rc = pack_table_add(&pt, w, B.wd, B.cout, B.cin, 1, 1, cp.BN)) return rc;
+    }
+  }
+  if (int rc = launch_pack_table(pt, st)) return rc;
+  for (int l = 0; l < kLayers; ++l) {
+    LayerBuf& B = P.L[l];
     const ViewDesc v = make_view(P, c, l);
-    if (int rc = launch_conv3x3(v, B.wf, B.z, c.training ? B.stat_part : nullptr, B.cout, c.fwd_terms, 0,
-                                (c.variant & 3) | ((pingpong_env() && (l & 1)) ? 1024 : 0), st))
+    if (int rc = launch_conv3x3(v, B.wf, B.z, c.training ? B.stat_part : nullptr, B.cout, c.fwd_terms, 0, c.variant & 3, st))
       return rc;
     if (int rc = launch_bn_finalize(B.stat_part, B.stat_rows, (double)c.n * B.H * B.W, (const float*)params[l * 6 + 1],
                                     (const float*)params[l * 6 + 2], (float*)params[l * 6 + 3],
@@ -231,8 +266,7 @@ static int forward_enqueue(const tnb_tracknet_cfg_t& c, const float* x, void* co
   if (c.training) {
     CounterTable t;
     for (int l = 0; l < kLayers; ++l) t.p[l] = (long long*)params[l * 6 + 5];
-    inc_counters_kernel2<<<1, 32, 0, st>>>(t);
-    TNB_CHECK_CUDA(cudaGetLastError());
+    if (int rc = launch_pdl(inc_counters_kernel2, dim3(1), dim3(32), 0, st, t)) return rc;
   }
   const SrcDesc last = make_src(P, c, kLayers - 1, SRC_AFFINE_RELU);
   return launch_predictor_fwd(last, c.n, c.h, c.w, (const float*)params[kLayers * 6 + 0],
@@ -247,25 +281,17 @@ static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const 
   TNB_REQUIRE(ws_bytes >= P.bytes, "tracknet_backward: workspace too small (%zu < %zu)", ws_bytes, P.bytes);
   const SrcDesc last = make_src(P, c, kLayers - 1, SRC_AFFINE_RELU);
   if (int rc = launch_predictor_bwd(last, c.n, c.h, c.w, (const float*)params[kLayers * 6 + 0], c.out_dim, dy, y,
-                                    P.dA_pred, (float*)grads[kLayers * 3 + 0], (float*)grads[kLayers * 3 + 1], st))
+                                    P.dA_pred, (float*)grads[kLayers * 3 + 0], (float*)grads[kLayers * 3 + 1], P.pred_ws,
+                                    st))
     return rc;
   auto run_wgrad = [&](int layer, const ViewDesc& pv) -> int {
     LayerBuf& W = P.L[layer];
     float* dw = (float*)grads[layer * 3 + 0];
-    if (c.variant & 512) {  // variant bit 512: add the split-K partials straight into dw (ablation of the tap-major buffer)
+    if (c.variant & 512) {  // variant bit 512: split-K partials added straight into dw with atomics (ablation; not deterministic)
       TNB_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)W.cout * W.cin_real * 9, st));
       return launch_wgrad3x3(pv, W.dz, dw, W.cout, W.cin_real, c.bwd_terms, (c.variant >> 2) & 3, st);
     }
     return launch_wgrad3x3(pv, W.dz, dw, W.cout, W.cin_real, c.bwd_terms, (c.variant >> 2) & 3, st, P.wgrad_ws);
-  };
-  auto plain_presplit_view = [&](int layer) {
-    const LayerBuf& W = P.L[layer];
-    ViewDesc pv;
-    memset(&pv, 0, sizeof(pv));
-    pv.N = c.n; pv.H = W.H; pv.W = W.W; pv.C = pv.C0 = W.cin;
-    pv.s[0] = SrcDesc{reinterpret_cast<const float*>(P.vsplit), nullptr, nullptr, W.cin, W.H, W.W, SRC_PRESPLIT};
-    pv.s[1] = pv.s[0];
-    return pv;
   };
   int pending = -1;  // layer whose wgrad waits for its operand from the next BatchNorm-backward apply pass
   for (int l = kLayers - 1; l >= 0; --l) {
@@ -293,60 +319,43 @@ static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const 
     a.N = c.n; a.H = B.H; a.W = B.W; a.C = B.cout;
     a.part = B.bwd_part; a.sums = B.bwd_sums; a.dz = B.dz; a.amax = nullptr; a.dz_format = 1;  // dz -> pre-split bf16
     a.inv_count = (float)(1.0 / ((double)c.n * B.H * B.W));
-    const int pp = pingpong_env();
-    const int red_rev = pp ? (((kLayers - 1 - l) & 1) == 0 ? 1 : 0) : -1;  // -1: TNB_BN_REVERSE decides
     if (B.fused_rows == 0)
-      if (int rc = launch_bn_bwd_reduce(a, st, red_rev)) return rc;
+      if (int rc = launch_bn_bwd_reduce(a, st)) return rc;
     if (int rc = launch_bn_bwd_finalize(B.bwd_part, B.fused_rows > 0 ? B.fused_rows : B.bwd_rows, B.cout, B.bwd_sums,
                                         (float*)grads[l * 3 + 1], (float*)grads[l * 3 + 2], st))
       return rc;
     a.act_presplit = (pending == l + 1) ? P.vsplit : nullptr;
-    if (int rc = launch_bn_bwd_apply(a, st, pp ? 1 - red_rev : -1)) return rc;
+    if (int rc = launch_bn_bwd_apply(a, st)) return rc;
     if (pending == l + 1) {
-      if (int rc = run_wgrad(pending, plain_presplit_view(pending))) return rc;
+      if (int rc = run_wgrad(pending, wgrad_view(c, pending, P.vsplit))) return rc;
       pending = -1;
     }
-    const float* w = (const float*)params[l * 6 + 0];
     if (l > 0) {
       ViewDesc dv;
       memset(&dv, 0, sizeof(dv));
       dv.s[0] = SrcDesc{B.dz, nullptr, nullptr, B.cout, B.H, B.W, SRC_PRESPLIT};
       dv.s[1] = dv.s[0];
       dv.C0 = dv.C = B.cout; dv.N = c.n; dv.H = B.H; dv.W = B.W;
-      ConvPlan cp;
       const LayerBuf* Pp = (l > 0 && P.L[l - 1].fused_rows > 0) ? &P.L[l - 1] : nullptr;  // producer whose reduction rides along
       BnBwdFuse fuse{};
       if (Pp != nullptr) fuse = BnBwdFuse{Pp->z, Pp->scale, Pp->shift, Pp->mean, Pp->invstd};
-      if (int rc = conv3x3_plan(c.n, B.H, B.W, B.cout, B.cin, c.bwd_terms, &cp, Pp != nullptr)) return rc;
-      if (int rc = launch_pack_weights(w, B.wd, B.cout, B.cin, 1, 1, cp.BN, st)) return rc;
+      // B.wd: the dgrad weight image, packed by the forward call of this step
       if (int rc = launch_conv3x3(dv, B.wd, B.din, Pp != nullptr ? Pp->bwd_part : nullptr, B.cin, c.bwd_terms, 1,
-                                  (c.variant & 3) | ((pp && red_rev == 1) ? 1024 : 0), st, Pp != nullptr ? &fuse : nullptr))
+                                  c.variant & 3, st, Pp != nullptr ? &fuse : nullptr))
         return rc;
     }
     if (wgrad_operand_from_bn_bwd(c, l)) { pending = l; continue; }
     // materialise the input view once (bf16 hi/lo), then both wgrad operands are plain copies
     const ViewDesc v = make_view(P, c, l);
-    ViewDesc pv;
-    memset(&pv, 0, sizeof(pv));
-    pv.N = c.n; pv.H = B.H; pv.W = B.W; pv.C = B.cin;
-    if (v.C0 < v.C && v.s[0].mode == SRC_AFFINE_RELU_UP && v.s[1].mode == SRC_AFFINE_RELU) {
-      // decoder concat [up(x), skip]: the up-sampled half is materialised at ITS OWN (half) resolution and read by
-      // the wgrad fill through (h/2, w/2) addressing - a quarter of the bytes of the up-sampled tensor
+    const ViewDesc pv = wgrad_view(c, l, P.vsplit);
+    if (pv.C0 < pv.C) {  // decoder concat [up(x), skip]: two tensors, see wgrad_view
       ViewDesc v0 = v, v1 = v;
       v0.s[0].mode = SRC_AFFINE_RELU; v0.s[1] = v0.s[0]; v0.C0 = v0.C = v.C0; v0.H = v.s[0].Hs; v0.W = v.s[0].Ws;
       v1.s[0] = v.s[1]; v1.s[1] = v.s[1]; v1.C0 = v1.C = v.C - v.C0;
-      uint8_t* up = P.vsplit;
-      uint8_t* skip = P.vsplit + (size_t)c.n * v0.H * v0.W * v0.C * 4;
-      if (int rc = launch_view_presplit(v0, up, 1, st)) return rc;
-      if (int rc = launch_view_presplit(v1, skip, 1, st)) return rc;
-      pv.s[0] = SrcDesc{reinterpret_cast<const float*>(up), nullptr, nullptr, v0.C, v0.H, v0.W, SRC_PRESPLIT_UP};
-      pv.s[1] = SrcDesc{reinterpret_cast<const float*>(skip), nullptr, nullptr, v1.C, B.H, B.W, SRC_PRESPLIT};
-      pv.C0 = v0.C;
+      if (int rc = launch_view_presplit(v0, const_cast<float*>(pv.s[0].ptr), 1, st)) return rc;
+      if (int rc = launch_view_presplit(v1, const_cast<float*>(pv.s[1].ptr), 1, st)) return rc;
     } else {
       if (int rc = launch_view_presplit(v, P.vsplit, 1, st)) return rc;
-      pv.s[0] = SrcDesc{reinterpret_cast<const float*>(P.vsplit), nullptr, nullptr, B.cin, B.H, B.W, SRC_PRESPLIT};
-      pv.s[1] = pv.s[0];
-      pv.C0 = B.cin;
     }
     if (int rc = run_wgrad(l, pv)) return rc;
   }
@@ -490,17 +499,18 @@ int set_graph_replay(int on) {
 }
 
 int tracknet_num_launches(const tnb_tracknet_cfg_t& c, int backward) {
-  if (!backward) return 1 + kLayers * 3 + (c.training ? 1 : 0) + 1;  // pack, (wpack, conv, bn_finalize) x17, counters, predictor
+  const int pred_groups = (c.out_dim + 15) / 16;  // the predictor kernels take 16 output channels per launch
+  // pack_input, pack_weights (all tensors), (conv, bn_finalize) x17, counters, predictor
+  if (!backward) return 1 + 1 + kLayers * 2 + (c.training ? 1 : 0) + pred_groups;
   int fused = 0;
   for (int l = 0; l < kLayers; ++l) fused += ((c.variant & 64) && bn_reduce_fusable(l)) ? 1 : 0;
-  // predictor_bwd, (reduce [unless fused into the next layer's dgrad], finalize, apply, view_presplit, wgrad) x17,
-  // (wpack, dgrad) x16
   int emitted = 0;  // wgrad operands written by the BatchNorm-backward apply pass: no view_presplit launch
   for (int l = 0; l < kLayers; ++l) emitted += wgrad_operand_from_bn_bwd(c, l) ? 1 : 0;
-  // + second view_presplit of the 3 decoder concat layers, + one memset per weight gradient is not a kernel
-  const int scatter = (c.variant & 512) ? 0 : kLayers;  // tap-major weight-gradient buffer -> OIHW, one per layer
-  // predictor backward is two kernels
-  return 2 + kLayers * 5 - fused - emitted + (kLayers - 1) * 2 + 3 + scatter;
+  const int scatter = (c.variant & 512) ? 0 : kLayers;  // split-K slabs -> OIHW, one ordered-sum launch per layer
+  // predictor backward (dA + dW per group, final sum), (reduce [unless fused into the next layer's dgrad], finalize,
+  // apply, wgrad) x17, view_presplit for the layers whose operand the apply pass did not emit (+ the second tensor of
+  // the 3 decoder concat layers), dgrad x16, scatter
+  return 2 * pred_groups + 1 + kLayers * 4 - fused + (kLayers - emitted) + 3 + (kLayers - 1) + scatter;
 }
 
 }  // namespace tnb

@@ -40,7 +40,8 @@ struct WgradArgs {
   int ndy;  // filter rows per CTA: 3 when all 9 taps fit in TMEM (9 * NT <= 512), else 1 (grid.x carries dy)
   int tiles_h, tiles_w, ktiles, ktiles_per_cta, ncot, ncit;
   int ci_tile_base;  // first input-channel tile of this launch (concat views with two gather modes use two launches)
-  float* ws;         // optional tap-major accumulation buffer [9][Cin_view][Cout] (see launch_wgrad_scatter); nullptr: dw
+  float* ws;         // optional split-K slabs [splits][9][Cin_view][Cout] (see wgrad_scatter_kernel); nullptr: atomics into dw
+  long long slab;    // floats per slab = 9 * Cin_view * Cout
 };
 
 template <int MODE> TNB_DEVINL int view_off_t(const SrcDesc& s, int n, int h, int w) {
@@ -107,6 +108,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();  // the prologue above touched shared memory and TMEM only
+  pdl_wait();
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -330,14 +333,19 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
           uint32_t rg[16];
           tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * NT + col0), rg);
           tmem_ld_wait();
-          if (row < cvalid && kt1 > kt0 && !(a.variant & 16)) {
+          if (row < cvalid) {
+            // With a slab buffer every split-K CTA owns its slab: plain stores (lanes = consecutive output channels, one
+            // 128-byte store per warp instruction), summed in split order by wgrad_scatter_kernel - bit-identical from
+            // run to run, like the reference's cudnn.deterministic = True (train.py:205). Without one: atomics into dw.
+            float* slab = a.ws != nullptr ? a.ws + (size_t)blockIdx.y * a.slab : nullptr;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int ci = ci0 + col0 + j;
-              if (a.ws != nullptr)  // lanes = consecutive output channels: one 128-byte reduction per warp instruction
-                atomicAdd(a.ws + ((size_t)(dy0 * 3 + t) * V.C + ci) * a.Cout + co0 + row, __uint_as_float(rg[j]));
-              else if (ci < a.CinReal)
-                atomicAdd(a.dw + ((size_t)(co0 + row) * a.CinReal + ci) * 9 + dy0 * 3 + t, __uint_as_float(rg[j]));
+              const float v = kt1 > kt0 ? __uint_as_float(rg[j]) : 0.f;
+              if (slab != nullptr)
+                slab[((size_t)(dy0 * 3 + t) * V.C + ci) * a.Cout + co0 + row] = v;
+              else if (ci < a.CinReal && kt1 > kt0)
+                atomicAdd(a.dw + ((size_t)(co0 + row) * a.CinReal + ci) * 9 + dy0 * 3 + t, v);
             }
           }
         }
@@ -377,9 +385,6 @@ __host__ __device__ inline int pad_sel(int px, int mode) {
   return px + ((want - r) & 7);
 }
 
-// LEAN (experiment, TNB_WGRAD_LEAN=1): lean issue loop, see wgrad3x3_stacked_kernel / conv_kernel.inc - the issuing warp of
-// this kernel is busy all the time too (ncu source page: ~10 instructions and ~78 clocks per 64-clock MMA).
-template <bool LEAN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     wgrad3x3_pair_kernel(const __grid_constant__ WgradArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -425,6 +430,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -441,32 +448,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         tc_fence_after();
         const uint64_t a_st = a_desc0 + (uint64_t)(s * stage16);
         const uint64_t b_st = b_desc0 + (uint64_t)(s * stage16);
-        if (LEAN) {
-          const uint32_t a_w_st = (uint32_t)a_st, b_w_st = (uint32_t)b_st;  // low descriptor words: start address | LBO << 16
-          const uint32_t a_hi32 = (uint32_t)(a_desc0 >> 32), b_hi32 = (uint32_t)(b_desc0 >> 32);
-          const uint32_t first_acc = kt != kt0 ? 1u : 0u;
-          auto issue = [&](auto terms_tag) {
-            constexpr int TERMS = decltype(terms_tag)::value;
-            if (lead) {
-#pragma unroll
-              for (int dx = 0; dx < 3; ++dx) {
-                const uint32_t d_tmem = tmem_base + dx * 128;
-#pragma unroll
-                for (int r = 0; r < kTileH; ++r) {
-                  const uint32_t a_w = a_w_st + (uint32_t)(r * kTileW);
-                  const uint32_t b_w = b_w_st + (uint32_t)(r * kHaloW + dx);
-                  const uint32_t acc = r != 0 ? 1u : first_acc;
-                  umma_f16_w_pair(d_tmem, a_w, a_hi32, b_w, b_hi32, idesc, acc);
-                  if (TERMS > 1) {
-                    umma_f16_w_pair(d_tmem, a_w + a_lo16, a_hi32, b_w, b_hi32, idesc, 1);
-                    umma_f16_w_pair(d_tmem, a_w, a_hi32, b_w + b_lo16, b_hi32, idesc, 1);
-                  }
-                }
-              }
-            }
-          };
-          if (a.nterms > 1) issue(std::integral_constant<int, 3>{}); else issue(std::integral_constant<int, 1>{});
-        } else
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
           const uint32_t d_tmem = tmem_base + dx * 128;
@@ -575,14 +556,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           uint32_t rg[16];
           tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 128 + col0), rg);
           tmem_ld_wait();
-          if (kt1 > kt0) {
+          {
+            float* slab = a.ws != nullptr ? a.ws + (size_t)blockIdx.y * a.slab : nullptr;  // see wgrad3x3_kernel
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int ci = ci0 + col0 + j;
-              if (a.ws != nullptr)  // lanes = consecutive output channels: one 128-byte reduction per warp instruction
-                atomicAdd(a.ws + ((size_t)(dy0 * 3 + t) * V.C + ci) * a.Cout + co0 + row, __uint_as_float(rg[j]));
-              else if (ci < a.CinReal)
-                atomicAdd(a.dw + ((size_t)(co0 + row) * a.CinReal + ci) * 9 + dy0 * 3 + t, __uint_as_float(rg[j]));
+              const float v = kt1 > kt0 ? __uint_as_float(rg[j]) : 0.f;
+              if (slab != nullptr)
+                slab[((size_t)(dy0 * 3 + t) * V.C + ci) * a.Cout + co0 + row] = v;
+              else if (ci < a.CinReal && kt1 > kt0)
+                atomicAdd(a.dw + ((size_t)(co0 + row) * a.CinReal + ci) * 9 + dy0 * 3 + t, v);
             }
           }
         }
@@ -623,13 +606,10 @@ struct WgradSArgs {
   float* dw;
   int N, H, W, C, Cout, CinReal, P /*planes per ci tile: 8 or 4*/, nterms, ncit, ncot;
   int tiles_h, tiles_w, ktiles, ktiles_per_cta;
-  float* ws;  // optional tap-major accumulation buffer [9][Cout][C] (see launch_wgrad_scatter); nullptr: dw
+  float* ws;  // optional split-K slabs [splits][9][Cout][C] (see wgrad_scatter_kernel); nullptr: atomics into dw
+  long long slab;  // floats per slab = 9 * Cout * C
 };
 
-// LEAN (experiment, TNB_WGRAD_LEAN=1, not yet run on a GPU): the issue loop of the elected thread with the term count
-// compile-time, one branch per K tile and 32-bit descriptor stepping (see the lean path of conv_kernel.inc) - the N = 64
-// MMAs of this kernel last 48 clocks, the generic loop spends ~7 instructions on each.
-template <bool LEAN>
 __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __grid_constant__ WgradSArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
@@ -680,6 +660,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -697,35 +679,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __g
         tc_fence_after();
         const uint64_t a_st = a_desc0 + (uint64_t)(s * stage16);
         const uint64_t b_st = b_desc0 + (uint64_t)(s * stage16);
-        if (LEAN) {
-          const uint32_t a_w_st = (uint32_t)a_st, b_w_st = (uint32_t)b_st;  // low descriptor words: start address | LBO << 16
-          const uint32_t a_hi32 = (uint32_t)(a_desc0 >> 32), b_hi32 = (uint32_t)(b_desc0 >> 32);
-          const uint32_t first_acc = kt != kt0 ? 1u : 0u;
-          auto issue = [&](auto terms_tag) {
-            constexpr int TERMS = decltype(terms_tag)::value;
-            if (lead) {
-              for (int g = 0; g < nacc; g += 3) {  // filter-row group {dy, dy + 1}: halo rows r + dyb
-                const uint32_t a_g = a_w_st + (uint32_t)((g / 3) * 2) * row16;
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                  const uint32_t d_tmem = tmem_base + (uint32_t)(g + dx) * 64;
-#pragma unroll
-                  for (int r = 0; r < kTileH; ++r) {
-                    const uint32_t a_w = a_g + (uint32_t)r * row16 + (uint32_t)dx;
-                    const uint32_t b_w = b_w_st + (uint32_t)(r * kTileW);
-                    const uint32_t acc = r != 0 ? 1u : first_acc;
-                    umma_f16_w(d_tmem, a_w, a_hi32, b_w, b_hi32, idesc, acc);
-                    if (TERMS > 1) {
-                      umma_f16_w(d_tmem, a_w + a_lo16, a_hi32, b_w, b_hi32, idesc, 1);
-                      umma_f16_w(d_tmem, a_w, a_hi32, b_w + b_lo16, b_hi32, idesc, 1);
-                    }
-                  }
-                }
-              }
-            }
-          };
-          if (a.nterms > 1) issue(std::integral_constant<int, 3>{}); else issue(std::integral_constant<int, 1>{});
-        } else
         for (int acc_i = 0; acc_i < nacc; ++acc_i) {  // one accumulator = one chain of 4 rows x nterms MMAs
           const int dx = acc_i % 3, dyb = (acc_i / 3) * 2;
           const uint32_t d_tmem = tmem_base + acc_i * 64;
@@ -823,7 +776,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __g
       for (int acc_i = 0; acc_i < nacc; ++acc_i) {
         const int dx = acc_i % 3;
         const int dy = P == 8 ? (acc_i / 3) * 2 + slot : slot;
-        const bool live = (P == 8 ? (acc_i < 3 || slot == 0) : slot < 3) && ci < a.CinReal && kt1 > kt0;
+        const bool live = (P == 8 ? (acc_i < 3 || slot == 0) : slot < 3) && ci < a.CinReal;
+        float* slab = a.ws != nullptr ? a.ws + (size_t)blockIdx.y * a.slab : nullptr;  // see wgrad3x3_kernel
         for (int col0 = 0; col0 < 64; col0 += 16) {
           uint32_t rg[16];
           tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc_i * 64 + col0), rg);
@@ -831,10 +785,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __g
           if (live) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              if (a.ws != nullptr)  // lanes = consecutive input channels: one 128-byte reduction per warp instruction
-                atomicAdd(a.ws + ((size_t)(dy * 3 + dx) * a.Cout + co0 + col0 + j) * a.C + ci, __uint_as_float(rg[j]));
-              else
-                atomicAdd(a.dw + ((size_t)(co0 + col0 + j) * a.CinReal + ci) * 9 + dy * 3 + dx, __uint_as_float(rg[j]));
+              const float v = kt1 > kt0 ? __uint_as_float(rg[j]) : 0.f;
+              if (slab != nullptr)  // lanes = consecutive input channels: one 128-byte store per warp instruction
+                slab[((size_t)(dy * 3 + dx) * a.Cout + co0 + col0 + j) * a.C + ci] = v;
+              else if (kt1 > kt0)
+                atomicAdd(a.dw + ((size_t)(co0 + col0 + j) * a.CinReal + ci) * 9 + dy * 3 + dx, v);
             }
           }
         }
@@ -860,59 +815,31 @@ static bool stacked_applicable(const ViewDesc& view, int Cout) {
   return ok0 && ok1;
 }
 
-// dw[co][ci][tap] = ws[...]: the tap-major accumulation buffer back to the reference's OIHW layout (plain stores).
-// layout 0: ws[tap][ci][co] (generic kernel), layout 1: ws[tap][co][ci] (stacked kernel); ci over the padded view channels.
+// dw[co][ci][tap] = sum over the split-K slabs, in split order (fixed order: the result is bit-identical from run to run),
+// written to the reference's OIHW layout with plain stores.
+// layout 0: slab[tap][ci][co] (generic / pair kernel), layout 1: slab[tap][co][ci] (stacked kernel); ci over the padded
+// view channels.
 __global__ void __launch_bounds__(256) wgrad_scatter_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cout,
-                                                            int Cin, int CinReal, int layout) {
+                                                            int Cin, int CinReal, int layout, int splits) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)9 * Cout * Cin;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int tap = (int)(i / ((long long)Cout * Cin));
     const int r = (int)(i - (long long)tap * Cout * Cin);
     const int co = layout == 0 ? r % Cout : r / Cin, ci = layout == 0 ? r / Cout : r % Cin;
-    if (ci < CinReal) dw[((size_t)co * CinReal + ci) * 9 + tap] = ws[i];
+    if (ci < CinReal) {
+      float acc = 0.f;
+      for (int sp = 0; sp < splits; ++sp) acc += ws[(size_t)sp * total + i];
+      dw[((size_t)co * CinReal + ci) * 9 + tap] = acc;
+    }
   }
 }
-static int launch_wgrad_scatter(const float* ws, float* dw, int Cout, int Cin, int CinReal, int layout, cudaStream_t st) {
+static int launch_wgrad_scatter(const float* ws, float* dw, int Cout, int Cin, int CinReal, int layout, int splits,
+                                cudaStream_t st) {
   const long long total = (long long)9 * Cout * Cin;
-  wgrad_scatter_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 8), 256, 0, st>>>(ws, dw, Cout, Cin, CinReal,
-                                                                                              layout);
-  TNB_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
-static int launch_wgrad3x3_stacked(const ViewDesc& view, const void* dz_presplit, float* dw, int Cout, int CinReal,
-                                   int nterms, cudaStream_t st, float* ws) {
-  WgradSArgs a;
-  a.ws = ws;
-  a.view = reinterpret_cast<const uint8_t*>(view.s[0].ptr); a.dz = (const uint8_t*)dz_presplit; a.dw = dw;
-  a.view1 = reinterpret_cast<const uint8_t*>(view.C0 < view.C ? view.s[1].ptr : view.s[0].ptr);
-  a.C0 = view.C0; a.Cs0 = view.s[0].C; a.Cs1 = view.C0 < view.C ? view.s[1].C : view.s[0].C;
-  a.up0 = view.s[0].mode == SRC_PRESPLIT_UP ? 1 : 0; a.Hs0 = view.s[0].Hs; a.Ws0 = view.s[0].Ws;
-  a.N = view.N; a.H = view.H; a.W = view.W; a.C = view.C; a.Cout = Cout; a.CinReal = CinReal; a.nterms = nterms;
-  a.P = view.C == 32 ? 4 : 8;
-  a.ncit = view.C / (a.P * 8); a.ncot = Cout / 64;
-  a.tiles_h = (view.H + kTileH - 1) / kTileH;
-  a.tiles_w = (view.W + kTileW - 1) / kTileW;
-  a.ktiles = view.N * a.tiles_h * a.tiles_w;
-  const int gx = a.ncit * a.ncot;
-  int splits = 148 / gx;
-  if (splits > (a.ktiles + 7) / 8) splits = (a.ktiles + 7) / 8;
-  if (splits < 1) splits = 1;
-  a.ktiles_per_cta = (a.ktiles + splits - 1) / splits;
-  splits = (a.ktiles + a.ktiles_per_cta - 1) / a.ktiles_per_cta;
-  const int TP = nterms > 1 ? 2 : 1;
-  const size_t smem = kHdrBytes + kSStages * (size_t)(TP * kSRows * a.P * kSRP + TP * 8 * pad_px(kTileH * kTileW) * 16);
-  TNB_REQUIRE(smem <= 232448, "wgrad3x3 (stacked): shared memory plan too large (%zu)", smem);
-  static const int lean_env = [] { const char* e = getenv("TNB_WGRAD_LEAN"); return e ? atoi(e) : 0; }();
-  TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_stacked_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_stacked_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ProfScope prof(PROF_WGRAD, st, view.N, view.H, view.W, view.C, Cout);
-  if (ws != nullptr) TNB_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 9 * (size_t)Cout * view.C, st));
-  if (lean_env) wgrad3x3_stacked_kernel<true><<<dim3(gx, splits), kThreads, smem, st>>>(a);
-  else          wgrad3x3_stacked_kernel<false><<<dim3(gx, splits), kThreads, smem, st>>>(a);
-  TNB_CHECK_CUDA(cudaGetLastError());
-  if (ws != nullptr) return launch_wgrad_scatter(ws, dw, Cout, view.C, CinReal, 1, st);
-  return 0;
+  return launch_pdl(wgrad_scatter_kernel, dim3((unsigned)std::min<long long>((total + 255) / 256, 148 * 8)), dim3(256), 0, st,
+                    ws, dw, Cout, Cin, CinReal, layout, splits);
 }
 
 // input-channel tile: divides Cin and (for concat views) the first source, so that a CTA's channels come from ONE
@@ -924,76 +851,118 @@ static int pick_nt(int cin, int c0) {
   return 0;
 }
 
+// Which kernel, which tiling, how many split-K CTAs: shared by the launcher and the scratch-size query.
+struct WgradPlan {
+  int kind;  // 0 single-CTA generic, 1 CTA pair, 2 tap-stacked
+  int NT, ndy, ncot, ncit, P, gx, splits, ktiles, ktiles_per_cta, tiles_h, tiles_w, mode0, mode1;
+};
+static int plan_wgrad(const ViewDesc& view, int Cout, int variant, WgradPlan* p) {
+  TNB_REQUIRE(view.C % 32 == 0 && Cout % 64 == 0, "wgrad3x3: unsupported channels Cin=%d Cout=%d", view.C, Cout);
+  p->tiles_h = (view.H + kTileH - 1) / kTileH;
+  p->tiles_w = (view.W + kTileW - 1) / kTileW;
+  p->ktiles = view.N * p->tiles_h * p->tiles_w;
+  auto canon = [](int m) { return m == SRC_PRESPLIT_UP ? (int)SRC_PRESPLIT : m; };
+  p->mode0 = canon(view.s[0].mode);
+  p->mode1 = canon((view.C0 < view.C) ? view.s[1].mode : view.s[0].mode);
+  p->NT = 0; p->ndy = 1; p->P = 0;
+  if (!(variant & 32) && stacked_applicable(view, Cout)) {  // variant bit 32: force the generic kernel (tests, ablation)
+    p->kind = 2;
+    p->P = view.C == 32 ? 4 : 8;
+    p->ncit = view.C / (p->P * 8); p->ncot = Cout / 64;
+    p->gx = p->ncit * p->ncot;
+  } else {
+    p->NT = pick_nt(view.C, view.C0);
+    TNB_REQUIRE(p->NT > 0, "wgrad3x3: no input-channel tile for Cin=%d (first source %d)", view.C, view.C0);
+    p->ncot = (Cout + 127) / 128;
+    p->ncit = view.C / p->NT;
+    p->ndy = (9 * p->NT <= 512) ? 3 : 1;
+    p->gx = p->ncot * p->ncit * (3 / p->ndy);
+    // CTA pairs (cta_group::2) share the view operand: 256 output channels x one 128-channel input tile per pair.
+    // variant bit 64 / TNB_WGRAD_PAIR=0 force the single-CTA kernel (tests, ablation).
+    static const int pair_env = [] { const char* e = getenv("TNB_WGRAD_PAIR"); return e ? atoi(e) : 1; }();
+    p->kind = (pair_env && !(variant & 64) && Cout % 256 == 0 && p->NT == 128 && p->ndy == 1 && p->mode0 == SRC_PRESPLIT &&
+               p->mode1 == SRC_PRESPLIT) ? 1 : 0;
+  }
+  // split the pixel (K) range so that the grid is ~1 wave of 148 SMs (every CTA ends with its epilogue stores, so
+  // fewer, longer CTAs are better), each CTA owning >= 8 K tiles; never more CTAs than SMs: a 149th would cost a second wave
+  int splits = 148 / p->gx;
+  if (splits > (p->ktiles + 7) / 8) splits = (p->ktiles + 7) / 8;
+  if (splits < 1) splits = 1;
+  p->ktiles_per_cta = (p->ktiles + splits - 1) / splits;
+  p->splits = (p->ktiles + p->ktiles_per_cta - 1) / p->ktiles_per_cta;  // every split owns at least one K tile
+  return 0;
+}
+size_t wgrad3x3_ws_floats(const ViewDesc& view, int Cout) {
+  WgradPlan p;
+  if (plan_wgrad(view, Cout, 0, &p)) return 0;
+  return (size_t)p.splits * 9 * Cout * view.C;
+}
+
+static int launch_wgrad3x3_stacked(const ViewDesc& view, const void* dz_presplit, float* dw, int Cout, int CinReal,
+                                   int nterms, const WgradPlan& p, cudaStream_t st, float* ws) {
+  WgradSArgs a;
+  a.ws = ws; a.slab = (long long)9 * Cout * view.C;
+  a.view = reinterpret_cast<const uint8_t*>(view.s[0].ptr); a.dz = (const uint8_t*)dz_presplit; a.dw = dw;
+  a.view1 = reinterpret_cast<const uint8_t*>(view.C0 < view.C ? view.s[1].ptr : view.s[0].ptr);
+  a.C0 = view.C0; a.Cs0 = view.s[0].C; a.Cs1 = view.C0 < view.C ? view.s[1].C : view.s[0].C;
+  a.up0 = view.s[0].mode == SRC_PRESPLIT_UP ? 1 : 0; a.Hs0 = view.s[0].Hs; a.Ws0 = view.s[0].Ws;
+  a.N = view.N; a.H = view.H; a.W = view.W; a.C = view.C; a.Cout = Cout; a.CinReal = CinReal; a.nterms = nterms;
+  a.P = p.P; a.ncit = p.ncit; a.ncot = p.ncot;
+  a.tiles_h = p.tiles_h; a.tiles_w = p.tiles_w; a.ktiles = p.ktiles; a.ktiles_per_cta = p.ktiles_per_cta;
+  const int TP = nterms > 1 ? 2 : 1;
+  const size_t smem = kHdrBytes + kSStages * (size_t)(TP * kSRows * a.P * kSRP + TP * 8 * pad_px(kTileH * kTileW) * 16);
+  TNB_REQUIRE(smem <= 232448, "wgrad3x3 (stacked): shared memory plan too large (%zu)", smem);
+  TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_stacked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope prof(PROF_WGRAD, st, view.N, view.H, view.W, view.C, Cout);
+  if (int rc = launch_pdl(wgrad3x3_stacked_kernel, dim3(p.gx, p.splits), dim3(kThreads), smem, st, a)) return rc;
+  if (ws != nullptr) return launch_wgrad_scatter(ws, dw, Cout, view.C, CinReal, 1, p.splits, st);
+  return 0;
+}
+
 int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, int Cout, int CinReal, int nterms,
                     int variant, cudaStream_t st, float* ws) {
-  TNB_REQUIRE(view.C % 32 == 0 && Cout % 64 == 0, "wgrad3x3: unsupported channels Cin=%d Cout=%d", view.C, Cout);
-  if (!(variant & 32) && stacked_applicable(view, Cout))  // variant bit 32: force the generic kernel (tests, ablation)
-    return launch_wgrad3x3_stacked(view, dz_presplit, dw, Cout, CinReal, nterms, st, ws);
+  WgradPlan p;
+  if (int rc = plan_wgrad(view, Cout, variant, &p)) return rc;
+  if (p.kind == 2) return launch_wgrad3x3_stacked(view, dz_presplit, dw, Cout, CinReal, nterms, p, st, ws);
   WgradArgs a;
-  a.ws = ws;
-  if (ws != nullptr) TNB_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 9 * (size_t)Cout * view.C, st));
+  a.ws = ws; a.slab = (long long)9 * Cout * view.C;
   a.view = view; a.dz = (const uint8_t*)dz_presplit; a.dw = dw; a.Cout = Cout; a.CinReal = CinReal;
   a.nterms = nterms; a.variant = variant; a.ci_tile_base = 0;
-  a.NT = pick_nt(view.C, view.C0);
-  TNB_REQUIRE(a.NT > 0, "wgrad3x3: no input-channel tile for Cin=%d (first source %d)", view.C, view.C0);
-  a.tiles_h = (view.H + kTileH - 1) / kTileH;
-  a.tiles_w = (view.W + kTileW - 1) / kTileW;
-  a.ktiles = view.N * a.tiles_h * a.tiles_w;
-  a.ncot = (Cout + 127) / 128;
-  a.ncit = view.C / a.NT;
-  a.ndy = (9 * a.NT <= 512) ? 3 : 1;
-  const int gx = a.ncot * a.ncit * (3 / a.ndy);
-  // split the pixel (K) range so that the grid is ~1 wave of 148 SMs (every CTA ends with 128 x NT x 3 atomics,
-  // so fewer, longer CTAs are better), each CTA owning >= 8 K tiles
-  int splits = 148 / gx;  // never more CTAs than SMs: a 149th CTA would cost a whole second wave
-  if (splits > (a.ktiles + 7) / 8) splits = (a.ktiles + 7) / 8;
-  if (splits < 1) splits = 1;
-  a.ktiles_per_cta = (a.ktiles + splits - 1) / splits;
-  splits = (a.ktiles + a.ktiles_per_cta - 1) / a.ktiles_per_cta;
+  a.NT = p.NT; a.tiles_h = p.tiles_h; a.tiles_w = p.tiles_w; a.ktiles = p.ktiles; a.ncot = p.ncot; a.ncit = p.ncit;
+  a.ndy = p.ndy; a.ktiles_per_cta = p.ktiles_per_cta;
+  const int gx = p.gx, splits = p.splits;
   const int TP = nterms > 1 ? 2 : 1;
-  auto canon = [](int m) { return m == SRC_PRESPLIT_UP ? (int)SRC_PRESPLIT : m; };
-  const int mode0 = canon(view.s[0].mode), mode1 = canon((view.C0 < view.C) ? view.s[1].mode : view.s[0].mode);
+  const int mode0 = p.mode0, mode1 = p.mode1;
   ProfScope prof(PROF_WGRAD, st, view.N, view.H, view.W, view.C, Cout);
-  // CTA pairs (cta_group::2) share the view operand: 256 output channels x one 128-channel input tile per pair.
-  // variant bit 64 / TNB_WGRAD_PAIR=0 force the single-CTA kernel (tests, ablation).
-  static const int pair_env = [] { const char* e = getenv("TNB_WGRAD_PAIR"); return e ? atoi(e) : 1; }();
-  if (pair_env && !(variant & 64) && Cout % 256 == 0 && a.NT == 128 && a.ndy == 1 && mode0 == SRC_PRESPLIT &&
-      mode1 == SRC_PRESPLIT) {
+  if (p.kind == 1) {
     const int padm = (variant >> 7) & 3;
     const size_t psmem = kHdrBytes + kPStages * (size_t)(TP * 16 * pad_sel(kTileH * kTileW, padm) * 16 +
                                                          TP * 8 * pad_sel(kTileH * kHaloW, padm) * 16);
     TNB_REQUIRE(psmem <= 232448, "wgrad3x3 (pair): shared memory plan too large (%zu)", psmem);
-    static const int lean_env = [] { const char* e = getenv("TNB_WGRAD_LEAN"); return e ? atoi(e) : 0; }();
-    TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-    TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+    TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
     // gx = ncot * ncit * 3 with ncot even
-    if (lean_env) wgrad3x3_pair_kernel<true><<<dim3(gx, splits), kThreads, psmem, st>>>(a);
-    else          wgrad3x3_pair_kernel<false><<<dim3(gx, splits), kThreads, psmem, st>>>(a);
-    TNB_CHECK_CUDA(cudaGetLastError());
-    if (ws != nullptr) return launch_wgrad_scatter(ws, dw, Cout, view.C, CinReal, 0, st);
+    if (int rc = launch_pdl(wgrad3x3_pair_kernel, dim3(gx, splits), dim3(kThreads), psmem, st, a)) return rc;
+    if (ws != nullptr) return launch_wgrad_scatter(ws, dw, Cout, view.C, CinReal, 0, splits, st);
     return 0;
   }
   const size_t smem = kHdrBytes + kStages * (size_t)(TP * 16 * pad_px(kTileH * kTileW) * 16 +
                                                      TP * (a.NT / 8) * pad_px((kTileH + a.ndy - 1) * kHaloW) * 16);
   TNB_REQUIRE(smem <= 232448, "wgrad3x3: shared memory plan too large (%zu)", smem);
   // one gather mode per launch: a concat view whose two halves use different modes is split by the channel tiling
-  // (pick_nt keeps every CTA inside one source), but the kernel is instantiated per mode -> require equal modes or
-  // fall back to the first source's mode only when the second source is unused
+  // (pick_nt keeps every CTA inside one source), but the kernel is instantiated per mode.
   // a half-resolution pre-split source differs from a full-resolution one by an address shift only: same instantiation
-  auto launch = [&](auto tag, const WgradArgs& args, int gx_first, int gx_count) -> int {
+  auto launch = [&](auto tag, const WgradArgs& args, int gx_count) -> int {
     constexpr int M = decltype(tag)::value;
     TNB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    (void)gx_first;
-    wgrad3x3_kernel<M><<<dim3(gx_count, splits), kThreads, smem, st>>>(args);
-    return 0;
+    return launch_pdl(wgrad3x3_kernel<M>, dim3(gx_count, splits), dim3(kThreads), smem, st, args);
   };
   auto dispatch = [&](int mode, const WgradArgs& args, int gx_count) -> int {
     switch (mode) {
-      case SRC_IDENTITY: return launch(std::integral_constant<int, SRC_IDENTITY>{}, args, 0, gx_count);
-      case SRC_AFFINE_RELU: return launch(std::integral_constant<int, SRC_AFFINE_RELU>{}, args, 0, gx_count);
-      case SRC_AFFINE_RELU_POOL: return launch(std::integral_constant<int, SRC_AFFINE_RELU_POOL>{}, args, 0, gx_count);
-      case SRC_AFFINE_RELU_UP: return launch(std::integral_constant<int, SRC_AFFINE_RELU_UP>{}, args, 0, gx_count);
-      case SRC_PRESPLIT: return launch(std::integral_constant<int, SRC_PRESPLIT>{}, args, 0, gx_count);
+      case SRC_IDENTITY: return launch(std::integral_constant<int, SRC_IDENTITY>{}, args, gx_count);
+      case SRC_AFFINE_RELU: return launch(std::integral_constant<int, SRC_AFFINE_RELU>{}, args, gx_count);
+      case SRC_AFFINE_RELU_POOL: return launch(std::integral_constant<int, SRC_AFFINE_RELU_POOL>{}, args, gx_count);
+      case SRC_AFFINE_RELU_UP: return launch(std::integral_constant<int, SRC_AFFINE_RELU_UP>{}, args, gx_count);
+      case SRC_PRESPLIT: return launch(std::integral_constant<int, SRC_PRESPLIT>{}, args, gx_count);
       default: tnb::set_last_error("wgrad3x3: bad view mode %d", mode); return -2;
     }
   };
@@ -1010,8 +979,7 @@ int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, in
     if (int rc = dispatch(mode0, a0, a.ncot * a0.ncit * (3 / a.ndy))) return rc;
     if (int rc = dispatch(mode1, a1, a.ncot * a1.ncit * (3 / a.ndy))) return rc;
   }
-  TNB_CHECK_CUDA(cudaGetLastError());
-  if (ws != nullptr) return launch_wgrad_scatter(ws, dw, Cout, view.C, CinReal, 0, st);
+  if (ws != nullptr) return launch_wgrad_scatter(ws, dw, Cout, view.C, CinReal, 0, splits, st);
   return 0;
 }
 
