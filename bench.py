@@ -8,13 +8,23 @@ Workload (BASELINE.json configs[1]): TrackNet seq_len 8, bg_mode concat (in 27 /
 per GPU, 288x512, one "step" = forward + WBCELoss + backward (reference train.py:92-95) on synthetic frames
 and binary-disc labels (reference dataset.py:401-410). frames = batch x seq_len.
 
-Printed JSON (one line, rank 0): value = frames/s with inputs resident in HBM; e2e = the same step through
-the reference-facing modules with pinned-host inputs copied H2D every step and loss.item() read back;
-roofline = the tcgen05 conv kernel's algorithmic TFLOP/s from per-launch CUDA events (the same steps repeated once
-more right after the timed region, which itself runs as CUDA-graph replays) against the measured dense bf16 peak; cpu_baseline = the oracle port of the reference on the host cores.
+Printed JSON (one line, rank 0):
+  value        frames/s with the fp32 input stack and labels resident in HBM (CUDA events, max over ranks);
+  e2e          the same step through the public modules starting from HOST data every step: uint8 frames + integer
+               label centres in pinned memory -> H2D on a copy stream (DevicePrefetcher) -> FramePreprocessor (resize /
+               stack / 255 on the GPU) -> label_discs -> TrackNet -> WBCELoss -> backward -> loss.item();
+  roofline     the tcgen05 conv kernel's algorithmic TFLOP/s from per-launch CUDA events (the same steps repeated once
+               more right after the timed region, which itself runs as CUDA-graph replays) against the measured dense
+               bf16 peak; `traffic` from the committed ncu pass, refused (null) when the kernel sources changed since;
+  train_step   the secondary region of SURVEY.md 8(d): zero_grad + mixup + forward + loss + .item() + backward + FusedAdam
+               (reference train.py:85-96), with the Adam / mixup kernels' own HBM fractions;
+  torch_cuda_baseline  the reference architecture on stock torch-CUDA on the same box right after (the >= 6x target's
+               denominator): torch defaults as the reference runs them, strict fp32, best-effort torch;
+  cpu_baseline the oracle port of the reference on the host cores (a reported baseline, not the target).
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -27,30 +37,48 @@ sys.path.insert(0, ROOT)
 
 METRIC = "frames/sec TrackNet seq_len=8 288x512 bs=10 fwd+bwd"
 SEQ_LEN, IN_DIM, OUT_DIM, BATCH, H, W = 8, 27, 8, 10, 288, 512
+WORKLOAD = "TrackNet seq_len=8 bg=concat (27->8 ch) 288x512 fwd+WBCE+bwd, BASELINE configs[1]"
 
 # (cin, cout, level) of the 17 3x3 convolutions, reference model.py:47-53 (SURVEY.md §8a layer table)
 LAYERS = [(IN_DIM, 64, 0), (64, 64, 0), (64, 128, 1), (128, 128, 1), (128, 256, 2), (256, 256, 2), (256, 256, 2),
           (256, 512, 3), (512, 512, 3), (512, 512, 3), (768, 256, 2), (256, 256, 2), (256, 256, 2), (384, 128, 1),
           (128, 128, 1), (192, 64, 0), (64, 64, 0)]
+# sources whose change invalidates the committed per-kernel DRAM traffic of the conv kernel
+TRAFFIC_SOURCES = ["conv_kernel.inc", "conv.cu", "conv_lean.cu", "common.cuh", "igemm.cuh"]
 
 
 def conv_flops(n, cin, cout, level):
     return 2.0 * n * (H >> level) * (W >> level) * cin * cout * 9
 
 
+def synthetic_host_batch(n, seed):
+    """What a loader holds on the host for one batch: uint8 RGB frames (n, L, H, W, 3), one uint8 median frame
+    (H, W, 3) and the integer label centres (n, L, 2), ~15 % of them (0, 0) = "no shuttlecock" (dataset.py:402-403)."""
+    import numpy as np
+    import torch
+    rng = np.random.default_rng(seed)
+    frames = torch.from_numpy(rng.integers(0, 256, size=(n, SEQ_LEN, H, W, 3), dtype=np.uint8))
+    median = torch.from_numpy(rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8))
+    centers = np.stack([rng.integers(0, W, size=(n, SEQ_LEN)), rng.integers(0, H, size=(n, SEQ_LEN))], -1).astype(np.int32)
+    centers[rng.random((n, SEQ_LEN)) < 0.15] = 0
+    return frames, median, torch.from_numpy(centers)
+
+
 def synthetic_batch(n, seed):
-    """x ~ U[0,1) like /255 frames; y = radius-2.5 binary discs at random centres, ~15% empty maps."""
+    """The same batch as fp32 tensors on the host, the way the reference's dataset hands it to the step (x = stacked
+    frames / 255 with the median first, y = radius-2.5 discs): input of the CPU arm and of the torch-CUDA baseline."""
     import numpy as np
     import torch
     from oracle.tracknet_oracle import label_disc  # label rule only (dataset.py:401-410); not on the timed path
-    g = torch.Generator().manual_seed(seed)
-    x = torch.rand(n, IN_DIM, H, W, generator=g)
-    rng = np.random.default_rng(seed)
+    frames, median, centers = synthetic_host_batch(n, seed)
+    x = torch.cat([median.permute(2, 0, 1).unsqueeze(0).expand(n, 3, H, W),
+                   frames.permute(0, 1, 4, 2, 3).reshape(n, SEQ_LEN * 3, H, W)], dim=1).double().div(255.).float()
     y = np.zeros((n, OUT_DIM, H, W), dtype=np.float32)
     for i in range(n):
         for f in range(OUT_DIM):
-            if rng.random() > 0.15:
-                y[i, f] = label_disc(int(rng.integers(0, W)), int(rng.integers(0, H)))
+            cx, cy = int(centers[i, f, 0]), int(centers[i, f, 1])
+            if cx != 0 or cy != 0:
+                y[i, f] = label_disc(cx, cy)
     return x, torch.from_numpy(y)
 
 
@@ -61,6 +89,29 @@ def load_peaks():
         return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))),
                     hbm=float(d.get("hbm_gbs", 6650.0)), source="measured (MEASURED_PEAKS.json, sustained bf16)")
     return dict(tflops=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md, sustained)")
+
+
+def sources_sha():
+    h = hashlib.sha256()
+    for fn in TRAFFIC_SOURCES:
+        h.update(open(os.path.join(ROOT, "tracknetv3_b200", "csrc", fn), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def committed_traffic(precision):
+    """Mean DRAM read+write bytes per conv launch from the newest committed ncu pass - only if that pass was taken on
+    the kernel sources of THIS tree (profiles/kernel_metrics_r*.json carry the hash); otherwise (None, why)."""
+    cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("kernel_metrics_r") and f.endswith(".json"))
+    if not cands or precision != "fp32x3":
+        return None, "no committed ncu pass for this precision"
+    path = os.path.join("profiles", cands[-1])
+    km = json.load(open(os.path.join(ROOT, path)))
+    meta = km.get("_meta", {})
+    if meta.get("sources_sha") != sources_sha():
+        return None, f"{path} is stale: taken on other kernel sources (sha {meta.get('sources_sha')} != {sources_sha()})"
+    conv = [v for k, v in km.items() if k.startswith("conv3x3")]
+    traffic = sum(v["dram_bytes_per_launch"] * v["launches"] for v in conv) / sum(v["launches"] for v in conv)
+    return traffic, f"{path} (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per conv launch; HEAD {meta.get('head')})"
 
 
 class ClockSampler:
@@ -100,13 +151,22 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_step_rate(steps, warmup, batch=1):
-    """The reference algorithm (oracle port: plain torch CPU fp32, all host threads) on a bounded sample:
-    `batch` samples of the same 288x512 seq_len-8 workload per step. Returns (frames/s, ms/step, cores)."""
+def host_threads():
+    """Threads for the CPU arm: every core this process may run on, whatever the launcher put into OMP_NUM_THREADS
+    (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_reference_step_rate(steps, warmup, batch, threads=None):
+    """The reference algorithm (oracle port: plain torch CPU fp32) on `batch` samples of the same 288x512 seq_len-8
+    workload per step. Returns (frames/s, ms/step, threads)."""
     import torch
     from oracle import tracknet_oracle as O
-    # torch's default intra-op pool = the physical cores it detects; oversubscribing all SMT siblings of a big
-    # host makes these small convolutions slower, so the default is "all the threads torch will use"
+    if threads is not None:
+        torch.set_num_threads(threads)
     cores = torch.get_num_threads()
     sd = O.init_tracknet_state(13, IN_DIM, OUT_DIM)
     x, y = synthetic_batch(batch, 13)
@@ -120,16 +180,33 @@ def cpu_reference_step_rate(steps, warmup, batch=1):
 
 
 def run_reference_arm(args, rank):
+    """`--impl reference`: the reference's algorithm on the host cores (the reference is pure Python / PyTorch with no
+    package to install: the arm runs the oracle port, pinned to the real reference by tests/golden). Same metric, unit
+    and config as the GPU arm; K timed + W warm-up steps as asked; each step is a bounded sample of the bs-10 workload -
+    as many samples per step (10, 5, 2 or 1) as keep the whole run within a few minutes on this host."""
     if rank != 0:
         return
-    steps, warmup = min(args.steps, 8), min(args.warmup, 2)
-    fps, ms, cores = cpu_reference_step_rate(steps, warmup, batch=1)
-    sample = f"bs=1 of the bs={BATCH} workload per step ({steps} timed + {warmup} warm-up steps), torch CPU fp32, {cores} threads"
+    os.environ.pop("OMP_NUM_THREADS", None)  # torchrun's per-worker default of 1 is not this arm's thread count
+    threads = host_threads()
+    steps, warmup = max(args.steps, 1), max(args.warmup, 0)
+    batch = args.cpu_batch
+    if batch <= 0:
+        _, ms1, _ = cpu_reference_step_rate(1, 1, 1, threads)     # probe: one sample, after one warm-up
+        budget_s = 150.0
+        batch = 1
+        for b in (10, 5, 2):
+            if (steps + warmup) * b * ms1 * 1e-3 <= budget_s:
+                batch = b
+                break
+    fps, ms, cores = cpu_reference_step_rate(steps, warmup, batch, threads)
+    sample = (f"bs={batch} of the bs={BATCH} workload per step ({steps} timed + {warmup} warm-up steps), torch CPU fp32 "
+              f"(oracle port of the reference), {cores} threads")
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "TrackNet seq_len=8 bg=concat 288x512 fwd+WBCE+bwd (configs[1])",
-                       "global_batch": 1, "note": "reference is pure Python/PyTorch: CPU arm = oracle port"},
+            "config": {"workload": WORKLOAD, "global_batch": BATCH * args.gpus, "per_gpu_batch": BATCH,
+                       "parallelism": f"dp{args.gpus}", "precision": args.precision,
+                       "l2": "working set ~10 GB per step >> 126 MB L2 (inputs larger than L2; no explicit flush)"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -141,10 +218,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="fp32x3", choices=["fp32x3", "tf32like"])
+    ap.add_argument("--precision", default="fp32x3", choices=["fp32x3", "tf32like", "fp32x3_bwd1"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-torch-baseline", action="store_true", help="skip the torch-CUDA reference-architecture timing")
     ap.add_argument("--per-launch", action="store_true", help="print the mean duration of every profiled launch to stderr")
     ap.add_argument("--variant", type=int, default=0, help="kernel experiment bits (tnb_tracknet_cfg_t.variant)")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="samples per step of the CPU arm (0 = as many of 10 as fit the time budget)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -152,6 +231,7 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args, rank)
 
+    import numpy as np
     import torch
     import torch.distributed as dist
     import tracknetv3_b200 as T
@@ -166,14 +246,23 @@ def main():
     warmup = max(args.warmup, 3)
 
     torch.manual_seed(13)  # reference train.py:195 default seed
+    np.random.seed(13)
     model = T.TrackNet(IN_DIM, OUT_DIM, precision=args.precision).cuda().train()
     model._variant = args.variant
     if world > 1:
         broadcast_module(model)
     bucket = GradBucket(model)
-    x_host, y_host = synthetic_batch(BATCH, 13 + rank)
-    x_pin, y_pin = x_host.pin_memory(), y_host.pin_memory()
-    x_dev, y_dev = x_pin.cuda(), y_pin.cuda()
+    frames_h, median_h, centers_h = synthetic_host_batch(BATCH, 13 + rank)
+    frames_pin, median_pin, centers_pin = frames_h.pin_memory(), median_h.pin_memory(), centers_h.pin_memory()
+    fp = T.FramePreprocessor(H, W, H, W)
+
+    def stage(frames_d, median_d, centers_d):
+        """host layout -> the tensors the step consumes, on the device: resize (identity at 288x512) / stack / 255, and
+        the label discs from their centres"""
+        x = fp.process(frames_d, fp.prepare_median(median_d), bg_mode='concat')
+        return x, T.label_discs(centers_d, H, W)
+
+    x_dev, y_dev = stage(frames_pin.cuda(), median_pin.cuda(), centers_pin.cuda())
 
     def step_resident():
         for p in model.parameters():
@@ -183,14 +272,15 @@ def main():
         bucket.allreduce()
         return loss
 
-    # e2e: every step's inputs start in pinned host memory and are copied H2D inside the timed region (side stream,
-    # overlapped with the previous step's compute by the package's DevicePrefetcher); the loss is read back every step
+    # e2e: every step's inputs start in pinned host memory (uint8 frames, the median frame, int32 label centres) and
+    # are copied H2D inside the timed region (side stream, overlapped with the previous step's compute by the package's
+    # DevicePrefetcher); preprocessing and labels run on the GPU; the loss is read back every step
     e2e_state = {"loader": None}
 
     def step_e2e():
         for p in model.parameters():
             p.grad = None
-        xd, yd = next(e2e_state["loader"])
+        xd, yd = stage(*next(e2e_state["loader"]))
         loss = T.WBCELoss(model(xd), yd)
         loss.backward()
         bucket.allreduce()
@@ -198,17 +288,19 @@ def main():
 
     def host_batches(count):
         for _ in range(count):
-            yield (x_pin, y_pin)
+            yield (frames_pin, median_pin, centers_pin)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, before=None):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
+        if before is not None:
+            before()
         for _ in range(steps):
             fn()
         ev1.record()
@@ -234,24 +326,49 @@ def main():
     desc = (C.c_int * (6 * maxrec))()
     kms = (C.c_float * maxrec)()
     nrec = lib.tnb_profile_collect(maxrec, desc, kms)
-    e2e_state["loader"] = T.DevicePrefetcher(host_batches(1))
-    step_e2e()  # untimed warm-up of the e2e path
 
-    def timed_e2e(steps):
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        ev0.record()
-        e2e_state["loader"] = T.DevicePrefetcher(host_batches(steps))  # the first copy is issued inside the region
-        for _ in range(steps):
-            step_e2e()
-        ev1.record()
-        barrier()
-        ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
+    e2e_state["loader"] = T.DevicePrefetcher(host_batches(2))
+    step_e2e(); step_e2e()  # untimed warm-up of the e2e path (both prefetcher slots)
 
-    ms_e2e = timed_e2e(args.steps)
+    def start_loader():  # the first copy is issued inside the timed region
+        e2e_state["loader"] = T.DevicePrefetcher(host_batches(args.steps))
+
+    ms_e2e = timed(step_e2e, args.steps, before=start_loader)
+
+    # ---- secondary region: the whole reference train step, train.py:85-96 ----
+    from train import mixup
+    opt = T.FusedAdam(model.parameters(), lr=1e-3)
+
+    def step_train():
+        opt.zero_grad()
+        x, y = mixup(x_dev, y_dev, 0.5)
+        loss = T.WBCELoss(model(x), y)
+        v = loss.item()
+        loss.backward()
+        bucket.allreduce()
+        opt.step()
+        return v
+
+    for _ in range(3):
+        step_train()
+    ms_train = timed(step_train, args.steps)
+
+    def kernel_alone(fn, iters=10):
+        fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    ms_adam = kernel_alone(opt.step)
+    ms_mixup = kernel_alone(lambda: mixup(x_dev, y_dev, 0.5))
+    nparams = sum(p.numel() for p in model.parameters())
+    adam_bytes = 28.0 * nparams                                   # p, g, m, v read; p, m, v written (fp32)
+    mixup_bytes = 12.0 * (x_dev.numel() + y_dev.numel())          # x[i], x[perm[i]] read, out written, for x and y
 
     if rank != 0:
         if world > 1:
@@ -288,15 +405,12 @@ def main():
     conv_fl = sum(per_kind.get(k, [0, 0, 0])[1] for k in (0, 1))
     conv_launches = sum(per_kind.get(k, [0, 0, 0])[2] for k in (0, 1))
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-    terms = 3 if args.precision == "fp32x3" else 1
-    traffic, traffic_src = None, None
-    prof = os.path.join(ROOT, "profiles", "kernel_metrics_r1.json")
-    if os.path.exists(prof) and args.precision == "fp32x3":  # dram read+write per conv launch from the committed ncu pass
-        km = json.load(open(prof))
-        conv = [v for k, v in km.items() if k.startswith("conv3x3_kernel")]
-        traffic = sum(v["dram_bytes_per_launch"] * v["launches"] for v in conv) / sum(v["launches"] for v in conv)
-        traffic_src = "profiles/kernel_metrics_r1.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per conv launch)"
-    roofline = {"bound": "tensor", "kernel": "conv3x3_kernel (forward + dgrad launches)", "achieved": achieved,
+    fwd_terms, bwd_terms = {"fp32x3": (3, 3), "tf32like": (1, 1), "fp32x3_bwd1": (3, 1)}[args.precision]
+    # executed MMA FLOPs per algorithmic FLOP of the profiled conv launches (forward + dgrad)
+    fl_f, fl_d = per_kind.get(0, [0, 0, 0])[1], per_kind.get(1, [0, 0, 0])[1]
+    terms = (fwd_terms * fl_f + bwd_terms * fl_d) / max(fl_f + fl_d, 1.0)
+    traffic, traffic_src = committed_traffic(args.precision)
+    roofline = {"bound": "tensor", "kernel": "conv3x3_kernel / conv3x3_lean_kernel (forward + dgrad launches)", "achieved": achieved,
                 "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
                 "traffic_source": traffic_src,
                 "peak_source": peaks["source"], "avg_launch_ms": conv_ms / max(conv_launches, 1),
@@ -307,36 +421,67 @@ def main():
                           "(the timed region itself replays CUDA graphs)",
                 "whole_step_frac": (84.78e9 * value / world) / (peaks["tflops"] * 1e12)}
 
-    cfg = _lib.TrackNetCfg(n=BATCH, h=H, w=W, in_dim=IN_DIM, out_dim=OUT_DIM, training=1, fwd_terms=terms,
-                           bwd_terms=terms, variant=args.variant, bn_eps=1e-5, bn_momentum=0.1)
+    cfg = _lib.TrackNetCfg(n=BATCH, h=H, w=W, in_dim=IN_DIM, out_dim=OUT_DIM, training=1, fwd_terms=fwd_terms,
+                           bwd_terms=bwd_terms, variant=args.variant, bn_eps=1e-5, bn_momentum=0.1)
     launches = (lib.tnb_tracknet_num_launches(C.byref(cfg), 0) + lib.tnb_tracknet_num_launches(C.byref(cfg), 1)
                 + 3) * args.steps  # + WBCE forward (2 kernels) and backward (1)
 
+    train_step = {"region": "zero_grad + mixup + forward + WBCE + loss.item() + backward + FusedAdam.step (reference train.py:85-96)",
+                  "value": frames / (ms_train * 1e-3), "unit": "frames/s", "ms_per_step": ms_train / args.steps,
+                  "adam_kernel": {"ms": ms_adam, "algorithmic_bytes": adam_bytes, "gbs": adam_bytes / ms_adam / 1e6,
+                                  "frac_of_hbm_peak": adam_bytes / ms_adam / 1e6 / peaks["hbm"]},
+                  "mixup_kernel": {"ms": ms_mixup, "algorithmic_bytes": mixup_bytes, "gbs": mixup_bytes / ms_mixup / 1e6,
+                                   "frac_of_hbm_peak": mixup_bytes / ms_mixup / 1e6 / peaks["hbm"],
+                                   "note": "two launches (x, y) + the host RNG draws of train.py:32-35"}}
+
+    torch_base = None
+    if not args.no_torch_baseline and world == 1:
+        # the reference architecture on stock torch-CUDA, same box, same batch, same timed region; our tensors first make
+        # room (the workspaces are cached in the model)
+        from tools import ref_arch
+        xt, yt = x_dev.clone(), y_dev.clone()
+        model._ws_saved = model._ws_scratch = None
+        torch.cuda.empty_cache()
+        torch_base = {"region": "forward + WBCE + backward, batch resident in HBM (= `value`)", "torch": torch.__version__,
+                      "cudnn": torch.backends.cudnn.version()}
+        for name in ref_arch.VARIANTS:
+            try:
+                ms = ref_arch.time_variant(name, xt, yt, IN_DIM, OUT_DIM, 10, 3)
+                torch_base[name] = {"ms_per_step": ms, "frames_per_s": BATCH * SEQ_LEN / ms * 1e3,
+                                    "this_repo_over_it": ms / (ms_total / args.steps)}
+            except Exception as e:  # the baseline must never take the bench line down
+                torch_base[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        fps, ms_cpu, cores = cpu_reference_step_rate(3, 1, batch=1)
+        threads = host_threads()
+        _, ms1, _ = cpu_reference_step_rate(1, 1, 1, threads)
+        batch = 2 if 4 * 2 * ms1 * 1e-3 <= 25.0 else 1       # ~10-30 s of CPU work
+        fps, ms_cpu, cores = cpu_reference_step_rate(3, 1, batch, threads)
         cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-               "sample": "bs=1 of the bs=10 workload, 3 timed + 1 warm-up train steps, torch CPU fp32 (oracle port)"}
+               "sample": f"bs={batch} of the bs={BATCH} workload, 3 timed + 1 warm-up train steps, torch CPU fp32 (oracle port)"}
 
     gs = (C.c_longlong * 4)()
     lib.tnb_graph_stats(gs)
-    nbytes_in = x_pin.numel() * 4 + y_pin.numel() * 4
+    nbytes_in = frames_pin.numel() + median_pin.numel() + centers_pin.numel() * 4
+    dtypes = {"fp32x3": "fp16x3 / bf16x3 (3-term hi/lo split operands, fp32 accumulate: fp32-faithful)",
+              "tf32like": "fp16 / bf16 single pass, fp32 accumulate (TF32-class)",
+              "fp32x3_bwd1": "forward fp16x3 (fp32-faithful), backward single bf16 pass (TF32-class gradients)"}
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None,
-            "dtype": "fp16x3 (3-term hi/lo split operands, fp32 accumulate: fp32-faithful)" if terms == 3
-            else "fp16 single pass, fp32 accumulate (TF32-class)",
-            "data": "synthetic",
-            "config": {"workload": "TrackNet seq_len=8 bg=concat (27->8 ch) 288x512 fwd+WBCE+bwd, BASELINE configs[1]",
-                       "global_batch": BATCH * world, "per_gpu_batch": BATCH, "parallelism": f"dp{world}",
-                       "precision": args.precision,
+            "vs_baseline": None, "dtype": dtypes[args.precision], "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "per_gpu_batch": BATCH,
+                       "parallelism": f"dp{world}", "precision": args.precision,
                        "l2": "working set ~10 GB per step >> 126 MB L2 (inputs larger than L2; no explicit flush)"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": 4,
+                    "path": "pinned uint8 frames + median + int32 label centres -> DevicePrefetcher (copy stream) -> "
+                            "FramePreprocessor + label_discs (GPU) -> TrackNet -> WBCELoss -> backward -> loss.item()"},
             "gpu_launches": launches,
             "cuda_graphs": {"captured": gs[0], "replayed_calls": gs[1], "stream_launched_calls": gs[2], "capture_failures": gs[3]},
-            "roofline": roofline, "kernel_breakdown": breakdown, "cpu_baseline": cpu}
+            "roofline": roofline, "kernel_breakdown": breakdown, "train_step": train_step,
+            "torch_cuda_baseline": torch_base, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

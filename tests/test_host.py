@@ -273,8 +273,10 @@ def test_bench_reference_arm_prints_the_contract_line():
     same metric / unit / config family as the GPU arm, zero transfer bytes, and a cpu_baseline that describes itself."""
     import json
     import subprocess
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                       capture_output=True, text=True, cwd=ROOT, timeout=600)
+    # --cpu-batch 1: one sample per step (the default takes as many of the 10 as fit its time budget on the host)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-batch", "1"], capture_output=True, text=True, cwd=ROOT, timeout=600,
+                       env=dict(os.environ, OMP_NUM_THREADS="1"))   # what torchrun exports to its workers
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads(r.stdout.strip().splitlines()[-1])
     import bench
@@ -283,9 +285,12 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and abs(d["value"] - 8 / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]  # bs 1 x seq_len 8 per step
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "bs=1" in cb["sample"]
+    assert cb["kind"] == "port" and cb["value"] == d["value"] and "bs=1" in cb["sample"]
+    assert cb["cores"] == len(os.sched_getaffinity(0))              # all host threads, whatever OMP_NUM_THREADS said
+    assert d["steps"] == 1 and d["warmup"] == 0                     # K and W as asked
+    assert d["config"]["workload"] == bench.WORKLOAD and d["config"]["global_batch"] == bench.BATCH  # the GPU arm's config
     # non-zero ranks of a torchrun launch stay silent
-    r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1"],
+    r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--cpu-batch", "1"],
                         capture_output=True, text=True, cwd=ROOT, timeout=600, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r2.returncode == 0 and r2.stdout.strip() == ""
 
@@ -303,3 +308,26 @@ def test_predict_windows_match_the_reference_dataset():
         want = g[key]
         assert tuple(win.shape) == want.shape[:2], key
         assert np.array_equal(P._as_indices(win).numpy(), want), key
+
+
+def test_ref_arch_is_the_reference_model():
+    """tools/ref_arch.Net (the torch-CUDA baseline of bench.py; /root/reference is absent on the GPU box) is the
+    reference's module graph: with the fixture's weights it reproduces the stored output of the REAL reference on the C1
+    input (tests/golden/tracknet_c1.npz), train-mode BatchNorm."""
+    from tools import ref_arch
+    from oracle import tracknet_oracle as O
+    g = np.load(os.path.join(ROOT, "tests", "golden", "tracknet_c1.npz"))
+    seed = int(g["seed"])
+    sd = O.init_tracknet_state(seed, 12, 4)
+    gen = torch.Generator().manual_seed(seed)
+    for key, shape in O.tracknet_state_keys(12, 4):      # replay the generator stream of gen_golden (weights, then x)
+        if key.endswith("conv.weight") or key.startswith("predictor."):
+            torch.rand(shape, generator=gen)
+    x = torch.rand(tuple(g["shape"]), generator=gen)
+    net = ref_arch.Net(12, 4).train()
+    own = net.state_dict()
+    assert [tuple(v.shape) for v in own.values()] == [tuple(v.shape) for v in sd.values()]   # same 104 tensors, same order
+    net.load_state_dict(dict(zip(own.keys(), sd.values())))
+    with torch.no_grad():
+        y = net(x)
+    assert np.abs(y.numpy() - g["y_train"]).max() < 5e-5

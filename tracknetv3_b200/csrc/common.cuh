@@ -46,14 +46,31 @@ void set_last_error(const char* fmt, ...);
 // a predecessor's output AND writes to anything a predecessor may still read). Both instructions are no-ops in a kernel
 // launched without the attribute. TNB_PDL=0 launches everything fully serialised (ablation).
 // ---------------------------------------------------------------------------------------------
-TNB_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-TNB_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-inline bool pdl_enabled() {
+// TNB_PDL (experiment matrix, read once per process): 0 = plain stream order; 1 = attribute + every kernel releases its
+// dependents right after its prologue; 2 = attribute only (dependents are released when the grid exits: only the launch
+// latency is hidden); 3 = like 1 for the small elementwise kernels, like 2 for the persistent tensor-core kernels.
+inline int pdl_mode() {
   static const int v = [] { const char* e = getenv("TNB_PDL"); return e ? atoi(e) : 1; }();
-  return v != 0;
+  return v;
+}
+inline bool pdl_enabled() { return pdl_mode() != 0; }
+static __constant__ int c_pdl_early[2] = {1, 1};  // [0]: small kernels, [1]: persistent tensor-core kernels (per translation unit)
+static inline void pdl_sync_constant() {
+  static bool done = false;
+  if (done) return;
+  const int m = pdl_mode();
+  const int v[2] = {m == 1 || m == 3, m == 1};
+  cudaMemcpyToSymbol(c_pdl_early, v, sizeof(v));
+  done = true;
+}
+TNB_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// big = 1 in the persistent tcgen05 kernels
+TNB_DEVINL void pdl_launch_dependents(int big = 0) {
+  if (c_pdl_early[big]) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 template <typename... KArgs, typename... Args>
 inline int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  pdl_sync_constant();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];

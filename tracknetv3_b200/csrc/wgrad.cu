@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  pdl_launch_dependents();  // the prologue above touched shared memory and TMEM only
+  pdl_launch_dependents(1);  // the prologue above touched shared memory and TMEM only
   pdl_wait();
 
   if (warp < 4) {
@@ -430,7 +430,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  pdl_launch_dependents();
+  pdl_launch_dependents(1);
   pdl_wait();
 
   if (warp < 4) {
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  pdl_launch_dependents();
+  pdl_launch_dependents(1);
   pdl_wait();
 
   if (warp < 4) {

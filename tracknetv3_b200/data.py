@@ -2,6 +2,24 @@
 per step): the next batch's pinned-host tensors are copied on a side stream while the current step computes."""
 import torch
 
+from . import _lib
+
+
+def label_discs(centers, height=288, width=512, sigma=2.5):
+    """The training labels of the reference's dataset (dataset.py:400-410 `_get_heatmap`, called with integer centres at
+    :632) built ON the device from the coordinates: ``centers`` int (N, L, 2) = (cx, cy) per frame -> float32
+    (N, L, height, width) binary discs of radius ``sigma``, all-zero maps where cx == cy == 0. 8 bytes per map cross
+    PCIe instead of a 590 KB fp32 heatmap."""
+    lib = _lib.load()
+    _lib.require_cuda(centers)
+    if centers.dim() != 3 or centers.shape[2] != 2:
+        raise RuntimeError(f"label_discs expects integer centres (N, L, 2), got {tuple(centers.shape)}")
+    c = centers.to(torch.int32).contiguous()
+    n, l = c.shape[0], c.shape[1]
+    out = torch.empty((n, l, height, width), dtype=torch.float32, device=c.device)
+    _lib.check(lib.tnb_label_discs(c.data_ptr(), n * l, height, width, float(sigma), out.data_ptr(), _lib.stream_ptr()))
+    return out
+
 
 class DevicePrefetcher:
     """Iterate over an iterable of tuples of (pinned) host tensors, yielding the same tuples on the GPU.

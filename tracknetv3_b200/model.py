@@ -44,8 +44,12 @@ class Triple2DConv(nn.Module):
         self.conv_3 = Conv2DBlock(out_dim, out_dim)
 
 
+# (forward terms, backward terms) of the 3x3 convolutions' operand split
+_PRECISIONS = {"fp32x3": (3, 3), "tf32like": (1, 1), "fp32x3_bwd1": (3, 1)}
+
+
 def _cfg(n, h, w, in_dim, out_dim, training, precision, variant=0):
-    terms = {"fp32x3": (3, 3), "tf32like": (1, 1)}[precision]
+    terms = _PRECISIONS[precision]
     return _lib.TrackNetCfg(n=n, h=h, w=w, in_dim=in_dim, out_dim=out_dim, training=int(training),
                             fwd_terms=terms[0], bwd_terms=terms[1], variant=variant, bn_eps=1e-5, bn_momentum=0.1)
 
@@ -114,7 +118,9 @@ class TrackNet(nn.Module):
 
     ``precision``: "fp32x3" (default) computes every 3x3 convolution as a 3-term fp16 hi/lo split product with
     fp32 accumulation (gradients are pre-scaled by a power of two) - within ~4e-5 of the reference's fp32 heatmaps;
-    "tf32like" is a single 16-bit pass (what the reference's own cuDNN TF32 path amounts to; ~7e-3).
+    "tf32like" is a single 16-bit pass (what the reference's own cuDNN TF32 path amounts to; ~7e-3);
+    "fp32x3_bwd1" keeps the fp32-faithful forward (the heatmap bound) and runs dgrad / wgrad as a single bf16 pass -
+    measured next to the default by ``bench.py --precision fp32x3_bwd1``, never the headline.
     """
 
     def __init__(self, in_dim, out_dim, precision="fp32x3"):
@@ -129,8 +135,8 @@ class TrackNet(nn.Module):
         self.predictor = nn.Conv2d(64, out_dim, (1, 1))
         self.sigmoid = nn.Sigmoid()
         self.in_dim, self.out_dim = in_dim, out_dim
-        if precision not in ("fp32x3", "tf32like"):
-            raise ValueError("precision must be 'fp32x3' or 'tf32like'")
+        if precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
         self.precision = precision
         self._variant = 0
         self._ws_scratch = None   # forwards that keep nothing for a backward (eval(), no_grad)

@@ -43,8 +43,11 @@ class GradBucket:
         grads = [p.grad for p in self.params if p.grad is not None]
         flat = self._shared_flat(grads)
         if flat is not None:  # in place: no flatten / copy-back passes around the collective
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-            flat.div_(self.world)
+            if dist.get_backend(self.group) == "nccl":  # ncclAvg: the division rides inside the collective
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+                flat.div_(self.world)
             return
         flat = _flatten_dense_tensors(grads)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
