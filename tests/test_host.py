@@ -331,3 +331,61 @@ def test_ref_arch_is_the_reference_model():
     with torch.no_grad():
         y = net(x)
     assert np.abs(y.numpy() - g["y_train"]).max() < 5e-5
+
+
+def _dp_fit_worker(rank, world, port, save_dir, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import train as TR
+    r, w, _ = TR.init_distributed()                 # gloo here (no GPU): the same code path torchrun drives with NCCL
+    assert (r, w) == (rank, world)
+    torch.manual_seed(50 + rank)                     # replicas start different: fit() must synchronise them to rank 0
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    evals = []
+
+    def train_fn(model, optimizer, loader, param_dict, bucket):
+        losses = []
+        for x, y in loader:
+            optimizer.zero_grad()
+            loss = ((model(x) - y) ** 2).mean()
+            loss.backward()
+            bucket.allreduce()
+            optimizer.step()
+            losses.append(loss.item())
+        return float(np.mean(losses))
+
+    def eval_fn(model, loader, param_dict):
+        evals.append(rank)
+        return 0.25, {"accuracy": 0.5 + 0.1 * len(evals)}
+
+    def loader():                                    # every rank draws its own batches
+        g = torch.Generator().manual_seed(7 + 1000 * rank)
+        return [(torch.randn(4, 6, generator=g), torch.randn(4, 1, generator=g)) for _ in range(3)]
+
+    pd = {"model_name": "TrackNet", "epochs": 2}
+    best, hist = TR.fit(net, opt, None, loader, loader, pd, train_fn, eval_fn, save_dir=save_dir, log=lambda s: None,
+                        rank=rank, world=world)
+    flat = torch.cat([p.detach().flatten() for p in net.parameters()])
+    q.put((rank, flat.numpy(), best, [h[3] for h in hist], len(evals)))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_fit_gloo_world2(tmp_path):
+    """train.fit with world 2 (gloo on CPU; NCCL under torchrun on GPUs): replicas synchronised to rank 0, gradients
+    averaged every step (so the replicas stay identical although their batches differ), rank 0 alone evaluates and writes
+    the checkpoints, and every rank learns the validation accuracy."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_fit_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    [p.join(60) for p in procs]
+    assert np.array_equal(res[0][1], res[1][1])                      # identical replicas after 6 averaged steps
+    assert res[0][2] == res[1][2] == 0.7 and res[0][3] == res[1][3] == [0.6, 0.7]
+    assert (res[0][4], res[1][4]) == (2, 0)                          # only rank 0 evaluated
+    ck = torch.load(tmp_path / "TrackNet_cur.pt", weights_only=False)
+    assert ck["epoch"] == 1 and ck["max_val_acc"] == 0.7 and (tmp_path / "TrackNet_best.pt").exists()
+    # the checkpoint holds the synchronised weights
+    assert np.array_equal(torch.cat([v.flatten() for v in ck["model"].values()]).numpy(), res[0][1])

@@ -6,6 +6,12 @@ yielding the reference's (i, x, y, c, _) tuples and runs the step of train.py:85
 scheduler choices, the checkpoint layout and the resume logic of the reference's __main__ (:236-305) are here as
 `make_optimizer`, `make_scheduler`, `checkpoint_dict`, `resume_from` and `fit`; `python train.py` takes the reference's
 command line and trains on synthetic batches.
+
+Data parallel (BASELINE configs[2]; the reference itself is single-GPU): launched as
+`python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 train.py ...` every process drives one GPU
+with `--batch_size` samples per step, the replicas start from rank 0's weights (`broadcast_module`), every rank draws its
+own batches (seed + rank), the gradients are averaged with ONE in-place NCCL allreduce of the flat bucket per step
+(`GradBucket`, torch-DDP semantics: BatchNorm statistics stay per replica), validation and the checkpoints are rank 0's.
 """
 import argparse
 
@@ -37,8 +43,10 @@ def mixup(x, y, alpha=0.5):
     return outs[0], outs[1]
 
 
-def train_tracknet(model, optimizer, data_loader, param_dict):
-    """ Train TrackNet model for one epoch (step semantics of reference :84-96). Returns the mean loss. """
+def train_tracknet(model, optimizer, data_loader, param_dict, bucket=None):
+    """ Train TrackNet model for one epoch (step semantics of reference :84-96). Returns the mean loss.
+        bucket (tracknetv3_b200.parallel.GradBucket, optional): data parallel - average the gradients over the ranks
+        between backward and the optimizer step. """
     model.train()
     epoch_loss = []
     for step, (_, x, y, c, _) in enumerate(data_loader):
@@ -50,6 +58,8 @@ def train_tracknet(model, optimizer, data_loader, param_dict):
         loss = WBCELoss(y_pred, y)
         epoch_loss.append(loss.item())
         loss.backward()
+        if bucket is not None:
+            bucket.allreduce()
         optimizer.step()
     return float(np.mean(epoch_loss))
 
@@ -61,7 +71,7 @@ def get_random_mask(mask_size, mask_ratio):
     return mask
 
 
-def train_inpaintnet(model, optimizer, data_loader, param_dict):
+def train_inpaintnet(model, optimizer, data_loader, param_dict, bucket=None):
     """ Train InpaintNet model for one epoch (step semantics of reference :147-163): random mask AND visibility,
         masked coordinates zeroed, MSE on the masked entries, clip_grad_norm_(1), optimizer step. Returns mean loss.
         The model's forward and backward are one kernel each; the few (N, L, 2)-sized loss ops stay torch ops. """
@@ -77,6 +87,8 @@ def train_inpaintnet(model, optimizer, data_loader, param_dict):
         loss = torch.nn.MSELoss()(refine_coor * inpaint_mask, coor_gt * inpaint_mask)
         epoch_loss.append(loss.item())
         loss.backward()
+        if bucket is not None:
+            bucket.allreduce()
         torch.nn.utils.clip_grad_norm_(model.parameters(), 1)
         optimizer.step()
     return float(np.mean(epoch_loss))
@@ -122,32 +134,62 @@ def resume_from(ckpt, model, optimizer, scheduler):
     return ckpt['epoch'] + 1, ckpt['max_val_acc']
 
 
+def init_distributed():
+    """ (rank, world, local_rank) from the torchrun environment; initialises the process group (NCCL on GPUs, gloo
+        without) and binds this process to its GPU. A plain `python train.py` is rank 0 of a world of 1. """
+    import os
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank, local = int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0'))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl' if torch.cuda.is_available() else 'gloo')
+    return rank, world, local
+
+
 def fit(model, optimizer, scheduler, train_loader_fn, val_loader_fn, param_dict, train_fn, eval_fn,
-        start_epoch=0, max_val_acc=0., save_dir=None, log=print):
+        start_epoch=0, max_val_acc=0., save_dir=None, log=print, rank=0, world=1):
     """ Epoch loop of reference :268-305 without the TensorBoard writer: train, evaluate, scheduler step, `<model>_best.pt`
         when the validation accuracy does not drop, `<model>_cur.pt` every epoch. The loaders are given as callables
-        returning a fresh iterable per epoch. Returns (max_val_acc, history). """
+        returning a fresh iterable per epoch. Returns (max_val_acc, history).
+        world > 1 (data parallel): the replicas are synchronised to rank 0 first, every step averages the gradients over
+        the ranks, rank 0 alone evaluates, logs and writes the checkpoints and shares the accuracy with the others. """
     import os
     name = param_dict['model_name']
     history = []
+    bucket = None
+    if world > 1:
+        import torch.distributed as dist
+        from tracknetv3_b200.parallel import GradBucket, broadcast_module
+        broadcast_module(model)
+        bucket = GradBucket(model)
     for epoch in range(start_epoch, param_dict['epochs']):
-        train_loss = train_fn(model, optimizer, train_loader_fn(), param_dict)
-        val_loss, val_res = eval_fn(model, val_loader_fn(), param_dict)
+        train_loss = train_fn(model, optimizer, train_loader_fn(), param_dict, bucket) if world > 1 else \
+            train_fn(model, optimizer, train_loader_fn(), param_dict)
+        val = [0., 0.]
+        if rank == 0:
+            val_loss, val_res = eval_fn(model, val_loader_fn(), param_dict)
+            val = [val_loss, val_res['accuracy'] if name == 'TrackNet' else val_res['inpaint']['accuracy']]
+        if world > 1:
+            t = torch.tensor(val, dtype=torch.float64, device=next(model.parameters()).device)
+            dist.broadcast(t, src=0)
+            val = t.tolist()
+        val_loss, cur_val_acc = val
         if scheduler is not None:
             scheduler.step()
-        cur_val_acc = val_res['accuracy'] if name == 'TrackNet' else val_res['inpaint']['accuracy']
         history.append((epoch, train_loss, val_loss, cur_val_acc))
-        log(f'Epoch [{epoch + 1} / {param_dict["epochs"]}] train loss {train_loss:.6f} val loss {val_loss:.6f} '
-            f'val accuracy {cur_val_acc:.4f}')
-        if save_dir is not None:
+        if rank == 0:
+            log(f'Epoch [{epoch + 1} / {param_dict["epochs"]}] train loss {train_loss:.6f} val loss {val_loss:.6f} '
+                f'val accuracy {cur_val_acc:.4f}')
+        if save_dir is not None and rank == 0:
             if cur_val_acc >= max_val_acc:
-                max_val_acc = cur_val_acc
-                torch.save(checkpoint_dict(epoch, max_val_acc, model, optimizer, scheduler, param_dict),
+                torch.save(checkpoint_dict(epoch, cur_val_acc, model, optimizer, scheduler, param_dict),
                            os.path.join(save_dir, f'{name}_best.pt'))
-            torch.save(checkpoint_dict(epoch, max_val_acc, model, optimizer, scheduler, param_dict),
+            torch.save(checkpoint_dict(epoch, max(max_val_acc, cur_val_acc), model, optimizer, scheduler, param_dict),
                        os.path.join(save_dir, f'{name}_cur.pt'))
-        else:
-            max_val_acc = max(max_val_acc, cur_val_acc)
+        max_val_acc = max(max_val_acc, cur_val_acc)
     return max_val_acc, history
 
 
@@ -214,8 +256,9 @@ if __name__ == '__main__':
     parser.add_argument('--synthetic_steps', type=int, default=5, help='random batches per epoch (no dataset in this repo)')
     args = parser.parse_args()
     param_dict = vars(args)
-    np.random.seed(args.seed)
-    torch.manual_seed(args.seed)
+    rank, world, _ = init_distributed()
+    np.random.seed(args.seed + rank)      # mixup / random-mask draws differ per replica; the weights come from rank 0
+    torch.manual_seed(args.seed + rank)
     os.makedirs(args.save_dir, exist_ok=True)
     ckpt = None
     if args.resume_training:
@@ -225,7 +268,8 @@ if __name__ == '__main__':
         param_dict = dict(ckpt['param_dict'], resume_training=True, epochs=args.epochs, verbose=args.verbose)
         param_dict.setdefault('synthetic_steps', args.synthetic_steps)
     P = argparse.Namespace(**param_dict)
-    print(f'Parameters: {param_dict}')
+    if rank == 0:
+        print(f'Parameters: {param_dict}' + (f' (data parallel over {world} GPUs, global batch {world * P.batch_size})' if world > 1 else ''))
     from test import eval_tracknet, eval_inpaintnet
     tracknet = P.model_name == 'TrackNet'
     model = get_model(P.model_name, P.seq_len, P.bg_mode).cuda() if tracknet else get_model(P.model_name).cuda()
@@ -236,7 +280,11 @@ if __name__ == '__main__':
         loaders = lambda seed: (lambda: _synthetic_tracknet_loader(P.synthetic_steps, P.batch_size, P.seq_len, P.bg_mode, seed=seed))
     else:
         loaders = lambda seed: (lambda: _synthetic_inpaintnet_loader(P.synthetic_steps, P.batch_size, P.seq_len, seed=seed))
-    best, _ = fit(model, optimizer, scheduler, loaders(P.seed), loaders(P.seed + 1), param_dict,
+    # every rank trains on its own batches (seed + rank); the validation batches are rank 0's
+    best, _ = fit(model, optimizer, scheduler, loaders(P.seed + 1000 * rank), loaders(P.seed + 1), param_dict,
                   train_tracknet if tracknet else train_inpaintnet, eval_tracknet if tracknet else eval_inpaintnet,
-                  start_epoch, max_val_acc, P.save_dir)
-    print(f'best validation accuracy {best:.4f}; checkpoints in {P.save_dir}')
+                  start_epoch, max_val_acc, P.save_dir, rank=rank, world=world)
+    if rank == 0:
+        print(f'best validation accuracy {best:.4f}; checkpoints in {P.save_dir}')
+    if world > 1:
+        torch.distributed.destroy_process_group()
