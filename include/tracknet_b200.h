@@ -190,8 +190,9 @@ int tnb_mixup(const float* x, const float* lam, const long long* perm, float* ou
               void* stream);
 
 /* torch.optim.Adam step over many tensors in one launch (train.py:96,242). table: device array of
- * {float* p; const float* g; float* m; float* v; long long n;}. step counts from 1. */
-int tnb_adam_multi(const void* table_dev, int ntensors, long long max_n, float lr, float beta1, float beta2,
+ * {float* p; const float* g; float* m; float* v; long long n;}; total_n = the sum of n over the table (sizes the grid: one
+ * CTA per 4096-element chunk of a tensor). step counts from 1. */
+int tnb_adam_multi(const void* table_dev, int ntensors, long long total_n, float lr, float beta1, float beta2,
                    float eps, float weight_decay, int step, void* stream);
 
 /* predict_location (test.py:52-79) for a batch of maps on the GPU. maps: nmaps x h x w, float (foreground =

@@ -263,19 +263,24 @@ if __name__ == '__main__':
     parser.add_argument('--save_dir', type=str, default='pred_result', help='directory to save the prediction result')
     parser.add_argument('--frames', type=int, default=40, help='length of the synthetic clip (no --video_file)')
     args = parser.parse_args()
-    if args.video_file:
-        assert args.tracknet_file, 'a TrackNet checkpoint is required with --video_file'
+    # models: from checkpoints in the reference's layout (predict.py:98-108), else randomly initialised
+    if args.tracknet_file:
         tracknet, inpaintnet, seq_len, bg_mode, inpaint_seq_len = load_models(args.tracknet_file, args.inpaintnet_file)
-        frames = np.array(generate_frames(args.video_file))[:, :, :, ::-1]      # BGR -> RGB, as predict.py:128
+    else:
+        assert not args.video_file, 'a TrackNet checkpoint is required with --video_file'
+        torch.manual_seed(0)
+        seq_len, bg_mode, inpaint_seq_len = 8, 'concat', 16
+        tracknet, inpaintnet = get_model('TrackNet', seq_len, bg_mode), get_model('InpaintNet')
+    # frames: the video file (all frames in memory, BGR -> RGB as predict.py:128), else a synthetic clip
+    if args.video_file:
+        frames = np.array(generate_frames(args.video_file))[:, :, :, ::-1]
         video = torch.from_numpy(np.ascontiguousarray(frames))
         name = os.path.basename(args.video_file)[:-4]
     else:
-        torch.manual_seed(0)
-        seq_len, bg_mode, name, inpaint_seq_len = 8, 'concat', 'synthetic', 16
-        video = torch.randint(0, 40, (args.frames, 360, 640, 3), dtype=torch.uint8)
+        name = 'synthetic'
+        video = torch.randint(0, 40, (args.frames, 360, 640, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(0))
         for i in range(args.frames):                                   # a bright ball crossing a dark noisy court
             video[i, 100 + 3 * i:108 + 3 * i, 50 + 10 * i:58 + 10 * i] = 250
-        tracknet, inpaintnet = get_model('TrackNet', seq_len, bg_mode), get_model('InpaintNet')
     tracknet = tracknet.cuda().eval()
     inpaintnet = inpaintnet.cuda().eval() if inpaintnet is not None else None
     h, w = video.shape[1], video.shape[2]

@@ -322,3 +322,87 @@ def test_out_dim_above_16():
     for k, tol in (("predictor.weight", 2e-2), ("predictor.bias", 2e-2), ("up_block_3.conv_2.conv.weight", 6e-2)):
         g = dict(m.named_parameters())[k].grad
         assert G.rel_err(g, r_grads[k]) < tol, k
+
+
+def _disc_labels(n, l, h, w, gen):
+    y = torch.zeros(n, l, h, w)
+    for i in range(n):
+        for f in range(l):
+            cx, cy = int(torch.randint(0, w, (1,), generator=gen)), int(torch.randint(0, h, (1,), generator=gen))
+            if f != 3:
+                y[i, f] = torch.from_numpy(O.label_disc(cx, cy, h, w))
+    return y
+
+
+def test_baseline_config_bs10_train_step_vs_oracle_on_device():
+    """BASELINE configs[1] at its FULL size - bs 10, seq_len 8, bg concat, 288x512 - forward + WBCE + backward against the
+    oracle executed in fp32 on the same GPU (TF32 off): heatmap within the north_star bound, loss to 1e-4, and the
+    gradients of the last block / predictor (no downstream ReLU or pool decision) tightly; the deep gradients get the
+    fp64 yardstick at bs 2 in test_c2_shape_train_step_vs_oracle_on_device."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = _model(13, 27, 8).train()
+    sd = {k: v.to(G.DEV) for k, v in O.init_tracknet_state(13, 27, 8).items()}
+    gen = torch.Generator().manual_seed(15)
+    x = torch.rand(10, 27, 288, 512, generator=gen).to(G.DEV)
+    y = _disc_labels(10, 8, 288, 512, gen).to(G.DEV)
+    y_pred = m(x)
+    loss = T.WBCELoss(y_pred, y)
+    loss.backward()
+    r_pred, r_loss, r_grads = O.tracknet_loss_and_grads(sd, x, y, True)
+    assert G.max_abs(y_pred, r_pred) < HEAT_TOL
+    assert abs(loss.item() - r_loss.item()) < 1e-4 * abs(r_loss.item())
+    grads = dict(m.named_parameters())
+    for k in ("predictor.weight", "predictor.bias", "up_block_3.conv_2.conv.weight", "up_block_3.conv_2.bn.weight",
+              "up_block_3.conv_2.bn.bias"):
+        assert G.rel_err(grads[k].grad, r_grads[k]) < 2e-3, k
+    for k, p in grads.items():                                   # every gradient in the right ball park, none missing
+        assert G.rel_err(p.grad, r_grads[k]) < 5e-2, k
+    # BatchNorm running statistics after the step (momentum 0.1, unbiased variance), every layer
+    for k, v in m.state_dict().items():
+        if k.endswith(("running_mean", "running_var")):
+            assert G.rel_err(v, sd[k]) < 1e-4, k
+
+
+def test_twenty_adam_steps_track_the_oracle():
+    """A multi-step trajectory: 20 steps of forward + WBCE + backward + Adam(lr 1e-3) (reference train.py:85-96, :242) with
+    the CUDA path + FusedAdam against the oracle + torch.optim.Adam in fp32 on the same GPU, same batches. A small
+    systematic bias in any gradient would compound; the loss curves must stay together."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = _model(31, 12, 4).train()
+    sd = {k: v.to(G.DEV) for k, v in O.init_tracknet_state(31, 12, 4).items()}
+    pkeys = [k for k, _ in m.named_parameters()]
+    ref_params = [sd[k].clone().requires_grad_(True) for k in pkeys]
+    opt = T.FusedAdam(m.parameters(), lr=1e-3)
+    ref_opt = torch.optim.Adam(ref_params, lr=1e-3)
+    gen = torch.Generator().manual_seed(32)
+    batches = [(torch.rand(2, 12, 96, 160, generator=gen).to(G.DEV), _disc_labels(2, 4, 96, 160, gen).to(G.DEV))
+               for _ in range(4)]
+    ours, theirs = [], []
+    for step in range(20):
+        x, y = batches[step % 4]
+        opt.zero_grad()
+        loss = T.WBCELoss(m(x), y)
+        loss.backward()
+        opt.step()
+        ours.append(loss.item())
+        work = dict(sd)
+        work.update(dict(zip(pkeys, ref_params)))
+        ref_opt.zero_grad()
+        r_loss = O.wbce_loss(O.tracknet_forward(work, x, True), y)
+        r_loss.backward()
+        ref_opt.step()
+        for k in sd:  # running statistics advanced by the oracle's forward
+            if k.endswith(("running_mean", "running_var", "num_batches_tracked")):
+                sd[k] = work[k]
+        theirs.append(r_loss.item())
+    assert theirs[-1] < 0.8 * theirs[0]                          # the trajectory goes somewhere
+    for step, (a, b) in enumerate(zip(ours, theirs)):
+        assert abs(a - b) < 5e-3 * abs(b) + 1e-7, (step, a, b)
+    with torch.no_grad():                                        # and ends at the same network
+        m.eval()
+        xe = batches[0][0]
+        work = dict(sd)
+        work.update(dict(zip(pkeys, ref_params)))
+        assert G.max_abs(m(xe), O.tracknet_forward(work, xe, False)) < 5e-3

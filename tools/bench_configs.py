@@ -49,7 +49,8 @@ def inference_path(bs=32, seq_len=8, h=288, w=512, steps=10):
         out["ensemble_ms"] = timed(ens_step, steps, 3)
         ens = ens_step()
         out["ensemble_decode_ms"] = timed(lambda: T.decode_heatmaps(ens.unsqueeze(1)), steps, 3)
-        out["inpaintnet_fwd_ms"] = timed(lambda: inp(coor * (1 - mask), mask), steps, 3)
+        from utils.general import COOR_TH
+        out["inpaintnet_fwd_ms"] = timed(lambda: inp.rectify(coor * (1 - mask), mask, COOR_TH), steps, 3)  # fwd + blend + threshold
     # GPU input pipeline: bs x seq_len 720p RGB frames -> Pillow-exact 288x512 -> (bs, 27, H, W)
     fp = T.FramePreprocessor(720, 1280, h, w)
     frames = torch.randint(0, 256, (bs, seq_len, 720, 1280, 3), dtype=torch.uint8, device="cuda")
@@ -86,6 +87,31 @@ def resolution_sweep(bs=8, steps=5):
         torch.cuda.empty_cache()
 
 
+def small_batch_latency(steps=30):
+    """configs[0] (seq_len 4, bg none, bs 1) eval forward latency and a bs-1 train step: ~40 / ~150 dependent launches of
+    short kernels, where launch latency shows (TNB_PDL / TNB_GRAPHS A/B: both are read once per process)."""
+    torch.manual_seed(0)
+    net = T.TrackNet(12, 4).cuda().eval()
+    x = torch.rand(1, 12, 288, 512, device="cuda")
+    with torch.no_grad():
+        ms_eval = timed(lambda: net(x), steps, 5)
+    net.train()
+    y = (torch.rand(1, 4, 288, 512, device="cuda") > 0.999).float()
+
+    def step():
+        for p in net.parameters():
+            p.grad = None
+        T.WBCELoss(net(x), y).backward()
+    ms_train = timed(step, steps, 5)
+    print(json.dumps({"config": "configs[0]: seq_len=4 bs=1 288x512", "eval_forward_ms": ms_eval, "train_step_ms": ms_train,
+                      "TNB_PDL": os.environ.get("TNB_PDL", "default"), "TNB_GRAPHS": os.environ.get("TNB_GRAPHS", "default")}),
+          flush=True)
+
+
 if __name__ == "__main__":
-    inference_path()
-    resolution_sweep()
+    if len(sys.argv) > 1 and sys.argv[1] == "latency":
+        small_batch_latency()
+    else:
+        inference_path()
+        resolution_sweep()
+        small_batch_latency()

@@ -119,10 +119,10 @@ int tnb_mixup(const float* x, const float* lam, const long long* perm, float* ou
               void* stream) {
   return launch_mixup(x, lam, perm, out, n, per_sample, ST(stream));
 }
-int tnb_adam_multi(const void* table, int ntensors, long long max_n, float lr, float b1, float b2, float eps, float wd,
+int tnb_adam_multi(const void* table, int ntensors, long long total_n, float lr, float b1, float b2, float eps, float wd,
                    int step, void* stream) {
   TNB_REQUIRE(step >= 1, "adam_multi: step counts from 1");
-  return launch_adam((const AdamTensor*)table, ntensors, max_n, lr, b1, b2, eps, wd, step, ST(stream));
+  return launch_adam((const AdamTensor*)table, ntensors, total_n, lr, b1, b2, eps, wd, step, ST(stream));
 }
 size_t tnb_heatmap_decode_workspace_bytes(int nmaps, int h, int w) { return decode_workspace_bytes(nmaps, h, w); }
 int tnb_heatmap_decode(const void* maps, int is_u8, float thresh, int nmaps, int h, int w, void* workspace, int* out,

@@ -34,7 +34,7 @@ int launch_mixup(const float* x, const float* lam, const long long* perm, float*
                  cudaStream_t st);
 
 struct AdamTensor { float* p; const float* g; float* m; float* v; long long n; };
-int launch_adam(const AdamTensor* table_dev, int ntensors, long long max_n, float lr, float b1, float b2, float eps,
+int launch_adam(const AdamTensor* table_dev, int ntensors, long long total_n, float lr, float b1, float b2, float eps,
                 float wd, int step, cudaStream_t st);
 
 size_t decode_workspace_bytes(int nmaps, int H, int W);

@@ -71,6 +71,6 @@ class FusedAdam(torch.optim.Optimizer):
             # launch - one launch in the train loop of the reference, where every parameter gets a gradient every step
             for step, bucket in by_step.items():
                 _lib.check(lib.tnb_adam_multi(self._table(bucket).data_ptr(), len(bucket),
-                                              max(p.numel() for p in bucket), group["lr"], b1, b2, group["eps"],
+                                              sum(p.numel() for p in bucket), group["lr"], b1, b2, group["eps"],
                                               group["weight_decay"], step, _lib.stream_ptr()))
         return loss
