@@ -37,40 +37,25 @@ void set_last_error(const char* fmt, ...);
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
-// Programmatic dependent launch (griddepcontrol). The network's passes are ~60 + ~110 dependent launches of 5-900 us
-// kernels; launched back to back each one pays its launch latency and its prologue (barrier init, TMEM allocation,
-// table build) after the predecessor's last CTA has retired. With the launch attribute below the NEXT kernel's CTAs
-// are scheduled as soon as every CTA of this one has passed pdl_launch_dependents() and an SM has room for them; they
-// run their prologue and then block in pdl_wait() until this grid has completed and its memory is visible.
-// Contract: a kernel launched through launch_pdl() calls pdl_wait() before its first global-memory access (reads of
-// a predecessor's output AND writes to anything a predecessor may still read). Both instructions are no-ops in a kernel
-// launched without the attribute. TNB_PDL=0 launches everything fully serialised (ablation).
+// Programmatic dependent launch (griddepcontrol). The network's passes are ~40 + ~115 dependent launches, many of them
+// 3-10 us elementwise kernels between the tensor-core kernels. Launched with the attribute below, the NEXT kernel's CTAs
+// are scheduled as soon as every CTA of the running one has passed pdl_launch_dependents() (or exited) and an SM has
+// room; they run their prologue and block in pdl_wait() until the running grid has completed and its memory is visible.
+// Contract: a kernel launched through launch_pdl() calls pdl_wait() before its first global-memory access (reads of a
+// predecessor's output AND writes to anything a predecessor may still read).
+// Measured on one box (profiles/r2_experiments.md): releasing the dependents early from the SMALL kernels only and letting
+// the persistent tcgen05 kernels release theirs at exit is 2-3 % faster at batch 1 (1.07 -> 1.03 ms eval forward,
+// 3.70 -> 3.61 ms train step; 9 % without CUDA graphs) and neutral at batch 10; an early release from the persistent
+// kernels as well costs 0.8 ms per bs-10 step and is not done. TNB_PDL=0 launches everything fully serialised (ablation).
 // ---------------------------------------------------------------------------------------------
-// TNB_PDL (experiment matrix, read once per process): 0 = plain stream order; 1 = attribute + every kernel releases its
-// dependents right after its prologue; 2 = attribute only (dependents are released when the grid exits: only the launch
-// latency is hidden); 3 = like 1 for the small elementwise kernels, like 2 for the persistent tensor-core kernels.
-inline int pdl_mode() {
+inline bool pdl_enabled() {
   static const int v = [] { const char* e = getenv("TNB_PDL"); return e ? atoi(e) : 1; }();
-  return v;
-}
-inline bool pdl_enabled() { return pdl_mode() != 0; }
-static __constant__ int c_pdl_early[2] = {1, 1};  // [0]: small kernels, [1]: persistent tensor-core kernels (per translation unit)
-static inline void pdl_sync_constant() {
-  static bool done = false;
-  if (done) return;
-  const int m = pdl_mode();
-  const int v[2] = {m == 1 || m == 3, m == 1};
-  cudaMemcpyToSymbol(c_pdl_early, v, sizeof(v));
-  done = true;
+  return v != 0;
 }
 TNB_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-// big = 1 in the persistent tcgen05 kernels
-TNB_DEVINL void pdl_launch_dependents(int big = 0) {
-  if (c_pdl_early[big]) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
+TNB_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <typename... KArgs, typename... Args>
 inline int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  pdl_sync_constant();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -108,8 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  pdl_launch_dependents(1);  // the prologue above touched shared memory and TMEM only
-  pdl_wait();
+  pdl_wait();  // the prologue above touched shared memory and TMEM only: it overlaps the previous kernel's tail
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -430,7 +429,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  pdl_launch_dependents(1);
   pdl_wait();
 
   if (warp < 4) {
@@ -660,7 +658,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  pdl_launch_dependents(1);
   pdl_wait();
 
   if (warp < 4) {
