@@ -122,8 +122,7 @@ int tnb_conv3x3_pack_weights(const float* w_oihw, uint16_t* out, int cout, int c
 int tnb_conv3x3_stat_rows(int n, int h, int w, int cin, int cout, int terms);
 /* The launch plan tnb_conv3x3_fwd will use for this shape (pure host arithmetic, no device needed): out[0..11] = output-
  * channel tile BN, M tiles per CTA tile MT, halo-tile stages, weight-ring slots, taps per weight stage, TMEM accumulator
- * buffers, TMEM columns, dynamic shared memory in bytes, merged-weights flag, tile orientation, resident weights (0 = ring,
- * else the planes per halo-tile stage: 4 or 2),
+ * buffers, TMEM columns, dynamic shared memory in bytes, merged-weights flag, tile orientation, 0 (reserved),
  * weight-pack layout (0 [term][plane][rows], 1 [plane][term][rows]). Returns 0 or an error code. */
 int tnb_conv3x3_plan_query(int n, int h, int w, int cin, int cout, int terms, int* out12);
 int tnb_conv3x3_fwd(const tnb_view_t* view, const uint16_t* wpack, float* out, float* stat_part, int cout,

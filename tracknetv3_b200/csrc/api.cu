@@ -49,7 +49,7 @@ int tnb_conv3x3_pack_weights(const float* w, uint16_t* out, int cout, int cin, i
 int tnb_conv3x3_plan_query(int n, int h, int w, int cin, int cout, int terms, int* out12) {
   ConvPlan p;
   if (int rc = conv3x3_plan(n, h, w, (cin + 31) / 32 * 32, cout, terms, &p)) return rc;
-  const int v[12] = {p.BN, p.MT, p.SA, p.SB, p.G, p.nbuf, p.tmem_cols, (int)p.smem_bytes, p.merged, p.tall, p.resident ? p.nps : 0,
+  const int v[12] = {p.BN, p.MT, p.SA, p.SB, p.G, p.nbuf, p.tmem_cols, (int)p.smem_bytes, p.merged, p.tall, 0 /* (was: CTA-pair flag) */,
                      conv3x3_weight_layout(p.BN)};
   for (int i = 0; i < 12; ++i) out12[i] = v[i];
   return 0;

@@ -116,28 +116,6 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
     }
   }
   TNB_REQUIRE(found, "conv3x3: no shared-memory plan for Cin=%d Cout=%d", Cin, Cout);
-  // Resident weights. With ONE output-channel tile (Cout == BN) whose weight images all fit next to the halo-tile
-  // stages, every CTA loads them once and keeps them for the whole launch instead of re-streaming them for every pixel
-  // tile through the ring: on the 64 -> 64 layers that stream is 147 KB per 16 x 16-pixel tile against 82 KB of
-  // activations - 64 % of the kernel's L2 -> SM traffic, which at the MMA-bound rate would need ~80 % of the chip's L2
-  // bandwidth - plus six ring handshakes per tile. 64 -> 64 (147 KB of weights) only fits with 16-channel halo-tile
-  // stages (nps = 2, three of them); 27(32) -> 64 (74 KB) keeps 32-channel stages. TNB_CONV_RESIDENT=0: ring (ablation).
-  plan->nps = 4; plan->resident = 0;
-  static const int res_env = [] { const char* e = getenv("TNB_CONV_RESIDENT"); return e ? atoi(e) : 1; }();
-  if (res_env && Cout == BN && 9 % G == 0 && (Cin / 32) * (9 / G) <= 8) {
-    const int pitch = 8 * MT + 2, halo = 18 * pitch;
-    const size_t a_plane = (size_t)pad_px(halo) * 16;
-    const size_t wbytes = (size_t)(Cin / 32) * 9 * (merged ? 2 : TP) * 64 * BN;
-    const size_t fixed = kHdrBytes + ((halo * 8 + 127) & ~127) + (size_t)4 * 2 * BN * 4 + (bn_bwd_fused ? BN * 16 : 0);
-    for (int nps = 4; nps >= 2 && !plan->resident; nps >>= 1)
-      for (int sa = nps == 4 ? 3 : 4; sa >= (nps == 4 ? 2 : 3); --sa)
-        if (fixed + sa * TP * nps * a_plane + wbytes <= (size_t)kMaxSmem) {
-          plan->resident = 1; plan->nps = nps;
-          SA = sa; SB = (Cin / 32) * (9 / G);
-          smem = fixed + sa * TP * nps * a_plane + wbytes;
-          break;
-        }
-  }
   plan->BN = BN; plan->MT = MT; plan->SA = SA; plan->SB = SB; plan->G = G;
   plan->nbuf = (2 * MT * ACCW <= 512) ? 2 : 1;
   plan->tmem_cols = pow2_cols(plan->nbuf * MT * ACCW);

@@ -142,7 +142,6 @@ __host__ __device__ inline int pad_px(int px) {  // plane stride = 2 (mod 8) pix
 
 struct ConvPlan {
   int BN, MT, SA, SB, G, nbuf, tmem_cols, merged;
-  int nps, resident;  // planes per halo-tile stage (4 / 2); all weight images resident in shared memory (see conv3x3_plan)
   size_t smem_bytes;
   int tiles_h, tiles_w;
   int tall;  // tile orientation, see conv3x3_plan
