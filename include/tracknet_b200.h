@@ -66,9 +66,15 @@ typedef struct {
   float* dz;         /* apply:  [N,H,W,C] */
   float inv_count;
   float* amax;       /* apply, optional: device scalar, atomically raised to max|dz| (zero it first) */
-  int dz_format;     /* apply: 0 = fp32 [N,H,W,C]; 1 = pre-split bf16 (same byte size, see tnb_presplit_bf16) */
+  int dz_format;     /* apply: 0 = fp32 [N,H,W,C]; 1 = pre-split bf16 (same byte size, see tnb_presplit_bf16); 2 = pre-split
+                        fp16 after multiplication by a power of two chosen from gmax (22-bit operands for the tensor
+                        cores instead of 16; the multiplier is published in *dz_mul) */
   void* act_presplit; /* apply, optional: also write relu(scale*z+shift) - this layer's activation, the wgrad operand of
-                         the next layer - in the pre-split bf16 format (saves a tnb_view_presplit pass); NULL = off */
+                         the next layer - in the pre-split format (bf16, or fp16 with dz_format 2; saves a
+                         tnb_view_presplit pass); NULL = off */
+  float* gmax;       /* reduce, optional: device scalar, atomically raised to max |g| of the masked incoming gradient (zero
+                        it first); apply with dz_format 2: read */
+  float* dz_mul;     /* apply with dz_format 2: device scalar that receives the power-of-two multiplier dz was stored with */
 } tnb_bnbwd_t;
 
 typedef struct {
@@ -100,13 +106,19 @@ int tnb_pack_nchw_to_nhwc(const float* x_nchw, float* out_nhwc, int n, int c, in
  * (dz) are produced in this format by tnb_bn_relu_bwd_apply(dz_format = 1) and consumed by dgrad
  * (TNB_SRC_PRESPLIT view) and wgrad without any per-element arithmetic in the consumers. */
 int tnb_presplit_bf16(const float* x_nhwc, void* out, long long npixels, int c, void* stream);
+/* The same layout with fp16 (hi, lo) pairs of x * mul (x * mul ~ hi + lo to 2^-22; mul = a power of two that brings the
+ * tensor into fp16's range, values beyond +-65504 are clamped). What tnb_bn_relu_bwd_apply(dz_format = 2) writes; the
+ * consumers divide their results by mul (tnb_src_t.scale of a TNB_SRC_PRESPLIT source / the dz_mul arguments). */
+int tnb_presplit_fp16(const float* x_nhwc, void* out, long long npixels, int c, float mul, void* stream);
 /* Materialise a whole logical view (BN affine + ReLU + MaxPool / Upsample / cat of the producers) in the pre-split
  * format: out is [N,H,W][2 (hi, lo)][C] 16-bit, fmt 0 = fp16 (values clamped to +-65504), 1 = bf16. Used by the backward
  * pass so that the weight-gradient kernel's operand fills are plain copies (TNB_SRC_PRESPLIT). */
 int tnb_view_presplit(const tnb_view_t* view, void* out, int fmt, void* stream);
 
 /* Weight pre-packing for the tcgen05 kernels. mode 0: forward operand, mode 1: dgrad operand (rotated,
- * transposed). fmt 0: fp16 split, 1: bf16 split. Source is the reference's canonical OIHW parameter
+ * transposed). fmt 0: fp16 split of w * 2^10 (so that the lo halves of ~1e-2 weights stay normal fp16 numbers and the
+ * pair keeps 22 bits; tnb_conv3x3_fwd with fmt 0 multiplies its accumulators by 2^-10), 1: bf16 split. Source is the
+ * reference's canonical OIHW parameter
  * (`<block>.conv.weight`, model.py:8). The packed buffer is opaque: it is the shared-memory image the consuming
  * tnb_conv3x3_fwd launch streams with bulk TMA, one image per (output-channel tile, 32-channel chunk, filter tap), and
  * its inner layout follows the tile width the launcher will pick for this N side ([hi | lo][plane][rows], or
@@ -140,11 +152,13 @@ int tnb_conv3x3_dgrad_bnreduce(const tnb_view_t* view, const uint16_t* wpack, fl
 
 /* Weight gradient of the same convolution (autograd of model.py:13 via train.py:95):
  * dw[cout][cin_real][3][3] += sum dz * view. dw must be zeroed by the caller. dz is in the pre-split bf16 format
- * ([N,H,W,cout] logical); the view operand is split to bf16 on the fly. With a pre-split view three kernels exist:
+ * ([N,H,W,cout] logical) or, with fmt = 0, fp16 pairs of dz * (*dz_mul) (dz_mul: device scalar, may be NULL = 1; the
+ * result is divided by it); both operands must be of the SAME 16-bit format (fmt: 0 fp16, 1 bf16), a view operand that is
+ * not pre-split is split to that format on the fly. With a pre-split view three kernels exist:
  * CTA pairs (tcgen05 cta_group::2) when cout % 256 == 0 and the input tile is 128 channels, the tap-stacked kernel for
  * cout == 64, the single-CTA kernel otherwise; variant bit 32 forces the generic kernels, bit 64 the single-CTA one. */
 int tnb_conv3x3_wgrad(const tnb_view_t* view, const void* dz_presplit, float* dw_oihw, int cout, int cin_real,
-                      int terms, int variant, void* stream);
+                      int terms, int variant, int fmt, const float* dz_mul, void* stream);
 /* The same, DETERMINISTIC, with a scratch buffer of tnb_conv3x3_wgrad_ws_elems(view, cout) floats: every split-K CTA
  * stores its partial tap-major into its own slab (plain coalesced stores, no atomics) and a second small kernel sums the
  * slabs in split order into dw_oihw (dw need not be zeroed). Gradients are bit-identical from run to run, which is what
@@ -152,7 +166,7 @@ int tnb_conv3x3_wgrad(const tnb_view_t* view, const void* dz_presplit, float* dw
  * tnb_tracknet_backward uses. */
 size_t tnb_conv3x3_wgrad_ws_elems(const tnb_view_t* view, int cout);
 int tnb_conv3x3_wgrad_ws(const tnb_view_t* view, const void* dz_presplit, float* dw_oihw, int cout, int cin_real,
-                         int terms, int variant, float* scratch, void* stream);
+                         int terms, int variant, float* scratch, int fmt, const float* dz_mul, void* stream);
 
 /* BatchNorm2d statistics -> fused affine + running-stat update (model.py:9; torch defaults eps 1e-5,
  * momentum 0.1, unbiased running_var). training==0 uses the running statistics (model.eval()). */
@@ -285,6 +299,13 @@ int tnb_set_graph_replay(int on);
 int tnb_graph_stats(long long* out4);
 /* number of kernels launched by one forward / backward call (for bench.py's gpu_launches) */
 int tnb_tracknet_num_launches(const tnb_tracknet_cfg_t* cfg, int backward);
+/* Debugging aid (tools/diag_layers.py): where layer `layer` (0..16, state_dict order) keeps its tensors inside a
+ * workspace laid out for cfg. out_ptr[0..7] = z (raw conv output, fp32 NHWC), BatchNorm scale, shift, mean, invstd
+ * ([cout] fp32 each), dz (gradient w.r.t. z in the pre-split 16-bit format the backward pass uses), din (gradient w.r.t.
+ * the layer's input view, fp32 NHWC [N,H,W,cin]; NULL for layer 0), dz multiplier (device scalar; fp16 pairs only, else
+ * NULL); out_dim[0..4] = H, W, cin, cout, 16-bit format of dz (0 fp16 pairs of dz * multiplier, 1 bf16 pairs). Pointers
+ * are valid after tnb_tracknet_forward (z, scale ...) / tnb_tracknet_backward (dz, din) of the same cfg and workspace. */
+int tnb_tracknet_debug_layer(const tnb_tracknet_cfg_t* cfg, void* workspace, int layer, void** out_ptr8, int* out_dim5);
 
 /* ---- measurement support (bench.py roofline leg) -------------------------------------------- */
 /* Per-launch CUDA-event timing of the tensor-core and BN-backward kernels, recorded on the launching

@@ -67,36 +67,67 @@ def conv3x3(view, w_oihw, cout, terms=3, fmt=0, variant=0, stats=False, mode=0):
     return out, part
 
 
-def presplit(t_nhwc):
-    """fp32 NHWC -> the pre-split bf16 format (same byte size); returned as an opaque uint8 tensor."""
+BWD_FMT = 1  # 16-bit format of the backward pass's pre-split operands: 1 = bf16 pairs (the 3-term default), 0 = fp16 pairs of x * 2^k
+             # backward uses), 1 = bf16 pairs; the `bwd_fmt` fixture of the conv tests runs both
+
+
+def pow2_mul(t):
+    """the power of two that brings max |t| into [2^7, 2^8) (the rule of bn_bwd_kernel's dz_format 2)"""
+    m = float(t.abs().max())
+    if not (m > 0.0) or not np.isfinite(m):
+        return 1.0
+    return float(2.0 ** (8 - np.frexp(m)[1]))
+
+
+def presplit(t_nhwc, fmt=None, mul=1.0):
+    """fp32 NHWC -> the pre-split format (same byte size): bf16 (hi, lo) pairs, or fp16 pairs of x * mul; returned as an
+    opaque uint8 tensor."""
     L = lib()
+    fmt = BWD_FMT if fmt is None else fmt
     n, h, w, c = t_nhwc.shape
     out = torch.empty(t_nhwc.numel() * 4, dtype=torch.uint8, device=DEV)
-    _lib.check(L.tnb_presplit_bf16(t_nhwc.data_ptr(), out.data_ptr(), n * h * w, c, st()))
+    if fmt == 1:
+        assert mul == 1.0
+        _lib.check(L.tnb_presplit_bf16(t_nhwc.data_ptr(), out.data_ptr(), n * h * w, c, st()))
+    else:
+        _lib.check(L.tnb_presplit_fp16(t_nhwc.data_ptr(), out.data_ptr(), n * h * w, c, mul, st()))
     return out
 
 
-def unsplit(buf, shape_nhwc):
-    """inverse of presplit (hi + lo) for checking: uint8 buffer -> fp32 NHWC."""
+def unsplit(buf, shape_nhwc, fmt=None, mul=1.0):
+    """inverse of presplit ((hi + lo) / mul) for checking: uint8 buffer -> fp32 NHWC."""
+    fmt = BWD_FMT if fmt is None else fmt
     n, h, w, c = shape_nhwc
-    v = buf.view(torch.bfloat16).reshape(n, h, w, 2, c).float()  # [pixel][2 (hi, lo)][C]
-    return v[..., 0, :] + v[..., 1, :]
+    v = buf.view(torch.bfloat16 if fmt == 1 else torch.float16).reshape(n, h, w, 2, c).double()  # [pixel][2 (hi, lo)][C]
+    return ((v[..., 0, :] + v[..., 1, :]) / mul).float()
 
 
-def wgrad3x3(view, dz_nhwc, cout, cin_real, terms=3, variant=0, scratch=False):
-    """production configuration: dz pre-split to bf16, view split on the fly. scratch=True: the deterministic split-K
+def split_tol(fmt=None):
+    """relative size of what hi + lo drops: 2^-17 for bf16 pairs, 2^-23 for fp16 pairs (fp32 itself)"""
+    fmt = BWD_FMT if fmt is None else fmt
+    return 2e-5 if fmt == 1 else 3e-7
+
+
+def wgrad3x3(view, dz_nhwc, cout, cin_real, terms=3, variant=0, scratch=False, fmt=None):
+    """production configuration: dz pre-split (fp16 pairs of dz * 2^k with the multiplier in a device scalar, or bf16
+    pairs), a view that is not pre-split is split to the same format on the fly. scratch=True: the deterministic split-K
     slab + ordered-sum path that tnb_tracknet_backward uses (slabs and dw start as NaN: every element must be written)."""
     L = lib()
-    dzs = presplit(dz_nhwc)
+    fmt = BWD_FMT if fmt is None else fmt
+    mul = pow2_mul(dz_nhwc) if fmt == 0 else 1.0
+    dzs = presplit(dz_nhwc, fmt, mul)
+    mul_dev = torch.tensor([mul], device=DEV) if fmt == 0 else None
+    mul_ptr = mul_dev.data_ptr() if mul_dev is not None else None
     if scratch:
         dw = torch.full((cout, cin_real, 3, 3), float("nan"), device=DEV)
         ws = torch.full((L.tnb_conv3x3_wgrad_ws_elems(C.byref(view), cout),), float("nan"), device=DEV)
         _lib.check(L.tnb_conv3x3_wgrad_ws(C.byref(view), dzs.data_ptr(), dw.data_ptr(), cout, cin_real, terms, variant,
-                                          ws.data_ptr(), st()))
+                                          ws.data_ptr(), fmt, mul_ptr, st()))
         torch.cuda.synchronize()
         return dw
     dw = torch.zeros((cout, cin_real, 3, 3), device=DEV)
-    _lib.check(L.tnb_conv3x3_wgrad(C.byref(view), dzs.data_ptr(), dw.data_ptr(), cout, cin_real, terms, variant, st()))
+    _lib.check(L.tnb_conv3x3_wgrad(C.byref(view), dzs.data_ptr(), dw.data_ptr(), cout, cin_real, terms, variant, fmt,
+                                   mul_ptr, st()))
     torch.cuda.synchronize()
     return dw
 

@@ -14,6 +14,25 @@ pytestmark = pytest.mark.gpu
 TOL = {3: 2e-5, 1: 4e-3}  # relative to the output max-abs: 3-term split is fp32-faithful, 1-term is TF32-class
 
 
+@pytest.fixture(params=[0, 1], ids=["fp16x2^k", "bf16"])
+def bwd_fmt(request):
+    """format of the backward pass's pre-split operands: fp16 pairs of x * 2^k (the network's backward), bf16 pairs"""
+    old, G.BWD_FMT = G.BWD_FMT, request.param
+    yield request.param
+    G.BWD_FMT = old
+
+
+def _dz_src(dz_nhwc, cout, h, w, fmt, keep):
+    """pre-split gradient tensor as a dgrad view source; fp16: stored multiplied by 2^k, `scale` points at the multiplier"""
+    mul = G.pow2_mul(dz_nhwc) if fmt == 0 else 1.0
+    ts = G.presplit(dz_nhwc, fmt, mul)
+    mul_dev = torch.tensor([mul], device=G.DEV)
+    keep += [ts, mul_dev]
+    src = _lib.Src(ptr=ts.data_ptr(), scale=mul_dev.data_ptr() if fmt == 0 else None, shift=None, C=cout, Hs=h, Ws=w,
+                   mode=_lib.SRC_PRESPLIT)
+    return src, ts, mul
+
+
 def _rand(*shape, seed=0, scale=1.0):
     return (torch.rand(*shape, generator=torch.Generator().manual_seed(seed)) * 2 - 1) * scale
 
@@ -60,7 +79,7 @@ def test_conv3x3_first_layer_padding_27_channels():
 
 
 @pytest.mark.parametrize("mode", ["affine_relu", "pool", "up_concat"])
-def test_conv3x3_fused_views(mode):
+def test_conv3x3_fused_views(mode, bwd_fmt):
     """BatchNorm-apply + ReLU (+ MaxPool | Upsample + cat) fused into the operand load (model.py:14-15,59-69)."""
     n, h, w = 1, 16, 24
     gen = torch.Generator().manual_seed(5)
@@ -101,8 +120,8 @@ def test_conv3x3_fused_views(mode):
     L = G.lib()
     view = G.make_view(srcs, n, h, w)
     vs = torch.empty(n * h * w * xin.shape[1] * 4, dtype=torch.uint8, device=G.DEV)
-    _lib.check(L.tnb_view_presplit(C.byref(view), vs.data_ptr(), 1, G.st()))
-    assert G.max_abs(G.unsplit(vs, (n, h, w, xin.shape[1])), xin.permute(0, 2, 3, 1)) < 2e-5 * xin.abs().max().item()
+    _lib.check(L.tnb_view_presplit(C.byref(view), vs.data_ptr(), bwd_fmt, G.st()))
+    assert G.max_abs(G.unsplit(vs, (n, h, w, xin.shape[1])), xin.permute(0, 2, 3, 1)) < G.split_tol() * xin.abs().max().item()
     psrc = _lib.Src(ptr=vs.data_ptr(), scale=None, shift=None, C=xin.shape[1], Hs=h, Ws=w, mode=_lib.SRC_PRESPLIT)
     dw2 = G.wgrad3x3(G.make_view([psrc], n, h, w), keep[-1], 64, xin.shape[1])
     assert G.rel_err(dw2, wz.grad) < 2e-4
@@ -111,21 +130,22 @@ def test_conv3x3_fused_views(mode):
 
 @pytest.mark.parametrize("terms", [3, 1])
 @pytest.mark.parametrize("n,h,w,cin,cout", [(1, 16, 16, 64, 64), (2, 20, 24, 192, 64), (1, 16, 16, 128, 256)])
-def test_conv3x3_dgrad(n, h, w, cin, cout, terms):
-    """dIn = conv(dz, rot180(W)^T) through the same kernel: weights packed with mode 1 (bf16), dz (~1e-6, needs
-    fp32's exponent range) supplied in the pre-split bf16 format so that the operand fill is a pure copy."""
+def test_conv3x3_dgrad(n, h, w, cin, cout, terms, bwd_fmt):
+    """dIn = conv(dz, rot180(W)^T) through the same kernel: weights packed with mode 1, dz (~1e-6: bf16 pairs keep fp32's
+    exponent range, fp16 pairs are stored multiplied by a power of two that the epilogue divides out) supplied in the
+    pre-split format so that the operand fill is a pure copy."""
     dz = _rand(n, cout, h, w, seed=11, scale=1e-6)
     wt = _rand(cout, cin, 3, 3, seed=12, scale=0.2)
     ref = F.conv_transpose2d(dz, wt, padding=1)
     t = G.nhwc(dz)
-    ts = G.presplit(t)
-    assert G.max_abs(G.unsplit(ts, t.shape), t) < 2e-5 * 1e-6  # hi + lo reproduces dz to ~2^-17
-    src = _lib.Src(ptr=ts.data_ptr(), scale=None, shift=None, C=cout, Hs=h, Ws=w, mode=_lib.SRC_PRESPLIT)
-    out, _ = G.conv3x3(G.make_view([src], n, h, w), wt.to(G.DEV), cin, terms=terms, fmt=1, mode=1)
+    keep = []
+    src, ts, mul = _dz_src(t, cout, h, w, bwd_fmt, keep)
+    assert G.max_abs(G.unsplit(ts, t.shape, bwd_fmt, mul), t) < G.split_tol() * 1e-6  # hi + lo: dz to ~2^-17 / 2^-23
+    out, _ = G.conv3x3(G.make_view([src], n, h, w), wt.to(G.DEV), cin, terms=terms, fmt=bwd_fmt, mode=1)
     assert G.rel_err(G.nchw(out), ref) < (2e-4 if terms == 3 else 2e-2)
-    # identity (fp32) source with on-the-fly bf16 split gives the same numbers
+    # identity (fp32) source with on-the-fly bf16 split gives the same numbers as the pre-split bf16 source
     out2, _ = G.conv3x3(G.make_view([G.make_src(t)], n, h, w), wt.to(G.DEV), cin, terms=terms, fmt=1, mode=1)
-    assert G.rel_err(out2, out) < 1e-6
+    assert G.rel_err(out2, out) < (1e-6 if bwd_fmt == 1 else (2e-4 if terms == 3 else 2e-2))
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout", [(1, 16, 16, 64, 64), (2, 20, 24, 128, 256), (1, 24, 40, 512, 512)])
@@ -146,7 +166,7 @@ def test_conv3x3_dgrad_fused_bn_reduce(n, h, w, cin, cout):
     g = torch.where(z * bc(scale) + bc(shift) > 0, din, torch.zeros_like(din)).double()
     ref1 = g.sum((0, 2, 3))
     ref2 = (g * ((z.double() - bc(mean).double()) * bc(invstd).double())).sum((0, 2, 3))
-    ts = G.presplit(G.nhwc(dz))
+    ts = G.presplit(G.nhwc(dz), 1)  # this (experimental) entry point takes bf16 pairs only
     src = _lib.Src(ptr=ts.data_ptr(), scale=None, shift=None, C=cout, Hs=h, Ws=w, mode=_lib.SRC_PRESPLIT)
     view = G.make_view([src], n, h, w)
     wp = G.pack_weights(wt.to(G.DEV), 1, 1)
@@ -176,7 +196,7 @@ def test_conv3x3_dgrad_fused_bn_reduce(n, h, w, cin, cout):
     (1, 8, 16, 128, 128, 256),   # two co tiles, NT = 128
     (2, 12, 40, 256, 256, 128),  # ragged 4x16 K tiles, two ci tiles of 128
 ])
-def test_conv3x3_wgrad(n, h, w, cin, cin_real, cout, terms):
+def test_conv3x3_wgrad(n, h, w, cin, cin_real, cout, terms, bwd_fmt):
     x = _rand(n, cin, h, w, seed=13)
     x[:, cin_real:] = 0
     dz = _rand(n, cout, h, w, seed=14, scale=1e-5)
@@ -198,7 +218,7 @@ def test_conv3x3_wgrad(n, h, w, cin, cin_real, cout, terms):
     (2, 12, 40, 192, 192),    # up_block_3.conv_1: three ci tiles
     (1, 4, 16, 128, 128),     # a single K tile per CTA
 ])
-def test_conv3x3_wgrad_tap_stacked(n, h, w, cin, cin_real, terms):
+def test_conv3x3_wgrad_tap_stacked(n, h, w, cin, cin_real, terms, bwd_fmt):
     """Cout = 64 with a pre-split view takes the tap-stacked kernel (two filter rows per MMA); the generic kernel on
     the same operands (variant bit 32) must agree with it and both with the oracle op."""
     cout = 64
@@ -229,7 +249,7 @@ def test_conv3x3_wgrad_tap_stacked(n, h, w, cin, cin_real, terms):
     (1, 20, 24, 128, 512),    # two pairs along the output channels
     (3, 16, 48, 384, 256),    # three input-channel tiles, K range split over several CTAs
 ])
-def test_conv3x3_wgrad_cta_pair(n, h, w, cin, cout, terms):
+def test_conv3x3_wgrad_cta_pair(n, h, w, cin, cout, terms, bwd_fmt):
     """Cout % 256 == 0 with pre-split operands and a 128-channel input tile runs on CTA pairs (tcgen05 cta_group::2:
     each CTA loads its own 128 dz rows and half of the view tile); the single-CTA kernel on the same operands (variant
     bit 64) must agree with it and both with the oracle op."""
@@ -251,7 +271,7 @@ def test_conv3x3_wgrad_cta_pair(n, h, w, cin, cout, terms):
 
 
 @pytest.mark.parametrize("c_up,c_skip,cout", [(128, 64, 64), (64, 64, 64), (256, 128, 128), (512, 256, 256)])
-def test_conv3x3_wgrad_concat_of_half_resolution_source(c_up, c_skip, cout):
+def test_conv3x3_wgrad_concat_of_half_resolution_source(c_up, c_skip, cout, bwd_fmt):
     """Decoder concat view [upsample(x), skip] given as two pre-split sources, the first one at half resolution
     (TNB_SRC_PRESPLIT_UP: the fill reads pixel (h/2, w/2)): Cout 64 runs the tap-stacked kernel with per-tile source
     selection, larger Cout the generic kernel (one launch per source)."""

@@ -341,17 +341,30 @@ def test_bn_relu_backward_with_gradient_routing(consumers):
     torch.cuda.synchronize()
     assert G.rel_err(G.nchw(dz), z.grad) < 2e-4
     assert amax.item() == dz.abs().max().item()
-    # production format: the same dz emitted pre-split (bf16 hi/lo) for the dgrad / wgrad operand fills
-    dzs = torch.zeros(n * h * w * c * 4, dtype=torch.uint8, device=G.DEV)
-    args.dz, args.dz_format, args.amax = dzs.data_ptr(), 1, None
+    # production formats: the same dz emitted pre-split for the dgrad / wgrad operand fills - bf16 (hi, lo) pairs
+    # (dz_format 1), or fp16 pairs of dz * 2^k with k derived from max |g|, which the reduction pass measures (dz_format 2)
     # ... and, in the same pass, the layer's own activation relu(bn(z)) pre-split: the next layer's wgrad operand
-    acts = torch.zeros(n * h * w * c * 4, dtype=torch.uint8, device=G.DEV)
-    args.act_presplit = acts.data_ptr()
-    _lib.check(L.tnb_bn_relu_bwd_apply(C.byref(args), G.st()))
-    torch.cuda.synchronize()
-    assert G.max_abs(G.unsplit(dzs, (n, h, w, c)), dz) <= 2e-5 * dz.abs().max().item()
     act_ref = F.relu(z.detach() * scale[None, :, None, None] + shift[None, :, None, None])
-    assert G.max_abs(G.unsplit(acts, (n, h, w, c)), G.nhwc(act_ref)) <= 2e-5 * act_ref.abs().max().item()
+    for dz_format in (1, 2):
+        fmt = 1 if dz_format == 1 else 0
+        dzs = torch.zeros(n * h * w * c * 4, dtype=torch.uint8, device=G.DEV)
+        acts = torch.zeros(n * h * w * c * 4, dtype=torch.uint8, device=G.DEV)
+        gm = torch.zeros(2, device=G.DEV)  # [max |g|, multiplier]
+        args.dz, args.dz_format, args.amax = dzs.data_ptr(), dz_format, None
+        args.act_presplit = acts.data_ptr()
+        mul = 1.0
+        if dz_format == 2:
+            args.gmax, args.dz_mul = gm.data_ptr(), gm.data_ptr() + 4
+            _lib.check(L.tnb_bn_relu_bwd_reduce(C.byref(args), G.st()))  # measures max |g| (partials as before)
+        _lib.check(L.tnb_bn_relu_bwd_apply(C.byref(args), G.st()))
+        torch.cuda.synchronize()
+        if dz_format == 2:
+            gmax, mul = gm.tolist()
+            assert gmax > 0 and mul == 2.0 ** round(np.log2(mul))  # a power of two ...
+            assert 2.0 ** 7 <= mul * gmax * scale.abs().max().item() < 2.0 ** 8  # ... chosen by the documented rule
+            assert dz.abs().max().item() * mul < 65504  # nothing was clamped
+        assert G.max_abs(G.unsplit(dzs, (n, h, w, c), fmt, mul), dz) <= G.split_tol(fmt) * dz.abs().max().item()
+        assert G.max_abs(G.unsplit(acts, (n, h, w, c), fmt), G.nhwc(act_ref)) <= G.split_tol(fmt) * act_ref.abs().max().item()
     # d gamma / d beta from the same reductions (checked through a second autograd pass)
     z2 = z.detach().clone(); g2 = gamma.clone().requires_grad_(True); b2 = beta.clone().requires_grad_(True)
     a2 = F.relu(F.batch_norm(z2, None, None, g2, b2, True, 0.1, 1e-5))

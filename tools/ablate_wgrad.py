@@ -12,12 +12,12 @@ L = G.lib()
 def time_wgrad(n, h, w, cin, cout, variant, terms=3, reps=5):
     x = torch.rand(n, h, w, cin, device="cuda")
     dz = (torch.rand(n, h, w, cout, device="cuda") - 0.5) * 1e-5
-    xs, dzs = G.presplit(x), G.presplit(dz)
+    xs, dzs = G.presplit(x, 1), G.presplit(dz, 1)  # bf16 pairs
     src = _lib.Src(ptr=xs.data_ptr(), scale=None, shift=None, C=cin, Hs=h, Ws=w, mode=_lib.SRC_PRESPLIT)
     view = G.make_view([src], n, h, w)
     dw = torch.zeros(cout, cin, 3, 3, device="cuda")
     def run():
-        _lib.check(L.tnb_conv3x3_wgrad(C.byref(view), dzs.data_ptr(), dw.data_ptr(), cout, cin, terms, variant, G.st()))
+        _lib.check(L.tnb_conv3x3_wgrad(C.byref(view), dzs.data_ptr(), dw.data_ptr(), cout, cin, terms, variant, 1, None, G.st()))
     for _ in range(2): run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -33,7 +33,8 @@ class BnBwd(C.Structure):  # tnb_bnbwd_t
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
                 ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
                 ("part", C.c_void_p), ("sums", C.c_void_p), ("dz", C.c_void_p), ("inv_count", C.c_float),
-                ("amax", C.c_void_p), ("dz_format", C.c_int), ("act_presplit", C.c_void_p)]
+                ("amax", C.c_void_p), ("dz_format", C.c_int), ("act_presplit", C.c_void_p),
+                ("gmax", C.c_void_p), ("dz_mul", C.c_void_p)]
 
 
 class TrackNetCfg(C.Structure):  # tnb_tracknet_cfg_t
@@ -59,10 +60,11 @@ SIGNATURES = {
     "tnb_conv3x3_fwd": (i32, [C.POINTER(View), vp, vp, vp, i32, i32, i32, i32, vp]),
     "tnb_conv3x3_dgrad_bnreduce_rows": (i32, [i32, i32, i32, i32, i32, i32]),
     "tnb_conv3x3_dgrad_bnreduce": (i32, [C.POINTER(View), vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
-    "tnb_conv3x3_wgrad": (i32, [C.POINTER(View), vp, vp, i32, i32, i32, i32, vp]),
+    "tnb_conv3x3_wgrad": (i32, [C.POINTER(View), vp, vp, i32, i32, i32, i32, i32, vp, vp]),
     "tnb_conv3x3_wgrad_ws_elems": (sz, [C.POINTER(View), i32]),
-    "tnb_conv3x3_wgrad_ws": (i32, [C.POINTER(View), vp, vp, i32, i32, i32, i32, vp, vp]),
+    "tnb_conv3x3_wgrad_ws": (i32, [C.POINTER(View), vp, vp, i32, i32, i32, i32, vp, i32, vp, vp]),
     "tnb_presplit_bf16": (i32, [vp, vp, i64, i32, vp]),
+    "tnb_presplit_fp16": (i32, [vp, vp, i64, i32, f32, vp]),
     "tnb_view_presplit": (i32, [C.POINTER(View), vp, i32, vp]),
     "tnb_bn_finalize": (i32, [vp, i32, f64, vp, vp, vp, vp, f32, f32, i32, vp, vp, vp, vp, i32, vp]),
     "tnb_bn_bwd_blocks": (i32, [i32, i32, i32, i32]),
@@ -94,6 +96,7 @@ SIGNATURES = {
     "tnb_set_graph_replay": (i32, [i32]),
     "tnb_graph_stats": (i32, [C.POINTER(C.c_longlong)]),
     "tnb_tracknet_num_launches": (i32, [C.POINTER(TrackNetCfg), i32]),
+    "tnb_tracknet_debug_layer": (i32, [C.POINTER(TrackNetCfg), vp, i32, C.POINTER(vp), C.POINTER(i32)]),
     "tnb_profile_enable": (i32, [i32]),
     "tnb_profile_collect": (i32, [i32, vp, vp]),
 }

@@ -16,12 +16,17 @@ int tracknet_forward(const tnb_tracknet_cfg_t& c, const float* x, void* const* p
 int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float* y, void* const* params,
                       void* const* grads, void* ws, size_t ws_bytes, cudaStream_t st);
 int tracknet_num_launches(const tnb_tracknet_cfg_t& c, int backward);
+int tracknet_debug_layer(const tnb_tracknet_cfg_t& c, void* ws, int layer, void** out_ptr8, int* out_dim5);
 int set_graph_replay(int on);
 void graph_stats(long long* out4);
 }  // namespace tnb
 
 using namespace tnb;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+#ifdef TNB_TRACE
+namespace tnb { long long* g_conv_trace = nullptr; }
+#endif
 
 extern "C" {
 
@@ -33,7 +38,10 @@ int tnb_pack_nchw_to_nhwc(const float* x, float* out, int n, int c, int h, int w
   return launch_pack_input(x, out, n, c, h, w, cpad, ST(stream));
 }
 int tnb_presplit_bf16(const float* x, void* out, long long npixels, int c, void* stream) {
-  return launch_presplit_bf16(x, out, npixels, c, ST(stream));
+  return launch_presplit(x, out, npixels, c, 1, 1.f, ST(stream));
+}
+int tnb_presplit_fp16(const float* x, void* out, long long npixels, int c, float mul, void* stream) {
+  return launch_presplit(x, out, npixels, c, 0, mul, ST(stream));
 }
 int tnb_view_presplit(const tnb_view_t* view, void* out, int fmt, void* stream) {
   return launch_view_presplit(*view, out, fmt, ST(stream));
@@ -71,13 +79,13 @@ int tnb_conv3x3_dgrad_bnreduce(const tnb_view_t* view, const uint16_t* wpack, fl
   return launch_conv3x3(*view, wpack, out, part, cout, terms, 1, 0, ST(stream), &fuse);
 }
 int tnb_conv3x3_wgrad(const tnb_view_t* view, const void* dz_presplit, float* dw, int cout, int cin_real, int terms,
-                      int variant, void* stream) {
-  return launch_wgrad3x3(*view, dz_presplit, dw, cout, cin_real, terms, variant, ST(stream));
+                      int variant, int fmt, const float* dz_mul, void* stream) {
+  return launch_wgrad3x3(*view, dz_presplit, dw, cout, cin_real, terms, variant, ST(stream), nullptr, fmt, dz_mul);
 }
 size_t tnb_conv3x3_wgrad_ws_elems(const tnb_view_t* view, int cout) { return wgrad3x3_ws_floats(*view, cout); }
 int tnb_conv3x3_wgrad_ws(const tnb_view_t* view, const void* dz_presplit, float* dw, int cout, int cin_real, int terms,
-                         int variant, float* scratch, void* stream) {
-  return launch_wgrad3x3(*view, dz_presplit, dw, cout, cin_real, terms, variant, ST(stream), scratch);
+                         int variant, float* scratch, int fmt, const float* dz_mul, void* stream) {
+  return launch_wgrad3x3(*view, dz_presplit, dw, cout, cin_real, terms, variant, ST(stream), scratch, fmt, dz_mul);
 }
 int tnb_bn_finalize(const float* part, int rows, double count, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, float momentum, float eps, int training, float* scale,
@@ -194,5 +202,13 @@ int tnb_graph_stats(long long* out4) { graph_stats(out4); return 0; }
 int tnb_tracknet_num_launches(const tnb_tracknet_cfg_t* cfg, int backward) {
   return tracknet_num_launches(*cfg, backward);
 }
+int tnb_tracknet_debug_layer(const tnb_tracknet_cfg_t* cfg, void* workspace, int layer, void** out_ptr8, int* out_dim5) {
+  return tracknet_debug_layer(*cfg, workspace, layer, out_ptr8, out_dim5);
+}
 
+#ifdef TNB_TRACE
+// debug build only (make TRACE=1 -> libtracknet_b200_trace.so; not part of the ABI): per-role clock64 stamps of CTA 0 of
+// the conv kernels into a device buffer of 4 * 24 * 32 int64 (tools/trace_conv.py)
+int tnb_debug_set_trace(void* dev_buf) { tnb::g_conv_trace = (long long*)dev_buf; return 0; }
+#endif
 }  // extern "C"

@@ -343,6 +343,14 @@ TNB_DEVINL uint32_t make_idesc2(int M, int N, int a_format, int b_format, int a_
 // fp32 -> (hi, lo) 16-bit split. x ~= hi + lo with hi = rn16(x), lo = rn16(x - hi).
 // FMT 0: fp16 (clamped to the finite range), FMT 1: bf16.
 // ---------------------------------------------------------------------------------------------
+// fp16 (hi, lo) pairs carry 22 bits only while lo = fp16(x - hi) ~ 2^-11 |x| stays a NORMAL fp16 number, i.e. for
+// |x| >= 2^-3. Convolution weights are ~1e-2 (Kaiming bound 1 / sqrt(9 Cin)): unscaled, their lo halves are subnormal and
+// the pair keeps ~18 bits (measured: that alone was the forward's 4e-5 heatmap distance and 10-20x the fp32 rate of ReLU
+// mask flips in the backward pass). Weights packed in fp16 are therefore stored multiplied by 2^10 (22 bits for every
+// |w| >= 2^-13, clamped beyond |w| = 63.97) and the convolution epilogue multiplies the accumulator by 2^-10: exact.
+constexpr float kW16Mul = 1024.f;
+constexpr float kW16Inv = 1.f / 1024.f;
+
 template <int FMT>
 TNB_DEVINL void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
   if (FMT == 0) {

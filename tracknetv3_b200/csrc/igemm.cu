@@ -67,7 +67,13 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant
       v[e] = x;
     }
     uint4 hi, lo;
-    if (E.fmt == 0) split8<0>(v, hi, lo); else split8<1>(v, hi, lo);
+    if (E.fmt == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] *= kW16Mul;  // keeps the lo halves normal fp16 numbers, see common.cuh
+      split8<0>(v, hi, lo);
+    } else {
+      split8<1>(v, hi, lo);
+    }
     // stage base (uint16 elements): ((ntile*nchunks + chunk)*9 + tap) * (2*4*BN*8)
     const size_t stage = (((size_t)ntile * nchunks + chunk) * 9 + tap) * (size_t)(64 * BN);
     // [term][plane][BN rows][8], or for the merged 64-wide tiles [plane][term][BN rows][8] (conv3x3_merged): hi and lo

@@ -170,6 +170,9 @@ int launch_conv3x3_generic(const ViewDesc& view, const uint16_t* wpack, float* o
 int launch_conv3x3_lean(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout, int nterms,
                         int fmt, int variant, const ConvPlan& plan, cudaStream_t st, const BnBwdFuse* fuse = nullptr);
 int num_sms();
+#ifdef TNB_TRACE
+extern long long* g_conv_trace;  // debug build (make TRACE=1): set by tnb_debug_set_trace, read by the conv launchers
+#endif
 int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout,
                    int nterms, int fmt, int variant, cudaStream_t st, const BnBwdFuse* fuse = nullptr);
 int conv3x3_num_stat_rows(int N, int H, int W, int Cin, int Cout, int nterms, bool bn_bwd_fused = false);
@@ -179,7 +182,9 @@ int conv3x3_num_stat_rows(int N, int H, int W, int Cin, int Cout, int nterms, bo
 // dw_oihw: deterministic, plain stores, dw need not be zeroed. Without it the partials are added into dw_oihw with
 // atomics (the caller zeroes it; summation order, hence the last bits, vary from run to run).
 size_t wgrad3x3_ws_floats(const ViewDesc& view, int Cout);
+// fmt: 16-bit format of the pre-split operands (0 fp16, 1 bf16; the view operand, if split on the fly, follows it);
+// dz_mul: optional device scalar dz was stored multiplied by (tnb_bnbwd_t.dz_format 2) - the result is divided by it
 int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw_oihw, int Cout, int CinReal, int nterms,
-                    int variant, cudaStream_t st, float* ws = nullptr);
+                    int variant, cudaStream_t st, float* ws = nullptr, int fmt = 1, const float* dz_mul = nullptr);
 
 }  // namespace tnb

@@ -406,6 +406,29 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnB
   const unsigned cq_shift = 31 - __clz(CQ);             // CQ is a power of two (256 % CQ == 0)
   float4 acc1 = make_float4(0, 0, 0, 0), acc2 = make_float4(0, 0, 0, 0);
   float amax = 0.f;
+  // dz_format 2: dz leaves as an fp16 (hi, lo) pair - 22 bits instead of bf16's 16 - after multiplication by a power of
+  // two that brings the tensor into fp16's range. |dz| <= max_c |scale_c| * (|g| + |mean g| + |xhat| |mean g xhat|) with
+  // max |g| measured by the reduction pass: the multiplier puts max_c |scale_c| * max |g| into [2^7, 2^8), which leaves
+  // a factor 256 of head room for the bracket (values beyond are clamped by the split, never infinite). Every CTA
+  // derives the same multiplier; block 0 publishes it for the consumers (dgrad / wgrad divide their accumulators by it).
+  float dz_mul = 1.f;
+  if (APPLY && a.dz_format == 2) {
+    __shared__ float s_scmax[8];
+    float m = 0.f;
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) m = fmaxf(m, fabsf(a.scale[c]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) s_scmax[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = 0.f;
+    for (int i = 0; i < 8; ++i) m = fmaxf(m, s_scmax[i]);
+    const float bound = m * (*a.gmax);
+    if (bound > 0.f && bound < 3.0e38f) {
+      int e;
+      frexpf(bound, &e);
+      dz_mul = ldexpf(1.f, max(-100, min(100, 8 - e)));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.dz_mul = dz_mul;
+  }
   for (unsigned it0 = blockIdx.x * blockDim.x + threadIdx.x; it0 < items; it0 += stride) {
     const unsigned it = it0;
     const int cq = (int)(it & (CQ - 1));
@@ -525,24 +548,35 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnB
         if (a.dz_format == 0) {
           *reinterpret_cast<float4*>(a.dz + pix * a.C + c) = o;
         } else {
-          // pre-split bf16: [pixel][2 (hi, lo)][C]; this thread owns channels c..c+3 (8 bytes of each term)
+          // pre-split: [pixel][2 (hi, lo)][C]; this thread owns channels c..c+3 (8 bytes of each term)
           uint32_t h01, l01, h23, l23;
-          split2<1>(o.x, o.y, h01, l01);
-          split2<1>(o.z, o.w, h23, l23);
+          if (a.dz_format == 2) {
+            split2<0>(o.x * dz_mul, o.y * dz_mul, h01, l01);
+            split2<0>(o.z * dz_mul, o.w * dz_mul, h23, l23);
+          } else {
+            split2<1>(o.x, o.y, h01, l01);
+            split2<1>(o.z, o.w, h23, l23);
+          }
           uint8_t* base = reinterpret_cast<uint8_t*>(a.dz) + (pix * 2 * a.C + c) * 2;
           *reinterpret_cast<uint2*>(base) = make_uint2(h01, h23);
           *reinterpret_cast<uint2*>(base + 2 * a.C) = make_uint2(l01, l23);
         }
         if (a.act_presplit != nullptr) {  // the activation itself, pre-split: the next layer's wgrad operand
           uint32_t h01, l01, h23, l23;
+          if (a.dz_format == 2) {
+            split2<0>(fmaxf(act[k].x, 0.f), fmaxf(act[k].y, 0.f), h01, l01);
+            split2<0>(fmaxf(act[k].z, 0.f), fmaxf(act[k].w, 0.f), h23, l23);
+          } else {
           split2<1>(fmaxf(act[k].x, 0.f), fmaxf(act[k].y, 0.f), h01, l01);
           split2<1>(fmaxf(act[k].z, 0.f), fmaxf(act[k].w, 0.f), h23, l23);
+          }
           uint8_t* base = reinterpret_cast<uint8_t*>(a.act_presplit) + (pix * 2 * a.C + c) * 2;
           *reinterpret_cast<uint2*>(base) = make_uint2(h01, h23);
           *reinterpret_cast<uint2*>(base + 2 * a.C) = make_uint2(l01, l23);
         }
         amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
       } else {
+        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w))));  // max |g|
         acc1 = f4add(acc1, d);
         acc2.x = fmaf(d.x, xh.x, acc2.x);
         acc2.y = fmaf(d.y, xh.y, acc2.y);
@@ -554,6 +588,10 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnB
   if (APPLY && a.amax != nullptr) {
     amax = warp_max(amax);  // non-negative floats order like their bit patterns
     if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(reinterpret_cast<int*>(a.amax), __float_as_int(amax));
+  }
+  if (!APPLY && a.gmax != nullptr) {  // max |g| over the tensor (a maximum: the order of the atomics does not matter)
+    amax = warp_max(amax);
+    if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(reinterpret_cast<int*>(a.gmax), __float_as_int(amax));
   }
   if (!APPLY) {
     // every thread keeps one channel quad for its whole grid-stride loop (256 % CQ == 0, stride % CQ == 0)
@@ -583,6 +621,8 @@ static int bn_bwd_cfg(const BnBwdArgs& a) {
 }
 static int bn_bwd_check(const BnBwdArgs& a) {
   TNB_REQUIRE(a.C % 4 == 0 && 256 % (a.C / 4) == 0, "bn_bwd: unsupported channel count %d", a.C);
+  TNB_REQUIRE(a.dz_format >= 0 && a.dz_format <= 2 && (a.dz_format != 2 || (a.gmax != nullptr && a.dz_mul != nullptr)),
+              "bn_bwd: dz_format %d (2 needs the gmax / dz_mul scalars)", a.dz_format);
   TNB_REQUIRE((long long)a.N * ((a.H + 1) / 2) * ((a.W + 1) / 2) * (a.C / 4) < (1ll << 31), "bn_bwd: tensor too large");
   return 0;
 }
@@ -628,15 +668,22 @@ int launch_bn_bwd_finalize(const float* part, int rows, int C, float* sums, floa
   return 0;
 }
 
-// fp32 NHWC -> pre-split bf16 [pixel][2 (hi, lo)][C] (see include/tracknet_b200.h)
-__global__ void presplit_bf16_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, long long nchunks, int C) {
+// fp32 NHWC -> pre-split [pixel][2 (hi, lo)][C] (see include/tracknet_b200.h): bf16, or fp16 after multiplication by mul
+__global__ void presplit_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, long long nchunks, int C, int fmt,
+                                float mul) {
   const int nch = C >> 3;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nchunks;
        i += (long long)gridDim.x * blockDim.x) {
     float v[8];
     ld8(x + i * 8, v);
     uint4 hi, lo;
-    split8<1>(v, hi, lo);
+    if (fmt == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] *= mul;
+      split8<0>(v, hi, lo);
+    } else {
+      split8<1>(v, hi, lo);
+    }
     const long long pix = i / nch;
     const int c = (int)(i - pix * nch) * 8;
     uint8_t* dst = out + ((size_t)pix * 2 * C + c) * 2;  // [pixel][2 (hi, lo)][C] 16-bit
@@ -682,10 +729,11 @@ int launch_view_presplit(const ViewDesc& view, void* out, int fmt, cudaStream_t 
   return 0;
 }
 
-int launch_presplit_bf16(const float* x, void* out, long long npixels, int C, cudaStream_t st) {
+int launch_presplit(const float* x, void* out, long long npixels, int C, int fmt, float mul, cudaStream_t st) {
+  TNB_REQUIRE(fmt == 0 || fmt == 1, "presplit: format %d (0 = fp16, 1 = bf16)", fmt);
   TNB_REQUIRE(C % 8 == 0, "presplit: channels %d must be a multiple of 8", C);
   const long long nchunks = npixels * (C / 8);
-  presplit_bf16_kernel<<<min(cdiv(nchunks, 256), 148 * 16), 256, 0, st>>>(x, (uint8_t*)out, nchunks, C);
+  presplit_kernel<<<min(cdiv(nchunks, 256), 148 * 16), 256, 0, st>>>(x, (uint8_t*)out, nchunks, C, fmt, mul);
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -65,7 +65,8 @@ struct Plan {
   float* wgrad_ws;  // scratch: split-K slabs of the current layer's weight gradient (deterministic ordered sum)
   float* pred_ws;   // scratch: per-block partials of the predictor's weight / bias gradient
   uint8_t* vsplit;  // scratch: the current layer's input view materialised as pre-split bf16 (largest: 192 ch @ full res)
-  float* amax_all;  // [kLayers] max|dz| per layer, raised atomically by bn_bwd apply
+  float* amax_all;  // [2 * kLayers]: max |g| per layer (raised by the BatchNorm-backward reduction pass), then the power of
+                    // two each layer's dz is stored multiplied by (written by the apply pass, read by dgrad / wgrad)
   float* xin;
   float* dA_pred;
   int cpad;
@@ -90,6 +91,25 @@ struct Bump {
 bool wgrad_operand_from_bn_bwd(const tnb_tracknet_cfg_t& c, int l) {
   if (c.variant & 128) return false;  // variant bit 128: always materialise with tnb_view_presplit (ablation)
   return l > 0 && kDefs[l].src0 == l - 1 && kDefs[l].src1 < 0 && kDefs[l].mode0 == SRC_AFFINE_RELU;
+}
+
+// Operand format of the backward pass's tensor-core kernels. 3-term products (the default precision): bf16 (hi, lo) pairs,
+// 16 bits, fp32's exponent range, no scaling. Single-pass backward (bwd_terms 1): fp16, 11 bits instead of bf16's 8 -
+// every dz tensor is then stored multiplied by a power of two derived from the measured max |g| (bn_bwd_kernel,
+// dz_format 2) and the consumers divide it out. fp16 (hi, lo) pairs (22 bits) for the 3-term products are an ablation
+// (variant bit 2048 / TNB_BWD_FMT=fp16): measured 2-4x closer to fp64 on single kernels with short accumulation chains,
+// no different at network level (the truncating fp32 accumulation of tcgen05.mma dominates) and 1.2 % slower.
+// The fused dgrad + BatchNorm-reduction epilogue (variant bit 64) does not measure max |g|: bf16 only.
+int bwd_fmt(const tnb_tracknet_cfg_t& c) {
+  static const int env = [] {  // ablation, read once: TNB_BWD_FMT=fp16 | bf16
+    const char* e = getenv("TNB_BWD_FMT");
+    return e == nullptr ? -1 : (strcmp(e, "fp16") == 0 ? 0 : 1);
+  }();
+  if (c.variant & 64) return 1;
+  if (env >= 0) return env;
+  if (c.variant & 2048) return 0;
+  if (c.variant & 1024) return 1;
+  return c.bwd_terms == 1 ? 0 : 1;
 }
 
 int layer_cin(const tnb_tracknet_cfg_t& c, int l) {
@@ -133,7 +153,7 @@ int build_plan(const tnb_tracknet_cfg_t& c, void* ws, Plan* P) {
   Bump b{reinterpret_cast<uint8_t*>(ws), 0};
   P->cpad = (c.in_dim + 31) / 32 * 32;
   const size_t npix0 = (size_t)c.n * c.h * c.w;
-  P->amax_all = b.take<float>(kLayers);
+  P->amax_all = b.take<float>(2 * kLayers);
   P->vsplit = nullptr;
   if (c.training) {
     size_t vmax = 0;
@@ -248,7 +268,7 @@ static int forward_enqueue(const tnb_tracknet_cfg_t& c, const float* x, void* co
     if (c.training && l > 0) {
       const bool fused = P.L[l - 1].fused_rows > 0;
       if (int rc = conv3x3_plan(c.n, B.H, B.W, B.cout, B.cin, c.bwd_terms, &cp, fused)) return rc;
-      if (int rc = pack_table_add(&pt, w, B.wd, B.cout, B.cin, 1, 1, cp.BN)) return rc;
+      if (int rc = pack_table_add(&pt, w, B.wd, B.cout, B.cin, 1, bwd_fmt(c), cp.BN)) return rc;
     }
   }
   if (int rc = launch_pack_table(pt, st)) return rc;
@@ -284,14 +304,19 @@ static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const 
                                     P.dA_pred, (float*)grads[kLayers * 3 + 0], (float*)grads[kLayers * 3 + 1], P.pred_ws,
                                     st))
     return rc;
+  const int bf = bwd_fmt(c);
+  float* gmax_all = P.amax_all;            // [kLayers]
+  float* mul_all = P.amax_all + kLayers;   // [kLayers]
+  if (bf == 0) TNB_CHECK_CUDA(cudaMemsetAsync(gmax_all, 0, sizeof(float) * kLayers, st));
   auto run_wgrad = [&](int layer, const ViewDesc& pv) -> int {
     LayerBuf& W = P.L[layer];
     float* dw = (float*)grads[layer * 3 + 0];
+    const float* mul = bf == 0 ? mul_all + layer : nullptr;
     if (c.variant & 512) {  // variant bit 512: split-K partials added straight into dw with atomics (ablation; not deterministic)
       TNB_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)W.cout * W.cin_real * 9, st));
-      return launch_wgrad3x3(pv, W.dz, dw, W.cout, W.cin_real, c.bwd_terms, (c.variant >> 2) & 3, st);
+      return launch_wgrad3x3(pv, W.dz, dw, W.cout, W.cin_real, c.bwd_terms, (c.variant >> 2) & 3, st, nullptr, bf, mul);
     }
-    return launch_wgrad3x3(pv, W.dz, dw, W.cout, W.cin_real, c.bwd_terms, (c.variant >> 2) & 3, st, P.wgrad_ws);
+    return launch_wgrad3x3(pv, W.dz, dw, W.cout, W.cin_real, c.bwd_terms, (c.variant >> 2) & 3, st, P.wgrad_ws, bf, mul);
   };
   int pending = -1;  // layer whose wgrad waits for its operand from the next BatchNorm-backward apply pass
   for (int l = kLayers - 1; l >= 0; --l) {
@@ -317,7 +342,9 @@ static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const 
     }
     a.z = B.z; a.scale = B.scale; a.shift = B.shift; a.mean = B.mean; a.invstd = B.invstd;
     a.N = c.n; a.H = B.H; a.W = B.W; a.C = B.cout;
-    a.part = B.bwd_part; a.sums = B.bwd_sums; a.dz = B.dz; a.amax = nullptr; a.dz_format = 1;  // dz -> pre-split bf16
+    a.part = B.bwd_part; a.sums = B.bwd_sums; a.dz = B.dz; a.amax = nullptr;
+    a.dz_format = bf == 0 ? 2 : 1;  // dz -> pre-split fp16 (scaled) / bf16
+    a.gmax = bf == 0 ? gmax_all + l : nullptr; a.dz_mul = bf == 0 ? mul_all + l : nullptr;
     a.inv_count = (float)(1.0 / ((double)c.n * B.H * B.W));
     if (B.fused_rows == 0)
       if (int rc = launch_bn_bwd_reduce(a, st)) return rc;
@@ -333,14 +360,14 @@ static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const 
     if (l > 0) {
       ViewDesc dv;
       memset(&dv, 0, sizeof(dv));
-      dv.s[0] = SrcDesc{B.dz, nullptr, nullptr, B.cout, B.H, B.W, SRC_PRESPLIT};
+      dv.s[0] = SrcDesc{B.dz, bf == 0 ? mul_all + l : nullptr, nullptr, B.cout, B.H, B.W, SRC_PRESPLIT};
       dv.s[1] = dv.s[0];
       dv.C0 = dv.C = B.cout; dv.N = c.n; dv.H = B.H; dv.W = B.W;
       const LayerBuf* Pp = (l > 0 && P.L[l - 1].fused_rows > 0) ? &P.L[l - 1] : nullptr;  // producer whose reduction rides along
       BnBwdFuse fuse{};
       if (Pp != nullptr) fuse = BnBwdFuse{Pp->z, Pp->scale, Pp->shift, Pp->mean, Pp->invstd};
       // B.wd: the dgrad weight image, packed by the forward call of this step
-      if (int rc = launch_conv3x3(dv, B.wd, B.din, Pp != nullptr ? Pp->bwd_part : nullptr, B.cin, c.bwd_terms, 1,
+      if (int rc = launch_conv3x3(dv, B.wd, B.din, Pp != nullptr ? Pp->bwd_part : nullptr, B.cin, c.bwd_terms, bf,
                                   c.variant & 3, st, Pp != nullptr ? &fuse : nullptr))
         return rc;
     }
@@ -352,10 +379,10 @@ static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const 
       ViewDesc v0 = v, v1 = v;
       v0.s[0].mode = SRC_AFFINE_RELU; v0.s[1] = v0.s[0]; v0.C0 = v0.C = v.C0; v0.H = v.s[0].Hs; v0.W = v.s[0].Ws;
       v1.s[0] = v.s[1]; v1.s[1] = v.s[1]; v1.C0 = v1.C = v.C - v.C0;
-      if (int rc = launch_view_presplit(v0, const_cast<float*>(pv.s[0].ptr), 1, st)) return rc;
-      if (int rc = launch_view_presplit(v1, const_cast<float*>(pv.s[1].ptr), 1, st)) return rc;
+      if (int rc = launch_view_presplit(v0, const_cast<float*>(pv.s[0].ptr), bf, st)) return rc;
+      if (int rc = launch_view_presplit(v1, const_cast<float*>(pv.s[1].ptr), bf, st)) return rc;
     } else {
-      if (int rc = launch_view_presplit(v, P.vsplit, 1, st)) return rc;
+      if (int rc = launch_view_presplit(v, P.vsplit, bf, st)) return rc;
     }
     if (int rc = run_wgrad(l, pv)) return rc;
   }
@@ -496,6 +523,19 @@ int set_graph_replay(int on) {
   const int prev = g_graph_switch;
   g_graph_switch = on ? 1 : 0;
   return prev;
+}
+
+int tracknet_debug_layer(const tnb_tracknet_cfg_t& c, void* ws, int layer, void** out_ptr8, int* out_dim5) {
+  TNB_REQUIRE(layer >= 0 && layer < kLayers, "tracknet_debug_layer: layer %d", layer);
+  Plan P;
+  if (int rc = build_plan(c, ws, &P)) return rc;
+  const LayerBuf& B = P.L[layer];
+  const int bf = bwd_fmt(c);
+  void* ptrs[8] = {B.z, B.scale, B.shift, B.mean, B.invstd, B.dz, B.din,
+                   (c.training && bf == 0) ? (void*)(P.amax_all + kLayers + layer) : nullptr};
+  for (int i = 0; i < 8; ++i) out_ptr8[i] = ptrs[i];
+  out_dim5[0] = B.H; out_dim5[1] = B.W; out_dim5[2] = B.cin; out_dim5[3] = B.cout; out_dim5[4] = bf;
+  return 0;
 }
 
 int tracknet_num_launches(const tnb_tracknet_cfg_t& c, int backward) {

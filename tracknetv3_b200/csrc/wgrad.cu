@@ -42,6 +42,8 @@ struct WgradArgs {
   int ci_tile_base;  // first input-channel tile of this launch (concat views with two gather modes use two launches)
   float* ws;         // optional split-K slabs [splits][9][Cin_view][Cout] (see wgrad_scatter_kernel); nullptr: atomics into dw
   long long slab;    // floats per slab = 9 * Cin_view * Cout
+  int fmt;           // 16-bit format of BOTH operands: 0 = fp16 hi/lo, 1 = bf16 hi/lo (mixing is an illegal instruction)
+  const float* dz_mul;  // optional device scalar: the power of two dz was stored multiplied by (results are divided by it)
 };
 
 template <int MODE> TNB_DEVINL int view_off_t(const SrcDesc& s, int n, int h, int w) {
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
     if (warp == 0) {
       // whole warp runs the uniform loops (descriptor math in uniform registers); one lane issues
       const bool lead = elect_one();
-            const uint32_t idesc = make_idesc(128, NT, 1 /*bf16: A and B formats must match (mixed = illegal instruction)*/, 1, 1);
+      const uint32_t idesc = make_idesc(128, NT, a.fmt /* A and B formats must match (mixed = illegal instruction) */, 1, 1);
       // MN-major planar tiles: SBO = plane stride (next 8 channels), LBO = 128 B (next 8 pixels).
       uint32_t a_lbo = 128, a_sbo = DZPL, b_lbo = 128, b_sbo = VPL;
       if (a.variant & 1) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; }
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
                 } else {
                   float v[8];
                   view_finish<MODE>(raw[u], sc, sh, 1.f, v);
-                  split8<1>(v, hi, lo);
+                  if (a.fmt == 0) split8<0>(v, hi, lo); else split8<1>(v, hi, lo);
                 }
               }
               *reinterpret_cast<uint4*>(vwp + p * 16) = hi;
@@ -324,6 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
 
     if (warp < 8) {
       const int q = warp & 3;
+      const float out_mul = a.dz_mul != nullptr ? 1.f / *a.dz_mul : 1.f;
       mbar_wait(tmem_full, 0);
       tc_fence_after();
       const int row = 32 * q + lane;
@@ -340,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int ci = ci0 + col0 + j;
-              const float v = kt1 > kt0 ? __uint_as_float(rg[j]) : 0.f;
+              const float v = kt1 > kt0 ? __uint_as_float(rg[j]) * out_mul : 0.f;
               if (slab != nullptr)
                 slab[((size_t)(dy0 * 3 + t) * V.C + ci) * a.Cout + co0 + row] = v;
               else if (ci < a.CinReal && kt1 > kt0)
@@ -435,7 +438,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0 && rank == 0) {
       const bool lead = elect_one();
-      const uint32_t idesc = make_idesc(256, 128, 1, 1, 1);  // bf16 x bf16, both operands MN-major, M = 2 x 128
+      const uint32_t idesc = make_idesc(256, 128, a.fmt, 1, 1);  // both operands MN-major and of one 16-bit format, M = 2 x 128
       const uint64_t a_desc0 = make_smem_desc(smem_u32(st_base), 128, DZPL);
       const uint64_t b_desc0 = make_smem_desc(smem_u32(st_base) + DZ_BYTES, 128, VPL);
       const uint32_t stage16 = STAGE >> 4, a_lo16 = (16 * DZPL) >> 4, b_lo16 = (NPLC * VPL) >> 4;
@@ -546,6 +549,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 
     if (warp < 8) {
       const int q = warp & 3;
+      const float out_mul = a.dz_mul != nullptr ? 1.f / *a.dz_mul : 1.f;
       mbar_wait(tmem_full, 0);
       tc_fence_after();
       const int row = 32 * q + lane;  // TMEM lane = output channel co0 + row of THIS CTA
@@ -559,7 +563,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int ci = ci0 + col0 + j;
-              const float v = kt1 > kt0 ? __uint_as_float(rg[j]) : 0.f;
+              const float v = kt1 > kt0 ? __uint_as_float(rg[j]) * out_mul : 0.f;
               if (slab != nullptr)
                 slab[((size_t)(dy0 * 3 + t) * V.C + ci) * a.Cout + co0 + row] = v;
               else if (ci < a.CinReal && kt1 > kt0)
@@ -606,6 +610,8 @@ struct WgradSArgs {
   int tiles_h, tiles_w, ktiles, ktiles_per_cta;
   float* ws;  // optional split-K slabs [splits][9][Cout][C] (see wgrad_scatter_kernel); nullptr: atomics into dw
   long long slab;  // floats per slab = 9 * Cout * C
+  int fmt;         // see WgradArgs
+  const float* dz_mul;
 };
 
 __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __grid_constant__ WgradSArgs a) {
@@ -664,7 +670,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __g
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
       const bool lead = elect_one();
-      const uint32_t idesc = make_idesc(128, 64, 1, 1, 1);  // bf16 x bf16, both operands MN-major
+      const uint32_t idesc = make_idesc(128, 64, a.fmt, 1, 1);  // both operands MN-major and of one 16-bit format
       const uint64_t a_desc0 = make_smem_desc(smem_u32(st_base), 128, kSRP);
       const uint64_t b_desc0 = make_smem_desc(smem_u32(st_base) + A_BYTES, 128, DZPL);
       const uint32_t stage16 = STAGE >> 4, a_lo16 = A_TERM >> 4, b_lo16 = B_TERM >> 4;
@@ -766,6 +772,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __g
 
     if (warp < 8) {
       const int q = warp & 3;
+      const float out_mul = a.dz_mul != nullptr ? 1.f / *a.dz_mul : 1.f;
       mbar_wait(tmem_full, 0);
       tc_fence_after();
       const int m = 32 * q + lane;  // accumulator row = (tap slot, input channel)
@@ -782,7 +789,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_stacked_kernel(const __g
           if (live) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float v = kt1 > kt0 ? __uint_as_float(rg[j]) : 0.f;
+              const float v = kt1 > kt0 ? __uint_as_float(rg[j]) * out_mul : 0.f;
               if (slab != nullptr)  // lanes = consecutive input channels: one 128-byte store per warp instruction
                 slab[((size_t)(dy * 3 + dx) * a.Cout + co0 + col0 + j) * a.C + ci] = v;
               else if (kt1 > kt0)
@@ -896,9 +903,9 @@ size_t wgrad3x3_ws_floats(const ViewDesc& view, int Cout) {
 }
 
 static int launch_wgrad3x3_stacked(const ViewDesc& view, const void* dz_presplit, float* dw, int Cout, int CinReal,
-                                   int nterms, const WgradPlan& p, cudaStream_t st, float* ws) {
+                                   int nterms, const WgradPlan& p, cudaStream_t st, float* ws, int fmt, const float* dz_mul) {
   WgradSArgs a;
-  a.ws = ws; a.slab = (long long)9 * Cout * view.C;
+  a.ws = ws; a.slab = (long long)9 * Cout * view.C; a.fmt = fmt; a.dz_mul = dz_mul;
   a.view = reinterpret_cast<const uint8_t*>(view.s[0].ptr); a.dz = (const uint8_t*)dz_presplit; a.dw = dw;
   a.view1 = reinterpret_cast<const uint8_t*>(view.C0 < view.C ? view.s[1].ptr : view.s[0].ptr);
   a.C0 = view.C0; a.Cs0 = view.s[0].C; a.Cs1 = view.C0 < view.C ? view.s[1].C : view.s[0].C;
@@ -917,12 +924,13 @@ static int launch_wgrad3x3_stacked(const ViewDesc& view, const void* dz_presplit
 }
 
 int launch_wgrad3x3(const ViewDesc& view, const void* dz_presplit, float* dw, int Cout, int CinReal, int nterms,
-                    int variant, cudaStream_t st, float* ws) {
+                    int variant, cudaStream_t st, float* ws, int fmt, const float* dz_mul) {
+  TNB_REQUIRE(fmt == 0 || fmt == 1, "wgrad3x3: operand format %d (0 = fp16, 1 = bf16)", fmt);
   WgradPlan p;
   if (int rc = plan_wgrad(view, Cout, variant, &p)) return rc;
-  if (p.kind == 2) return launch_wgrad3x3_stacked(view, dz_presplit, dw, Cout, CinReal, nterms, p, st, ws);
+  if (p.kind == 2) return launch_wgrad3x3_stacked(view, dz_presplit, dw, Cout, CinReal, nterms, p, st, ws, fmt, dz_mul);
   WgradArgs a;
-  a.ws = ws; a.slab = (long long)9 * Cout * view.C;
+  a.ws = ws; a.slab = (long long)9 * Cout * view.C; a.fmt = fmt; a.dz_mul = dz_mul;
   a.view = view; a.dz = (const uint8_t*)dz_presplit; a.dw = dw; a.Cout = Cout; a.CinReal = CinReal;
   a.nterms = nterms; a.variant = variant; a.ci_tile_base = 0;
   a.NT = p.NT; a.tiles_h = p.tiles_h; a.tiles_w = p.tiles_w; a.ktiles = p.ktiles; a.ncot = p.ncot; a.ncit = p.ncit;

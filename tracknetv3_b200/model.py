@@ -116,11 +116,13 @@ class _WorkspaceToken:
 class TrackNet(nn.Module):
     """Drop-in for reference ``model.TrackNet`` (model.py:44-73).
 
-    ``precision``: "fp32x3" (default) computes every 3x3 convolution as a 3-term fp16 hi/lo split product with
-    fp32 accumulation (gradients are pre-scaled by a power of two) - within ~4e-5 of the reference's fp32 heatmaps;
+    ``precision``: "fp32x3" (default) computes every 3x3 convolution as a 3-term (hi, lo) split product with fp32
+    accumulation - fp16 pairs in the forward pass (weights pre-scaled by 2^10 so that their lo halves stay normal
+    numbers), bf16 pairs in the backward pass - within ~4e-5 of the reference's fp32 heatmaps;
     "tf32like" is a single 16-bit pass (what the reference's own cuDNN TF32 path amounts to; ~7e-3);
-    "fp32x3_bwd1" keeps the fp32-faithful forward (the heatmap bound) and runs dgrad / wgrad as a single bf16 pass -
-    measured next to the default by ``bench.py --precision fp32x3_bwd1``, never the headline.
+    "fp32x3_bwd1" keeps the fp32-faithful forward (the heatmap bound) and runs dgrad / wgrad as a single fp16 pass
+    (11-bit operands, gradients stored multiplied by a per-layer power of two; TF32, what the reference's own GPU
+    backward runs in, has 10) - measured next to the default by ``bench.py --precision fp32x3_bwd1``, never the headline.
     """
 
     def __init__(self, in_dim, out_dim, precision="fp32x3"):
