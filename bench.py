@@ -20,6 +20,8 @@ Printed JSON (one line, rank 0):
                (reference train.py:85-96), with the Adam / mixup kernels' own HBM fractions;
   torch_cuda_baseline  the reference architecture on stock torch-CUDA on the same box right after (the >= 6x target's
                denominator): torch defaults as the reference runs them, strict fp32, best-effort torch;
+  alt_precision a second, labelled line: the same step with precision="fp32x3_bwd1" (forward unchanged, backward as one
+               fp16 pass); never the headline, see profiles/r2_numerics.md;
   cpu_baseline the oracle port of the reference on the host cores (a reported baseline, not the target).
 """
 import argparse
@@ -221,6 +223,7 @@ def main():
     ap.add_argument("--precision", default="fp32x3", choices=["fp32x3", "tf32like", "fp32x3_bwd1"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the torch-CUDA reference-architecture timing")
+    ap.add_argument("--no-alt-precision", action="store_true", help="skip the second line (precision fp32x3_bwd1)")
     ap.add_argument("--per-launch", action="store_true", help="print the mean duration of every profiled launch to stderr")
     ap.add_argument("--variant", type=int, default=0, help="kernel experiment bits (tnb_tracknet_cfg_t.variant)")
     ap.add_argument("--cpu-batch", type=int, default=0, help="samples per step of the CPU arm (0 = as many of 10 as fit the time budget)")
@@ -434,6 +437,31 @@ def main():
                                    "frac_of_hbm_peak": mixup_bytes / ms_mixup / 1e6 / peaks["hbm"],
                                    "note": "two launches (x, y) + the host RNG draws of train.py:32-35"}}
 
+    # second, clearly labelled line: the same step with the backward pass as ONE fp16 pass on
+    # power-of-two scaled gradients (forward - heatmaps, loss - bit-identical to the headline). Never the headline:
+    # profiles/r2_numerics.md has the gradient table and the 5-seed Adam trajectories that say what it costs (nothing
+    # measurable) - the BASELINE metric stays on the fp32-faithful 3-term products in both directions.
+    alt = None
+    if args.precision == "fp32x3" and world == 1 and not args.no_alt_precision:
+        m1 = T.TrackNet(IN_DIM, OUT_DIM, precision="fp32x3_bwd1").cuda().train()
+        m1.load_state_dict(model.state_dict())
+
+        def step_alt():
+            for p in m1.parameters():
+                p.grad = None
+            T.WBCELoss(m1(x_dev), y_dev).backward()
+
+        for _ in range(3):
+            step_alt()
+        n_alt = min(args.steps, 10)
+        ms_alt = timed(step_alt, n_alt) / n_alt
+        alt = {"precision": "fp32x3_bwd1", "dtype": "forward fp16x3 (fp32-faithful, identical heatmaps), backward single fp16 "
+               "pass on 2^k-scaled gradients (11-bit operands; TF32, the reference's GPU default, has 10)",
+               "ms_per_step": ms_alt, "value": BATCH * SEQ_LEN / ms_alt * 1e3, "unit": "frames/s", "steps": n_alt,
+               "evidence": "profiles/r2_numerics.md"}
+        del m1
+        torch.cuda.empty_cache()
+
     torch_base = None
     if not args.no_torch_baseline and world == 1:
         # the reference architecture on stock torch-CUDA, same box, same batch, same timed region; our tensors first make
@@ -466,7 +494,7 @@ def main():
     nbytes_in = frames_pin.numel() + median_pin.numel() + centers_pin.numel() * 4
     dtypes = {"fp32x3": "fp16x3 / bf16x3 (3-term hi/lo split operands, fp32 accumulate: fp32-faithful)",
               "tf32like": "fp16 / bf16 single pass, fp32 accumulate (TF32-class)",
-              "fp32x3_bwd1": "forward fp16x3 (fp32-faithful), backward single bf16 pass (TF32-class gradients)"}
+              "fp32x3_bwd1": "forward fp16x3 (fp32-faithful), backward single fp16 pass on 2^k-scaled gradients (TF32-class)"}
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": dtypes[args.precision], "data": "synthetic",
@@ -481,7 +509,7 @@ def main():
             "gpu_launches": launches,
             "cuda_graphs": {"captured": gs[0], "replayed_calls": gs[1], "stream_launched_calls": gs[2], "capture_failures": gs[3]},
             "roofline": roofline, "kernel_breakdown": breakdown, "train_step": train_step,
-            "torch_cuda_baseline": torch_base, "cpu_baseline": cpu}
+            "alt_precision": alt, "torch_cuda_baseline": torch_base, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

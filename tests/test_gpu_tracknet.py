@@ -64,10 +64,12 @@ def test_train_step_vs_reference_fixture(golden_dir):
     for k, ref in (("predictor.weight", "grad_pred_w"), ("predictor.bias", "grad_pred_b")):
         assert G.rel_err(named[k].grad, torch.from_numpy(g[ref])) < 1e-2, k
     # last 3x3 conv: a ReLU mask flip of ITS output is an event of one output channel (tools/diag_fixture.py: on this 2 x
-    # 32 x 64 fixture all 676 elements beyond 1e-3 sit in one of the 64 channels) - all but two channels tight, none wild
+    # 32 x 64 fixture 3 of the 64 channels carry one - 1.9e-2, 4e-3, 4e-3 - the other 61 sit at 2e-5 ... 8e-5): the
+    # typical channel tight, a few flipped ones allowed, none wild
     last, ref = named["up_block_3.conv_2.conv.weight"].grad.double().cpu(), torch.from_numpy(g["grad_last"]).double()
     per_channel = (last - ref).abs().flatten(1).max(1).values / ref.abs().max()
-    assert (per_channel > 2e-3).sum().item() <= 2 and per_channel.max().item() < 5e-2, per_channel.topk(4)
+    assert per_channel.median().item() < 2e-4 and (per_channel > 2e-3).sum().item() <= 6 and per_channel.max().item() < 5e-2, \
+        per_channel.topk(8)
     for k, ref in (("down_block_1.conv_1.conv.weight", "grad_first"), ("up_block_1.conv_1.bn.weight", "grad_bn_w")):
         assert G.rel_err(named[k].grad, torch.from_numpy(g[ref])) < 5e-2, k
     for i, k in enumerate(names):  # all 53 gradients through their statistics

@@ -15,7 +15,7 @@ timeout -k 5 200 ncu --metrics $M --clock-control none -k regex:"conv3x3|wgrad3x
 full() {  # name, kernel regex, skip
   timeout -k 5 100 ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c 1 -o $OUT/$1 python tools/profile_step.py 0 1 > $OUT/ncu_$1.log 2>&1; echo "full $1 rc=$?" >> $OUT/summary.txt
 }
-full prof_fwd_64_64_resident 'conv3x3_lean_kernel' 1        # forward launches in layer order: 0 = 27(32)->64, 1 = 64->64 (resident weights)
+full prof_fwd_64_64 'conv3x3_lean_kernel' 1                 # forward launches in layer order: 0 = 27(32)->64, 1 = 64->64
 full prof_fwd_768_256 'conv3x3_lean_kernel' 10              # decoder up_block_1.conv_1
 full prof_fwd_192_64 'conv3x3_lean_kernel' 15               # decoder up_block_3.conv_1, the longest forward launch
 full prof_dgrad_256_256 'conv3x3_kernel<' 3                 # generic-loop dgrad launches (N side > 64): 64->192, 128->128, 128->384, 256->256

@@ -30,7 +30,7 @@ km["_meta"] = {"sources_sha": bench.sources_sha(), "head": head, "pass": os.path
                "sources": bench.TRAFFIC_SOURCES}
 json.dump(km, open(js, "w"), indent=1)
 body += "\n## 3. Full captures (`ncu --set full --import-source on`; the .ncu-rep files stay in gpurun_out/)\n\n"
-caps = (("prof_fwd_64_64_resident", "1.0872e11"), ("prof_fwd_768_256", "3.2615e11"), ("prof_fwd_192_64", "3.2615e11"),
+caps = (("prof_fwd_64_64", "1.0872e11"), ("prof_fwd_768_256", "3.2615e11"), ("prof_fwd_192_64", "3.2615e11"),
         ("prof_dgrad_256_256", "1.0872e11"), ("prof_wgrad_pair", "1.0872e11"), ("prof_wgrad_stacked", "1.0872e11"),
         ("prof_bn_bwd_apply", None))
 for f, fl in caps:
