@@ -31,7 +31,10 @@ extern "C" {
 /* How one channel-slice of a conv layer's logical input is produced from a stored tensor. */
 enum { TNB_SRC_IDENTITY = 0, TNB_SRC_AFFINE_RELU = 1, TNB_SRC_AFFINE_RELU_POOL = 2, TNB_SRC_AFFINE_RELU_UP = 3,
        TNB_SRC_PRESPLIT = 4 /* ptr holds the "pre-split" 16-bit format, see tnb_presplit_bf16 */,
-       TNB_SRC_PRESPLIT_UP = 5 /* pre-split tensor at HALF resolution read through nearest x2 upsampling (wgrad only) */ };
+       TNB_SRC_PRESPLIT_UP = 5 /* pre-split tensor at HALF resolution read through nearest x2 upsampling (wgrad only) */,
+       TNB_SRC_PLANAR16 = 6 /* planar fp16 (hi, lo) pairs, see tnb_pack_nchw_to_planar16: the forward convolution stages
+                               its halo tiles with tensor-TMA (cp.async.bulk.tensor), padding ring zero-filled by the
+                               hardware; single-source views, forward only */ };
 typedef struct {
   const float* ptr;   /* [N, Hs, Ws, C] fp32 NHWC */
   const float* scale; /* [C] fused BatchNorm scale (gamma * invstd). IDENTITY: NULL, or a pointer to ONE float =
@@ -98,6 +101,12 @@ int tnb_abi_version(void);
 /* NCHW fp32 -> NHWC fp32 with channels zero-padded to cpad. Replaces the layout the reference feeds
  * to Conv2d directly (train.py:86 `x.float().cuda()`, model.py:58). */
 int tnb_pack_nchw_to_nhwc(const float* x_nchw, float* out_nhwc, int n, int c, int h, int w, int cpad, void* stream);
+/* The same input in the layout the first convolution stages with tensor-TMA (TNB_SRC_PLANAR16): fp16 (hi, lo) pairs
+ * (x ~ hi + lo to 2^-22), planar - out is [N][cpad / 32 chunks][2 (hi, lo)][4 planes of 8 channels][H][W][8] 16-bit,
+ * n * h * w * cpad * 4 bytes like the fp32 NHWC tensor. With out_nhwc != NULL the fp32 NHWC tensor of
+ * tnb_pack_nchw_to_nhwc is written by the same launch (the weight gradient of the first layer reads it). */
+int tnb_pack_nchw_to_planar16(const float* x_nchw, void* out_planar16, float* out_nhwc, int n, int c, int h, int w,
+                              int cpad, void* stream);
 
 /* "Pre-split" tensor format: every fp32 value x is stored as two bf16 numbers hi = rn(x), lo = rn(x - hi)
  * (x ~ hi + lo to 2^-17), laid out [pixel][2 (hi, lo)][C] 16-bit: the hi terms of a pixel's channels are contiguous

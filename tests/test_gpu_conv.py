@@ -304,3 +304,38 @@ def test_conv3x3_full_resolution_layer_vs_torch_cuda():
     out, part = G.conv3x3(G.make_view([G.make_src(t)], 1, 288, 512), wt, 64, stats=True)
     assert G.rel_err(G.nchw(out), ref) < 2e-5
     assert torch.allclose(part.sum(0)[0], ref.sum((0, 2, 3)), rtol=1e-3, atol=1.0)
+
+
+@pytest.mark.parametrize("n,h,w,c,cout", [
+    (2, 32, 48, 27, 64),      # the network's first layer: 27 real channels padded to 32, one chunk
+    (1, 20, 40, 12, 64),      # ragged rows and columns: the padding ring AND the tile overhang are TMA zero-fill
+    (1, 16, 16, 40, 128),     # two 32-channel chunks (cpad 64), BN = 128
+])
+def test_conv3x3_forward_tensor_tma_input(n, h, w, c, cout):
+    """TNB_SRC_PLANAR16: the network input packed as planar fp16 (hi, lo) planes and staged by tensor-TMA
+    (cp.async.bulk.tensor, padding ring zero-filled by the hardware). Same split, same products: the result must equal the
+    gather path on the fp32 NHWC tensor BIT FOR BIT, and both the oracle op."""
+    L = G.lib()
+    cpad = (c + 31) // 32 * 32
+    x = torch.rand(n, c, h, w, generator=torch.Generator().manual_seed(51))
+    wt = _rand(cout, c, 3, 3, seed=52, scale=0.2)
+    xd = x.to(G.DEV).contiguous()
+    planar = torch.full((n * h * w * cpad * 4,), 255, dtype=torch.uint8, device=G.DEV)
+    nhwc = torch.full((n, h, w, cpad), float("nan"), device=G.DEV)
+    _lib.check(L.tnb_pack_nchw_to_planar16(xd.data_ptr(), planar.data_ptr(), nhwc.data_ptr(), n, c, h, w, cpad, G.st()))
+    torch.cuda.synchronize()
+    ref_nhwc = torch.zeros(n, h, w, cpad)
+    ref_nhwc[..., :c] = x.permute(0, 2, 3, 1)
+    assert torch.equal(nhwc.cpu(), ref_nhwc)
+    # the planar tensor: [N][chunk][term][plane][H][W][8] fp16, hi + lo == x to 2^-22
+    pl = planar.view(torch.float16).reshape(n, cpad // 32, 2, 4, h, w, 8).float()
+    back = (pl[:, :, 0] + pl[:, :, 1]).permute(0, 3, 4, 1, 2, 5).reshape(n, h, w, cpad)  # -> [n, h, w, chunk, plane, 8]
+    assert G.max_abs(back, ref_nhwc) < 3e-7
+    wpad = torch.zeros(cout, cpad, 3, 3)
+    wpad[:, :c] = wt
+    wdev = wpad.to(G.DEV)
+    src_t = _lib.Src(ptr=planar.data_ptr(), scale=None, shift=None, C=cpad, Hs=h, Ws=w, mode=_lib.SRC_PLANAR16)
+    out_t, part_t = G.conv3x3(G.make_view([src_t], n, h, w), wdev, cout, stats=True)
+    out_g, part_g = G.conv3x3(G.make_view([G.make_src(nhwc)], n, h, w), wdev, cout, stats=True)
+    assert torch.equal(out_t, out_g) and torch.equal(part_t, part_g)
+    assert G.rel_err(G.nchw(out_t), F.conv2d(x, wt, padding=1)) < TOL[3]

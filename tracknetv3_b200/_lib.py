@@ -43,7 +43,7 @@ class TrackNetCfg(C.Structure):  # tnb_tracknet_cfg_t
                 ("bn_eps", C.c_float), ("bn_momentum", C.c_float)]
 
 
-SRC_IDENTITY, SRC_AFFINE_RELU, SRC_AFFINE_RELU_POOL, SRC_AFFINE_RELU_UP, SRC_PRESPLIT, SRC_PRESPLIT_UP = 0, 1, 2, 3, 4, 5
+SRC_IDENTITY, SRC_AFFINE_RELU, SRC_AFFINE_RELU_POOL, SRC_AFFINE_RELU_UP, SRC_PRESPLIT, SRC_PRESPLIT_UP, SRC_PLANAR16 = 0, 1, 2, 3, 4, 5, 6
 GRAD_SAME, GRAD_POOL, GRAD_UP = 0, 1, 2
 
 vp, i32, i64, f32, f64, sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double, C.c_size_t
@@ -63,6 +63,7 @@ SIGNATURES = {
     "tnb_conv3x3_wgrad": (i32, [C.POINTER(View), vp, vp, i32, i32, i32, i32, i32, vp, vp]),
     "tnb_conv3x3_wgrad_ws_elems": (sz, [C.POINTER(View), i32]),
     "tnb_conv3x3_wgrad_ws": (i32, [C.POINTER(View), vp, vp, i32, i32, i32, i32, vp, i32, vp, vp]),
+    "tnb_pack_nchw_to_planar16": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "tnb_presplit_bf16": (i32, [vp, vp, i64, i32, vp]),
     "tnb_presplit_fp16": (i32, [vp, vp, i64, i32, f32, vp]),
     "tnb_view_presplit": (i32, [C.POINTER(View), vp, i32, vp]),

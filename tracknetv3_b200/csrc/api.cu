@@ -37,6 +37,10 @@ int tnb_pack_nchw_to_nhwc(const float* x, float* out, int n, int c, int h, int w
   TNB_REQUIRE(cpad % 4 == 0 && cpad >= c, "pack_nchw_to_nhwc: bad cpad %d for c %d", cpad, c);
   return launch_pack_input(x, out, n, c, h, w, cpad, ST(stream));
 }
+int tnb_pack_nchw_to_planar16(const float* x, void* out_planar16, float* out_nhwc, int n, int c, int h, int w, int cpad,
+                              void* stream) {
+  return launch_pack_input(x, out_nhwc, n, c, h, w, cpad, ST(stream), out_planar16);
+}
 int tnb_presplit_bf16(const float* x, void* out, long long npixels, int c, void* stream) {
   return launch_presplit(x, out, npixels, c, 1, 1.f, ST(stream));
 }

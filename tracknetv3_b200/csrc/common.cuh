@@ -145,6 +145,19 @@ TNB_DEVINL void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint6
       : "memory");
 }
 
+// Tensor-TMA: one 4-D box (cp.async.bulk.tensor, SASS UTMALDG) from the tensor described by `tmap` to shared memory;
+// out-of-range coordinates (the convolution's padding ring) arrive as zeros; completion as bytes on the mbarrier.
+TNB_DEVINL void tma_load_4d(void* smem_dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+TNB_DEVINL void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
 // 16-byte asynchronous global->shared copy (LDGSTS). src_bytes = 0 zero-fills the destination without reading.
 // ca = true allocates the line in L1 (.ca) instead of bypassing it (.cg). With .cg every 16-byte copy fetches its own
 // 32-byte sector from L2 even when the neighbouring thread copies the other half (measured with ncu on the wgrad fill:

@@ -41,6 +41,32 @@ static int pow2_cols(int c) {
   while (p < c) p <<= 1;
   return p;
 }
+int make_planar16_tmap(CUtensorMap* out, const void* base, int N, int H, int W, int C, int box_w, int box_h) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    EncodeFn f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return f;
+  }();
+  TNB_REQUIRE(encode != nullptr, "tensor-TMA: the driver does not export cuTensorMapEncodeTiled");
+  TNB_REQUIRE(C % 32 == 0 && box_w * 8 <= 256 && box_h <= 256 && (reinterpret_cast<uintptr_t>(base) & 15) == 0,
+              "tensor-TMA: bad planar16 tensor (C %d, box %d x %d)", C, box_w, box_h);
+  const cuuint64_t planes = (cuuint64_t)C / 32 * 8;  // per chunk: hi 4 | lo 4 planes of 8 channels
+  cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, planes, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)H * W * 16 * planes};  // bytes, dims 1..3
+  cuuint32_t box[4] = {(cuuint32_t)box_w * 8, (cuuint32_t)box_h, 8, 1}, es[4] = {1, 1, 1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TNB_REQUIRE(r == CUDA_SUCCESS, "tensor-TMA: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -1,6 +1,7 @@
 // Shared declarations for the tcgen05 implicit-GEMM convolution kernels (igemm.cu) and the
 // elementwise kernels that consume the same "view" description of a layer input.
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 #include "../../include/tracknet_b200.h"
 
@@ -15,7 +16,8 @@ enum SrcMode : int {
   SRC_AFFINE_RELU_POOL = TNB_SRC_AFFINE_RELU_POOL,  // maxpool2x2(relu(z*scale+shift)), z is 2H x 2W (model.py:59,61,63)
   SRC_AFFINE_RELU_UP = TNB_SRC_AFFINE_RELU_UP,      // nearest x2 upsample of relu(z*scale+shift)  (model.py:65,67,69)
   SRC_PRESPLIT = TNB_SRC_PRESPLIT,                  // already (hi, lo) 16-bit, [pixel][2][C]: pure copy
-  SRC_PRESPLIT_UP = TNB_SRC_PRESPLIT_UP             // the same at half resolution, read as its nearest x2 upsampling (wgrad)
+  SRC_PRESPLIT_UP = TNB_SRC_PRESPLIT_UP,            // the same at half resolution, read as its nearest x2 upsampling (wgrad)
+  SRC_PLANAR16 = TNB_SRC_PLANAR16                   // planar fp16 (hi, lo) planes [N][plane][H][W][8]: staged by tensor-TMA
 };
 using SrcDesc = tnb_src_t;    // see include/tracknet_b200.h
 using ViewDesc = tnb_view_t;
@@ -170,6 +172,10 @@ int launch_conv3x3_generic(const ViewDesc& view, const uint16_t* wpack, float* o
 int launch_conv3x3_lean(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout, int nterms,
                         int fmt, int variant, const ConvPlan& plan, cudaStream_t st, const BnBwdFuse* fuse = nullptr);
 int num_sms();
+// Tensor map of a TNB_SRC_PLANAR16 tensor ([N][C / 32][2][4][H][W][8] fp16) for the convolution's halo tiles: dims
+// {8 W, H, planes, N}, box {8 box_w, box_h, 8 planes, 1}, no swizzle, out-of-range elements read as zero. The encoder
+// (cuTensorMapEncodeTiled) is fetched from the driver through the runtime: no link-time dependency on libcuda.
+int make_planar16_tmap(CUtensorMap* out, const void* base, int N, int H, int W, int C, int box_w, int box_h);
 #ifdef TNB_TRACE
 extern long long* g_conv_trace;  // debug build (make TRACE=1): set by tnb_debug_set_trace, read by the conv launchers
 #endif

@@ -12,8 +12,8 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 // =============================================================================================
 // input packing: NCHW fp32 (reference train.py:86 x.float().cuda()) -> NHWC fp32, channels padded to Cpad
 // =============================================================================================
-__global__ void pack_input_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int C, int H, int W,
-                                  int Cpad) {
+__global__ void pack_input_kernel(const float* __restrict__ x, float* __restrict__ out, uint8_t* __restrict__ planar,
+                                  int N, int C, int H, int W, int Cpad) {
   pdl_launch_dependents();
   pdl_wait();
   const long long npix = (long long)N * H * W;
@@ -23,19 +23,33 @@ __global__ void pack_input_kernel(const float* __restrict__ x, float* __restrict
     const long long n = p / hw, r = p - n * hw;
     const float* src = x + n * C * hw + r;
     float4* dst = reinterpret_cast<float4*>(out + p * Cpad);
-    for (int c4 = 0; c4 < Cpad; c4 += 4) {
-      float4 v;
-      v.x = (c4 + 0 < C) ? __ldg(src + (long long)(c4 + 0) * hw) : 0.f;
-      v.y = (c4 + 1 < C) ? __ldg(src + (long long)(c4 + 1) * hw) : 0.f;
-      v.z = (c4 + 2 < C) ? __ldg(src + (long long)(c4 + 2) * hw) : 0.f;
-      v.w = (c4 + 3 < C) ? __ldg(src + (long long)(c4 + 3) * hw) : 0.f;
-      dst[c4 >> 2] = v;
+    for (int c8 = 0; c8 < Cpad; c8 += 8) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = (c8 + e < C) ? __ldg(src + (long long)(c8 + e) * hw) : 0.f;
+      if (out != nullptr) {
+        dst[c8 >> 2] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[(c8 >> 2) + 1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+      if (planar != nullptr) {
+        // [N][chunk of 32 ch][term][plane of 8 ch][H][W][8 x fp16]: consecutive threads = consecutive pixels of a
+        // row = consecutive 16-byte elements of a plane (coalesced), and what a TMA box {8 W', H', planes} lands as the
+        // planar halo tile [plane][row][pixel][16 B] of the tcgen05 convolution
+        uint4 hi, lo;
+        split8<0>(v, hi, lo);
+        const int chunk = c8 >> 5, pl = (c8 >> 3) & 3;
+        const size_t plane_hi = ((size_t)n * (Cpad >> 5) + chunk) * 8 + pl;
+        *reinterpret_cast<uint4*>(planar + (plane_hi * hw + r) * 16) = hi;
+        *reinterpret_cast<uint4*>(planar + ((plane_hi + 4) * hw + r) * 16) = lo;
+      }
     }
   }
 }
-int launch_pack_input(const float* x, float* out, int N, int C, int H, int W, int Cpad, cudaStream_t st) {
+int launch_pack_input(const float* x, float* out, int N, int C, int H, int W, int Cpad, cudaStream_t st, void* planar) {
+  TNB_REQUIRE(Cpad % 8 == 0 && (planar == nullptr || Cpad % 32 == 0), "pack_input: padded channel count %d", Cpad);
   const long long npix = (long long)N * H * W;
-  if (int rc = launch_pdl(pack_input_kernel, dim3(min(cdiv(npix, 256), 148 * 16)), dim3(256), 0, st, x, out, N, C, H, W, Cpad)) return rc;
+  if (int rc = launch_pdl(pack_input_kernel, dim3(min(cdiv(npix, 256), 148 * 16)), dim3(256), 0, st, x, out,
+                          (uint8_t*)planar, N, C, H, W, Cpad)) return rc;
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -67,7 +67,10 @@ struct Plan {
   uint8_t* vsplit;  // scratch: the current layer's input view materialised as pre-split bf16 (largest: 192 ch @ full res)
   float* amax_all;  // [2 * kLayers]: max |g| per layer (raised by the BatchNorm-backward reduction pass), then the power of
                     // two each layer's dz is stored multiplied by (written by the apply pass, read by dgrad / wgrad)
-  float* xin;
+  float* xin;       // network input, fp32 NHWC padded to cpad channels (first layer's wgrad view; its forward view when
+                    // the tensor-TMA path does not apply)
+  uint8_t* xin16;   // the same as planar fp16 (hi, lo) planes (TNB_SRC_PLANAR16): the first convolution stages its halo
+                    // tiles from it with tensor-TMA; nullptr when the layer's tile plan is not row-major / <= 30 columns
   float* dA_pred;
   int cpad;
   size_t bytes;
@@ -173,6 +176,16 @@ int build_plan(const tnb_tracknet_cfg_t& c, void* ws, Plan* P) {
     P->pred_ws = b.take<float>(predictor_bwd_workspace_bytes(c.n, c.h, c.w, c.out_dim) / sizeof(float));
   }
   P->xin = b.take<float>(npix0 * P->cpad);
+  P->xin16 = nullptr;
+  {
+    // tensor-TMA staging of the network input: 3-term forward on row-major tiles whose halo row fits a TMA box (256
+    // elements = 32 pixels). TNB_INPUT_TMA=0 / variant bit 4096: the gather path on the fp32 tensor (ablation).
+    static const int env = [] { const char* e = getenv("TNB_INPUT_TMA"); return e ? atoi(e) : 1; }();
+    ConvPlan cp;
+    if (int rc = conv3x3_plan(c.n, c.h, c.w, P->cpad, kDefs[0].cout, c.fwd_terms, &cp)) return rc;
+    if (env != 0 && !(c.variant & 4096) && c.fwd_terms == 3 && !cp.tall && (8 * cp.MT + 2) * 8 <= 256)
+      P->xin16 = b.take<uint8_t>(npix0 * P->cpad * 4);
+  }
   P->dA_pred = b.take<float>(npix0 * 64);
   for (int l = 0; l < kLayers; ++l) {
     LayerBuf& B = P->L[l];
@@ -215,6 +228,7 @@ SrcDesc make_src(const Plan& P, const tnb_tracknet_cfg_t& c, int layer, int mode
   SrcDesc s;
   if (layer < 0) {
     s.ptr = P.xin; s.scale = nullptr; s.shift = nullptr; s.C = P.cpad; s.Hs = c.h; s.Ws = c.w; s.mode = SRC_IDENTITY;
+    if (mode == SRC_PLANAR16) { s.ptr = reinterpret_cast<const float*>(P.xin16); s.mode = SRC_PLANAR16; }
   } else {
     const LayerBuf& B = P.L[layer];
     s.ptr = B.z; s.scale = B.scale; s.shift = B.shift; s.C = B.cout; s.Hs = B.H; s.Ws = B.W; s.mode = mode;
@@ -254,7 +268,9 @@ static int forward_enqueue(const tnb_tracknet_cfg_t& c, const float* x, void* co
   Plan P;
   if (int rc = build_plan(c, ws, &P)) return rc;
   TNB_REQUIRE(ws_bytes >= P.bytes, "tracknet_forward: workspace too small (%zu < %zu)", ws_bytes, P.bytes);
-  if (int rc = launch_pack_input(x, P.xin, c.n, c.in_dim, c.h, c.w, P.cpad, st)) return rc;
+  // fp32 NHWC for the first layer's weight gradient (training) or its gather path; planar fp16 pairs for tensor-TMA
+  float* xin32 = (c.training || P.xin16 == nullptr) ? P.xin : nullptr;
+  if (int rc = launch_pack_input(x, xin32, c.n, c.in_dim, c.h, c.w, P.cpad, st, P.xin16)) return rc;
   // every weight operand of the step in ONE launch: the 17 forward images (fp16 hi/lo) and, when a backward will
   // follow, the 16 dgrad images (bf16 hi/lo, rotated / transposed) - the parameters do not change in between
   PackTable pt;
@@ -274,7 +290,8 @@ static int forward_enqueue(const tnb_tracknet_cfg_t& c, const float* x, void* co
   if (int rc = launch_pack_table(pt, st)) return rc;
   for (int l = 0; l < kLayers; ++l) {
     LayerBuf& B = P.L[l];
-    const ViewDesc v = make_view(P, c, l);
+    ViewDesc v = make_view(P, c, l);
+    if (l == 0 && P.xin16 != nullptr) { v.s[0] = make_src(P, c, -1, SRC_PLANAR16); v.s[1] = v.s[0]; }
     if (int rc = launch_conv3x3(v, B.wf, B.z, c.training ? B.stat_part : nullptr, B.cout, c.fwd_terms, 0, c.variant & 3, st))
       return rc;
     if (int rc = launch_bn_finalize(B.stat_part, B.stat_rows, (double)c.n * B.H * B.W, (const float*)params[l * 6 + 1],
