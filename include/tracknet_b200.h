@@ -300,6 +300,17 @@ int tnb_tracknet_forward(const tnb_tracknet_cfg_t* cfg, const float* x_nchw, voi
 int tnb_tracknet_backward(const tnb_tracknet_cfg_t* cfg, const float* dy_nchw, const float* y_nchw,
                           void* const* params, void* const* grads, void* workspace, size_t workspace_bytes,
                           void* stream);
+/* The backward pass in pieces, for data-parallel training (the reference has no multi-GPU code; torch DDP overlaps its
+ * bucketed allreduce with the backward the same way): layers layer_hi .. layer_lo of the 17 convolution blocks in
+ * backward order (state_dict numbering, 16 = up_block_3.conv_2 ... 0 = down_block_1.conv_1); layer_hi = 16 also runs the
+ * predictor's backward. Calling (16, s) and then (s - 1, 0) equals tnb_tracknet_backward; after the first call returns,
+ * the gradients of layers >= s and of the predictor are final on `stream` and can be reduced across ranks on another
+ * stream while the second call computes. tnb_tracknet_grad_split_layer() = the s this library recommends (7: 85 % of the
+ * parameters lie behind it and no weight gradient is pending across that boundary). */
+int tnb_tracknet_backward_range(const tnb_tracknet_cfg_t* cfg, const float* dy_nchw, const float* y_nchw,
+                                void* const* params, void* const* grads, void* workspace, size_t workspace_bytes,
+                                int layer_hi, int layer_lo, void* stream);
+int tnb_tracknet_grad_split_layer(void);
 /* tnb_tracknet_forward / tnb_tracknet_backward replay their launch sequence from a CUDA graph once the same
  * argument set (cfg and every pointer) is seen again; per-launch profiling and a caller-side stream capture bypass it.
  * This switch turns the replay off (0) or on (1, default; env TNB_GRAPHS=0 also disables); returns the old value. */

@@ -42,6 +42,21 @@ def _worker(rank, world, port, q):
     bucket.allreduce()
     avg = torch.cat([p.grad.flatten() for p in model.parameters()])
     want = sum(gathered) / world
+    # overlapped mode: the backward runs as two ranges, the bottleneck / decoder / predictor gradients are all-reduced on a
+    # side stream under the encoder's backward. Same weights, same batches: the per-rank gradients are bit-identical to
+    # the ones gathered above, so every one of several steps must give exactly the same average
+    bucket2 = GradBucket(model, overlap=True)
+    assert bucket2.split is not None and model._grad_split is bucket2.split
+    worst = 0.0
+    for _ in range(6):
+        for p in model.parameters():
+            p.grad = None
+        T.WBCELoss(model(x), y).backward()
+        assert bucket2.split.first_param == 3 * 7
+        bucket2.allreduce()
+        avg2 = torch.cat([p.grad.flatten() for p in model.parameters()])
+        worst = max(worst, (avg2 - avg).abs().max().item())
+    assert worst == 0.0, worst
     weights = torch.cat([p.detach().flatten() for p in model.parameters()])
     rm = model.down_block_1.conv_1.bn.running_mean.clone()
     q.put((rank, (avg - want).abs().max().item(), want.abs().max().item(), (gathered[0] - gathered[1]).abs().max().item(),

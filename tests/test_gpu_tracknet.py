@@ -141,6 +141,26 @@ def test_single_pass_fp16_backward_mode():
         assert G.rel_err(p.grad, g3[k].grad) < 5e-2, k
 
 
+def test_backward_in_two_ranges_equals_the_whole_pass():
+    """tnb_tracknet_backward_range (16, 7) + (6, 0) - what data-parallel training runs so that the first part's gradients
+    can be all-reduced under the second - against the single call: bit-identical gradients, eager and replayed."""
+    from tracknetv3_b200.parallel import _GradSplit
+    gen = torch.Generator().manual_seed(9)
+    x = torch.rand(2, 12, 64, 96, generator=gen).to(G.DEV)
+    y = _disc_labels(2, 4, 64, 96, gen).to(G.DEV)
+    whole, split = _model(6, 12, 4).train(), _model(6, 12, 4).train()
+    split._grad_split = _GradSplit()
+    for it in range(3):  # third iteration: both replay their CUDA graphs
+        for m in (whole, split):
+            for p in m.parameters():
+                p.grad = None
+            T.WBCELoss(m(x), y).backward()
+        assert split._grad_split.first_param == 21 and split._grad_split.event.query() in (True, False)
+        torch.cuda.synchronize()
+        for (k, a), b in zip(whole.named_parameters(), split.parameters()):
+            assert torch.equal(a.grad, b.grad), (it, k)
+
+
 def test_errors_mirror_reference():
     m = _model(5, 12, 4)
     with pytest.raises(RuntimeError, match="divisible by 8"):

@@ -94,6 +94,8 @@ SIGNATURES = {
     "tnb_tracknet_workspace_bytes": (sz, [C.POINTER(TrackNetCfg)]),
     "tnb_tracknet_forward": (i32, [C.POINTER(TrackNetCfg), vp, C.POINTER(vp), vp, vp, sz, vp]),
     "tnb_tracknet_backward": (i32, [C.POINTER(TrackNetCfg), vp, vp, C.POINTER(vp), C.POINTER(vp), vp, sz, vp]),
+    "tnb_tracknet_backward_range": (i32, [C.POINTER(TrackNetCfg), vp, vp, C.POINTER(vp), C.POINTER(vp), vp, sz, i32, i32, vp]),
+    "tnb_tracknet_grad_split_layer": (i32, []),
     "tnb_set_graph_replay": (i32, [i32]),
     "tnb_graph_stats": (i32, [C.POINTER(C.c_longlong)]),
     "tnb_tracknet_num_launches": (i32, [C.POINTER(TrackNetCfg), i32]),

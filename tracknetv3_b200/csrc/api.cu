@@ -14,7 +14,8 @@ size_t tracknet_workspace_bytes(const tnb_tracknet_cfg_t& c);
 int tracknet_forward(const tnb_tracknet_cfg_t& c, const float* x, void* const* params, float* y, void* ws,
                      size_t ws_bytes, cudaStream_t st);
 int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float* y, void* const* params,
-                      void* const* grads, void* ws, size_t ws_bytes, cudaStream_t st);
+                      void* const* grads, void* ws, size_t ws_bytes, cudaStream_t st, int hi, int lo);
+int tracknet_grad_split_layer();
 int tracknet_num_launches(const tnb_tracknet_cfg_t& c, int backward);
 int tracknet_debug_layer(const tnb_tracknet_cfg_t& c, void* ws, int layer, void** out_ptr8, int* out_dim5);
 int set_graph_replay(int on);
@@ -199,8 +200,13 @@ int tnb_tracknet_forward(const tnb_tracknet_cfg_t* cfg, const float* x, void* co
 }
 int tnb_tracknet_backward(const tnb_tracknet_cfg_t* cfg, const float* dy, const float* y, void* const* params,
                           void* const* grads, void* ws, size_t ws_bytes, void* stream) {
-  return tracknet_backward(*cfg, dy, y, params, grads, ws, ws_bytes, ST(stream));
+  return tracknet_backward(*cfg, dy, y, params, grads, ws, ws_bytes, ST(stream), 16, 0);
 }
+int tnb_tracknet_backward_range(const tnb_tracknet_cfg_t* cfg, const float* dy, const float* y, void* const* params,
+                                void* const* grads, void* ws, size_t ws_bytes, int layer_hi, int layer_lo, void* stream) {
+  return tracknet_backward(*cfg, dy, y, params, grads, ws, ws_bytes, ST(stream), layer_hi, layer_lo);
+}
+int tnb_tracknet_grad_split_layer(void) { return tracknet_grad_split_layer(); }
 int tnb_set_graph_replay(int on) { return set_graph_replay(on); }
 int tnb_graph_stats(long long* out4) { graph_stats(out4); return 0; }
 int tnb_tracknet_num_launches(const tnb_tracknet_cfg_t* cfg, int backward) {

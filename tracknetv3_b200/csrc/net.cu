@@ -310,21 +310,28 @@ static int forward_enqueue(const tnb_tracknet_cfg_t& c, const float* x, void* co
                               (const float*)params[kLayers * 6 + 1], c.out_dim, y, st);
 }
 
+// Layers hi .. lo of the backward pass (hi == kLayers - 1: preceded by the predictor's backward). A whole pass is
+// (kLayers - 1, 0); data-parallel training runs it as two ranges so that the gradients of the first one (bottleneck and
+// decoder: 85 % of the parameters) can be all-reduced while the second one still computes.
 static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const float* y, void* const* params,
-                            void* const* grads, void* ws, size_t ws_bytes, cudaStream_t st) {
+                            void* const* grads, void* ws, size_t ws_bytes, cudaStream_t st, int hi = kLayers - 1,
+                            int lo = 0) {
   TNB_REQUIRE(c.training, "tracknet_backward: only the training-mode (batch-statistics) backward is implemented");
+  TNB_REQUIRE(0 <= lo && lo <= hi && hi < kLayers, "tracknet_backward: layer range %d..%d", hi, lo);
   Plan P;
   if (int rc = build_plan(c, ws, &P)) return rc;
   TNB_REQUIRE(ws_bytes >= P.bytes, "tracknet_backward: workspace too small (%zu < %zu)", ws_bytes, P.bytes);
-  const SrcDesc last = make_src(P, c, kLayers - 1, SRC_AFFINE_RELU);
-  if (int rc = launch_predictor_bwd(last, c.n, c.h, c.w, (const float*)params[kLayers * 6 + 0], c.out_dim, dy, y,
-                                    P.dA_pred, (float*)grads[kLayers * 3 + 0], (float*)grads[kLayers * 3 + 1], P.pred_ws,
-                                    st))
-    return rc;
   const int bf = bwd_fmt(c);
   float* gmax_all = P.amax_all;            // [kLayers]
   float* mul_all = P.amax_all + kLayers;   // [kLayers]
-  if (bf == 0) TNB_CHECK_CUDA(cudaMemsetAsync(gmax_all, 0, sizeof(float) * kLayers, st));
+  if (hi == kLayers - 1) {
+    const SrcDesc last = make_src(P, c, kLayers - 1, SRC_AFFINE_RELU);
+    if (int rc = launch_predictor_bwd(last, c.n, c.h, c.w, (const float*)params[kLayers * 6 + 0], c.out_dim, dy, y,
+                                      P.dA_pred, (float*)grads[kLayers * 3 + 0], (float*)grads[kLayers * 3 + 1],
+                                      P.pred_ws, st))
+      return rc;
+    if (bf == 0) TNB_CHECK_CUDA(cudaMemsetAsync(gmax_all, 0, sizeof(float) * kLayers, st));
+  }
   auto run_wgrad = [&](int layer, const ViewDesc& pv) -> int {
     LayerBuf& W = P.L[layer];
     float* dw = (float*)grads[layer * 3 + 0];
@@ -335,8 +342,10 @@ static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const 
     }
     return launch_wgrad3x3(pv, W.dz, dw, W.cout, W.cin_real, c.bwd_terms, (c.variant >> 2) & 3, st, P.wgrad_ws, bf, mul);
   };
-  int pending = -1;  // layer whose wgrad waits for its operand from the next BatchNorm-backward apply pass
-  for (int l = kLayers - 1; l >= 0; --l) {
+  // layer whose wgrad waits for its operand from the next BatchNorm-backward apply pass; a range that does not start
+  // at the top inherits the one its predecessor left behind
+  int pending = (hi + 1 < kLayers && wgrad_operand_from_bn_bwd(c, hi + 1)) ? hi + 1 : -1;
+  for (int l = hi; l >= lo; --l) {
     LayerBuf& B = P.L[l];
     BnBwdArgs a;
     memset(&a, 0, sizeof(a));
@@ -522,14 +531,21 @@ int tracknet_forward(const tnb_tracknet_cfg_t& c, const float* x, void* const* p
 }
 
 int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float* y, void* const* params,
-                      void* const* grads, void* ws, size_t ws_bytes, cudaStream_t st) {
-  uint64_t key = key_common(c, 1, ws, ws_bytes);
+                      void* const* grads, void* ws, size_t ws_bytes, cudaStream_t st, int hi, int lo) {
+  TNB_REQUIRE(0 <= lo && lo <= hi && hi < kLayers, "tracknet_backward: layer range %d..%d", hi, lo);
+  uint64_t key = key_common(c, 1 + (hi << 8) + (lo << 16), ws, ws_bytes);
   key = fnv(key, &dy, sizeof(dy)); key = fnv(key, &y, sizeof(y));
   key = fnv(key, params, sizeof(void*) * (kLayers * 6 + 2));
   key = fnv(key, grads, sizeof(void*) * (kLayers * 3 + 2));
-  return run_maybe_graphed(key, st,
-                           [&](cudaStream_t s) { return backward_enqueue(c, dy, y, params, grads, ws, ws_bytes, s); });
+  return run_maybe_graphed(key, st, [&](cudaStream_t s) {
+    return backward_enqueue(c, dy, y, params, grads, ws, ws_bytes, s, hi, lo);
+  });
 }
+
+// First layer of the backward pass's second range in data-parallel training (tnb_tracknet_backward_range): the wgrad
+// of bottleneck.conv_1 (layer 7) reads a pooled view, so no weight gradient is left pending across this boundary, and
+// layers 7..16 + the predictor hold 9.59 M of TrackNet's 11.34 M parameters.
+int tracknet_grad_split_layer() { return 7; }
 
 void graph_stats(long long* out4) {
   std::lock_guard<std::mutex> lock(g_graphs.mu);

@@ -99,9 +99,22 @@ class _TrackNetFunction(torch.autograd.Function):
             grads.append(flat[off:off + p.numel()].view_as(p))
             off += p.numel()
         dy = dy.contiguous()
-        _lib.check(lib.tnb_tracknet_backward(C.byref(ctx.cfg), dy.data_ptr(), y.data_ptr(),
-                                             _lib.ptr_array(module._state_tensors()), _lib.ptr_array(grads),
-                                             ctx.ws.data_ptr(), ctx.nbytes, _lib.stream_ptr()))
+        state, gptr = _lib.ptr_array(module._state_tensors()), _lib.ptr_array(grads)
+        split = module._grad_split
+        if split is None:
+            _lib.check(lib.tnb_tracknet_backward(C.byref(ctx.cfg), dy.data_ptr(), y.data_ptr(), state, gptr,
+                                                 ctx.ws.data_ptr(), ctx.nbytes, _lib.stream_ptr()))
+        else:
+            # data parallel (parallel.GradBucket.overlap): two ranges with an event in between - the gradients of the
+            # bottleneck / decoder / predictor are final at the event and get all-reduced on the bucket's side stream
+            # while the encoder's backward still runs
+            s = lib.tnb_tracknet_grad_split_layer()
+            for hi, lo in ((16, s), (s - 1, 0)):
+                _lib.check(lib.tnb_tracknet_backward_range(C.byref(ctx.cfg), dy.data_ptr(), y.data_ptr(), state, gptr,
+                                                           ctx.ws.data_ptr(), ctx.nbytes, hi, lo, _lib.stream_ptr()))
+                if lo == s:
+                    split.first_param = 3 * s  # parameters are (conv.weight, bn.weight, bn.bias) per block, predictor last
+                    split.event.record()
         return (None, None, None) + tuple(grads)
 
 
@@ -141,6 +154,7 @@ class TrackNet(nn.Module):
             raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
         self.precision = precision
         self._variant = 0
+        self._grad_split = None   # set by parallel.GradBucket(overlap=True): run the backward as two ranges (see backward)
         self._ws_scratch = None   # forwards that keep nothing for a backward (eval(), no_grad)
         self._ws_saved = None     # the newest training forward's activations until its backward has run
         self._ws_saved_token = None

@@ -164,7 +164,7 @@ def fit(model, optimizer, scheduler, train_loader_fn, val_loader_fn, param_dict,
         import torch.distributed as dist
         from tracknetv3_b200.parallel import GradBucket, broadcast_module
         broadcast_module(model)
-        bucket = GradBucket(model)
+        bucket = GradBucket(model, overlap=True)
     for epoch in range(start_epoch, param_dict['epochs']):
         train_loss = train_fn(model, optimizer, train_loader_fn(), param_dict, bucket) if world > 1 else \
             train_fn(model, optimizer, train_loader_fn(), param_dict)
