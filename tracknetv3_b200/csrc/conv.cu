@@ -170,7 +170,7 @@ int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, floa
   // ~5 % faster (per-launch A/B on one box, profiles/r2_experiments.md). TNB_CONV_LEAN=0 / 1 forces one of them (ablation).
   static const int lean_env = [] { const char* e = getenv("TNB_CONV_LEAN"); return e ? atoi(e) : -1; }();
   const bool dgrad = view.s[0].mode == SRC_PRESPLIT;  // copy fill (pre-split gradients); the forward gathers and splits
-  const bool lean = lean_env >= 0 ? lean_env != 0 : (!dgrad || p.BN == 64);
+  const bool lean = !dgrad || (lean_env >= 0 ? lean_env != 0 : p.BN == 64);  // the switch acts on the dgrad launches
   return lean ? launch_conv3x3_lean(view, wpack, out, stat_part, Cout, nterms, fmt, variant, p, st, fuse)
               : launch_conv3x3_generic(view, wpack, out, stat_part, Cout, nterms, fmt, variant, p, st, fuse);
 }
