@@ -89,7 +89,7 @@ bool conv3x3_merged(int BN) {
 }
 int conv3x3_weight_layout(int BN) { return conv3x3_merged(BN) ? 1 : 0; }
 
-int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* plan, bool bn_bwd_fused) {
+int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* plan, bool bn_bwd_fused, bool copy_fill) {
   TNB_REQUIRE(Cin % 32 == 0, "conv3x3: view channels %d must be a multiple of 32", Cin);
   const int BN = pick_bn(Cout);
   TNB_REQUIRE(BN >= 32 && BN % 16 == 0, "conv3x3: unsupported output channel count %d", Cout);
@@ -116,7 +116,14 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
   };
   const bool tall = plan_mode != 2 && padded(MT, true) < padded(MT, false);
   while (MT > 1 && 8 * (MT - 1) >= (tall ? H : W)) --MT;  // do not tile wider (taller) than the image
-  int SA = 2, SB = 0, G = 1;
+  // Halo-tile stages: 2 for the gathering (forward) views, 3 for the copy-filled dgrad views. A/B on one box, two runs
+  // each (profiles/r2_sa_summary.txt): the third stage lets the producers start the next tile's second chunk before the
+  // current tile's has retired - dgrad 5.40 -> 5.18 ms per step, every launch 3-9 % faster; on the forward launches it
+  // costs the gathers 42 KB of L1 (64 -> 64 +5 %, 64 -> 128 +10 %, the rest unchanged). TNB_CONV_SA=<forward><dgrad>,
+  // two digits 2..4, overrides (ablation).
+  static const int sa_env = [] { const char* e = getenv("TNB_CONV_SA"); return e ? atoi(e) : 0; }();
+  const int sa_pick = copy_fill ? sa_env % 10 : sa_env / 10;
+  int SA = (sa_pick >= 2 && sa_pick <= 4) ? sa_pick : (copy_fill ? 3 : 2), SB = 0, G = 1;
   size_t smem = 0;
   const int mt_max = MT;
   bool found = false;
@@ -133,7 +140,10 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
       if (fixed + 2 * b_stage <= (size_t)kMaxSmem) {
         G = g;
         SB = (int)((kMaxSmem - fixed) / b_stage);
-        const int cap = g == 3 ? 3 : 8;  // deeper rings measured no better (cap 5), one tap per slot clearly worse
+        // deeper rings measured no better (cap 5: round 1, and again with the lean issue loop, TNB_CONV_SB_CAP), one tap
+        // per slot clearly worse
+        static const int cap_env = [] { const char* e = getenv("TNB_CONV_SB_CAP"); return e ? atoi(e) : 0; }();
+        const int cap = g == 3 ? (cap_env >= 2 && cap_env <= 8 ? cap_env : 3) : 8;
         if (SB > cap) SB = cap;
         smem = fixed + SB * b_stage;
         found = true;
@@ -163,13 +173,13 @@ int conv3x3_num_stat_rows(int N, int H, int W, int Cin, int Cout, int nterms, bo
 int launch_conv3x3(const ViewDesc& view, const uint16_t* wpack, float* out, float* stat_part, int Cout,
                    int nterms, int fmt, int variant, cudaStream_t st, const BnBwdFuse* fuse) {
   ConvPlan p;
-  int rc = conv3x3_plan(view.N, view.H, view.W, view.C, Cout, nterms, &p, fuse != nullptr);
+  const bool dgrad = view.s[0].mode == SRC_PRESPLIT;  // copy fill (pre-split gradients); the forward gathers and splits
+  int rc = conv3x3_plan(view.N, view.H, view.W, view.C, Cout, nterms, &p, fuse != nullptr, dgrad);
   if (rc) return rc;
   // Which MMA-issue loop (conv_kernel.inc): the lean one for the forward pass and wherever the tile is 64 wide (short MMAs:
   // the generic loop's ~20 instructions per MMA fall behind), the generic one on the wide dgrad tiles, where it measured
   // ~5 % faster (per-launch A/B on one box, profiles/r2_experiments.md). TNB_CONV_LEAN=0 / 1 forces one of them (ablation).
   static const int lean_env = [] { const char* e = getenv("TNB_CONV_LEAN"); return e ? atoi(e) : -1; }();
-  const bool dgrad = view.s[0].mode == SRC_PRESPLIT;  // copy fill (pre-split gradients); the forward gathers and splits
   const bool lean = !dgrad || (lean_env >= 0 ? lean_env != 0 : p.BN == 64);  // the switch acts on the dgrad launches
   return lean ? launch_conv3x3_lean(view, wpack, out, stat_part, Cout, nterms, fmt, variant, p, st, fuse)
               : launch_conv3x3_generic(view, wpack, out, stat_part, Cout, nterms, fmt, variant, p, st, fuse);

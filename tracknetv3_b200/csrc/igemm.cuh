@@ -152,7 +152,10 @@ struct ConvPlan {
 // bn_bwd_fused: reserve the per-channel constant table of the fused BatchNorm-backward reduction (dgrad epilogue)
 int conv3x3_weight_layout(int BN);    // 0 plain [term][plane][BN], 1 merged [plane][term][BN]
 bool conv3x3_merged(int BN);  // weights of this tile width are packed [plane][hi | lo][BN] (one MMA for x_hi * [w_hi | w_lo])
-int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* plan, bool bn_bwd_fused = false);
+// copy_fill: the view is a pre-split tensor (dgrad) whose halo tiles are filled by cp.async copies - only the number of
+// halo-tile stages (and with it the shared-memory size) depends on it, never the tiling
+int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* plan, bool bn_bwd_fused = false,
+                 bool copy_fill = false);
 size_t conv3x3_wpack_elems(int Kside, int Nside);  // uint16 elements of a packed weight buffer
 int launch_pack_weights(const float* w_oihw, uint16_t* out, int Co, int Ci, int mode /*0 fwd, 1 dgrad*/,
                         int fmt, int BN, cudaStream_t st);
