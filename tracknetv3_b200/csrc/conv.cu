@@ -123,7 +123,11 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
   // two digits 2..4, overrides (ablation).
   static const int sa_env = [] { const char* e = getenv("TNB_CONV_SA"); return e ? atoi(e) : 0; }();
   const int sa_pick = copy_fill ? sa_env % 10 : sa_env / 10;
-  int SA = (sa_pick >= 2 && sa_pick <= 4) ? sa_pick : (copy_fill ? 3 : 2), SB = 0, G = 1;
+  const int sa_want = (sa_pick >= 2 && sa_pick <= 4) ? sa_pick : (copy_fill ? 3 : 2);
+  // The tiling (MT, taps per weight stage) is chosen with 2 stages and never depends on the wish for more: per-tile
+  // partial rows and the packed-weight layout are computed by callers that do not know the fill kind. Extra stages are
+  // taken afterwards if they fit next to at least two weight stages.
+  int SA = 2, SB = 0, G = 1;
   size_t smem = 0;
   const int mt_max = MT;
   bool found = false;
@@ -136,7 +140,7 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
       const size_t a_stage = (size_t)TP * 4 * pad_px(halo) * 16;
       const size_t b_stage = (size_t)g * (merged ? 2 : TP) * 64 * BN;
       const size_t fixed = kHdrBytes + ((halo * 8 + 127) & ~127) + (size_t)4 * 2 * BN * 4 + (bn_bwd_fused ? BN * 16 : 0) +
-                           SA * a_stage;
+                           2 * a_stage;
       if (fixed + 2 * b_stage <= (size_t)kMaxSmem) {
         G = g;
         SB = (int)((kMaxSmem - fixed) / b_stage);
@@ -144,8 +148,11 @@ int conv3x3_plan(int N, int H, int W, int Cin, int Cout, int nterms, ConvPlan* p
         // per slot clearly worse
         static const int cap_env = [] { const char* e = getenv("TNB_CONV_SB_CAP"); return e ? atoi(e) : 0; }();
         const int cap = g == 3 ? (cap_env >= 2 && cap_env <= 8 ? cap_env : 3) : 8;
+        while (SA < sa_want && fixed + (SA + 1 - 2) * a_stage + 2 * b_stage <= (size_t)kMaxSmem) ++SA;
+        const size_t fixed_sa = fixed + (SA - 2) * a_stage;
+        SB = (int)((kMaxSmem - fixed_sa) / b_stage);
         if (SB > cap) SB = cap;
-        smem = fixed + SB * b_stage;
+        smem = fixed_sa + SB * b_stage;
         found = true;
         break;
       }
