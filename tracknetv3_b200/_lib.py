@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtracknet_b200.so")
+# TNB_LIBRARY: another build of the same ABI (experiments: A/B of a compile-time constant on one box)
+LIB_PATH = os.environ.get("TNB_LIBRARY") or os.path.join(_HERE, "libtracknet_b200.so")
 
 
 class TnbError(RuntimeError):
