@@ -149,12 +149,15 @@ static constexpr int kMaxPredO = 16;
 // 4 threads per pixel, 16 channels each, interleaved in float4 units (thread qd owns channels 16*i + 4*qd .. +3):
 // every load instruction of a warp reads whole 32-byte sectors (64 contiguous bytes per pixel); the 4 partial dot
 // products are folded with two shuffles and thread qd stores outputs o = qd, qd + 4, ...
-template <int O_MAX>
+// FULL: O == O_MAX, known at compile time (the network's out_dim 8): the per-channel `o < O` tests - a quarter of the
+// kernel's instructions as branches, predicates and reconvergence points (ncu source page) - disappear
+template <int O_MAX, bool FULL>
 __global__ void __launch_bounds__(256) predictor_fwd_kernel(SrcDesc src, int N, int H, int W,
                                                             const float* __restrict__ wp,
-                                                            const float* __restrict__ bias, int O, int o0, int OT,
+                                                            const float* __restrict__ bias, int O_rt, int o0, int OT,
                                                             float* __restrict__ y) {
   // this launch computes output channels [o0, o0 + O) of OT (wp / bias already point at channel o0)
+  const int O = FULL ? O_MAX : O_rt;
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float sw[kMaxPredO * 64 + kMaxPredO];
@@ -164,7 +167,13 @@ __global__ void __launch_bounds__(256) predictor_fwd_kernel(SrcDesc src, int N, 
   const bool affine = src.mode != SRC_IDENTITY;
   const long long hw = (long long)H * W, npix = (long long)N * hw;
   const long long total = (npix * 4 + 31) / 32 * 32;  // whole warps: the shuffles below need every lane
-  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < total; it += (long long)gridDim.x * blockDim.x) {
+  // (sample, pixel in sample) of this thread's item, advanced incrementally: a 64-bit division per item was a fifth of the
+  // kernel's instructions (ncu: 706 warp instructions per 8 pixels, issue slots 64 % busy)
+  const long long it0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long pstep = ((long long)gridDim.x * blockDim.x) >> 2;  // blockDim.x is a multiple of 4
+  long long n = (it0 >> 2) / hw, r = (it0 >> 2) - n * hw;
+  for (long long it = it0; it < total; it += (long long)gridDim.x * blockDim.x, r += pstep) {
+    while (r >= hw) { r -= hw; ++n; }
     const long long p = it >> 2;
     const int qd = (int)(it & 3);
     const bool ok = p < npix;
@@ -193,7 +202,6 @@ __global__ void __launch_bounds__(256) predictor_fwd_kernel(SrcDesc src, int N, 
       s[o] += __shfl_xor_sync(0xffffffffu, s[o], 2);
     }
     if (ok) {
-      const long long n = p / hw, r = p - n * hw;
 #pragma unroll
       for (int o = 0; o < O_MAX; ++o)
         if ((o & 3) == qd && o < O) y[(n * OT + o0 + o) * hw + r] = 1.f / (1.f + expf(-(s[o] + sw[kMaxPredO * 64 + o])));
@@ -211,10 +219,9 @@ int launch_predictor_fwd(const SrcDesc& src, int N, int H, int W, const float* w
   // any out_dim (the reference accepts any seq_len, utils/general.py:66-74): groups of up to 16 output channels per launch
   for (int o0 = 0; o0 < O; o0 += kMaxPredO) {
     const int og = std::min(O - o0, kMaxPredO);
-    if (int rc = og <= 8 ? launch_pdl(predictor_fwd_kernel<8>, dim3(grid), dim3(256), 0, st, src, N, H, W, wp + o0 * 64,
-                                      bias + o0, og, o0, O, y)
-                         : launch_pdl(predictor_fwd_kernel<kMaxPredO>, dim3(grid), dim3(256), 0, st, src, N, H, W,
-                                      wp + o0 * 64, bias + o0, og, o0, O, y))
+    auto go = [&](auto kern) { return launch_pdl(kern, dim3(grid), dim3(256), 0, st, src, N, H, W, wp + o0 * 64, bias + o0, og, o0, O, y); };
+    if (int rc = og == 8 ? go(predictor_fwd_kernel<8, true>) : og < 8 ? go(predictor_fwd_kernel<8, false>)
+               : og == kMaxPredO ? go(predictor_fwd_kernel<kMaxPredO, true>) : go(predictor_fwd_kernel<kMaxPredO, false>))
       return rc;
   }
   return 0;
@@ -224,11 +231,12 @@ int launch_predictor_fwd(const SrcDesc& src, int N, int H, int W, const float* w
 // dW[o][c] = sum_p dl[p][o] a[p][c]; db[o] = sum_p dl[p][o]   (autograd of model.py:71-72)
 // Two streaming kernels without block-level barriers (a single tiled kernel with load -> barrier -> compute phases ran
 // at 1.7 TB/s): dA needs only dl and W; dW / db need dl and the activation, reduced in registers along the pixels.
-template <int O_MAX>
+template <int O_MAX, bool FULL>
 __global__ void __launch_bounds__(256) predictor_bwd_da_kernel(long long npix, long long hw, const float* __restrict__ wp,
-                                                               int O, int o0, int OT, const float* __restrict__ dy,
+                                                               int O_rt, int o0, int OT, const float* __restrict__ dy,
                                                                const float* __restrict__ y, float* __restrict__ dA) {
   // output channels [o0, o0 + O) of OT; groups after the first (o0 > 0) add to what the earlier launches wrote
+  const int O = FULL ? O_MAX : O_rt;
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float sw[kMaxPredO * 64];
@@ -237,10 +245,13 @@ __global__ void __launch_bounds__(256) predictor_bwd_da_kernel(long long npix, l
   // 4 threads per pixel, 16 channels each, interleaved in float4 units (thread qd owns channels 16*i + 4*qd .. +3,
   // i = 0..3): every store instruction of a warp then writes whole 32-byte sectors (64 contiguous bytes per pixel)
   const long long total = npix * 4;
-  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < total; it += (long long)gridDim.x * blockDim.x) {
+  const long long it0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long pstep = ((long long)gridDim.x * blockDim.x) >> 2;
+  long long n = (it0 >> 2) / hw, r = (it0 >> 2) - n * hw;  // advanced incrementally (no division in the loop)
+  for (long long it = it0; it < total; it += (long long)gridDim.x * blockDim.x, r += pstep) {
+    while (r >= hw) { r -= hw; ++n; }
     const long long p = it >> 2;
     const int qd = (int)(it & 3);
-    const long long n = p / hw, r = p - n * hw;
     float g[16], yv[O_MAX], dv[O_MAX];
 #pragma unroll
     for (int i = 0; i < 16; ++i) g[i] = 0.f;
@@ -294,10 +305,12 @@ __global__ void __launch_bounds__(256) predictor_bwd_dw_kernel(SrcDesc src, long
   for (int o = 0; o < O_MAX; ++o) { acc[o][0] = acc[o][1] = acc[o][2] = acc[o][3] = 0.f; dsum[o] = 0.f; }
   const long long nchunks = (npix + 31) / 32;
   const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long ch = blockIdx.x * (long long)(blockDim.x >> 5) + warp; ch < nchunks; ch += wstride) {
+  const long long ch0 = blockIdx.x * (long long)(blockDim.x >> 5) + warp;
+  long long n = (ch0 * 32 + lane) / hw, r = (ch0 * 32 + lane) - n * hw;  // of pixel p, advanced incrementally
+  for (long long ch = ch0; ch < nchunks; ch += wstride, r += wstride * 32) {
+    while (r >= hw) { r -= hw; ++n; }
     const long long p0 = ch * 32, p = p0 + lane;
     float d[O_MAX], yv[O_MAX];
-    const long long n = p < npix ? p / hw : 0, r = p < npix ? p - n * hw : 0;
 #pragma unroll
     for (int o = 0; o < O_MAX; ++o) {
       const bool ok = o < O && p < npix;
@@ -384,10 +397,9 @@ int launch_predictor_bwd(const SrcDesc& src, int N, int H, int W, const float* w
   const int gridw = predictor_dw_blocks(npix);
   for (int o0 = 0; o0 < O; o0 += kMaxPredO) {  // groups of up to 16 output channels, see launch_predictor_fwd
     const int og = std::min(O - o0, kMaxPredO);
-    if (int rc = og <= 8 ? launch_pdl(predictor_bwd_da_kernel<8>, dim3(grida), dim3(256), 0, st, npix, hw, wp + o0 * 64, og, o0,
-                                      O, dy, y, dA)
-                         : launch_pdl(predictor_bwd_da_kernel<kMaxPredO>, dim3(grida), dim3(256), 0, st, npix, hw,
-                                      wp + o0 * 64, og, o0, O, dy, y, dA))
+    auto go_a = [&](auto kern) { return launch_pdl(kern, dim3(grida), dim3(256), 0, st, npix, hw, wp + o0 * 64, og, o0, O, dy, y, dA); };
+    if (int rc = og == 8 ? go_a(predictor_bwd_da_kernel<8, true>) : og < 8 ? go_a(predictor_bwd_da_kernel<8, false>)
+               : og == kMaxPredO ? go_a(predictor_bwd_da_kernel<kMaxPredO, true>) : go_a(predictor_bwd_da_kernel<kMaxPredO, false>))
       return rc;
     if (int rc = og <= 8 ? launch_pdl(predictor_bwd_dw_kernel<8>, dim3(gridw), dim3(256), 0, st, src, npix, hw, og, o0, O, dy, y,
                                       part)
