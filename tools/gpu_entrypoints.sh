@@ -20,5 +20,5 @@ if [ "$NG" -ge 2 ]; then
   tail -3 $OUT/train_dp2.log >> $OUT/summary.txt
 fi
 ls -la $EXP/t $EXP/i >> $OUT/summary.txt 2>&1
-tail -3 $OUT/train.log $OUT/train_inpaint.log $OUT/predict_weight.log >> $OUT/summary.txt
+for f in $OUT/train.log $OUT/train_inpaint.log $OUT/predict_weight.log; do tail -n 3 $f >> $OUT/summary.txt; done
 cat $OUT/summary.txt
