@@ -16,6 +16,9 @@ using namespace tnb;
 struct Args {
   int N, a_sbo, a_off, a_lbo, taps, iters;  // taps: 1 = same address every MMA, 9 = (dy, dx) pattern with row pitch a_sbo
   unsigned long long* clocks;
+  int merged;  // 0: uniform MMAs of width N. The 64-wide conv tiles issue x_hi * [w_hi | w_lo] (N = 128) and x_lo * w_hi
+               // (N = 64) into one accumulator: 1 = alternating per K step (what the kernel does), 2 = the N = 128 MMAs
+               // of a 3-tap weight stage first, then its N = 64 MMAs (two shape switches per stage instead of twelve)
 };
 
 __global__ void __launch_bounds__(128, 1) probe_kernel(const Args a) {
@@ -42,7 +45,38 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const Args a) {
     const uint64_t a_desc0 = make_smem_desc(smem_u32(a_base) + a.a_off, a.a_lbo, a.a_sbo);
     const uint64_t b_desc0 = make_smem_desc(smem_u32(b_base), a.N * 16, 128);
     long long t0 = 0;
-    if (lead) {
+    if (lead && a.merged) {
+      const uint32_t id128 = make_idesc(128, 128, 0, 0, 0), id64 = make_idesc(128, 64, 0, 0, 0);
+      const uint64_t b128 = make_smem_desc(smem_u32(b_base), 128 * 16, 128);  // [plane][hi 64 | lo 64 rows]
+      t0 = clock64();
+      for (int it = 0; it < a.iters; ++it) {
+        for (int g = 0; g < 3; ++g) {  // one weight stage = one filter row: 3 taps x 2 K steps, two M tiles
+          for (int mt = 0; mt < 2; ++mt) {
+            const uint32_t d = tmem_base + mt * 128;
+            if (a.merged == 1) {
+              for (int t = 0; t < 3; ++t)
+                for (int ks = 0; ks < 2; ++ks) {
+                  const uint32_t off = (uint32_t)(g * a.a_sbo + t * 16 + mt * 128 + ks * 2 * a.a_lbo);
+                  umma_f16(d, a_desc0 + (off >> 4), b128 + ((ks * 2 * 128 * 16) >> 4), id128, 1);
+                  umma_f16(d, a_desc0 + ((off + 4 * a.a_lbo) >> 4), b128 + ((ks * 2 * 128 * 16) >> 4), id64, 1);
+                }
+            } else {
+              for (int t = 0; t < 3; ++t)
+                for (int ks = 0; ks < 2; ++ks) {
+                  const uint32_t off = (uint32_t)(g * a.a_sbo + t * 16 + mt * 128 + ks * 2 * a.a_lbo);
+                  umma_f16(d, a_desc0 + (off >> 4), b128 + ((ks * 2 * 128 * 16) >> 4), id128, 1);
+                }
+              for (int t = 0; t < 3; ++t)
+                for (int ks = 0; ks < 2; ++ks) {
+                  const uint32_t off = (uint32_t)(g * a.a_sbo + t * 16 + mt * 128 + ks * 2 * a.a_lbo);
+                  umma_f16(d, a_desc0 + ((off + 4 * a.a_lbo) >> 4), b128 + ((ks * 2 * 128 * 16) >> 4), id64, 1);
+                }
+            }
+          }
+        }
+      }
+      umma_commit(bar);
+    } else if (lead) {
       t0 = clock64();
       for (int it = 0; it < a.iters; ++it) {
         for (int tap = 0; tap < a.taps; ++tap) {
@@ -88,7 +122,7 @@ int main() {
   };
   for (int N : Ns)
     for (const Cfg& c : cfgs) {
-      Args a{N, c.sbo, c.off, c.lbo, c.taps, c.taps == 9 ? 400 : 3600, clocks};
+      Args a{N, c.sbo, c.off, c.lbo, c.taps, c.taps == 9 ? 400 : 3600, clocks, 0};
       unsigned long long best = ~0ull;
       for (int rep = 0; rep < 3; ++rep) {
         probe_kernel<<<sms, 128, smem>>>(a);
@@ -103,5 +137,21 @@ int main() {
       printf("N %3d  %-70s %7.1f clk/MMA  (floor %3d, A 4096 + B %5d bytes -> %5.1f B/clk)\n", N, c.what, per, N / 2, N * 32,
              (4096.0 + N * 32) / per);
     }
+  printf("merged 64-wide form: pairs of one N = 128 and one N = 64 MMA (floor 64 + 32 = 96 clocks of math, 14 KB of operands = 112 clocks)\n");
+  for (int merged = 1; merged <= 2; ++merged) {
+    Args a{64, 288, 0, 5280, 9, 300, clocks, merged};
+    unsigned long long best = ~0ull;
+    for (int rep = 0; rep < 3; ++rep) {
+      probe_kernel<<<sms, 128, smem>>>(a);
+      CK(cudaDeviceSynchronize());
+      std::vector<unsigned long long> h(sms);
+      CK(cudaMemcpy(h.data(), clocks, sizeof(unsigned long long) * sms, cudaMemcpyDeviceToHost));
+      unsigned long long mx = 0;
+      for (auto v : h) mx = v > mx ? v : mx;
+      if (mx < best) best = mx;
+    }
+    printf("  %-60s %7.1f clocks per pair\n", merged == 1 ? "alternating N = 128 / N = 64 (issue order of the kernel)" : "grouped: six N = 128 MMAs, then six N = 64 MMAs per weight stage",
+           (double)best / (a.iters * 3 * 2 * 6));
+  }
   return 0;
 }
