@@ -78,6 +78,9 @@ typedef struct {
   float* gmax;       /* reduce, optional: device scalar, atomically raised to max |g| of the masked incoming gradient (zero
                         it first); apply with dz_format 2: read */
   float* dz_mul;     /* apply with dz_format 2: device scalar that receives the power-of-two multiplier dz was stored with */
+  int act_pool;      /* apply with act_presplit: 0 = the activation at this layer's resolution [N,H,W][2][C]; 1 = its
+                        2x2 max-pool [N,H/2,W/2][2][C] (H, W even) - the wgrad operand of a next layer that reads this one
+                        through MaxPool2d (model.py:59,61,63) */
 } tnb_bnbwd_t;
 
 typedef struct {

@@ -365,6 +365,14 @@ def test_bn_relu_backward_with_gradient_routing(consumers):
             assert dz.abs().max().item() * mul < 65504  # nothing was clamped
         assert G.max_abs(G.unsplit(dzs, (n, h, w, c), fmt, mul), dz) <= G.split_tol(fmt) * dz.abs().max().item()
         assert G.max_abs(G.unsplit(acts, (n, h, w, c), fmt), G.nhwc(act_ref)) <= G.split_tol(fmt) * act_ref.abs().max().item()
+    # ... or its 2x2 max-pool at half resolution (act_pool): the operand of a next layer that reads this one through MaxPool2d
+    pooled = torch.zeros(n * (h // 2) * (w // 2) * c * 4, dtype=torch.uint8, device=G.DEV)
+    args.dz_format, args.act_presplit, args.act_pool = 1, pooled.data_ptr(), 1
+    _lib.check(L.tnb_bn_relu_bwd_apply(C.byref(args), G.st()))
+    torch.cuda.synchronize()
+    pool_ref = F.max_pool2d(act_ref, 2, 2)
+    assert G.max_abs(G.unsplit(pooled, (n, h // 2, w // 2, c), 1), G.nhwc(pool_ref)) <= G.split_tol(1) * pool_ref.abs().max().item()
+    args.act_pool, args.act_presplit = 0, None
     # d gamma / d beta from the same reductions (checked through a second autograd pass)
     z2 = z.detach().clone(); g2 = gamma.clone().requires_grad_(True); b2 = beta.clone().requires_grad_(True)
     a2 = F.relu(F.batch_norm(z2, None, None, g2, b2, True, 0.1, 1e-5))

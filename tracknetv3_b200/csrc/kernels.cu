@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnB
           *reinterpret_cast<uint2*>(base) = make_uint2(h01, h23);
           *reinterpret_cast<uint2*>(base + 2 * a.C) = make_uint2(l01, l23);
         }
-        if (a.act_presplit != nullptr) {  // the activation itself, pre-split: the next layer's wgrad operand
+        if (a.act_presplit != nullptr && !a.act_pool) {  // the activation itself, pre-split: the next layer's wgrad operand
           uint32_t h01, l01, h23, l23;
           if (a.dz_format == 2) {
             split2<0>(fmaxf(act[k].x, 0.f), fmaxf(act[k].y, 0.f), h01, l01);
@@ -609,6 +609,23 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnB
         acc2.z = fmaf(d.z, xh.z, acc2.z);
         acc2.w = fmaf(d.w, xh.w, acc2.w);
       }
+    }
+    if (APPLY && a.act_presplit != nullptr && a.act_pool) {
+      // the 2x2 window this thread holds IS a max-pool window: maxpool(relu(bn(z))) of the next layer's input view,
+      // pre-split, one pixel of the half-resolution tensor (H, W even: all four elements are valid)
+      float4 mx = make_float4(0.f, 0.f, 0.f, 0.f);  // relu: the maximum is at least 0
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        mx.x = fmaxf(mx.x, act[k].x); mx.y = fmaxf(mx.y, act[k].y);
+        mx.z = fmaxf(mx.z, act[k].z); mx.w = fmaxf(mx.w, act[k].w);
+      }
+      uint32_t h01, l01, h23, l23;
+      if (a.dz_format == 2) { split2<0>(mx.x, mx.y, h01, l01); split2<0>(mx.z, mx.w, h23, l23); }
+      else                  { split2<1>(mx.x, mx.y, h01, l01); split2<1>(mx.z, mx.w, h23, l23); }
+      const size_t ppix = (size_t)(n * (a.H >> 1) + wh) * (a.W >> 1) + ww;
+      uint8_t* base = reinterpret_cast<uint8_t*>(a.act_presplit) + (ppix * 2 * a.C + c) * 2;
+      *reinterpret_cast<uint2*>(base) = make_uint2(h01, h23);
+      *reinterpret_cast<uint2*>(base + 2 * a.C) = make_uint2(l01, l23);
     }
   }
   if (APPLY && a.amax != nullptr) {
@@ -647,6 +664,8 @@ static int bn_bwd_cfg(const BnBwdArgs& a) {
 }
 static int bn_bwd_check(const BnBwdArgs& a) {
   TNB_REQUIRE(a.C % 4 == 0 && 256 % (a.C / 4) == 0, "bn_bwd: unsupported channel count %d", a.C);
+  TNB_REQUIRE(!(a.act_presplit != nullptr && a.act_pool) || (a.H % 2 == 0 && a.W % 2 == 0),
+              "bn_bwd: the pooled activation needs even H, W (got %d x %d)", a.H, a.W);
   TNB_REQUIRE(a.dz_format >= 0 && a.dz_format <= 2 && (a.dz_format != 2 || (a.gmax != nullptr && a.dz_mul != nullptr)),
               "bn_bwd: dz_format %d (2 needs the gmax / dz_mul scalars)", a.dz_format);
   TNB_REQUIRE((long long)a.N * ((a.H + 1) / 2) * ((a.W + 1) / 2) * (a.C / 4) < (1ll << 31), "bn_bwd: tensor too large");

@@ -88,12 +88,19 @@ struct Bump {
   }
 };
 
-// Layer l reads the activation of layer l - 1 as it is (BN + ReLU, same resolution, no concat): its wgrad operand can
-// be written by the BatchNorm-backward apply pass of layer l - 1 (which recomputes that activation anyway) instead of
-// a separate view pass; the wgrad of layer l is then launched right after that pass.
+// Layer l reads the activation of layer l - 1 - as it is, through MaxPool2d, or (first half of a decoder concat) through
+// the x2 upsampling: that operand of its weight gradient is written by the BatchNorm-backward apply pass of layer l - 1,
+// which recomputes the activation anyway (tnb_bnbwd_t.act_presplit: at its own resolution - the upsampled half is read
+// through (h/2, w/2) addressing - or max-pooled, act_pool), instead of a separate view pass over z; the wgrad of layer l
+// is launched right after that pass. The skip half of a concat still comes from a view pass: its producer's apply pass
+// runs many layers later.
 bool wgrad_operand_from_bn_bwd(const tnb_tracknet_cfg_t& c, int l) {
   if (c.variant & 128) return false;  // variant bit 128: always materialise with tnb_view_presplit (ablation)
-  return l > 0 && kDefs[l].src0 == l - 1 && kDefs[l].src1 < 0 && kDefs[l].mode0 == SRC_AFFINE_RELU;
+  if (l <= 0 || kDefs[l].src0 != l - 1) return false;
+  const LayerDef& d = kDefs[l];
+  if (c.variant & 8192) return d.src1 < 0 && d.mode0 == SRC_AFFINE_RELU;  // bit 8192: plain layers only (ablation)
+  if (d.src1 < 0) return d.mode0 == SRC_AFFINE_RELU || d.mode0 == SRC_AFFINE_RELU_POOL;
+  return d.mode0 == SRC_AFFINE_RELU_UP && d.mode1 == SRC_AFFINE_RELU;
 }
 
 // Operand format of the backward pass's tensor-core kernels. 3-term products (the default precision): bf16 (hi, lo) pairs,
@@ -342,9 +349,10 @@ static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const 
     }
     return launch_wgrad3x3(pv, W.dz, dw, W.cout, W.cin_real, c.bwd_terms, (c.variant >> 2) & 3, st, P.wgrad_ws, bf, mul);
   };
-  // layer whose wgrad waits for its operand from the next BatchNorm-backward apply pass; a range that does not start
-  // at the top inherits the one its predecessor left behind
-  int pending = (hi + 1 < kLayers && wgrad_operand_from_bn_bwd(c, hi + 1)) ? hi + 1 : -1;
+  // layer whose wgrad waits for its operand from the next BatchNorm-backward apply pass. Nothing waits across the end
+  // of a range: the last layer of a range that is not the last range materialises its view with a view pass instead
+  // (same values bit for bit), so that all gradients of the range are final when the call returns
+  int pending = -1;
   for (int l = hi; l >= lo; --l) {
     LayerBuf& B = P.L[l];
     BnBwdArgs a;
@@ -378,9 +386,17 @@ static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const 
                                         (float*)grads[l * 3 + 1], (float*)grads[l * 3 + 2], st))
       return rc;
     a.act_presplit = (pending == l + 1) ? P.vsplit : nullptr;
+    a.act_pool = (pending == l + 1 && kDefs[pending].mode0 == SRC_AFFINE_RELU_POOL) ? 1 : 0;
     if (int rc = launch_bn_bwd_apply(a, st)) return rc;
     if (pending == l + 1) {
-      if (int rc = run_wgrad(pending, wgrad_view(c, pending, P.vsplit))) return rc;
+      const ViewDesc pv = wgrad_view(c, pending, P.vsplit);
+      if (pv.C0 < pv.C) {  // decoder concat: the skip half (second source) from a view pass, behind the half just written
+        const ViewDesc v = make_view(P, c, pending);
+        ViewDesc v1 = v;
+        v1.s[0] = v.s[1]; v1.s[1] = v.s[1]; v1.C0 = v1.C = v.C - v.C0;
+        if (int rc = launch_view_presplit(v1, const_cast<float*>(pv.s[1].ptr), bf, st)) return rc;
+      }
+      if (int rc = run_wgrad(pending, pv)) return rc;
       pending = -1;
     }
     if (l > 0) {
@@ -397,7 +413,7 @@ static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const 
                                   c.variant & 3, st, Pp != nullptr ? &fuse : nullptr))
         return rc;
     }
-    if (wgrad_operand_from_bn_bwd(c, l)) { pending = l; continue; }
+    if (wgrad_operand_from_bn_bwd(c, l) && !(l == lo && lo > 0)) { pending = l; continue; }
     // materialise the input view once (bf16 hi/lo), then both wgrad operands are plain copies
     const ViewDesc v = make_view(P, c, l);
     const ViewDesc pv = wgrad_view(c, l, P.vsplit);
@@ -542,9 +558,8 @@ int tracknet_backward(const tnb_tracknet_cfg_t& c, const float* dy, const float*
   });
 }
 
-// First layer of the backward pass's second range in data-parallel training (tnb_tracknet_backward_range): the wgrad
-// of bottleneck.conv_1 (layer 7) reads a pooled view, so no weight gradient is left pending across this boundary, and
-// layers 7..16 + the predictor hold 9.59 M of TrackNet's 11.34 M parameters.
+// First layer of the backward pass's second range in data-parallel training (tnb_tracknet_backward_range): layers
+// 7..16 + the predictor hold 9.59 M of TrackNet's 11.34 M parameters.
 int tracknet_grad_split_layer() { return 7; }
 
 void graph_stats(long long* out4) {
