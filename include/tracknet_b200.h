@@ -81,6 +81,9 @@ typedef struct {
   int act_pool;      /* apply with act_presplit: 0 = the activation at this layer's resolution [N,H,W][2][C]; 1 = its
                         2x2 max-pool [N,H/2,W/2][2][C] (H, W even) - the wgrad operand of a next layer that reads this one
                         through MaxPool2d (model.py:59,61,63) */
+  void* act_full;    /* apply, optional: the activation at this layer's resolution [N,H,W][2][C] pre-split, in addition to
+                        act_presplit (an encoder block's last layer feeds the next block through the pool AND a decoder
+                        concat as the skip connection: both wgrad operands come out of one pass) */
 } tnb_bnbwd_t;
 
 typedef struct {

@@ -52,10 +52,12 @@ def test_workspace_and_plan_queries():
     assert lib.tnb_tracknet_num_launches(C.byref(cfg), 0) == 37
     cfg.training = 1
     assert lib.tnb_tracknet_num_launches(C.byref(cfg), 0) == 38       # + the num_batches_tracked counters
-    # backward: predictor (dA, dW, final sum) 3, (reduce, finalize, apply, wgrad) x 17, view_presplit 1 (network input)
-    # + 3 (skip halves of the decoder concats; every other wgrad operand comes out of a BatchNorm-backward apply pass),
-    # dgrad 16, ordered split-K sums 17
+    # backward: predictor (dA, dW, final sum) 3, (reduce, finalize, apply, wgrad) x 17, view_presplit 1 (the network
+    # input: every other wgrad operand comes out of a BatchNorm-backward apply pass), dgrad 16, ordered split-K sums 17
+    assert lib.tnb_tracknet_num_launches(C.byref(cfg), 1) == 105
+    cfg.variant = 16384                                                # skip halves of the 3 decoder concats by view passes
     assert lib.tnb_tracknet_num_launches(C.byref(cfg), 1) == 108
+    cfg.variant = 0
     cfg.out_dim = 20                                                   # predictor kernels take 16 output channels per launch
     assert lib.tnb_tracknet_num_launches(C.byref(cfg), 0) == 39
     assert lib.tnb_heatmap_decode_workspace_bytes(256, 288, 512) == 256 * 5 * 288 * 512 * 4

@@ -35,7 +35,7 @@ class BnBwd(C.Structure):  # tnb_bnbwd_t
                 ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
                 ("part", C.c_void_p), ("sums", C.c_void_p), ("dz", C.c_void_p), ("inv_count", C.c_float),
                 ("amax", C.c_void_p), ("dz_format", C.c_int), ("act_presplit", C.c_void_p),
-                ("gmax", C.c_void_p), ("dz_mul", C.c_void_p), ("act_pool", C.c_int)]
+                ("gmax", C.c_void_p), ("dz_mul", C.c_void_p), ("act_pool", C.c_int), ("act_full", C.c_void_p)]
 
 
 class TrackNetCfg(C.Structure):  # tnb_tracknet_cfg_t

@@ -587,7 +587,8 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnB
           *reinterpret_cast<uint2*>(base) = make_uint2(h01, h23);
           *reinterpret_cast<uint2*>(base + 2 * a.C) = make_uint2(l01, l23);
         }
-        if (a.act_presplit != nullptr && !a.act_pool) {  // the activation itself, pre-split: the next layer's wgrad operand
+        void* const act_out = (a.act_presplit != nullptr && !a.act_pool) ? a.act_presplit : a.act_full;
+        if (act_out != nullptr) {  // the activation itself, pre-split: a later layer's wgrad operand
           uint32_t h01, l01, h23, l23;
           if (a.dz_format == 2) {
             split2<0>(fmaxf(act[k].x, 0.f), fmaxf(act[k].y, 0.f), h01, l01);
@@ -596,7 +597,7 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __grid_constant__ BnB
           split2<1>(fmaxf(act[k].x, 0.f), fmaxf(act[k].y, 0.f), h01, l01);
           split2<1>(fmaxf(act[k].z, 0.f), fmaxf(act[k].w, 0.f), h23, l23);
           }
-          uint8_t* base = reinterpret_cast<uint8_t*>(a.act_presplit) + (pix * 2 * a.C + c) * 2;
+          uint8_t* base = reinterpret_cast<uint8_t*>(act_out) + (pix * 2 * a.C + c) * 2;
           *reinterpret_cast<uint2*>(base) = make_uint2(h01, h23);
           *reinterpret_cast<uint2*>(base + 2 * a.C) = make_uint2(l01, l23);
         }
@@ -664,6 +665,8 @@ static int bn_bwd_cfg(const BnBwdArgs& a) {
 }
 static int bn_bwd_check(const BnBwdArgs& a) {
   TNB_REQUIRE(a.C % 4 == 0 && 256 % (a.C / 4) == 0, "bn_bwd: unsupported channel count %d", a.C);
+  TNB_REQUIRE(a.act_full == nullptr || a.act_presplit == nullptr || a.act_pool,
+              "bn_bwd: act_full is the second output next to a POOLED act_presplit (use act_presplit alone otherwise)");
   TNB_REQUIRE(!(a.act_presplit != nullptr && a.act_pool) || (a.H % 2 == 0 && a.W % 2 == 0),
               "bn_bwd: the pooled activation needs even H, W (got %d x %d)", a.H, a.W);
   TNB_REQUIRE(a.dz_format >= 0 && a.dz_format <= 2 && (a.dz_format != 2 || (a.gmax != nullptr && a.dz_mul != nullptr)),

@@ -48,6 +48,8 @@ struct LayerBuf {
   int bwd_rows;
   int fused_rows;  // > 0: the BatchNorm-backward reduction of THIS layer is produced by the dgrad epilogue of layer + 1
   uint16_t *wf, *wd;
+  uint8_t* cat16;  // decoder concat layers (training): their own pre-split wgrad operand [up half at half resolution | skip
+                   // half], filled by two apply passes many layers apart (whole-pass backward), else nullptr
 };
 
 // The reduction pass of layer p's BatchNorm backward can ride on the dgrad of layer p + 1 when that convolution is
@@ -223,8 +225,14 @@ int build_plan(const tnb_tracknet_cfg_t& c, void* ws, Plan* P) {
       B.bwd_sums = b.take<float>(2 * B.cout);
       B.amax = P->amax_all + l;
       B.wd = (l > 0) ? b.take<uint16_t>(conv3x3_wpack_elems(B.cout, B.cin)) : nullptr;
+      B.cat16 = nullptr;
+      if (d.src1 >= 0 && d.mode0 == SRC_AFFINE_RELU_UP && d.mode1 == SRC_AFFINE_RELU) {
+        const size_t up = (size_t)c.n * (c.h >> kDefs[d.src0].level) * (c.w >> kDefs[d.src0].level) * kDefs[d.src0].cout;
+        B.cat16 = b.take<uint8_t>((up + npix * kDefs[d.src1].cout) * 4);
+      }
     } else {
       B.dz = B.din = B.bwd_part = B.bwd_sums = B.amax = nullptr; B.wd = nullptr; B.bwd_rows = 0; B.fused_rows = 0;
+      B.cat16 = nullptr;
     }
   }
   P->bytes = (b.off + 255) & ~(size_t)255;
@@ -353,6 +361,13 @@ static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const 
   // of a range: the last layer of a range that is not the last range materialises its view with a view pass instead
   // (same values bit for bit), so that all gradients of the range are final when the call returns
   int pending = -1;
+  // Whole-pass backward: the wgrad of a decoder concat layer j waits until the apply pass of its SKIP producer (an
+  // encoder layer, many layers later) has written the second half of its operand too - no view pass at all for it; its
+  // operand lives in the layer's own buffer (cat16) meanwhile. A ranged backward (data parallel) keeps the view pass for
+  // the skip half: every gradient of a range has to be final when the range returns. Variant bit 16384: never defer.
+  const bool defer_skip = hi == kLayers - 1 && lo == 0 && !(c.variant & (128 | 8192 | 16384));
+  int deferred_for[kLayers];  // skip producer layer -> concat layer waiting for it (-1: none)
+  for (int i = 0; i < kLayers; ++i) deferred_for[i] = -1;
   for (int l = hi; l >= lo; --l) {
     LayerBuf& B = P.L[l];
     BnBwdArgs a;
@@ -385,19 +400,34 @@ static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const 
     if (int rc = launch_bn_bwd_finalize(B.bwd_part, B.fused_rows > 0 ? B.fused_rows : B.bwd_rows, B.cout, B.bwd_sums,
                                         (float*)grads[l * 3 + 1], (float*)grads[l * 3 + 2], st))
       return rc;
-    a.act_presplit = (pending == l + 1) ? P.vsplit : nullptr;
+    const bool pend_cat = pending == l + 1 && kDefs[pending].src1 >= 0;  // the waiting layer is a decoder concat
+    a.act_presplit = (pending == l + 1) ? ((pend_cat && defer_skip) ? P.L[pending].cat16 : P.vsplit) : nullptr;
     a.act_pool = (pending == l + 1 && kDefs[pending].mode0 == SRC_AFFINE_RELU_POOL) ? 1 : 0;
+    const int waiting = deferred_for[l];  // concat layer whose skip half is this layer's activation
+    if (waiting >= 0) {
+      const ViewDesc wv = wgrad_view(c, waiting, P.L[waiting].cat16);
+      a.act_full = const_cast<float*>(wv.s[1].ptr);
+      TNB_REQUIRE(a.act_presplit == nullptr || a.act_pool, "tracknet_backward: skip producer %d feeds a plain layer too", l);
+    }
     if (int rc = launch_bn_bwd_apply(a, st)) return rc;
     if (pending == l + 1) {
-      const ViewDesc pv = wgrad_view(c, pending, P.vsplit);
-      if (pv.C0 < pv.C) {  // decoder concat: the skip half (second source) from a view pass, behind the half just written
-        const ViewDesc v = make_view(P, c, pending);
-        ViewDesc v1 = v;
-        v1.s[0] = v.s[1]; v1.s[1] = v.s[1]; v1.C0 = v1.C = v.C - v.C0;
-        if (int rc = launch_view_presplit(v1, const_cast<float*>(pv.s[1].ptr), bf, st)) return rc;
+      if (pend_cat && defer_skip) {
+        deferred_for[kDefs[pending].src1] = pending;  // up half written; the skip half follows with that layer's apply pass
+      } else {
+        const ViewDesc pv = wgrad_view(c, pending, P.vsplit);
+        if (pv.C0 < pv.C) {  // decoder concat: the skip half (second source) from a view pass, behind the half just written
+          const ViewDesc v = make_view(P, c, pending);
+          ViewDesc v1 = v;
+          v1.s[0] = v.s[1]; v1.s[1] = v.s[1]; v1.C0 = v1.C = v.C - v.C0;
+          if (int rc = launch_view_presplit(v1, const_cast<float*>(pv.s[1].ptr), bf, st)) return rc;
+        }
+        if (int rc = run_wgrad(pending, pv)) return rc;
       }
-      if (int rc = run_wgrad(pending, pv)) return rc;
       pending = -1;
+    }
+    if (waiting >= 0) {
+      if (int rc = run_wgrad(waiting, wgrad_view(c, waiting, P.L[waiting].cat16))) return rc;
+      deferred_for[l] = -1;
     }
     if (l > 0) {
       ViewDesc dv;
@@ -598,7 +628,9 @@ int tracknet_num_launches(const tnb_tracknet_cfg_t& c, int backward) {
   // predictor backward (dA + dW per group, final sum), (reduce [unless fused into the next layer's dgrad], finalize,
   // apply, wgrad) x17, view_presplit for the layers whose operand the apply pass did not emit (+ the second tensor of
   // the 3 decoder concat layers), dgrad x16, scatter
-  return 2 * pred_groups + 1 + kLayers * 4 - fused + (kLayers - emitted) + 3 + (kLayers - 1) + scatter;
+  // (whole pass: the skip halves of the 3 decoder concats come out of apply passes as well unless a variant bit says no)
+  const int skip_views = (c.variant & (128 | 8192 | 16384)) ? 3 : 0;
+  return 2 * pred_groups + 1 + kLayers * 4 - fused + (kLayers - emitted) + skip_views + (kLayers - 1) + scatter;
 }
 
 }  // namespace tnb
