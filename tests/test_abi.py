@@ -52,11 +52,12 @@ def test_workspace_and_plan_queries():
     assert lib.tnb_tracknet_num_launches(C.byref(cfg), 0) == 37
     cfg.training = 1
     assert lib.tnb_tracknet_num_launches(C.byref(cfg), 0) == 38       # + the num_batches_tracked counters
-    # backward: predictor (dA, dW, final sum) 3, (reduce, finalize, apply, wgrad) x 17, view_presplit 1 (the network
-    # input: every other wgrad operand comes out of a BatchNorm-backward apply pass), dgrad 16, ordered split-K sums 17
-    assert lib.tnb_tracknet_num_launches(C.byref(cfg), 1) == 105
+    # backward: predictor (dA, dW, final sum) 3, (reduce, finalize, apply, wgrad) x 17, no view pass at all (the network
+    # input is pre-split by the forward's pack launch, every other wgrad operand comes out of a BatchNorm-backward apply
+    # pass), dgrad 16, ordered split-K sums 17
+    assert lib.tnb_tracknet_num_launches(C.byref(cfg), 1) == 104
     cfg.variant = 16384                                                # skip halves of the 3 decoder concats by view passes
-    assert lib.tnb_tracknet_num_launches(C.byref(cfg), 1) == 108
+    assert lib.tnb_tracknet_num_launches(C.byref(cfg), 1) == 107
     cfg.variant = 0
     cfg.out_dim = 20                                                   # predictor kernels take 16 output channels per launch
     assert lib.tnb_tracknet_num_launches(C.byref(cfg), 0) == 39

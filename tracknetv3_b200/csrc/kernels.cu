@@ -13,7 +13,7 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 // input packing: NCHW fp32 (reference train.py:86 x.float().cuda()) -> NHWC fp32, channels padded to Cpad
 // =============================================================================================
 __global__ void pack_input_kernel(const float* __restrict__ x, float* __restrict__ out, uint8_t* __restrict__ planar,
-                                  int N, int C, int H, int W, int Cpad) {
+                                  uint8_t* __restrict__ presplit, int presplit_fmt, int N, int C, int H, int W, int Cpad) {
   pdl_launch_dependents();
   pdl_wait();
   const long long npix = (long long)N * H * W;
@@ -42,14 +42,22 @@ __global__ void pack_input_kernel(const float* __restrict__ x, float* __restrict
         *reinterpret_cast<uint4*>(planar + (plane_hi * hw + r) * 16) = hi;
         *reinterpret_cast<uint4*>(planar + ((plane_hi + 4) * hw + r) * 16) = lo;
       }
+      if (presplit != nullptr) {  // [pixel][2 (hi, lo)][Cpad] 16-bit: the first layer's weight-gradient operand
+        uint4 hi, lo;
+        if (presplit_fmt == 0) split8<0>(v, hi, lo); else split8<1>(v, hi, lo);
+        uint8_t* dst16 = presplit + ((size_t)p * 2 * Cpad + c8) * 2;
+        *reinterpret_cast<uint4*>(dst16) = hi;
+        *reinterpret_cast<uint4*>(dst16 + 2 * Cpad) = lo;
+      }
     }
   }
 }
-int launch_pack_input(const float* x, float* out, int N, int C, int H, int W, int Cpad, cudaStream_t st, void* planar) {
+int launch_pack_input(const float* x, float* out, int N, int C, int H, int W, int Cpad, cudaStream_t st, void* planar,
+                      void* presplit, int presplit_fmt) {
   TNB_REQUIRE(Cpad % 8 == 0 && (planar == nullptr || Cpad % 32 == 0), "pack_input: padded channel count %d", Cpad);
   const long long npix = (long long)N * H * W;
   if (int rc = launch_pdl(pack_input_kernel, dim3(min(cdiv(npix, 256), 148 * 16)), dim3(256), 0, st, x, out,
-                          (uint8_t*)planar, N, C, H, W, Cpad)) return rc;
+                          (uint8_t*)planar, (uint8_t*)presplit, presplit_fmt, N, C, H, W, Cpad)) return rc;
   TNB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -11,7 +11,7 @@ using BnBwdArgs = tnb_bnbwd_t;
 int launch_view_presplit(const ViewDesc& view, void* out, int fmt, cudaStream_t st);
 int launch_presplit(const float* x, void* out, long long npixels, int C, int fmt, float mul, cudaStream_t st);
 int launch_pack_input(const float* x_nchw, float* out_nhwc, int N, int C, int H, int W, int Cpad, cudaStream_t st,
-                      void* out_planar16 = nullptr);
+                      void* out_planar16 = nullptr, void* out_presplit = nullptr, int presplit_fmt = 1);
 int launch_bn_finalize(const float* part, int rows, double count, const float* gamma, const float* beta,
                        float* running_mean, float* running_var, float momentum, float eps, int training,
                        float* scale, float* shift, float* mean, float* invstd, int C, cudaStream_t st);

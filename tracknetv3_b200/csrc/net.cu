@@ -71,6 +71,9 @@ struct Plan {
                     // two each layer's dz is stored multiplied by (written by the apply pass, read by dgrad / wgrad)
   float* xin;       // network input, fp32 NHWC padded to cpad channels (first layer's wgrad view; its forward view when
                     // the tensor-TMA path does not apply)
+  uint8_t* xin_split;  // training with the tensor-TMA input path: the input pre-split [pixel][hi | lo][cpad] in the
+                       // backward pass's 16-bit format - the first layer's weight-gradient operand, written by the same
+                       // pack launch (the fp32 tensor and a view pass over it are then not needed at all)
   uint8_t* xin16;   // the same as planar fp16 (hi, lo) planes (TNB_SRC_PLANAR16): the first convolution stages its halo
                     // tiles from it with tensor-TMA; nullptr when the layer's tile plan is not row-major / <= 30 columns
   float* dA_pred;
@@ -195,6 +198,7 @@ int build_plan(const tnb_tracknet_cfg_t& c, void* ws, Plan* P) {
     if (env != 0 && !(c.variant & 4096) && c.fwd_terms == 3 && !cp.tall && (8 * cp.MT + 2) * 8 <= 256)
       P->xin16 = b.take<uint8_t>(npix0 * P->cpad * 4);
   }
+  P->xin_split = (P->xin16 != nullptr && c.training && !(c.variant & 128)) ? b.take<uint8_t>(npix0 * P->cpad * 4) : nullptr;
   P->dA_pred = b.take<float>(npix0 * 64);
   for (int l = 0; l < kLayers; ++l) {
     LayerBuf& B = P->L[l];
@@ -284,8 +288,8 @@ static int forward_enqueue(const tnb_tracknet_cfg_t& c, const float* x, void* co
   if (int rc = build_plan(c, ws, &P)) return rc;
   TNB_REQUIRE(ws_bytes >= P.bytes, "tracknet_forward: workspace too small (%zu < %zu)", ws_bytes, P.bytes);
   // fp32 NHWC for the first layer's weight gradient (training) or its gather path; planar fp16 pairs for tensor-TMA
-  float* xin32 = (c.training || P.xin16 == nullptr) ? P.xin : nullptr;
-  if (int rc = launch_pack_input(x, xin32, c.n, c.in_dim, c.h, c.w, P.cpad, st, P.xin16)) return rc;
+  float* xin32 = ((c.training && P.xin_split == nullptr) || P.xin16 == nullptr) ? P.xin : nullptr;
+  if (int rc = launch_pack_input(x, xin32, c.n, c.in_dim, c.h, c.w, P.cpad, st, P.xin16, P.xin_split, bwd_fmt(c))) return rc;
   // every weight operand of the step in ONE launch: the 17 forward images (fp16 hi/lo) and, when a backward will
   // follow, the 16 dgrad images (bf16 hi/lo, rotated / transposed) - the parameters do not change in between
   PackTable pt;
@@ -444,6 +448,10 @@ static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const 
         return rc;
     }
     if (wgrad_operand_from_bn_bwd(c, l) && !(l == lo && lo > 0)) { pending = l; continue; }
+    if (l == 0 && P.xin_split != nullptr) {  // the network input, pre-split by the forward's pack launch
+      if (int rc = run_wgrad(0, wgrad_view(c, 0, P.xin_split))) return rc;
+      continue;
+    }
     // materialise the input view once (bf16 hi/lo), then both wgrad operands are plain copies
     const ViewDesc v = make_view(P, c, l);
     const ViewDesc pv = wgrad_view(c, l, P.vsplit);
@@ -630,7 +638,10 @@ int tracknet_num_launches(const tnb_tracknet_cfg_t& c, int backward) {
   // the 3 decoder concat layers), dgrad x16, scatter
   // (whole pass: the skip halves of the 3 decoder concats come out of apply passes as well unless a variant bit says no)
   const int skip_views = (c.variant & (128 | 8192 | 16384)) ? 3 : 0;
-  return 2 * pred_groups + 1 + kLayers * 4 - fused + (kLayers - emitted) + skip_views + (kLayers - 1) + scatter;
+  Plan P;  // does the pack launch of the forward pre-split the network input (no view pass for the first layer)?
+  const bool input_presplit = build_plan(c, nullptr, &P) == 0 && P.xin_split != nullptr;
+  return 2 * pred_groups + 1 + kLayers * 4 - fused + (kLayers - emitted) - (input_presplit ? 1 : 0) + skip_views +
+         (kLayers - 1) + scatter;
 }
 
 }  // namespace tnb
