@@ -10,8 +10,8 @@ export TNB_GRAPHS=0   # plain stream launches under the profiler (the library wo
 export TNB_PDL=0      # ncu serialises launches anyway; keep the kernels' own durations free of dependent-launch waits
 timeout -k 5 120 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv python tools/profile_step.py 1 1 > $OUT/ncu_launches.log 2>&1; echo "launch list rc=$?" > $OUT/summary.txt
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,lts__t_bytes.sum
-# 94 matching launches per step (17 fwd + 16 dgrad + 17 wgrad + 10 view_presplit + 34 bn_bwd): skip the warm-up step's
-timeout -k 5 200 ncu --metrics $M --clock-control none -k regex:"conv3x3|wgrad3x3|view_presplit|bn_bwd_kernel" -s 94 --csv --log-file $OUT/tensor_metrics.csv python tools/profile_step.py 1 1 > $OUT/ncu_metrics.log 2>&1; echo "metrics rc=$?" >> $OUT/summary.txt
+# 84 matching launches per step (17 fwd + 16 dgrad + 17 wgrad + 34 bn_bwd; no view pass is left): skip the warm-up step's
+timeout -k 5 200 ncu --metrics $M --clock-control none -k regex:"conv3x3|wgrad3x3|view_presplit|bn_bwd_kernel" -s 84 --csv --log-file $OUT/tensor_metrics.csv python tools/profile_step.py 1 1 > $OUT/ncu_metrics.log 2>&1; echo "metrics rc=$?" >> $OUT/summary.txt
 full() {  # name, kernel regex, skip
   timeout -k 5 100 ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c 1 -o $OUT/$1 python tools/profile_step.py 0 1 > $OUT/ncu_$1.log 2>&1; echo "full $1 rc=$?" >> $OUT/summary.txt
 }
