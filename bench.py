@@ -12,7 +12,8 @@ Printed JSON (one line, rank 0):
   value        frames/s with the fp32 input stack and labels resident in HBM (CUDA events, max over ranks);
   e2e          the same step through the public modules starting from HOST data every step: uint8 frames + integer
                label centres in pinned memory -> H2D on a copy stream (DevicePrefetcher) -> FramePreprocessor (resize /
-               stack / 255 on the GPU) -> label_discs -> TrackNet -> WBCELoss -> backward -> loss.item();
+               stack / 255 on the GPU) -> label_discs -> TrackNet -> WBCELoss -> backward, the loss read back by the host
+               every step (ScalarReader: a side-stream copy that does not drain the compute stream);
   roofline     the tcgen05 conv kernel's algorithmic TFLOP/s from per-launch CUDA events (the same steps repeated once
                more right after the timed region, which itself runs as CUDA-graph replays) against the measured dense
                bf16 peak; `traffic` from the committed ncu pass, refused (null) when the kernel sources changed since;
@@ -279,15 +280,17 @@ def main():
     # are copied H2D inside the timed region (side stream, overlapped with the previous step's compute by the package's
     # DevicePrefetcher); preprocessing and labels run on the GPU; the loss is read back every step
     e2e_state = {"loader": None}
+    reader = T.ScalarReader()
 
     def step_e2e():
         for p in model.parameters():
             p.grad = None
         xd, yd = stage(*next(e2e_state["loader"]))
         loss = T.WBCELoss(model(xd), yd)
+        reader.read(loss)      # D2H copy of the step result (train.py:94) on a side stream, behind the loss kernel only
         loss.backward()
         bucket.allreduce()
-        return loss.item()  # D2H read of the step result, like train.py:94
+        return reader.value()  # the host has this step's loss before the next step starts; the backward is not waited for
 
     def host_batches(count):
         for _ in range(count):
@@ -505,7 +508,8 @@ def main():
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": 4,
                     "path": "pinned uint8 frames + median + int32 label centres -> DevicePrefetcher (copy stream) -> "
-                            "FramePreprocessor + label_discs (GPU) -> TrackNet -> WBCELoss -> backward -> loss.item()"},
+                            "FramePreprocessor + label_discs (GPU) -> TrackNet -> WBCELoss -> backward; the loss is read back every "
+                            "step by ScalarReader (side-stream D2H copy behind the loss kernel, host waits for it each step)"},
             "gpu_launches": launches,
             "cuda_graphs": {"captured": gs[0], "replayed_calls": gs[1], "stream_launched_calls": gs[2], "capture_failures": gs[3]},
             "roofline": roofline, "kernel_breakdown": breakdown, "train_step": train_step,

@@ -576,3 +576,28 @@ def test_eval_loops_vs_oracle():
     for t, (ct, cp) in {"inpaint": (coor, ci), "reconstruct": (coor_pred, ci), "baseline": (coor, coor_pred)}.items():
         w = TT.get_eval_res(D.evaluate(idx2.numpy(), c_true=ct.numpy(), c_pred=cp.numpy(), tolerance=4))
         assert [res2[t][k] for k in ("TP", "TN", "FP1", "FP2", "FN")] == w.tolist(), t
+
+
+def test_scalar_reader_returns_the_value_without_waiting_for_later_work():
+    """ScalarReader: the host gets the scalar that was ready at read(), whatever is enqueued on the compute stream
+    afterwards (the value is not the tensor's LATER content, and value() does not wait for the later kernels)."""
+    import time
+    reader = T.ScalarReader()
+    t = torch.full((1,), 3.5, device=G.DEV)
+    big = torch.rand(8192, 8192, device=G.DEV)
+    torch.cuda.synchronize()
+    reader.read(t)
+    t.add_(1.0)                                   # later work on the compute stream must not leak into the value
+    for _ in range(20):
+        big = big @ big.clamp(-1e-3, 1e-3)        # ~20 x 1.1 TFLOP of later work
+    t0 = time.perf_counter()
+    v = reader.value()
+    waited = time.perf_counter() - t0
+    busy = not torch.cuda.current_stream().query()
+    torch.cuda.synchronize()
+    assert v == 3.5 and t.item() == 4.5
+    assert busy and waited < 0.05, (busy, waited)  # the matmuls were still running when the value arrived
+    with pytest.raises(RuntimeError):
+        reader.value()
+    with pytest.raises(RuntimeError):
+        reader.read(torch.zeros(2, device=G.DEV))

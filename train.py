@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from tracknetv3_b200 import _lib
+from tracknetv3_b200.data import ScalarReader
 from utils.general import get_model
 from utils.metric import WBCELoss
 
@@ -49,6 +50,7 @@ def train_tracknet(model, optimizer, data_loader, param_dict, bucket=None):
         between backward and the optimizer step. """
     model.train()
     epoch_loss = []
+    reader = None  # created with the first CUDA loss (the host-logic tests drive this loop with CPU stand-ins)
     for step, (_, x, y, c, _) in enumerate(data_loader):
         optimizer.zero_grad()
         x, y = x.float().cuda(), y.float().cuda()
@@ -56,11 +58,17 @@ def train_tracknet(model, optimizer, data_loader, param_dict, bucket=None):
             x, y = mixup(x, y, param_dict['alpha'])
         y_pred = model(x)
         loss = WBCELoss(y_pred, y)
-        epoch_loss.append(loss.item())
+        if loss.is_cuda:                       # reference: epoch_loss.append(loss.item()) - here without draining the stream
+            reader = reader or ScalarReader()
+            reader.read(loss)
+        else:
+            epoch_loss.append(loss.item())
         loss.backward()
         if bucket is not None:
             bucket.allreduce()
         optimizer.step()
+        if loss.is_cuda:
+            epoch_loss.append(reader.value())
     return float(np.mean(epoch_loss))
 
 
