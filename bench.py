@@ -255,7 +255,7 @@ def main():
     model._variant = args.variant
     if world > 1:
         broadcast_module(model)
-    bucket = GradBucket(model, overlap=True)
+    bucket = GradBucket(model, overlap=os.environ.get("TNB_ALLREDUCE_OVERLAP") == "1")  # measured: off is faster
     frames_h, median_h, centers_h = synthetic_host_batch(BATCH, 13 + rank)
     frames_pin, median_pin, centers_pin = frames_h.pin_memory(), median_h.pin_memory(), centers_h.pin_memory()
     fp = T.FramePreprocessor(H, W, H, W)

@@ -9,7 +9,7 @@ mkdir -p $OUT
 timeout -k 5 400 python -m pytest tests/test_gpu_dp.py tests/test_gpu_tracknet.py -x -q -m gpu -k "nccl or two_ranges or data_parallel" --timeout=300 > $OUT/pytest_dp.log 2>&1; echo "pytest dp rc=$?" > $OUT/summary.txt
 tail -4 $OUT/pytest_dp.log | cut -c1-300 >> $OUT/summary.txt
 P=29531
-for ov in 1 0 1; do
+for ov in 1 0; do
   P=$((P+1))
   TNB_ALLREDUCE_OVERLAP=$ov timeout -k 5 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $P bench.py --gpus 2 --steps 30 --warmup 5 > $OUT/bench_n2_ov$ov.log 2>&1
   tail -1 $OUT/bench_n2_ov$ov.log | python -c "

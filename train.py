@@ -14,6 +14,7 @@ own batches (seed + rank), the gradients are averaged with ONE in-place NCCL all
 (`GradBucket`, torch-DDP semantics: BatchNorm statistics stay per replica), validation and the checkpoints are rank 0's.
 """
 import argparse
+import os
 
 import numpy as np
 import torch
@@ -172,7 +173,7 @@ def fit(model, optimizer, scheduler, train_loader_fn, val_loader_fn, param_dict,
         import torch.distributed as dist
         from tracknetv3_b200.parallel import GradBucket, broadcast_module
         broadcast_module(model)
-        bucket = GradBucket(model, overlap=True)
+        bucket = GradBucket(model, overlap=os.environ.get("TNB_ALLREDUCE_OVERLAP") == "1")  # measured: off is faster
     for epoch in range(start_epoch, param_dict['epochs']):
         train_loss = train_fn(model, optimizer, train_loader_fn(), param_dict, bucket) if world > 1 else \
             train_fn(model, optimizer, train_loader_fn(), param_dict)
