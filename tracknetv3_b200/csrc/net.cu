@@ -490,7 +490,7 @@ struct GraphCache {
   cudaStream_t side[64] = {};        // per-device capture stream (the caller's stream may be the legacy default stream,
                                      // which cannot be captured); the instantiated graph is launched into the caller's
 };
-constexpr int kMaxGraphs = 8, kMaxSeen = 32;
+constexpr int kMaxGraphs = 16, kMaxSeen = 64;
 GraphCache g_graphs;
 
 int g_graph_switch = [] { const char* e = getenv("TNB_GRAPHS"); return e ? (atoi(e) != 0 ? 1 : 0) : 1; }();

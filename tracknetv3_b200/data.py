@@ -5,18 +5,21 @@ import torch
 from . import _lib
 
 
-def label_discs(centers, height=288, width=512, sigma=2.5):
+def label_discs(centers, height=288, width=512, sigma=2.5, out=None):
     """The training labels of the reference's dataset (dataset.py:400-410 `_get_heatmap`, called with integer centres at
     :632) built ON the device from the coordinates: ``centers`` int (N, L, 2) = (cx, cy) per frame -> float32
     (N, L, height, width) binary discs of radius ``sigma``, all-zero maps where cx == cy == 0. 8 bytes per map cross
-    PCIe instead of a 590 KB fp32 heatmap."""
+    PCIe instead of a 590 KB fp32 heatmap. ``out``: optional preallocated float32 (N, L, height, width) CUDA tensor."""
     lib = _lib.load()
     _lib.require_cuda(centers)
     if centers.dim() != 3 or centers.shape[2] != 2:
         raise RuntimeError(f"label_discs expects integer centres (N, L, 2), got {tuple(centers.shape)}")
     c = centers.to(torch.int32).contiguous()
     n, l = c.shape[0], c.shape[1]
-    out = torch.empty((n, l, height, width), dtype=torch.float32, device=c.device)
+    if out is None:
+        out = torch.empty((n, l, height, width), dtype=torch.float32, device=c.device)
+    elif tuple(out.shape) != (n, l, height, width) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != c.device:
+        raise RuntimeError(f"label_discs: out must be a contiguous float32 {(n, l, height, width)} tensor on {c.device}")
     _lib.check(lib.tnb_label_discs(c.data_ptr(), n * l, height, width, float(sigma), out.data_ptr(), _lib.stream_ptr()))
     return out
 
@@ -27,7 +30,10 @@ class DevicePrefetcher:
     The copy of batch k+1 is enqueued on a dedicated CUDA stream as soon as batch k is handed out, so it overlaps
     with the compute of batch k; the consumer's stream waits on the copy's event, no host synchronisation.
     Two fixed sets of device buffers are cycled (no allocator traffic in the loop): a yielded batch is valid until
-    the next-but-one ``next()`` call, which is what a train / predict loop needs.
+    the next-but-one ``next()`` call, which is what a train / predict loop needs. Only COPIES run on the side stream:
+    running the staging kernels (FramePreprocessor, label discs) there too, next to the compute of the previous batch, was
+    measured and dropped - small grids interleaved with persistent one-CTA-per-SM kernels made the step time erratic
+    (22.8 ... 37 ms per step over four runs, profiles/r2_summary.md).
     """
 
     def __init__(self, host_batches, device=None):

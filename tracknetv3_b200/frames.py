@@ -125,10 +125,11 @@ class FramePreprocessor:
                                           diff.data_ptr(), _lib.stream_ptr()))
         return diff
 
-    def process(self, imgs, median=None, bg_mode=None):
+    def process(self, imgs, median=None, bg_mode=None, out=None):
         """bg_mode: '' | 'concat' (median = prepare_median(...) output) | 'subtract' | 'subtract_concat' (median = the
         float64 (Hs, Ws, 3) median at the source resolution, dataset.py:108-109). Default: 'concat' if a median is
-        given, else ''. Output channels: 3L, 3L + 3, L, 4L (utils/general.py:66-74 get_model's in_dim)."""
+        given, else ''. Output channels: 3L, 3L + 3, L, 4L (utils/general.py:66-74 get_model's in_dim). ``out``: optional
+        preallocated result tensor (a step loop that cycles two of them allocates nothing)."""
         if bg_mode is None:
             bg_mode = 'concat' if median is not None else ''
         if bg_mode not in ('', 'concat', 'subtract', 'subtract_concat'):
@@ -140,7 +141,11 @@ class FramePreprocessor:
         flat = imgs.reshape(n * l, *imgs.shape[2:]).contiguous()
         per_frame = {'': 3, 'concat': 3, 'subtract': 1, 'subtract_concat': 4}[bg_mode]
         extra = 3 if bg_mode == 'concat' else 0
-        out = torch.empty((n, per_frame * l + extra, self.h, self.w), dtype=torch.float32, device=self.device)
+        shape = (n, per_frame * l + extra, self.h, self.w)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != self.device:
+            raise RuntimeError(f"FramePreprocessor.process: out must be a contiguous float32 {shape} tensor on {self.device}")
         if bg_mode in ('subtract', 'subtract_concat'):
             self._run(self._difference(flat, median), out, l, per_frame - 1, per_frame)
         if bg_mode != 'subtract':
