@@ -64,6 +64,34 @@ def test_workspace_and_plan_queries():
     assert lib.tnb_heatmap_decode_workspace_bytes(256, 288, 512) == 256 * 5 * 288 * 512 * 4
 
 
+def test_backward_range_split_and_debug_layer_queries():
+    """Host-only queries of the data-parallel / debugging entry points (no device work)."""
+    lib = _lib.load()
+    assert lib.tnb_tracknet_grad_split_layer() == 7   # bottleneck.conv_1: 9.59 M of 11.34 M parameters lie behind it
+    import tracknetv3_b200 as T
+    m = T.TrackNet(27, 8)
+    params = list(m.parameters())
+    tail = sum(p.numel() for p in params[3 * 7:])
+    assert len(params) == 53 and sum(p.numel() for p in params) == 11341000 and tail == 9590536
+    cfg = _lib.TrackNetCfg(n=2, h=64, w=96, in_dim=27, out_dim=8, training=1, fwd_terms=3, bwd_terms=3, variant=0,
+                           bn_eps=1e-5, bn_momentum=0.1)
+    nbytes = lib.tnb_tracknet_workspace_bytes(C.byref(cfg))
+    ptrs, dims = (C.c_void_p * 8)(), (C.c_int * 5)()
+    seen = []
+    for layer, (hh, ww, cin, cout) in ((0, (64, 96, 32, 64)), (7, (8, 12, 256, 512)), (10, (16, 24, 768, 256)), (16, (64, 96, 64, 64))):
+        # workspace = NULL: the "pointers" are the byte offsets of the layer's tensors inside a workspace
+        _lib.check(lib.tnb_tracknet_debug_layer(C.byref(cfg), None, layer, ptrs, dims))
+        assert tuple(dims)[:4] == (hh, ww, cin, cout) and dims[4] == 1          # bf16 pairs in the 3-term backward
+        offs = [ptrs[i] or 0 for i in range(8)]
+        assert 0 < offs[0] < offs[5] < nbytes and (layer == 0) == (offs[6] == 0) and offs[7] == 0
+        seen.append(offs[0])
+    assert seen == sorted(seen)                                                   # layers are laid out in order
+    cfg.bwd_terms = 1                                                             # single-pass backward: fp16 pairs + multiplier
+    _lib.check(lib.tnb_tracknet_debug_layer(C.byref(cfg), None, 3, ptrs, dims))
+    assert dims[4] == 0 and (ptrs[7] or 0) > 0
+    assert lib.tnb_tracknet_debug_layer(C.byref(cfg), None, 17, ptrs, dims) != 0  # no such layer
+
+
 def test_no_oracle_or_torch_fallback_in_product():
     """The product path must not import the oracle, and must fail loudly without CUDA."""
     import torch
