@@ -88,7 +88,8 @@ def _worker(rank, world, port, q):
     for p in net.parameters():
         p.grad = flat[off:off + p.numel()].view_as(p)
         off += p.numel()
-    bucket = GradBucket(net)
+    bucket = GradBucket(net, overlap=True)  # asked for, not available (gloo, a module without a two-range backward): one call
+    assert bucket.split is None and not hasattr(net, "_grad_split")
     assert bucket._shared_flat([p.grad for p in net.parameters()]) is not None
     bucket.allreduce()
     assert torch.equal(flat, g) and torch.equal(torch.cat([p.grad.flatten() for p in net.parameters()]), g)
