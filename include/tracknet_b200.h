@@ -330,7 +330,8 @@ int tnb_tracknet_num_launches(const tnb_tracknet_cfg_t* cfg, int backward);
  * ([cout] fp32 each), dz (gradient w.r.t. z in the pre-split 16-bit format the backward pass uses), din (gradient w.r.t.
  * the layer's input view, fp32 NHWC [N,H,W,cin]; NULL for layer 0), dz multiplier (device scalar; fp16 pairs only, else
  * NULL); out_dim[0..4] = H, W, cin, cout, 16-bit format of dz (0 fp16 pairs of dz * multiplier, 1 bf16 pairs). Pointers
- * are valid after tnb_tracknet_forward (z, scale ...) / tnb_tracknet_backward (dz, din) of the same cfg and workspace. */
+ * are valid after tnb_tracknet_forward (z, scale ...) / tnb_tracknet_backward (dz, din) of the same cfg and workspace.
+ * Pure host arithmetic: with workspace = NULL the "pointers" are the tensors' byte offsets inside a workspace. */
 int tnb_tracknet_debug_layer(const tnb_tracknet_cfg_t* cfg, void* workspace, int layer, void** out_ptr8, int* out_dim5);
 
 /* ---- measurement support (bench.py roofline leg) -------------------------------------------- */

@@ -124,6 +124,8 @@ class ScalarReader:
         _lib.require_cuda(t)
         if t.numel() != 1:
             raise RuntimeError(f"ScalarReader.read expects a one-element tensor, got shape {tuple(t.shape)}")
+        if self.pending:
+            raise RuntimeError("ScalarReader.read() while the previous value has not been taken (one host slot: call value())")
         src = t.detach().reshape(1).float()
         self.ready.record(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
