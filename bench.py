@@ -16,7 +16,8 @@ Printed JSON (one line, rank 0):
                every step (ScalarReader: a side-stream copy that does not drain the compute stream);
   roofline     the tcgen05 conv kernel's algorithmic TFLOP/s from per-launch CUDA events (the same steps repeated once
                more right after the timed region, which itself runs as CUDA-graph replays) against the measured dense
-               bf16 peak; `traffic` from the committed ncu pass, refused (null) when the kernel sources changed since;
+               bf16 peak; `traffic` and `ncu` (tensor-pipe-active % per kernel, time-weighted over the step: the second half of
+               BASELINE.json's metric) from the committed ncu pass, refused (null) when the kernel sources changed since;
   train_step   the secondary region of SURVEY.md 8(d): zero_grad + mixup + forward + loss + .item() + backward + FusedAdam
                (reference train.py:85-96), with the Adam / mixup kernels' own HBM fractions;
   torch_cuda_baseline  the reference architecture on stock torch-CUDA on the same box right after (the >= 6x target's
@@ -115,6 +116,33 @@ def committed_traffic(precision):
     conv = [v for k, v in km.items() if k.startswith("conv3x3")]
     traffic = sum(v["dram_bytes_per_launch"] * v["launches"] for v in conv) / sum(v["launches"] for v in conv)
     return traffic, f"{path} (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per conv launch; HEAD {meta.get('head')})"
+
+
+def committed_ncu_summary(precision):
+    """What the same committed ncu pass says besides the traffic (None when it is stale): tensor-pipe-active % of the
+    conv (forward + dgrad) and wgrad kernels, time-weighted over the step's launches, and the DRAM GB/s of the
+    BatchNorm-backward kernels - the `conv tensor-pipe %` half of BASELINE.json's metric. ncu numbers (serialised,
+    cold-cache replays), not taken in this run: they describe the kernels, the timed region describes the step."""
+    traffic, _ = committed_traffic(precision)
+    if traffic is None:
+        return None
+    cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("kernel_metrics_r") and f.endswith(".json"))
+    km = json.load(open(os.path.join(ROOT, "profiles", cands[-1])))
+    km.pop("_meta", None)
+
+    def weighted(prefix):
+        sel = [v for k, v in km.items() if k.startswith(prefix)]
+        ms = sum(v["ms"] for v in sel)
+        return sum(v["tensor_pipe_pct"] * v["ms"] for v in sel) / ms if ms > 0 else None
+
+    bn = [v for k, v in km.items() if k.startswith("bn_bwd")]
+    bn_bytes = sum(v["dram_bytes_per_launch"] * v["launches"] for v in bn)
+    bn_ms = sum(v["ms"] for v in bn)
+    return {"source": os.path.join("profiles", cands[-1]),
+            "conv_fwd_dgrad_tensor_pipe_active_pct": weighted("conv3x3"),
+            "wgrad_tensor_pipe_active_pct": weighted("wgrad3x3"),
+            "by_kernel_tensor_pipe_active_pct": {k: v["tensor_pipe_pct"] for k, v in km.items() if v["tensor_pipe_pct"] > 0},
+            "bn_bwd_dram_gbs": bn_bytes / bn_ms / 1e6 if bn_ms > 0 else None}
 
 
 class ClockSampler:
@@ -449,7 +477,8 @@ def main():
                 "frac_executed": achieved * terms / peaks["tflops"],
                 "timing": f"CUDA event pair around every conv launch, {prof_steps} steps run right after the timed region "
                           "(the timed region itself replays CUDA graphs)",
-                "whole_step_frac": (84.78e9 * value / world) / (peaks["tflops"] * 1e12)}
+                "whole_step_frac": (84.78e9 * value / world) / (peaks["tflops"] * 1e12),
+                "ncu": committed_ncu_summary(args.precision)}
 
     cfg = _lib.TrackNetCfg(n=BATCH, h=H, w=W, in_dim=IN_DIM, out_dim=OUT_DIM, training=1, fwd_terms=fwd_terms,
                            bwd_terms=bwd_terms, variant=args.variant, bn_eps=1e-5, bn_momentum=0.1)
