@@ -90,7 +90,11 @@ typedef struct {
   int n, h, w;     /* batch, height, width (h, w multiples of 8 like the reference, model.py:59-69) */
   int in_dim;      /* TrackNet(in_dim, out_dim), reference model.py:45 */
   int out_dim;
-  int training;    /* 1: BatchNorm uses batch statistics and updates running stats (model.train()) */
+  int training;    /* 1: BatchNorm uses batch statistics and updates running stats (model.train()), the state of a backward
+                      pass is kept in the workspace; 0: running statistics, nothing kept (model.eval() under no_grad);
+                      2: running statistics AND the backward state (model.eval() with gradients enabled - autograd through
+                      frozen BatchNorm layers, which the reference's modules allow, model.py:4-16): tnb_tracknet_backward
+                      then returns dz = gamma / sqrt(running_var + eps) * g without the batch-statistics terms */
   int fwd_terms;   /* 3 = fp16 hi/lo split, fp32-faithful (default); 1 = single fp16 pass (TF32-class) */
   int bwd_terms;   /* 3 = bf16 hi/lo split (default; gradients need fp32's exponent range); 1 = single bf16 pass */
   int variant;     /* bring-up probe bits; 0 in production */

@@ -56,6 +56,13 @@ def test_workspace_and_plan_queries():
     # input is pre-split by the forward's pack launch, every other wgrad operand comes out of a BatchNorm-backward apply
     # pass), dgrad 16, ordered split-K sums 17
     assert lib.tnb_tracknet_num_launches(C.byref(cfg), 1) == 104
+    cfg.training = 2                                                   # eval() with gradients enabled: running statistics,
+    assert lib.tnb_tracknet_workspace_bytes(C.byref(cfg)) == train_bytes   # the backward state of a training forward,
+    assert lib.tnb_tracknet_num_launches(C.byref(cfg), 0) == 37        # no counter launch,
+    assert lib.tnb_tracknet_num_launches(C.byref(cfg), 1) == 104       # the same backward launches
+    cfg.training = 3
+    assert lib.tnb_tracknet_workspace_bytes(C.byref(cfg)) == 0 and b"training must be" in lib.tnb_last_error()
+    cfg.training = 1
     cfg.variant = 16384                                                # skip halves of the 3 decoder concats by view passes
     assert lib.tnb_tracknet_num_launches(C.byref(cfg), 1) == 107
     cfg.variant = 0

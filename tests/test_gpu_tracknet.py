@@ -491,3 +491,75 @@ def test_twenty_adam_steps_track_the_oracle():
         print(f"adam seeds ({init_seed}, {data_seed}): ours / fp64 - 1 over steps 10-19: {late[-1]:+.4f}, at step 19 {ours[-1] / ref64[-1] - 1:+.4f}")
         assert abs(late[-1]) < 0.12, ("adam", init_seed, late[-1])
     assert abs(sum(late) / len(late)) < 0.04, late
+
+
+def test_eval_mode_backward_frozen_batchnorm_vs_oracle():
+    """A model in eval() called with gradients enabled (fine-tuning with frozen BatchNorm layers - the reference's modules
+    are plain autograd, model.py:4-16): tnb_tracknet_cfg_t.training = 2. The forward uses the running statistics and
+    leaves them and the counters untouched; the backward drops the batch-statistics terms of the BatchNorm gradient.
+    Heatmaps bit-identical to the no_grad eval forward; loss and all 53 gradients against the oracle's eval-mode step
+    (yardstick as in smoke(): the oracle's own sensitivity to a 2e-5 relative weight perturbation); and, independent of
+    any reference, <grad, d> against central finite differences of our own eval-mode loss."""
+    sd = O.init_tracknet_state(31, 12, 4)
+    gen = torch.Generator().manual_seed(32)
+    x = torch.rand(2, 12, 64, 96, generator=gen)
+    y = (torch.rand(2, 4, 64, 96, generator=gen) > 0.98).float()
+    with torch.no_grad():
+        for _ in range(40):                      # running statistics of a "trained" model: close to this data's
+            O.tracknet_forward(sd, x, True)
+    m = T.TrackNet(12, 4).to(G.DEV)
+    m.load_state_dict(sd)
+    m.eval()
+    xd, yd = x.to(G.DEV), y.to(G.DEV)
+    with torch.no_grad():
+        y_ng = m(xd).clone()
+    before = {k: v.clone() for k, v in m.state_dict().items() if "running" in k or "tracked" in k}
+    y_pred = m(xd)
+    assert y_pred.requires_grad and torch.equal(y_pred.detach(), y_ng)
+    loss = T.WBCELoss(y_pred, yd)
+    loss.backward()
+    for k, v in m.state_dict().items():
+        if k in before:
+            assert torch.equal(v, before[k]), k
+    r_pred, r_loss, r_grads = O.tracknet_loss_and_grads(dict(sd), x, y, False)
+    assert G.max_abs(y_pred, r_pred) < HEAT_TOL
+    assert abs(loss.item() - r_loss.item()) < 1e-4 * abs(r_loss.item())
+    g = torch.Generator().manual_seed(3)
+    sd_p = {k: (v * (1 + 2e-5 * torch.randn(v.shape, generator=g)) if k.endswith("conv.weight") else v.clone())
+            for k, v in sd.items()}
+    _, _, p_grads = O.tracknet_loss_and_grads(sd_p, x, y, False)
+    for k, p in m.named_parameters():
+        tol = 2e-2 if k.startswith(("predictor", "up_block_3.conv_2")) else 3 * G.rel_err(p_grads[k], r_grads[k]) + 2e-2
+        assert G.rel_err(p.grad, r_grads[k]) < tol, (k, G.rel_err(p.grad, r_grads[k]), tol)
+
+    def loss_at():
+        with torch.no_grad():
+            return T.WBCELoss(m(xd), yd).double().item()
+
+    params = list(m.parameters())
+    grads = [p.grad.detach().clone().double() for p in params]
+    errs = []
+    for trial in range(3):
+        dirs = [torch.randn(p.shape, generator=torch.Generator().manual_seed(300 + trial * 64 + i)).to(G.DEV)
+                * p.detach().abs().mean().clamp_min(1e-3) for i, p in enumerate(params)]
+        analytic = sum((gr * d.double()).sum().item() for gr, d in zip(grads, dirs))
+        eps = 2e-3
+        with torch.no_grad():
+            for p, d in zip(params, dirs):
+                p.add_(eps * d)
+            lp = loss_at()
+            for p, d in zip(params, dirs):
+                p.sub_(2 * eps * d)
+            lm = loss_at()
+            for p, d in zip(params, dirs):
+                p.add_(eps * d)
+        fd = (lp - lm) / (2 * eps)
+        print(f"eval-mode gradcheck trial {trial}: analytic {analytic:.6e} finite-difference {fd:.6e}")
+        errs.append((analytic - fd, abs(fd)))
+    scale = sum(f for _, f in errs) / len(errs)
+    assert max(abs(e) for e, _ in errs) < 0.08 * scale, errs
+    # a training-mode forward afterwards is the batch-statistics path again
+    m.train()
+    with torch.no_grad():
+        m(xd)
+    assert int(m.state_dict()["bottleneck.conv_1.bn.num_batches_tracked"]) == 41

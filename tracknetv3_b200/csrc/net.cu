@@ -99,6 +99,12 @@ struct Bump {
 // through (h/2, w/2) addressing - or max-pooled, act_pool), instead of a separate view pass over z; the wgrad of layer l
 // is launched right after that pass. The skip half of a concat still comes from a view pass: its producer's apply pass
 // runs many layers later.
+// tnb_tracknet_cfg_t.training: 0 = running statistics, nothing kept (inference); 1 = batch statistics, running statistics
+// and counters advanced, everything a backward pass needs kept (model.train()); 2 = running statistics like 0 AND the
+// backward state of 1 (a model in eval() called with gradients enabled: fine-tuning with frozen BatchNorm layers, which
+// the reference's autograd path allows, model.py:4-16). `c.training != 0` sizes and fills the backward state.
+bool batch_stats(const tnb_tracknet_cfg_t& c) { return c.training == 1; }
+
 bool wgrad_operand_from_bn_bwd(const tnb_tracknet_cfg_t& c, int l) {
   if (c.variant & 128) return false;  // variant bit 128: always materialise with tnb_view_presplit (ablation)
   if (l <= 0 || kDefs[l].src0 != l - 1) return false;
@@ -163,6 +169,7 @@ int build_plan(const tnb_tracknet_cfg_t& c, void* ws, Plan* P) {
               "tracknet: input %dx%d must be divisible by 8 (reference model.py:59-69 pools 3x then concatenates)",
               c.h, c.w);
   TNB_REQUIRE(c.in_dim > 0 && c.out_dim > 0, "tracknet: bad in_dim/out_dim %d/%d", c.in_dim, c.out_dim);
+  TNB_REQUIRE(c.training >= 0 && c.training <= 2, "tracknet: training must be 0, 1 or 2 (got %d)", c.training);
   TNB_REQUIRE((c.fwd_terms == 1 || c.fwd_terms == 3) && (c.bwd_terms == 1 || c.bwd_terms == 3),
               "tracknet: terms must be 1 or 3");
   Bump b{reinterpret_cast<uint8_t*>(ws), 0};
@@ -311,15 +318,15 @@ static int forward_enqueue(const tnb_tracknet_cfg_t& c, const float* x, void* co
     LayerBuf& B = P.L[l];
     ViewDesc v = make_view(P, c, l);
     if (l == 0 && P.xin16 != nullptr) { v.s[0] = make_src(P, c, -1, SRC_PLANAR16); v.s[1] = v.s[0]; }
-    if (int rc = launch_conv3x3(v, B.wf, B.z, c.training ? B.stat_part : nullptr, B.cout, c.fwd_terms, 0, c.variant & 3, st))
+    if (int rc = launch_conv3x3(v, B.wf, B.z, batch_stats(c) ? B.stat_part : nullptr, B.cout, c.fwd_terms, 0, c.variant & 3, st))
       return rc;
     if (int rc = launch_bn_finalize(B.stat_part, B.stat_rows, (double)c.n * B.H * B.W, (const float*)params[l * 6 + 1],
                                     (const float*)params[l * 6 + 2], (float*)params[l * 6 + 3],
-                                    (float*)params[l * 6 + 4], c.bn_momentum, c.bn_eps, c.training, B.scale, B.shift,
+                                    (float*)params[l * 6 + 4], c.bn_momentum, c.bn_eps, batch_stats(c) ? 1 : 0, B.scale, B.shift,
                                     B.mean, B.invstd, B.cout, st))
       return rc;
   }
-  if (c.training) {
+  if (batch_stats(c)) {
     CounterTable t;
     for (int l = 0; l < kLayers; ++l) t.p[l] = (long long*)params[l * 6 + 5];
     if (int rc = launch_pdl(inc_counters_kernel2, dim3(1), dim3(32), 0, st, t)) return rc;
@@ -335,7 +342,8 @@ static int forward_enqueue(const tnb_tracknet_cfg_t& c, const float* x, void* co
 static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const float* y, void* const* params,
                             void* const* grads, void* ws, size_t ws_bytes, cudaStream_t st, int hi = kLayers - 1,
                             int lo = 0) {
-  TNB_REQUIRE(c.training, "tracknet_backward: only the training-mode (batch-statistics) backward is implemented");
+  TNB_REQUIRE(c.training != 0, "tracknet_backward: the forward call ran with training = 0 and kept no state for a backward pass "
+                               "(training = 2 is the running-statistics forward that does)");
   TNB_REQUIRE(0 <= lo && lo <= hi && hi < kLayers, "tracknet_backward: layer range %d..%d", hi, lo);
   Plan P;
   if (int rc = build_plan(c, ws, &P)) return rc;
@@ -398,7 +406,9 @@ static int backward_enqueue(const tnb_tracknet_cfg_t& c, const float* dy, const 
     a.part = B.bwd_part; a.sums = B.bwd_sums; a.dz = B.dz; a.amax = nullptr;
     a.dz_format = bf == 0 ? 2 : 1;  // dz -> pre-split fp16 (scaled) / bf16
     a.gmax = bf == 0 ? gmax_all + l : nullptr; a.dz_mul = bf == 0 ? mul_all + l : nullptr;
-    a.inv_count = (float)(1.0 / ((double)c.n * B.H * B.W));
+    // running statistics (training == 2): mean and variance are constants of the layer, so the two batch-statistics terms
+    // of dz = scale * (g - mean(g) - xhat * mean(g * xhat)) vanish - the apply pass multiplies both sums by inv_count
+    a.inv_count = batch_stats(c) ? (float)(1.0 / ((double)c.n * B.H * B.W)) : 0.f;
     if (B.fused_rows == 0)
       if (int rc = launch_bn_bwd_reduce(a, st)) return rc;
     if (int rc = launch_bn_bwd_finalize(B.bwd_part, B.fused_rows > 0 ? B.fused_rows : B.bwd_rows, B.cout, B.bwd_sums,
@@ -627,7 +637,7 @@ int tracknet_debug_layer(const tnb_tracknet_cfg_t& c, void* ws, int layer, void*
 int tracknet_num_launches(const tnb_tracknet_cfg_t& c, int backward) {
   const int pred_groups = (c.out_dim + 15) / 16;  // the predictor kernels take 16 output channels per launch
   // pack_input, pack_weights (all tensors), (conv, bn_finalize) x17, counters, predictor
-  if (!backward) return 1 + 1 + kLayers * 2 + (c.training ? 1 : 0) + pred_groups;
+  if (!backward) return 1 + 1 + kLayers * 2 + (batch_stats(c) ? 1 : 0) + pred_groups;
   int fused = 0;
   for (int l = 0; l < kLayers; ++l) fused += ((c.variant & 64) && bn_reduce_fusable(l)) ? 1 : 0;
   int emitted = 0;  // wgrad operands written by the BatchNorm-backward apply pass: no view_presplit launch

@@ -61,7 +61,9 @@ class _TrackNetFunction(torch.autograd.Function):
     def forward(ctx, x, module, saves_state, *params):
         lib = _lib.load()
         n, _, h, w = x.shape
-        cfg = _cfg(n, h, w, module.in_dim, module.out_dim, module.training, module.precision, module._variant)
+        # training: 1 = batch statistics; 2 = eval() with a backward to follow (running statistics, backward state kept)
+        mode = 1 if module.training else (2 if saves_state else 0)
+        cfg = _cfg(n, h, w, module.in_dim, module.out_dim, mode, module.precision, module._variant)
         nbytes = lib.tnb_tracknet_workspace_bytes(C.byref(cfg))
         if nbytes == 0:
             # mirror the reference's failure for sizes its pooling / concat cannot handle (model.py:59-69)
@@ -81,8 +83,6 @@ class _TrackNetFunction(torch.autograd.Function):
         lib = _lib.load()
         (y,) = ctx.saved_tensors
         module = ctx.module
-        if not ctx.cfg.training:
-            raise RuntimeError("tracknet_b200: backward through an eval()-mode TrackNet is not implemented")
         if ctx.needs_input_grad[0]:
             raise RuntimeError("tracknet_b200: the gradient w.r.t. the input frames is not computed (the reference's "
                                "train step never asks for it, train.py:86-95); pass x without requires_grad")
@@ -136,6 +136,10 @@ class TrackNet(nn.Module):
     "fp32x3_bwd1" keeps the fp32-faithful forward (the heatmap bound) and runs dgrad / wgrad as a single fp16 pass
     (11-bit operands, gradients stored multiplied by a per-layer power of two; TF32, what the reference's own GPU
     backward runs in, has 10) - measured next to the default by ``bench.py --precision fp32x3_bwd1``, never the headline.
+
+    ``train()``: batch statistics, running statistics and counters advanced. ``eval()``: running statistics; under
+    ``torch.no_grad()`` nothing is kept, with gradients enabled the forward keeps what ``backward()`` needs and the
+    BatchNorm layers act as frozen affine maps in it (``tnb_tracknet_cfg_t.training`` = 1 / 0 / 2).
     """
 
     def __init__(self, in_dim, out_dim, precision="fp32x3"):
@@ -208,7 +212,7 @@ class TrackNet(nn.Module):
                                    "are not supported")
         x = x.contiguous().float()
         # decided HERE: inside autograd.Function.forward grad mode is always off
-        saves_state = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        saves_state = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         return _TrackNetFunction.apply(x, self, saves_state, *self.parameters())
 
 
@@ -292,6 +296,9 @@ class InpaintNet(nn.Module):
         tensors = self._param_tensors()
         for t in tensors:
             _lib.require_cuda(t)
+            if t.device != x.device or t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("tracknet_b200: InpaintNet parameters must be contiguous fp32 tensors on the input's "
+                                   f"device (found {t.dtype} on {t.device}, input on {x.device})")
         return x.contiguous().float(), m.contiguous().float(), tensors
 
     def forward(self, x, m):
