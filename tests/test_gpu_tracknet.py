@@ -532,32 +532,43 @@ def test_eval_mode_backward_frozen_batchnorm_vs_oracle():
         tol = 2e-2 if k.startswith(("predictor", "up_block_3.conv_2")) else 3 * G.rel_err(p_grads[k], r_grads[k]) + 2e-2
         assert G.rel_err(p.grad, r_grads[k]) < tol, (k, G.rel_err(p.grad, r_grads[k]), tol)
 
+    # directional derivatives <grad, d> along random parameter directions: against the exact ones (the oracle's eval-mode
+    # step in fp64) and against central finite differences of OUR eval-mode loss. Without batch renormalisation the loss
+    # is strongly curved along such directions (on the fp64 oracle itself the secant is 9 % off the tangent at eps 2e-3,
+    # 1.3 % at 1e-4), hence the small step.
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    _, _, e_grads = O.tracknet_loss_and_grads(sd64, x.double(), y.double(), False)
+
     def loss_at():
         with torch.no_grad():
             return T.WBCELoss(m(xd), yd).double().item()
 
-    params = list(m.parameters())
-    grads = [p.grad.detach().clone().double() for p in params]
-    errs = []
+    named = list(m.named_parameters())
+    grads = [p.grad.detach().clone().double() for _, p in named]
+    rows = []
     for trial in range(3):
-        dirs = [torch.randn(p.shape, generator=torch.Generator().manual_seed(300 + trial * 64 + i)).to(G.DEV)
-                * p.detach().abs().mean().clamp_min(1e-3) for i, p in enumerate(params)]
+        dirs = [torch.randn(p.shape, generator=torch.Generator().manual_seed(300 + trial * 64 + i))
+                * p.detach().abs().mean().clamp_min(1e-3).cpu() for i, (_, p) in enumerate(named)]
+        exact = sum((e_grads[k] * d.double()).sum().item() for (k, _), d in zip(named, dirs))
+        dirs = [d.to(G.DEV) for d in dirs]
         analytic = sum((gr * d.double()).sum().item() for gr, d in zip(grads, dirs))
-        eps = 2e-3
+        eps = 1e-4
         with torch.no_grad():
-            for p, d in zip(params, dirs):
+            for (_, p), d in zip(named, dirs):
                 p.add_(eps * d)
             lp = loss_at()
-            for p, d in zip(params, dirs):
+            for (_, p), d in zip(named, dirs):
                 p.sub_(2 * eps * d)
             lm = loss_at()
-            for p, d in zip(params, dirs):
+            for (_, p), d in zip(named, dirs):
                 p.add_(eps * d)
         fd = (lp - lm) / (2 * eps)
-        print(f"eval-mode gradcheck trial {trial}: analytic {analytic:.6e} finite-difference {fd:.6e}")
-        errs.append((analytic - fd, abs(fd)))
-    scale = sum(f for _, f in errs) / len(errs)
-    assert max(abs(e) for e, _ in errs) < 0.08 * scale, errs
+        print(f"eval-mode gradcheck trial {trial}: analytic {analytic:.6e} exact (fp64 oracle) {exact:.6e} "
+              f"finite-difference {fd:.6e}")
+        rows.append((analytic, exact, fd))
+    scale = max(abs(e) for _, e, _ in rows)
+    assert max(abs(a - e) for a, e, _ in rows) < 2e-2 * scale, rows
+    assert max(abs(a - f) for a, _, f in rows) < 5e-2 * scale, rows
     # a training-mode forward afterwards is the batch-statistics path again
     m.train()
     with torch.no_grad():
