@@ -152,6 +152,11 @@ def test_inpaintnet_vs_reference_fixture_and_oracle(golden_dir):
     with torch.no_grad():
         out = net((x * (1 - m)).to(G.DEV), m.to(G.DEV))
     assert G.max_abs(out, O.inpaintnet_forward(sd, x * (1 - m), m)) < 1e-5
+    # the kernels read raw fp32 pointers: a converted model must be refused, not misread
+    with pytest.raises(RuntimeError, match="contiguous fp32"):
+        net.half()(x.to(G.DEV), m.to(G.DEV))
+    with pytest.raises(RuntimeError, match=r"\(N, L, 2\)"):
+        net.float()(x[:, :, :1].to(G.DEV), m.to(G.DEV))
 
 
 def test_inpaintnet_train_step_vs_reference_fixture(golden_dir):
