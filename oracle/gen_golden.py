@@ -78,6 +78,39 @@ def gen_inpaint_train(refmodel):
     np.savez_compressed(f"{OUT}/inpaintnet_train.npz", **out)
 
 
+def gen_tracknet_eval_step(refmodel, refmetric):
+    """fwd + WBCE + backward through the REAL reference TrackNet in eval() mode (BatchNorm layers frozen at their running
+    statistics; plain autograd, reference model.py:4-16), after five train-mode forwards have moved those statistics off
+    their initial (0, 1): pins the oracle's eval-mode step, which in turn pins tnb_tracknet_cfg_t.training = 2."""
+    torch.manual_seed(23)
+    m = refmodel.TrackNet(27, 8)
+    x = torch.rand(2, 27, 32, 64)
+    y = (torch.rand(2, 8, 32, 64) > 0.97).float()
+    m.train()
+    with torch.no_grad():
+        for _ in range(5):
+            m(x)
+    m.eval()
+    before = {k: v.clone() for k, v in m.state_dict().items() if "running" in k or "tracked" in k}
+    y_pred = m(x)
+    loss = refmetric.WBCELoss(y_pred, y)
+    loss.backward()
+    assert all(torch.equal(v, before[k]) for k, v in m.state_dict().items() if k in before)
+    names = [n for n, _ in m.named_parameters()]
+    sd = m.state_dict()
+    np.savez_compressed(f"{OUT}/tracknet_eval_step.npz", seed=23, x=x.numpy(), y=y.numpy(), y_pred=y_pred.detach().numpy(),
+                        loss=loss.item(), grad_stats=np.stack([grad_stats(p.grad) for _, p in m.named_parameters()]),
+                        grad_names=np.array(names),
+                        grad_first=m.down_block_1.conv_1.conv.weight.grad.numpy(),
+                        grad_last=m.up_block_3.conv_2.conv.weight.grad.numpy(),
+                        grad_bn_w=m.bottleneck.conv_2.bn.weight.grad.numpy(),
+                        grad_bn_b=m.down_block_2.conv_1.bn.bias.grad.numpy(),
+                        grad_pred_w=m.predictor.weight.grad.numpy(),
+                        running_mean_mid=sd["bottleneck.conv_1.bn.running_mean"].numpy(),
+                        running_var_last=sd["up_block_3.conv_2.bn.running_var"].numpy(),
+                        nbt=int(sd["bottleneck.conv_2.bn.num_batches_tracked"]))
+
+
 def _find_stream_loop(tree, names):
     """The `for step, (<names>) in enumerate(tqdm(data_loader))` loop of predict.py's __main__ whose body holds the
     per-sample `for b in range(b_size)` ensemble loop."""
@@ -306,6 +339,10 @@ def main():
         print("temporal_ensemble.npz written")
         return
     refmetric = load_module("ref_metric", f"{REF}/utils/metric.py")
+    if len(sys.argv) > 1 and sys.argv[1] == "eval_step":
+        gen_tracknet_eval_step(refmodel, refmetric)
+        print("tracknet_eval_step.npz written")
+        return
     import cv2
     env = {"np": np, "cv2": cv2, "torch": torch, "math": math}
     extract_functions(f"{REF}/test.py", {"predict_location", "get_ensemble_weight"}, env)
@@ -402,6 +439,7 @@ def main():
         out = net(coor, mask)
     np.savez_compressed(f"{OUT}/inpaintnet.npz", seed=7, coor=coor.numpy(), mask=mask.numpy(), out=out.numpy())
 
+    gen_tracknet_eval_step(refmodel, refmetric)
     gen_inpaint_train(refmodel)
     gen_temporal_ensemble()
     gen_evaluate()

@@ -37,6 +37,36 @@ def test_tracknet_train_step_matches_reference(golden_dir):
     assert int(sd["bottleneck.conv_2.bn.num_batches_tracked"]) == int(g["nbt"]) == 1
 
 
+def test_tracknet_eval_mode_step_matches_reference(golden_dir):
+    """The oracle's eval-mode step (BatchNorm frozen at its running statistics) against the REAL reference module run the
+    same way (oracle/gen_golden.py eval_step): what tests/test_gpu_tracknet.py checks training = 2 against."""
+    g = _load(golden_dir, "tracknet_eval_step.npz")
+    sd = O.init_tracknet_state(int(g["seed"]), 27, 8)
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    with torch.no_grad():
+        for _ in range(5):
+            O.tracknet_forward(sd, x, True)
+    assert np.abs(sd["bottleneck.conv_1.bn.running_mean"].numpy() - g["running_mean_mid"]).max() < 1e-6
+    assert np.abs(sd["up_block_3.conv_2.bn.running_var"].numpy() - g["running_var_last"]).max() < 1e-5
+    frozen = {k: v.clone() for k, v in sd.items() if "running" in k or "tracked" in k}
+    y_pred, loss, grads = O.tracknet_loss_and_grads(sd, x, y, training=False)
+    assert all(torch.equal(sd[k], v) for k, v in frozen.items())       # an eval-mode step advances nothing
+    assert int(sd["bottleneck.conv_2.bn.num_batches_tracked"]) == int(g["nbt"]) == 5
+    assert np.abs(y_pred.numpy() - g["y_pred"]).max() < 2e-5
+    assert abs(loss.item() - float(g["loss"])) < 1e-6 * max(1, abs(float(g["loss"])))
+    names = [str(n) for n in g["grad_names"]]
+    assert names == list(grads.keys())
+    for k, ref in (("down_block_1.conv_1.conv.weight", "grad_first"), ("up_block_3.conv_2.conv.weight", "grad_last"),
+                   ("bottleneck.conv_2.bn.weight", "grad_bn_w"), ("down_block_2.conv_1.bn.bias", "grad_bn_b"),
+                   ("predictor.weight", "grad_pred_w")):
+        scale = np.abs(g[ref]).max()
+        assert np.abs(grads[k].numpy() - g[ref]).max() <= 2e-4 * scale + 1e-10, k
+    for i, k in enumerate(names):
+        gs = g["grad_stats"][i]
+        mine = grads[k].double().flatten()
+        assert abs(mine.abs().sum().item() - gs[1]) <= 2e-3 * gs[1] + 1e-12, k
+
+
 @pytest.mark.parametrize("h,w", [(32, 48)])
 def test_tracknet_small_forward_is_deterministic(h, w):
     sd = O.init_tracknet_state(1, 12, 4)
