@@ -114,6 +114,26 @@ def test_no_oracle_or_torch_fallback_in_product():
         T.WBCELoss(torch.rand(1, 1, 4, 4), torch.rand(1, 1, 4, 4))
 
 
+def test_missing_library_fails_loudly():
+    """Without the built extension every op refuses to run (no eager / CPU substitute): the loader raises with the build
+    instruction. Checked in a fresh interpreter whose TNB_LIBRARY points at a file that does not exist."""
+    import subprocess
+    import sys
+    code = ("import torch, tracknetv3_b200 as T\n"
+            "for call in (lambda: T._lib.load(), lambda: T.decode_heatmaps(torch.zeros(1, 4, 4)),\n"
+            "             lambda: T.FusedAdam([torch.nn.Parameter(torch.zeros(2))]).step()):\n"
+            "    try:\n"
+            "        call()\n"
+            "    except RuntimeError as e:\n"
+            "        assert 'not built' in str(e) and 'no CPU / PyTorch fallback' in str(e), e\n"
+            "    else:\n"
+            "        raise SystemExit('an op ran without the library')\n"
+            "print('refused')\n")
+    env = dict(os.environ, TNB_LIBRARY=os.path.join(ROOT, "tracknetv3_b200", "no_such_library.so"))
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("refused"), r.stdout + r.stderr
+
+
 _LAYER_SHAPES = [(27, 64, 0), (64, 64, 0), (64, 128, 1), (128, 128, 1), (128, 256, 2), (256, 256, 2), (256, 512, 3),
                  (512, 512, 3), (768, 256, 2), (384, 128, 1), (192, 64, 0)]  # (cin, cout, level) of TrackNet's 3x3 layers
 
